@@ -1,0 +1,262 @@
+/*
+ * rloa_b200.h — C ABI of librloa_b200.so, the B200 (sm_100a) native library behind the
+ * robotic_manipulator_rloa hot path.
+ *
+ * The reference (JavierMtz5/robotic_manipulator_rloa) is pure Python and has no FFI of its own: the
+ * native work on its hot path is done by two third-party wheels, PyBullet and PyTorch.  Every entry
+ * point below therefore cites the reference call site whose native work it replaces
+ * (paths relative to /root/reference/robotic_manipulator_rloa/).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++ or torch types;
+ *   - every function returns 0 on success, a negative rloa_status on failure, and leaves a
+ *     thread-local message readable through rloa_last_error();
+ *   - all `const float*` / `float*` data arguments are DEVICE pointers unless the name ends in
+ *     `_host`; buffers are caller-owned, row-major contiguous, fp32 unless stated;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are
+ *     asynchronous on that stream, contain no hidden synchronisation and can be captured into a
+ *     CUDA graph (exceptions: *_create / *_destroy / *_host getters, which synchronise);
+ *   - a handle is bound to the CUDA device that was current when it was created and is not
+ *     thread-safe: one host thread (one rank) per GPU drives it.
+ */
+#ifndef RLOA_B200_H
+#define RLOA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLOA_MAX_LINKS 32      /* links == PyBullet getNumJoints(); one warp lane per link */
+#define RLOA_MAX_SHAPES 32     /* collision primitives; one warp lane per primitive */
+#define RLOA_MAX_DOF 16        /* movable joints (PGS rows = dof + active limit rows <= 32) */
+
+typedef enum {
+    RLOA_OK = 0,
+    RLOA_ERR_INVALID = -1,     /* bad argument / unsupported model */
+    RLOA_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+    RLOA_ERR_NO_DEVICE = -3    /* no sm_100 device visible */
+} rloa_status;
+
+enum { RLOA_JOINT_FIXED = 0, RLOA_JOINT_REVOLUTE = 1, RLOA_JOINT_PRISMATIC = 2 };
+enum { RLOA_SHAPE_SPHERE = 1, RLOA_SHAPE_CAPSULE = 2, RLOA_SHAPE_BOX = 3 };
+
+const char* rloa_last_error(void);
+int rloa_version(void);
+/* number of kernels this library has launched in the calling process (bench.py gpu_launches) */
+uint64_t rloa_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Robot model.  Replaces p.loadURDF / p.loadSDF / p.getNumJoints (environment/environment.py:224-238)
+ * and the obstacle / target bodies (environment.py:252-255).  All arrays are HOST pointers, double
+ * precision, link frames at the centre of mass with principal axes (Bullet's btMultiBody layout).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t nl;                 /* links / joints */
+    const int32_t* parent;      /* [nl] -1 = fixed base; links numbered depth first (parent < child) */
+    const int32_t* jtype;       /* [nl] RLOA_JOINT_* */
+    const double* E0;           /* [nl][9] child COM frame <- parent COM frame at q = 0 */
+    const double* e;            /* [nl][3] parent COM -> joint pivot, parent COM frame */
+    const double* d;            /* [nl][3] joint pivot -> child COM, child COM frame */
+    const double* axis;         /* [nl][3] unit joint axis, child COM frame */
+    const double* mass;         /* [nl] */
+    const double* inertia;      /* [nl][3] principal moments */
+    const double* damping;      /* [nl] joint damping */
+    const double* lower;        /* [nl] */
+    const double* upper;        /* [nl] */
+    const int32_t* has_limit;   /* [nl] */
+    double base_R[9];           /* world <- base COM frame */
+    double base_p[3];
+    double lin_damp, ang_damp;  /* Bullet per-link velocity drag (0.04) */
+    double gravity[3];
+    double dt;                  /* 1/240 */
+    int32_t iters;              /* PGS iterations (50) */
+    double resid_thresh;        /* 1e-7, on the squared row velocity change */
+    double erp;                 /* 0.2 */
+    double max_vel;             /* 100 */
+    double limit_max_impulse;   /* 100 */
+    int32_t ns;                 /* collision primitives */
+    const int32_t* s_link;      /* [ns] owning link */
+    const int32_t* s_type;      /* [ns] RLOA_SHAPE_* */
+    const double* s_R;          /* [ns][9] link COM frame <- shape frame */
+    const double* s_p;          /* [ns][3] */
+    const double* s_dim;        /* [ns][3] sphere r,-,- | capsule r,half_len,- (local z) | box half extents */
+    double obstacle_radius;     /* sphere_small.urdf x 2.5 -> 0.075 */
+    double target_half[3];      /* cube_small.urdf -> 0.025 each */
+    int32_t ee_link;            /* endeffector_index */
+    int32_t n_obs_joints;       /* len(involved_joints); get_state reads joints 0..n-1 (environment.py:442-444) */
+} rloa_model_desc;
+
+typedef struct rloa_model rloa_model;
+int rloa_model_create(const rloa_model_desc* desc, rloa_model** out);
+void rloa_model_destroy(rloa_model* m);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched simulator: n_envs independent arms, one warp per arm.
+ * Replaces the PyBullet world owned by Environment (environment.py:207-210) and
+ * p.setJointMotorControl2 / p.stepSimulation / p.getJointState / p.getLinkState /
+ * p.getClosestPoints on Environment.step / reset / get_state / get_reward / is_terminal_state
+ * (environment.py:264-309, 311-371, 431-485; utils/collision_detector.py:33-61).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rloa_sim rloa_sim;
+int rloa_sim_create(const rloa_model* m, int32_t n_envs, rloa_sim** out);
+void rloa_sim_destroy(rloa_sim* s);
+int rloa_sim_num_envs(const rloa_sim* s);
+int rloa_sim_obs_size(const rloa_sim* s);      /* 9 + 2 * n_obs_joints */
+
+/* per-env target / obstacle positions, [n_envs][3] (environment.py:212-213 broadcast per env) */
+int rloa_sim_set_task(rloa_sim* s, const float* target, const float* obstacle, void* stream);
+
+/* joint coordinates, [n_envs][nl] (fixed joints carry 0); for parity tests and checkpoints */
+int rloa_sim_set_state(rloa_sim* s, const float* q, const float* qd, void* stream);
+int rloa_sim_get_state(const rloa_sim* s, float* q, float* qd, void* stream);
+
+/* motor table, [n_envs][nl] each: what setJointMotorControl2 leaves behind in Bullet
+ * (kd is 1 in every mode the reference uses).  NULL pointers are skipped. */
+int rloa_sim_set_motors(rloa_sim* s, const float* kp, const float* target_pos, const float* target_vel,
+                        const float* max_impulse, void* stream);
+/* back to the load-time state: q = qd = 0, default motors (velocity target 0, max impulse 1) */
+int rloa_sim_clear(rloa_sim* s, void* stream);
+
+typedef struct {
+    int32_t n_act;                          /* len(involved_joints) */
+    int32_t act_joint[RLOA_MAX_LINKS];      /* involved_joints */
+    int32_t n_fixed;                        /* len(fixed_joints) */
+    int32_t fixed_joint[RLOA_MAX_LINKS];    /* fixed_joints */
+    float max_force;                        /* environment.py:469 force=max_force */
+    float target_threshold;                 /* 0.05  (environment.py:311, 364) */
+    float obstacle_threshold;               /* 0.0   (environment.py:311, 368) */
+} rloa_step_config;
+
+/* Environment.step for every env (environment.py:453-485):
+ *   actions [n_envs][n_act] -> obs [n_envs][S], reward [n_envs], done [n_envs] (uint8).
+ * active (uint8 [n_envs]) may be NULL; envs with active == 0 are left untouched. */
+int rloa_sim_step(rloa_sim* s, const rloa_step_config* cfg, const float* actions, const uint8_t* active,
+                  float* obs, float* reward, uint8_t* done, void* stream);
+
+/* Environment.reset for the envs with mask != 0 (environment.py:264-309):
+ * POSITION_CONTROL targets init_targets [n_envs][n_init] on joints 0..n_init-1, then n_substeps
+ * (50) simulation steps; writes the new state of those envs into obs [n_envs][S].
+ * mask may be NULL (= all envs). */
+int rloa_sim_reset(rloa_sim* s, const uint8_t* mask, const float* init_targets, int32_t n_init,
+                   int32_t n_substeps, float* obs, void* stream);
+
+/* get_state without stepping (environment.py:431-451), plus the distances consumed by
+ * get_reward / is_terminal_state: link_obstacle [n_envs][nl] (10.0 when a link has no collision
+ * shape, collision_detector.py:56-57) and ee_target [n_envs].  Any output may be NULL. */
+int rloa_sim_observe(const rloa_sim* s, float* obs, float* link_obstacle, float* ee_target, void* stream);
+
+/* diagnostics: PGS iterations used by the last substep of every env, [n_envs] int32 */
+int rloa_sim_last_iterations(const rloa_sim* s, int32_t* iters, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Episode bookkeeping for the vectorised rollout loop
+ * (naf_components/naf_algorithm.py:243-277, rl_framework.py:336-354).
+ * score += reward; frame += 1; finished = done | (frame >= frames);
+ * finished envs get their (score, frame, reward) appended to the episode log ring and are flagged
+ * in reset_mask; their counters restart at 0.
+ * ---------------------------------------------------------------------------------------------- */
+int rloa_episode_update(int32_t n_envs, int32_t frames, const float* reward, const uint8_t* done,
+                        const uint8_t* active, float* score, int32_t* frame, uint8_t* reset_mask,
+                        float* log_score, int32_t* log_frame, float* log_last_reward, int32_t* log_env,
+                        int32_t log_capacity, int32_t* log_count, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * NAF network (naf_components/naf_neural_network.py:8-123).  Parameters live in caller-owned
+ * device tensors (the torch nn.Module owns them, so state_dict()/load_state_dict() keep the
+ * checkpoint layout of naf_algorithm.py:280-289); the struct below just carries the pointers.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t state_size, action_size, hidden;     /* S, A, H (H = 256 in the reference, rl_framework.py:452) */
+    float *w1, *b1;                              /* input_layer   [H][S], [H] */
+    float *bn1_w, *bn1_b, *bn1_mean, *bn1_var;   /* bn1 affine + running stats [H] */
+    int64_t* bn1_batches;                        /* bn1.num_batches_tracked */
+    float *w2, *b2;                              /* hidden_layer  [H][H], [H] */
+    float *bn2_w, *bn2_b, *bn2_mean, *bn2_var;
+    int64_t* bn2_batches;
+    float *w_mu, *b_mu;                          /* action_values [A][H], [A] */
+    float *w_v, *b_v;                            /* value         [1][H], [1] */
+    float *w_l, *b_l;                            /* matrix_entries [A(A+1)/2][H], [..] */
+} rloa_naf_params;
+
+typedef struct rloa_naf_ws rloa_naf_ws;          /* activations / gradients / optimiser workspace */
+int rloa_naf_ws_create(int32_t state_size, int32_t action_size, int32_t hidden, int32_t max_batch,
+                       rloa_naf_ws** out);
+void rloa_naf_ws_destroy(rloa_naf_ws* ws);
+/* 0 = fp32 CUDA-core trunk (reference-exact numerics), 1 = tcgen05 tensor-core trunk
+ * (bf16 operands, fp32 TMEM accumulation; looser bound) */
+int rloa_naf_ws_set_trunk(rloa_naf_ws* ws, int32_t mode);
+
+/* NAF.forward (naf_neural_network.py:56-123) without the sampling tail:
+ * mu [B][A], pdiag [B][A] (= diag of P = L o L^T, i.e. exp(2 tanh z_kk)), V [B], and when
+ * action != NULL, Q [B] = -1/2 sum_k P_kk (u_k - mu_k)^2 + V.  train_mode != 0 uses batch
+ * statistics and updates the running stats / num_batches_tracked like nn.BatchNorm1d.
+ * trunc_action != 0 applies the reference's .long() cast to the actions (replay_buffer.py:60). */
+int rloa_naf_forward(rloa_naf_ws* ws, const rloa_naf_params* p, const float* states, const float* action,
+                     int32_t batch, int32_t train_mode, int32_t trunc_action, float* mu, float* pdiag,
+                     float* q, float* v, void* stream);
+
+/* NAFAgent.act for a batch of states (naf_algorithm.py:158-178 + naf_neural_network.py:119-121):
+ * eval-mode forward, action = clamp(mu + exp(-tanh z_kk) * eps, -1, 1), eps ~ N(0,1) from
+ * Philox4x32-10 keyed by (seed, step, row).  noise_scale = 0 gives the mean action. */
+int rloa_naf_act(rloa_naf_ws* ws, const rloa_naf_params* p, const float* states, int32_t batch,
+                 uint64_t seed, uint64_t step, float noise_scale, float* actions, void* stream);
+
+typedef struct {
+    float gamma, tau, lr;
+    float beta1, beta2, eps;       /* Adam defaults 0.9, 0.999, 1e-8 (naf_algorithm.py:83) */
+    float clip_norm;               /* 1.0 (naf_algorithm.py:209) */
+    int32_t trunc_action;          /* 1 = reference .long() cast (replay_buffer.py:60) */
+    int32_t use_done_mask;         /* 0 = reference (naf_algorithm.py:199 ignores done) */
+    float grad_scale;              /* multiplies the gradient before clipping (1/world_size under DP) */
+} rloa_naf_hyper;
+
+typedef struct {
+    float *m, *v;                  /* Adam moments, flat [n_params] in rloa_naf_param_order */
+    int64_t* step;                 /* device scalar */
+} rloa_adam_state;
+
+int rloa_naf_num_params(int32_t state_size, int32_t action_size, int32_t hidden);
+
+/* NAFAgent.learn split at the gradient all-reduce (naf_algorithm.py:180-213):
+ *   _grads : target forward on next_states (train-mode BN), TD target r + gamma V', main forward
+ *            on (states, actions), MSE loss, backward -> flat gradient grad [n_params], loss [1];
+ *   _apply : clip_grad_norm_(1) + Adam + soft update of the target parameters (naf_algorithm.py:209-226).
+ * Between the two the caller may all-reduce `grad` across ranks. */
+int rloa_naf_learn_grads(rloa_naf_ws* ws, const rloa_naf_params* main_net, const rloa_naf_params* target_net,
+                         const float* states, const float* actions, const float* rewards,
+                         const float* next_states, const float* dones, int32_t batch,
+                         const rloa_naf_hyper* hp, float* grad, float* loss, void* stream);
+int rloa_naf_learn_apply(rloa_naf_ws* ws, const rloa_naf_params* main_net, const rloa_naf_params* target_net,
+                         const rloa_adam_state* adam, const rloa_naf_hyper* hp, float* grad,
+                         float* grad_norm, void* stream);
+/* NAFAgent.soft_update alone (naf_algorithm.py:217-226) */
+int rloa_naf_soft_update(const rloa_naf_params* main_net, const rloa_naf_params* target_net, float tau,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Replay ring in HBM (utils/replay_buffer.py:14-75).  Storage is caller-owned:
+ * states/next_states [capacity][S], actions [capacity][A], rewards/dones [capacity].
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t capacity, state_size, action_size;
+    float *states, *actions, *rewards, *next_states, *dones;
+    int64_t* cursor;               /* device scalar: total transitions ever appended */
+} rloa_replay;
+
+/* ReplayBuffer.add for n transitions (deque(maxlen) overwrite order, replay_buffer.py:32-45);
+ * rows with valid == 0 are skipped (valid may be NULL). */
+int rloa_replay_append(const rloa_replay* rb, int32_t n, const float* states, const float* actions,
+                       const float* rewards, const float* next_states, const uint8_t* dones,
+                       const uint8_t* valid, void* stream);
+/* ReplayBuffer.sample (replay_buffer.py:47-67): `batch` distinct slots drawn uniformly from the
+ * live window with a keyed Feistel permutation (seed, draw); gathers the five fields. */
+int rloa_replay_sample(const rloa_replay* rb, int32_t batch, uint64_t seed, uint64_t draw, float* states,
+                       float* actions, float* rewards, float* next_states, float* dones, int32_t* indices,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLOA_B200_H */

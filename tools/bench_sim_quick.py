@@ -1,0 +1,27 @@
+"""Quick simulator throughput probe (sim-only, U(-1,1) actions); prints env-steps/s for a few N."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from robotic_manipulator_rloa_b200.environment.robot_model import load_manipulator
+from robotic_manipulator_rloa_b200.environment.simulator import BatchedSimulator
+
+model = load_manipulator('kuka_iiwa/kuka_with_gripper2.sdf')
+for n in [int(x) for x in (sys.argv[1:] or ['4096', '16384', '65536', '262144'])]:
+    sim = BatchedSimulator(model, n, 13, [0, 1, 2, 3, 4, 5], list(range(6, 14)))
+    sim.set_task([0.4, 0.85, 0.71], [0.45, 0.55, 0.55])
+    start = torch.tensor([0.9, 0.45, 0, 0, 0, 0], device='cuda') + 0.5 * (torch.rand(n, 6, device='cuda') - 0.5)
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(); sim.reset(start); t1.record(); torch.cuda.synchronize()
+    print(f'N={n}: reset (50 substeps) {t0.elapsed_time(t1):.3f} ms -> {n*50/t0.elapsed_time(t1)*1e3:.3e} sim-steps/s')
+    acts = [2 * torch.rand(n, 6, device='cuda') - 1 for _ in range(8)]
+    for i in range(5):
+        sim.step(acts[i % 8])
+    torch.cuda.synchronize()
+    K = 50
+    t0.record()
+    for i in range(K):
+        sim.step(acts[i % 8])
+    t1.record(); torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / K
+    print(f'N={n}: step {ms*1e3:.1f} us -> {n/ms*1e3:.3e} env-steps/s; mean PGS iters {sim.last_iterations().float().mean().item():.1f}')
+    sim.close()
