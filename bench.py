@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""
+bench.py — env-steps/s of the vectorised rollout + NAF training hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs E] [--batch B]
+
+Workload (config.workload): BASELINE.json configs[1] — KUKA IIWA, fixed target / obstacle, E = 4096 envs per
+GPU, 400-step episodes with lock-step asynchronous resets, NAF replay batch 1024, one NAF update per
+vectorised step, actions from the live policy (seed-0 init, reference exploration noise).
+One "step" = act (4096 states) -> Environment.step (4096 arms) -> replay append -> episode bookkeeping / reset
+scheduling -> replay sample -> NAFAgent.learn.  `value` = policy-visible transitions (reset sub-steps excluded)
+per second over all GPUs; inputs are resident in HBM; per-step CUDA events, L2 flushed between timed steps.
+`e2e` = the same loop with every step's states / actions / results crossing pinned HOST buffers.
+
+--impl reference times the CPU restatement of the same loop (oracle/: fp64 Bullet restatement with OpenMP over
+all host cores + torch-CPU NAF), because the reference's own PyBullet path cannot run in this image.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+KUKA = dict(file='kuka_iiwa/kuka_with_gripper2.sdf', ee=13, involved=[0, 1, 2, 3, 4, 5],
+            fixed=[6, 7, 8, 9, 10, 11, 12, 13], target=[0.4, 0.85, 0.71], obstacle=[0.45, 0.55, 0.55],
+            start=[0.9, 0.45, 0, 0, 0, 0], var=[0, 0, 0, 0, 0, 0])
+FRAMES = 400
+FLOP_PER_ENV_STEP = 1.0e5        # KUKA 14 links / 12 dof / 34 rows / 50 iterations
+BYTES_PER_ENV_STEP = 329         # sim_step kernel only: q,qd r/w 192 + action 24 + task 24 + obs 84 + reward/done 5
+METRIC = 'env-steps/sec KUKA IIWA (4096 envs/GPU, 400-step episodes, NAF batch 1024, 1 update/step)'
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return float(p['hbm_gbs']), float(p.get('sm_max_mhz', 1965.0)), 'measured'
+    except Exception:
+        return 6650.0, 1965.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(',')]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU restatement of the loop (oracle/) — the --impl reference arm and the cpu_baseline leg
+# ------------------------------------------------------------------------------------------------------------
+class CpuLoop:
+    def __init__(self, n_envs: int, batch: int, update_every: int, cores: int, seed: int = 0):
+        import numpy as np
+        import torch
+        from helpers import make_oracle, step_motors
+        from oracle.naf_restatement import NAFRef
+        self.np, self.torch = np, torch
+        torch.set_num_threads(cores)
+        self.cores, self.n, self.batch, self.update_every = cores, n_envs, batch, update_every
+        self.cfg = dict(KUKA)
+        self.model, self.orc = make_oracle(dict(file=KUKA['file'], ee=KUKA['ee'], involved=KUKA['involved']))
+        self.rng = np.random.default_rng(seed)
+        nl = self.model.nl
+        self.q, self.qd = np.zeros((n_envs, nl)), np.zeros((n_envs, nl))
+        init = np.tile(np.asarray(KUKA['start'], dtype=np.float64), (n_envs, 1))
+        self.orc.batch_reset(self.q, self.qd, init, 50, nthreads=cores)
+        for j in range(len(KUKA['start'])):
+            self.orc.set_position_control(j, KUKA['start'][j])
+        step_motors(self.orc, KUKA)
+        self.main, self.target = NAFRef(21, 6, 256, seed=0), NAFRef(21, 6, 256, seed=0)
+        self.opt = torch.optim.Adam(self.main.parameters(), lr=1e-3)
+        self.obs = np.zeros((n_envs, 21), dtype=np.float32)
+        for e in range(n_envs):
+            self.obs[e] = self.orc.observe(self.q[e], self.qd[e], KUKA['obstacle'], KUKA['target'])[0]
+        cap = 100000
+        self.rs, self.ra = np.zeros((cap, 21), np.float32), np.zeros((cap, 6), np.float32)
+        self.rr, self.rs2, self.rd = np.zeros((cap, 1), np.float32), np.zeros((cap, 21), np.float32), np.zeros((cap, 1), np.float32)
+        self.cursor, self.cap, self.t = 0, cap, 0
+        self.frame = self.rng.integers(0, FRAMES, n_envs)
+        self.transitions = 0
+
+    def step(self):
+        np, torch = self.np, self.torch
+        from oracle.naf_restatement import learn_ref
+        self.main.eval()
+        with torch.no_grad():
+            mu, P, _, _ = self.main.heads(torch.from_numpy(self.obs))
+            std = torch.rsqrt(torch.diagonal(P, dim1=1, dim2=2))
+            act = torch.clamp(mu + std * torch.randn_like(mu), -1, 1).numpy()
+        obs2, rew, done, _ = self.orc.batch_step(self.q, self.qd, act.astype(np.float64), KUKA['involved'], 200.0,
+                                                 KUKA['obstacle'], KUKA['target'], nthreads=self.cores)
+        idx = (self.cursor + np.arange(self.n)) % self.cap
+        self.rs[idx], self.ra[idx], self.rr[idx, 0] = self.obs, act, rew
+        self.rs2[idx], self.rd[idx, 0] = obs2, done
+        self.cursor += self.n
+        self.transitions += self.n
+        self.t += 1
+        if self.t % self.update_every == 0 and min(self.cursor, self.cap) > self.batch:
+            pick = self.rng.choice(min(self.cursor, self.cap), self.batch, replace=False)
+            b = (torch.from_numpy(self.rs[pick]), torch.from_numpy(self.ra[pick]).long(), torch.from_numpy(self.rr[pick]),
+                 torch.from_numpy(self.rs2[pick]), torch.from_numpy(self.rd[pick]))
+            learn_ref(self.main, self.target, self.opt, b, 0.99, 1e-3)
+        self.frame += 1
+        fin = (done != 0) | (self.frame >= FRAMES)
+        self.obs = obs2.astype(np.float32)
+        if fin.any():            # synchronous Environment.reset of the finished envs, as the reference does
+            k = np.nonzero(fin)[0]
+            q, qd = np.ascontiguousarray(self.q[k]), np.ascontiguousarray(self.qd[k])
+            init = np.tile(np.asarray(KUKA['start'], dtype=np.float64), (len(k), 1))
+            self.orc.batch_reset(q, qd, init, 50, nthreads=self.cores)
+            self.q[k], self.qd[k] = q, qd
+            for i, e in enumerate(k):
+                self.obs[e] = self.orc.observe(q[i], qd[i], KUKA['obstacle'], KUKA['target'])[0]
+            self.frame[k] = 0
+
+
+def run_cpu(steps: int, warmup: int, n_envs: int, batch: int, update_every: int):
+    cores = os.cpu_count() or 1
+    loop = CpuLoop(n_envs, batch, update_every, cores)
+    for _ in range(warmup):
+        loop.step()
+    loop.transitions = 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loop.step()
+    dt = time.perf_counter() - t0
+    return loop.transitions / dt, dt / steps * 1e3, cores
+
+
+def reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n_cpu, every = 512, 8        # 512 envs per step, one B=1024 update per 8 steps = 1 update per 4096 env-steps
+    value, ms, cores = run_cpu(args.steps, args.warmup, n_cpu, args.batch, every)
+    sample = (f'{n_cpu} envs per step (1/8 of the 4096-env workload), one batch-{args.batch} NAF update every {every} '
+              f'steps (same update:data ratio), {args.steps} steps')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args, 'cpu'),
+        'cpu_baseline': {'value': value, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'note': 'PyBullet is absent from this image: the CPU arm is the fp64 C restatement of the Bullet step '
+                '(oracle/, OpenMP over all host cores) + the torch-CPU NAF restatement',
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, where):
+    return {'workload': 'BASELINE.json configs[1]: KUKA IIWA kuka_with_gripper2 (stand-in asset), fixed target/obstacle, '
+                        f'{args.envs} envs per GPU, {FRAMES}-step episodes, NAF batch {args.batch}, 1 update per '
+                        'vectorised step, live-policy actions',
+            'envs_per_gpu': args.envs, 'replay_batch': args.batch, 'frames': FRAMES, 'parallelism': f'env-dp{args.gpus}',
+            'l2': 'flushed between timed steps (256 MiB fill, untimed)' if where == 'gpu' else 'n/a',
+            'trunk': getattr(args, 'trunk', 'fp32')}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    from robotic_manipulator_rloa_b200 import _native
+    from robotic_manipulator_rloa_b200.environment.environment import Environment, EnvironmentConfiguration
+    from robotic_manipulator_rloa_b200.naf_components.naf_algorithm import NAFAgent
+
+    rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+    lib = _native.lib()
+
+    import logging
+    logging.getLogger().setLevel(logging.ERROR)
+    cfg = EnvironmentConfiguration(endeffector_index=KUKA['ee'], fixed_joints=KUKA['fixed'],
+                                   involved_joints=KUKA['involved'], target_position=KUKA['target'],
+                                   obstacle_position=KUKA['obstacle'], initial_joint_positions=KUKA['start'],
+                                   initial_positions_variation_range=KUKA['var'], visualize=False)
+    env = Environment(KUKA['file'], cfg, n_envs=args.envs, device=dev, seed=rank)
+    agent = NAFAgent(env, 21, 6, 256, args.batch, 100000, 1e-3, 1e-3, 0.99, 1, 1, 500, dev, seed=0)
+    agent.seed = 1000 + rank                      # exploration noise differs per rank; weights start identical
+    agent.memory.seed = 2000 + rank
+    if args.trunk == 'tc':
+        agent.set_trunk_mode(1)
+    loop = agent.make_loop(FRAMES, 1 << 22)
+    loop.reset_all()
+    # steady-state episode phases: spread the 400-step timeouts uniformly
+    loop.frame.copy_(torch.randint(0, FRAMES, (args.envs,), device=dev, dtype=torch.int32))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if not args.no_flush else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        loop.step()
+    barrier()
+
+    # ---- timed region: K steps, per-step CUDA events, L2 flushed between steps -------------------------------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sim_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    loop.transitions.zero_()
+    launches0 = lib.rloa_launch_count()
+    orig_step = env.sim.step
+
+    def timed_sim_step(*a, **k):
+        i = timed_sim_step.i
+        sim_ev[i][0].record()
+        out = orig_step(*a, **k)
+        sim_ev[i][1].record()
+        return out
+    env.sim.step = timed_sim_step
+    barrier()
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        if flush is not None:
+            flush.fill_(i & 0xff)
+        timed_sim_step.i = i
+        ev[i][0].record()
+        loop.step()
+        ev[i][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    env.sim.step = orig_step
+    launches = lib.rloa_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    sim_ms = [a.elapsed_time(b) for a, b in sim_ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    trans = loop.transitions.clone().to(torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(trans, op=dist.ReduceOp.SUM)
+    total_ms, trans = float(total_ms.item()), float(trans.item())
+    value = trans / (total_ms * 1e-3)
+
+    # ---- e2e: same loop, every step's states/actions/results cross pinned host buffers -----------------------
+    n, S, A = args.envs, 21, 6
+    h_state = torch.zeros(n, S).pin_memory(); h_act = torch.zeros(n, A).pin_memory()
+    h_rew = torch.zeros(n).pin_memory(); h_done = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    h_state.copy_(loop.state)
+    e2e_steps = max(10, args.steps // 4)
+    loop.transitions.zero_()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(e2e_steps):
+        loop.state.copy_(h_state, non_blocking=True)                      # H2D: this step's states
+        agent.act_batch(loop.state, out=loop.actions)
+        h_act.copy_(loop.actions, non_blocking=True)                      # D2H: actions to the caller
+        torch.cuda.current_stream().synchronize()
+        loop.actions.copy_(h_act, non_blocking=True)                      # H2D: actions into Environment.step
+        env.sim.step(loop.actions, out=(loop.next_state, loop.reward, loop.done), valid=loop.valid)
+        h_state.copy_(loop.next_state, non_blocking=True)                 # D2H: (state, reward, done)
+        h_rew.copy_(loop.reward, non_blocking=True)
+        h_done.copy_(loop.done, non_blocking=True)
+        agent.memory.add_batch(loop.state, loop.actions, loop.reward, loop.next_state, loop.done, valid=loop.valid)
+        agent._maybe_learn()
+        _native.check(lib.rloa_episode_update(n, FRAMES, loop.reward.data_ptr(), loop.done.data_ptr(), loop.valid.data_ptr(),
+                                              loop.score.data_ptr(), loop.frame.data_ptr(), loop.reset_mask.data_ptr(),
+                                              loop.log_score.data_ptr(), loop.log_frame.data_ptr(), loop.log_last.data_ptr(),
+                                              loop.log_env.data_ptr(), loop.cap, loop.log_count.data_ptr(),
+                                              loop.transitions.data_ptr(), agent._stream()))
+        env.sim.begin_reset(env.initial_targets(), mask=loop.reset_mask)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    e2e_tr = loop.transitions.clone().to(torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_tr, op=dist.ReduceOp.SUM)
+    e2e_value = float(e2e_tr.item()) / (float(e2e_ms.item()) * 1e-3)
+
+    if rank == 0:
+        hbm_peak, sm_max, which = measured_peaks()
+        sim_avg_ms = sum(sim_ms) / len(sim_ms)
+        # env sub-steps executed per launch (action steps + reset sub-steps): every env runs one
+        gbs = BYTES_PER_ENV_STEP * args.envs / (sim_avg_ms * 1e-3) / 1e9
+        sm_mhz = (clocks or {}).get('sm_mhz') or sm_max
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        tflops = FLOP_PER_ENV_STEP * args.envs / (sim_avg_ms * 1e-3) / 1e12
+        cpu_value, cpu_ms, cores = (None, None, os.cpu_count())
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cpu_value, cpu_ms, cores = run_cpu(48, 4, 512, args.batch, 8)
+            cpu = {'value': cpu_value, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
+                   'sample': '48 steps x 512 envs (1/8 of the workload per step), one batch-%d NAF update every 8 steps; '
+                             'fp64 C restatement of the Bullet step (OpenMP, all cores) + torch-CPU NAF' % args.batch}
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args, 'gpu'),
+            'naf_updates_per_s': args.steps / (total_ms * 1e-3),
+            'sim_substeps_per_s': world * args.envs * args.steps / (total_ms * 1e-3),
+            'wall_ms_per_step_incl_flush': t_wall / args.steps * 1e3,
+            'roofline': {'kernel': 'sim_step_kernel', 'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                         'frac': gbs / hbm_peak, 'traffic': None, 'peak_source': which,
+                         'avg_launch_ms': sim_avg_ms, 'share_of_step': sim_avg_ms * args.steps / total_ms,
+                         'note': 'the kernel is FP32-issue / latency bound, not HBM bound (SURVEY 8d): see fp32',
+                         'fp32': {'achieved': tflops, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': tflops / fp32_peak,
+                                  'flop_per_env_step': FLOP_PER_ENV_STEP, 'sm_mhz': sm_mhz}},
+            'cpu_baseline': cpu,
+            'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n * (S + A) * 4,
+                    'd2h_bytes_per_step': n * (A * 4 + S * 4 + 4 + 1), 'steps': e2e_steps},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--envs', type=int, default=4096, help='envs per GPU')
+    ap.add_argument('--batch', type=int, default=1024, help='replay batch per GPU')
+    ap.add_argument('--trunk', default='fp32', choices=['fp32', 'tc'])
+    ap.add_argument('--no-flush', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == '__main__':
+    main()

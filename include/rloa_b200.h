@@ -131,9 +131,19 @@ typedef struct {
 
 /* Environment.step for every env (environment.py:453-485):
  *   actions [n_envs][n_act] -> obs [n_envs][S], reward [n_envs], done [n_envs] (uint8).
- * active (uint8 [n_envs]) may be NULL; envs with active == 0 are left untouched. */
+ * active (uint8 [n_envs]) may be NULL; envs with active == 0 are left untouched.
+ * An env with pending reset sub-steps (rloa_sim_begin_reset) runs one of them instead of an action step
+ * and reports valid = 0, reward = 0, done = 0; valid (uint8 [n_envs]) may be NULL. */
 int rloa_sim_step(rloa_sim* s, const rloa_step_config* cfg, const float* actions, const uint8_t* active,
-                  float* obs, float* reward, uint8_t* done, void* stream);
+                  float* obs, float* reward, uint8_t* done, uint8_t* valid, void* stream);
+
+/* Lock-step asynchronous Environment.reset for the vectorised loop: arms the POSITION_CONTROL motors of
+ * the masked envs (joints 0..n_init-1 -> init_targets) and schedules n_substeps (50) reset sub-steps,
+ * executed one per rloa_sim_step launch, so envs that keep acting never wait for a resetting one
+ * (environment.py:295-301).  The obs written by the launch that finishes the last sub-step is the new
+ * episode's first state. */
+int rloa_sim_begin_reset(rloa_sim* s, const uint8_t* mask, const float* init_targets, int32_t n_init,
+                         int32_t n_substeps, void* stream);
 
 /* Environment.reset for the envs with mask != 0 (environment.py:264-309):
  * POSITION_CONTROL targets init_targets [n_envs][n_init] on joints 0..n_init-1, then n_substeps
@@ -155,12 +165,13 @@ int rloa_sim_last_iterations(const rloa_sim* s, int32_t* iters, void* stream);
  * (naf_components/naf_algorithm.py:243-277, rl_framework.py:336-354).
  * score += reward; frame += 1; finished = done | (frame >= frames);
  * finished envs get their (score, frame, reward) appended to the episode log ring and are flagged
- * in reset_mask; their counters restart at 0.
+ * in reset_mask; their counters restart at 0.  `active` (may be NULL) selects the envs that produced a
+ * transition this step; `transitions` (device int64, may be NULL) accumulates their number.
  * ---------------------------------------------------------------------------------------------- */
 int rloa_episode_update(int32_t n_envs, int32_t frames, const float* reward, const uint8_t* done,
                         const uint8_t* active, float* score, int32_t* frame, uint8_t* reset_mask,
                         float* log_score, int32_t* log_frame, float* log_last_reward, int32_t* log_env,
-                        int32_t log_capacity, int32_t* log_count, void* stream);
+                        int32_t log_capacity, int32_t* log_count, int64_t* transitions, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * NAF network (naf_components/naf_neural_network.py:8-123).  Parameters live in caller-owned
@@ -243,6 +254,7 @@ typedef struct {
     int32_t capacity, state_size, action_size;
     float *states, *actions, *rewards, *next_states, *dones;
     int64_t* cursor;               /* device scalar: total transitions ever appended */
+    int32_t* scratch;              /* device, >= (max n per append + 1023) / 1024 + 1 ints (valid-mask compaction) */
 } rloa_replay;
 
 /* ReplayBuffer.add for n transitions (deque(maxlen) overwrite order, replay_buffer.py:32-45);

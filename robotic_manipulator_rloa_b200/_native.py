@@ -70,7 +70,7 @@ class AdamState(C.Structure):
 class Replay(C.Structure):
     _fields_ = [('capacity', C.c_int32), ('state_size', C.c_int32), ('action_size', C.c_int32),
                 ('states', _fp), ('actions', _fp), ('rewards', _fp), ('next_states', _fp), ('dones', _fp),
-                ('cursor', _fp)]
+                ('cursor', _fp), ('scratch', _fp)]
 
 
 _VP = C.c_void_p
@@ -94,11 +94,12 @@ SIGNATURES = {
     'rloa_sim_get_state': (C.c_int, [_VP, _fp, _fp, _VP]),
     'rloa_sim_set_motors': (C.c_int, [_VP, _fp, _fp, _fp, _fp, _VP]),
     'rloa_sim_clear': (C.c_int, [_VP, _VP]),
-    'rloa_sim_step': (C.c_int, [_VP, C.POINTER(StepConfig), _fp, _fp, _fp, _fp, _fp, _VP]),
+    'rloa_sim_step': (C.c_int, [_VP, C.POINTER(StepConfig), _fp, _fp, _fp, _fp, _fp, _fp, _VP]),
+    'rloa_sim_begin_reset': (C.c_int, [_VP, _fp, _fp, _I, _I, _VP]),
     'rloa_sim_reset': (C.c_int, [_VP, _fp, _fp, _I, _I, _fp, _VP]),
     'rloa_sim_observe': (C.c_int, [_VP, _fp, _fp, _fp, _VP]),
     'rloa_sim_last_iterations': (C.c_int, [_VP, _fp, _VP]),
-    'rloa_episode_update': (C.c_int, [_I, _I, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _I, _fp, _VP]),
+    'rloa_episode_update': (C.c_int, [_I, _I, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _I, _fp, _fp, _VP]),
     'rloa_naf_ws_create': (C.c_int, [_I, _I, _I, _I, C.POINTER(_VP)]),
     'rloa_naf_ws_destroy': (None, [_VP]),
     'rloa_naf_ws_set_trunk': (C.c_int, [_VP, _I]),

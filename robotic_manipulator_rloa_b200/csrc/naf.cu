@@ -1,14 +1,883 @@
-// placeholder: NAF entry points (filled in next)
+// librloa_b200: NAF network kernels and C ABI (include/rloa_b200.h).
+//
+// Replaces the torch ops under NAF.forward (reference naf_components/naf_neural_network.py:56-123),
+// NAFAgent.act / learn / soft_update (naf_components/naf_algorithm.py:158-226).
+// Reference quirks reproduced on purpose: P = L o L^T is elementwise, so only
+// the diagonal of L matters and P_kk = exp(2 tanh z_kk); replayed actions are truncated like .long();
+// the TD target has no (1 - done) factor; both nets run train-mode BatchNorm inside learn().
+//
+// fp32 CUDA-core path: tiled SGEMMs with fused BN+ReLU prologues, column-owned BatchNorm statistics
+// (two-pass, no atomics), one fused head kernel (mu, V, diag L, advantage, TD error, head gradients),
+// deterministic split-K weight gradients, fused clip-norm + Adam + soft target update.
+#include <cmath>
+#include <cstring>
+#include <new>
+
 #include "common.cuh"
+#include "naf_trunk_tc.cuh"
+
+namespace rloa {
+
+constexpr float kBnEps = 1e-5f;        // nn.BatchNorm1d defaults
+constexpr float kBnMomentum = 0.1f;
+
+// ------------------------------------------------------------------------------------------------
+// generic tiled SGEMM  C[i][j] = sum_k Aop(i,k) Bop(k,j)
+//   NT: Aop = pro(A[i][k]),  Bop = W[j][k]      (forward linear, + bias[j])
+//   NN: Aop = A[i][k],       Bop = W[k][j]      (input gradient)
+//   TN: Aop = A[k][i],       Bop = pro(B[k][j]) (weight gradient, split over k = batch)
+// pro(x, f) = relu(x * scale[f] + shift[f]) re-creates the BN+ReLU activation on the fly.
+// ------------------------------------------------------------------------------------------------
+enum { kNT = 0, kNN = 1, kTN = 2 };
+constexpr int BM = 64, BN = 64, BK = 16, kGemmThreads = 256, kPad = 4;
+
+struct GemmArgs {
+    const float* A; int lda;
+    const float* B; int ldb;
+    float* C; int ldc;
+    const float* bias;
+    const float* pro_scale; const float* pro_shift;
+    int M, N, K;
+    int ksplit;                 // TN: k-range length per blockIdx.z (0 = no split)
+};
+struct GemmBatch {
+    GemmArgs a[2];
+};
+
+template <int LAYOUT, bool PRO>
+__global__ void __launch_bounds__(kGemmThreads) gemm_kernel(GemmBatch batch) {
+    const GemmArgs& g = (LAYOUT == kTN) ? batch.a[0] : batch.a[blockIdx.z];
+    __shared__ float As[BK][BM + kPad];
+    __shared__ float Bs[BK][BN + kPad];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+    int k_begin = 0, k_end = g.K;
+    float* C = g.C;
+    if (LAYOUT == kTN && g.ksplit > 0) {
+        k_begin = blockIdx.z * g.ksplit;
+        k_end = min(g.K, k_begin + g.ksplit);
+        C += (size_t)blockIdx.z * g.M * g.ldc;
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int e = tid + r * kGemmThreads;
+            {   // A tile
+                int i, k;
+                if (LAYOUT == kTN) { i = e & (BM - 1); k = e / BM; }
+                else { k = e & (BK - 1); i = e / BK; }
+                const int gi = i0 + i, gk = k0 + k;
+                float v = 0.f;
+                if (gi < g.M && gk < k_end) {
+                    if (LAYOUT == kTN) v = g.A[(size_t)gk * g.lda + gi];
+                    else {
+                        v = g.A[(size_t)gi * g.lda + gk];
+                        if (PRO && LAYOUT == kNT) v = fmaxf(fmaf(v, g.pro_scale[gk], g.pro_shift[gk]), 0.f);
+                    }
+                }
+                As[k][i] = v;
+            }
+            {   // B tile
+                int j, k;
+                if (LAYOUT == kNT) { k = e & (BK - 1); j = e / BK; }
+                else { j = e & (BN - 1); k = e / BN; }
+                const int gj = j0 + j, gk = k0 + k;
+                float v = 0.f;
+                if (gj < g.N && gk < k_end) {
+                    if (LAYOUT == kNT) v = g.B[(size_t)gj * g.ldb + gk];
+                    else {
+                        v = g.B[(size_t)gk * g.ldb + gj];
+                        if (PRO && LAYOUT == kTN) v = fmaxf(fmaf(v, g.pro_scale[gj], g.pro_shift[gj]), 0.f);
+                    }
+                }
+                Bs[k][j] = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; k++) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int gi = i0 + ty * 4 + i;
+        if (gi >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int gj = j0 + tx * 4 + j;
+            if (gj >= g.N) continue;
+            float v = acc[i][j];
+            if (LAYOUT == kNT && g.bias != nullptr) v += g.bias[gj];
+            C[(size_t)gi * g.ldc + gj] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm1d statistics, one block per 32 features, all rows (two-pass: mean, then centred variance).
+// train: scale = w / sqrt(var_b + eps), shift = b - mean_b scale; running stats updated with momentum 0.1
+// and the unbiased variance; num_batches_tracked += 1.   eval: the same from the running statistics.
+// ------------------------------------------------------------------------------------------------
+struct BnArgs {
+    const float* z;             // [B][H]
+    const float *w, *b;
+    float *run_mean, *run_var;
+    int64_t* batches;
+    float *scale, *shift, *mean, *rstd;
+};
+struct BnBatch {
+    BnArgs a[2];
+};
+
+__device__ __forceinline__ float block_colsum_32x8(float v, float (*red)[33]) {
+    // 256 threads = 8 row lanes x 32 columns; returns the column total to every thread of the column
+    const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+    red[r][c] = v;
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += red[k][c];
+    __syncthreads();
+    return s;
+}
+
+__global__ void __launch_bounds__(256) bn_stats_kernel(BnBatch batch, int B, int H, int train) {
+    const BnArgs& a = batch.a[blockIdx.y];
+    __shared__ float red[8][33];
+    const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int f = blockIdx.x * 32 + c;
+    if (f >= H) return;         // H is a multiple of 32 (checked on the host): whole block stays converged
+    float mean, var;
+    if (train) {
+        float s = 0.f;
+        for (int row = r; row < B; row += 8) s += a.z[(size_t)row * H + f];
+        mean = block_colsum_32x8(s, red) / (float)B;
+        float m2 = 0.f;
+        for (int row = r; row < B; row += 8) {
+            const float d = a.z[(size_t)row * H + f] - mean;
+            m2 = fmaf(d, d, m2);
+        }
+        m2 = block_colsum_32x8(m2, red);
+        var = m2 / (float)B;
+        if (r == 0) {
+            const float unbiased = B > 1 ? m2 / (float)(B - 1) : var;
+            a.run_mean[f] = fmaf(kBnMomentum, mean - a.run_mean[f], a.run_mean[f]);
+            a.run_var[f] = fmaf(kBnMomentum, unbiased - a.run_var[f], a.run_var[f]);
+            if (blockIdx.x == 0 && c == 0 && a.batches != nullptr) *a.batches += 1;
+        }
+    } else {
+        mean = a.run_mean[f];
+        var = a.run_var[f];
+    }
+    if (r == 0) {
+        const float rstd = 1.f / sqrtf(var + kBnEps);
+        const float sc = a.w[f] * rstd;
+        a.scale[f] = sc;
+        a.shift[f] = fmaf(-mean, sc, a.b[f]);
+        a.mean[f] = mean;
+        a.rstd[f] = rstd;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN + ReLU backward, column owned: g = da * [z scale + shift > 0]; dgamma = sum g xhat; dbeta = sum g;
+// dz = w rstd (g - dbeta/B - xhat dgamma/B) written in place over da; dbias(linear) = sum dz.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_relu_backward_kernel(float* __restrict__ da, const float* __restrict__ z, const float* __restrict__ w,
+                        const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                        const float* __restrict__ rstd, int B, int H, float* __restrict__ d_w, float* __restrict__ d_b,
+                        float* __restrict__ d_lin_bias) {
+    __shared__ float red[8][33];
+    const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int f = blockIdx.x * 32 + c;
+    if (f >= H) return;
+    const float sc = scale[f], sh = shift[f], mu = mean[f], rs = rstd[f];
+    float sg = 0.f, sgx = 0.f;
+    for (int row = r; row < B; row += 8) {
+        const size_t idx = (size_t)row * H + f;
+        const float zz = z[idx];
+        const float g = fmaf(zz, sc, sh) > 0.f ? da[idx] : 0.f;
+        sg += g;
+        sgx = fmaf(g, (zz - mu) * rs, sgx);
+    }
+    sg = block_colsum_32x8(sg, red);
+    sgx = block_colsum_32x8(sgx, red);
+    const float k1 = w[f] * rs, c1 = sg / (float)B, c2 = sgx / (float)B;
+    float sdz = 0.f;
+    for (int row = r; row < B; row += 8) {
+        const size_t idx = (size_t)row * H + f;
+        const float zz = z[idx];
+        const float g = fmaf(zz, sc, sh) > 0.f ? da[idx] : 0.f;
+        const float dz = k1 * (g - c1 - (zz - mu) * rs * c2);
+        da[idx] = dz;
+        sdz += dz;
+    }
+    sdz = block_colsum_32x8(sdz, red);
+    if (r == 0) {
+        d_w[f] = sgx;
+        d_b[f] = sg;
+        d_lin_bias[f] = sdz;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller for the exploration noise (replaces MultivariateNormal.sample())
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+// ------------------------------------------------------------------------------------------------
+// Fused head: a2 = relu(bn2(z2)); [mu | V | L-entries] = a2 Wh^T + bh; mu = tanh, l_kk = tanh;
+// P_kk = exp(2 l_kk); Q = V - 1/2 sum_k P_kk (u_k - mu_k)^2; TD error; gradients of the head
+// pre-activations; or (act mode) the clamped noisy action.   One warp per row, lane = head output.
+// ------------------------------------------------------------------------------------------------
+struct HeadArgs {
+    const float* z2; const float *scale, *shift;    // [B][H], [H]
+    const float *w_mu, *b_mu, *w_v, *b_v, *w_l, *b_l;
+    int B, H, A, NL;
+    const float* action;         // [B][A] or null
+    int trunc_action;
+    // outputs (any may be null)
+    float *mu, *pdiag, *q, *v;
+    // TD-target production (target net): y = reward + gamma * V * (use_done ? 1 - done : 1)
+    const float *reward, *done; float gamma; int use_done; float* y_out;
+    // training (main net): y_in -> loss partial + dZh
+    const float* y_in; float* dzh; float* loss_part;
+    // act mode
+    float* act_out; unsigned long long seed, step; float noise_scale;
+};
+
+constexpr int kHeadWarps = 8;
+
+__global__ void __launch_bounds__(kHeadWarps * 32) naf_head_kernel(HeadArgs h) {
+    extern __shared__ float hs[];
+    const int H = h.H, A = h.A, NL = h.NL, NH = A + 1 + NL, HS = H + 1;
+    float* Wh = hs;                               // [NH][H+1]
+    float* bh = Wh + NH * HS;                     // [NH]
+    float* arow = bh + ((NH + 31) & ~31);         // [warps][H]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int idx = tid; idx < NH * H; idx += blockDim.x) {
+        const int o = idx / H, k = idx - o * H;
+        float w;
+        if (o < A) w = h.w_mu[o * H + k];
+        else if (o == A) w = h.w_v[k];
+        else w = h.w_l[(o - A - 1) * H + k];
+        Wh[o * HS + k] = w;
+    }
+    for (int o = tid; o < NH; o += blockDim.x) bh[o] = o < A ? h.b_mu[o] : (o == A ? h.b_v[0] : h.b_l[o - A - 1]);
+    __syncthreads();
+    float* ar = arow + warp * H;
+    float loss_acc = 0.f;
+    const int row_stride = gridDim.x * kHeadWarps;
+    for (int row = blockIdx.x * kHeadWarps + warp; row < h.B; row += row_stride) {
+        for (int k = lane; k < H; k += 32) ar[k] = fmaxf(fmaf(h.z2[(size_t)row * H + k], h.scale[k], h.shift[k]), 0.f);
+        __syncwarp();
+        float zo[2] = {0.f, 0.f};                 // head pre-activations of outputs lane, lane + 32
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int o = lane + 32 * s;
+            if (o < NH) {
+                const float* wr = Wh + o * HS;
+                float acc0 = 0.f, acc1 = 0.f;
+                for (int k = 0; k < H; k += 2) {
+                    acc0 = fmaf(ar[k], wr[k], acc0);
+                    acc1 = fmaf(ar[k + 1], wr[k + 1], acc1);
+                }
+                zo[s] = acc0 + acc1 + bh[o];
+            }
+        }
+        __syncwarp();
+        // lane k < A gathers its mu pre-activation (own slot 0) and the diagonal entry k(k+3)/2 of L
+        const int didx = A + 1 + (lane * (lane + 3)) / 2;
+        const int dsrc = (lane < A) ? (didx & 31) : lane;
+        const float d0 = __shfl_sync(0xffffffffu, zo[0], dsrc), d1 = __shfl_sync(0xffffffffu, zo[1], dsrc);
+        const float vval = __shfl_sync(0xffffffffu, zo[0], A & 31);     // A < 32
+        float mu = 0.f, t = 0.f, P = 0.f, diff = 0.f, adv = 0.f;
+        if (lane < A) {
+            mu = tanhf(zo[0]);
+            t = tanhf(didx < 32 ? d0 : d1);
+            P = expf(2.f * t);
+            if (h.action != nullptr) {
+                float u = h.action[(size_t)row * A + lane];
+                if (h.trunc_action) u = truncf(u);
+                diff = u - mu;
+                adv = -0.5f * P * diff * diff;
+            }
+            if (h.mu) h.mu[(size_t)row * A + lane] = mu;
+            if (h.pdiag) h.pdiag[(size_t)row * A + lane] = P;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) adv += __shfl_xor_sync(0xffffffffu, adv, off);
+        const float q = adv + vval;
+        if (lane == 0) {
+            if (h.v) h.v[row] = vval;
+            if (h.q && h.action) h.q[row] = q;
+            if (h.y_out) {
+                float vv = vval;
+                if (h.use_done && h.done) vv *= (1.f - h.done[row]);
+                h.y_out[row] = fmaf(h.gamma, vv, h.reward[row]);
+            }
+        }
+        if (h.dzh != nullptr) {
+            // MSE over the batch: dLoss/dQ = 2 (Q - y) / B
+            const float err = q - h.y_in[row];
+            if (lane == 0) loss_acc = fmaf(err, err, loss_acc);
+            const float dq = 2.f * err / (float)h.B;
+            const float g_mu = dq * P * diff * (1.f - mu * mu);         // lanes < A
+            const float g_l = dq * (-P * diff * diff) * (1.f - t * t);  // lanes < A, belongs to output didx
+            // route g_l from lane k to the lane/slot that owns output didx(k)
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const int o = lane + 32 * s;
+                float g = 0.f;
+                // which k (if any) has didx(k) == o ?  k(k+3)/2 = o - A - 1
+                int ksrc = -1;
+                const int e = o - A - 1;
+                if (e >= 0) {
+                    for (int k = 0; k < A; k++) if ((k * (k + 3)) / 2 == e) ksrc = k;
+                }
+                const float gl = __shfl_sync(0xffffffffu, g_l, ksrc < 0 ? 0 : ksrc);
+                if (o < A) g = g_mu;
+                else if (o == A) g = dq;
+                else if (ksrc >= 0) g = gl;
+                if (o < NH) h.dzh[(size_t)row * NH + o] = g;
+            }
+        }
+        if (h.act_out != nullptr && lane < A) {
+            // action ~ N(mu, P^-1) with diagonal P: std_k = exp(-l_kk); clamp to [-1, 1]
+            uint32_t c[4] = {(uint32_t)row, (uint32_t)lane, (uint32_t)h.step, (uint32_t)(h.step >> 32)};
+            philox4x32_10(c, (uint32_t)h.seed, (uint32_t)(h.seed >> 32));
+            const float r = sqrtf(-2.f * logf(u01(c[0])));
+            const float eps = r * cospif(2.f * u01(c[1]));
+            const float a = fmaf(h.noise_scale * expf(-t), eps, mu);
+            h.act_out[(size_t)row * A + lane] = fminf(fmaxf(a, -1.f), 1.f);
+        }
+        __syncwarp();
+    }
+    if (h.loss_part != nullptr) {
+        __shared__ float lp[kHeadWarps];
+        if (lane == 0) lp[warp] = loss_acc;
+        __syncthreads();
+        if (tid == 0) {
+            float s = 0.f;
+            for (int w = 0; w < kHeadWarps; w++) s += lp[w];
+            h.loss_part[blockIdx.x] = s;
+        }
+    }
+}
+
+// column sums of dZh [B][NH] -> head bias gradients, and the loss scalar from the per-block partials
+__global__ void __launch_bounds__(256)
+head_bias_grad_kernel(const float* __restrict__ dzh, int B, int NH, int A, float* __restrict__ g_bmu,
+                      float* __restrict__ g_bv, float* __restrict__ g_bl, const float* __restrict__ loss_part, int nparts,
+                      float* __restrict__ loss) {
+    __shared__ float red[256];
+    const int o = blockIdx.x;
+    float s = 0.f;
+    if (o < NH) {
+        for (int row = threadIdx.x; row < B; row += 256) s += dzh[(size_t)row * NH + o];
+    } else {
+        for (int i = threadIdx.x; i < nparts; i += 256) s += loss_part[i];
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float t = red[0];
+        if (o < A) g_bmu[o] = t;
+        else if (o == A) g_bv[0] = t;
+        else if (o < NH) g_bl[o - A - 1] = t;
+        else if (loss != nullptr) *loss = t / (float)B;
+    }
+}
+
+// sums the split-K partials of up to 3 weight gradients in a fixed order (deterministic)
+struct ReduceSeg {
+    const float* part; float* out; int n; int nsplit; size_t pstride;
+};
+struct ReduceArgs {
+    ReduceSeg s[5];
+};
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(ReduceArgs r) {
+    const ReduceSeg& s = r.s[blockIdx.y];
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < s.n; i += gridDim.x * 256) {
+        float t = 0.f;
+        for (int k = 0; k < s.nsplit; k++) t += s.part[k * s.pstride + i];
+        s.out[i] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// optimiser: global grad norm, then clip + Adam + soft target update in one vectorised pass
+// ------------------------------------------------------------------------------------------------
+constexpr int kNormBlocks = 64;
+__global__ void __launch_bounds__(256) grad_sqsum_kernel(const float* __restrict__ g, int n, float scale,
+                                                         float* __restrict__ partial, int64_t* __restrict__ step_ptr) {
+    __shared__ float red[256];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && step_ptr != nullptr) *step_ptr += 1;   // optimizer.step() counter
+    float s = 0.f;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const float x = g[i] * scale;
+        s = fmaf(x, x, s);
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+struct ParamTable {               // the 14 parameter tensors in nn.Module.parameters() order
+    float* main[14];
+    float* target[14];
+    int offset[15];
+};
+
+__global__ void __launch_bounds__(256)
+adam_soft_update_kernel(ParamTable pt, const float* __restrict__ grad, const float* __restrict__ sq_partial,
+                        float* __restrict__ m, float* __restrict__ v, int64_t* __restrict__ step_ptr, rloa_naf_hyper hp,
+                        float* __restrict__ grad_norm_out) {
+    __shared__ float s_clip;
+    __shared__ float s_bc1, s_bc2;
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < kNormBlocks; i++) t += sq_partial[i];
+        const float norm = sqrtf(t);
+        // clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to 1
+        s_clip = fminf(hp.clip_norm / (norm + 1e-6f), 1.f) * hp.grad_scale;
+        const int64_t st = *step_ptr;          // already incremented by grad_sqsum_kernel
+        s_bc1 = 1.f - powf(hp.beta1, (float)st);
+        s_bc2 = 1.f - powf(hp.beta2, (float)st);
+        if (blockIdx.x == 0 && grad_norm_out != nullptr) *grad_norm_out = norm;
+    }
+    __syncthreads();
+    const float clip = s_clip, bc1 = s_bc1, bc2s = sqrtf(s_bc2);
+    const int n = pt.offset[14];
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        int t = 0;
+#pragma unroll
+        for (int k = 1; k < 14; k++) t += (i >= pt.offset[k]) ? 1 : 0;
+        const int j = i - pt.offset[t];
+        const float g = grad[i] * clip;
+        const float mi = fmaf(1.f - hp.beta1, g - m[i], m[i]);          // m = b1 m + (1-b1) g
+        const float vi = fmaf(1.f - hp.beta2, g * g - v[i], v[i]);      // v = b2 v + (1-b2) g^2
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2s + hp.eps;
+        const float p = pt.main[t][j] - (hp.lr / bc1) * (mi / denom);
+        pt.main[t][j] = p;
+        // soft update with the freshly updated main parameter (naf_algorithm.py:213, 225-226)
+        pt.target[t][j] = hp.tau * p + (1.f - hp.tau) * pt.target[t][j];
+    }
+}
+
+__global__ void __launch_bounds__(256) soft_update_kernel(ParamTable pt, float tau) {
+    const int n = pt.offset[14];
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        int t = 0;
+#pragma unroll
+        for (int k = 1; k < 14; k++) t += (i >= pt.offset[k]) ? 1 : 0;
+        const int j = i - pt.offset[t];
+        pt.target[t][j] = tau * pt.main[t][j] + (1.f - tau) * pt.target[t][j];
+    }
+}
+
+// [mu | V | L] head weights packed as one [NH][H] matrix for the input-gradient GEMM
+__global__ void __launch_bounds__(256) pack_heads_kernel(const float* __restrict__ w_mu, const float* __restrict__ w_v,
+                                                         const float* __restrict__ w_l, int A, int NL, int H,
+                                                         float* __restrict__ out) {
+    const int n = (A + 1 + NL) * H;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const int o = i / H, k = i - o * H;
+        out[i] = o < A ? w_mu[o * H + k] : (o == A ? w_v[k] : w_l[(o - A - 1) * H + k]);
+    }
+}
+
+}  // namespace rloa
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
 using namespace rloa;
-struct rloa_naf_ws { int dummy; };
-#define NOTIMPL(name) return fail(RLOA_ERR_INVALID, name ": not implemented yet")
-extern "C" int rloa_naf_ws_create(int32_t, int32_t, int32_t, int32_t, rloa_naf_ws**) { NOTIMPL("rloa_naf_ws_create"); }
-extern "C" void rloa_naf_ws_destroy(rloa_naf_ws*) {}
-extern "C" int rloa_naf_ws_set_trunk(rloa_naf_ws*, int32_t) { NOTIMPL("rloa_naf_ws_set_trunk"); }
-extern "C" int rloa_naf_forward(rloa_naf_ws*, const rloa_naf_params*, const float*, const float*, int32_t, int32_t, int32_t, float*, float*, float*, float*, void*) { NOTIMPL("rloa_naf_forward"); }
-extern "C" int rloa_naf_act(rloa_naf_ws*, const rloa_naf_params*, const float*, int32_t, uint64_t, uint64_t, float, float*, void*) { NOTIMPL("rloa_naf_act"); }
-extern "C" int rloa_naf_num_params(int32_t, int32_t, int32_t) { NOTIMPL("rloa_naf_num_params"); }
-extern "C" int rloa_naf_learn_grads(rloa_naf_ws*, const rloa_naf_params*, const rloa_naf_params*, const float*, const float*, const float*, const float*, const float*, int32_t, const rloa_naf_hyper*, float*, float*, void*) { NOTIMPL("rloa_naf_learn_grads"); }
-extern "C" int rloa_naf_learn_apply(rloa_naf_ws*, const rloa_naf_params*, const rloa_naf_params*, const rloa_adam_state*, const rloa_naf_hyper*, float*, float*, void*) { NOTIMPL("rloa_naf_learn_apply"); }
-extern "C" int rloa_naf_soft_update(const rloa_naf_params*, const rloa_naf_params*, float, void*) { NOTIMPL("rloa_naf_soft_update"); }
+
+struct rloa_naf_ws {
+    int S, A, H, NL, NH, max_batch;
+    int trunk_mode = 0;
+    float* block = nullptr;
+    // per net (0 = main / single, 1 = target)
+    float *z1[2], *z2[2];
+    float *scale[2][2], *shift[2][2], *mean[2][2], *rstd[2][2];   // [net][layer]
+    float *dzh, *da, *y, *loss_part, *splitk, *sq_partial, *wh_pack;
+    float *v_tmp;
+    size_t splitk_floats;
+    int n_loss_parts;
+    TrunkTC tc;                  // tcgen05 trunk state (bf16 staging buffers)
+};
+
+static int naf_nparams(int S, int A, int H) {
+    const int NL = A * (A + 1) / 2;
+    return H * S + H + H + H + H * H + H + H + H + A * H + A + H + 1 + NL * H + NL;
+}
+
+// flat gradient layout = nn.Module.parameters() order (14 tensors)
+struct FlatLayout {
+    int w1, b1, bn1w, bn1b, w2, b2, bn2w, bn2b, wmu, bmu, wv, bv, wl, bl, total;
+};
+static FlatLayout flat_layout(int S, int A, int H) {
+    const int NL = A * (A + 1) / 2;
+    FlatLayout f;
+    int o = 0;
+    f.w1 = o; o += H * S;
+    f.b1 = o; o += H;
+    f.bn1w = o; o += H;
+    f.bn1b = o; o += H;
+    f.w2 = o; o += H * H;
+    f.b2 = o; o += H;
+    f.bn2w = o; o += H;
+    f.bn2b = o; o += H;
+    f.wmu = o; o += A * H;
+    f.bmu = o; o += A;
+    f.wv = o; o += H;
+    f.bv = o; o += 1;
+    f.wl = o; o += NL * H;
+    f.bl = o; o += NL;
+    f.total = o;
+    return f;
+}
+
+extern "C" int rloa_naf_num_params(int32_t S, int32_t A, int32_t H) {
+    RLOA_REQUIRE(S >= 1 && A >= 1 && H >= 1, "rloa_naf_num_params: sizes must be positive");
+    return naf_nparams(S, A, H);
+}
+
+static int splitk_len(int B) { return 128; }
+static int splitk_count(int B) { return (B + splitk_len(B) - 1) / splitk_len(B); }
+
+extern "C" int rloa_naf_ws_create(int32_t S, int32_t A, int32_t H, int32_t max_batch, rloa_naf_ws** out) {
+    RLOA_REQUIRE(out != nullptr, "rloa_naf_ws_create: null out");
+    RLOA_REQUIRE(S >= 1 && S <= 4096, "rloa_naf_ws_create: state_size out of range");
+    RLOA_REQUIRE(A >= 1 && A <= 10, "rloa_naf_ws_create: 1 <= action_size <= 10 supported (head outputs <= 64)");
+    RLOA_REQUIRE(H >= 32 && H % 32 == 0 && H <= 1024, "rloa_naf_ws_create: hidden size must be a multiple of 32 (<= 1024)");
+    RLOA_REQUIRE(max_batch >= 1, "rloa_naf_ws_create: max_batch >= 1 required");
+    rloa_naf_ws* ws = new (std::nothrow) rloa_naf_ws();
+    RLOA_REQUIRE(ws != nullptr, "rloa_naf_ws_create: out of host memory");
+    ws->S = S; ws->A = A; ws->H = H; ws->NL = A * (A + 1) / 2; ws->NH = A + 1 + ws->NL; ws->max_batch = max_batch;
+    const size_t BH = (size_t)max_batch * H;
+    const int nsplit = splitk_count(max_batch);
+    ws->splitk_floats = (size_t)nsplit * ((size_t)H * H + (size_t)H * S + (size_t)ws->NH * H);
+    ws->n_loss_parts = 148;
+    size_t total = 4 * BH            // z1[2], z2[2]
+                   + 16 * (size_t)H  // scale/shift/mean/rstd [2][2]
+                   + (size_t)max_batch * ws->NH + BH + 2 * (size_t)max_batch + ws->n_loss_parts + ws->splitk_floats +
+                   kNormBlocks + (size_t)ws->NH * H;
+    if (cudaMalloc(&ws->block, total * sizeof(float)) != cudaSuccess) {
+        set_error("rloa_naf_ws_create: cudaMalloc of %zu bytes failed: %s", total * sizeof(float),
+                  cudaGetErrorString(cudaGetLastError()));
+        delete ws;
+        return RLOA_ERR_CUDA;
+    }
+    float* p = ws->block;
+    for (int n = 0; n < 2; n++) { ws->z1[n] = p; p += BH; ws->z2[n] = p; p += BH; }
+    for (int n = 0; n < 2; n++)
+        for (int l = 0; l < 2; l++) {
+            ws->scale[n][l] = p; p += H; ws->shift[n][l] = p; p += H; ws->mean[n][l] = p; p += H; ws->rstd[n][l] = p; p += H;
+        }
+    ws->dzh = p; p += (size_t)max_batch * ws->NH;
+    ws->da = p; p += BH;
+    ws->y = p; p += max_batch;
+    ws->v_tmp = p; p += max_batch;
+    ws->loss_part = p; p += ws->n_loss_parts;
+    ws->splitk = p; p += ws->splitk_floats;
+    ws->sq_partial = p; p += kNormBlocks;
+    ws->wh_pack = p; p += (size_t)ws->NH * H;
+    const int hb = (ws->NH * (H + 1) + ((ws->NH + 31) & ~31) + kHeadWarps * H) * (int)sizeof(float);
+    if (hb > 48 * 1024) cudaFuncSetAttribute(naf_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
+    trunk_tc_init(&ws->tc);
+    *out = ws;
+    return RLOA_OK;
+}
+
+extern "C" void rloa_naf_ws_destroy(rloa_naf_ws* ws) {
+    if (ws == nullptr) return;
+    trunk_tc_free(&ws->tc);
+    if (ws->block) cudaFree(ws->block);
+    delete ws;
+}
+
+extern "C" int rloa_naf_ws_set_trunk(rloa_naf_ws* ws, int32_t mode) {
+    RLOA_REQUIRE(ws != nullptr, "rloa_naf_ws_set_trunk: null workspace");
+    RLOA_REQUIRE(mode == 0 || mode == 1, "rloa_naf_ws_set_trunk: mode must be 0 (fp32) or 1 (tcgen05)");
+    if (mode == 1) {
+        RLOA_REQUIRE(ws->H == 256, "rloa_naf_ws_set_trunk: the tcgen05 trunk is built for hidden = 256");
+        const int rc = trunk_tc_prepare(&ws->tc, ws->max_batch, ws->H);
+        if (rc != RLOA_OK) return rc;
+    }
+    ws->trunk_mode = mode;
+    return RLOA_OK;
+}
+
+static size_t head_smem_bytes(const rloa_naf_ws* ws) {
+    return (size_t)(ws->NH * (ws->H + 1) + ((ws->NH + 31) & ~31) + kHeadWarps * ws->H) * sizeof(float);
+}
+
+static int check_params(const rloa_naf_ws* ws, const rloa_naf_params* p, const char* who) {
+    if (p == nullptr || p->state_size != ws->S || p->action_size != ws->A || p->hidden != ws->H) {
+        set_error("%s: parameter block does not match the workspace (S=%d A=%d H=%d)", who, ws->S, ws->A, ws->H);
+        return RLOA_ERR_INVALID;
+    }
+    return RLOA_OK;
+}
+
+// trunk forward for `nets` networks at once: z1 = x W1^T + b1, BN1 coefficients, z2 = relu(bn1(z1)) W2^T + b2,
+// BN2 coefficients.  x[n] are the inputs, P[n] the parameter blocks.
+static int trunk_forward(rloa_naf_ws* ws, int nets, const rloa_naf_params* const* P, const float* const* x, int B,
+                         int train, cudaStream_t st) {
+    const int H = ws->H, S = ws->S;
+    GemmBatch gb{};
+    BnBatch bb{};
+    for (int n = 0; n < nets; n++) {
+        gb.a[n] = GemmArgs{x[n], S, P[n]->w1, S, ws->z1[n], H, P[n]->b1, nullptr, nullptr, B, H, S, 0};
+        bb.a[n] = BnArgs{ws->z1[n], P[n]->bn1_w, P[n]->bn1_b, P[n]->bn1_mean, P[n]->bn1_var, P[n]->bn1_batches,
+                         ws->scale[n][0], ws->shift[n][0], ws->mean[n][0], ws->rstd[n][0]};
+    }
+    dim3 grid((H + BN - 1) / BN, (B + BM - 1) / BM, nets);
+    gemm_kernel<kNT, false><<<grid, kGemmThreads, 0, st>>>(gb);
+    RLOA_LAUNCHED();
+    bn_stats_kernel<<<dim3(H / 32, nets), 256, 0, st>>>(bb, B, H, train);
+    RLOA_LAUNCHED();
+    if (ws->trunk_mode == 1) {
+        for (int n = 0; n < nets; n++) {
+            const int rc = trunk_tc_layer2(&ws->tc, ws->z1[n], ws->scale[n][0], ws->shift[n][0], P[n]->w2, P[n]->b2,
+                                           ws->z2[n], B, H, st);
+            if (rc != RLOA_OK) return rc;
+        }
+    } else {
+        for (int n = 0; n < nets; n++)
+            gb.a[n] = GemmArgs{ws->z1[n], H, P[n]->w2, H, ws->z2[n], H, P[n]->b2, ws->scale[n][0], ws->shift[n][0], B, H, H, 0};
+        gemm_kernel<kNT, true><<<grid, kGemmThreads, 0, st>>>(gb);
+        RLOA_LAUNCHED();
+    }
+    for (int n = 0; n < nets; n++)
+        bb.a[n] = BnArgs{ws->z2[n], P[n]->bn2_w, P[n]->bn2_b, P[n]->bn2_mean, P[n]->bn2_var, P[n]->bn2_batches,
+                         ws->scale[n][1], ws->shift[n][1], ws->mean[n][1], ws->rstd[n][1]};
+    bn_stats_kernel<<<dim3(H / 32, nets), 256, 0, st>>>(bb, B, H, train);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
+static HeadArgs head_base(const rloa_naf_ws* ws, int net, const rloa_naf_params* p, int B) {
+    HeadArgs h{};
+    h.z2 = ws->z2[net]; h.scale = ws->scale[net][1]; h.shift = ws->shift[net][1];
+    h.w_mu = p->w_mu; h.b_mu = p->b_mu; h.w_v = p->w_v; h.b_v = p->b_v; h.w_l = p->w_l; h.b_l = p->b_l;
+    h.B = B; h.H = ws->H; h.A = ws->A; h.NL = ws->NL;
+    return h;
+}
+
+static int head_blocks(int B) {
+    const int need = (B + kHeadWarps - 1) / kHeadWarps;
+    return need < 148 ? need : 148;
+}
+
+extern "C" int rloa_naf_forward(rloa_naf_ws* ws, const rloa_naf_params* p, const float* states, const float* action,
+                                int32_t batch, int32_t train_mode, int32_t trunc_action, float* mu, float* pdiag,
+                                float* q, float* v, void* stream) {
+    RLOA_REQUIRE(ws != nullptr && states != nullptr, "rloa_naf_forward: null argument");
+    RLOA_REQUIRE(batch >= 1 && batch <= ws->max_batch, "rloa_naf_forward: batch exceeds the workspace");
+    RLOA_REQUIRE(!(train_mode && batch < 2), "rloa_naf_forward: train-mode BatchNorm needs more than 1 row");
+    int rc = check_params(ws, p, "rloa_naf_forward");
+    if (rc != RLOA_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    const rloa_naf_params* P[1] = {p};
+    const float* X[1] = {states};
+    rc = trunk_forward(ws, 1, P, X, batch, train_mode, st);
+    if (rc != RLOA_OK) return rc;
+    HeadArgs h = head_base(ws, 0, p, batch);
+    h.action = action; h.trunc_action = trunc_action;
+    h.mu = mu; h.pdiag = pdiag; h.q = q; h.v = v;
+    naf_head_kernel<<<head_blocks(batch), kHeadWarps * 32, head_smem_bytes(ws), st>>>(h);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
+extern "C" int rloa_naf_act(rloa_naf_ws* ws, const rloa_naf_params* p, const float* states, int32_t batch,
+                            uint64_t seed, uint64_t step, float noise_scale, float* actions, void* stream) {
+    RLOA_REQUIRE(ws != nullptr && states != nullptr && actions != nullptr, "rloa_naf_act: null argument");
+    RLOA_REQUIRE(batch >= 1 && batch <= ws->max_batch, "rloa_naf_act: batch exceeds the workspace");
+    int rc = check_params(ws, p, "rloa_naf_act");
+    if (rc != RLOA_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    const rloa_naf_params* P[1] = {p};
+    const float* X[1] = {states};
+    rc = trunk_forward(ws, 1, P, X, batch, 0, st);      // qnetwork_main.eval() (naf_algorithm.py:170)
+    if (rc != RLOA_OK) return rc;
+    HeadArgs h = head_base(ws, 0, p, batch);
+    h.act_out = actions; h.seed = seed; h.step = step; h.noise_scale = noise_scale;
+    naf_head_kernel<<<head_blocks(batch), kHeadWarps * 32, head_smem_bytes(ws), st>>>(h);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
+extern "C" int rloa_naf_learn_grads(rloa_naf_ws* ws, const rloa_naf_params* mn, const rloa_naf_params* tg,
+                                    const float* states, const float* actions, const float* rewards,
+                                    const float* next_states, const float* dones, int32_t batch,
+                                    const rloa_naf_hyper* hp, float* grad, float* loss, void* stream) {
+    RLOA_REQUIRE(ws && states && actions && rewards && next_states && hp && grad, "rloa_naf_learn_grads: null argument");
+    RLOA_REQUIRE(batch >= 2 && batch <= ws->max_batch, "rloa_naf_learn_grads: 2 <= batch <= workspace max_batch required");
+    RLOA_REQUIRE(!(hp->use_done_mask && dones == nullptr), "rloa_naf_learn_grads: use_done_mask needs dones");
+    int rc = check_params(ws, mn, "rloa_naf_learn_grads(main)");
+    if (rc != RLOA_OK) return rc;
+    rc = check_params(ws, tg, "rloa_naf_learn_grads(target)");
+    if (rc != RLOA_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    const int B = batch, H = ws->H, S = ws->S, A = ws->A, NH = ws->NH, NL = ws->NL;
+    const FlatLayout fl = flat_layout(S, A, H);
+    // forward of both nets with train-mode BatchNorm (naf_algorithm.py:194-202):
+    // net 0 = main on states, net 1 = target on next_states
+    const rloa_naf_params* P[2] = {mn, tg};
+    const float* X[2] = {states, next_states};
+    rc = trunk_forward(ws, 2, P, X, B, 1, st);
+    if (rc != RLOA_OK) return rc;
+    const size_t hsm = head_smem_bytes(ws);
+    const int hblocks = head_blocks(B);
+    {   // target head: y = r + gamma V'(s')   (naf_algorithm.py:199)
+        HeadArgs h = head_base(ws, 1, tg, B);
+        h.reward = rewards; h.done = dones; h.gamma = hp->gamma; h.use_done = hp->use_done_mask; h.y_out = ws->y;
+        naf_head_kernel<<<hblocks, kHeadWarps * 32, hsm, st>>>(h);
+        RLOA_LAUNCHED();
+    }
+    {   // main head: Q(s, a), squared TD error, gradients of the head pre-activations
+        HeadArgs h = head_base(ws, 0, mn, B);
+        h.action = actions; h.trunc_action = hp->trunc_action; h.y_in = ws->y; h.dzh = ws->dzh; h.loss_part = ws->loss_part;
+        naf_head_kernel<<<hblocks, kHeadWarps * 32, hsm, st>>>(h);
+        RLOA_LAUNCHED();
+    }
+    head_bias_grad_kernel<<<NH + 1, 256, 0, st>>>(ws->dzh, B, NH, A, grad + fl.bmu, grad + fl.bv, grad + fl.bl,
+                                                  ws->loss_part, hblocks, loss);
+    RLOA_LAUNCHED();
+    pack_heads_kernel<<<(NH * H + 255) / 256, 256, 0, st>>>(mn->w_mu, mn->w_v, mn->w_l, A, NL, H, ws->wh_pack);
+    RLOA_LAUNCHED();
+    const int klen = splitk_len(B), nsplit = splitk_count(B);
+    float* part_w2 = ws->splitk;
+    float* part_w1 = part_w2 + (size_t)nsplit * H * H;
+    float* part_wh = part_w1 + (size_t)nsplit * H * S;
+    GemmBatch gb{};
+    // dWh [NH][H] = dZh^T a2, a2 = relu(bn2(z2)) re-created in the prologue
+    gb.a[0] = GemmArgs{ws->dzh, NH, ws->z2[0], H, part_wh, H, nullptr, ws->scale[0][1], ws->shift[0][1], NH, H, B, klen};
+    gemm_kernel<kTN, true><<<dim3((H + BN - 1) / BN, (NH + BM - 1) / BM, nsplit), kGemmThreads, 0, st>>>(gb);
+    RLOA_LAUNCHED();
+    // da2 [B][H] = dZh Wh
+    gb.a[0] = GemmArgs{ws->dzh, NH, ws->wh_pack, H, ws->da, H, nullptr, nullptr, nullptr, B, H, NH, 0};
+    gemm_kernel<kNN, false><<<dim3((H + BN - 1) / BN, (B + BM - 1) / BM, 1), kGemmThreads, 0, st>>>(gb);
+    RLOA_LAUNCHED();
+    // through ReLU + BN2: da -> dz2 in place; bn2 weight/bias and hidden_layer.bias gradients
+    bn_relu_backward_kernel<<<H / 32, 256, 0, st>>>(ws->da, ws->z2[0], mn->bn2_w, ws->scale[0][1], ws->shift[0][1],
+                                                    ws->mean[0][1], ws->rstd[0][1], B, H, grad + fl.bn2w, grad + fl.bn2b,
+                                                    grad + fl.b2);
+    RLOA_LAUNCHED();
+    // dW2 [H][H] = dz2^T a1, a1 = relu(bn1(z1))
+    gb.a[0] = GemmArgs{ws->da, H, ws->z1[0], H, part_w2, H, nullptr, ws->scale[0][0], ws->shift[0][0], H, H, B, klen};
+    gemm_kernel<kTN, true><<<dim3((H + BN - 1) / BN, (H + BM - 1) / BM, nsplit), kGemmThreads, 0, st>>>(gb);
+    RLOA_LAUNCHED();
+    // da1 [B][H] = dz2 W2 -> reuse z2[1] (the target's z2 is no longer needed) as the output buffer
+    float* da1 = ws->z2[1];
+    gb.a[0] = GemmArgs{ws->da, H, mn->w2, H, da1, H, nullptr, nullptr, nullptr, B, H, H, 0};
+    gemm_kernel<kNN, false><<<dim3((H + BN - 1) / BN, (B + BM - 1) / BM, 1), kGemmThreads, 0, st>>>(gb);
+    RLOA_LAUNCHED();
+    bn_relu_backward_kernel<<<H / 32, 256, 0, st>>>(da1, ws->z1[0], mn->bn1_w, ws->scale[0][0], ws->shift[0][0],
+                                                    ws->mean[0][0], ws->rstd[0][0], B, H, grad + fl.bn1w, grad + fl.bn1b,
+                                                    grad + fl.b1);
+    RLOA_LAUNCHED();
+    // dW1 [H][S] = dz1^T x
+    gb.a[0] = GemmArgs{da1, H, states, S, part_w1, S, nullptr, nullptr, nullptr, H, S, B, klen};
+    gemm_kernel<kTN, false><<<dim3((S + BN - 1) / BN, (H + BM - 1) / BM, nsplit), kGemmThreads, 0, st>>>(gb);
+    RLOA_LAUNCHED();
+    // fixed-order reduction of the split-K partials into the flat gradient
+    ReduceArgs ra{};
+    ra.s[0] = ReduceSeg{part_w2, grad + fl.w2, H * H, nsplit, (size_t)H * H};
+    ra.s[1] = ReduceSeg{part_w1, grad + fl.w1, H * S, nsplit, (size_t)H * S};
+    ra.s[2] = ReduceSeg{part_wh, grad + fl.wmu, A * H, nsplit, (size_t)NH * H};
+    ra.s[3] = ReduceSeg{part_wh + (size_t)A * H, grad + fl.wv, H, nsplit, (size_t)NH * H};
+    ra.s[4] = ReduceSeg{part_wh + (size_t)(A + 1) * H, grad + fl.wl, NL * H, nsplit, (size_t)NH * H};
+    splitk_reduce_kernel<<<dim3(64, 5), 256, 0, st>>>(ra);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
+static void fill_param_table(const rloa_naf_params* mn, const rloa_naf_params* tg, ParamTable* pt) {
+    const int S = mn->state_size, A = mn->action_size, H = mn->hidden, NL = A * (A + 1) / 2;
+    float* m[14] = {mn->w1, mn->b1, mn->bn1_w, mn->bn1_b, mn->w2, mn->b2, mn->bn2_w, mn->bn2_b, mn->w_mu, mn->b_mu,
+                    mn->w_v, mn->b_v, mn->w_l, mn->b_l};
+    float* t[14] = {tg->w1, tg->b1, tg->bn1_w, tg->bn1_b, tg->w2, tg->b2, tg->bn2_w, tg->bn2_b, tg->w_mu, tg->b_mu,
+                    tg->w_v, tg->b_v, tg->w_l, tg->b_l};
+    const int sz[14] = {H * S, H, H, H, H * H, H, H, H, A * H, A, H, 1, NL * H, NL};
+    int o = 0;
+    for (int i = 0; i < 14; i++) {
+        pt->main[i] = m[i];
+        pt->target[i] = t[i];
+        pt->offset[i] = o;
+        o += sz[i];
+    }
+    pt->offset[14] = o;
+}
+
+extern "C" int rloa_naf_learn_apply(rloa_naf_ws* ws, const rloa_naf_params* mn, const rloa_naf_params* tg,
+                                    const rloa_adam_state* adam, const rloa_naf_hyper* hp, float* grad,
+                                    float* grad_norm, void* stream) {
+    RLOA_REQUIRE(ws && adam && hp && grad && adam->m && adam->v && adam->step, "rloa_naf_learn_apply: null argument");
+    int rc = check_params(ws, mn, "rloa_naf_learn_apply(main)");
+    if (rc != RLOA_OK) return rc;
+    rc = check_params(ws, tg, "rloa_naf_learn_apply(target)");
+    if (rc != RLOA_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    ParamTable pt;
+    fill_param_table(mn, tg, &pt);
+    const int n = pt.offset[14];
+    grad_sqsum_kernel<<<kNormBlocks, 256, 0, st>>>(grad, n, hp->grad_scale, ws->sq_partial, adam->step);
+    RLOA_LAUNCHED();
+    adam_soft_update_kernel<<<(n + 1023) / 1024, 256, 0, st>>>(pt, grad, ws->sq_partial, adam->m, adam->v, adam->step, *hp,
+                                                             grad_norm);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
+extern "C" int rloa_naf_soft_update(const rloa_naf_params* mn, const rloa_naf_params* tg, float tau, void* stream) {
+    RLOA_REQUIRE(mn && tg, "rloa_naf_soft_update: null argument");
+    RLOA_REQUIRE(mn->state_size == tg->state_size && mn->action_size == tg->action_size && mn->hidden == tg->hidden,
+                 "rloa_naf_soft_update: parameter blocks differ in shape");
+    ParamTable pt;
+    fill_param_table(mn, tg, &pt);
+    const int n = pt.offset[14];
+    soft_update_kernel<<<(n + 1023) / 1024, 256, 0, as_stream(stream)>>>(pt, tau);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}

@@ -1,5 +1,180 @@
-// placeholder: replay entry points (filled in next)
+// librloa_b200: replay ring in HBM (include/rloa_b200.h).
+//
+// Replaces utils/replay_buffer.py of the reference: `deque(maxlen)` of host namedtuples becomes a
+// struct-of-arrays ring resident in HBM (append = coalesced row copies at (cursor + rank) % capacity),
+// `random.sample(memory, k)` becomes a keyed Feistel permutation of the live window with cycle walking
+// (k distinct slots, no rejection table, no host round trip), and the np.stack / .to(device) copies
+// (replay_buffer.py:57-65) become one gather kernel.
 #include "common.cuh"
+
+namespace rloa {
+
+constexpr int kAppendRows = 1024;      // rows per block in the compaction scan
+
+__global__ void __launch_bounds__(kAppendRows) replay_count_kernel(const uint8_t* __restrict__ valid, int n,
+                                                                   int* __restrict__ block_counts) {
+    const int i = blockIdx.x * kAppendRows + threadIdx.x;
+    const int v = (i < n && valid[i] != 0) ? 1 : 0;
+    const int c = __syncthreads_count(v);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+}
+
+// one warp per transition row inside a 1024-row block; rank = exclusive scan of the valid flags
+__global__ void __launch_bounds__(kAppendRows)
+replay_append_kernel(rloa_replay rb, int n, const float* __restrict__ states, const float* __restrict__ actions,
+                     const float* __restrict__ rewards, const float* __restrict__ next_states,
+                     const uint8_t* __restrict__ dones, const uint8_t* __restrict__ valid,
+                     const int* __restrict__ block_counts) {
+    __shared__ int warp_sums[32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = blockIdx.x * kAppendRows + tid;
+    const bool v = i < n && (valid == nullptr || valid[i] != 0);
+    // block-level exclusive scan of v
+    const unsigned bal = __ballot_sync(0xffffffffu, v);
+    const int in_warp = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_sums[warp] = __popc(bal);
+    if (tid == 0) {
+        int base = 0;
+        if (valid != nullptr) for (int b = 0; b < (int)blockIdx.x; b++) base += block_counts[b];
+        else base = blockIdx.x * kAppendRows;
+        s_base = base;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int x = warp_sums[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= off) x += y;
+        }
+        warp_sums[lane] = x - warp_sums[lane];      // exclusive
+    }
+    __syncthreads();
+    const int rank = s_base + warp_sums[warp] + in_warp;
+    const long long cur = *rb.cursor;
+    const int S = rb.state_size, A = rb.action_size;
+    // every lane of the warp helps copy each valid row of the warp (coalesced S/A-float rows)
+    for (int src_lane = 0; src_lane < 32; src_lane++) {
+        const bool sv = __shfl_sync(0xffffffffu, (int)v, src_lane) != 0;
+        if (!sv) continue;
+        const int row = blockIdx.x * kAppendRows + warp * 32 + src_lane;
+        const int rrank = __shfl_sync(0xffffffffu, rank, src_lane);
+        const size_t slot = (size_t)((cur + rrank) % rb.capacity);
+        for (int k = lane; k < S; k += 32) {
+            rb.states[slot * S + k] = states[(size_t)row * S + k];
+            rb.next_states[slot * S + k] = next_states[(size_t)row * S + k];
+        }
+        for (int k = lane; k < A; k += 32) rb.actions[slot * A + k] = actions[(size_t)row * A + k];
+        if (lane == 0) {
+            rb.rewards[slot] = rewards[row];
+            rb.dones[slot] = dones != nullptr ? (float)dones[row] : 0.f;
+        }
+    }
+}
+
+__global__ void replay_cursor_bump_kernel(long long* cursor, const int* __restrict__ block_counts, int nblocks, int n_all) {
+    long long add = n_all;
+    if (block_counts != nullptr) {
+        add = 0;
+        for (int b = 0; b < nblocks; b++) add += block_counts[b];
+    }
+    *cursor += add;
+}
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return x;
+}
+// keyed bijection of [0, 2^bits): 6-round Feistel over (hi: bits - bits/2, lo: bits/2) with alternating halves
+__device__ __forceinline__ uint32_t feistel(uint32_t x, int bits, uint32_t k0, uint32_t k1) {
+    const int lb = bits >> 1, hb = bits - lb;
+    uint32_t lo = x & ((1u << lb) - 1u), hi = x >> lb;
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        if ((r & 1) == 0) hi = (hi ^ mix32(lo * 0x9E3779B9u + k0 + r)) & ((1u << hb) - 1u);
+        else lo = (lo ^ mix32(hi * 0x7FEB352Du + k1 + r)) & ((1u << lb) - 1u);
+    }
+    return (hi << lb) | lo;
+}
+
+__global__ void __launch_bounds__(256)
+replay_sample_kernel(rloa_replay rb, int batch, unsigned long long seed, unsigned long long draw,
+                     float* __restrict__ states, float* __restrict__ actions, float* __restrict__ rewards,
+                     float* __restrict__ next_states, float* __restrict__ dones, int* __restrict__ indices) {
+    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= batch) return;
+    const long long cur = *rb.cursor;
+    const uint32_t live = (uint32_t)(cur < rb.capacity ? cur : rb.capacity);
+    if (live == 0) return;
+    int bits = 1;
+    while ((1u << bits) < live) bits++;
+    if (bits < 2) bits = 2;
+    const uint32_t k0 = mix32((uint32_t)seed ^ mix32((uint32_t)draw)), k1 = mix32((uint32_t)(seed >> 32) + 0x68E31DA4u ^ (uint32_t)(draw >> 32) ^ k0);
+    uint32_t x = (uint32_t)warp % live;
+    do {
+        x = feistel(x, bits, k0, k1);
+    } while (x >= live);                          // cycle walking keeps the map a bijection of [0, live)
+    // x counts from the oldest live transition, like indexing the deque
+    const size_t slot = (size_t)(((cur < rb.capacity ? 0 : cur) + x) % rb.capacity);
+    const int S = rb.state_size, A = rb.action_size;
+    for (int k = lane; k < S; k += 32) {
+        states[(size_t)warp * S + k] = rb.states[slot * S + k];
+        next_states[(size_t)warp * S + k] = rb.next_states[slot * S + k];
+    }
+    for (int k = lane; k < A; k += 32) actions[(size_t)warp * A + k] = rb.actions[slot * A + k];
+    if (lane == 0) {
+        rewards[warp] = rb.rewards[slot];
+        if (dones != nullptr) dones[warp] = rb.dones[slot];
+        if (indices != nullptr) indices[warp] = (int)slot;
+    }
+}
+
+}  // namespace rloa
+
 using namespace rloa;
-extern "C" int rloa_replay_append(const rloa_replay*, int32_t, const float*, const float*, const float*, const float*, const uint8_t*, const uint8_t*, void*) { return fail(RLOA_ERR_INVALID, "rloa_replay_append: not implemented yet"); }
-extern "C" int rloa_replay_sample(const rloa_replay*, int32_t, uint64_t, uint64_t, float*, float*, float*, float*, float*, int32_t*, void*) { return fail(RLOA_ERR_INVALID, "rloa_replay_sample: not implemented yet"); }
+
+static int check_rb(const rloa_replay* rb, const char* who) {
+    if (rb == nullptr || rb->capacity < 1 || rb->state_size < 1 || rb->action_size < 1 || !rb->states || !rb->actions ||
+        !rb->rewards || !rb->next_states || !rb->dones || !rb->cursor) {
+        set_error("%s: incomplete replay descriptor", who);
+        return RLOA_ERR_INVALID;
+    }
+    return RLOA_OK;
+}
+
+extern "C" int rloa_replay_append(const rloa_replay* rb, int32_t n, const float* states, const float* actions,
+                                  const float* rewards, const float* next_states, const uint8_t* dones,
+                                  const uint8_t* valid, void* stream) {
+    int rc = check_rb(rb, "rloa_replay_append");
+    if (rc != RLOA_OK) return rc;
+    RLOA_REQUIRE(n >= 1 && states && actions && rewards && next_states, "rloa_replay_append: null argument");
+    RLOA_REQUIRE(n <= rb->capacity, "rloa_replay_append: more transitions than the ring holds in one call");
+    RLOA_REQUIRE(valid == nullptr || rb->scratch != nullptr, "rloa_replay_append: a valid mask needs rb->scratch");
+    cudaStream_t st = as_stream(stream);
+    const int nblocks = (n + kAppendRows - 1) / kAppendRows;
+    if (valid != nullptr) {
+        replay_count_kernel<<<nblocks, kAppendRows, 0, st>>>(valid, n, rb->scratch);
+        RLOA_LAUNCHED();
+    }
+    replay_append_kernel<<<nblocks, kAppendRows, 0, st>>>(*rb, n, states, actions, rewards, next_states, dones, valid,
+                                                         rb->scratch);
+    RLOA_LAUNCHED();
+    replay_cursor_bump_kernel<<<1, 1, 0, st>>>(reinterpret_cast<long long*>(rb->cursor),
+                                               valid != nullptr ? rb->scratch : nullptr, nblocks, n);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
+extern "C" int rloa_replay_sample(const rloa_replay* rb, int32_t batch, uint64_t seed, uint64_t draw, float* states,
+                                  float* actions, float* rewards, float* next_states, float* dones, int32_t* indices,
+                                  void* stream) {
+    int rc = check_rb(rb, "rloa_replay_sample");
+    if (rc != RLOA_OK) return rc;
+    RLOA_REQUIRE(batch >= 1 && states && actions && rewards && next_states, "rloa_replay_sample: null argument");
+    const int blocks = (batch * 32 + 255) / 256;
+    replay_sample_kernel<<<blocks, 256, 0, as_stream(stream)>>>(*rb, batch, seed, draw, states, actions, rewards,
+                                                               next_states, dones, indices);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}

@@ -18,6 +18,7 @@ struct SimArrays {
     float *kp, *tpos, *tvel, *maximp;       // [N][nl] motor table
     float *target, *obstacle;               // [N][3]
     int* iters;                             // [N]
+    int* reset_left;                        // [N] pending reset sub-steps (lock-step asynchronous reset)
 };
 
 struct StepCfgDev {
@@ -50,7 +51,7 @@ __device__ __forceinline__ V3 load3(const float* p) { return v3(p[0], p[1], p[2]
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 sim_step_kernel(const ModelDev* __restrict__ M, SimArrays S, StepCfgDev cfg, const float* __restrict__ actions,
                 const uint8_t* __restrict__ active, float* __restrict__ obs, float* __restrict__ reward,
-                uint8_t* __restrict__ done) {
+                uint8_t* __restrict__ done, uint8_t* __restrict__ valid_out) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * kWarpsPerBlock + warp;
@@ -62,6 +63,34 @@ sim_step_kernel(const ModelDev* __restrict__ M, SimArrays S, StepCfgDev cfg, con
     const size_t base = (size_t)env * nl + (valid ? lane : 0);
     float q = 0.f, qd = 0.f;
     Motor mot{0.f, 0.f, 0.f, 0.f};
+    // an env with pending reset sub-steps spends this launch on one of them (motors as begin_reset left
+    // them) instead of an action step; it emits no transition (valid = 0)
+    const int pending = S.reset_left[env];
+    if (pending > 0) {
+        if (valid) {
+            q = S.q[base];
+            qd = S.qd[base];
+            mot = Motor{S.kp[base], S.tpos[base], S.tvel[base], S.maximp[base]};
+        }
+        const int it = warp_substep(M, sm, lane, q, qd, mot);
+        if (valid) {
+            S.q[base] = q;
+            S.qd[base] = qd;
+        }
+        M3 R;
+        V3 p;
+        lane_fk(M, valid ? lane : 0, valid, q, R, p);
+        const V3 tg = load3(S.target + 3 * (size_t)env), ob = load3(S.obstacle + 3 * (size_t)env);
+        write_obs(M, lane, q, qd, sh3(p, M->ee_link), tg, ob, obs + (size_t)env * (9 + 2 * M->n_obs));
+        if (lane == 0) {
+            S.reset_left[env] = pending - 1;
+            reward[env] = 0.f;
+            done[env] = 0;
+            S.iters[env] = it;
+            if (valid_out != nullptr) valid_out[env] = 0;
+        }
+        return;
+    }
     if (valid) {
         q = S.q[base];
         qd = S.qd[base];
@@ -98,7 +127,23 @@ sim_step_kernel(const ModelDev* __restrict__ M, SimArrays S, StepCfgDev cfg, con
         reward[env] = goal ? 250.f : (o.hit ? -1000.f : -(o.ee_target - cfg.target_thr));
         done[env] = (o.hit || goal) ? 1 : 0;         // is_terminal_state (environment.py:326-333)
         S.iters[env] = it;
+        if (valid_out != nullptr) valid_out[env] = 1;
     }
+}
+
+// lock-step asynchronous Environment.reset: arm the POSITION_CONTROL motors of the masked envs and let
+// the next n_substeps step launches run their reset sub-steps (environment.py:295-301)
+__global__ void sim_begin_reset_kernel(SimArrays S, const uint8_t* __restrict__ mask,
+                                       const float* __restrict__ init_targets, int n_init, int nsub, float pos_maximp) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n = (size_t)S.n_envs * S.nl;
+    if (i >= n) return;
+    const int env = (int)(i / S.nl), j = (int)(i - (size_t)env * S.nl);
+    if (mask != nullptr && mask[env] == 0) return;
+    if (j < n_init) {
+        S.kp[i] = 0.1f; S.tpos[i] = init_targets[(size_t)env * n_init + j]; S.tvel[i] = 0.f; S.maximp[i] = pos_maximp;
+    }
+    if (j == 0) S.reset_left[env] = nsub;
 }
 
 // Environment.reset (reference environment.py:264-309) for the masked envs
@@ -133,7 +178,10 @@ sim_reset_kernel(const ModelDev* __restrict__ M, SimArrays S, const uint8_t* __r
         S.q[base] = q;
         S.qd[base] = qd;
     }
-    if (lane == 0) S.iters[env] = it;
+    if (lane == 0) {
+        S.iters[env] = it;
+        S.reset_left[env] = 0;
+    }
     if (obs != nullptr) {
         M3 R;
         V3 p;
@@ -172,7 +220,7 @@ __global__ void sim_clear_kernel(SimArrays S) {
         S.q[i] = 0.f; S.qd[i] = 0.f;
         S.kp[i] = 0.f; S.tpos[i] = 0.f; S.tvel[i] = 0.f; S.maximp[i] = 1.f;   // load-time default motor
     }
-    if (i < (size_t)S.n_envs) S.iters[i] = 0;
+    if (i < (size_t)S.n_envs) { S.iters[i] = 0; S.reset_left[i] = 0; }
 }
 
 // Episode bookkeeping of the vectorised rollout (naf_algorithm.py:263-277, rl_framework.py:343-354)
@@ -181,10 +229,13 @@ __global__ void episode_update_kernel(int n, int frames, const float* __restrict
                                       float* __restrict__ score, int* __restrict__ frame, uint8_t* __restrict__ reset_mask,
                                       float* __restrict__ log_score, int* __restrict__ log_frame,
                                       float* __restrict__ log_last, int* __restrict__ log_env, int log_cap,
-                                      int* __restrict__ log_count) {
+                                      int* __restrict__ log_count, unsigned long long* __restrict__ transitions) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = e < n && (active == nullptr || active[e] != 0);
+    const int nlive = __syncthreads_count(live);
+    if (threadIdx.x == 0 && transitions != nullptr && nlive > 0) atomicAdd(transitions, (unsigned long long)nlive);
     if (e >= n) return;
-    if (active != nullptr && active[e] == 0) {
+    if (!live) {
         reset_mask[e] = 0;
         return;
     }
@@ -361,7 +412,7 @@ extern "C" int rloa_sim_create(const rloa_model* m, int32_t n_envs, rloa_sim** o
     s->a.nl = nl;
     float* block = nullptr;
     // one allocation: q qd kp tpos tvel maximp | target obstacle | iters
-    const size_t floats = 6 * n + 6 * (size_t)n_envs + (size_t)n_envs;
+    const size_t floats = 6 * n + 6 * (size_t)n_envs + 2 * (size_t)n_envs;
     if (cudaMalloc(&block, floats * sizeof(float)) != cudaSuccess) {
         set_error("rloa_sim_create: cudaMalloc of %zu bytes failed: %s", floats * sizeof(float), cudaGetErrorString(cudaGetLastError()));
         delete s;
@@ -371,6 +422,7 @@ extern "C" int rloa_sim_create(const rloa_model* m, int32_t n_envs, rloa_sim** o
     s->a.tvel = block + 4 * n; s->a.maximp = block + 5 * n;
     s->a.target = block + 6 * n; s->a.obstacle = s->a.target + 3 * (size_t)n_envs;
     s->a.iters = reinterpret_cast<int*>(s->a.obstacle + 3 * (size_t)n_envs);
+    s->a.reset_left = s->a.iters + n_envs;
     s->smem_bytes = (size_t)kWarpsPerBlock * sim_smem_floats_per_warp(nl) * sizeof(float);
     if (s->smem_bytes > 48 * 1024) {
         cudaFuncSetAttribute(sim_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
@@ -468,14 +520,27 @@ static int make_step_cfg(const rloa_sim* s, const rloa_step_config* c, StepCfgDe
 }
 
 extern "C" int rloa_sim_step(rloa_sim* s, const rloa_step_config* cfg, const float* actions, const uint8_t* active,
-                             float* obs, float* reward, uint8_t* done, void* stream) {
+                             float* obs, float* reward, uint8_t* done, uint8_t* valid, void* stream) {
     RLOA_REQUIRE(s && cfg && actions && obs && reward && done, "rloa_sim_step: null argument");
     StepCfgDev c;
     const int rc = make_step_cfg(s, cfg, &c);
     if (rc != RLOA_OK) return rc;
     const unsigned blocks = (unsigned)((s->a.n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
     sim_step_kernel<<<blocks, kWarpsPerBlock * 32, s->smem_bytes, as_stream(stream)>>>(s->model->dev, s->a, c, actions,
-                                                                                     active, obs, reward, done);
+                                                                                     active, obs, reward, done, valid);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
+extern "C" int rloa_sim_begin_reset(rloa_sim* s, const uint8_t* mask, const float* init_targets, int32_t n_init,
+                                    int32_t n_substeps, void* stream) {
+    RLOA_REQUIRE(s != nullptr, "rloa_sim_begin_reset: null sim");
+    RLOA_REQUIRE(n_init >= 0 && n_init <= s->a.nl, "rloa_sim_begin_reset: n_init out of range");
+    RLOA_REQUIRE(n_init == 0 || init_targets != nullptr, "rloa_sim_begin_reset: init_targets missing");
+    RLOA_REQUIRE(n_substeps >= 0, "rloa_sim_begin_reset: n_substeps < 0");
+    const size_t n = (size_t)s->a.n_envs * s->a.nl;
+    sim_begin_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+        s->a, mask, init_targets, n_init, n_substeps, 100000.f * s->model->host.dt);
     RLOA_LAUNCHED();
     return RLOA_OK;
 }
@@ -512,13 +577,13 @@ extern "C" int rloa_sim_last_iterations(const rloa_sim* s, int32_t* iters, void*
 extern "C" int rloa_episode_update(int32_t n_envs, int32_t frames, const float* reward, const uint8_t* done,
                                    const uint8_t* active, float* score, int32_t* frame, uint8_t* reset_mask,
                                    float* log_score, int32_t* log_frame, float* log_last_reward, int32_t* log_env,
-                                   int32_t log_capacity, int32_t* log_count, void* stream) {
+                                   int32_t log_capacity, int32_t* log_count, int64_t* transitions, void* stream) {
     RLOA_REQUIRE(reward && done && score && frame && reset_mask && log_score && log_frame && log_last_reward &&
                      log_env && log_count, "rloa_episode_update: null argument");
     RLOA_REQUIRE(n_envs >= 1, "rloa_episode_update: n_envs >= 1 required");
     episode_update_kernel<<<(unsigned)((n_envs + 255) / 256), 256, 0, as_stream(stream)>>>(
         n_envs, frames, reward, done, active, score, frame, reset_mask, log_score, log_frame, log_last_reward, log_env,
-        log_capacity, log_count);
+        log_capacity, log_count, reinterpret_cast<unsigned long long*>(transitions));
     RLOA_LAUNCHED();
     return RLOA_OK;
 }

@@ -108,7 +108,8 @@ class BatchedSimulator:
     def clear(self) -> None:
         N.check(self.lib.rloa_sim_clear(self._h_sim, self._stream()), 'rloa_sim_clear')
 
-    def step(self, actions: torch.Tensor, active: Optional[torch.Tensor] = None, out=None):
+    def step(self, actions: torch.Tensor, active: Optional[torch.Tensor] = None, out=None,
+             valid: Optional[torch.Tensor] = None):
         """Environment.step for every env.  actions: fp32 [n_envs, n_act] on the device."""
         if actions.dtype != torch.float32 or not actions.is_contiguous() or actions.device != self.device:
             actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
@@ -116,8 +117,16 @@ class BatchedSimulator:
             raise ValueError(f'actions must have shape {(self.n_envs, self.n_act)}')
         obs, reward, done = out if out is not None else (self.obs, self.reward, self.done)
         N.check(self.lib.rloa_sim_step(self._h_sim, C.byref(self.cfg), actions.data_ptr(), N.ptr(active), obs.data_ptr(),
-                                       reward.data_ptr(), done.data_ptr(), self._stream()), 'rloa_sim_step')
+                                       reward.data_ptr(), done.data_ptr(), N.ptr(valid), self._stream()),
+                'rloa_sim_step')
         return obs, reward, done
+
+    def begin_reset(self, init_targets: torch.Tensor, mask: Optional[torch.Tensor] = None,
+                    substeps: int = RESET_SUBSTEPS) -> None:
+        """Schedule a lock-step asynchronous reset of the masked envs (one sub-step per step() call)."""
+        n_init = init_targets.shape[1]
+        N.check(self.lib.rloa_sim_begin_reset(self._h_sim, N.ptr(mask), init_targets.data_ptr() if n_init else None,
+                                              n_init, int(substeps), self._stream()), 'rloa_sim_begin_reset')
 
     def reset(self, init_targets, mask: Optional[torch.Tensor] = None, substeps: int = RESET_SUBSTEPS,
               obs: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -1,0 +1,362 @@
+"""
+NAFAgent — drop-in for /root/reference/robotic_manipulator_rloa/naf_components/naf_algorithm.py with the
+whole loop device-resident: batched policy inference (rloa_naf_act), the batched simulator step, the
+HBM replay ring, and NAFAgent.learn as two native calls (rloa_naf_learn_grads -> optional NCCL gradient
+all-reduce -> rloa_naf_learn_apply = clip-norm + Adam + soft target update).
+
+Constructor keywords, attributes, ``run()`` return value, checkpoint files and log lines follow the
+reference (naf_algorithm.py:27-89, 228-292).  Reference quirks are reproduced by default (SURVEY.md
+Appendix B): replayed actions are truncated like ``.long()``, the TD target ignores ``done``, both nets
+use train-mode BatchNorm in ``learn``, ``act`` always adds N(0, P^-1) noise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import random
+import time
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+from numpy.typing import NDArray
+
+from .. import _native as N
+from ..utils.exceptions import MissingWeightsFile
+from ..utils.logger import get_global_logger
+from ..utils.replay_buffer import ReplayBuffer
+from .naf_neural_network import NAF, NafWorkspace
+
+logger = get_global_logger()
+
+
+class FusedAdam:
+    """State of the fused clip + Adam + soft-update kernel (flat moments in nn.Module.parameters() order).
+    Stands where the reference keeps ``optim.Adam`` (naf_algorithm.py:83); ``step()`` is not a separate call —
+    the update happens inside ``NAFAgent.learn``."""
+
+    def __init__(self, n_params: int, lr: float, device: torch.device):
+        self.defaults = dict(lr=lr, betas=(0.9, 0.999), eps=1e-8)
+        self.param_groups = [dict(self.defaults)]
+        self.device = device
+        self.n_params = n_params
+        self.exp_avg = None
+        self.exp_avg_sq = None
+        self.step_count = None
+        if torch.device(device).type == 'cuda':
+            self.exp_avg = torch.zeros(n_params, dtype=torch.float32, device=device)
+            self.exp_avg_sq = torch.zeros(n_params, dtype=torch.float32, device=device)
+            self.step_count = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def zero_grad(self) -> None:        # gradients are overwritten, never accumulated
+        pass
+
+    def state_dict(self) -> dict:
+        return {'state': {'exp_avg': self.exp_avg, 'exp_avg_sq': self.exp_avg_sq, 'step': self.step_count},
+                'param_groups': self.param_groups}
+
+    def native(self) -> N.AdamState:
+        a = N.AdamState()
+        a.m, a.v, a.step = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.step_count.data_ptr()
+        return a
+
+
+class NAFAgent:
+    MODEL_PATH = 'model.p'
+
+    def __init__(self, environment, state_size: int, action_size: int, layer_size: int, batch_size: int,
+                 buffer_size: int, learning_rate: float, tau: float, gamma: float, update_freq: int, num_updates: int,
+                 checkpoint_frequency: int, device: torch.device, seed: int) -> None:
+        os.makedirs('checkpoints/', exist_ok=True)
+        self.environment = environment
+        self.state_size = state_size
+        self.action_size = action_size
+        self.layer_size = layer_size
+        self.buffer_size = buffer_size
+        self.learning_rate = learning_rate
+        random.seed(seed)
+        self.device = torch.device(device)
+        self.tau = tau
+        self.gamma = gamma
+        self.update_freq = update_freq
+        self.num_updates = num_updates
+        self.batch_size = batch_size
+        self.checkpoint_frequency = checkpoint_frequency
+        self.seed = seed
+        # opt-in corrections of reference quirks (defaults reproduce the reference)
+        self.truncate_replayed_actions = True       # replay_buffer.py:60 `.long()`
+        self.use_done_mask = False                  # naf_algorithm.py:199 ignores `done`
+        self.noise_scale = 1.0                      # naf_neural_network.py:119-121 noise at every act()
+
+        self.qnetwork_main = NAF(state_size, action_size, layer_size, seed, self.device).to(self.device)
+        self.qnetwork_target = NAF(state_size, action_size, layer_size, seed, self.device).to(self.device)
+        self.n_params = sum(p.numel() for p in self.qnetwork_main.parameters())
+        self.optimizer = FusedAdam(self.n_params, learning_rate, self.device)
+        n_envs = getattr(environment, 'n_envs', 1) if environment is not None else 1
+        self.memory = ReplayBuffer(buffer_size, batch_size, self.device, seed,
+                                   state_size if self.device.type == 'cuda' else None,
+                                   action_size if self.device.type == 'cuda' else None, max_append=n_envs)
+        self.update_t_step = 0
+        self._act_calls = 0
+        self._ws: Optional[NafWorkspace] = None
+        self._bufs = None
+        self.last_loss = None
+        self.last_grad_norm = None
+        self.world_size = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world_size = torch.distributed.get_world_size()
+
+    # ------------------------------------------------------------------------------------------
+    # native plumbing
+    def _require_cuda(self) -> None:
+        if self.device.type != 'cuda':
+            raise N.NativeLibraryError('NAFAgent runs on librloa_b200.so (sm_100a): a CUDA device is required, '
+                                       'there is no CPU fallback')
+
+    def _workspace(self, rows: int) -> NafWorkspace:
+        if self._ws is None or self._ws.max_batch < rows:
+            if self._ws is not None:
+                self._ws.close()
+            self._ws = NafWorkspace(self.state_size, self.action_size, self.layer_size, max(rows, self.batch_size, 256),
+                                    self.device)
+            if self.qnetwork_main.trunk_mode:
+                self._ws.set_trunk(self.qnetwork_main.trunk_mode)
+        return self._ws
+
+    def set_trunk_mode(self, mode: int) -> None:
+        """0 = fp32 CUDA-core trunk (reference-exact), 1 = tcgen05 tensor-core trunk (bf16 operands)."""
+        self.qnetwork_main.trunk_mode = int(mode)
+        self.qnetwork_target.trunk_mode = int(mode)
+        if self._ws is not None:
+            self._ws.set_trunk(int(mode))
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _hyper(self) -> N.NafHyper:
+        h = N.NafHyper()
+        h.gamma, h.tau, h.lr = float(self.gamma), float(self.tau), float(self.learning_rate)
+        h.beta1, h.beta2, h.eps, h.clip_norm = 0.9, 0.999, 1e-8, 1.0
+        h.trunc_action = 1 if self.truncate_replayed_actions else 0
+        h.use_done_mask = 1 if self.use_done_mask else 0
+        h.grad_scale = 1.0 / float(self.world_size)
+        return h
+
+    def _learn_buffers(self):
+        if self._bufs is None:
+            f32 = dict(dtype=torch.float32, device=self.device)
+            B = self.batch_size
+            self._bufs = dict(s=torch.empty(B, self.state_size, **f32), a=torch.empty(B, self.action_size, **f32),
+                              r=torch.empty(B, **f32), s2=torch.empty(B, self.state_size, **f32),
+                              d=torch.empty(B, **f32), grad=torch.zeros(self.n_params, **f32),
+                              loss=torch.zeros(1, **f32), gnorm=torch.zeros(1, **f32))
+        return self._bufs
+
+    # ------------------------------------------------------------------------------------------
+    # checkpoints (naf_algorithm.py:91-127)
+    def initialize_pretrained_agent_from_episode(self, episode: int) -> None:
+        if not os.path.isfile(f'checkpoints/{episode}/weights.p'):
+            raise MissingWeightsFile
+        logger.debug(f'Loading naf_components weights from trained naf_components on episode {episode}...')
+        self.qnetwork_main.load_state_dict(torch.load(f'checkpoints/{episode}/weights.p', map_location=self.device))
+        self.qnetwork_target.load_state_dict(torch.load(f'checkpoints/{episode}/weights.p', map_location=self.device))
+        logger.info(f'Loaded weights from trained naf_components on episode {episode}')
+
+    def initialize_pretrained_agent_from_weights_file(self, weights_path: str) -> None:
+        if not os.path.isfile(weights_path):
+            raise MissingWeightsFile
+        logger.debug('Loading naf_components weights from trained naf_components...')
+        self.qnetwork_main.load_state_dict(torch.load(weights_path, map_location=self.device))
+        self.qnetwork_target.load_state_dict(torch.load(weights_path, map_location=self.device))
+        logger.info('Loaded pre-trained weights for the NN')
+
+    def _cpu_state_dict(self):
+        return {k: v.detach().cpu() for k, v in self.qnetwork_main.state_dict().items()}
+
+    # ------------------------------------------------------------------------------------------
+    def act_batch(self, states: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Eval-mode policy for a batch of device states -> noisy clamped actions [n, A] (stays on the device)."""
+        self._require_cuda()
+        n = states.shape[0]
+        ws = self._workspace(n)
+        if out is None:
+            out = torch.empty(n, self.action_size, dtype=torch.float32, device=self.device)
+        p = self.qnetwork_main.native_params()
+        N.check(ws.lib.rloa_naf_act(ws.handle, C.byref(p), states.data_ptr(), n, self.seed, self._act_calls,
+                                    float(self.noise_scale), out.data_ptr(), self._stream()), 'rloa_naf_act')
+        self._act_calls += 1
+        return out
+
+    def act(self, state):
+        """Reference contract (naf_algorithm.py:158-178): ndarray[S] -> ndarray[A]; device tensors [n, S] map to
+        device tensors [n, A]."""
+        if isinstance(state, torch.Tensor) and state.dim() == 2:
+            return self.act_batch(state.to(device=self.device, dtype=torch.float32).contiguous())
+        s = torch.from_numpy(np.asarray(state, dtype=np.float32)).to(self.device).reshape(1, -1)
+        return self.act_batch(s).cpu().squeeze().numpy()
+
+    def step(self, state: NDArray, action: NDArray, reward: float, next_state: NDArray, done: int) -> None:
+        """Store one transition and learn when due (naf_algorithm.py:129-156)."""
+        self.memory.add(state, action, reward, next_state, done)
+        self._maybe_learn()
+
+    def _maybe_learn(self) -> None:
+        self.update_t_step = (self.update_t_step + 1) % self.update_freq
+        if self.update_t_step == 0 and len(self.memory) > self.batch_size:
+            for _ in range(self.num_updates):
+                self.learn_from_memory()
+
+    def learn_from_memory(self) -> None:
+        """sample + learn without leaving the device (replay_buffer.py:47-67 + naf_algorithm.py:180-213)."""
+        b = self._learn_buffers()
+        self.memory.sample_into(b['s'], b['a'], b['r'], b['s2'], b['d'])
+        self._learn_device(b['s'], b['a'], b['r'], b['s2'], b['d'])
+
+    def learn(self, experiences: Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]) -> None:
+        """Reference signature: a 5-tuple of tensors as ReplayBuffer.sample returns them."""
+        self._require_cuda()
+        states, actions, rewards, next_states, dones = experiences
+        f = lambda t: t.to(device=self.device, dtype=torch.float32).contiguous()
+        self._learn_device(f(states), f(actions), f(rewards).reshape(-1), f(next_states), f(dones).reshape(-1))
+
+    def _learn_device(self, s, a, r, s2, d) -> None:
+        self._require_cuda()
+        B = s.shape[0]
+        ws = self._workspace(B)
+        b = self._learn_buffers()
+        hp = self._hyper()
+        pm, pt = self.qnetwork_main.native_params(), self.qnetwork_target.native_params()
+        st = self._stream()
+        N.check(ws.lib.rloa_naf_learn_grads(ws.handle, C.byref(pm), C.byref(pt), s.data_ptr(), a.data_ptr(),
+                                            r.data_ptr(), s2.data_ptr(), d.data_ptr(), B, C.byref(hp),
+                                            b['grad'].data_ptr(), b['loss'].data_ptr(), st), 'rloa_naf_learn_grads')
+        if self.world_size > 1:          # the one exchange step of the data-parallel path (NCCL over NVLink)
+            torch.distributed.all_reduce(b['grad'])
+        adam = self.optimizer.native()
+        N.check(ws.lib.rloa_naf_learn_apply(ws.handle, C.byref(pm), C.byref(pt), C.byref(adam), C.byref(hp),
+                                            b['grad'].data_ptr(), b['gnorm'].data_ptr(), st), 'rloa_naf_learn_apply')
+        self.last_loss, self.last_grad_norm = b['loss'], b['gnorm']
+
+    def soft_update(self, main_nn: NAF, target_nn: NAF) -> None:
+        """theta_target = tau theta_main + (1 - tau) theta_target over parameters (naf_algorithm.py:217-226)."""
+        self._require_cuda()
+        pm, pt = main_nn.native_params(), target_nn.native_params()
+        N.check(N.lib().rloa_naf_soft_update(C.byref(pm), C.byref(pt), float(self.tau), self._stream()),
+                'rloa_naf_soft_update')
+
+    # ------------------------------------------------------------------------------------------
+    def make_loop(self, frames: int, log_capacity: int, learn: bool = True) -> 'VectorLoop':
+        return VectorLoop(self, frames, log_capacity, learn)
+
+    def run(self, frames: int = 1000, episodes: int = 1000, verbose: bool = True) -> Dict[int, Tuple[float, int]]:
+        """Training loop (naf_algorithm.py:228-292) over ``environment.n_envs`` arms in lock step.
+        ``episodes`` counts completed episodes over all envs, numbered in completion order; with one env the
+        sequence of resets, steps, updates, log lines and checkpoints is the reference's."""
+        self._require_cuda()
+        env = self.environment
+        n = env.n_envs
+        logger.info('Training started')
+        scores = {episode: (0, 0) for episode in range(1, episodes + 1)}
+        loop = self.make_loop(frames, episodes + 2 * n + 1)
+        completed, start = 0, time.time()
+        if n == 1:
+            logger.info(f'Running Episode {completed + 1}')
+        loop.reset_all(verbose)
+        sync_every = 1 if n == 1 else 4
+        it = 0
+        while completed < episodes:
+            if n == 1 and verbose:
+                logger.info(f'Running frame {int(loop.frame.item()) + 1} in episode {completed + 1}')
+                logger.info(f'Current State: {loop.state[0].cpu().numpy()}')
+            loop.step(auto_reset=(n > 1))
+            it += 1
+            if n == 1 and verbose:
+                logger.info(f'Action chosen for the given state is: {loop.actions[0].cpu().numpy()}')
+                logger.info(f'Reward: {float(loop.reward.item())}\n')
+            if it % sync_every:
+                continue
+            n_done = int(loop.log_count.item())          # the one host read of the loop
+            if n_done <= completed:
+                continue
+            hi = min(n_done, episodes)
+            ls, lf = loop.log_score[completed:hi].cpu().numpy(), loop.log_frame[completed:hi].cpu().numpy()
+            for k in range(hi - completed):
+                ep = completed + k + 1
+                scores[ep] = (float(ls[k]), int(lf[k]))
+                logger.info(f'Reward:                             {float(ls[k])}')
+                logger.info(f'Number of frames:                   {int(lf[k])}')
+                logger.info(f'Mean of rewards on this episode:    {float(ls[k]) / frames}')
+                logger.info(f'Time taken for this episode:        {round(time.time() - start, 3)} secs\n')
+                if ep % self.checkpoint_frequency == 0:
+                    os.makedirs(f'checkpoints/{ep}/', exist_ok=True)
+                    torch.save(self._cpu_state_dict(), f'checkpoints/{ep}/weights.p')
+                    with open(f'checkpoints/{ep}/scores.txt', 'w') as f:
+                        f.write(json.dumps(scores))
+            completed = hi
+            start = time.time()
+            if completed < episodes and n == 1:
+                logger.info(f'Running Episode {completed + 1}')
+                loop.reset_all(verbose)
+        torch.save(self._cpu_state_dict(), self.MODEL_PATH)
+        logger.info(f'Model has been successfully saved in {self.MODEL_PATH}')
+        return scores
+
+
+class VectorLoop:
+    """Device-resident buffers and one sync-free iteration of the vectorised act -> step -> store -> learn loop
+    (the body of naf_algorithm.py:249-270 for every env at once).  Nothing in ``step`` reads back to the host."""
+
+    def __init__(self, agent: NAFAgent, frames: int, log_capacity: int, learn: bool = True):
+        self.agent, self.env = agent, agent.environment
+        self.frames, self.learn = int(frames), learn
+        n, dev = self.env.n_envs, agent.device
+        self.n = n
+        f32 = dict(dtype=torch.float32, device=dev)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.state = torch.zeros(n, agent.state_size, **f32)
+        self.next_state = torch.zeros(n, agent.state_size, **f32)
+        self.reward = torch.zeros(n, **f32)
+        self.done = torch.zeros(n, **u8)
+        self.valid = torch.ones(n, **u8)
+        self.actions = torch.zeros(n, agent.action_size, **f32)
+        self.score = torch.zeros(n, **f32)
+        self.frame = torch.zeros(n, **i32)
+        self.reset_mask = torch.zeros(n, **u8)
+        self.cap = int(log_capacity)
+        self.log_score = torch.zeros(self.cap, **f32)
+        self.log_frame = torch.zeros(self.cap, **i32)
+        self.log_last = torch.zeros(self.cap, **f32)
+        self.log_env = torch.zeros(self.cap, **i32)
+        self.log_count = torch.zeros(1, **i32)
+        self.transitions = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.lib = N.lib()
+
+    def reset_all(self, verbose: bool = False) -> None:
+        """Synchronous Environment.reset of every env (50 sub-steps) -> self.state."""
+        if self.n == 1:
+            s = np.asarray(self.env.reset(verbose), dtype=np.float32)
+            self.state.copy_(torch.from_numpy(s).to(self.state.device).reshape(1, -1))
+        else:
+            self.env.reset_batch(obs=self.state)
+        self.score.zero_()
+        self.frame.zero_()
+
+    def step(self, auto_reset: bool = True) -> None:
+        a, env = self.agent, self.env
+        a.act_batch(self.state, out=self.actions)
+        env.sim.step(self.actions, out=(self.next_state, self.reward, self.done), valid=self.valid)
+        a.memory.add_batch(self.state, self.actions, self.reward, self.next_state, self.done,
+                           valid=self.valid if auto_reset else None)
+        if self.learn:
+            a._maybe_learn()
+        N.check(self.lib.rloa_episode_update(self.n, self.frames, self.reward.data_ptr(), self.done.data_ptr(),
+                                             self.valid.data_ptr(), self.score.data_ptr(), self.frame.data_ptr(),
+                                             self.reset_mask.data_ptr(), self.log_score.data_ptr(),
+                                             self.log_frame.data_ptr(), self.log_last.data_ptr(),
+                                             self.log_env.data_ptr(), self.cap, self.log_count.data_ptr(),
+                                             self.transitions.data_ptr(), a._stream()), 'rloa_episode_update')
+        if auto_reset:      # finished envs start their 50 reset sub-steps, one per following step() (lock step)
+            env.sim.begin_reset(env.initial_targets(), mask=self.reset_mask)
+        self.state, self.next_state = self.next_state, self.state

@@ -1,0 +1,46 @@
+"""
+CollisionObject / CollisionDetector — API-compatible with
+/root/reference/robotic_manipulator_rloa/utils/collision_detector.py:9-61, answered by the batched
+simulator's closest-distance kernel (rloa_sim_observe) instead of p.getClosestPoints.
+`body` is the Environment's simulator, `obstacle_ids` are the tokens Environment hands out
+('obstacle' / 'target').  Link-vs-link queries (compute_collisions_in_manipulator, :63-98) are outside
+the hot path and not provided.
+"""
+from dataclasses import dataclass
+from typing import List
+
+import numpy as np
+
+
+@dataclass
+class CollisionObject:
+    body: object
+    link: int
+
+
+class CollisionDetector:
+
+    def __init__(self, collision_object: CollisionObject, obstacle_ids: List[str]):
+        self.obstacles = obstacle_ids
+        self.collision_object = collision_object
+
+    def compute_distances(self, max_distance: float = 10.0, env_index: int = 0) -> np.ndarray:
+        """Closest distance from the link to each obstacle token; saturates at max_distance (:33-61)."""
+        sim = self.collision_object.body
+        _, link_obstacle, ee_target = sim.observe(want_distances=True)
+        out = []
+        for token in self.obstacles:
+            if token == 'obstacle':
+                d = float(link_obstacle[env_index, self.collision_object.link].item())
+            elif token == 'target':
+                if self.collision_object.link != sim.endeffector_index:
+                    raise NotImplementedError('target distances are computed for the end-effector link only')
+                d = float(ee_target[env_index].item())
+            else:
+                raise ValueError(f'unknown obstacle token {token!r}')
+            out.append(min(d, max_distance))
+        return np.array(out)
+
+    def compute_collisions_in_manipulator(self, affected_joints, max_distance: float = 10.):
+        raise NotImplementedError('self-collision queries are out of scope of the B200 hot path '
+                                  '(Environment.step never enables consider_autocollision)')

@@ -1,0 +1,119 @@
+"""
+ReplayBuffer — drop-in for /root/reference/robotic_manipulator_rloa/utils/replay_buffer.py, with the
+storage moved into HBM: a struct-of-arrays ring (rloa_replay_append) instead of a host deque of
+namedtuples, and a device sampler + gather (rloa_replay_sample) instead of random.sample + np.stack
++ five H2D copies.  ``sample()`` keeps the reference dtypes: states f32 [B,S], actions int64 [B,A]
+(the .long() cast of replay_buffer.py:60), rewards f32 [B,1], next_states f32 [B,S], dones f32 [B,1].
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from .. import _native as N
+
+
+class ReplayBuffer:
+
+    def __init__(self, buffer_size: int, batch_size: int, device: torch.device, seed: int,
+                 state_size: Optional[int] = None, action_size: Optional[int] = None, max_append: int = 1):
+        self.device = torch.device(device)
+        self.buffer_size = int(buffer_size)
+        self.batch_size = int(batch_size)
+        self.seed = int(seed)
+        self._draws = 0
+        self._len = 0                       # host mirror of min(cursor, capacity)
+        self._max_append = int(max_append)
+        self._rb: Optional[N.Replay] = None
+        self.state_size, self.action_size = state_size, action_size
+        if state_size is not None and action_size is not None:
+            self._allocate(state_size, action_size)
+
+    def _allocate(self, state_size: int, action_size: int) -> None:
+        if self.device.type != 'cuda':
+            raise N.NativeLibraryError('ReplayBuffer storage lives in HBM: a CUDA device is required (no CPU fallback)')
+        self.lib = N.lib()
+        self.state_size, self.action_size = int(state_size), int(action_size)
+        f32 = dict(dtype=torch.float32, device=self.device)
+        cap = self.buffer_size
+        self.states = torch.zeros(cap, self.state_size, **f32)
+        self.next_states = torch.zeros(cap, self.state_size, **f32)
+        self.actions = torch.zeros(cap, self.action_size, **f32)
+        self.rewards = torch.zeros(cap, **f32)
+        self.dones = torch.zeros(cap, **f32)
+        self.cursor = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.scratch = torch.zeros((self._max_append + 1023) // 1024 + 1, dtype=torch.int32, device=self.device)
+        rb = N.Replay()
+        rb.capacity, rb.state_size, rb.action_size = cap, self.state_size, self.action_size
+        rb.states, rb.actions, rb.rewards = self.states.data_ptr(), self.actions.data_ptr(), self.rewards.data_ptr()
+        rb.next_states, rb.dones, rb.cursor = self.next_states.data_ptr(), self.dones.data_ptr(), self.cursor.data_ptr()
+        rb.scratch = self.scratch.data_ptr()
+        self._rb = rb
+        B = self.batch_size
+        self._out = (torch.empty(B, self.state_size, **f32), torch.empty(B, self.action_size, **f32),
+                     torch.empty(B, 1, **f32), torch.empty(B, self.state_size, **f32), torch.empty(B, 1, **f32))
+        self._idx = torch.empty(B, dtype=torch.int32, device=self.device)
+
+    @property
+    def native(self) -> N.Replay:
+        return self._rb
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ---- reference API ------------------------------------------------------------------------
+    def add(self, state, action, reward, next_state, done) -> None:
+        """One transition from host values (replay_buffer.py:32-45)."""
+        s = np.asarray(state[0] if isinstance(state, tuple) else state, dtype=np.float32).reshape(1, -1)
+        a = np.asarray(action, dtype=np.float32).reshape(1, -1)
+        if self._rb is None:
+            self._allocate(s.shape[1], a.shape[1])
+        dev = self.device
+        self.add_batch(torch.from_numpy(s).to(dev), torch.from_numpy(a).to(dev),
+                       torch.tensor([float(reward)], dtype=torch.float32, device=dev),
+                       torch.from_numpy(np.asarray(next_state, dtype=np.float32).reshape(1, -1)).to(dev),
+                       torch.tensor([1 if done else 0], dtype=torch.uint8, device=dev))
+
+    def add_batch(self, states: torch.Tensor, actions: torch.Tensor, rewards: torch.Tensor, next_states: torch.Tensor,
+                  dones: torch.Tensor, valid: Optional[torch.Tensor] = None, n_valid: Optional[int] = None) -> None:
+        """n transitions already on the device (fp32 rows, uint8 dones / valid)."""
+        n = states.shape[0]
+        if self._rb is None:
+            self._allocate(states.shape[1], actions.shape[1])
+        if n > self._max_append and valid is not None:
+            self._max_append = n
+            self.scratch = torch.zeros((n + 1023) // 1024 + 1, dtype=torch.int32, device=self.device)
+            self._rb.scratch = self.scratch.data_ptr()
+        N.check(self.lib.rloa_replay_append(C.byref(self._rb), n, states.data_ptr(), actions.data_ptr(),
+                                            rewards.data_ptr(), next_states.data_ptr(), N.ptr(dones), N.ptr(valid),
+                                            self._stream()), 'rloa_replay_append')
+        # host mirror of the live count; with a valid mask and no n_valid it is an upper bound (exact value:
+        # sync_len()) — the `len(memory) > batch_size` gate only matters before the ring first fills a batch
+        added = n if (valid is None or n_valid is None) else int(n_valid)
+        self._len = min(self.buffer_size, self._len + added)
+
+    def sync_len(self) -> int:
+        """Exact live count read back from the device cursor (synchronises)."""
+        if self._rb is not None:
+            self._len = min(self.buffer_size, int(self.cursor.item()))
+        return self._len
+
+    def sample_into(self, states, actions, rewards, next_states, dones, indices=None) -> None:
+        N.check(self.lib.rloa_replay_sample(C.byref(self._rb), states.shape[0], self.seed, self._draws,
+                                            states.data_ptr(), actions.data_ptr(), rewards.data_ptr(),
+                                            next_states.data_ptr(), N.ptr(dones), N.ptr(indices), self._stream()),
+                'rloa_replay_sample')
+        self._draws += 1
+
+    def sample(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+        if self._rb is None or self._len < self.batch_size:
+            raise ValueError('Sample larger than population or is negative')     # what random.sample raises
+        s, a, r, s2, d = self._out
+        self.sample_into(s, a, r, s2, d, self._idx)
+        return s.clone(), a.long(), r.clone(), s2.clone(), d.clone()
+
+    def __len__(self) -> int:
+        return self._len

@@ -46,3 +46,16 @@ def random_states(model, n, seed, vel=2.0, frac_limit=0.95, near_limit=0.0, held
             q[:, i] = rng.uniform(-held_range, held_range, n)
             qd[:, i] = rng.uniform(-0.2, 0.2, n)
     return q, qd
+
+
+def assert_params_close(got, want, name, rtol=2e-4, atol=2e-6, lr=1e-3, max_frac=1e-3):
+    """Post-Adam parameters: Adam moves every element by ~lr * g / (|g| + eps) — for elements whose gradient is at
+    rounding-noise level the direction is arbitrary, so a small fraction of elements may differ by up to a couple of
+    lr-sized steps; everything else must agree tightly."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    if got.dtype.kind != 'f' or got.ndim == 0:
+        assert np.array_equal(got, want), name
+        return
+    bad = np.abs(got - want) > atol + rtol * np.abs(want)
+    assert bad.mean() <= max_frac, f'{name}: {bad.sum()} of {bad.size} elements differ'
+    assert np.abs(got - want).max() <= 3.1 * lr, f'{name}: max diff {np.abs(got - want).max():.3e}'

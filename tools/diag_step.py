@@ -28,3 +28,22 @@ w = np.argsort(-err.max(axis=1))[:5]
 for e in w:
     print('env', e, 'it', it_g[e], it_o[e], 'err', err[e], 'qd_o', qd32[e], 'qd_in', qd0[e])
 # single substep with no PGS influence: compare free acceleration through a zero-impulse motor table
+from helpers import PANDA
+cfg = PANDA
+model, orc = make_oracle(cfg)
+q, qd = random_states(model, n, seed=7, vel=1.0, near_limit=0.25, held=cfg['fixed'])
+rng = np.random.default_rng(11)
+actions = rng.uniform(-1, 1, (n, 7)); actions[: n // 8] = np.sign(actions[: n // 8])
+sim = BatchedSimulator(model, n, cfg['ee'], cfg['involved'], cfg['fixed']); sim.set_task(cfg['target'], cfg['obstacle'])
+sim.set_state(q, qd)
+sim.step(torch.as_tensor(actions, dtype=torch.float32, device='cuda'))
+qg, qdg = sim.get_state(); it_g = sim.last_iterations().cpu().numpy()
+step_motors(orc, cfg)
+q32, qd32 = q.astype(np.float32).astype(np.float64), qd.astype(np.float32).astype(np.float64)
+q0, qd0 = q32.copy(), qd32.copy()
+orc.batch_step(q32, qd32, actions.astype(np.float32).astype(np.float64), cfg['involved'], 200.0, cfg['obstacle'], cfg['target'], nthreads=8)
+err = np.abs(qdg.cpu().numpy() - qd32)
+print('PANDA per-joint max |dqd|:', err.max(axis=0))
+w = np.argsort(-err.max(axis=1))[:3]
+for e in w:
+    print('env', e, 'it', it_g[e], 'err', err[e], '\n qd_o', qd32[e], '\n q_in', q0[e], '\n lower', model.lower, '\n upper', model.upper)
