@@ -12,205 +12,277 @@ namespace rloa {
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-struct SimArrays {
-    int n_envs, nl;
-    float *q, *qd;                          // [N][nl]
-    float *kp, *tpos, *tvel, *maximp;       // [N][nl] motor table
-    float *target, *obstacle;               // [N][3]
-    int* iters;                             // [N]
-    int* reset_left;                        // [N] pending reset sub-steps (lock-step asynchronous reset)
-};
+enum { kModeStep = 0, kModeResetOnly = 1 };
 
-struct StepCfgDev {
-    signed char act_index[kMaxLinks];       // index into the action vector, -1 = not involved
-    unsigned fixed_mask;                    // joints held with POSITION_CONTROL target 0
-    int n_act;
-    float vel_maximp;                       // max_force * dt
-    float pos_maximp;                       // 1e5 * dt (pybullet POSITION_CONTROL default force)
-    float target_thr, obstacle_thr;
-};
+// launch 1 of an env-step: thread = arm
+template <int NLMAX>
+__global__ void __launch_bounds__(kTpb) sim_dynamics_kernel(const __grid_constant__ ModelDev M, SimArrays S) {
+    const int env = blockIdx.x * kTpb + threadIdx.x;
+    if (env < S.n_envs) arm_dynamics<NLMAX>(M, S, env);
+}
 
-__device__ __forceinline__ void write_obs(const ModelDev* __restrict__ M, int lane, float q, float qd, V3 ee, V3 tg,
-                                          V3 ob, float* __restrict__ o) {
-    const int n = M->n_obs;
-    if (lane < n) {
-        o[lane] = q;
-        o[n + lane] = qd;
+// launch 2: block = 32 arms x ndof columns, warp = one column of M^-1 for 32 arms
+__global__ void __launch_bounds__(32 * kMaxDof) sim_minv_kernel(const __grid_constant__ ModelDev M, SimArrays S) {
+    const int env = blockIdx.x * 32 + threadIdx.x;
+    if (env < S.n_envs) arm_minv_column(M, S, env, threadIdx.y);
+}
+
+// symmetric M^-1 kept in registers: entry (a, b) of the lower triangle
+__device__ __forceinline__ constexpr int tri(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
+
+// launch 3: thread = arm.  Environment.step (reference environment.py:453-485) from the free velocity on:
+// motor / limit rows, projected Gauss-Seidel, integration, get_state, get_reward, is_terminal_state.
+template <int D, int NLMAX>
+__global__ void __launch_bounds__(kTpb)
+sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_constant__ StepCfgDev cfg, int mode,
+                 const float* __restrict__ actions, const uint8_t* __restrict__ active, float* __restrict__ obs,
+                 float* __restrict__ reward, uint8_t* __restrict__ done, uint8_t* __restrict__ valid_out) {
+    extern __shared__ float smem[];
+    const int tid = threadIdx.x;
+    const int N = S.n_envs;
+    const int env = blockIdx.x * kTpb + tid;
+    const int so = 9 + 2 * M.n_obs;
+    float* sm_obs = smem + tid * so;                    // [kTpb][so] staging for a coalesced obs write
+    float* sm_lim = smem + kTpb * so + tid;             // [4][D][kTpb]: limit rows rhs_lo, app_lo, rhs_hi, app_hi
+    bool run = env < N && (active == nullptr || active[env] != 0);
+    // an env with pending reset sub-steps spends this launch on one of them (motors as begin_reset left
+    // them) instead of an action step; it emits no transition (valid = 0)
+    const int pending = run ? S.reset_left[env] : 0;
+    if (mode == kModeResetOnly && pending == 0) run = false;
+    const bool is_reset = pending > 0;
+    bool staged = false;
+    if (run) {
+        const int ndof = M.ndof;
+        const size_t sN = (size_t)N;
+        float Mi[D * (D + 1) / 2];
+#pragma unroll
+        for (int a = 0; a < D; a++)
+#pragma unroll
+            for (int b = 0; b <= a; b++)
+                Mi[tri(a, b)] = a < ndof ? S.minv[((size_t)a * ndof + b) * sN + env] : 0.f;
+
+        // ---- constraint rows: joint limits first (created at import), then one motor row per dof ----
+        float rhs[D], mx[D], jdi[D], dv[D], app[D];
+        unsigned mlo = 0u, mhi = 0u;
+        const float inv_dt = M.inv_dt;
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            rhs[d] = 0.f; mx[d] = 0.f; jdi[d] = 0.f; dv[d] = 0.f; app[d] = 0.f;
+            if (d < ndof) {
+                const int link = M.doflink[d];
+                const size_t at = (size_t)link * sN + env;
+                const float q = S.q[at], qs = S.qs[at];
+                // setJointMotorControl2: VELOCITY_CONTROL on involved joints (environment.py:464-469), then
+                // POSITION_CONTROL target 0 on the fixed joints (:472-476); other joints keep their motor
+                const int ai = cfg.act_index[link];
+                const bool fixedj = (cfg.fixed_mask >> link) & 1u;
+                float kp, tpos, tvel, maximp;
+                if (is_reset || (!fixedj && ai < 0)) {
+                    kp = S.kp[at]; tpos = S.tpos[at]; tvel = S.tvel[at]; maximp = S.maximp[at];
+                } else {
+                    if (fixedj) {
+                        kp = 0.1f; tpos = 0.f; tvel = 0.f; maximp = cfg.pos_maximp;
+                    } else {
+                        kp = 0.f; tpos = 0.f; tvel = actions[(size_t)env * cfg.n_act + ai]; maximp = cfg.vel_maximp;
+                    }
+                    S.kp[at] = kp; S.tpos[at] = tpos; S.tvel[at] = tvel; S.maximp[at] = maximp;
+                }
+                const float j = 1.f / Mi[tri(d, d)];
+                jdi[d] = j;
+                mx[d] = maximp;
+                // btMultiBodyJointMotor: rhs = kp (q_des - q)/dt + qs + kd (qd_des - qs), kd = 1, erp = 1
+                // (the row's right-hand side is rhs - qs; formed directly to avoid the cancellation)
+                rhs[d] = fmaf(kp * (tpos - q), inv_dt, tvel - qs) * j;
+                if (M.has_limit[link]) {
+                    const float pen0 = q - M.lower[link], pen1 = M.upper[link] - q;
+                    if (!(pen0 > 0.f)) {
+                        mlo |= 1u << d;
+                        sm_lim[(0 * D + d) * kTpb] = (-pen0 * M.erp * inv_dt - qs) * j;
+                        sm_lim[(1 * D + d) * kTpb] = 0.f;
+                    }
+                    if (!(pen1 > 0.f)) {
+                        mhi |= 1u << d;
+                        sm_lim[(2 * D + d) * kTpb] = (-pen1 * M.erp * inv_dt + qs) * j;
+                        sm_lim[(3 * D + d) * kTpb] = 0.f;
+                    }
+                }
+            }
+        }
+
+        // ---- projected Gauss-Seidel, M^-1 in registers; sweep direction alternates like Bullet's ----
+        const float limit_hi = M.limit_max_imp, thresh = M.resid_thresh;
+        const int iters = M.iters;
+        int it = 0;
+        float resid = 0.f;
+        auto motor_row = [&](const int d) {
+            float delta = fmaf(-dv[d], jdi[d], rhs[d]);
+            const float sum = app[d] + delta;
+            float napp = sum;
+            if (sum < -mx[d]) { delta = -mx[d] - app[d]; napp = -mx[d]; }
+            else if (sum > mx[d]) { delta = mx[d] - app[d]; napp = mx[d]; }
+            app[d] = napp;
+#pragma unroll
+            for (int k = 0; k < D; k++) dv[k] = fmaf(delta, Mi[tri(d, k)], dv[k]);
+            const float dvel = delta * Mi[tri(d, d)];
+            resid = fmaxf(resid, dvel * dvel);
+        };
+        auto limit_row = [&](const int d, const int side) {
+            const float sgn = side ? -1.f : 1.f;
+            float* r = sm_lim + (2 * side * D + d) * kTpb;
+            const float a0 = r[D * kTpb];
+            float delta = fmaf(-(sgn * dv[d]), jdi[d], r[0]);
+            const float sum = a0 + delta;
+            float napp = sum;
+            if (sum < 0.f) { delta = -a0; napp = 0.f; }
+            else if (sum > limit_hi) { delta = limit_hi - a0; napp = limit_hi; }
+            r[D * kTpb] = napp;
+            const float sd = sgn * delta;
+#pragma unroll
+            for (int k = 0; k < D; k++) dv[k] = fmaf(sd, Mi[tri(d, k)], dv[k]);
+            const float dvel = delta * Mi[tri(d, d)];
+            resid = fmaxf(resid, dvel * dvel);
+        };
+        for (it = 0; it < iters; it++) {
+            resid = 0.f;
+            if (it & 1) {
+                if (mlo | mhi) {
+#pragma unroll
+                    for (int d = 0; d < D; d++) {
+                        if ((mlo >> d) & 1u) limit_row(d, 0);
+                        if ((mhi >> d) & 1u) limit_row(d, 1);
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < D; d++)
+                    if (d < ndof) motor_row(d);
+            } else {
+#pragma unroll
+                for (int d = D - 1; d >= 0; d--)
+                    if (d < ndof) motor_row(d);
+                if (mlo | mhi) {
+#pragma unroll
+                    for (int d = D - 1; d >= 0; d--) {
+                        if ((mhi >> d) & 1u) limit_row(d, 1);
+                        if ((mlo >> d) & 1u) limit_row(d, 0);
+                    }
+                }
+            }
+            if (!(resid > thresh) || it >= iters - 1) { it++; break; }
+        }
+
+        // ---- velocity and position update (stepPositionsMultiDof) ----
+        const float max_vel = M.max_vel, dt = M.dt;
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            if (d < ndof) {
+                const size_t at = (size_t)M.doflink[d] * sN + env;
+                const float x = fminf(fmaxf(S.qs[at] + dv[d], -max_vel), max_vel);
+                S.qd[at] = x;
+                S.q[at] = fmaf(dt, x, S.q[at]);
+            }
+        }
+        const int nl = M.nl;
+        for (int i = 0; i < nl; i++)
+            if (M.dofidx[i] < 0) S.qd[(size_t)i * sN + env] = 0.f;
+
+        // ---- state / reward / done from the post-step configuration ----
+        const V3 tg = ld3(S.target + 3 * (size_t)env), ob = ld3(S.obstacle + 3 * (size_t)env);
+        const ObsOut o = fk_and_distances<NLMAX>(M, S.q + env, N, ob, tg, cfg.obstacle_thr, !is_reset, nullptr, 0);
+        if (obs != nullptr) {
+            const int n = M.n_obs;
+            for (int i = 0; i < n; i++) {
+                sm_obs[i] = S.q[(size_t)i * sN + env];
+                sm_obs[n + i] = S.qd[(size_t)i * sN + env];
+            }
+            float* t = sm_obs + 2 * n;
+            t[0] = o.ee_pos.x; t[1] = o.ee_pos.y; t[2] = o.ee_pos.z;
+            t[3] = tg.x; t[4] = tg.y; t[5] = tg.z;
+            t[6] = ob.x; t[7] = ob.y; t[8] = ob.z;
+            staged = true;
+        }
+        S.iters[env] = it;
+        if (is_reset) {
+            S.reset_left[env] = pending - 1;
+            if (mode == kModeStep) {
+                reward[env] = 0.f;
+                done[env] = 0;
+                if (valid_out != nullptr) valid_out[env] = 0;
+            }
+        } else {
+            const bool goal = o.ee_target < cfg.target_thr;
+            // get_reward (environment.py:364-371): goal first, then collision, else -(d - threshold)
+            reward[env] = goal ? 250.f : (o.hit ? -1000.f : -(o.ee_target - cfg.target_thr));
+            done[env] = (o.hit || goal) ? 1 : 0;         // is_terminal_state (environment.py:326-333)
+            if (valid_out != nullptr) valid_out[env] = 1;
+        }
     }
-    if (lane == 0) {
-        float* t = o + 2 * n;
-        t[0] = ee.x; t[1] = ee.y; t[2] = ee.z;
-        t[3] = tg.x; t[4] = tg.y; t[5] = tg.z;
-        t[6] = ob.x; t[7] = ob.y; t[8] = ob.z;
+    // obs rows of a block are contiguous: write them coalesced when every arm of the block produced one
+    if (obs == nullptr) return;
+    const int nvalid = min(kTpb, N - blockIdx.x * kTpb);
+    const unsigned all = __ballot_sync(0xffffffffu, staged || tid >= nvalid);
+    __syncwarp();
+    if (all == 0xffffffffu) {
+        float* dst = obs + (size_t)blockIdx.x * kTpb * so;
+        for (int k = tid; k < nvalid * so; k += kTpb) dst[k] = smem[k];
+    } else if (staged) {
+        float* dst = obs + (size_t)env * so;
+        for (int k = 0; k < so; k++) dst[k] = sm_obs[k];
     }
 }
 
-__device__ __forceinline__ V3 load3(const float* p) { return v3(p[0], p[1], p[2]); }
-
-// Environment.step (reference environment.py:453-485) for one env per warp
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-sim_step_kernel(const ModelDev* __restrict__ M, SimArrays S, StepCfgDev cfg, const float* __restrict__ actions,
-                const uint8_t* __restrict__ active, float* __restrict__ obs, float* __restrict__ reward,
-                uint8_t* __restrict__ done, uint8_t* __restrict__ valid_out) {
-    extern __shared__ float smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * kWarpsPerBlock + warp;
-    if (env >= S.n_envs) return;
-    if (active != nullptr && active[env] == 0) return;
-    const int nl = S.nl;
-    float* sm = smem + warp * sim_smem_floats_per_warp(nl);
-    const bool valid = lane < nl;
-    const size_t base = (size_t)env * nl + (valid ? lane : 0);
-    float q = 0.f, qd = 0.f;
-    Motor mot{0.f, 0.f, 0.f, 0.f};
-    // an env with pending reset sub-steps spends this launch on one of them (motors as begin_reset left
-    // them) instead of an action step; it emits no transition (valid = 0)
-    const int pending = S.reset_left[env];
-    if (pending > 0) {
-        if (valid) {
-            q = S.q[base];
-            qd = S.qd[base];
-            mot = Motor{S.kp[base], S.tpos[base], S.tvel[base], S.maximp[base]};
+// get_state + the distances behind get_reward / is_terminal_state, without stepping
+template <int NLMAX>
+__global__ void __launch_bounds__(kTpb)
+sim_observe_kernel(const __grid_constant__ ModelDev M, SimArrays S, float* __restrict__ obs,
+                   float* __restrict__ link_obst, float* __restrict__ ee_target) {
+    const int env = blockIdx.x * kTpb + threadIdx.x;
+    const int N = S.n_envs;
+    if (env >= N) return;
+    const V3 tg = ld3(S.target + 3 * (size_t)env), ob = ld3(S.obstacle + 3 * (size_t)env);
+    const ObsOut o = fk_and_distances<NLMAX>(M, S.q + env, N, ob, tg, 0.f, true,
+                                             link_obst ? link_obst + (size_t)env * M.nl : nullptr, 1);
+    if (obs != nullptr) {
+        const int n = M.n_obs;
+        float* t = obs + (size_t)env * (9 + 2 * n);
+        for (int i = 0; i < n; i++) {
+            t[i] = S.q[(size_t)i * N + env];
+            t[n + i] = S.qd[(size_t)i * N + env];
         }
-        const int it = warp_substep(M, sm, lane, q, qd, mot);
-        if (valid) {
-            S.q[base] = q;
-            S.qd[base] = qd;
-        }
-        M3 R;
-        V3 p;
-        lane_fk(M, valid ? lane : 0, valid, q, R, p);
-        const V3 tg = load3(S.target + 3 * (size_t)env), ob = load3(S.obstacle + 3 * (size_t)env);
-        write_obs(M, lane, q, qd, sh3(p, M->ee_link), tg, ob, obs + (size_t)env * (9 + 2 * M->n_obs));
-        if (lane == 0) {
-            S.reset_left[env] = pending - 1;
-            reward[env] = 0.f;
-            done[env] = 0;
-            S.iters[env] = it;
-            if (valid_out != nullptr) valid_out[env] = 0;
-        }
-        return;
+        t += 2 * n;
+        t[0] = o.ee_pos.x; t[1] = o.ee_pos.y; t[2] = o.ee_pos.z;
+        t[3] = tg.x; t[4] = tg.y; t[5] = tg.z;
+        t[6] = ob.x; t[7] = ob.y; t[8] = ob.z;
     }
-    if (valid) {
-        q = S.q[base];
-        qd = S.qd[base];
-        // setJointMotorControl2: VELOCITY_CONTROL on involved joints (environment.py:464-469), then
-        // POSITION_CONTROL target 0 on the fixed joints (:472-476); other joints keep their motor
-        const int ai = cfg.act_index[lane];
-        const bool fixedj = (cfg.fixed_mask >> lane) & 1u;
-        if (fixedj) {
-            mot = Motor{0.1f, 0.f, 0.f, cfg.pos_maximp};
-        } else if (ai >= 0) {
-            mot = Motor{0.f, 0.f, actions[(size_t)env * cfg.n_act + ai], cfg.vel_maximp};
-        } else {
-            mot = Motor{S.kp[base], S.tpos[base], S.tvel[base], S.maximp[base]};
-        }
-        if (fixedj || ai >= 0) {
-            S.kp[base] = mot.kp; S.tpos[base] = mot.tpos; S.tvel[base] = mot.tvel; S.maximp[base] = mot.maximp;
-        }
-    }
-    const int it = warp_substep(M, sm, lane, q, qd, mot);
-    if (valid) {
-        S.q[base] = q;
-        S.qd[base] = qd;
-    }
-    // state / reward / done from the post-step configuration
-    M3 R;
-    V3 p;
-    lane_fk(M, valid ? lane : 0, valid, q, R, p);
-    const V3 tg = load3(S.target + 3 * (size_t)env), ob = load3(S.obstacle + 3 * (size_t)env);
-    const ObsOut o = lane_distances(M, lane, R, p, ob, tg, cfg.obstacle_thr, false);
-    write_obs(M, lane, q, qd, o.ee_pos, tg, ob, obs + (size_t)env * (9 + 2 * M->n_obs));
-    if (lane == 0) {
-        const bool goal = o.ee_target < cfg.target_thr;
-        // get_reward (environment.py:364-371): goal first, then collision, else -(d - threshold)
-        reward[env] = goal ? 250.f : (o.hit ? -1000.f : -(o.ee_target - cfg.target_thr));
-        done[env] = (o.hit || goal) ? 1 : 0;         // is_terminal_state (environment.py:326-333)
-        S.iters[env] = it;
-        if (valid_out != nullptr) valid_out[env] = 1;
-    }
+    if (ee_target != nullptr) ee_target[env] = o.ee_target;
 }
 
 // lock-step asynchronous Environment.reset: arm the POSITION_CONTROL motors of the masked envs and let
 // the next n_substeps step launches run their reset sub-steps (environment.py:295-301)
 __global__ void sim_begin_reset_kernel(SimArrays S, const uint8_t* __restrict__ mask,
                                        const float* __restrict__ init_targets, int n_init, int nsub, float pos_maximp) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= S.n_envs) return;
+    if (mask != nullptr && mask[env] == 0) return;
+    const size_t N = (size_t)S.n_envs;
+    for (int j = 0; j < n_init; j++) {
+        const size_t at = (size_t)j * N + env;
+        S.kp[at] = 0.1f; S.tpos[at] = init_targets[(size_t)env * n_init + j]; S.tvel[at] = 0.f; S.maximp[at] = pos_maximp;
+    }
+    S.reset_left[env] = nsub;
+}
+
+// [N][nl] (C ABI layout) <-> [nl][N] (device layout)
+__global__ void sim_scatter_kernel(int n_envs, int nl, const float* __restrict__ src, float* __restrict__ dst) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t n = (size_t)S.n_envs * S.nl;
-    if (i >= n) return;
-    const int env = (int)(i / S.nl), j = (int)(i - (size_t)env * S.nl);
-    if (mask != nullptr && mask[env] == 0) return;
-    if (j < n_init) {
-        S.kp[i] = 0.1f; S.tpos[i] = init_targets[(size_t)env * n_init + j]; S.tvel[i] = 0.f; S.maximp[i] = pos_maximp;
-    }
-    if (j == 0) S.reset_left[env] = nsub;
+    if (i >= (size_t)n_envs * nl) return;
+    const int env = (int)(i / nl), j = (int)(i - (size_t)env * nl);
+    dst[(size_t)j * n_envs + env] = src[i];
 }
-
-// Environment.reset (reference environment.py:264-309) for the masked envs
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-sim_reset_kernel(const ModelDev* __restrict__ M, SimArrays S, const uint8_t* __restrict__ mask,
-                 const float* __restrict__ init_targets, int n_init, int nsub, float pos_maximp,
-                 float* __restrict__ obs) {
-    extern __shared__ float smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * kWarpsPerBlock + warp;
-    if (env >= S.n_envs) return;
-    if (mask != nullptr && mask[env] == 0) return;
-    const int nl = S.nl;
-    float* sm = smem + warp * sim_smem_floats_per_warp(nl);
-    const bool valid = lane < nl;
-    const size_t base = (size_t)env * nl + (valid ? lane : 0);
-    float q = 0.f, qd = 0.f;
-    Motor mot{0.f, 0.f, 0.f, 0.f};
-    if (valid) {
-        q = S.q[base];
-        qd = S.qd[base];
-        if (lane < n_init) {   // POSITION_CONTROL defaults: kp 0.1, kd 1, force 1e5 (environment.py:295-298)
-            mot = Motor{0.1f, init_targets[(size_t)env * n_init + lane], 0.f, pos_maximp};
-            S.kp[base] = mot.kp; S.tpos[base] = mot.tpos; S.tvel[base] = mot.tvel; S.maximp[base] = mot.maximp;
-        } else {
-            mot = Motor{S.kp[base], S.tpos[base], S.tvel[base], S.maximp[base]};
-        }
-    }
-    int it = 0;
-    for (int s = 0; s < nsub; s++) it = warp_substep(M, sm, lane, q, qd, mot);
-    if (valid) {
-        S.q[base] = q;
-        S.qd[base] = qd;
-    }
-    if (lane == 0) {
-        S.iters[env] = it;
-        S.reset_left[env] = 0;
-    }
-    if (obs != nullptr) {
-        M3 R;
-        V3 p;
-        lane_fk(M, valid ? lane : 0, valid, q, R, p);
-        const V3 tg = load3(S.target + 3 * (size_t)env), ob = load3(S.obstacle + 3 * (size_t)env);
-        const V3 ee = sh3(p, M->ee_link);
-        write_obs(M, lane, q, qd, ee, tg, ob, obs + (size_t)env * (9 + 2 * M->n_obs));
-    }
-}
-
-// get_state + the distances behind get_reward / is_terminal_state, without stepping
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-sim_observe_kernel(const ModelDev* __restrict__ M, SimArrays S, float* __restrict__ obs, float* __restrict__ link_obst,
-                   float* __restrict__ ee_target) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * kWarpsPerBlock + warp;
-    if (env >= S.n_envs) return;
-    const int nl = S.nl;
-    const bool valid = lane < nl;
-    const size_t base = (size_t)env * nl + (valid ? lane : 0);
-    const float q = valid ? S.q[base] : 0.f, qd = valid ? S.qd[base] : 0.f;
-    M3 R;
-    V3 p;
-    lane_fk(M, valid ? lane : 0, valid, q, R, p);
-    const V3 tg = load3(S.target + 3 * (size_t)env), ob = load3(S.obstacle + 3 * (size_t)env);
-    const ObsOut o = lane_distances(M, lane, R, p, ob, tg, 0.f, link_obst != nullptr);
-    if (obs != nullptr) write_obs(M, lane, q, qd, o.ee_pos, tg, ob, obs + (size_t)env * (9 + 2 * M->n_obs));
-    if (link_obst != nullptr && valid) link_obst[base] = o.link_dist;
-    if (ee_target != nullptr && lane == 0) ee_target[env] = o.ee_target;
+__global__ void sim_gather_kernel(int n_envs, int nl, const float* __restrict__ src, float* __restrict__ dst) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n_envs * nl) return;
+    const int env = (int)(i / nl), j = (int)(i - (size_t)env * nl);
+    dst[i] = src[(size_t)j * n_envs + env];
 }
 
 __global__ void sim_clear_kernel(SimArrays S) {
@@ -269,15 +341,14 @@ using namespace rloa;
 
 struct rloa_model {
     ModelDev host;
-    ModelDev* dev = nullptr;
     int device = 0;
 };
 
 struct rloa_sim {
     const rloa_model* model = nullptr;
     SimArrays a{};
+    float* block = nullptr;
     int device = 0;
-    size_t smem_bytes = 0;
 };
 
 static void mat3_mul(const double* A, const double* B, double* C) {
@@ -308,15 +379,13 @@ extern "C" int rloa_model_create(const rloa_model_desc* d, rloa_model** out) {
     h.limit_max_imp = (float)d->limit_max_impulse;
     for (int k = 0; k < 3; k++) { h.gravity[k] = (float)d->gravity[k]; h.target_half[k] = (float)d->target_half[k]; }
     h.obstacle_radius = (float)d->obstacle_radius;
-    int ndof = 0, maxdepth = 0, nslots = 0;
+    int ndof = 0, nslots = 0;
     std::vector<int> slot(nl, -1);
     for (int i = 0; i < nl; i++) {
         const int p = d->parent[i];
         if (!(p >= -1 && p < i)) { delete m; return fail(RLOA_ERR_INVALID, "rloa_model_create: links must be numbered depth first (parent < child)"); }
         h.parent[i] = p;
         h.jtype[i] = d->jtype[i];
-        h.depth[i] = p < 0 ? 0 : h.depth[p] + 1;
-        if (h.depth[i] > maxdepth) maxdepth = h.depth[i];
         h.has_limit[i] = d->has_limit[i];
         h.dofidx[i] = -1;
         if (d->jtype[i] != RLOA_JOINT_FIXED) {
@@ -325,11 +394,6 @@ extern "C" int rloa_model_create(const rloa_model_desc* d, rloa_model** out) {
             h.dofidx[i] = ndof;
             h.doflink[ndof++] = i;
         }
-        if (p >= 0) {
-            if (h.nch[p] >= kMaxChildren) { delete m; return fail(RLOA_ERR_INVALID, "rloa_model_create: at most 4 children per link supported"); }
-            h.child[p][h.nch[p]++] = i;
-        }
-        h.anc_mask[i] = (1u << i) | (p >= 0 ? h.anc_mask[p] : 0u);
         // parent COM frame <- child COM frame at q = 0; the fixed base pose is folded into root links
         double E0T[9], ee[3];
         for (int a = 0; a < 3; a++)
@@ -355,25 +419,30 @@ extern "C" int rloa_model_create(const rloa_model_desc* d, rloa_model** out) {
         h.lower[i] = (float)d->lower[i];
         h.upper[i] = (float)d->upper[i];
     }
-    h.ndof = ndof; h.maxdepth = maxdepth;
-    h.nrounds = 0;
-    while ((1 << h.nrounds) < maxdepth + 1) h.nrounds++;
-    for (int i = 0; i < nl; i++) {          // where the unit-response sweep finds the parent's acceleration
+    if (ndof < 1) { delete m; return fail(RLOA_ERR_INVALID, "rloa_model_create: the model has no movable joint"); }
+    h.ndof = ndof;
+    // where the serial sweeps find a link's parent value: the previous link (running register), or a slot
+    // kept for links whose children are not numbered right after them
+    for (int i = 0; i < nl; i++) {
         const int p = h.parent[i];
-        h.accsave[i] = -1;
-        if (p < 0) h.accsrc[i] = 0;
-        else if (p == i - 1) h.accsrc[i] = 1;
+        h.bwsrc[i] = 0;
+        if (p < 0) { h.fwsrc[i] = 0; h.bwdst[i] = -1; }
+        else if (p == i - 1) { h.fwsrc[i] = 1; h.bwdst[i] = 0; }
         else {
             if (slot[p] < 0) {
                 if (nslots >= kMaxSlots) { delete m; return fail(RLOA_ERR_INVALID, "rloa_model_create: too many branching links (max 3)"); }
                 slot[p] = nslots++;
             }
-            h.accsrc[i] = 2 + slot[p];
+            h.fwsrc[i] = 2 + slot[p];
+            h.bwdst[i] = 1 + slot[p];
         }
     }
-    for (int i = 0; i < nl; i++) h.accsave[i] = slot[i];
-    for (int i = 0; i < nl; i++)
-        if (h.nch[i] > h.lvl_maxch[h.depth[i] + 1]) h.lvl_maxch[h.depth[i] + 1] = h.nch[i];
+    h.nslots = nslots;
+    for (int i = 0; i < nl; i++) {
+        h.fwsave[i] = slot[i];
+        if (i + 1 < nl && h.parent[i + 1] == i) h.bwsrc[i] |= 1;
+        if (slot[i] >= 0) h.bwsrc[i] |= (slot[i] + 1) << 1;
+    }
     for (int s = 0; s < d->ns; s++) {
         if (!(d->s_link[s] >= 0 && d->s_link[s] < nl)) { delete m; return fail(RLOA_ERR_INVALID, "rloa_model_create: shape link out of range"); }
         h.s_link[s] = d->s_link[s];
@@ -383,21 +452,12 @@ extern "C" int rloa_model_create(const rloa_model_desc* d, rloa_model** out) {
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { delete m; cudaGetLastError(); return fail(RLOA_ERR_NO_DEVICE, "rloa_model_create: no CUDA device visible"); }
-    if (cudaGetDevice(&m->device) != cudaSuccess || cudaMalloc(&m->dev, sizeof(ModelDev)) != cudaSuccess ||
-        cudaMemcpy(m->dev, &h, sizeof(ModelDev), cudaMemcpyHostToDevice) != cudaSuccess) {
-        set_error("rloa_model_create: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-        delete m;
-        return RLOA_ERR_CUDA;
-    }
+    if (cudaGetDevice(&m->device) != cudaSuccess) { delete m; return fail(RLOA_ERR_CUDA, "rloa_model_create: cudaGetDevice failed"); }
     *out = m;
     return RLOA_OK;
 }
 
-extern "C" void rloa_model_destroy(rloa_model* m) {
-    if (m == nullptr) return;
-    if (m->dev) cudaFree(m->dev);
-    delete m;
-}
+extern "C" void rloa_model_destroy(rloa_model* m) { delete m; }
 
 extern "C" int rloa_sim_create(const rloa_model* m, int32_t n_envs, rloa_sim** out) {
     RLOA_REQUIRE(m != nullptr && out != nullptr, "rloa_sim_create: null argument");
@@ -406,35 +466,32 @@ extern "C" int rloa_sim_create(const rloa_model* m, int32_t n_envs, rloa_sim** o
     RLOA_REQUIRE(s != nullptr, "rloa_sim_create: out of host memory");
     s->model = m;
     s->device = m->device;
-    const int nl = m->host.nl;
-    const size_t n = (size_t)n_envs * nl;
+    const int nl = m->host.nl, ndof = m->host.ndof;
+    const size_t N = (size_t)n_envs, n = N * nl;
     s->a.n_envs = n_envs;
     s->a.nl = nl;
-    float* block = nullptr;
-    // one allocation: q qd kp tpos tvel maximp | target obstacle | iters
-    const size_t floats = 6 * n + 6 * (size_t)n_envs + 2 * (size_t)n_envs;
-    if (cudaMalloc(&block, floats * sizeof(float)) != cudaSuccess) {
+    s->a.ndof = ndof;
+    // one allocation: q qd kp tpos tvel maximp qs | F | minv | target obstacle | iters reset_left
+    const size_t floats = 7 * n + n * kFRec + N * ndof * ndof + 6 * N + 2 * N;
+    if (cudaMalloc(&s->block, floats * sizeof(float)) != cudaSuccess) {
         set_error("rloa_sim_create: cudaMalloc of %zu bytes failed: %s", floats * sizeof(float), cudaGetErrorString(cudaGetLastError()));
         delete s;
         return RLOA_ERR_CUDA;
     }
-    s->a.q = block; s->a.qd = block + n; s->a.kp = block + 2 * n; s->a.tpos = block + 3 * n;
-    s->a.tvel = block + 4 * n; s->a.maximp = block + 5 * n;
-    s->a.target = block + 6 * n; s->a.obstacle = s->a.target + 3 * (size_t)n_envs;
-    s->a.iters = reinterpret_cast<int*>(s->a.obstacle + 3 * (size_t)n_envs);
+    float* b = s->block;
+    s->a.q = b; s->a.qd = b + n; s->a.kp = b + 2 * n; s->a.tpos = b + 3 * n;
+    s->a.tvel = b + 4 * n; s->a.maximp = b + 5 * n; s->a.qs = b + 6 * n;
+    s->a.F = b + 7 * n;
+    s->a.minv = s->a.F + n * kFRec;
+    s->a.target = s->a.minv + N * ndof * ndof; s->a.obstacle = s->a.target + 3 * N;
+    s->a.iters = reinterpret_cast<int*>(s->a.obstacle + 3 * N);
     s->a.reset_left = s->a.iters + n_envs;
-    s->smem_bytes = (size_t)kWarpsPerBlock * sim_smem_floats_per_warp(nl) * sizeof(float);
-    if (s->smem_bytes > 48 * 1024) {
-        cudaFuncSetAttribute(sim_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
-        cudaFuncSetAttribute(sim_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
-    }
-    cudaMemset(s->a.target, 0, 6 * (size_t)n_envs * sizeof(float));
-    const int threads = 256;
-    sim_clear_kernel<<<(unsigned)((n + threads - 1) / threads), threads>>>(s->a);
+    cudaMemset(s->block, 0, floats * sizeof(float));
+    sim_clear_kernel<<<(unsigned)((n + 255) / 256), 256>>>(s->a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (cudaDeviceSynchronize() != cudaSuccess) {
         set_error("rloa_sim_create: initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
-        cudaFree(block);
+        cudaFree(s->block);
         delete s;
         return RLOA_ERR_CUDA;
     }
@@ -444,7 +501,7 @@ extern "C" int rloa_sim_create(const rloa_model* m, int32_t n_envs, rloa_sim** o
 
 extern "C" void rloa_sim_destroy(rloa_sim* s) {
     if (s == nullptr) return;
-    if (s->a.q) cudaFree(s->a.q);
+    if (s->block) cudaFree(s->block);
     delete s;
 }
 
@@ -459,30 +516,44 @@ extern "C" int rloa_sim_set_task(rloa_sim* s, const float* target, const float* 
     return RLOA_OK;
 }
 
+// [N][nl] caller layout -> [nl][N] device layout (and back)
+static int scatter(const rloa_sim* s, const float* src, float* dst, void* stream) {
+    const size_t n = (size_t)s->a.n_envs * s->a.nl;
+    sim_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(s->a.n_envs, s->a.nl, src, dst);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+static int gather(const rloa_sim* s, const float* src, float* dst, void* stream) {
+    const size_t n = (size_t)s->a.n_envs * s->a.nl;
+    sim_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(s->a.n_envs, s->a.nl, src, dst);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
 extern "C" int rloa_sim_set_state(rloa_sim* s, const float* q, const float* qd, void* stream) {
     RLOA_REQUIRE(s != nullptr, "rloa_sim_set_state: null sim");
-    const size_t bytes = (size_t)s->a.n_envs * s->a.nl * sizeof(float);
-    if (q) RLOA_CUDA(cudaMemcpyAsync(s->a.q, q, bytes, cudaMemcpyDeviceToDevice, as_stream(stream)));
-    if (qd) RLOA_CUDA(cudaMemcpyAsync(s->a.qd, qd, bytes, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    int rc = RLOA_OK;
+    if (q && (rc = scatter(s, q, s->a.q, stream)) != RLOA_OK) return rc;
+    if (qd && (rc = scatter(s, qd, s->a.qd, stream)) != RLOA_OK) return rc;
     return RLOA_OK;
 }
 
 extern "C" int rloa_sim_get_state(const rloa_sim* s, float* q, float* qd, void* stream) {
     RLOA_REQUIRE(s != nullptr, "rloa_sim_get_state: null sim");
-    const size_t bytes = (size_t)s->a.n_envs * s->a.nl * sizeof(float);
-    if (q) RLOA_CUDA(cudaMemcpyAsync(q, s->a.q, bytes, cudaMemcpyDeviceToDevice, as_stream(stream)));
-    if (qd) RLOA_CUDA(cudaMemcpyAsync(qd, s->a.qd, bytes, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    int rc = RLOA_OK;
+    if (q && (rc = gather(s, s->a.q, q, stream)) != RLOA_OK) return rc;
+    if (qd && (rc = gather(s, s->a.qd, qd, stream)) != RLOA_OK) return rc;
     return RLOA_OK;
 }
 
 extern "C" int rloa_sim_set_motors(rloa_sim* s, const float* kp, const float* tpos, const float* tvel,
                                    const float* maximp, void* stream) {
     RLOA_REQUIRE(s != nullptr, "rloa_sim_set_motors: null sim");
-    const size_t bytes = (size_t)s->a.n_envs * s->a.nl * sizeof(float);
-    if (kp) RLOA_CUDA(cudaMemcpyAsync(s->a.kp, kp, bytes, cudaMemcpyDeviceToDevice, as_stream(stream)));
-    if (tpos) RLOA_CUDA(cudaMemcpyAsync(s->a.tpos, tpos, bytes, cudaMemcpyDeviceToDevice, as_stream(stream)));
-    if (tvel) RLOA_CUDA(cudaMemcpyAsync(s->a.tvel, tvel, bytes, cudaMemcpyDeviceToDevice, as_stream(stream)));
-    if (maximp) RLOA_CUDA(cudaMemcpyAsync(s->a.maximp, maximp, bytes, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    int rc = RLOA_OK;
+    if (kp && (rc = scatter(s, kp, s->a.kp, stream)) != RLOA_OK) return rc;
+    if (tpos && (rc = scatter(s, tpos, s->a.tpos, stream)) != RLOA_OK) return rc;
+    if (tvel && (rc = scatter(s, tvel, s->a.tvel, stream)) != RLOA_OK) return rc;
+    if (maximp && (rc = scatter(s, maximp, s->a.maximp, stream)) != RLOA_OK) return rc;
     return RLOA_OK;
 }
 
@@ -499,6 +570,7 @@ static int make_step_cfg(const rloa_sim* s, const rloa_step_config* c, StepCfgDe
     RLOA_REQUIRE(c->n_act >= 0 && c->n_act <= kMaxLinks && c->n_fixed >= 0 && c->n_fixed <= kMaxLinks,
                  "rloa_sim_step: joint list too long");
     RLOA_REQUIRE(c->n_act == h.n_obs, "rloa_sim_step: n_act must equal the model's n_obs_joints");
+    std::memset(out, 0, sizeof(*out));
     for (int i = 0; i < kMaxLinks; i++) out->act_index[i] = -1;
     out->fixed_mask = 0;
     for (int k = 0; k < c->n_act; k++) {
@@ -519,17 +591,46 @@ static int make_step_cfg(const rloa_sim* s, const rloa_step_config* c, StepCfgDe
     return RLOA_OK;
 }
 
+template <int NLMAX>
+static int launch_solve(const rloa_sim* s, const StepCfgDev& c, int mode, const float* actions, const uint8_t* active,
+                        float* obs, float* reward, uint8_t* done, uint8_t* valid, cudaStream_t st) {
+    const ModelDev& h = s->model->host;
+    const unsigned blocks = (unsigned)((s->a.n_envs + kTpb - 1) / kTpb);
+    const int so = 9 + 2 * h.n_obs;
+#define RLOA_SOLVE(D)                                                                                              \
+    sim_solve_kernel<D, NLMAX><<<blocks, kTpb, (size_t)(kTpb * so + 4 * D * kTpb) * sizeof(float), st>>>(          \
+        h, s->a, c, mode, actions, active, obs, reward, done, valid)
+    if (h.ndof <= 4) RLOA_SOLVE(4);
+    else if (h.ndof <= 8) RLOA_SOLVE(8);
+    else if (h.ndof <= 9) RLOA_SOLVE(9);
+    else if (h.ndof <= 12) RLOA_SOLVE(12);
+    else RLOA_SOLVE(16);
+#undef RLOA_SOLVE
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
+// one stepSimulation for every env = three launches on the caller's stream
+static int launch_substep(const rloa_sim* s, const StepCfgDev& c, int mode, const float* actions, const uint8_t* active,
+                          float* obs, float* reward, uint8_t* done, uint8_t* valid, cudaStream_t st) {
+    const ModelDev& h = s->model->host;
+    const unsigned blocks = (unsigned)((s->a.n_envs + kTpb - 1) / kTpb);
+    if (h.nl <= 16) sim_dynamics_kernel<16><<<blocks, kTpb, 0, st>>>(h, s->a);
+    else sim_dynamics_kernel<32><<<blocks, kTpb, 0, st>>>(h, s->a);
+    RLOA_LAUNCHED();
+    sim_minv_kernel<<<blocks, dim3(32, h.ndof), 0, st>>>(h, s->a);
+    RLOA_LAUNCHED();
+    if (h.nl <= 16) return launch_solve<16>(s, c, mode, actions, active, obs, reward, done, valid, st);
+    return launch_solve<32>(s, c, mode, actions, active, obs, reward, done, valid, st);
+}
+
 extern "C" int rloa_sim_step(rloa_sim* s, const rloa_step_config* cfg, const float* actions, const uint8_t* active,
                              float* obs, float* reward, uint8_t* done, uint8_t* valid, void* stream) {
     RLOA_REQUIRE(s && cfg && actions && obs && reward && done, "rloa_sim_step: null argument");
     StepCfgDev c;
     const int rc = make_step_cfg(s, cfg, &c);
     if (rc != RLOA_OK) return rc;
-    const unsigned blocks = (unsigned)((s->a.n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    sim_step_kernel<<<blocks, kWarpsPerBlock * 32, s->smem_bytes, as_stream(stream)>>>(s->model->dev, s->a, c, actions,
-                                                                                     active, obs, reward, done, valid);
-    RLOA_LAUNCHED();
-    return RLOA_OK;
+    return launch_substep(s, c, kModeStep, actions, active, obs, reward, done, valid, as_stream(stream));
 }
 
 extern "C" int rloa_sim_begin_reset(rloa_sim* s, const uint8_t* mask, const float* init_targets, int32_t n_init,
@@ -538,8 +639,7 @@ extern "C" int rloa_sim_begin_reset(rloa_sim* s, const uint8_t* mask, const floa
     RLOA_REQUIRE(n_init >= 0 && n_init <= s->a.nl, "rloa_sim_begin_reset: n_init out of range");
     RLOA_REQUIRE(n_init == 0 || init_targets != nullptr, "rloa_sim_begin_reset: init_targets missing");
     RLOA_REQUIRE(n_substeps >= 0, "rloa_sim_begin_reset: n_substeps < 0");
-    const size_t n = (size_t)s->a.n_envs * s->a.nl;
-    sim_begin_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+    sim_begin_reset_kernel<<<(unsigned)((s->a.n_envs + 255) / 256), 256, 0, as_stream(stream)>>>(
         s->a, mask, init_targets, n_init, n_substeps, 100000.f * s->model->host.dt);
     RLOA_LAUNCHED();
     return RLOA_OK;
@@ -547,22 +647,27 @@ extern "C" int rloa_sim_begin_reset(rloa_sim* s, const uint8_t* mask, const floa
 
 extern "C" int rloa_sim_reset(rloa_sim* s, const uint8_t* mask, const float* init_targets, int32_t n_init,
                               int32_t n_substeps, float* obs, void* stream) {
-    RLOA_REQUIRE(s != nullptr, "rloa_sim_reset: null sim");
-    RLOA_REQUIRE(n_init >= 0 && n_init <= s->a.nl, "rloa_sim_reset: n_init out of range");
-    RLOA_REQUIRE(n_init == 0 || init_targets != nullptr, "rloa_sim_reset: init_targets missing");
-    RLOA_REQUIRE(n_substeps >= 0, "rloa_sim_reset: n_substeps < 0");
-    const unsigned blocks = (unsigned)((s->a.n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    sim_reset_kernel<<<blocks, kWarpsPerBlock * 32, s->smem_bytes, as_stream(stream)>>>(
-        s->model->dev, s->a, mask, init_targets, n_init, n_substeps, 100000.f * s->model->host.dt, obs);
-    RLOA_LAUNCHED();
+    const int rc = rloa_sim_begin_reset(s, mask, init_targets, n_init, n_substeps, stream);
+    if (rc != RLOA_OK) return rc;
+    StepCfgDev c;
+    std::memset(&c, 0, sizeof(c));
+    for (int i = 0; i < kMaxLinks; i++) c.act_index[i] = -1;
+    // the masked envs run their n_substeps reset sub-steps back to back; the last one writes their state
+    for (int k = 0; k < n_substeps; k++) {
+        const int r = launch_substep(s, c, kModeResetOnly, nullptr, nullptr, k == n_substeps - 1 ? obs : nullptr, nullptr,
+                                     nullptr, nullptr, as_stream(stream));
+        if (r != RLOA_OK) return r;
+    }
+    if (n_substeps == 0 && obs != nullptr) return rloa_sim_observe(s, obs, nullptr, nullptr, stream);
     return RLOA_OK;
 }
 
 extern "C" int rloa_sim_observe(const rloa_sim* s, float* obs, float* link_obstacle, float* ee_target, void* stream) {
     RLOA_REQUIRE(s != nullptr, "rloa_sim_observe: null sim");
-    const unsigned blocks = (unsigned)((s->a.n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    sim_observe_kernel<<<blocks, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(s->model->dev, s->a, obs, link_obstacle,
-                                                                            ee_target);
+    const ModelDev& h = s->model->host;
+    const unsigned blocks = (unsigned)((s->a.n_envs + kTpb - 1) / kTpb);
+    if (h.nl <= 16) sim_observe_kernel<16><<<blocks, kTpb, 0, as_stream(stream)>>>(h, s->a, obs, link_obstacle, ee_target);
+    else sim_observe_kernel<32><<<blocks, kTpb, 0, as_stream(stream)>>>(h, s->a, obs, link_obstacle, ee_target);
     RLOA_LAUNCHED();
     return RLOA_OK;
 }
