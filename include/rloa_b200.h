@@ -199,6 +199,13 @@ void rloa_naf_ws_destroy(rloa_naf_ws* ws);
  * (bf16 operands, fp32 TMEM accumulation; looser bound) */
 int rloa_naf_ws_set_trunk(rloa_naf_ws* ws, int32_t mode);
 
+/* The trunk's hidden layer on its own (naf_neural_network.py:77-78):
+ *   z2 [B][H] = relu(z1 * scale + shift) @ w2^T + b2,   scale / shift [H] = folded BatchNorm1 coefficients.
+ * Runs on the path selected by rloa_naf_ws_set_trunk (fp32 CUDA cores, or tcgen05 with bf16 operands and
+ * fp32 TMEM accumulation); exposed so the tensor-core kernel can be checked in isolation. */
+int rloa_naf_hidden_layer(rloa_naf_ws* ws, const float* z1, const float* scale, const float* shift,
+                          const float* w2, const float* b2, float* z2, int32_t batch, void* stream);
+
 /* NAF.forward (naf_neural_network.py:56-123) without the sampling tail:
  * mu [B][A], pdiag [B][A] (= diag of P = L o L^T, i.e. exp(2 tanh z_kk)), V [B], and when
  * action != NULL, Q [B] = -1/2 sum_k P_kk (u_k - mu_k)^2 + V.  train_mode != 0 uses batch

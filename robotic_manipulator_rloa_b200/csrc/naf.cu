@@ -541,7 +541,7 @@ struct rloa_naf_ws {
     float *v_tmp;
     size_t splitk_floats;
     int n_loss_parts;
-    TrunkTC tc;                  // tcgen05 trunk state (bf16 staging buffers)
+    TrunkTC tc;                  // tcgen05 trunk state
 };
 
 static int naf_nparams(int S, int A, int H) {
@@ -676,11 +676,14 @@ static int trunk_forward(rloa_naf_ws* ws, int nets, const rloa_naf_params* const
     bn_stats_kernel<<<dim3(H / 32, nets), 256, 0, st>>>(bb, B, H, train);
     RLOA_LAUNCHED();
     if (ws->trunk_mode == 1) {
+        const float *z1p[2], *scp[2], *shp[2], *w2p[2], *b2p[2];
+        float* z2p[2];
         for (int n = 0; n < nets; n++) {
-            const int rc = trunk_tc_layer2(&ws->tc, ws->z1[n], ws->scale[n][0], ws->shift[n][0], P[n]->w2, P[n]->b2,
-                                           ws->z2[n], B, H, st);
-            if (rc != RLOA_OK) return rc;
+            z1p[n] = ws->z1[n]; scp[n] = ws->scale[n][0]; shp[n] = ws->shift[n][0];
+            w2p[n] = P[n]->w2; b2p[n] = P[n]->b2; z2p[n] = ws->z2[n];
         }
+        const int rc = trunk_tc_layer2(&ws->tc, nets, z1p, scp, shp, w2p, b2p, z2p, B, H, st);
+        if (rc != RLOA_OK) return rc;
     } else {
         for (int n = 0; n < nets; n++)
             gb.a[n] = GemmArgs{ws->z1[n], H, P[n]->w2, H, ws->z2[n], H, P[n]->b2, ws->scale[n][0], ws->shift[n][0], B, H, H, 0};
@@ -691,6 +694,20 @@ static int trunk_forward(rloa_naf_ws* ws, int nets, const rloa_naf_params* const
         bb.a[n] = BnArgs{ws->z2[n], P[n]->bn2_w, P[n]->bn2_b, P[n]->bn2_mean, P[n]->bn2_var, P[n]->bn2_batches,
                          ws->scale[n][1], ws->shift[n][1], ws->mean[n][1], ws->rstd[n][1]};
     bn_stats_kernel<<<dim3(H / 32, nets), 256, 0, st>>>(bb, B, H, train);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
+extern "C" int rloa_naf_hidden_layer(rloa_naf_ws* ws, const float* z1, const float* scale, const float* shift,
+                                     const float* w2, const float* b2, float* z2, int32_t batch, void* stream) {
+    RLOA_REQUIRE(ws && z1 && scale && shift && w2 && b2 && z2, "rloa_naf_hidden_layer: null argument");
+    RLOA_REQUIRE(batch >= 1, "rloa_naf_hidden_layer: batch >= 1 required");
+    cudaStream_t st = as_stream(stream);
+    const int H = ws->H;
+    if (ws->trunk_mode == 1) return trunk_tc_layer2(&ws->tc, 1, &z1, &scale, &shift, &w2, &b2, &z2, batch, H, st);
+    GemmBatch gb{};
+    gb.a[0] = GemmArgs{z1, H, w2, H, z2, H, b2, scale, shift, batch, H, H, 0};
+    gemm_kernel<kNT, true><<<dim3((H + BN - 1) / BN, (batch + BM - 1) / BM, 1), kGemmThreads, 0, st>>>(gb);
     RLOA_LAUNCHED();
     return RLOA_OK;
 }

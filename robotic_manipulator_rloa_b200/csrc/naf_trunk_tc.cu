@@ -1,14 +1,238 @@
-// tcgen05 tensor-core trunk — placeholder until the UMMA kernel lands
+// tcgen05 tensor-core trunk: the hidden_layer contraction of the NAF network on the 5th-generation
+// tensor cores (reference naf_components/naf_neural_network.py:77-78, `hidden_layer(relu(bn1(.)))`).
+//
+//   z2[m][n] = sum_k bf16(relu(z1[m][k] * scale[k] + shift[k])) * bf16(W2[n][k]) + b2[n]      (fp32 accumulate)
+//
+// One CTA owns a 128 x 64 output tile (UMMA M = 128, N = 64, cta_group::1) and the full K = 256:
+//   1. all 4 warps read the fp32 operands from global (rows are contiguous: coalesced 1 KB per warp load),
+//      apply the BatchNorm + ReLU prologue, round to bf16 and store 16-byte chunks into shared memory in the
+//      canonical K-major SWIZZLE_128B layout (row pitch 128 B = 64 bf16, 8-row atoms of 1 KB, chunk index
+//      XOR row % 8) — the layout TMA would have produced, written by hand because the prologue has to touch
+//      every element anyway;
+//   2. fence.proxy.async makes those generic-proxy stores visible to the tensor core's async proxy;
+//   3. one elected thread issues 16 tcgen05.mma (kind::f16, 128 x 64 x 16 each) walking K through the shared
+//      memory descriptors; the accumulator lives in 64 TMEM columns; tcgen05.commit arrives on an mbarrier;
+//   4. every warp reads its 32 TMEM lanes (tcgen05.ld 32x32b), adds the bias and writes fp32 rows.
+// W2 is converted from the fp32 master weights inside the kernel (it changes every update), so there is no
+// bf16 shadow copy to keep coherent.  sm_100a only.
 #include "common.cuh"
 #include "naf_trunk_tc.cuh"
+
+#include <cuda_bf16.h>
+
 namespace rloa {
-void trunk_tc_init(TrunkTC* t) { *t = TrunkTC{}; }
-void trunk_tc_free(TrunkTC* t) {
-    if (t->a_bf16) cudaFree(t->a_bf16);
-    if (t->w_bf16) cudaFree(t->w_bf16);
-    *t = TrunkTC{};
+
+constexpr int kTcM = 128;                     // rows per CTA (UMMA M)
+constexpr int kTcN = 64;                      // output features per CTA (UMMA N)
+constexpr int kTcK = 256;                     // contraction length (hidden)
+constexpr int kTcThreads = 128;
+constexpr int kTcKBlocks = kTcK / 64;         // 128-byte swizzle rows hold 64 bf16
+constexpr uint32_t kABlockBytes = kTcM * 128; // one k-block of A: 128 rows x 128 B
+constexpr uint32_t kBBlockBytes = kTcN * 128;
+constexpr uint32_t kTcSmemBytes = kTcKBlocks * (kABlockBytes + kBBlockBytes) + 1024 /*alignment slack*/ + 64;
+constexpr uint32_t kTmemCols = 64;
+
+// instruction descriptor, kind::f16: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1), both K-major
+// (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared memory matrix descriptor, K-major SWIZZLE_128B: start address >> 4 (bits 0-13), leading byte offset
+// (unused for swizzled K-major, canonical value 1) at bits 16-29, stride byte offset = 1024 B between 8-row
+// atoms at bits 32-45, descriptor version 1 at bits 46-47, layout type 2 (SWIZZLE_128B) at bits 61-63
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
 }
-int trunk_tc_prepare(TrunkTC*, int, int) { return fail(RLOA_ERR_INVALID, "tcgen05 trunk: not built yet"); }
-int trunk_tc_layer2(TrunkTC*, const float*, const float*, const float*, const float*, const float*, float*, int, int,
-                    cudaStream_t) { return fail(RLOA_ERR_INVALID, "tcgen05 trunk: not built yet"); }
+
+struct TcNet {
+    const float* z1;            // [B][256]
+    const float *scale, *shift; // [256] BatchNorm1 folded coefficients
+    const float* w2;            // [256][256] hidden_layer.weight (out, in)
+    const float* b2;            // [256]
+    float* z2;                  // [B][256]
+};
+struct TcBatch {
+    TcNet n[2];
+};
+
+// 8 consecutive fp32 -> one 16-byte chunk of bf16
+template <bool PRO>
+__device__ __forceinline__ uint4 pack8(const float4 a, const float4 b, const float* sc, const float* sh) {
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (PRO) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = fmaxf(fmaf(v[i], sc[i], sh[i]), 0.f);
+    }
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 r;
+    r.x = *reinterpret_cast<uint32_t*>(&p0); r.y = *reinterpret_cast<uint32_t*>(&p1);
+    r.z = *reinterpret_cast<uint32_t*>(&p2); r.w = *reinterpret_cast<uint32_t*>(&p3);
+    return r;
+}
+
+__global__ void __launch_bounds__(kTcThreads) trunk_tc_layer2_kernel(const __grid_constant__ TcBatch batch, int B) {
+    extern __shared__ uint8_t tc_smem_raw[];
+    const TcNet& g = batch.n[blockIdx.z];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * kTcM, n0 = blockIdx.y * kTcN;
+
+    const uint32_t raw = smem_u32(tc_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;              // SWIZZLE_128B atoms need 1024-byte alignment
+    uint8_t* sm = tc_smem_raw + (base - raw);
+    const uint32_t a_base = base, b_base = base + kTcKBlocks * kABlockBytes;
+    uint8_t* sm_a = sm;
+    uint8_t* sm_b = sm + kTcKBlocks * kABlockBytes;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + kTcKBlocks * (kABlockBytes + kBBlockBytes));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+
+    // ---- operands -> shared memory (bf16, K-major, 128-byte swizzle) ----
+    // lane owns the 16-byte chunk (8 bf16) k = 8 lane .. 8 lane + 7 of a row: k-block lane / 8, chunk lane % 8
+    const int kb = lane >> 3, ch = lane & 7;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        sc[i] = g.scale[lane * 8 + i];
+        sh[i] = g.shift[lane * 8 + i];
+    }
+#pragma unroll 4
+    for (int r = warp; r < kTcM; r += 4) {
+        const int row = m0 + r;
+        uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+        if (row < B) {
+            const float4* src = reinterpret_cast<const float4*>(g.z1 + (size_t)row * kTcK + lane * 8);
+            packed = pack8<true>(src[0], src[1], sc, sh);
+        }
+        const uint32_t off = kb * kABlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(sm_a + off) = packed;
+    }
+#pragma unroll 4
+    for (int r = warp; r < kTcN; r += 4) {
+        const float4* src = reinterpret_cast<const float4*>(g.w2 + (size_t)(n0 + r) * kTcK + lane * 8);
+        const uint4 packed = pack8<false>(src[0], src[1], nullptr, nullptr);
+        const uint32_t off = kb * kBBlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(sm_b + off) = packed;
+    }
+    // generic-proxy writes -> visible to the async proxy (tensor core operand fetch)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    // ---- one thread issues the 16 MMAs of the tile, then commits to the mbarrier ----
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < kTcK / 16; k++) {
+            // k-block k / 4 (64 bf16 = one 128-byte swizzle row), 32-byte step k % 4 inside the swizzle atom
+            const uint64_t adesc = umma_desc_sw128(a_base + (k >> 2) * kABlockBytes + (k & 3) * 32);
+            const uint64_t bdesc = umma_desc_sw128(b_base + (k >> 2) * kBBlockBytes + (k & 3) * 32);
+            const uint32_t accumulate = k > 0 ? 1u : 0u;
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+                "}\n" ::"r"(tmem),
+                "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+                : "memory");
+        }
+        // commit: the mbarrier completes when every MMA issued above has finished (implies before_thread_sync)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                     : "memory");
+    }
+    __syncwarp();
+    {   // wait for phase 0 of the mbarrier
+        uint32_t done = 0;
+        const uint32_t bar_addr = smem_u32(bar);
+        while (!done) {
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t"
+                "}\n"
+                : "=r"(done)
+                : "r"(bar_addr), "r"(0u)
+                : "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue: TMEM lane = tile row; warp w owns lanes 32 w .. 32 w + 31 ----
+    const int row = m0 + warp * 32 + lane;
+    float* dst = g.z2 + (size_t)row * kTcK + n0;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + half * 32;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < B) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 bias = *reinterpret_cast<const float4*>(g.b2 + n0 + half * 32 + j);
+                float4 o;
+                o.x = __uint_as_float(v[j]) + bias.x;
+                o.y = __uint_as_float(v[j + 1]) + bias.y;
+                o.z = __uint_as_float(v[j + 2]) + bias.z;
+                o.w = __uint_as_float(v[j + 3]) + bias.w;
+                *reinterpret_cast<float4*>(dst + half * 32 + j) = o;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+    }
+}
+
+void trunk_tc_init(TrunkTC* t) { *t = TrunkTC{}; }
+void trunk_tc_free(TrunkTC* t) { *t = TrunkTC{}; }
+
+int trunk_tc_prepare(TrunkTC* t, int max_batch, int H) {
+    RLOA_REQUIRE(H == kTcK, "tcgen05 trunk: hidden size must be 256");
+    int dev = 0, major = 0;
+    RLOA_CUDA(cudaGetDevice(&dev));
+    RLOA_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    RLOA_REQUIRE(major == 10, "tcgen05 trunk: needs an sm_100 device");
+    RLOA_CUDA(cudaFuncSetAttribute(trunk_tc_layer2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    t->max_batch = max_batch;
+    t->ready = true;
+    return RLOA_OK;
+}
+
+int trunk_tc_layer2(TrunkTC* t, int nets, const float* const* z1, const float* const* scale, const float* const* shift,
+                    const float* const* w2, const float* const* b2, float* const* z2, int B, int H, cudaStream_t st) {
+    RLOA_REQUIRE(t->ready, "tcgen05 trunk: rloa_naf_ws_set_trunk(1) was not called");
+    RLOA_REQUIRE(H == kTcK && nets >= 1 && nets <= 2, "tcgen05 trunk: hidden = 256 and 1..2 networks per launch");
+    TcBatch tb{};
+    for (int n = 0; n < nets; n++) tb.n[n] = TcNet{z1[n], scale[n], shift[n], w2[n], b2[n], z2[n]};
+    dim3 grid((B + kTcM - 1) / kTcM, kTcK / kTcN, nets);
+    trunk_tc_layer2_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(tb, B);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
 }  // namespace rloa

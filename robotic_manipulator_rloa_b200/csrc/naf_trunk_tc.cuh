@@ -6,17 +6,16 @@
 namespace rloa {
 
 struct TrunkTC {
-    void* a_bf16 = nullptr;     // [max_batch][256] activations, bf16
-    void* w_bf16 = nullptr;     // [256][256] weights, bf16
     int max_batch = 0;
     bool ready = false;
 };
 
 void trunk_tc_init(TrunkTC* t);
 void trunk_tc_free(TrunkTC* t);
+// checks the device, opts the kernel into its dynamic shared memory size
 int trunk_tc_prepare(TrunkTC* t, int max_batch, int H);
-// z2[B][H] = relu(z1 * scale + shift) @ w2^T + b2 on the tensor cores
-int trunk_tc_layer2(TrunkTC* t, const float* z1, const float* scale, const float* shift, const float* w2,
-                    const float* b2, float* z2, int B, int H, cudaStream_t st);
+// for each of `nets` networks: z2[B][H] = bf16(relu(z1 * scale + shift)) @ bf16(w2)^T + b2, fp32 accumulation in TMEM
+int trunk_tc_layer2(TrunkTC* t, int nets, const float* const* z1, const float* const* scale, const float* const* shift,
+                    const float* const* w2, const float* const* b2, float* const* z2, int B, int H, cudaStream_t st);
 
 }  // namespace rloa

@@ -126,8 +126,8 @@ class NAFAgent:
 
     def set_trunk_mode(self, mode: int) -> None:
         """0 = fp32 CUDA-core trunk (reference-exact), 1 = tcgen05 tensor-core trunk (bf16 operands)."""
-        self.qnetwork_main.trunk_mode = int(mode)
-        self.qnetwork_target.trunk_mode = int(mode)
+        self.qnetwork_main.set_trunk_mode(int(mode))
+        self.qnetwork_target.set_trunk_mode(int(mode))
         if self._ws is not None:
             self._ws.set_trunk(int(mode))
 
