@@ -203,8 +203,9 @@ def workload_config(args, where):
                         f'{args.envs} envs per GPU, {FRAMES}-step episodes, NAF batch {args.batch}, 1 update per '
                         'vectorised step, live-policy actions',
             'envs_per_gpu': args.envs, 'replay_batch': args.batch, 'frames': FRAMES, 'parallelism': f'env-dp{args.gpus}',
-            'l2': 'flushed between timed steps (256 MiB fill, untimed)' if where == 'gpu' else 'n/a',
-            'trunk': getattr(args, 'trunk', 'fp32')}
+            'l2': 'flushed between timed step pairs (256 MiB fill, untimed)' if where == 'gpu' else 'n/a',
+            'trunk': getattr(args, 'trunk', 'fp32'),
+            'launch': 'eager' if getattr(args, 'no_graph', False) or where == 'cpu' else 'cuda-graph of 2 loop iterations'}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -247,43 +248,61 @@ def ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # events recorded around rloa_sim_step inside the loop body; `external` lets them sit inside a CUDA graph
+    use_graph = not args.no_graph
+    try:
+        sim_pair = [(torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
+                    for _ in range(2)] if use_graph else None
+    except TypeError:
+        sim_pair, use_graph = None, False
+    if not use_graph:
+        sim_pair = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2)]
+    loop.sim_events = sim_pair
     for _ in range(max(args.warmup, 3)):
         loop.step()
+    graphed = bool(use_graph and loop.capture())
+    if graphed:
+        loop.replay_pair()                        # one untimed replay
     barrier()
 
-    # ---- timed region: K steps, per-step CUDA events, L2 flushed between steps -------------------------------
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sim_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # ---- timed region: K steps in pairs (the state buffers ping-pong), CUDA events per pair, L2 flushed between pairs ----
+    npairs, odd = args.steps // 2, args.steps % 2
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(npairs + odd)]
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     loop.transitions.zero_()
     launches0 = lib.rloa_launch_count()
-    orig_step = env.sim.step
-
-    def timed_sim_step(*a, **k):
-        i = timed_sim_step.i
-        sim_ev[i][0].record()
-        out = orig_step(*a, **k)
-        sim_ev[i][1].record()
-        return out
-    env.sim.step = timed_sim_step
+    sim_ms = []
     barrier()
     t_wall = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(npairs + odd):
         if flush is not None:
             flush.fill_(i & 0xff)
-        timed_sim_step.i = i
         ev[i][0].record()
-        loop.step()
+        if i < npairs:
+            if graphed:
+                loop.replay_pair()
+            else:
+                loop._body(True, True, 0)
+                loop._body(True, True, 1)
+        else:
+            loop._body(True, True, 0)
         ev[i][1].record()
+        if graphed or i % 16 == 15 or i == npairs + odd - 1:
+            # the sim events are re-recorded by every pair: read them before the next pair overwrites them
+            ev[i][1].synchronize()
+            sim_ms.append(sim_pair[0][0].elapsed_time(sim_pair[0][1]))
+            if i < npairs:
+                sim_ms.append(sim_pair[1][0].elapsed_time(sim_pair[1][1]))
     barrier()
     t_wall = time.perf_counter() - t_wall
-    env.sim.step = orig_step
+    loop.sim_events = None
     launches = lib.rloa_launch_count() - launches0
+    if graphed:      # a graph replay re-launches the kernels recorded at capture: count them per replay
+        launches = loop.graph_kernels * npairs + launches
     clocks = sampler.stop() if rank == 0 else None
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    sim_ms = [a.elapsed_time(b) for a, b in sim_ev]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     trans = loop.transitions.clone().to(torch.float64)
     if world > 1:
@@ -304,7 +323,7 @@ def ours(args):
     e0.record()
     for i in range(e2e_steps):
         loop.state.copy_(h_state, non_blocking=True)                      # H2D: this step's states
-        agent.act_batch(loop.state, out=loop.actions)
+        agent.act_batch(loop.state, out=loop.actions, tick=loop.tick)
         h_act.copy_(loop.actions, non_blocking=True)                      # D2H: actions to the caller
         torch.cuda.current_stream().synchronize()
         loop.actions.copy_(h_act, non_blocking=True)                      # H2D: actions into Environment.step
@@ -313,13 +332,13 @@ def ours(args):
         h_rew.copy_(loop.reward, non_blocking=True)
         h_done.copy_(loop.done, non_blocking=True)
         agent.memory.add_batch(loop.state, loop.actions, loop.reward, loop.next_state, loop.done, valid=loop.valid)
-        agent._maybe_learn()
+        agent._maybe_learn(tick=loop.tick)
         _native.check(lib.rloa_episode_update(n, FRAMES, loop.reward.data_ptr(), loop.done.data_ptr(), loop.valid.data_ptr(),
                                               loop.score.data_ptr(), loop.frame.data_ptr(), loop.reset_mask.data_ptr(),
                                               loop.log_score.data_ptr(), loop.log_frame.data_ptr(), loop.log_last.data_ptr(),
                                               loop.log_env.data_ptr(), loop.cap, loop.log_count.data_ptr(),
-                                              loop.transitions.data_ptr(), agent._stream()))
-        env.sim.begin_reset(env.initial_targets(), mask=loop.reset_mask)
+                                              loop.transitions.data_ptr(), loop.tick.data_ptr(), agent._stream()))
+        env.begin_reset_masked(loop.reset_mask, tick=loop.tick)
         torch.cuda.current_stream().synchronize()
     e1.record()
     barrier()
@@ -363,6 +382,7 @@ def ours(args):
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n * (S + A) * 4,
                     'd2h_bytes_per_step': n * (A * 4 + S * 4 + 4 + 1), 'steps': e2e_steps},
             'gpu_launches': int(launches),
+            'graphed': graphed, 'graph_error': loop.graph_error,
             'clocks': clocks,
         }
         print(json.dumps(line))
@@ -380,6 +400,7 @@ def main():
     ap.add_argument('--batch', type=int, default=1024, help='replay batch per GPU')
     ap.add_argument('--trunk', default='fp32', choices=['fp32', 'tc'])
     ap.add_argument('--no-flush', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly instead of replaying the CUDA graph')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -145,6 +145,13 @@ int rloa_sim_step(rloa_sim* s, const rloa_step_config* cfg, const float* actions
 int rloa_sim_begin_reset(rloa_sim* s, const uint8_t* mask, const float* init_targets, int32_t n_init,
                          int32_t n_substeps, void* stream);
 
+/* rloa_sim_begin_reset with the start pose drawn on the device (environment.py:284-293):
+ * target_j = pos[j] + var[j] * U(-1, 1) for j < n_init, Philox4x32-10 keyed by (seed, *tick, env, j).
+ * pos / var are DEVICE arrays [n_init] (NULL = zeros); tick is a DEVICE counter (may be NULL). */
+int rloa_sim_begin_reset_random(rloa_sim* s, const uint8_t* mask, const float* pos, const float* var,
+                                int32_t n_init, int32_t n_substeps, uint64_t seed, const uint64_t* tick,
+                                void* stream);
+
 /* Environment.reset for the envs with mask != 0 (environment.py:264-309):
  * POSITION_CONTROL targets init_targets [n_envs][n_init] on joints 0..n_init-1, then n_substeps
  * (50) simulation steps; writes the new state of those envs into obs [n_envs][S].
@@ -166,12 +173,16 @@ int rloa_sim_last_iterations(const rloa_sim* s, int32_t* iters, void* stream);
  * score += reward; frame += 1; finished = done | (frame >= frames);
  * finished envs get their (score, frame, reward) appended to the episode log ring and are flagged
  * in reset_mask; their counters restart at 0.  `active` (may be NULL) selects the envs that produced a
- * transition this step; `transitions` (device int64, may be NULL) accumulates their number.
+ * transition this step; `transitions` (device int64, may be NULL) accumulates their number; `tick`
+ * (device uint64, may be NULL) is incremented once per call — the device-resident loop counter that
+ * rloa_naf_act / rloa_replay_sample read through their *_offset arguments, so that a CUDA graph of
+ * the whole loop iteration draws fresh random numbers on every replay.
  * ---------------------------------------------------------------------------------------------- */
 int rloa_episode_update(int32_t n_envs, int32_t frames, const float* reward, const uint8_t* done,
                         const uint8_t* active, float* score, int32_t* frame, uint8_t* reset_mask,
                         float* log_score, int32_t* log_frame, float* log_last_reward, int32_t* log_env,
-                        int32_t log_capacity, int32_t* log_count, int64_t* transitions, void* stream);
+                        int32_t log_capacity, int32_t* log_count, int64_t* transitions, uint64_t* tick,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * NAF network (naf_components/naf_neural_network.py:8-123).  Parameters live in caller-owned
@@ -217,9 +228,11 @@ int rloa_naf_forward(rloa_naf_ws* ws, const rloa_naf_params* p, const float* sta
 
 /* NAFAgent.act for a batch of states (naf_algorithm.py:158-178 + naf_neural_network.py:119-121):
  * eval-mode forward, action = clamp(mu + exp(-tanh z_kk) * eps, -1, 1), eps ~ N(0,1) from
- * Philox4x32-10 keyed by (seed, step, row).  noise_scale = 0 gives the mean action. */
+ * Philox4x32-10 keyed by (seed, step + *step_offset, row); step_offset is a DEVICE counter and may be
+ * NULL.  noise_scale = 0 gives the mean action. */
 int rloa_naf_act(rloa_naf_ws* ws, const rloa_naf_params* p, const float* states, int32_t batch,
-                 uint64_t seed, uint64_t step, float noise_scale, float* actions, void* stream);
+                 uint64_t seed, uint64_t step, const uint64_t* step_offset, float noise_scale, float* actions,
+                 void* stream);
 
 typedef struct {
     float gamma, tau, lr;
@@ -261,7 +274,8 @@ typedef struct {
     int32_t capacity, state_size, action_size;
     float *states, *actions, *rewards, *next_states, *dones;
     int64_t* cursor;               /* device scalar: total transitions ever appended */
-    int32_t* scratch;              /* device, >= (max n per append + 1023) / 1024 + 1 ints (valid-mask compaction) */
+    int32_t* scratch;              /* device, ZERO-INITIALISED, >= (max n per append + 255) / 256 + 1 ints:
+                                      [0] completion ticket (returns to 0), [1..] per-block valid counts */
 } rloa_replay;
 
 /* ReplayBuffer.add for n transitions (deque(maxlen) overwrite order, replay_buffer.py:32-45);
@@ -270,10 +284,11 @@ int rloa_replay_append(const rloa_replay* rb, int32_t n, const float* states, co
                        const float* rewards, const float* next_states, const uint8_t* dones,
                        const uint8_t* valid, void* stream);
 /* ReplayBuffer.sample (replay_buffer.py:47-67): `batch` distinct slots drawn uniformly from the
- * live window with a keyed Feistel permutation (seed, draw); gathers the five fields. */
-int rloa_replay_sample(const rloa_replay* rb, int32_t batch, uint64_t seed, uint64_t draw, float* states,
-                       float* actions, float* rewards, float* next_states, float* dones, int32_t* indices,
-                       void* stream);
+ * live window with a keyed Feistel permutation (seed, draw + *draw_offset); draw_offset is a DEVICE
+ * counter and may be NULL; gathers the five fields. */
+int rloa_replay_sample(const rloa_replay* rb, int32_t batch, uint64_t seed, uint64_t draw,
+                       const uint64_t* draw_offset, float* states, float* actions, float* rewards,
+                       float* next_states, float* dones, int32_t* indices, void* stream);
 
 #ifdef __cplusplus
 }

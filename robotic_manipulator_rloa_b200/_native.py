@@ -96,16 +96,17 @@ SIGNATURES = {
     'rloa_sim_clear': (C.c_int, [_VP, _VP]),
     'rloa_sim_step': (C.c_int, [_VP, C.POINTER(StepConfig), _fp, _fp, _fp, _fp, _fp, _fp, _VP]),
     'rloa_sim_begin_reset': (C.c_int, [_VP, _fp, _fp, _I, _I, _VP]),
+    'rloa_sim_begin_reset_random': (C.c_int, [_VP, _fp, _fp, _fp, _I, _I, _U64, _fp, _VP]),
     'rloa_sim_reset': (C.c_int, [_VP, _fp, _fp, _I, _I, _fp, _VP]),
     'rloa_sim_observe': (C.c_int, [_VP, _fp, _fp, _fp, _VP]),
     'rloa_sim_last_iterations': (C.c_int, [_VP, _fp, _VP]),
-    'rloa_episode_update': (C.c_int, [_I, _I, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _I, _fp, _fp, _VP]),
+    'rloa_episode_update': (C.c_int, [_I, _I, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _I, _fp, _fp, _fp, _VP]),
     'rloa_naf_ws_create': (C.c_int, [_I, _I, _I, _I, C.POINTER(_VP)]),
     'rloa_naf_ws_destroy': (None, [_VP]),
     'rloa_naf_ws_set_trunk': (C.c_int, [_VP, _I]),
     'rloa_naf_hidden_layer': (C.c_int, [_VP, _fp, _fp, _fp, _fp, _fp, _fp, _I, _VP]),
     'rloa_naf_forward': (C.c_int, [_VP, C.POINTER(NafParams), _fp, _fp, _I, _I, _I, _fp, _fp, _fp, _fp, _VP]),
-    'rloa_naf_act': (C.c_int, [_VP, C.POINTER(NafParams), _fp, _I, _U64, _U64, _F, _fp, _VP]),
+    'rloa_naf_act': (C.c_int, [_VP, C.POINTER(NafParams), _fp, _I, _U64, _U64, _fp, _F, _fp, _VP]),
     'rloa_naf_num_params': (C.c_int, [_I, _I, _I]),
     'rloa_naf_learn_grads': (C.c_int, [_VP, C.POINTER(NafParams), C.POINTER(NafParams), _fp, _fp, _fp, _fp, _fp, _I,
                                        C.POINTER(NafHyper), _fp, _fp, _VP]),
@@ -113,7 +114,7 @@ SIGNATURES = {
                                        C.POINTER(NafHyper), _fp, _fp, _VP]),
     'rloa_naf_soft_update': (C.c_int, [C.POINTER(NafParams), C.POINTER(NafParams), _F, _VP]),
     'rloa_replay_append': (C.c_int, [C.POINTER(Replay), _I, _fp, _fp, _fp, _fp, _fp, _fp, _VP]),
-    'rloa_replay_sample': (C.c_int, [C.POINTER(Replay), _I, _U64, _U64, _fp, _fp, _fp, _fp, _fp, _fp, _VP]),
+    'rloa_replay_sample': (C.c_int, [C.POINTER(Replay), _I, _U64, _U64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _VP]),
 }
 
 _lib: Optional[C.CDLL] = None

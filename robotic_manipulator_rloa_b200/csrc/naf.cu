@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "naf_trunk_tc.cuh"
+#include "philox.cuh"
 
 namespace rloa {
 
@@ -128,6 +129,135 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(GemmBatch batch) {
     }
 }
 
+// Vectorised, double-buffered version of the same tile (used whenever lda, ldb, K-range and N are multiples of
+// 4 and the operands are 16-byte aligned — every contraction of the network except the two that touch the
+// S-wide input).  One float4 global load per operand per thread per k-step, issued a full tile ahead of the FMAs
+// that consume it (registers -> the other shared-memory buffer), float4 shared-memory reads in the inner loop.
+__device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <int LAYOUT, bool PRO>
+__global__ void __launch_bounds__(kGemmThreads) gemm_vec_kernel(GemmBatch batch) {
+    const GemmArgs& g = (LAYOUT == kTN) ? batch.a[0] : batch.a[blockIdx.z];
+    __shared__ __align__(16) float As[2][BK][BM + kPad];
+    __shared__ __align__(16) float Bs[2][BK][BN + kPad];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+    int k_begin = 0, k_end = g.K;
+    float* C = g.C;
+    if (LAYOUT == kTN && g.ksplit > 0) {
+        k_begin = blockIdx.z * g.ksplit;
+        k_end = min(g.K, k_begin + g.ksplit);
+        C += (size_t)blockIdx.z * g.M * g.ldc;
+    }
+    // operand fetch coordinates: "row-of-4-k" operands (A of NT/NN, B of NT) use (r = tid / 4, kq = tid % 4);
+    // "row-of-4-mn" operands (A of TN, B of NN/TN) use (k = tid / 16, q = tid % 16)
+    const int r4 = tid >> 2, kq = tid & 3, k16 = tid >> 4, q16 = tid & 15;
+    float4 ra, rb;
+    auto fetch = [&](int k0) {
+        ra = make_float4(0.f, 0.f, 0.f, 0.f);
+        rb = ra;
+        if (LAYOUT == kTN) {
+            const int gk = k0 + k16;
+            if (gk < k_end) {
+                if (i0 + 4 * q16 < g.M) ra = ldg4(g.A + (size_t)gk * g.lda + i0 + 4 * q16);
+                if (j0 + 4 * q16 < g.N) {
+                    rb = ldg4(g.B + (size_t)gk * g.ldb + j0 + 4 * q16);
+                    if (PRO) {
+                        const float4 sc = ldg4(g.pro_scale + j0 + 4 * q16), sh = ldg4(g.pro_shift + j0 + 4 * q16);
+                        rb.x = fmaxf(fmaf(rb.x, sc.x, sh.x), 0.f); rb.y = fmaxf(fmaf(rb.y, sc.y, sh.y), 0.f);
+                        rb.z = fmaxf(fmaf(rb.z, sc.z, sh.z), 0.f); rb.w = fmaxf(fmaf(rb.w, sc.w, sh.w), 0.f);
+                    }
+                }
+            }
+        } else {
+            const int gk = k0 + 4 * kq;
+            if (i0 + r4 < g.M && gk < k_end) {
+                ra = ldg4(g.A + (size_t)(i0 + r4) * g.lda + gk);
+                if (PRO) {
+                    const float4 sc = ldg4(g.pro_scale + gk), sh = ldg4(g.pro_shift + gk);
+                    ra.x = fmaxf(fmaf(ra.x, sc.x, sh.x), 0.f); ra.y = fmaxf(fmaf(ra.y, sc.y, sh.y), 0.f);
+                    ra.z = fmaxf(fmaf(ra.z, sc.z, sh.z), 0.f); ra.w = fmaxf(fmaf(ra.w, sc.w, sh.w), 0.f);
+                }
+            }
+            if (LAYOUT == kNT) {
+                if (j0 + r4 < g.N && gk < k_end) rb = ldg4(g.B + (size_t)(j0 + r4) * g.ldb + gk);
+            } else {
+                const int gk2 = k0 + k16;
+                if (gk2 < k_end && j0 + 4 * q16 < g.N) rb = ldg4(g.B + (size_t)gk2 * g.ldb + j0 + 4 * q16);
+            }
+        }
+    };
+    auto stash = [&](int buf) {
+        if (LAYOUT == kTN) {
+            *reinterpret_cast<float4*>(&As[buf][k16][4 * q16]) = ra;
+            *reinterpret_cast<float4*>(&Bs[buf][k16][4 * q16]) = rb;
+        } else {
+            As[buf][4 * kq][r4] = ra.x; As[buf][4 * kq + 1][r4] = ra.y; As[buf][4 * kq + 2][r4] = ra.z; As[buf][4 * kq + 3][r4] = ra.w;
+            if (LAYOUT == kNT) {
+                Bs[buf][4 * kq][r4] = rb.x; Bs[buf][4 * kq + 1][r4] = rb.y; Bs[buf][4 * kq + 2][r4] = rb.z; Bs[buf][4 * kq + 3][r4] = rb.w;
+            } else {
+                *reinterpret_cast<float4*>(&Bs[buf][k16][4 * q16]) = rb;
+            }
+        }
+    };
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+    fetch(k_begin);
+    stash(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+        const bool more = k0 + BK < k_end;
+        if (more) fetch(k0 + BK);
+#pragma unroll
+        for (int k = 0; k < BK; k++) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (more) stash(buf ^ 1);
+        __syncthreads();
+        buf ^= 1;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int gi = i0 + ty * 4 + i;
+        const int gj = j0 + tx * 4;
+        if (gi >= g.M || gj >= g.N) continue;
+        float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        if (LAYOUT == kNT && g.bias != nullptr) {
+            const float4 bb = ldg4(g.bias + gj);
+            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+        }
+        *reinterpret_cast<float4*>(C + (size_t)gi * g.ldc + gj) = o;
+    }
+}
+
+static bool gemm_vec_ok(const GemmArgs& g, int layout) {
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    bool ok = g.lda % 4 == 0 && g.ldb % 4 == 0 && g.ldc % 4 == 0 && g.N % 4 == 0 && al(g.A) && al(g.B) && al(g.C) &&
+              (g.bias == nullptr || al(g.bias)) && (g.pro_scale == nullptr || (al(g.pro_scale) && al(g.pro_shift)));
+    if (layout == kTN) ok = ok && g.M % 4 == 0;
+    else ok = ok && g.K % 4 == 0;
+    return ok;
+}
+
+// launches the vectorised kernel when every operand of the batch qualifies, the scalar one otherwise
+template <int LAYOUT, bool PRO>
+static void launch_gemm(const GemmBatch& gb, int nbatch, dim3 grid, cudaStream_t st) {
+    bool vec = true;
+    for (int n = 0; n < nbatch; n++) vec = vec && gemm_vec_ok(gb.a[n], LAYOUT);
+    if (vec) gemm_vec_kernel<LAYOUT, PRO><<<grid, kGemmThreads, 0, st>>>(gb);
+    else gemm_kernel<LAYOUT, PRO><<<grid, kGemmThreads, 0, st>>>(gb);
+}
+
 // ------------------------------------------------------------------------------------------------
 // BatchNorm1d statistics, one block per 32 features, all rows (two-pass: mean, then centred variance).
 // train: scale = w / sqrt(var_b + eps), shift = b - mean_b scale; running stats updated with momentum 0.1
@@ -194,6 +324,76 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(BnBatch batch, int B, int
     }
 }
 
+// Train-mode statistics at full-chip parallelism: grid (H/32, R row chunks, nets).  Every block computes the
+// (count, mean, M2) of its row chunk two-pass from registers; the last block to arrive for a column group
+// merges the R partials in a fixed order with Chan's pairwise update (deterministic, as accurate as the
+// two-pass form) and finalises exactly like bn_stats_kernel.  `ticket` counters return to 0 (graph replay).
+constexpr int kBnRowsPerThread = 8;            // 8 row lanes x 8 rows = 64 rows per block
+__global__ void __launch_bounds__(256)
+bn_stats_split_kernel(BnBatch batch, int B, int H, float* __restrict__ part, unsigned* __restrict__ ticket) {
+    const BnArgs& a = batch.a[blockIdx.z];
+    __shared__ float red[8][33];
+    __shared__ unsigned s_last;
+    const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int f = blockIdx.x * 32 + c;
+    const int R = gridDim.y;
+    const int row0 = blockIdx.y * (8 * kBnRowsPerThread);
+    const int nrows = min(8 * kBnRowsPerThread, B - row0);
+    float x[kBnRowsPerThread];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kBnRowsPerThread; k++) {
+        const int row = row0 + r + 8 * k;
+        x[k] = row < B ? a.z[(size_t)row * H + f] : 0.f;
+        s += x[k];
+    }
+    const float mean_c = block_colsum_32x8(s, red) / (float)nrows;
+    float m2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kBnRowsPerThread; k++) {
+        const int row = row0 + r + 8 * k;
+        const float d = row < B ? x[k] - mean_c : 0.f;
+        m2 = fmaf(d, d, m2);
+    }
+    m2 = block_colsum_32x8(m2, red);
+    float* P = part + ((size_t)blockIdx.z * R + blockIdx.y) * 2 * H;     // [net][chunk][mean | M2][H]
+    if (r == 0) {
+        P[f] = mean_c;
+        P[H + f] = m2;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&ticket[blockIdx.z * gridDim.x + blockIdx.x], 1u);
+        s_last = (t == (unsigned)R - 1u) ? 1u : 0u;
+        if (s_last) ticket[blockIdx.z * gridDim.x + blockIdx.x] = 0u;
+    }
+    __syncthreads();
+    if (!s_last || r != 0) return;
+    __threadfence();
+    const float* Q = part + (size_t)blockIdx.z * R * 2 * H;
+    float n = 0.f, mean = 0.f, M2 = 0.f;
+    for (int k = 0; k < R; k++) {
+        const float nb = (float)min(8 * kBnRowsPerThread, B - k * 8 * kBnRowsPerThread);
+        const float mb = __ldcg(Q + (size_t)k * 2 * H + f), Mb = __ldcg(Q + (size_t)k * 2 * H + H + f);
+        const float nn = n + nb, delta = mb - mean;
+        mean = fmaf(delta, nb / nn, mean);
+        M2 = M2 + Mb + delta * delta * (n * nb / nn);
+        n = nn;
+    }
+    const float var = M2 / (float)B;
+    const float unbiased = B > 1 ? M2 / (float)(B - 1) : var;
+    a.run_mean[f] = fmaf(kBnMomentum, mean - a.run_mean[f], a.run_mean[f]);
+    a.run_var[f] = fmaf(kBnMomentum, unbiased - a.run_var[f], a.run_var[f]);
+    if (blockIdx.x == 0 && c == 0 && a.batches != nullptr) *a.batches += 1;
+    const float rstd = 1.f / sqrtf(var + kBnEps);
+    const float sc = a.w[f] * rstd;
+    a.scale[f] = sc;
+    a.shift[f] = fmaf(-mean, sc, a.b[f]);
+    a.mean[f] = mean;
+    a.rstd[f] = rstd;
+}
+
 // ------------------------------------------------------------------------------------------------
 // BN + ReLU backward, column owned: g = da * [z scale + shift > 0]; dgamma = sum g xhat; dbeta = sum g;
 // dz = w rstd (g - dbeta/B - xhat dgamma/B) written in place over da; dbias(linear) = sum dz.
@@ -236,21 +436,100 @@ bn_relu_backward_kernel(float* __restrict__ da, const float* __restrict__ z, con
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Philox4x32-10 + Box-Muller for the exploration noise (replaces MultivariateNormal.sample())
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+// The same backward at full-chip parallelism.  Pass 1 (grid (H/32, R)): per-chunk column sums of g, g xhat and
+// (z - mean); the last block of a column group adds the R partials in a fixed order and leaves the per-column
+// coefficients of dz = k1 g - cB - cC (z - mean):  k1 = w rstd, cB = k1 sum(g)/B, cC = k1 rstd sum(g xhat)/B.
+// Pass 2 (elementwise, float4): da <- dz in place.
+struct BnBwdCoef {
+    float *k1, *cB, *cC;        // [H] each
+};
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict__ z, const float* __restrict__ w,
+                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, int B, int H, float* __restrict__ part, unsigned* __restrict__ ticket,
+                     BnBwdCoef coef, float* __restrict__ d_w, float* __restrict__ d_b, float* __restrict__ d_lin_bias) {
+    __shared__ float red[8][33];
+    __shared__ unsigned s_last;
+    const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int f = blockIdx.x * 32 + c;
+    const int R = gridDim.y;
+    const int row0 = blockIdx.y * (8 * kBnRowsPerThread);
+    const float sc = scale[f], sh = shift[f], mu = mean[f], rs = rstd[f];
+    float sg = 0.f, sgx = 0.f, sz = 0.f;
 #pragma unroll
-    for (int r = 0; r < 10; r++) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
-        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    for (int k = 0; k < kBnRowsPerThread; k++) {
+        const int row = row0 + r + 8 * k;
+        if (row < B) {
+            const size_t idx = (size_t)row * H + f;
+            const float zz = z[idx];
+            const float g = fmaf(zz, sc, sh) > 0.f ? da[idx] : 0.f;
+            sg += g;
+            sgx = fmaf(g, (zz - mu) * rs, sgx);
+            sz += zz - mu;
+        }
+    }
+    sg = block_colsum_32x8(sg, red);
+    sgx = block_colsum_32x8(sgx, red);
+    sz = block_colsum_32x8(sz, red);
+    float* P = part + (size_t)blockIdx.y * 3 * H;
+    if (r == 0) {
+        P[f] = sg;
+        P[H + f] = sgx;
+        P[2 * H + f] = sz;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&ticket[blockIdx.x], 1u);
+        s_last = (t == (unsigned)R - 1u) ? 1u : 0u;
+        if (s_last) ticket[blockIdx.x] = 0u;
+    }
+    __syncthreads();
+    if (!s_last || r != 0) return;
+    __threadfence();
+    float tg = 0.f, tgx = 0.f, tz = 0.f;
+    for (int k = 0; k < R; k++) {
+        tg += __ldcg(part + (size_t)k * 3 * H + f);
+        tgx += __ldcg(part + (size_t)k * 3 * H + H + f);
+        tz += __ldcg(part + (size_t)k * 3 * H + 2 * H + f);
+    }
+    const float k1 = w[f] * rs, c1 = tg / (float)B, c2 = tgx / (float)B;
+    coef.k1[f] = k1;
+    coef.cB[f] = k1 * c1;
+    coef.cC[f] = k1 * c2 * rs;
+    d_w[f] = tgx;
+    d_b[f] = tg;
+    // sum over rows of dz: analytically 0, numerically the rounding residue (as in the reference's autograd)
+    d_lin_bias[f] = k1 * (tg - (float)B * c1) - k1 * c2 * rs * tz;
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(float* __restrict__ da, const float* __restrict__ z, const float* __restrict__ scale,
+                    const float* __restrict__ shift, const float* __restrict__ mean, BnBwdCoef coef, int B, int H) {
+    const size_t n4 = (size_t)B * H / 4;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+        const int f = (int)((i * 4) % H);
+        const float4 zz = reinterpret_cast<const float4*>(z)[i];
+        float4 g = reinterpret_cast<float4*>(da)[i];
+        const float4 sc = *reinterpret_cast<const float4*>(scale + f), sh = *reinterpret_cast<const float4*>(shift + f);
+        const float4 mu = *reinterpret_cast<const float4*>(mean + f), k1 = *reinterpret_cast<const float4*>(coef.k1 + f);
+        const float4 cB = *reinterpret_cast<const float4*>(coef.cB + f), cC = *reinterpret_cast<const float4*>(coef.cC + f);
+        g.x = fmaf(zz.x, sc.x, sh.x) > 0.f ? g.x : 0.f;
+        g.y = fmaf(zz.y, sc.y, sh.y) > 0.f ? g.y : 0.f;
+        g.z = fmaf(zz.z, sc.z, sh.z) > 0.f ? g.z : 0.f;
+        g.w = fmaf(zz.w, sc.w, sh.w) > 0.f ? g.w : 0.f;
+        float4 o;
+        o.x = fmaf(k1.x, g.x, -cB.x) - cC.x * (zz.x - mu.x);
+        o.y = fmaf(k1.y, g.y, -cB.y) - cC.y * (zz.y - mu.y);
+        o.z = fmaf(k1.z, g.z, -cB.z) - cC.z * (zz.z - mu.z);
+        o.w = fmaf(k1.w, g.w, -cB.w) - cC.w * (zz.w - mu.w);
+        reinterpret_cast<float4*>(da)[i] = o;
     }
 }
-__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (philox.cuh) + Box-Muller for the exploration noise (replaces MultivariateNormal.sample())
+// ------------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------------
 // Fused head: a2 = relu(bn2(z2)); [mu | V | L-entries] = a2 Wh^T + bh; mu = tanh, l_kk = tanh;
 // P_kk = exp(2 l_kk); Q = V - 1/2 sum_k P_kk (u_k - mu_k)^2; TD error; gradients of the head
@@ -269,7 +548,7 @@ struct HeadArgs {
     // training (main net): y_in -> loss partial + dZh
     const float* y_in; float* dzh; float* loss_part;
     // act mode
-    float* act_out; unsigned long long seed, step; float noise_scale;
+    float* act_out; unsigned long long seed, step; const unsigned long long* step_offset; float noise_scale;
 };
 
 constexpr int kHeadWarps = 8;
@@ -370,7 +649,8 @@ __global__ void __launch_bounds__(kHeadWarps * 32) naf_head_kernel(HeadArgs h) {
         }
         if (h.act_out != nullptr && lane < A) {
             // action ~ N(mu, P^-1) with diagonal P: std_k = exp(-l_kk); clamp to [-1, 1]
-            uint32_t c[4] = {(uint32_t)row, (uint32_t)lane, (uint32_t)h.step, (uint32_t)(h.step >> 32)};
+            const unsigned long long stp = h.step + (h.step_offset != nullptr ? *h.step_offset : 0ull);
+            uint32_t c[4] = {(uint32_t)row, (uint32_t)lane, (uint32_t)stp, (uint32_t)(stp >> 32)};
             philox4x32_10(c, (uint32_t)h.seed, (uint32_t)(h.seed >> 32));
             const float r = sqrtf(-2.f * logf(u01(c[0])));
             const float eps = r * cospif(2.f * u01(c[1]));
@@ -539,6 +819,9 @@ struct rloa_naf_ws {
     float *scale[2][2], *shift[2][2], *mean[2][2], *rstd[2][2];   // [net][layer]
     float *dzh, *da, *y, *loss_part, *splitk, *sq_partial, *wh_pack;
     float *v_tmp;
+    float *bn_part;              // [2 nets][R][2][H] chunk statistics / [R][3][H] backward partial sums
+    float *bwd_coef;             // [3][H] k1, cB, cC of the BatchNorm backward
+    unsigned* tickets;           // [2 * H / 32] last-block-done counters (always return to 0)
     size_t splitk_floats;
     int n_loss_parts;
     TrunkTC tc;                  // tcgen05 trunk state
@@ -581,6 +864,8 @@ extern "C" int rloa_naf_num_params(int32_t S, int32_t A, int32_t H) {
 }
 
 static int splitk_len(int B) { return 128; }
+static int bn_chunks(int B) { return (B + 8 * kBnRowsPerThread - 1) / (8 * kBnRowsPerThread); }
+constexpr int kBnSplitMinBatch = 128;    // below this the single-block-per-column kernels are already short
 static int splitk_count(int B) { return (B + splitk_len(B) - 1) / splitk_len(B); }
 
 extern "C" int rloa_naf_ws_create(int32_t S, int32_t A, int32_t H, int32_t max_batch, rloa_naf_ws** out) {
@@ -599,7 +884,8 @@ extern "C" int rloa_naf_ws_create(int32_t S, int32_t A, int32_t H, int32_t max_b
     size_t total = 4 * BH            // z1[2], z2[2]
                    + 16 * (size_t)H  // scale/shift/mean/rstd [2][2]
                    + (size_t)max_batch * ws->NH + BH + 2 * (size_t)max_batch + ws->n_loss_parts + ws->splitk_floats +
-                   kNormBlocks + (size_t)ws->NH * H;
+                   kNormBlocks + (size_t)ws->NH * H +
+                   (size_t)bn_chunks(max_batch) * 4 * H + 3 * (size_t)H + 2 * (size_t)(H / 32);
     if (cudaMalloc(&ws->block, total * sizeof(float)) != cudaSuccess) {
         set_error("rloa_naf_ws_create: cudaMalloc of %zu bytes failed: %s", total * sizeof(float),
                   cudaGetErrorString(cudaGetLastError()));
@@ -620,6 +906,10 @@ extern "C" int rloa_naf_ws_create(int32_t S, int32_t A, int32_t H, int32_t max_b
     ws->splitk = p; p += ws->splitk_floats;
     ws->sq_partial = p; p += kNormBlocks;
     ws->wh_pack = p; p += (size_t)ws->NH * H;
+    ws->bn_part = p; p += (size_t)bn_chunks(max_batch) * 4 * H;
+    ws->bwd_coef = p; p += 3 * (size_t)H;
+    ws->tickets = reinterpret_cast<unsigned*>(p); p += 2 * (size_t)(H / 32);
+    cudaMemset(ws->tickets, 0, 2 * (size_t)(H / 32) * sizeof(unsigned));
     const int hb = (ws->NH * (H + 1) + ((ws->NH + 31) & ~31) + kHeadWarps * H) * (int)sizeof(float);
     if (hb > 48 * 1024) cudaFuncSetAttribute(naf_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
     trunk_tc_init(&ws->tc);
@@ -671,9 +961,12 @@ static int trunk_forward(rloa_naf_ws* ws, int nets, const rloa_naf_params* const
                          ws->scale[n][0], ws->shift[n][0], ws->mean[n][0], ws->rstd[n][0]};
     }
     dim3 grid((H + BN - 1) / BN, (B + BM - 1) / BM, nets);
-    gemm_kernel<kNT, false><<<grid, kGemmThreads, 0, st>>>(gb);
+    launch_gemm<kNT, false>(gb, nets, grid, st);
     RLOA_LAUNCHED();
-    bn_stats_kernel<<<dim3(H / 32, nets), 256, 0, st>>>(bb, B, H, train);
+    if (train && B >= kBnSplitMinBatch)
+        bn_stats_split_kernel<<<dim3(H / 32, bn_chunks(B), nets), 256, 0, st>>>(bb, B, H, ws->bn_part, ws->tickets);
+    else
+        bn_stats_kernel<<<dim3(H / 32, nets), 256, 0, st>>>(bb, B, H, train);
     RLOA_LAUNCHED();
     if (ws->trunk_mode == 1) {
         const float *z1p[2], *scp[2], *shp[2], *w2p[2], *b2p[2];
@@ -687,13 +980,16 @@ static int trunk_forward(rloa_naf_ws* ws, int nets, const rloa_naf_params* const
     } else {
         for (int n = 0; n < nets; n++)
             gb.a[n] = GemmArgs{ws->z1[n], H, P[n]->w2, H, ws->z2[n], H, P[n]->b2, ws->scale[n][0], ws->shift[n][0], B, H, H, 0};
-        gemm_kernel<kNT, true><<<grid, kGemmThreads, 0, st>>>(gb);
+        launch_gemm<kNT, true>(gb, nets, grid, st);
         RLOA_LAUNCHED();
     }
     for (int n = 0; n < nets; n++)
         bb.a[n] = BnArgs{ws->z2[n], P[n]->bn2_w, P[n]->bn2_b, P[n]->bn2_mean, P[n]->bn2_var, P[n]->bn2_batches,
                          ws->scale[n][1], ws->shift[n][1], ws->mean[n][1], ws->rstd[n][1]};
-    bn_stats_kernel<<<dim3(H / 32, nets), 256, 0, st>>>(bb, B, H, train);
+    if (train && B >= kBnSplitMinBatch)
+        bn_stats_split_kernel<<<dim3(H / 32, bn_chunks(B), nets), 256, 0, st>>>(bb, B, H, ws->bn_part, ws->tickets);
+    else
+        bn_stats_kernel<<<dim3(H / 32, nets), 256, 0, st>>>(bb, B, H, train);
     RLOA_LAUNCHED();
     return RLOA_OK;
 }
@@ -707,7 +1003,7 @@ extern "C" int rloa_naf_hidden_layer(rloa_naf_ws* ws, const float* z1, const flo
     if (ws->trunk_mode == 1) return trunk_tc_layer2(&ws->tc, 1, &z1, &scale, &shift, &w2, &b2, &z2, batch, H, st);
     GemmBatch gb{};
     gb.a[0] = GemmArgs{z1, H, w2, H, z2, H, b2, scale, shift, batch, H, H, 0};
-    gemm_kernel<kNT, true><<<dim3((H + BN - 1) / BN, (batch + BM - 1) / BM, 1), kGemmThreads, 0, st>>>(gb);
+    launch_gemm<kNT, true>(gb, 1, dim3((H + BN - 1) / BN, (batch + BM - 1) / BM, 1), st);
     RLOA_LAUNCHED();
     return RLOA_OK;
 }
@@ -747,7 +1043,8 @@ extern "C" int rloa_naf_forward(rloa_naf_ws* ws, const rloa_naf_params* p, const
 }
 
 extern "C" int rloa_naf_act(rloa_naf_ws* ws, const rloa_naf_params* p, const float* states, int32_t batch,
-                            uint64_t seed, uint64_t step, float noise_scale, float* actions, void* stream) {
+                            uint64_t seed, uint64_t step, const uint64_t* step_offset, float noise_scale,
+                            float* actions, void* stream) {
     RLOA_REQUIRE(ws != nullptr && states != nullptr && actions != nullptr, "rloa_naf_act: null argument");
     RLOA_REQUIRE(batch >= 1 && batch <= ws->max_batch, "rloa_naf_act: batch exceeds the workspace");
     int rc = check_params(ws, p, "rloa_naf_act");
@@ -759,7 +1056,30 @@ extern "C" int rloa_naf_act(rloa_naf_ws* ws, const rloa_naf_params* p, const flo
     if (rc != RLOA_OK) return rc;
     HeadArgs h = head_base(ws, 0, p, batch);
     h.act_out = actions; h.seed = seed; h.step = step; h.noise_scale = noise_scale;
+    h.step_offset = reinterpret_cast<const unsigned long long*>(step_offset);
     naf_head_kernel<<<head_blocks(batch), kHeadWarps * 32, head_smem_bytes(ws), st>>>(h);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
+// ReLU + BatchNorm backward of the main net's layer `layer` (0 / 1): da -> dz in place, gamma / beta / linear-bias grads
+static int bn_relu_backward(rloa_naf_ws* ws, float* da, const float* z, const float* bn_w, int layer, int B, float* d_w,
+                            float* d_b, float* d_lin_bias, cudaStream_t st) {
+    const int H = ws->H;
+    if (B < kBnSplitMinBatch) {
+        bn_relu_backward_kernel<<<H / 32, 256, 0, st>>>(da, z, bn_w, ws->scale[0][layer], ws->shift[0][layer],
+                                                        ws->mean[0][layer], ws->rstd[0][layer], B, H, d_w, d_b, d_lin_bias);
+        RLOA_LAUNCHED();
+        return RLOA_OK;
+    }
+    BnBwdCoef coef{ws->bwd_coef, ws->bwd_coef + H, ws->bwd_coef + 2 * H};
+    bn_bwd_reduce_kernel<<<dim3(H / 32, bn_chunks(B)), 256, 0, st>>>(da, z, bn_w, ws->scale[0][layer], ws->shift[0][layer],
+                                                                     ws->mean[0][layer], ws->rstd[0][layer], B, H, ws->bn_part,
+                                                                     ws->tickets, coef, d_w, d_b, d_lin_bias);
+    RLOA_LAUNCHED();
+    const int blocks = (int)(((size_t)B * H / 4 + 255) / 256);
+    bn_bwd_apply_kernel<<<blocks < 1184 ? blocks : 1184, 256, 0, st>>>(da, z, ws->scale[0][layer], ws->shift[0][layer],
+                                                                       ws->mean[0][layer], coef, B, H);
     RLOA_LAUNCHED();
     return RLOA_OK;
 }
@@ -810,33 +1130,29 @@ extern "C" int rloa_naf_learn_grads(rloa_naf_ws* ws, const rloa_naf_params* mn, 
     GemmBatch gb{};
     // dWh [NH][H] = dZh^T a2, a2 = relu(bn2(z2)) re-created in the prologue
     gb.a[0] = GemmArgs{ws->dzh, NH, ws->z2[0], H, part_wh, H, nullptr, ws->scale[0][1], ws->shift[0][1], NH, H, B, klen};
-    gemm_kernel<kTN, true><<<dim3((H + BN - 1) / BN, (NH + BM - 1) / BM, nsplit), kGemmThreads, 0, st>>>(gb);
+    launch_gemm<kTN, true>(gb, 1, dim3((H + BN - 1) / BN, (NH + BM - 1) / BM, nsplit), st);
     RLOA_LAUNCHED();
     // da2 [B][H] = dZh Wh
     gb.a[0] = GemmArgs{ws->dzh, NH, ws->wh_pack, H, ws->da, H, nullptr, nullptr, nullptr, B, H, NH, 0};
-    gemm_kernel<kNN, false><<<dim3((H + BN - 1) / BN, (B + BM - 1) / BM, 1), kGemmThreads, 0, st>>>(gb);
+    launch_gemm<kNN, false>(gb, 1, dim3((H + BN - 1) / BN, (B + BM - 1) / BM, 1), st);
     RLOA_LAUNCHED();
     // through ReLU + BN2: da -> dz2 in place; bn2 weight/bias and hidden_layer.bias gradients
-    bn_relu_backward_kernel<<<H / 32, 256, 0, st>>>(ws->da, ws->z2[0], mn->bn2_w, ws->scale[0][1], ws->shift[0][1],
-                                                    ws->mean[0][1], ws->rstd[0][1], B, H, grad + fl.bn2w, grad + fl.bn2b,
-                                                    grad + fl.b2);
-    RLOA_LAUNCHED();
+    rc = bn_relu_backward(ws, ws->da, ws->z2[0], mn->bn2_w, 1, B, grad + fl.bn2w, grad + fl.bn2b, grad + fl.b2, st);
+    if (rc != RLOA_OK) return rc;
     // dW2 [H][H] = dz2^T a1, a1 = relu(bn1(z1))
     gb.a[0] = GemmArgs{ws->da, H, ws->z1[0], H, part_w2, H, nullptr, ws->scale[0][0], ws->shift[0][0], H, H, B, klen};
-    gemm_kernel<kTN, true><<<dim3((H + BN - 1) / BN, (H + BM - 1) / BM, nsplit), kGemmThreads, 0, st>>>(gb);
+    launch_gemm<kTN, true>(gb, 1, dim3((H + BN - 1) / BN, (H + BM - 1) / BM, nsplit), st);
     RLOA_LAUNCHED();
     // da1 [B][H] = dz2 W2 -> reuse z2[1] (the target's z2 is no longer needed) as the output buffer
     float* da1 = ws->z2[1];
     gb.a[0] = GemmArgs{ws->da, H, mn->w2, H, da1, H, nullptr, nullptr, nullptr, B, H, H, 0};
-    gemm_kernel<kNN, false><<<dim3((H + BN - 1) / BN, (B + BM - 1) / BM, 1), kGemmThreads, 0, st>>>(gb);
+    launch_gemm<kNN, false>(gb, 1, dim3((H + BN - 1) / BN, (B + BM - 1) / BM, 1), st);
     RLOA_LAUNCHED();
-    bn_relu_backward_kernel<<<H / 32, 256, 0, st>>>(da1, ws->z1[0], mn->bn1_w, ws->scale[0][0], ws->shift[0][0],
-                                                    ws->mean[0][0], ws->rstd[0][0], B, H, grad + fl.bn1w, grad + fl.bn1b,
-                                                    grad + fl.b1);
-    RLOA_LAUNCHED();
+    rc = bn_relu_backward(ws, da1, ws->z1[0], mn->bn1_w, 0, B, grad + fl.bn1w, grad + fl.bn1b, grad + fl.b1, st);
+    if (rc != RLOA_OK) return rc;
     // dW1 [H][S] = dz1^T x
     gb.a[0] = GemmArgs{da1, H, states, S, part_w1, S, nullptr, nullptr, nullptr, H, S, B, klen};
-    gemm_kernel<kTN, false><<<dim3((S + BN - 1) / BN, (H + BM - 1) / BM, nsplit), kGemmThreads, 0, st>>>(gb);
+    launch_gemm<kTN, false>(gb, 1, dim3((S + BN - 1) / BN, (H + BM - 1) / BM, nsplit), st);
     RLOA_LAUNCHED();
     // fixed-order reduction of the split-K partials into the flat gradient
     ReduceArgs ra{};

@@ -9,7 +9,7 @@
 
 namespace rloa {
 
-constexpr int kAppendRows = 1024;      // rows per block in the compaction scan
+constexpr int kAppendRows = 256;       // transition rows per block
 
 __global__ void __launch_bounds__(kAppendRows) replay_count_kernel(const uint8_t* __restrict__ valid, int n,
                                                                    int* __restrict__ block_counts) {
@@ -19,67 +19,83 @@ __global__ void __launch_bounds__(kAppendRows) replay_count_kernel(const uint8_t
     if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
 }
 
-// one warp per transition row inside a 1024-row block; rank = exclusive scan of the valid flags
+// Block = 256 transition rows.  rank = (valid rows of earlier blocks) + exclusive scan of the valid flags; the
+// copies are flat loops over the block's [256][S] / [256][A] sub-matrices (coalesced reads, and coalesced writes
+// because ranks of neighbouring rows are consecutive).  The last block to finish bumps the cursor: every block
+// reads the cursor before it takes its ticket, so the bump cannot overtake a reader.
 __global__ void __launch_bounds__(kAppendRows)
 replay_append_kernel(rloa_replay rb, int n, const float* __restrict__ states, const float* __restrict__ actions,
                      const float* __restrict__ rewards, const float* __restrict__ next_states,
                      const uint8_t* __restrict__ dones, const uint8_t* __restrict__ valid,
-                     const int* __restrict__ block_counts) {
-    __shared__ int warp_sums[32];
-    __shared__ int s_base;
+                     const int* __restrict__ block_counts, unsigned* __restrict__ ticket) {
+    __shared__ int warp_sums[kAppendRows / 32];
+    __shared__ int s_slot[kAppendRows];
+    __shared__ int s_red[kAppendRows / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int i = blockIdx.x * kAppendRows + tid;
+    const int row0 = blockIdx.x * kAppendRows;
+    const int i = row0 + tid;
     const bool v = i < n && (valid == nullptr || valid[i] != 0);
-    // block-level exclusive scan of v
+    const long long cur = *reinterpret_cast<const volatile long long*>(rb.cursor);
+    // valid rows of the earlier blocks / of all blocks
+    int before = 0, total = 0;
+    if (valid != nullptr) {
+        for (int b = tid; b < (int)gridDim.x; b += kAppendRows) {
+            const int cnt = block_counts[b];
+            total += cnt;
+            if (b < (int)blockIdx.x) before += cnt;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            before += __shfl_xor_sync(0xffffffffu, before, off);
+            total += __shfl_xor_sync(0xffffffffu, total, off);
+        }
+        if (lane == 0) { warp_sums[warp] = before; s_red[warp] = total; }
+        __syncthreads();
+        before = 0; total = 0;
+        for (int w = 0; w < kAppendRows / 32; w++) { before += warp_sums[w]; total += s_red[w]; }
+        __syncthreads();
+    } else {
+        before = row0;
+        total = n;
+    }
     const unsigned bal = __ballot_sync(0xffffffffu, v);
     const int in_warp = __popc(bal & ((1u << lane) - 1u));
     if (lane == 0) warp_sums[warp] = __popc(bal);
-    if (tid == 0) {
-        int base = 0;
-        if (valid != nullptr) for (int b = 0; b < (int)blockIdx.x; b++) base += block_counts[b];
-        else base = blockIdx.x * kAppendRows;
-        s_base = base;
-    }
     __syncthreads();
-    if (warp == 0) {
-        int x = warp_sums[lane];
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, x, off);
-            if (lane >= off) x += y;
-        }
-        warp_sums[lane] = x - warp_sums[lane];      // exclusive
-    }
+    int wbase = 0;
+    for (int w = 0; w < warp; w++) wbase += warp_sums[w];
+    const int rank = before + wbase + in_warp;
+    s_slot[tid] = v ? (int)((cur + rank) % rb.capacity) : -1;
     __syncthreads();
-    const int rank = s_base + warp_sums[warp] + in_warp;
-    const long long cur = *rb.cursor;
     const int S = rb.state_size, A = rb.action_size;
-    // every lane of the warp helps copy each valid row of the warp (coalesced S/A-float rows)
-    for (int src_lane = 0; src_lane < 32; src_lane++) {
-        const bool sv = __shfl_sync(0xffffffffu, (int)v, src_lane) != 0;
-        if (!sv) continue;
-        const int row = blockIdx.x * kAppendRows + warp * 32 + src_lane;
-        const int rrank = __shfl_sync(0xffffffffu, rank, src_lane);
-        const size_t slot = (size_t)((cur + rrank) % rb.capacity);
-        for (int k = lane; k < S; k += 32) {
-            rb.states[slot * S + k] = states[(size_t)row * S + k];
-            rb.next_states[slot * S + k] = next_states[(size_t)row * S + k];
-        }
-        for (int k = lane; k < A; k += 32) rb.actions[slot * A + k] = actions[(size_t)row * A + k];
-        if (lane == 0) {
-            rb.rewards[slot] = rewards[row];
-            rb.dones[slot] = dones != nullptr ? (float)dones[row] : 0.f;
+    const int rows = min(kAppendRows, n - row0);
+    for (int e = tid; e < rows * S; e += kAppendRows) {
+        const int r = e / S, k = e - r * S;
+        const int slot = s_slot[r];
+        if (slot >= 0) {
+            rb.states[(size_t)slot * S + k] = states[(size_t)row0 * S + e];
+            rb.next_states[(size_t)slot * S + k] = next_states[(size_t)row0 * S + e];
         }
     }
-}
-
-__global__ void replay_cursor_bump_kernel(long long* cursor, const int* __restrict__ block_counts, int nblocks, int n_all) {
-    long long add = n_all;
-    if (block_counts != nullptr) {
-        add = 0;
-        for (int b = 0; b < nblocks; b++) add += block_counts[b];
+    for (int e = tid; e < rows * A; e += kAppendRows) {
+        const int r = e / A, k = e - r * A;
+        const int slot = s_slot[r];
+        if (slot >= 0) rb.actions[(size_t)slot * A + k] = actions[(size_t)row0 * A + e];
     }
-    *cursor += add;
+    if (v) {
+        const int slot = s_slot[tid];
+        rb.rewards[slot] = rewards[i];
+        rb.dones[slot] = dones != nullptr ? (float)dones[i] : 0.f;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1u) {
+            *ticket = 0u;
+            *reinterpret_cast<long long*>(rb.cursor) = cur + total;
+        }
+    }
 }
 
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
@@ -99,11 +115,12 @@ __device__ __forceinline__ uint32_t feistel(uint32_t x, int bits, uint32_t k0, u
 }
 
 __global__ void __launch_bounds__(256)
-replay_sample_kernel(rloa_replay rb, int batch, unsigned long long seed, unsigned long long draw,
-                     float* __restrict__ states, float* __restrict__ actions, float* __restrict__ rewards,
+replay_sample_kernel(rloa_replay rb, int batch, unsigned long long seed, unsigned long long draw0,
+                     const unsigned long long* __restrict__ draw_offset, float* __restrict__ states, float* __restrict__ actions, float* __restrict__ rewards,
                      float* __restrict__ next_states, float* __restrict__ dones, int* __restrict__ indices) {
     const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= batch) return;
+    const unsigned long long draw = draw0 + (draw_offset != nullptr ? *draw_offset : 0ull);
     const long long cur = *rb.cursor;
     const uint32_t live = (uint32_t)(cur < rb.capacity ? cur : rb.capacity);
     if (live == 0) return;
@@ -150,31 +167,30 @@ extern "C" int rloa_replay_append(const rloa_replay* rb, int32_t n, const float*
     if (rc != RLOA_OK) return rc;
     RLOA_REQUIRE(n >= 1 && states && actions && rewards && next_states, "rloa_replay_append: null argument");
     RLOA_REQUIRE(n <= rb->capacity, "rloa_replay_append: more transitions than the ring holds in one call");
-    RLOA_REQUIRE(valid == nullptr || rb->scratch != nullptr, "rloa_replay_append: a valid mask needs rb->scratch");
     cudaStream_t st = as_stream(stream);
     const int nblocks = (n + kAppendRows - 1) / kAppendRows;
+    RLOA_REQUIRE(rb->scratch != nullptr, "rloa_replay_append: rb->scratch is required");
     if (valid != nullptr) {
-        replay_count_kernel<<<nblocks, kAppendRows, 0, st>>>(valid, n, rb->scratch);
+        replay_count_kernel<<<nblocks, kAppendRows, 0, st>>>(valid, n, rb->scratch + 1);
         RLOA_LAUNCHED();
     }
+    // scratch[0] = ticket counter (zero at rest), scratch[1..] = per-block valid counts
     replay_append_kernel<<<nblocks, kAppendRows, 0, st>>>(*rb, n, states, actions, rewards, next_states, dones, valid,
-                                                         rb->scratch);
-    RLOA_LAUNCHED();
-    replay_cursor_bump_kernel<<<1, 1, 0, st>>>(reinterpret_cast<long long*>(rb->cursor),
-                                               valid != nullptr ? rb->scratch : nullptr, nblocks, n);
+                                                         rb->scratch + 1, reinterpret_cast<unsigned*>(rb->scratch));
     RLOA_LAUNCHED();
     return RLOA_OK;
 }
 
-extern "C" int rloa_replay_sample(const rloa_replay* rb, int32_t batch, uint64_t seed, uint64_t draw, float* states,
-                                  float* actions, float* rewards, float* next_states, float* dones, int32_t* indices,
-                                  void* stream) {
+extern "C" int rloa_replay_sample(const rloa_replay* rb, int32_t batch, uint64_t seed, uint64_t draw,
+                                  const uint64_t* draw_offset, float* states, float* actions, float* rewards,
+                                  float* next_states, float* dones, int32_t* indices, void* stream) {
     int rc = check_rb(rb, "rloa_replay_sample");
     if (rc != RLOA_OK) return rc;
     RLOA_REQUIRE(batch >= 1 && states && actions && rewards && next_states, "rloa_replay_sample: null argument");
     const int blocks = (batch * 32 + 255) / 256;
-    replay_sample_kernel<<<blocks, 256, 0, as_stream(stream)>>>(*rb, batch, seed, draw, states, actions, rewards,
-                                                               next_states, dones, indices);
+    replay_sample_kernel<<<blocks, 256, 0, as_stream(stream)>>>(*rb, batch, seed, draw,
+                                                               reinterpret_cast<const unsigned long long*>(draw_offset),
+                                                               states, actions, rewards, next_states, dones, indices);
     RLOA_LAUNCHED();
     return RLOA_OK;
 }

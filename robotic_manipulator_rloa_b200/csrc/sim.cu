@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "philox.cuh"
 #include "sim_device.cuh"
 
 namespace rloa {
@@ -271,6 +272,32 @@ __global__ void sim_begin_reset_kernel(SimArrays S, const uint8_t* __restrict__ 
     S.reset_left[env] = nsub;
 }
 
+// the same with the start pose drawn on the device: target_j = pos_j + var_j * U(-1, 1), Philox keyed by
+// (seed, tick, env, j) — random.uniform(pos - var, pos + var) of environment.py:288 for every masked env
+__global__ void sim_begin_reset_random_kernel(SimArrays S, const uint8_t* __restrict__ mask, const float* __restrict__ pos,
+                                              const float* __restrict__ var, int n_init, int nsub, float pos_maximp,
+                                              unsigned long long seed, const unsigned long long* __restrict__ tick) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= S.n_envs) return;
+    if (mask != nullptr && mask[env] == 0) return;
+    const size_t N = (size_t)S.n_envs;
+    const unsigned long long t = tick != nullptr ? *tick : 0ull;
+    for (int j0 = 0; j0 < n_init; j0 += 4) {
+        uint32_t c[4] = {(uint32_t)env, (uint32_t)(j0 >> 2), (uint32_t)t, (uint32_t)(t >> 32)};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x52455345u);
+        for (int k = 0; k < 4 && j0 + k < n_init; k++) {
+            const int j = j0 + k;
+            const size_t at = (size_t)j * N + env;
+            const float v = var != nullptr ? var[j] : 0.f;
+            S.kp[at] = 0.1f;
+            S.tpos[at] = fmaf(v, 2.f * u01(c[k]) - 1.f, pos != nullptr ? pos[j] : 0.f);
+            S.tvel[at] = 0.f;
+            S.maximp[at] = pos_maximp;
+        }
+    }
+    S.reset_left[env] = nsub;
+}
+
 // [N][nl] (C ABI layout) <-> [nl][N] (device layout)
 __global__ void sim_scatter_kernel(int n_envs, int nl, const float* __restrict__ src, float* __restrict__ dst) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -301,8 +328,10 @@ __global__ void episode_update_kernel(int n, int frames, const float* __restrict
                                       float* __restrict__ score, int* __restrict__ frame, uint8_t* __restrict__ reset_mask,
                                       float* __restrict__ log_score, int* __restrict__ log_frame,
                                       float* __restrict__ log_last, int* __restrict__ log_env, int log_cap,
-                                      int* __restrict__ log_count, unsigned long long* __restrict__ transitions) {
+                                      int* __restrict__ log_count, unsigned long long* __restrict__ transitions,
+                                      unsigned long long* __restrict__ tick) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0 && tick != nullptr) *tick += 1ull;
     const bool live = e < n && (active == nullptr || active[e] != 0);
     const int nlive = __syncthreads_count(live);
     if (threadIdx.x == 0 && transitions != nullptr && nlive > 0) atomicAdd(transitions, (unsigned long long)nlive);
@@ -645,6 +674,19 @@ extern "C" int rloa_sim_begin_reset(rloa_sim* s, const uint8_t* mask, const floa
     return RLOA_OK;
 }
 
+extern "C" int rloa_sim_begin_reset_random(rloa_sim* s, const uint8_t* mask, const float* pos, const float* var,
+                                           int32_t n_init, int32_t n_substeps, uint64_t seed, const uint64_t* tick,
+                                           void* stream) {
+    RLOA_REQUIRE(s != nullptr, "rloa_sim_begin_reset_random: null sim");
+    RLOA_REQUIRE(n_init >= 0 && n_init <= s->a.nl, "rloa_sim_begin_reset_random: n_init out of range");
+    RLOA_REQUIRE(n_substeps >= 0, "rloa_sim_begin_reset_random: n_substeps < 0");
+    sim_begin_reset_random_kernel<<<(unsigned)((s->a.n_envs + 255) / 256), 256, 0, as_stream(stream)>>>(
+        s->a, mask, pos, var, n_init, n_substeps, 100000.f * s->model->host.dt, seed,
+        reinterpret_cast<const unsigned long long*>(tick));
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
 extern "C" int rloa_sim_reset(rloa_sim* s, const uint8_t* mask, const float* init_targets, int32_t n_init,
                               int32_t n_substeps, float* obs, void* stream) {
     const int rc = rloa_sim_begin_reset(s, mask, init_targets, n_init, n_substeps, stream);
@@ -682,13 +724,15 @@ extern "C" int rloa_sim_last_iterations(const rloa_sim* s, int32_t* iters, void*
 extern "C" int rloa_episode_update(int32_t n_envs, int32_t frames, const float* reward, const uint8_t* done,
                                    const uint8_t* active, float* score, int32_t* frame, uint8_t* reset_mask,
                                    float* log_score, int32_t* log_frame, float* log_last_reward, int32_t* log_env,
-                                   int32_t log_capacity, int32_t* log_count, int64_t* transitions, void* stream) {
+                                   int32_t log_capacity, int32_t* log_count, int64_t* transitions, uint64_t* tick,
+                                   void* stream) {
     RLOA_REQUIRE(reward && done && score && frame && reset_mask && log_score && log_frame && log_last_reward &&
                      log_env && log_count, "rloa_episode_update: null argument");
     RLOA_REQUIRE(n_envs >= 1, "rloa_episode_update: n_envs >= 1 required");
     episode_update_kernel<<<(unsigned)((n_envs + 255) / 256), 256, 0, as_stream(stream)>>>(
         n_envs, frames, reward, done, active, score, frame, reset_mask, log_score, log_frame, log_last_reward, log_env,
-        log_capacity, log_count, reinterpret_cast<unsigned long long*>(transitions));
+        log_capacity, log_count, reinterpret_cast<unsigned long long*>(transitions),
+        reinterpret_cast<unsigned long long*>(tick));
     RLOA_LAUNCHED();
     return RLOA_OK;
 }

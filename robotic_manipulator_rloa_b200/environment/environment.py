@@ -111,6 +111,13 @@ class Environment:
         self._action_space = np.zeros((len(self.involved_joints),))
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(int(seed) + 0x5EED)
+        self.seed = int(seed)
+        n_init = self._n_init()
+        pos = list(self.initial_joint_positions[:n_init]) if self.initial_joint_positions else [0.0] * n_init
+        var = (list(self.initial_positions_variation_range[:n_init]) if self.initial_positions_variation_range
+               else [0.0] * n_init)
+        self._d_pos = torch.tensor(pos, dtype=torch.float32, device=self.device)
+        self._d_var = torch.tensor(var, dtype=torch.float32, device=self.device)
         # pinned staging for the single-env host API
         self._h_action = torch.zeros(self.n_envs, len(self.involved_joints), dtype=torch.float32).pin_memory()
         self._d_action = torch.zeros(self.n_envs, len(self.involved_joints), dtype=torch.float32, device=self.device)
@@ -149,6 +156,12 @@ class Environment:
         pos, var = pos.to(self.device), var.to(self.device)
         u = torch.rand(self.n_envs, n_init, generator=self._gen, device=self.device, dtype=torch.float32)
         return (pos + var * (2.0 * u - 1.0)).contiguous()
+
+    def begin_reset_masked(self, mask: torch.Tensor, tick: Optional[torch.Tensor] = None) -> None:
+        """Lock-step asynchronous reset of the masked envs with start poses drawn on the device
+        (environment.py:284-301); one launch, no host work, CUDA-graph capturable."""
+        self.sim.begin_reset_random(self._d_pos, self._d_var, self._n_init(), mask=mask, seed=self.seed + 0x5EED,
+                                    tick=tick)
 
     # ------------------------------------------------------------------------------------------
     # batched API (device tensors)

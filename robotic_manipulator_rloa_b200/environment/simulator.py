@@ -128,6 +128,14 @@ class BatchedSimulator:
         N.check(self.lib.rloa_sim_begin_reset(self._h_sim, N.ptr(mask), init_targets.data_ptr() if n_init else None,
                                               n_init, int(substeps), self._stream()), 'rloa_sim_begin_reset')
 
+    def begin_reset_random(self, pos: Optional[torch.Tensor], var: Optional[torch.Tensor], n_init: int,
+                           mask: Optional[torch.Tensor] = None, seed: int = 0, tick: Optional[torch.Tensor] = None,
+                           substeps: int = RESET_SUBSTEPS) -> None:
+        """begin_reset with start poses pos + var * U(-1, 1) drawn on the device (pos / var: fp32 [n_init])."""
+        N.check(self.lib.rloa_sim_begin_reset_random(self._h_sim, N.ptr(mask), N.ptr(pos), N.ptr(var), int(n_init),
+                                                     int(substeps), int(seed) & 0xFFFFFFFFFFFFFFFF, N.ptr(tick),
+                                                     self._stream()), 'rloa_sim_begin_reset_random')
+
     def reset(self, init_targets, mask: Optional[torch.Tensor] = None, substeps: int = RESET_SUBSTEPS,
               obs: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Environment.reset for the masked envs; init_targets fp32 [n_envs, n_init]."""

@@ -175,8 +175,10 @@ class NAFAgent:
         return {k: v.detach().cpu() for k, v in self.qnetwork_main.state_dict().items()}
 
     # ------------------------------------------------------------------------------------------
-    def act_batch(self, states: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Eval-mode policy for a batch of device states -> noisy clamped actions [n, A] (stays on the device)."""
+    def act_batch(self, states: torch.Tensor, out: Optional[torch.Tensor] = None,
+                  tick: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Eval-mode policy for a batch of device states -> noisy clamped actions [n, A] (stays on the device).
+        `tick`: device uint64 counter added to the Philox step (so a captured CUDA graph draws fresh noise)."""
         self._require_cuda()
         n = states.shape[0]
         ws = self._workspace(n)
@@ -184,7 +186,8 @@ class NAFAgent:
             out = torch.empty(n, self.action_size, dtype=torch.float32, device=self.device)
         p = self.qnetwork_main.native_params()
         N.check(ws.lib.rloa_naf_act(ws.handle, C.byref(p), states.data_ptr(), n, self.seed, self._act_calls,
-                                    float(self.noise_scale), out.data_ptr(), self._stream()), 'rloa_naf_act')
+                                    N.ptr(tick), float(self.noise_scale), out.data_ptr(), self._stream()),
+                'rloa_naf_act')
         self._act_calls += 1
         return out
 
@@ -201,16 +204,21 @@ class NAFAgent:
         self.memory.add(state, action, reward, next_state, done)
         self._maybe_learn()
 
-    def _maybe_learn(self) -> None:
+    def _learn_due(self, pending: int = 0) -> bool:
+        """The update gate of NAFAgent.step (naf_algorithm.py:147-150); advances the update_freq counter.
+        `pending` = transitions the caller is about to append before it learns."""
         self.update_t_step = (self.update_t_step + 1) % self.update_freq
-        if self.update_t_step == 0 and len(self.memory) > self.batch_size:
-            for _ in range(self.num_updates):
-                self.learn_from_memory()
+        return self.update_t_step == 0 and len(self.memory) + pending > self.batch_size
 
-    def learn_from_memory(self) -> None:
+    def _maybe_learn(self, tick: Optional[torch.Tensor] = None) -> None:
+        if self._learn_due():
+            for u in range(self.num_updates):
+                self.learn_from_memory(tick=tick, sub=u)
+
+    def learn_from_memory(self, tick: Optional[torch.Tensor] = None, sub: int = 0) -> None:
         """sample + learn without leaving the device (replay_buffer.py:47-67 + naf_algorithm.py:180-213)."""
         b = self._learn_buffers()
-        self.memory.sample_into(b['s'], b['a'], b['r'], b['s2'], b['d'])
+        self.memory.sample_into(b['s'], b['a'], b['r'], b['s2'], b['d'], tick=tick, sub=sub)
         self._learn_device(b['s'], b['a'], b['r'], b['s2'], b['d'])
 
     def learn(self, experiences: Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]) -> None:
@@ -305,7 +313,9 @@ class NAFAgent:
 
 class VectorLoop:
     """Device-resident buffers and one sync-free iteration of the vectorised act -> step -> store -> learn loop
-    (the body of naf_algorithm.py:249-270 for every env at once).  Nothing in ``step`` reads back to the host."""
+    (the body of naf_algorithm.py:249-270 for every env at once).  Nothing in ``step`` reads back to the host,
+    every random draw is keyed by the device counter ``tick``, and two consecutive iterations (the state buffers
+    ping-pong) can therefore be captured once into a CUDA graph and replayed (``run_steps``)."""
 
     def __init__(self, agent: NAFAgent, frames: int, log_capacity: int, learn: bool = True):
         self.agent, self.env = agent, agent.environment
@@ -331,7 +341,13 @@ class VectorLoop:
         self.log_env = torch.zeros(self.cap, **i32)
         self.log_count = torch.zeros(1, **i32)
         self.transitions = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.tick = torch.zeros(1, dtype=torch.int64, device=dev)      # device loop counter (uint64 bits)
         self.lib = N.lib()
+        self.sim_events = None          # optional [(start, end), (start, end)] events recorded around sim.step
+        self._graph = None              # CUDA graph of two consecutive iterations
+        self._graph_learn = False
+        self.graph_kernels = 0
+        self.graph_error: Optional[str] = None
 
     def reset_all(self, verbose: bool = False) -> None:
         """Synchronous Environment.reset of every env (50 sub-steps) -> self.state."""
@@ -343,20 +359,77 @@ class VectorLoop:
         self.score.zero_()
         self.frame.zero_()
 
-    def step(self, auto_reset: bool = True) -> None:
+    def _body(self, auto_reset: bool, learn_now: bool, parity: int) -> None:
         a, env = self.agent, self.env
-        a.act_batch(self.state, out=self.actions)
+        a.act_batch(self.state, out=self.actions, tick=self.tick)
+        if self.sim_events is not None:
+            self.sim_events[parity][0].record()
         env.sim.step(self.actions, out=(self.next_state, self.reward, self.done), valid=self.valid)
+        if self.sim_events is not None:
+            self.sim_events[parity][1].record()
         a.memory.add_batch(self.state, self.actions, self.reward, self.next_state, self.done,
                            valid=self.valid if auto_reset else None)
-        if self.learn:
-            a._maybe_learn()
+        if learn_now:
+            for u in range(a.num_updates):
+                a.learn_from_memory(tick=self.tick, sub=u)
         N.check(self.lib.rloa_episode_update(self.n, self.frames, self.reward.data_ptr(), self.done.data_ptr(),
                                              self.valid.data_ptr(), self.score.data_ptr(), self.frame.data_ptr(),
                                              self.reset_mask.data_ptr(), self.log_score.data_ptr(),
                                              self.log_frame.data_ptr(), self.log_last.data_ptr(),
                                              self.log_env.data_ptr(), self.cap, self.log_count.data_ptr(),
-                                             self.transitions.data_ptr(), a._stream()), 'rloa_episode_update')
+                                             self.transitions.data_ptr(), self.tick.data_ptr(), a._stream()),
+                'rloa_episode_update')
         if auto_reset:      # finished envs start their 50 reset sub-steps, one per following step() (lock step)
-            env.sim.begin_reset(env.initial_targets(), mask=self.reset_mask)
+            env.begin_reset_masked(self.reset_mask, tick=self.tick)
         self.state, self.next_state = self.next_state, self.state
+
+    def step(self, auto_reset: bool = True) -> None:
+        learn_now = self.learn and self.agent._learn_due(pending=self.n)
+        self._body(auto_reset, learn_now, 0)
+
+    # ---- CUDA graph of two iterations ---------------------------------------------------------------------
+    def _graphable(self) -> bool:
+        a = self.agent
+        return (not self.learn) or (a.update_freq == 1 and len(a.memory) > a.batch_size)
+
+    def capture(self) -> bool:
+        """Capture two consecutive auto-reset iterations (eager warm-up must have happened: workspaces exist).
+        Returns False (and keeps the eager path) when the loop is not in steady state or capture fails."""
+        if self._graph is not None:
+            return True
+        a = self.agent
+        if not self._graphable() or a._ws is None or (self.learn and a._bufs is None):
+            return False
+        host_len = a.memory._len
+        try:
+            torch.cuda.synchronize(self.agent.device)
+            g = torch.cuda.CUDAGraph()
+            launched = self.lib.rloa_launch_count()
+            with torch.cuda.graph(g):
+                self._body(True, self.learn, 0)
+                self._body(True, self.learn, 1)
+            self._graph, self._graph_learn = g, self.learn
+            self.graph_kernels = int(self.lib.rloa_launch_count() - launched)    # librloa kernels per replay
+            a.memory._len = host_len          # capturing does not execute: roll the host mirror back
+            return True
+        except Exception as err:          # pragma: no cover - depends on driver / NCCL capture support
+            self.graph_error = f'{type(err).__name__}: {err}'
+            self._graph = None
+            a.memory._len = host_len
+            torch.cuda.synchronize(self.agent.device)
+            return False
+
+    def replay_pair(self) -> None:
+        """Two iterations through the captured graph."""
+        self._graph.replay()
+        m = self.agent.memory
+        m._len = min(m.buffer_size, m._len + 2 * self.n)
+
+    def run_steps(self, k: int, use_graph: bool = True) -> None:
+        """k iterations with auto-reset; pairs go through the CUDA graph when it is (or can be) captured."""
+        if use_graph and k >= 2 and self.capture():
+            while k >= 2:
+                self.replay_pair()
+                k -= 2
+        for _ in range(k):
+            self.step()

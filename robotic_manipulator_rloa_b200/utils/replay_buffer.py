@@ -45,7 +45,7 @@ class ReplayBuffer:
         self.rewards = torch.zeros(cap, **f32)
         self.dones = torch.zeros(cap, **f32)
         self.cursor = torch.zeros(1, dtype=torch.int64, device=self.device)
-        self.scratch = torch.zeros((self._max_append + 1023) // 1024 + 1, dtype=torch.int32, device=self.device)
+        self.scratch = torch.zeros((self._max_append + 255) // 256 + 2, dtype=torch.int32, device=self.device)
         rb = N.Replay()
         rb.capacity, rb.state_size, rb.action_size = cap, self.state_size, self.action_size
         rb.states, rb.actions, rb.rewards = self.states.data_ptr(), self.actions.data_ptr(), self.rewards.data_ptr()
@@ -85,7 +85,7 @@ class ReplayBuffer:
             self._allocate(states.shape[1], actions.shape[1])
         if n > self._max_append and valid is not None:
             self._max_append = n
-            self.scratch = torch.zeros((n + 1023) // 1024 + 1, dtype=torch.int32, device=self.device)
+            self.scratch = torch.zeros((n + 255) // 256 + 2, dtype=torch.int32, device=self.device)
             self._rb.scratch = self.scratch.data_ptr()
         N.check(self.lib.rloa_replay_append(C.byref(self._rb), n, states.data_ptr(), actions.data_ptr(),
                                             rewards.data_ptr(), next_states.data_ptr(), N.ptr(dones), N.ptr(valid),
@@ -101,8 +101,10 @@ class ReplayBuffer:
             self._len = min(self.buffer_size, int(self.cursor.item()))
         return self._len
 
-    def sample_into(self, states, actions, rewards, next_states, dones, indices=None) -> None:
-        N.check(self.lib.rloa_replay_sample(C.byref(self._rb), states.shape[0], self.seed, self._draws,
+    def sample_into(self, states, actions, rewards, next_states, dones, indices=None, tick=None, sub: int = 0) -> None:
+        """`tick` (device uint64 counter) + `sub` replace the host draw counter when the call is captured in a CUDA graph."""
+        draw = self._draws if tick is None else (int(sub) << 32)
+        N.check(self.lib.rloa_replay_sample(C.byref(self._rb), states.shape[0], self.seed, draw, N.ptr(tick),
                                             states.data_ptr(), actions.data_ptr(), rewards.data_ptr(),
                                             next_states.data_ptr(), N.ptr(dones), N.ptr(indices), self._stream()),
                 'rloa_replay_sample')
