@@ -248,16 +248,19 @@ def ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # events recorded around rloa_sim_step inside the loop body; `external` lets them sit inside a CUDA graph
+    # phase-boundary events recorded inside the loop body (act | Environment.step | append | learn | tail);
+    # `external` lets them sit inside a CUDA graph as event-record nodes
     use_graph = not args.no_graph
-    try:
-        sim_pair = [(torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
-                    for _ in range(2)] if use_graph else None
-    except TypeError:
-        sim_pair, use_graph = None, False
-    if not use_graph:
-        sim_pair = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2)]
-    loop.sim_events = sim_pair
+    mk = lambda **kw: [[torch.cuda.Event(enable_timing=True, **kw) for _ in range(6)] for _ in range(2)]
+    phase_ev = None
+    if use_graph:
+        try:
+            phase_ev = mk(external=True)
+        except TypeError:
+            use_graph = False
+    if phase_ev is None:
+        phase_ev = mk()
+    loop.phase_events = phase_ev
     for _ in range(max(args.warmup, 3)):
         loop.step()
     graphed = bool(use_graph and loop.capture())
@@ -273,7 +276,7 @@ def ours(args):
         sampler.start()
     loop.transitions.zero_()
     launches0 = lib.rloa_launch_count()
-    sim_ms = []
+    phase_ms = [[] for _ in range(5)]
     barrier()
     t_wall = time.perf_counter()
     for i in range(npairs + odd):
@@ -289,15 +292,16 @@ def ours(args):
         else:
             loop._body(True, True, 0)
         ev[i][1].record()
-        if graphed or i % 16 == 15 or i == npairs + odd - 1:
-            # the sim events are re-recorded by every pair: read them before the next pair overwrites them
+        if graphed or i % 8 == 7 or i == npairs + odd - 1:
+            # the phase events are re-recorded by every pair: read them before the next pair overwrites them
             ev[i][1].synchronize()
-            sim_ms.append(sim_pair[0][0].elapsed_time(sim_pair[0][1]))
-            if i < npairs:
-                sim_ms.append(sim_pair[1][0].elapsed_time(sim_pair[1][1]))
+            for par in range(2 if i < npairs else 1):
+                for k in range(5):
+                    phase_ms[k].append(phase_ev[par][k].elapsed_time(phase_ev[par][k + 1]))
     barrier()
     t_wall = time.perf_counter() - t_wall
-    loop.sim_events = None
+    loop.phase_events = None
+    sim_ms = phase_ms[1]
     launches = lib.rloa_launch_count() - launches0
     if graphed:      # a graph replay re-launches the kernels recorded at capture: count them per replay
         launches = loop.graph_kernels * npairs + launches
@@ -381,6 +385,8 @@ def ours(args):
             'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n * (S + A) * 4,
                     'd2h_bytes_per_step': n * (A * 4 + S * 4 + 4 + 1), 'steps': e2e_steps},
+            'phases_ms': dict(zip(('act', 'env_step', 'replay_append', 'sample_learn', 'bookkeeping_reset'),
+                                  [round(sum(x) / len(x), 5) for x in phase_ms])),
             'gpu_launches': int(launches),
             'graphed': graphed, 'graph_error': loop.graph_error,
             'clocks': clocks,

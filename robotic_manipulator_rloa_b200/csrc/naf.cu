@@ -929,8 +929,12 @@ extern "C" int rloa_naf_ws_set_trunk(rloa_naf_ws* ws, int32_t mode) {
     RLOA_REQUIRE(mode == 0 || mode == 1, "rloa_naf_ws_set_trunk: mode must be 0 (fp32) or 1 (tcgen05)");
     if (mode == 1) {
         RLOA_REQUIRE(ws->H == 256, "rloa_naf_ws_set_trunk: the tcgen05 trunk is built for hidden = 256");
-        const int rc = trunk_tc_prepare(&ws->tc, ws->max_batch, ws->H);
+        int rc = trunk_tc_prepare(&ws->tc, ws->max_batch, ws->H);
         if (rc != RLOA_OK) return rc;
+        if (policy_tc_supported(ws->S, ws->A, ws->H)) {
+            rc = policy_tc_prepare(&ws->tc);
+            if (rc != RLOA_OK) return rc;
+        }
     }
     ws->trunk_mode = mode;
     return RLOA_OK;
@@ -1050,6 +1054,8 @@ extern "C" int rloa_naf_act(rloa_naf_ws* ws, const rloa_naf_params* p, const flo
     int rc = check_params(ws, p, "rloa_naf_act");
     if (rc != RLOA_OK) return rc;
     cudaStream_t st = as_stream(stream);
+    if (ws->trunk_mode == 1 && ws->tc.policy_image != nullptr)      // one fused tcgen05 launch (naf_policy_tc.cu)
+        return policy_tc_act(&ws->tc, p, states, batch, seed, step, step_offset, noise_scale, actions, st);
     const rloa_naf_params* P[1] = {p};
     const float* X[1] = {states};
     rc = trunk_forward(ws, 1, P, X, batch, 0, st);      // qnetwork_main.eval() (naf_algorithm.py:170)

@@ -1,0 +1,285 @@
+// Fused tcgen05 policy kernel: NAFAgent.act for 128 arms per CTA in ONE launch
+// (reference naf_components/naf_algorithm.py:158-178 = eval-mode NAF.forward, naf_neural_network.py:76-87,
+// 95-102, 119-121: trunk, mu head, diagonal of L, noise, clamp).
+//
+//   policy_pack_kernel   folds the eval-mode BatchNorms into per-column (scale, shift) vectors and writes the
+//                        "weight image": hidden_layer.weight and the 2A head rows that act() needs (mu, diag L)
+//                        as bf16 in the exact shared-memory byte order of a K-major SWIZZLE_128B UMMA operand.
+//   policy_act_tc_kernel per 128-row tile:
+//     0. one thread issues three 1-D TMA bulk copies (cp.async.bulk, mbarrier complete_tx): W2 image 128 KB,
+//        W1 + vectors 28 KB now, head image 16 KB later into the W1 region;
+//     1. layer 1 (K = S = 21: too thin for the tensor core, and the observation carries raw joint angles, so it
+//        stays fp32) on the CUDA cores while the W2 copy is in flight: thread = (row, half of the 256 columns),
+//        W1 broadcast from shared memory; relu(bn1(.)) -> bf16 -> A operand tile, hand-swizzled;
+//     2. layer 2: 16 x tcgen05.mma 128x256x16 (bf16 -> fp32 TMEM, 256 columns), commit -> mbarrier;
+//     3. epilogue 2: tcgen05.ld, relu(bn2(.)) -> bf16 -> the same A tile (layer-2 operands are dead);
+//     4. heads: 16 x tcgen05.mma 128x32x16 into TMEM columns 0-31 (the layer-2 accumulator is dead);
+//     5. epilogue: mu = tanh, l_kk = tanh, action = clamp(mu + noise_scale exp(-l_kk) eps, -1, 1) with the same
+//        Philox4x32-10 keying as the fp32 head kernel (seed, step + *step_offset, row, k).
+// Shared memory: A tile 64 KB + W2 128 KB + W1/head region 24 KB + vectors 4.2 KB = 220.2 KB of the 227 KB.
+#include "common.cuh"
+#include "naf_trunk_tc.cuh"
+#include "philox.cuh"
+#include "tc_common.cuh"
+
+namespace rloa {
+
+using namespace tc;
+
+constexpr int kPolH = 256;                     // hidden width the kernel is built for
+constexpr int kPolSP = 24;                     // padded state width (S <= 24: KUKA 21, Panda 23)
+constexpr int kPolNH = 32;                     // head rows in the image: [0,A) mu, [A,2A) diag L, rest zero
+constexpr int kPolThreads = 256;
+constexpr uint32_t kPolW2Bytes = kPolH * kPolH * 2;            // 131072
+constexpr uint32_t kPolWhBytes = kPolNH * kPolH * 2;           // 16384
+constexpr uint32_t kPolVecFloats = 4 * kPolH + kPolNH;         // sc1 sh1 sc2 sh2 bh
+constexpr uint32_t kPolVecBytes = kPolVecFloats * 4;           // 4224
+constexpr uint32_t kPolW1Bytes = kPolH * kPolSP * 4;           // 24576 (fp32 [256][24])
+constexpr uint32_t kPolOffWh = kPolW2Bytes;
+constexpr uint32_t kPolOffW1 = kPolOffWh + kPolWhBytes;        // W1 and the vectors are contiguous: one bulk copy
+constexpr uint32_t kPolOffVec = kPolOffW1 + kPolW1Bytes;
+constexpr uint32_t kPolImageBytes = kPolOffVec + kPolVecBytes;
+constexpr uint32_t kPolABytes = 128 * kPolH * 2;               // 65536
+constexpr uint32_t kPolSmemBytes = kPolABytes + kPolW2Bytes + kPolW1Bytes + kPolVecBytes + 64 + 1024;
+constexpr uint32_t kPolTmemCols = 256;
+
+size_t policy_image_bytes() { return kPolImageBytes; }
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) policy_pack_kernel(rloa_naf_params p, uint8_t* __restrict__ image) {
+    const int S = p.state_size, A = p.action_size;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    // (a) W2: one thread per 16-byte chunk (8 consecutive k of one output row n)
+    if (t < kPolH * kPolH / 8) {
+        const int n = t >> 5, kc = t & 31;             // 32 chunks per row
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = p.w2[(size_t)n * kPolH + kc * 8 + i];
+        const uint32_t off = (uint32_t)(kc >> 3) * (kPolH * 128) + sw128_chunk_offset(n, kc & 7);
+        *reinterpret_cast<uint4*>(image + off) = pack8_bf16(v);
+        return;
+    }
+    int u = t - kPolH * kPolH / 8;
+    // (b) head rows: [0,A) action_values, [A,2A) the diagonal entries k(k+3)/2 of matrix_entries
+    if (u < kPolNH * kPolH / 8) {
+        const int n = u >> 5, kc = u & 31;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int k = kc * 8 + i;
+            float w = 0.f;
+            if (n < A) w = p.w_mu[(size_t)n * kPolH + k];
+            else if (n < 2 * A) {
+                const int d = n - A;
+                w = p.w_l[(size_t)((d * (d + 3)) / 2) * kPolH + k];
+            }
+            v[i] = w;
+        }
+        const uint32_t off = kPolOffWh + (uint32_t)(kc >> 3) * (kPolNH * 128) + sw128_chunk_offset(n, kc & 7);
+        *reinterpret_cast<uint4*>(image + off) = pack8_bf16(v);
+        return;
+    }
+    u -= kPolNH * kPolH / 8;
+    // (c) W1 fp32, rows padded to 24
+    if (u < kPolH * kPolSP) {
+        const int j = u / kPolSP, k = u - j * kPolSP;
+        reinterpret_cast<float*>(image + kPolOffW1)[u] = k < S ? p.w1[(size_t)j * S + k] : 0.f;
+        return;
+    }
+    u -= kPolH * kPolSP;
+    // (d) eval-mode BatchNorm folded with the linear bias: a = relu(acc * sc + sh)
+    float* vec = reinterpret_cast<float*>(image + kPolOffVec);
+    if (u < kPolH) {
+        const float sc = p.bn1_w[u] / sqrtf(p.bn1_var[u] + 1e-5f);
+        vec[u] = sc;
+        vec[kPolH + u] = fmaf(p.b1[u] - p.bn1_mean[u], sc, p.bn1_b[u]);
+        const float sc2 = p.bn2_w[u] / sqrtf(p.bn2_var[u] + 1e-5f);
+        vec[2 * kPolH + u] = sc2;
+        vec[3 * kPolH + u] = fmaf(p.b2[u] - p.bn2_mean[u], sc2, p.bn2_b[u]);
+        if (u < kPolNH) {
+            float b = 0.f;
+            if (u < A) b = p.b_mu[u];
+            else if (u < 2 * A) b = p.b_l[((u - A) * (u - A + 3)) / 2];
+            vec[4 * kPolH + u] = b;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPolThreads, 1)
+policy_act_tc_kernel(const uint8_t* __restrict__ image, const float* __restrict__ states, int n_rows, int S, int A,
+                     unsigned long long seed, unsigned long long step0, const unsigned long long* __restrict__ step_offset,
+                     float noise_scale, float* __restrict__ actions) {
+    extern __shared__ uint8_t pol_smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int r = tid & 127, half = tid >> 7;            // tile row, which 128 of the 256 hidden columns
+    const int row = blockIdx.x * 128 + r;
+
+    const uint32_t raw = smem_u32(pol_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* sm = pol_smem_raw + (base - raw);
+    uint8_t* sm_a = sm;                                  // [4 k-blocks][128 rows][128 B]
+    uint8_t* sm_w2 = sm + kPolABytes;                    // [4 k-blocks][256 rows][128 B]
+    uint8_t* sm_r = sm_w2 + kPolW2Bytes;                 // W1 fp32 [256][24], later the head image [4][32 rows][128 B]
+    float* sm_vec = reinterpret_cast<float*>(sm_r + kPolW1Bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_r + kPolW1Bytes + kPolVecBytes);   // w2, w1, wh, mma
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    const uint32_t a_base = base, w2_base = base + kPolABytes, r_base = w2_base + kPolW2Bytes;
+
+    if (warp == 0) tmem_alloc(tmem_slot, kPolTmemCols);
+    if (tid == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);
+        mbar_init_fence();
+        mbar_expect_tx(&bars[1], kPolW1Bytes + kPolVecBytes);
+        bulk_g2s(sm_r, image + kPolOffW1, kPolW1Bytes + kPolVecBytes, &bars[1]);
+        mbar_expect_tx(&bars[0], kPolW2Bytes);
+        bulk_g2s(sm_w2, image, kPolW2Bytes, &bars[0]);
+    }
+    // this thread's observation row, fp32 registers
+    float x[kPolSP];
+#pragma unroll
+    for (int k = 0; k < kPolSP; k++) x[k] = (k < S && row < n_rows) ? states[(size_t)row * S + k] : 0.f;
+    fence_before_sync();
+    __syncthreads();                                     // barrier inits + TMEM address visible
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    // ---- layer 1 on the CUDA cores (fp32), 128 columns per thread, straight into the bf16 A tile ----
+    mbar_wait(&bars[1], 0);
+    {
+        const float* w1 = reinterpret_cast<const float*>(sm_r);
+        const float *sc1 = sm_vec, *sh1 = sm_vec + kPolH;
+#pragma unroll 1
+        for (int c8 = 0; c8 < 16; c8++) {                // 16 chunks of 8 columns
+            const int j0 = half * 128 + c8 * 8;
+            float a[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float4* wr = reinterpret_cast<const float4*>(w1 + (j0 + i) * kPolSP);
+                float acc = 0.f;
+#pragma unroll
+                for (int k4 = 0; k4 < kPolSP / 4; k4++) {
+                    const float4 w = wr[k4];
+                    acc = fmaf(x[4 * k4], w.x, acc); acc = fmaf(x[4 * k4 + 1], w.y, acc);
+                    acc = fmaf(x[4 * k4 + 2], w.z, acc); acc = fmaf(x[4 * k4 + 3], w.w, acc);
+                }
+                a[i] = fmaxf(fmaf(acc, sc1[j0 + i], sh1[j0 + i]), 0.f);
+            }
+            const int chunk = j0 >> 3;                   // 0..31 over K = 256
+            *reinterpret_cast<uint4*>(sm_a + (chunk >> 3) * (128 * 128) + sw128_chunk_offset(r, chunk & 7)) = pack8_bf16(a);
+        }
+    }
+    fence_proxy_async();                                 // A tile -> async proxy; also orders the W1 reads before the head copy
+    __syncthreads();
+
+    // ---- layer 2 on the tensor core ----
+    if (tid == 0) {
+        // the W1 region is free now: fetch the head image into it while layer 2 runs
+        mbar_expect_tx(&bars[2], kPolWhBytes);
+        bulk_g2s(sm_r, image + kPolOffWh, kPolWhBytes, &bars[2]);
+        mbar_wait(&bars[0], 0);                          // W2 image landed
+        fence_after_sync();
+        constexpr uint32_t idesc = idesc_bf16_f32(128, kPolH);
+#pragma unroll
+        for (int k = 0; k < kPolH / 16; k++)
+            mma_bf16(tmem, umma_desc_sw128(a_base + (k >> 2) * (128 * 128) + (k & 3) * 32),
+                     umma_desc_sw128(w2_base + (k >> 2) * (kPolH * 128) + (k & 3) * 32), idesc, k > 0);
+        mma_commit(&bars[3]);
+    }
+    __syncwarp();
+    mbar_wait(&bars[3], 0);
+    fence_after_sync();
+
+    // ---- epilogue 2: relu(bn2(.)) -> bf16 -> the A tile again (TMEM lane = row; warps 4-7 take columns 128-255) ----
+    {
+        const float *sc2 = sm_vec + 2 * kPolH, *sh2 = sm_vec + 3 * kPolH;
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) {
+            const int c0 = half * 128 + q * 32;
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                float a[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int j = c0 + g * 8 + i;
+                    a[i] = fmaxf(fmaf(__uint_as_float(v[g * 8 + i]), sc2[j], sh2[j]), 0.f);
+                }
+                const int chunk = (c0 >> 3) + g;
+                *reinterpret_cast<uint4*>(sm_a + (chunk >> 3) * (128 * 128) + sw128_chunk_offset(r, chunk & 7)) = pack8_bf16(a);
+            }
+        }
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+
+    // ---- heads on the tensor core: [mu | diag L] = a2 Wh^T, TMEM columns 0-31 ----
+    if (tid == 0) {
+        mbar_wait(&bars[2], 0);
+        fence_after_sync();
+        constexpr uint32_t idesc = idesc_bf16_f32(128, kPolNH);
+#pragma unroll
+        for (int k = 0; k < kPolH / 16; k++)
+            mma_bf16(tmem, umma_desc_sw128(a_base + (k >> 2) * (128 * 128) + (k & 3) * 32),
+                     umma_desc_sw128(r_base + (k >> 2) * (kPolNH * 128) + (k & 3) * 32), idesc, k > 0);
+        mma_commit(&bars[3]);
+    }
+    __syncwarp();
+    if (warp < 4) {
+        mbar_wait(&bars[3], 1);
+        fence_after_sync();
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
+        if (row < n_rows) {
+            const float* bh = sm_vec + 4 * kPolH;
+            const unsigned long long stp = step0 + (step_offset != nullptr ? *step_offset : 0ull);
+            for (int k = 0; k < A; k++) {
+                float zmu = 0.f, zl = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; i++) {           // register array: select by compile-time index
+                    if (i == k) zmu = __uint_as_float(v[i]);
+                    if (i == A + k) zl = __uint_as_float(v[i]);
+                }
+                const float mu = tanhf(zmu + bh[k]);
+                const float t = tanhf(zl + bh[A + k]);
+                uint32_t c[4] = {(uint32_t)row, (uint32_t)k, (uint32_t)stp, (uint32_t)(stp >> 32)};
+                philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+                const float rr = sqrtf(-2.f * logf(u01(c[0])));
+                const float eps = rr * cospif(2.f * u01(c[1]));
+                const float a = fmaf(noise_scale * expf(-t), eps, mu);
+                actions[(size_t)row * A + k] = fminf(fmaxf(a, -1.f), 1.f);
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, kPolTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------
+bool policy_tc_supported(int S, int A, int H) { return H == kPolH && S >= 1 && S <= kPolSP && A >= 1 && 2 * A <= kPolNH; }
+
+int policy_tc_prepare(TrunkTC* t) {
+    if (t->policy_image != nullptr) return RLOA_OK;
+    RLOA_CUDA(cudaFuncSetAttribute(policy_act_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolSmemBytes));
+    RLOA_CUDA(cudaMalloc(&t->policy_image, kPolImageBytes));
+    return RLOA_OK;
+}
+
+int policy_tc_act(TrunkTC* t, const rloa_naf_params* p, const float* states, int batch, uint64_t seed, uint64_t step,
+                  const uint64_t* step_offset, float noise_scale, float* actions, cudaStream_t st) {
+    RLOA_REQUIRE(t->policy_image != nullptr, "tcgen05 policy: rloa_naf_ws_set_trunk(1) was not called");
+    uint8_t* image = static_cast<uint8_t*>(t->policy_image);
+    const int pack_threads = kPolH * kPolH / 8 + kPolNH * kPolH / 8 + kPolH * kPolSP + kPolH;
+    policy_pack_kernel<<<(pack_threads + 255) / 256, 256, 0, st>>>(*p, image);
+    RLOA_LAUNCHED();
+    policy_act_tc_kernel<<<(batch + 127) / 128, kPolThreads, kPolSmemBytes, st>>>(
+        image, states, batch, p->state_size, p->action_size, seed, step,
+        reinterpret_cast<const unsigned long long*>(step_offset), noise_scale, actions);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
+}  // namespace rloa

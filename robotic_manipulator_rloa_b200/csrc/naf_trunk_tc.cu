@@ -18,7 +18,7 @@
 #include "common.cuh"
 #include "naf_trunk_tc.cuh"
 
-#include <cuda_bf16.h>
+#include "tc_common.cuh"
 
 namespace rloa {
 
@@ -32,19 +32,9 @@ constexpr uint32_t kBBlockBytes = kTcN * 128;
 constexpr uint32_t kTcSmemBytes = kTcKBlocks * (kABlockBytes + kBBlockBytes) + 1024 /*alignment slack*/ + 64;
 constexpr uint32_t kTmemCols = 64;
 
-// instruction descriptor, kind::f16: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1), both K-major
-// (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// shared memory matrix descriptor, K-major SWIZZLE_128B: start address >> 4 (bits 0-13), leading byte offset
-// (unused for swizzled K-major, canonical value 1) at bits 16-29, stride byte offset = 1024 B between 8-row
-// atoms at bits 32-45, descriptor version 1 at bits 46-47, layout type 2 (SWIZZLE_128B) at bits 61-63
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-           (2ull << 61);
-}
+constexpr uint32_t kIdesc = tc::idesc_bf16_f32(kTcM, kTcN);
+using tc::smem_u32;
+using tc::umma_desc_sw128;
 
 struct TcNet {
     const float* z1;            // [B][256]
@@ -209,7 +199,10 @@ __global__ void __launch_bounds__(kTcThreads) trunk_tc_layer2_kernel(const __gri
 }
 
 void trunk_tc_init(TrunkTC* t) { *t = TrunkTC{}; }
-void trunk_tc_free(TrunkTC* t) { *t = TrunkTC{}; }
+void trunk_tc_free(TrunkTC* t) {
+    if (t->policy_image != nullptr) cudaFree(t->policy_image);
+    *t = TrunkTC{};
+}
 
 int trunk_tc_prepare(TrunkTC* t, int max_batch, int H) {
     RLOA_REQUIRE(H == kTcK, "tcgen05 trunk: hidden size must be 256");

@@ -3,11 +3,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "rloa_b200.h"
+
 namespace rloa {
 
 struct TrunkTC {
     int max_batch = 0;
     bool ready = false;
+    void* policy_image = nullptr;   // device: bf16 weight image of the fused policy kernel (naf_policy_tc.cu)
 };
 
 void trunk_tc_init(TrunkTC* t);
@@ -17,5 +20,11 @@ int trunk_tc_prepare(TrunkTC* t, int max_batch, int H);
 // for each of `nets` networks: z2[B][H] = bf16(relu(z1 * scale + shift)) @ bf16(w2)^T + b2, fp32 accumulation in TMEM
 int trunk_tc_layer2(TrunkTC* t, int nets, const float* const* z1, const float* const* scale, const float* const* shift,
                     const float* const* w2, const float* const* b2, float* const* z2, int B, int H, cudaStream_t st);
+
+// fused eval-mode policy (naf_policy_tc.cu): supported shapes, one-time setup, and NAFAgent.act for `batch` rows
+bool policy_tc_supported(int S, int A, int H);
+int policy_tc_prepare(TrunkTC* t);
+int policy_tc_act(TrunkTC* t, const rloa_naf_params* p, const float* states, int batch, uint64_t seed, uint64_t step,
+                  const uint64_t* step_offset, float noise_scale, float* actions, cudaStream_t st);
 
 }  // namespace rloa

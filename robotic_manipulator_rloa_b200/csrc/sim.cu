@@ -115,12 +115,14 @@ sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_c
         const int iters = M.iters;
         int it = 0;
         float resid = 0.f;
+        // Row update, branch-free: Bullet clamps the accumulated impulse and re-derives delta only when the clamp
+        // is active (btMultiBodyConstraintSolver::resolveSingleConstraintRowGeneric); a select keeps the
+        // unclamped delta bit-identical while the compiler emits no divergent branch.
         auto motor_row = [&](const int d) {
-            float delta = fmaf(-dv[d], jdi[d], rhs[d]);
-            const float sum = app[d] + delta;
-            float napp = sum;
-            if (sum < -mx[d]) { delta = -mx[d] - app[d]; napp = -mx[d]; }
-            else if (sum > mx[d]) { delta = mx[d] - app[d]; napp = mx[d]; }
+            const float delta0 = fmaf(-dv[d], jdi[d], rhs[d]);
+            const float sum = app[d] + delta0;
+            const float napp = fminf(fmaxf(sum, -mx[d]), mx[d]);
+            const float delta = (napp == sum) ? delta0 : napp - app[d];
             app[d] = napp;
 #pragma unroll
             for (int k = 0; k < D; k++) dv[k] = fmaf(delta, Mi[tri(d, k)], dv[k]);
@@ -131,11 +133,10 @@ sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_c
             const float sgn = side ? -1.f : 1.f;
             float* r = sm_lim + (2 * side * D + d) * kTpb;
             const float a0 = r[D * kTpb];
-            float delta = fmaf(-(sgn * dv[d]), jdi[d], r[0]);
-            const float sum = a0 + delta;
-            float napp = sum;
-            if (sum < 0.f) { delta = -a0; napp = 0.f; }
-            else if (sum > limit_hi) { delta = limit_hi - a0; napp = limit_hi; }
+            const float delta0 = fmaf(-(sgn * dv[d]), jdi[d], r[0]);
+            const float sum = a0 + delta0;
+            const float napp = fminf(fmaxf(sum, 0.f), limit_hi);
+            const float delta = (napp == sum) ? delta0 : napp - a0;
             r[D * kTpb] = napp;
             const float sd = sgn * delta;
 #pragma unroll

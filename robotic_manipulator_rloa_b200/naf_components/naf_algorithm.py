@@ -343,7 +343,7 @@ class VectorLoop:
         self.transitions = torch.zeros(1, dtype=torch.int64, device=dev)
         self.tick = torch.zeros(1, dtype=torch.int64, device=dev)      # device loop counter (uint64 bits)
         self.lib = N.lib()
-        self.sim_events = None          # optional [(start, end), (start, end)] events recorded around sim.step
+        self.phase_events = None        # optional [6 events] x 2 iterations: act | sim | append | learn | tail
         self._graph = None              # CUDA graph of two consecutive iterations
         self._graph_learn = False
         self.graph_kernels = 0
@@ -359,19 +359,25 @@ class VectorLoop:
         self.score.zero_()
         self.frame.zero_()
 
+    def _mark(self, parity: int, k: int) -> None:
+        """Record phase-boundary event k of iteration `parity` (bench.py installs the events; no-op otherwise)."""
+        if self.phase_events is not None:
+            self.phase_events[parity][k].record()
+
     def _body(self, auto_reset: bool, learn_now: bool, parity: int) -> None:
         a, env = self.agent, self.env
+        self._mark(parity, 0)
         a.act_batch(self.state, out=self.actions, tick=self.tick)
-        if self.sim_events is not None:
-            self.sim_events[parity][0].record()
+        self._mark(parity, 1)
         env.sim.step(self.actions, out=(self.next_state, self.reward, self.done), valid=self.valid)
-        if self.sim_events is not None:
-            self.sim_events[parity][1].record()
+        self._mark(parity, 2)
         a.memory.add_batch(self.state, self.actions, self.reward, self.next_state, self.done,
                            valid=self.valid if auto_reset else None)
+        self._mark(parity, 3)
         if learn_now:
             for u in range(a.num_updates):
                 a.learn_from_memory(tick=self.tick, sub=u)
+        self._mark(parity, 4)
         N.check(self.lib.rloa_episode_update(self.n, self.frames, self.reward.data_ptr(), self.done.data_ptr(),
                                              self.valid.data_ptr(), self.score.data_ptr(), self.frame.data_ptr(),
                                              self.reset_mask.data_ptr(), self.log_score.data_ptr(),
@@ -381,6 +387,7 @@ class VectorLoop:
                 'rloa_episode_update')
         if auto_reset:      # finished envs start their 50 reset sub-steps, one per following step() (lock step)
             env.begin_reset_masked(self.reset_mask, tick=self.tick)
+        self._mark(parity, 5)
         self.state, self.next_state = self.next_state, self.state
 
     def step(self, auto_reset: bool = True) -> None:

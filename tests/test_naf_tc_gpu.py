@@ -88,3 +88,44 @@ def test_forward_and_learn_with_tensor_core_trunk():
     got, want = b['grad'].cpu().numpy(), flat_r.numpy()
     cos = float(np.dot(got, want) / (np.linalg.norm(got) * np.linalg.norm(want)))
     assert cos >= 0.999, cos
+
+
+@pytest.mark.parametrize('S,A,n', [(21, 6, 1), (21, 6, 100), (21, 6, 128), (23, 7, 4096), (21, 6, 5000)])
+def test_fused_policy_kernel_matches_fp32_act(S, A, n):
+    """NAFAgent.act through the fused tcgen05 policy kernel (trunk mode 1: one launch, W2 / heads in bf16, layer 1
+    fp32) against the fp32 kernels (mode 0) on the same states, weights, running BatchNorm statistics and Philox
+    keys.  Bound: bf16 operand rounding through two 256-long contractions ahead of a tanh — |d mu| <= 1e-2; with
+    noise the same eps is drawn, so clamped actions agree to 2e-2."""
+    from robotic_manipulator_rloa_b200.naf_components.naf_algorithm import NAFAgent
+    ref = NAFRef(S, A, H, seed=5)
+    g = torch.Generator().manual_seed(n)
+    with torch.no_grad():                                   # non-trivial eval-mode statistics and affine terms
+        for bn in (ref.bn1, ref.bn2):
+            bn.running_mean.copy_(0.3 * torch.randn(H, generator=g))
+            bn.running_var.copy_(0.5 + torch.rand(H, generator=g))
+            bn.weight.copy_(0.8 + 0.4 * torch.rand(H, generator=g))
+            bn.bias.copy_(0.1 * torch.randn(H, generator=g))
+    agent = NAFAgent(None, S, A, H, 128, 1000, 1e-3, 1e-3, 0.99, 1, 1, 500, DEV, 3)
+    agent.qnetwork_main.load_state_dict(ref.state_dict())
+    states = torch.randn(n, S, generator=g).to(DEV)
+    out = {}
+    for mode in (0, 1):
+        agent.set_trunk_mode(mode)
+        agent.noise_scale = 0.0
+        agent._act_calls = 7
+        mu = agent.act_batch(states).clone()
+        agent.noise_scale = 1.0
+        agent._act_calls = 7
+        noisy = agent.act_batch(states).clone()
+        out[mode] = (mu, noisy)
+    torch.cuda.synchronize()
+    ref.eval()
+    with torch.no_grad():
+        mu_ref = ref.heads(states.cpu())[0]
+    assert (out[0][0].cpu() - mu_ref).abs().max() <= 1e-5
+    assert torch.isfinite(out[1][0]).all() and torch.isfinite(out[1][1]).all()
+    d_mu = float((out[1][0] - out[0][0]).abs().max())
+    d_act = float((out[1][1] - out[0][1]).abs().max())
+    assert d_mu <= 1e-2, d_mu
+    assert d_act <= 2e-2, d_act
+    assert out[1][1].abs().max() <= 1.0
