@@ -204,7 +204,8 @@ def workload_config(args, where):
                         'vectorised step, live-policy actions',
             'envs_per_gpu': args.envs, 'replay_batch': args.batch, 'frames': FRAMES, 'parallelism': f'env-dp{args.gpus}',
             'l2': 'flushed between timed step pairs (256 MiB fill, untimed)' if where == 'gpu' else 'n/a',
-            'trunk': getattr(args, 'trunk', 'fp32'),
+            'naf_trunk': ('tcgen05: bf16 operands, fp32 TMEM accumulate (fused policy kernel + hidden layer); heads, BatchNorm, '
+                          'backward and optimiser fp32' if getattr(args, 'trunk', 'tc') == 'tc' and where == 'gpu' else 'fp32'),
             'launch': 'eager' if getattr(args, 'no_graph', False) or where == 'cpu' else 'cuda-graph of 2 loop iterations'}
 
 
@@ -404,7 +405,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--envs', type=int, default=4096, help='envs per GPU')
     ap.add_argument('--batch', type=int, default=1024, help='replay batch per GPU')
-    ap.add_argument('--trunk', default='fp32', choices=['fp32', 'tc'])
+    ap.add_argument('--trunk', default='tc', choices=['fp32', 'tc'],
+                    help='tc: tcgen05 policy kernel + hidden layer (bf16 operands, fp32 accumulate); fp32: CUDA-core reference-exact path')
     ap.add_argument('--no-flush', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly instead of replaying the CUDA graph')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')

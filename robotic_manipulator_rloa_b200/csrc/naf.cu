@@ -547,6 +547,10 @@ struct HeadArgs {
     const float *reward, *done; float gamma; int use_done; float* y_out;
     // training (main net): y_in -> loss partial + dZh
     const float* y_in; float* dzh; float* loss_part;
+    // fused learn: TD target of the SAME row from the target net's trunk output (row-local dependency), and the
+    // gradient with respect to a2, da2 = dZh Wh, written straight from the head weights held in shared memory
+    const float* t_z2; const float *t_scale, *t_shift, *t_wv, *t_bv;
+    float* da_out;
     // act mode
     float* act_out; unsigned long long seed, step; const unsigned long long* step_offset; float noise_scale;
 };
@@ -559,7 +563,10 @@ __global__ void __launch_bounds__(kHeadWarps * 32) naf_head_kernel(HeadArgs h) {
     float* Wh = hs;                               // [NH][H+1]
     float* bh = Wh + NH * HS;                     // [NH]
     float* arow = bh + ((NH + 31) & ~31);         // [warps][H]
+    float* twv = arow + kHeadWarps * H;           // [H] target value-head weights (fused learn only)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (h.t_z2 != nullptr)
+        for (int k = tid; k < H; k += blockDim.x) twv[k] = h.t_wv[k];
     for (int idx = tid; idx < NH * H; idx += blockDim.x) {
         const int o = idx / H, k = idx - o * H;
         float w;
@@ -574,6 +581,19 @@ __global__ void __launch_bounds__(kHeadWarps * 32) naf_head_kernel(HeadArgs h) {
     float loss_acc = 0.f;
     const int row_stride = gridDim.x * kHeadWarps;
     for (int row = blockIdx.x * kHeadWarps + warp; row < h.B; row += row_stride) {
+        float y_row = 0.f;
+        if (h.t_z2 != nullptr) {                  // y = r + gamma V_target(s') for this row (naf_algorithm.py:196-199)
+            float acc = 0.f;
+            for (int k = lane; k < H; k += 32)
+                acc = fmaf(fmaxf(fmaf(h.t_z2[(size_t)row * H + k], h.t_scale[k], h.t_shift[k]), 0.f), twv[k], acc);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            float vv = acc + h.t_bv[0];
+            if (h.use_done && h.done) vv *= (1.f - h.done[row]);
+            y_row = fmaf(h.gamma, vv, h.reward[row]);
+        } else if (h.y_in != nullptr) {
+            y_row = h.y_in[row];
+        }
         for (int k = lane; k < H; k += 32) ar[k] = fmaxf(fmaf(h.z2[(size_t)row * H + k], h.scale[k], h.shift[k]), 0.f);
         __syncwarp();
         float zo[2] = {0.f, 0.f};                 // head pre-activations of outputs lane, lane + 32
@@ -624,11 +644,12 @@ __global__ void __launch_bounds__(kHeadWarps * 32) naf_head_kernel(HeadArgs h) {
         }
         if (h.dzh != nullptr) {
             // MSE over the batch: dLoss/dQ = 2 (Q - y) / B
-            const float err = q - h.y_in[row];
+            const float err = q - y_row;
             if (lane == 0) loss_acc = fmaf(err, err, loss_acc);
             const float dq = 2.f * err / (float)h.B;
             const float g_mu = dq * P * diff * (1.f - mu * mu);         // lanes < A
             const float g_l = dq * (-P * diff * diff) * (1.f - t * t);  // lanes < A, belongs to output didx
+            float gs[2] = {0.f, 0.f};
             // route g_l from lane k to the lane/slot that owns output didx(k)
 #pragma unroll
             for (int s = 0; s < 2; s++) {
@@ -645,6 +666,22 @@ __global__ void __launch_bounds__(kHeadWarps * 32) naf_head_kernel(HeadArgs h) {
                 else if (o == A) g = dq;
                 else if (ksrc >= 0) g = gl;
                 if (o < NH) h.dzh[(size_t)row * NH + o] = g;
+                gs[s] = o < NH ? g : 0.f;
+            }
+            if (h.da_out != nullptr) {            // da2[row][f] = sum_o dZh[row][o] Wh[o][f], f = lane + 32 j (H <= 256)
+                float acc[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[j] = 0.f;
+                for (int o = 0; o < NH; o++) {
+                    const float go = __shfl_sync(0xffffffffu, o < 32 ? gs[0] : gs[1], o & 31);
+                    const float* wr = Wh + o * HS + lane;
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if (32 * j < H) acc[j] = fmaf(go, wr[32 * j], acc[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (32 * j < H) h.da_out[(size_t)row * H + lane + 32 * j] = acc[j];
             }
         }
         if (h.act_out != nullptr && lane < A) {
@@ -824,6 +861,8 @@ struct rloa_naf_ws {
     unsigned* tickets;           // [2 * H / 32] last-block-done counters (always return to 0)
     size_t splitk_floats;
     int n_loss_parts;
+    cudaStream_t side[2] = {nullptr, nullptr};   // weight-gradient contractions run beside the critical path
+    cudaEvent_t fork_ev[2] = {nullptr, nullptr}, join_ev[2] = {nullptr, nullptr};
     TrunkTC tc;                  // tcgen05 trunk state
 };
 
@@ -868,6 +907,8 @@ static int bn_chunks(int B) { return (B + 8 * kBnRowsPerThread - 1) / (8 * kBnRo
 constexpr int kBnSplitMinBatch = 128;    // below this the single-block-per-column kernels are already short
 static int splitk_count(int B) { return (B + splitk_len(B) - 1) / splitk_len(B); }
 
+extern "C" void rloa_naf_ws_destroy(rloa_naf_ws* ws);
+
 extern "C" int rloa_naf_ws_create(int32_t S, int32_t A, int32_t H, int32_t max_batch, rloa_naf_ws** out) {
     RLOA_REQUIRE(out != nullptr, "rloa_naf_ws_create: null out");
     RLOA_REQUIRE(S >= 1 && S <= 4096, "rloa_naf_ws_create: state_size out of range");
@@ -910,9 +951,18 @@ extern "C" int rloa_naf_ws_create(int32_t S, int32_t A, int32_t H, int32_t max_b
     ws->bwd_coef = p; p += 3 * (size_t)H;
     ws->tickets = reinterpret_cast<unsigned*>(p); p += 2 * (size_t)(H / 32);
     cudaMemset(ws->tickets, 0, 2 * (size_t)(H / 32) * sizeof(unsigned));
-    const int hb = (ws->NH * (H + 1) + ((ws->NH + 31) & ~31) + kHeadWarps * H) * (int)sizeof(float);
+    const int hb = (ws->NH * (H + 1) + ((ws->NH + 31) & ~31) + kHeadWarps * H + H) * (int)sizeof(float);
     if (hb > 48 * 1024) cudaFuncSetAttribute(naf_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
     trunk_tc_init(&ws->tc);
+    for (int i = 0; i < 2; i++) {
+        if (cudaStreamCreateWithFlags(&ws->side[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ws->fork_ev[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ws->join_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            set_error("rloa_naf_ws_create: stream / event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rloa_naf_ws_destroy(ws);
+            return RLOA_ERR_CUDA;
+        }
+    }
     *out = ws;
     return RLOA_OK;
 }
@@ -920,6 +970,11 @@ extern "C" int rloa_naf_ws_create(int32_t S, int32_t A, int32_t H, int32_t max_b
 extern "C" void rloa_naf_ws_destroy(rloa_naf_ws* ws) {
     if (ws == nullptr) return;
     trunk_tc_free(&ws->tc);
+    for (int i = 0; i < 2; i++) {
+        if (ws->side[i]) cudaStreamDestroy(ws->side[i]);
+        if (ws->fork_ev[i]) cudaEventDestroy(ws->fork_ev[i]);
+        if (ws->join_ev[i]) cudaEventDestroy(ws->join_ev[i]);
+    }
     if (ws->block) cudaFree(ws->block);
     delete ws;
 }
@@ -941,7 +996,7 @@ extern "C" int rloa_naf_ws_set_trunk(rloa_naf_ws* ws, int32_t mode) {
 }
 
 static size_t head_smem_bytes(const rloa_naf_ws* ws) {
-    return (size_t)(ws->NH * (ws->H + 1) + ((ws->NH + 31) & ~31) + kHeadWarps * ws->H) * sizeof(float);
+    return (size_t)(ws->NH * (ws->H + 1) + ((ws->NH + 31) & ~31) + kHeadWarps * ws->H + ws->H) * sizeof(float);
 }
 
 static int check_params(const rloa_naf_ws* ws, const rloa_naf_params* p, const char* who) {
@@ -1112,23 +1167,38 @@ extern "C" int rloa_naf_learn_grads(rloa_naf_ws* ws, const rloa_naf_params* mn, 
     if (rc != RLOA_OK) return rc;
     const size_t hsm = head_smem_bytes(ws);
     const int hblocks = head_blocks(B);
-    {   // target head: y = r + gamma V'(s')   (naf_algorithm.py:199)
+    const bool fused = H <= 256;
+    if (!fused) {   // target head: y = r + gamma V'(s')   (naf_algorithm.py:199)
         HeadArgs h = head_base(ws, 1, tg, B);
         h.reward = rewards; h.done = dones; h.gamma = hp->gamma; h.use_done = hp->use_done_mask; h.y_out = ws->y;
         naf_head_kernel<<<hblocks, kHeadWarps * 32, hsm, st>>>(h);
         RLOA_LAUNCHED();
     }
-    {   // main head: Q(s, a), squared TD error, gradients of the head pre-activations
+    {   // main head: Q(s, a), squared TD error, gradients of the head pre-activations; when fused, also the TD
+        // target of the same row from the target trunk and da2 = dZh Wh
         HeadArgs h = head_base(ws, 0, mn, B);
-        h.action = actions; h.trunc_action = hp->trunc_action; h.y_in = ws->y; h.dzh = ws->dzh; h.loss_part = ws->loss_part;
+        h.action = actions; h.trunc_action = hp->trunc_action; h.dzh = ws->dzh; h.loss_part = ws->loss_part;
+        if (fused) {
+            h.t_z2 = ws->z2[1]; h.t_scale = ws->scale[1][1]; h.t_shift = ws->shift[1][1]; h.t_wv = tg->w_v; h.t_bv = tg->b_v;
+            h.reward = rewards; h.done = dones; h.gamma = hp->gamma; h.use_done = hp->use_done_mask;
+            h.da_out = ws->da;
+        } else {
+            h.y_in = ws->y;
+        }
         naf_head_kernel<<<hblocks, kHeadWarps * 32, hsm, st>>>(h);
         RLOA_LAUNCHED();
     }
-    head_bias_grad_kernel<<<NH + 1, 256, 0, st>>>(ws->dzh, B, NH, A, grad + fl.bmu, grad + fl.bv, grad + fl.bl,
-                                                  ws->loss_part, hblocks, loss);
+    // fork: the head bias / weight gradients only feed the optimiser, so they run on a side stream beside the
+    // backward chain (in a captured CUDA graph this becomes a parallel branch) and join before the split-K sum
+    RLOA_CUDA(cudaEventRecord(ws->fork_ev[0], st));
+    RLOA_CUDA(cudaStreamWaitEvent(ws->side[0], ws->fork_ev[0], 0));
+    head_bias_grad_kernel<<<NH + 1, 256, 0, ws->side[0]>>>(ws->dzh, B, NH, A, grad + fl.bmu, grad + fl.bv, grad + fl.bl,
+                                                           ws->loss_part, hblocks, loss);
     RLOA_LAUNCHED();
-    pack_heads_kernel<<<(NH * H + 255) / 256, 256, 0, st>>>(mn->w_mu, mn->w_v, mn->w_l, A, NL, H, ws->wh_pack);
-    RLOA_LAUNCHED();
+    if (!fused) {
+        pack_heads_kernel<<<(NH * H + 255) / 256, 256, 0, st>>>(mn->w_mu, mn->w_v, mn->w_l, A, NL, H, ws->wh_pack);
+        RLOA_LAUNCHED();
+    }
     const int klen = splitk_len(B), nsplit = splitk_count(B);
     float* part_w2 = ws->splitk;
     float* part_w1 = part_w2 + (size_t)nsplit * H * H;
@@ -1136,19 +1206,24 @@ extern "C" int rloa_naf_learn_grads(rloa_naf_ws* ws, const rloa_naf_params* mn, 
     GemmBatch gb{};
     // dWh [NH][H] = dZh^T a2, a2 = relu(bn2(z2)) re-created in the prologue
     gb.a[0] = GemmArgs{ws->dzh, NH, ws->z2[0], H, part_wh, H, nullptr, ws->scale[0][1], ws->shift[0][1], NH, H, B, klen};
-    launch_gemm<kTN, true>(gb, 1, dim3((H + BN - 1) / BN, (NH + BM - 1) / BM, nsplit), st);
+    launch_gemm<kTN, true>(gb, 1, dim3((H + BN - 1) / BN, (NH + BM - 1) / BM, nsplit), ws->side[0]);
     RLOA_LAUNCHED();
-    // da2 [B][H] = dZh Wh
-    gb.a[0] = GemmArgs{ws->dzh, NH, ws->wh_pack, H, ws->da, H, nullptr, nullptr, nullptr, B, H, NH, 0};
-    launch_gemm<kNN, false>(gb, 1, dim3((H + BN - 1) / BN, (B + BM - 1) / BM, 1), st);
-    RLOA_LAUNCHED();
+    RLOA_CUDA(cudaEventRecord(ws->join_ev[0], ws->side[0]));
+    if (!fused) {   // da2 [B][H] = dZh Wh
+        gb.a[0] = GemmArgs{ws->dzh, NH, ws->wh_pack, H, ws->da, H, nullptr, nullptr, nullptr, B, H, NH, 0};
+        launch_gemm<kNN, false>(gb, 1, dim3((H + BN - 1) / BN, (B + BM - 1) / BM, 1), st);
+        RLOA_LAUNCHED();
+    }
     // through ReLU + BN2: da -> dz2 in place; bn2 weight/bias and hidden_layer.bias gradients
     rc = bn_relu_backward(ws, ws->da, ws->z2[0], mn->bn2_w, 1, B, grad + fl.bn2w, grad + fl.bn2b, grad + fl.b2, st);
     if (rc != RLOA_OK) return rc;
     // dW2 [H][H] = dz2^T a1, a1 = relu(bn1(z1))
     gb.a[0] = GemmArgs{ws->da, H, ws->z1[0], H, part_w2, H, nullptr, ws->scale[0][0], ws->shift[0][0], H, H, B, klen};
-    launch_gemm<kTN, true>(gb, 1, dim3((H + BN - 1) / BN, (H + BM - 1) / BM, nsplit), st);
+    RLOA_CUDA(cudaEventRecord(ws->fork_ev[1], st));
+    RLOA_CUDA(cudaStreamWaitEvent(ws->side[1], ws->fork_ev[1], 0));
+    launch_gemm<kTN, true>(gb, 1, dim3((H + BN - 1) / BN, (H + BM - 1) / BM, nsplit), ws->side[1]);
     RLOA_LAUNCHED();
+    RLOA_CUDA(cudaEventRecord(ws->join_ev[1], ws->side[1]));
     // da1 [B][H] = dz2 W2 -> reuse z2[1] (the target's z2 is no longer needed) as the output buffer
     float* da1 = ws->z2[1];
     gb.a[0] = GemmArgs{ws->da, H, mn->w2, H, da1, H, nullptr, nullptr, nullptr, B, H, H, 0};
@@ -1160,7 +1235,9 @@ extern "C" int rloa_naf_learn_grads(rloa_naf_ws* ws, const rloa_naf_params* mn, 
     gb.a[0] = GemmArgs{da1, H, states, S, part_w1, S, nullptr, nullptr, nullptr, H, S, B, klen};
     launch_gemm<kTN, false>(gb, 1, dim3((S + BN - 1) / BN, (H + BM - 1) / BM, nsplit), st);
     RLOA_LAUNCHED();
-    // fixed-order reduction of the split-K partials into the flat gradient
+    // join the side branches, then the fixed-order reduction of the split-K partials into the flat gradient
+    RLOA_CUDA(cudaStreamWaitEvent(st, ws->join_ev[0], 0));
+    RLOA_CUDA(cudaStreamWaitEvent(st, ws->join_ev[1], 0));
     ReduceArgs ra{};
     ra.s[0] = ReduceSeg{part_w2, grad + fl.w2, H * H, nsplit, (size_t)H * H};
     ra.s[1] = ReduceSeg{part_w1, grad + fl.w1, H * S, nsplit, (size_t)H * S};

@@ -22,18 +22,88 @@ __global__ void __launch_bounds__(kTpb) sim_dynamics_kernel(const __grid_constan
     if (env < S.n_envs) arm_dynamics<NLMAX>(M, S, env);
 }
 
-// launch 2: block = 32 arms x ndof columns, warp = one column of M^-1 for 32 arms
+// launch 2: block = 32 arms x ndof columns, warp = one column of M^-1 for 32 arms.  The factor records of the
+// block's 32 arms are staged once in shared memory ([link][component][arm], conflict-free) by all warps, so the
+// ndof column warps stop re-reading them from L2 and the serial tree walks see shared-memory latency.
 __global__ void __launch_bounds__(32 * kMaxDof) sim_minv_kernel(const __grid_constant__ ModelDev M, SimArrays S) {
-    const int env = blockIdx.x * 32 + threadIdx.x;
-    if (env < S.n_envs) arm_minv_column(M, S, env, threadIdx.y);
+    extern __shared__ float smF[];
+    const int env0 = blockIdx.x * 32;
+    const int N = S.n_envs, nrec = M.nl * kFRec;
+    const int nthreads = 32 * blockDim.y, flat = threadIdx.y * 32 + threadIdx.x;
+    for (int idx = flat; idx < nrec * 32; idx += nthreads) {
+        const int rec = idx >> 5, arm = idx & 31;
+        smF[idx] = env0 + arm < N ? S.F[(size_t)rec * N + env0 + arm] : 0.f;
+    }
+    __syncthreads();
+    const int env = env0 + threadIdx.x;
+    if (env < N) arm_minv_column(M, S, env, threadIdx.y, smF + threadIdx.x, 32, kFRec * 32);
 }
 
-// symmetric M^-1 kept in registers: entry (a, b) of the lower triangle
+// M^-1 and the velocity change dv of one arm, in registers, with two layouts:
+//   PACKED (ndof <= 12): full rows as float2 pairs, so a row update dv += delta * M^-1[d][:] is D/2 packed
+//       FFMA2 (fma.rn.f32x2, new on sm_100) instead of D scalar FFMAs — the Gauss-Seidel sweep is FMA-issue bound;
+//   scalar (ndof <= 16): lower triangle only (136 registers), scalar FFMAs.
 __device__ __forceinline__ constexpr int tri(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
+
+template <int D, bool PACKED>
+struct PgsState;
+
+template <int D>
+struct PgsState<D, false> {
+    float Mi[D * (D + 1) / 2];
+    float dv[D];
+    __device__ __forceinline__ void load(const float* __restrict__ minv, int ndof, size_t sN, int env) {
+#pragma unroll
+        for (int a = 0; a < D; a++) {
+            dv[a] = 0.f;
+#pragma unroll
+            for (int b = 0; b <= a; b++) Mi[tri(a, b)] = a < ndof ? minv[((size_t)a * ndof + b) * sN + env] : 0.f;
+        }
+    }
+    __device__ __forceinline__ float diag(int d) const { return Mi[tri(d, d)]; }
+    __device__ __forceinline__ float get(int d) const { return dv[d]; }
+    // dv += delta * M^-1[d][:]; the component the next row reads (`first`) is issued first
+    __device__ __forceinline__ void axpy(int d, float delta, int first) {
+        if (first >= 0 && first < D) dv[first] = fmaf(delta, Mi[tri(d, first)], dv[first]);
+#pragma unroll
+        for (int k = 0; k < D; k++)
+            if (k != first) dv[k] = fmaf(delta, Mi[tri(d, k)], dv[k]);
+    }
+};
+
+template <int D>
+struct PgsState<D, true> {
+    static constexpr int DP = (D + 1) / 2;
+    float2 M[D][DP];
+    float2 dv[DP];
+    __device__ __forceinline__ void load(const float* __restrict__ minv, int ndof, size_t sN, int env) {
+#pragma unroll
+        for (int k = 0; k < DP; k++) dv[k] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int a = 0; a < D; a++)
+#pragma unroll
+            for (int k = 0; k < DP; k++) {
+                const int b0 = 2 * k, b1 = 2 * k + 1;
+                M[a][k].x = (a < ndof && b0 < ndof) ? minv[((size_t)a * ndof + b0) * sN + env] : 0.f;
+                M[a][k].y = (a < ndof && b1 < ndof) ? minv[((size_t)a * ndof + b1) * sN + env] : 0.f;
+            }
+    }
+    __device__ __forceinline__ float diag(int d) const { return (d & 1) ? M[d][d >> 1].y : M[d][d >> 1].x; }
+    __device__ __forceinline__ float get(int d) const { return (d & 1) ? dv[d >> 1].y : dv[d >> 1].x; }
+    // dv += delta * M^-1[d][:]; the pair holding the component the next row reads (`first`) is issued first
+    __device__ __forceinline__ void axpy(int d, float delta, int first) {
+        const float2 dl = make_float2(delta, delta);
+        const int fp = (first >= 0 && first < D) ? (first >> 1) : -1;
+        if (fp >= 0) dv[fp] = __ffma2_rn(dl, M[d][fp], dv[fp]);
+#pragma unroll
+        for (int k = 0; k < DP; k++)
+            if (k != fp) dv[k] = __ffma2_rn(dl, M[d][k], dv[k]);
+    }
+};
 
 // launch 3: thread = arm.  Environment.step (reference environment.py:453-485) from the free velocity on:
 // motor / limit rows, projected Gauss-Seidel, integration, get_state, get_reward, is_terminal_state.
-template <int D, int NLMAX>
+template <int D, int NLMAX, bool PACKED, bool EXACT>
 __global__ void __launch_bounds__(kTpb)
 sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_constant__ StepCfgDev cfg, int mode,
                  const float* __restrict__ actions, const uint8_t* __restrict__ active, float* __restrict__ obs,
@@ -53,47 +123,54 @@ sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_c
     const bool is_reset = pending > 0;
     bool staged = false;
     if (run) {
-        const int ndof = M.ndof;
+        const int ndof = EXACT ? D : M.ndof;       // EXACT: the instantiation matches the model, no per-row guards
         const size_t sN = (size_t)N;
-        float Mi[D * (D + 1) / 2];
+        // ---- every global operand of the solve is requested up front, branch-free, so the whole batch costs one
+        // memory round trip (the stores to the motor table below would otherwise fence the loads of the next dof) ----
+        float q0[D], qs0[D], kp0[D], tp0[D], tv0[D], mi0[D], ac0[D];
 #pragma unroll
-        for (int a = 0; a < D; a++)
-#pragma unroll
-            for (int b = 0; b <= a; b++)
-                Mi[tri(a, b)] = a < ndof ? S.minv[((size_t)a * ndof + b) * sN + env] : 0.f;
+        for (int d = 0; d < D; d++) {
+            const int link = M.doflink[(EXACT || d < ndof) ? d : 0];
+            const size_t at = (size_t)link * sN + env;
+            q0[d] = S.q[at]; qs0[d] = S.qs[at];
+            kp0[d] = S.kp[at]; tp0[d] = S.tpos[at]; tv0[d] = S.tvel[at]; mi0[d] = S.maximp[at];
+            const int ai = cfg.act_index[link];
+            ac0[d] = (ai >= 0 && actions != nullptr) ? actions[(size_t)env * cfg.n_act + ai] : 0.f;
+        }
+        PgsState<D, PACKED> P;
+        P.load(S.minv, ndof, sN, env);
 
         // ---- constraint rows: joint limits first (created at import), then one motor row per dof ----
-        float rhs[D], mx[D], jdi[D], dv[D], app[D];
+        float rhs[D], mx[D], jdi[D], app[D], csum[D];   // csum = app + rhs, kept current off the critical path
         unsigned mlo = 0u, mhi = 0u;
         const float inv_dt = M.inv_dt;
 #pragma unroll
         for (int d = 0; d < D; d++) {
-            rhs[d] = 0.f; mx[d] = 0.f; jdi[d] = 0.f; dv[d] = 0.f; app[d] = 0.f;
-            if (d < ndof) {
+            rhs[d] = 0.f; mx[d] = 0.f; jdi[d] = 0.f; app[d] = 0.f; csum[d] = 0.f;
+            if (EXACT || d < ndof) {
                 const int link = M.doflink[d];
                 const size_t at = (size_t)link * sN + env;
-                const float q = S.q[at], qs = S.qs[at];
+                const float q = q0[d], qs = qs0[d];
                 // setJointMotorControl2: VELOCITY_CONTROL on involved joints (environment.py:464-469), then
                 // POSITION_CONTROL target 0 on the fixed joints (:472-476); other joints keep their motor
                 const int ai = cfg.act_index[link];
                 const bool fixedj = (cfg.fixed_mask >> link) & 1u;
-                float kp, tpos, tvel, maximp;
-                if (is_reset || (!fixedj && ai < 0)) {
-                    kp = S.kp[at]; tpos = S.tpos[at]; tvel = S.tvel[at]; maximp = S.maximp[at];
-                } else {
+                float kp = kp0[d], tpos = tp0[d], tvel = tv0[d], maximp = mi0[d];
+                if (!(is_reset || (!fixedj && ai < 0))) {
                     if (fixedj) {
                         kp = 0.1f; tpos = 0.f; tvel = 0.f; maximp = cfg.pos_maximp;
                     } else {
-                        kp = 0.f; tpos = 0.f; tvel = actions[(size_t)env * cfg.n_act + ai]; maximp = cfg.vel_maximp;
+                        kp = 0.f; tpos = 0.f; tvel = ac0[d]; maximp = cfg.vel_maximp;
                     }
                     S.kp[at] = kp; S.tpos[at] = tpos; S.tvel[at] = tvel; S.maximp[at] = maximp;
                 }
-                const float j = 1.f / Mi[tri(d, d)];
+                const float j = 1.f / P.diag(d);
                 jdi[d] = j;
                 mx[d] = maximp;
                 // btMultiBodyJointMotor: rhs = kp (q_des - q)/dt + qs + kd (qd_des - qs), kd = 1, erp = 1
                 // (the row's right-hand side is rhs - qs; formed directly to avoid the cancellation)
                 rhs[d] = fmaf(kp * (tpos - q), inv_dt, tvel - qs) * j;
+                csum[d] = rhs[d];
                 if (M.has_limit[link]) {
                     const float pen0 = q - M.lower[link], pen1 = M.upper[link] - q;
                     if (!(pen0 > 0.f)) {
@@ -115,33 +192,30 @@ sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_c
         const int iters = M.iters;
         int it = 0;
         float resid = 0.f;
-        // Row update, branch-free: Bullet clamps the accumulated impulse and re-derives delta only when the clamp
-        // is active (btMultiBodyConstraintSolver::resolveSingleConstraintRowGeneric); a select keeps the
-        // unclamped delta bit-identical while the compiler emits no divergent branch.
-        auto motor_row = [&](const int d) {
-            const float delta0 = fmaf(-dv[d], jdi[d], rhs[d]);
-            const float sum = app[d] + delta0;
+        // Row update (btMultiBodyConstraintSolver::resolveSingleConstraintRowGeneric), branch-free and with the
+        // shortest dependent chain from dv[d] to the dv the next row reads:
+        //   sum = (applied + rhs) - dv[d] / A_dd   [Bullet: applied + (rhs - dv[d] / A_dd); differs by one rounding]
+        //   applied' = clamp(sum) ; delta = applied' - applied ; dv += delta * M^-1[d][:]
+        auto motor_row = [&](const int d, const int next) {
+            const float sum = fmaf(-P.get(d), jdi[d], csum[d]);
             const float napp = fminf(fmaxf(sum, -mx[d]), mx[d]);
-            const float delta = (napp == sum) ? delta0 : napp - app[d];
+            const float delta = napp - app[d];
+            P.axpy(d, delta, next);
             app[d] = napp;
-#pragma unroll
-            for (int k = 0; k < D; k++) dv[k] = fmaf(delta, Mi[tri(d, k)], dv[k]);
-            const float dvel = delta * Mi[tri(d, d)];
+            csum[d] = napp + rhs[d];
+            const float dvel = delta * P.diag(d);
             resid = fmaxf(resid, dvel * dvel);
         };
         auto limit_row = [&](const int d, const int side) {
             const float sgn = side ? -1.f : 1.f;
             float* r = sm_lim + (2 * side * D + d) * kTpb;
             const float a0 = r[D * kTpb];
-            const float delta0 = fmaf(-(sgn * dv[d]), jdi[d], r[0]);
-            const float sum = a0 + delta0;
+            const float sum = fmaf(-(sgn * P.get(d)), jdi[d], a0 + r[0]);
             const float napp = fminf(fmaxf(sum, 0.f), limit_hi);
-            const float delta = (napp == sum) ? delta0 : napp - a0;
+            const float delta = napp - a0;
             r[D * kTpb] = napp;
-            const float sd = sgn * delta;
-#pragma unroll
-            for (int k = 0; k < D; k++) dv[k] = fmaf(sd, Mi[tri(d, k)], dv[k]);
-            const float dvel = delta * Mi[tri(d, d)];
+            P.axpy(d, sgn * delta, -1);
+            const float dvel = delta * P.diag(d);
             resid = fmaxf(resid, dvel * dvel);
         };
         for (it = 0; it < iters; it++) {
@@ -156,11 +230,11 @@ sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_c
                 }
 #pragma unroll
                 for (int d = 0; d < D; d++)
-                    if (d < ndof) motor_row(d);
+                    if (EXACT || d < ndof) motor_row(d, d + 1);
             } else {
 #pragma unroll
                 for (int d = D - 1; d >= 0; d--)
-                    if (d < ndof) motor_row(d);
+                    if (EXACT || d < ndof) motor_row(d, d - 1);
                 if (mlo | mhi) {
 #pragma unroll
                     for (int d = D - 1; d >= 0; d--) {
@@ -172,15 +246,23 @@ sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_c
             if (!(resid > thresh) || it >= iters - 1) { it++; break; }
         }
 
-        // ---- velocity and position update (stepPositionsMultiDof) ----
+        // ---- velocity and position update (stepPositionsMultiDof); q and the free velocity are re-read (one batch
+        // of independent L2 hits) rather than held in 24 registers across the sweep ----
         const float max_vel = M.max_vel, dt = M.dt;
+        float qe[D], qse[D];
 #pragma unroll
         for (int d = 0; d < D; d++) {
-            if (d < ndof) {
+            const size_t at = (size_t)M.doflink[(EXACT || d < ndof) ? d : 0] * sN + env;
+            qe[d] = S.q[at];
+            qse[d] = S.qs[at];
+        }
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            if (EXACT || d < ndof) {
                 const size_t at = (size_t)M.doflink[d] * sN + env;
-                const float x = fminf(fmaxf(S.qs[at] + dv[d], -max_vel), max_vel);
+                const float x = fminf(fmaxf(qse[d] + P.get(d), -max_vel), max_vel);
                 S.qd[at] = x;
-                S.q[at] = fmaf(dt, x, S.q[at]);
+                S.q[at] = fmaf(dt, x, qe[d]);
             }
         }
         const int nl = M.nl;
@@ -516,6 +598,7 @@ extern "C" int rloa_sim_create(const rloa_model* m, int32_t n_envs, rloa_sim** o
     s->a.target = s->a.minv + N * ndof * ndof; s->a.obstacle = s->a.target + 3 * N;
     s->a.iters = reinterpret_cast<int*>(s->a.obstacle + 3 * N);
     s->a.reset_left = s->a.iters + n_envs;
+    cudaFuncSetAttribute(sim_minv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxLinks * kFRec * 32 * (int)sizeof(float));
     cudaMemset(s->block, 0, floats * sizeof(float));
     sim_clear_kernel<<<(unsigned)((n + 255) / 256), 256>>>(s->a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -627,14 +710,17 @@ static int launch_solve(const rloa_sim* s, const StepCfgDev& c, int mode, const 
     const ModelDev& h = s->model->host;
     const unsigned blocks = (unsigned)((s->a.n_envs + kTpb - 1) / kTpb);
     const int so = 9 + 2 * h.n_obs;
-#define RLOA_SOLVE(D)                                                                                              \
-    sim_solve_kernel<D, NLMAX><<<blocks, kTpb, (size_t)(kTpb * so + 4 * D * kTpb) * sizeof(float), st>>>(          \
+#define RLOA_SOLVE(D, EXACT)                                                                                       \
+    sim_solve_kernel<D, NLMAX, (D <= 12), EXACT><<<blocks, kTpb, (size_t)(kTpb * so + 4 * D * kTpb) * sizeof(float), st>>>( \
         h, s->a, c, mode, actions, active, obs, reward, done, valid)
-    if (h.ndof <= 4) RLOA_SOLVE(4);
-    else if (h.ndof <= 8) RLOA_SOLVE(8);
-    else if (h.ndof <= 9) RLOA_SOLVE(9);
-    else if (h.ndof <= 12) RLOA_SOLVE(12);
-    else RLOA_SOLVE(16);
+    if (h.ndof == 12 && NLMAX == 16) RLOA_SOLVE(12, true);         // KUKA iiwa + gripper
+    else if (h.ndof == 9 && NLMAX == 16) RLOA_SOLVE(9, true);      // Panda
+    else if (h.ndof == 7 && NLMAX == 16) RLOA_SOLVE(7, true);      // bare 7-dof arm
+    else if (h.ndof <= 4) RLOA_SOLVE(4, false);
+    else if (h.ndof <= 8) RLOA_SOLVE(8, false);
+    else if (h.ndof <= 10) RLOA_SOLVE(10, false);
+    else if (h.ndof <= 12) RLOA_SOLVE(12, false);
+    else RLOA_SOLVE(16, false);
 #undef RLOA_SOLVE
     RLOA_LAUNCHED();
     return RLOA_OK;
@@ -648,7 +734,7 @@ static int launch_substep(const rloa_sim* s, const StepCfgDev& c, int mode, cons
     if (h.nl <= 16) sim_dynamics_kernel<16><<<blocks, kTpb, 0, st>>>(h, s->a);
     else sim_dynamics_kernel<32><<<blocks, kTpb, 0, st>>>(h, s->a);
     RLOA_LAUNCHED();
-    sim_minv_kernel<<<blocks, dim3(32, h.ndof), 0, st>>>(h, s->a);
+    sim_minv_kernel<<<blocks, dim3(32, h.ndof), (size_t)h.nl * kFRec * 32 * sizeof(float), st>>>(h, s->a);
     RLOA_LAUNCHED();
     if (h.nl <= 16) return launch_solve<16>(s, c, mode, actions, active, obs, reward, done, valid, st);
     return launch_solve<32>(s, c, mode, actions, active, obs, reward, done, valid, st);

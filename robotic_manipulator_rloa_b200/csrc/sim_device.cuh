@@ -320,6 +320,14 @@ __device__ __forceinline__ void arm_dynamics(const ModelDev& M, const SimArrays&
     const int N = S.n_envs, nl = M.nl;
     float L[NLMAX * kLRec];
     float slot[kMaxSlots * 27];          // forward sweeps use the first 18 / 6 floats of a slot
+    // all joint coordinates are requested before the serial sweep starts (one memory round trip instead of one
+    // per link); the sweep then reads them from L1-resident local memory
+    float qv[NLMAX], qdv[NLMAX];
+#pragma unroll
+    for (int i = 0; i < NLMAX; i++) {
+        qv[i] = i < nl ? S.q[(size_t)i * N + env] : 0.f;
+        qdv[i] = i < nl ? S.qd[(size_t)i * N + env] : 0.f;
+    }
 
     // ---- root -> leaves: poses, velocities, Coriolis terms, zero-acceleration forces ----
     {
@@ -339,7 +347,7 @@ __device__ __forceinline__ void arm_dynamics(const ModelDev& M, const SimArrays&
                 for (int k = 0; k < 9; k++) Rp.m[k] = sl[k];
                 pp = ld3(sl + 9); wp = ld3(sl + 12); vp = ld3(sl + 15);
             }
-            const float q = S.q[(size_t)i * N + env], qd = S.qd[(size_t)i * N + env];
+            const float q = qv[i], qd = qdv[i];
             M3 Rl;
             V3 pl, dd;
             joint_transform(M, i, q, Rl, pl, dd);
@@ -524,7 +532,7 @@ __device__ __forceinline__ void arm_dynamics(const ModelDev& M, const SimArrays&
                 st3(slot + sv * 27, a_a);
                 st3(slot + sv * 27 + 3, a_l);
             }
-            const float qd = S.qd[(size_t)i * N + env];
+            const float qd = qdv[i];
             const bool hasdof = M.jtype[i] != RLOA_JOINT_FIXED;
             S.qs[(size_t)i * N + env] = hasdof ? fminf(fmaxf(fmaf(dt, qdd, qd), -max_vel), max_vel) : 0.f;
         }
@@ -535,22 +543,24 @@ __device__ __forceinline__ void arm_dynamics(const ModelDev& M, const SimArrays&
 // Kernel 2 body: column j of M^-1 for one arm (calcAccelerationDeltasMultiDof with a unit impulse on
 // dof j): test force up the ancestors of the dof's link, accelerations down the whole tree.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void arm_minv_column(const ModelDev& M, const SimArrays& S, int env, int j) {
+// F: this arm's factor records, component k of link i at F[i * link_stride + k * k_stride] (shared-memory stage)
+__device__ __forceinline__ void arm_minv_column(const ModelDev& M, const SimArrays& S, int env, int j,
+                                                const float* __restrict__ F, int k_stride, int link_stride) {
     const int N = S.n_envs, nl = M.nl, ndof = M.ndof;
     const int lj = M.doflink[j];
     float Y[kMaxLinks];
 #pragma unroll
     for (int i = 0; i < kMaxLinks; i++) Y[i] = 0.f;
-    const float* F = S.F + env;
+    const int ks = k_stride;
     {
         V3 zf_a = v3(0.f, 0.f, 0.f), zf_l = zf_a;
         int cur = lj;
         while (cur >= 0) {
-            const float* Fi = F + (size_t)cur * kFRec * N;
-            const V3 sa = v3(Fi[0], Fi[(size_t)N], Fi[(size_t)2 * N]), sl = v3(Fi[(size_t)3 * N], Fi[(size_t)4 * N], Fi[(size_t)5 * N]);
-            const V3 ha = v3(Fi[(size_t)6 * N], Fi[(size_t)7 * N], Fi[(size_t)8 * N]), hl = v3(Fi[(size_t)9 * N], Fi[(size_t)10 * N], Fi[(size_t)11 * N]);
-            const V3 rr = v3(Fi[(size_t)12 * N], Fi[(size_t)13 * N], Fi[(size_t)14 * N]);
-            const float iD = Fi[(size_t)15 * N];
+            const float* Fi = F + cur * link_stride;
+            const V3 sa = v3(Fi[0], Fi[ks], Fi[2 * ks]), sl = v3(Fi[3 * ks], Fi[4 * ks], Fi[5 * ks]);
+            const V3 ha = v3(Fi[6 * ks], Fi[7 * ks], Fi[8 * ks]), hl = v3(Fi[9 * ks], Fi[10 * ks], Fi[11 * ks]);
+            const V3 rr = v3(Fi[12 * ks], Fi[13 * ks], Fi[14 * ks]);
+            const float iD = Fi[15 * ks];
             float y = (cur == lj ? 1.f : 0.f) - (dot(sa, zf_a) + dot(sl, zf_l));
             if (iD == 0.f) y = 0.f;
             Y[cur] = y;
@@ -565,7 +575,7 @@ __device__ __forceinline__ void arm_minv_column(const ModelDev& M, const SimArra
         V3 a_a = v3(0.f, 0.f, 0.f), a_l = a_a;
         float sv[kMaxSlots * 6];
         for (int i = 0; i < nl; i++) {
-            const float* Fi = F + (size_t)i * kFRec * N;
+            const float* Fi = F + i * link_stride;
             const int src = M.fwsrc[i];
             V3 p_a = a_a, p_l = a_l;
             if (src == 0) {
@@ -574,14 +584,14 @@ __device__ __forceinline__ void arm_minv_column(const ModelDev& M, const SimArra
                 p_a = ld3(sv + (src - 2) * 6);
                 p_l = ld3(sv + (src - 2) * 6 + 3);
             }
-            const V3 rr = v3(Fi[(size_t)12 * N], Fi[(size_t)13 * N], Fi[(size_t)14 * N]);
+            const V3 rr = v3(Fi[12 * ks], Fi[13 * ks], Fi[14 * ks]);
             a_a = p_a;
             a_l = p_l + cross(p_a, rr);
             const int di = M.dofidx[i];
             if (di >= 0) {
-                const V3 sa = v3(Fi[0], Fi[(size_t)N], Fi[(size_t)2 * N]), sl = v3(Fi[(size_t)3 * N], Fi[(size_t)4 * N], Fi[(size_t)5 * N]);
-                const V3 ha = v3(Fi[(size_t)6 * N], Fi[(size_t)7 * N], Fi[(size_t)8 * N]), hl = v3(Fi[(size_t)9 * N], Fi[(size_t)10 * N], Fi[(size_t)11 * N]);
-                const float x = (Y[i] - (dot(ha, a_a) + dot(hl, a_l))) * Fi[(size_t)15 * N];
+                const V3 sa = v3(Fi[0], Fi[ks], Fi[2 * ks]), sl = v3(Fi[3 * ks], Fi[4 * ks], Fi[5 * ks]);
+                const V3 ha = v3(Fi[6 * ks], Fi[7 * ks], Fi[8 * ks]), hl = v3(Fi[9 * ks], Fi[10 * ks], Fi[11 * ks]);
+                const float x = (Y[i] - (dot(ha, a_a) + dot(hl, a_l))) * Fi[15 * ks];
                 a_a = fma3(x, sa, a_a);
                 a_l = fma3(x, sl, a_l);
                 S.minv[((size_t)di * ndof + j) * N + env] = x;

@@ -26,6 +26,7 @@ from .. import _native as N
 from ..utils.exceptions import MissingWeightsFile
 from ..utils.logger import get_global_logger
 from ..utils.replay_buffer import ReplayBuffer
+from ..utils import distributed as rdist
 from .naf_neural_network import NAF, NafWorkspace
 
 logger = get_global_logger()
@@ -103,9 +104,7 @@ class NAFAgent:
         self._bufs = None
         self.last_loss = None
         self.last_grad_norm = None
-        self.world_size = 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            self.world_size = torch.distributed.get_world_size()
+        self.rank, self.world_size = rdist.world()
 
     # ------------------------------------------------------------------------------------------
     # native plumbing
@@ -240,7 +239,7 @@ class NAFAgent:
                                             r.data_ptr(), s2.data_ptr(), d.data_ptr(), B, C.byref(hp),
                                             b['grad'].data_ptr(), b['loss'].data_ptr(), st), 'rloa_naf_learn_grads')
         if self.world_size > 1:          # the one exchange step of the data-parallel path (NCCL over NVLink)
-            torch.distributed.all_reduce(b['grad'])
+            rdist.allreduce_gradient(b['grad'])
         adam = self.optimizer.native()
         N.check(ws.lib.rloa_naf_learn_apply(ws.handle, C.byref(pm), C.byref(pt), C.byref(adam), C.byref(hp),
                                             b['grad'].data_ptr(), b['gnorm'].data_ptr(), st), 'rloa_naf_learn_apply')

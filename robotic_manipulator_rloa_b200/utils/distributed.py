@@ -1,0 +1,47 @@
+"""
+Host-side plumbing of the data-parallel path: one process per GPU, env instances sharded by
+rank, no data-path collective in the rollout, and ONE exchange per NAF update — the all-reduce of the flat main-net
+gradient between rloa_naf_learn_grads and rloa_naf_learn_apply.  The reference is single-process
+(naf_components/naf_algorithm.py:180-213); these helpers define what "the same update on every rank" means.
+
+Backend-agnostic on purpose: NCCL on the GPUs, gloo in the CPU tests (tests/test_distributed_cpu.py).
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n_total: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Env index range [lo, hi) owned by `rank`: contiguous, disjoint, covering, sizes differing by at most one."""
+    if not (0 <= rank < world_size):
+        raise ValueError(f'rank {rank} outside world of {world_size}')
+    base, extra = divmod(int(n_total), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def rank_seed(seed: int, rank: int, stream: int = 0) -> int:
+    """Per-rank seed for exploration noise / replay sampling / start poses (stream 0, 1, 2).  Network
+    initialisation does NOT use this: every rank seeds the NAF weights with the same `seed`, so that parameters
+    start identical and stay identical without a broadcast."""
+    return (int(seed) + 1000003 * (int(rank) + 1) + 7919 * int(stream)) & 0x7FFFFFFFFFFFFFFF
+
+
+def allreduce_gradient(flat_grad: torch.Tensor) -> float:
+    """Sum the flat gradient over ranks in place; returns the scale (1 / world_size) the optimiser must apply
+    (rloa_naf_hyper.grad_scale), i.e. the ranks step with the MEAN gradient — clip norm and Adam update are
+    then computed from identical numbers on every rank."""
+    _, w = world()
+    if w > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+    return 1.0 / float(w)
