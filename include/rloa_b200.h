@@ -274,7 +274,7 @@ typedef struct {
     int32_t capacity, state_size, action_size;
     float *states, *actions, *rewards, *next_states, *dones;
     int64_t* cursor;               /* device scalar: total transitions ever appended */
-    int32_t* scratch;              /* device, ZERO-INITIALISED, >= (max n per append + 255) / 256 + 1 ints:
+    int32_t* scratch;              /* device, ZERO-INITIALISED, >= (max n per append + 63) / 64 + 1 ints:
                                       [0] completion ticket (returns to 0), [1..] per-block valid counts */
 } rloa_replay;
 

@@ -25,7 +25,7 @@ namespace rloa {
 constexpr int kTcM = 128;                     // rows per CTA (UMMA M)
 constexpr int kTcN = 64;                      // output features per CTA (UMMA N)
 constexpr int kTcK = 256;                     // contraction length (hidden)
-constexpr int kTcThreads = 128;
+constexpr int kTcThreads = 256;              // 8 warps stage the operands; warps 0-3 read the accumulator back
 constexpr int kTcKBlocks = kTcK / 64;         // 128-byte swizzle rows hold 64 bf16
 constexpr uint32_t kABlockBytes = kTcM * 128; // one k-block of A: 128 rows x 128 B
 constexpr uint32_t kBBlockBytes = kTcN * 128;
@@ -97,23 +97,45 @@ __global__ void __launch_bounds__(kTcThreads) trunk_tc_layer2_kernel(const __gri
         sc[i] = g.scale[lane * 8 + i];
         sh[i] = g.shift[lane * 8 + i];
     }
-#pragma unroll 4
-    for (int r = warp; r < kTcM; r += 4) {
-        const int row = m0 + r;
-        uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-        if (row < B) {
-            const float4* src = reinterpret_cast<const float4*>(g.z1 + (size_t)row * kTcK + lane * 8);
-            packed = pack8<true>(src[0], src[1], sc, sh);
+    // 8 rows per warp per batch, every load of a batch issued before the first conversion (memory-level
+    // parallelism: the kernel is one L2 round trip per batch, not per row)
+    constexpr int kWarps = kTcThreads / 32, kBatch = 8;
+#pragma unroll 1
+    for (int r0 = warp; r0 < kTcM; r0 += kWarps * kBatch) {
+        float4 lo[kBatch], hi[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; b++) {
+            const int row = m0 + r0 + b * kWarps;
+            lo[b] = hi[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < B) {
+                const float4* src = reinterpret_cast<const float4*>(g.z1 + (size_t)row * kTcK + lane * 8);
+                lo[b] = src[0];
+                hi[b] = src[1];
+            }
         }
-        const uint32_t off = kb * kABlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(sm_a + off) = packed;
+#pragma unroll
+        for (int b = 0; b < kBatch; b++) {
+            const int r = r0 + b * kWarps;
+            uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+            if (m0 + r < B) packed = pack8<true>(lo[b], hi[b], sc, sh);
+            const uint32_t off = kb * kABlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(sm_a + off) = packed;
+        }
     }
-#pragma unroll 4
-    for (int r = warp; r < kTcN; r += 4) {
-        const float4* src = reinterpret_cast<const float4*>(g.w2 + (size_t)(n0 + r) * kTcK + lane * 8);
-        const uint4 packed = pack8<false>(src[0], src[1], nullptr, nullptr);
-        const uint32_t off = kb * kBBlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(sm_b + off) = packed;
+    {
+        float4 lo[kTcN / kWarps], hi[kTcN / kWarps];
+#pragma unroll
+        for (int b = 0; b < kTcN / kWarps; b++) {
+            const float4* src = reinterpret_cast<const float4*>(g.w2 + (size_t)(n0 + warp + b * kWarps) * kTcK + lane * 8);
+            lo[b] = src[0];
+            hi[b] = src[1];
+        }
+#pragma unroll
+        for (int b = 0; b < kTcN / kWarps; b++) {
+            const int r = warp + b * kWarps;
+            const uint32_t off = kb * kBBlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(sm_b + off) = pack8<false>(lo[b], hi[b], nullptr, nullptr);
+        }
     }
     // generic-proxy writes -> visible to the async proxy (tensor core operand fetch)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -161,13 +183,14 @@ __global__ void __launch_bounds__(kTcThreads) trunk_tc_layer2_kernel(const __gri
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- epilogue: TMEM lane = tile row; warp w owns lanes 32 w .. 32 w + 31 ----
-    const int row = m0 + warp * 32 + lane;
+    // ---- epilogue: TMEM lane = tile row; warp w < 4 owns lanes 32 w .. 32 w + 31, columns 0-31 and 32-63 go to
+    // warps w and w + 4 (a warp may only touch the TMEM lanes 32 (w % 4) .. + 31) ----
+    const int row = m0 + (warp & 3) * 32 + lane;
     float* dst = g.z2 + (size_t)row * kTcK + n0;
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
+    {
+        const int half = warp >> 2;
         uint32_t v[32];
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + half * 32;
+        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * 32;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "

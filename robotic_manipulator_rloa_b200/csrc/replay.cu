@@ -9,7 +9,8 @@
 
 namespace rloa {
 
-constexpr int kAppendRows = 256;       // transition rows per block
+constexpr int kAppendRows = 64;        // transition rows per block
+constexpr int kAppendThreads = 256;
 
 __global__ void __launch_bounds__(kAppendRows) replay_count_kernel(const uint8_t* __restrict__ valid, int n,
                                                                    int* __restrict__ block_counts) {
@@ -23,23 +24,21 @@ __global__ void __launch_bounds__(kAppendRows) replay_count_kernel(const uint8_t
 // copies are flat loops over the block's [256][S] / [256][A] sub-matrices (coalesced reads, and coalesced writes
 // because ranks of neighbouring rows are consecutive).  The last block to finish bumps the cursor: every block
 // reads the cursor before it takes its ticket, so the bump cannot overtake a reader.
-__global__ void __launch_bounds__(kAppendRows)
+__global__ void __launch_bounds__(kAppendThreads)
 replay_append_kernel(rloa_replay rb, int n, const float* __restrict__ states, const float* __restrict__ actions,
                      const float* __restrict__ rewards, const float* __restrict__ next_states,
                      const uint8_t* __restrict__ dones, const uint8_t* __restrict__ valid,
                      const int* __restrict__ block_counts, unsigned* __restrict__ ticket) {
-    __shared__ int warp_sums[kAppendRows / 32];
     __shared__ int s_slot[kAppendRows];
-    __shared__ int s_red[kAppendRows / 32];
+    __shared__ int s_red[2][kAppendThreads / 32];
+    __shared__ int s_wsum[kAppendRows / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row0 = blockIdx.x * kAppendRows;
-    const int i = row0 + tid;
-    const bool v = i < n && (valid == nullptr || valid[i] != 0);
     const long long cur = *reinterpret_cast<const volatile long long*>(rb.cursor);
     // valid rows of the earlier blocks / of all blocks
     int before = 0, total = 0;
     if (valid != nullptr) {
-        for (int b = tid; b < (int)gridDim.x; b += kAppendRows) {
+        for (int b = tid; b < (int)gridDim.x; b += kAppendThreads) {
             const int cnt = block_counts[b];
             total += cnt;
             if (b < (int)blockIdx.x) before += cnt;
@@ -49,43 +48,65 @@ replay_append_kernel(rloa_replay rb, int n, const float* __restrict__ states, co
             before += __shfl_xor_sync(0xffffffffu, before, off);
             total += __shfl_xor_sync(0xffffffffu, total, off);
         }
-        if (lane == 0) { warp_sums[warp] = before; s_red[warp] = total; }
+        if (lane == 0) { s_red[0][warp] = before; s_red[1][warp] = total; }
         __syncthreads();
         before = 0; total = 0;
-        for (int w = 0; w < kAppendRows / 32; w++) { before += warp_sums[w]; total += s_red[w]; }
-        __syncthreads();
+        for (int w = 0; w < kAppendThreads / 32; w++) { before += s_red[0][w]; total += s_red[1][w]; }
     } else {
         before = row0;
         total = n;
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, v);
-    const int in_warp = __popc(bal & ((1u << lane) - 1u));
-    if (lane == 0) warp_sums[warp] = __popc(bal);
+    // ranks of this block's rows: the first kAppendRows threads own one row each
+    bool v = false;
+    int in_warp = 0;
+    if (tid < kAppendRows) {
+        const int i = row0 + tid;
+        v = i < n && (valid == nullptr || valid[i] != 0);
+        const unsigned bal = __ballot_sync(0xffffffffu, v);
+        in_warp = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) s_wsum[warp] = __popc(bal);
+    }
     __syncthreads();
-    int wbase = 0;
-    for (int w = 0; w < warp; w++) wbase += warp_sums[w];
-    const int rank = before + wbase + in_warp;
-    s_slot[tid] = v ? (int)((cur + rank) % rb.capacity) : -1;
+    if (tid < kAppendRows) {
+        int wbase = 0;
+        for (int w = 0; w < warp; w++) wbase += s_wsum[w];
+        const int rank = before + wbase + in_warp;
+        const int slot = v ? (int)((cur + rank) % rb.capacity) : -1;
+        s_slot[tid] = slot;
+        if (v) {
+            rb.rewards[slot] = rewards[row0 + tid];
+            rb.dones[slot] = dones != nullptr ? (float)dones[row0 + tid] : 0.f;
+        }
+    }
     __syncthreads();
     const int S = rb.state_size, A = rb.action_size;
     const int rows = min(kAppendRows, n - row0);
-    for (int e = tid; e < rows * S; e += kAppendRows) {
-        const int r = e / S, k = e - r * S;
-        const int slot = s_slot[r];
-        if (slot >= 0) {
-            rb.states[(size_t)slot * S + k] = states[(size_t)row0 * S + e];
-            rb.next_states[(size_t)slot * S + k] = next_states[(size_t)row0 * S + e];
+    // flat copies of the block's [rows][S] / [rows][A] sub-matrices, four independent loads in flight per thread
+    for (int e0 = tid; e0 < rows * S; e0 += 4 * kAppendThreads) {
+        float a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = e0 + u * kAppendThreads;
+            a[u] = e < rows * S ? states[(size_t)row0 * S + e] : 0.f;
+            b[u] = e < rows * S ? next_states[(size_t)row0 * S + e] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = e0 + u * kAppendThreads;
+            if (e < rows * S) {
+                const int r = e / S, k = e - r * S;
+                const int slot = s_slot[r];
+                if (slot >= 0) {
+                    rb.states[(size_t)slot * S + k] = a[u];
+                    rb.next_states[(size_t)slot * S + k] = b[u];
+                }
+            }
         }
     }
-    for (int e = tid; e < rows * A; e += kAppendRows) {
+    for (int e = tid; e < rows * A; e += kAppendThreads) {
         const int r = e / A, k = e - r * A;
         const int slot = s_slot[r];
         if (slot >= 0) rb.actions[(size_t)slot * A + k] = actions[(size_t)row0 * A + e];
-    }
-    if (v) {
-        const int slot = s_slot[tid];
-        rb.rewards[slot] = rewards[i];
-        rb.dones[slot] = dones != nullptr ? (float)dones[i] : 0.f;
     }
     __syncthreads();
     if (tid == 0) {
@@ -175,7 +196,7 @@ extern "C" int rloa_replay_append(const rloa_replay* rb, int32_t n, const float*
         RLOA_LAUNCHED();
     }
     // scratch[0] = ticket counter (zero at rest), scratch[1..] = per-block valid counts
-    replay_append_kernel<<<nblocks, kAppendRows, 0, st>>>(*rb, n, states, actions, rewards, next_states, dones, valid,
+    replay_append_kernel<<<nblocks, kAppendThreads, 0, st>>>(*rb, n, states, actions, rewards, next_states, dones, valid,
                                                          rb->scratch + 1, reinterpret_cast<unsigned*>(rb->scratch));
     RLOA_LAUNCHED();
     return RLOA_OK;

@@ -23,8 +23,11 @@ class NafWorkspace:
     """Owns an rloa_naf_ws handle (activations / gradient scratch) sized for ``max_batch`` rows."""
 
     def __init__(self, state_size: int, action_size: int, hidden: int, max_batch: int, device: torch.device):
-        self.lib = N.lib()
         self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise N.NativeLibraryError('the NAF network runs in librloa_b200.so (sm_100a): a CUDA device is required, '
+                                       'there is no CPU fallback')
+        self.lib = N.lib()
         self.shape = (state_size, action_size, hidden)
         self.max_batch = int(max_batch)
         self.trunk_mode = 0

@@ -45,7 +45,7 @@ class ReplayBuffer:
         self.rewards = torch.zeros(cap, **f32)
         self.dones = torch.zeros(cap, **f32)
         self.cursor = torch.zeros(1, dtype=torch.int64, device=self.device)
-        self.scratch = torch.zeros((self._max_append + 255) // 256 + 2, dtype=torch.int32, device=self.device)
+        self.scratch = torch.zeros((self._max_append + 63) // 64 + 2, dtype=torch.int32, device=self.device)
         rb = N.Replay()
         rb.capacity, rb.state_size, rb.action_size = cap, self.state_size, self.action_size
         rb.states, rb.actions, rb.rewards = self.states.data_ptr(), self.actions.data_ptr(), self.rewards.data_ptr()
@@ -85,7 +85,7 @@ class ReplayBuffer:
             self._allocate(states.shape[1], actions.shape[1])
         if n > self._max_append and valid is not None:
             self._max_append = n
-            self.scratch = torch.zeros((n + 255) // 256 + 2, dtype=torch.int32, device=self.device)
+            self.scratch = torch.zeros((n + 63) // 64 + 2, dtype=torch.int32, device=self.device)
             self._rb.scratch = self.scratch.data_ptr()
         N.check(self.lib.rloa_replay_append(C.byref(self._rb), n, states.data_ptr(), actions.data_ptr(),
                                             rewards.data_ptr(), next_states.data_ptr(), N.ptr(dones), N.ptr(valid),

@@ -1,0 +1,124 @@
+"""
+CPU pins of the physics oracle (oracle/bullet_restatement.c).  PyBullet itself is absent ("parity unpinned",
+DESIGN.md section 2), so the restatement is held to what CAN be checked without it:
+  * the closed-form regime of Bullet's motor model — exact to solver tolerance;
+  * rigid-body identities that any correct articulated-body implementation satisfies: M^-1 from unit impulses
+    through the ABA factors == inverse of the CRBA mass matrix; ABA accelerations == M^-1 (tau - bias);
+  * the reward / done truth table and the state layout pinned by the reference's mocked tests
+    (tests/robotic_manipulator_rloa/environment/test_environment.py:219-265, 514-520; environment.py:311-371, 431-451).
+"""
+import numpy as np
+import pytest
+
+from helpers import KUKA, PANDA, make_oracle, random_states, step_motors
+
+
+@pytest.mark.parametrize('cfg', [KUKA, PANDA], ids=['kuka', 'panda'])
+def test_model_shape_matches_the_survey(cfg):
+    model, _ = make_oracle(cfg)
+    nl, ndof = model.nl, int((np.asarray(model.jtype) != 0).sum())
+    assert (nl, ndof) == ((14, 12) if cfg is KUKA else (12, 9))          # SURVEY.md section 8 sizes
+    assert all(p < i for i, p in enumerate(model.parent))                # depth-first numbering
+
+
+@pytest.mark.parametrize('cfg', [KUKA, PANDA], ids=['kuka', 'panda'])
+def test_minv_is_the_inverse_of_the_crba_mass_matrix(cfg):
+    model, orc = make_oracle(cfg)
+    mov = np.nonzero(np.asarray(model.jtype) != 0)[0]
+    q, _ = random_states(model, 8, seed=2)
+    for e in range(8):
+        Mi = orc.minv(q[e])[np.ix_(mov, mov)]
+        Mm = orc.crba(q[e])[np.ix_(mov, mov)]
+        assert np.allclose(Mm, Mm.T, atol=1e-12) and np.all(np.linalg.eigvalsh(Mm) > 0)
+        assert np.abs(Mi @ Mm - np.eye(len(mov))).max() <= 1e-8
+
+
+def test_aba_equals_minv_times_generalised_force():
+    """qdd = M^-1 (tau - C(q, qd)): the ABA (with Bullet's link velocity drag, gyroscopic terms, gravity and joint
+    damping) against an independent recursive Newton-Euler bias and the unit-impulse M^-1."""
+    model, orc = make_oracle(KUKA)
+    mov = np.nonzero(np.asarray(model.jtype) != 0)[0]
+    q, qd = random_states(model, 6, seed=4)
+    rng = np.random.default_rng(0)
+    for e in range(6):
+        tau = np.zeros(model.nl); tau[mov] = rng.uniform(-5, 5, len(mov))
+        qdd = orc.aba(q[e], qd[e], tau)
+        rhs = tau - orc.bias(q[e], qd[e])                 # the RNEA bias already carries damping * qd and the drag
+        want = orc.minv(q[e])[np.ix_(mov, mov)] @ rhs[mov]
+        assert np.abs(qdd[mov] - want).max() <= 1e-7 * max(1.0, np.abs(want).max())
+
+
+def test_unsaturated_motors_are_kinematic():
+    """A.6: velocity-controlled joints reach the commanded velocity, q += a/240; position-held joints close 10 %
+    of their error per step (kp 0.1) and get velocity -24 q."""
+    cfg = KUKA
+    model, orc = make_oracle(cfg)
+    step_motors(orc, cfg)
+    n = 64
+    rng = np.random.default_rng(3)
+    q = np.zeros((n, model.nl)); qd = np.zeros((n, model.nl))
+    q[:, :6] = rng.uniform(-0.5, 0.5, (n, 6))
+    q[:, 6] = 0.2
+    a = rng.uniform(-0.02, 0.02, (n, 6))
+    qd[:, :6] = a
+    q0 = q.copy()
+    orc.batch_step(q, qd, a, cfg['involved'], 200.0, cfg['obstacle'], cfg['target'])
+    # PGS stops at a squared residual of 1e-7: a few times sqrt(1e-7) = 3e-4 rad/s from the exact solution
+    assert np.abs(qd[:, :6] - a).max() <= 2e-3
+    assert np.abs(q[:, :6] - (q0[:, :6] + qd[:, :6] / 240.0)).max() <= 1e-12       # semi-implicit Euler, exactly
+    assert np.abs(q[:, 6] - 0.9 * 0.2).max() <= 1e-4
+    assert np.abs(qd[:, 6] + 24.0 * 0.2).max() <= 2e-2
+
+
+def test_reset_drives_towards_the_start_pose():
+    """Environment.reset = 50 POSITION_CONTROL steps (environment.py:295-301): residual 0.9^50 of the error."""
+    cfg = KUKA
+    model, orc = make_oracle(cfg)
+    n = 4
+    q = np.zeros((n, model.nl)); qd = np.zeros((n, model.nl))
+    init = np.tile(np.asarray(cfg['start'], dtype=np.float64), (n, 1))
+    orc.batch_reset(q, qd, init, 50)
+    resid = 0.9 ** 50
+    assert np.abs(q[:, :6] - init * (1 - resid)).max() <= 2e-3
+    assert np.abs(q[:, 6:]).max() <= 5e-3                                         # never-commanded joints stay put
+
+
+def test_reward_and_done_truth_table():
+    """get_reward / is_terminal_state (environment.py:311-371): 250 & done on target; -1000 & done on obstacle;
+    -(d - 0.05) & not done otherwise; target wins the reward when both hold, done either way."""
+    cfg = KUKA
+    model, orc = make_oracle(cfg)
+    q = np.zeros(model.nl); q[:6] = cfg['start']
+    qd = np.zeros(model.nl)
+    _, ee = orc.fk(q)
+    ee = ee[cfg['ee']]
+    far = ee + np.array([0.0, 0.0, 5.0])
+    obs, rew, done = orc.observe(q, qd, far, far)                                  # nothing near
+    lo, d_ee, eep = orc.distances(q, far, far)
+    assert done == 0 and rew == pytest.approx(-(d_ee - 0.05), abs=1e-12) and rew < 0
+    assert obs.shape == (21,)                                                      # 9 + 2 * 6 (environment.py:261)
+    assert np.allclose(obs[:6], q[:6]) and np.allclose(obs[6:12], qd[:6])          # joints 0..n-1 (:442-444)
+    assert np.allclose(obs[12:15], eep) and np.allclose(obs[15:18], far) and np.allclose(obs[18:21], far)
+    _, rew, done = orc.observe(q, qd, far, ee)                                     # target on the end effector
+    assert (rew, done) == (250.0, 1)
+    _, rew, done = orc.observe(q, qd, ee, far)                                     # obstacle on the end effector
+    assert (rew, done) == (-1000.0, 1)
+    _, rew, done = orc.observe(q, qd, ee, ee)                                      # both: reward 250, done
+    assert (rew, done) == (250.0, 1)
+    lo, _, _ = orc.distances(q, far, far)
+    assert (lo[np.isin(np.arange(model.nl), np.asarray(model.s_link))] < 10.0).all()
+    no_shape = ~np.isin(np.arange(model.nl), np.asarray(model.s_link))
+    assert (lo[no_shape] == 10.0).all()                                            # collision_detector.py:56-57
+
+
+def test_joint_limits_hold():
+    """A.4: a joint commanded through its limit stops there (unilateral row, erp 0.2 push-out)."""
+    cfg = KUKA
+    model, orc = make_oracle(cfg)
+    step_motors(orc, cfg)
+    q = np.zeros((1, model.nl)); qd = np.zeros((1, model.nl))
+    q[0, 1] = model.upper[1] - 1e-3
+    a = np.zeros((1, 6)); a[0, 1] = 1.0
+    for _ in range(40):
+        orc.batch_step(q, qd, a, cfg['involved'], 200.0, [5, 5, 5], [5, 5, 6])
+    assert q[0, 1] <= model.upper[1] + 2e-3 and abs(qd[0, 1]) <= 5e-2
