@@ -392,9 +392,18 @@ def ours(args):
             'graphed': graphed, 'graph_error': loop.graph_error,
             'clocks': clocks,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # tear down in dependency order: the captured graph holds NCCL work, so it goes first; a communicator that
+        # still refuses to finalise must not turn a finished measurement into a hung job
+        loop._graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        import threading
+        threading.Timer(20.0, lambda: os._exit(0)).start()
         dist.destroy_process_group()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():

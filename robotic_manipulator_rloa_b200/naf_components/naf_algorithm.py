@@ -411,7 +411,8 @@ class VectorLoop:
             torch.cuda.synchronize(self.agent.device)
             g = torch.cuda.CUDAGraph()
             launched = self.lib.rloa_launch_count()
-            with torch.cuda.graph(g):
+            # thread_local: other host threads (NCCL watchdog, clock sampler) may keep calling the CUDA API
+            with torch.cuda.graph(g, capture_error_mode='thread_local'):
                 self._body(True, self.learn, 0)
                 self._body(True, self.learn, 1)
             self._graph, self._graph_learn = g, self.learn
