@@ -262,6 +262,26 @@ int rloa_naf_learn_grads(rloa_naf_ws* ws, const rloa_naf_params* main_net, const
 int rloa_naf_learn_apply(rloa_naf_ws* ws, const rloa_naf_params* main_net, const rloa_naf_params* target_net,
                          const rloa_adam_state* adam, const rloa_naf_hyper* hp, float* grad,
                          float* grad_norm, void* stream);
+/* ------------------------------------------------------------------------------------------------
+ * Gradient exchange over NVLink peer memory (N > 1 ranks on one node, one process per GPU).  Replaces the
+ * NCCL all-reduce between _grads and _apply: every rank owns an exchange block exported with CUDA IPC and
+ * mapped by its peers; rloa_naf_learn_apply_xchg publishes the local gradient, sums all ranks' gradients
+ * in rank order straight from the mapped peer blocks inside the optimiser's norm pass, then runs the same
+ * clip + Adam + soft-update kernel.  No reference counterpart (the reference is single-process).
+ *   rloa_xchg_create  -> rloa_xchg_handle (64-byte IPC handle, HOST) -> all-gather the handles by any
+ *   means -> rloa_xchg_connect(rank, world, handles [world][64] HOST).  world == 1 needs no handles.
+ * rloa_xchg_status returns 1 after a device-side wait for a peer timed out (~2 s), 0 otherwise.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rloa_xchg rloa_xchg;
+int rloa_xchg_create(int32_t n_floats, rloa_xchg** out);
+int rloa_xchg_handle(const rloa_xchg* x, uint8_t* handle_out_host);
+int rloa_xchg_connect(rloa_xchg* x, int32_t rank, int32_t world, const uint8_t* handles_host);
+int rloa_xchg_status(const rloa_xchg* x);
+void rloa_xchg_destroy(rloa_xchg* x);
+int rloa_naf_learn_apply_xchg(rloa_naf_ws* ws, const rloa_naf_params* main_net, const rloa_naf_params* target_net,
+                              const rloa_adam_state* adam, const rloa_naf_hyper* hp, rloa_xchg* xchg,
+                              const float* grad, float* grad_norm, void* stream);
+
 /* NAFAgent.soft_update alone (naf_algorithm.py:217-226) */
 int rloa_naf_soft_update(const rloa_naf_params* main_net, const rloa_naf_params* target_net, float tau,
                          void* stream);

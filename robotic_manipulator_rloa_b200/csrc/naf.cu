@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "naf_trunk_tc.cuh"
+#include "optim.cuh"
 #include "philox.cuh"
 
 namespace rloa {
@@ -755,13 +756,20 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(ReduceArgs r) {
 // ------------------------------------------------------------------------------------------------
 // optimiser: global grad norm, then clip + Adam + soft target update in one vectorised pass
 // ------------------------------------------------------------------------------------------------
-constexpr int kNormBlocks = 64;
 __global__ void __launch_bounds__(256) grad_sqsum_kernel(const float* __restrict__ g, int n, float scale,
                                                          float* __restrict__ partial, int64_t* __restrict__ step_ptr) {
     __shared__ float red[256];
     if (blockIdx.x == 0 && threadIdx.x == 0 && step_ptr != nullptr) *step_ptr += 1;   // optimizer.step() counter
+    // same element-to-thread mapping and accumulation order as xchg_reduce_kernel (grad_exchange.cu), so the
+    // single-rank and the exchanged update produce the same bits
     float s = 0.f;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const int n4 = ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) ? (n >> 2) : 0;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n4; i += gridDim.x * 256) {
+        const float4 v = reinterpret_cast<const float4*>(g)[i];
+        const float x0 = v.x * scale, x1 = v.y * scale, x2 = v.z * scale, x3 = v.w * scale;
+        s = fmaf(x0, x0, s); s = fmaf(x1, x1, s); s = fmaf(x2, x2, s); s = fmaf(x3, x3, s);
+    }
+    for (int i = 4 * n4 + blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
         const float x = g[i] * scale;
         s = fmaf(x, x, s);
     }
@@ -774,48 +782,20 @@ __global__ void __launch_bounds__(256) grad_sqsum_kernel(const float* __restrict
     if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
 }
 
-struct ParamTable {               // the 14 parameter tensors in nn.Module.parameters() order
-    float* main[14];
-    float* target[14];
-    int offset[15];
-};
-
 __global__ void __launch_bounds__(256)
 adam_soft_update_kernel(ParamTable pt, const float* __restrict__ grad, const float* __restrict__ sq_partial,
                         float* __restrict__ m, float* __restrict__ v, int64_t* __restrict__ step_ptr, rloa_naf_hyper hp,
                         float* __restrict__ grad_norm_out) {
-    __shared__ float s_clip;
-    __shared__ float s_bc1, s_bc2;
+    __shared__ AdamCoef s_c;
     if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int i = 0; i < kNormBlocks; i++) t += sq_partial[i];
-        const float norm = sqrtf(t);
-        // clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to 1
-        s_clip = fminf(hp.clip_norm / (norm + 1e-6f), 1.f) * hp.grad_scale;
-        const int64_t st = *step_ptr;          // already incremented by grad_sqsum_kernel
-        s_bc1 = 1.f - powf(hp.beta1, (float)st);
-        s_bc2 = 1.f - powf(hp.beta2, (float)st);
-        if (blockIdx.x == 0 && grad_norm_out != nullptr) *grad_norm_out = norm;
+        s_c = adam_coefficients(sq_partial, *step_ptr, hp);      // step already incremented by grad_sqsum_kernel
+        if (blockIdx.x == 0 && grad_norm_out != nullptr) *grad_norm_out = s_c.norm;
     }
     __syncthreads();
-    const float clip = s_clip, bc1 = s_bc1, bc2s = sqrtf(s_bc2);
+    const AdamCoef c = s_c;
     const int n = pt.offset[14];
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-        int t = 0;
-#pragma unroll
-        for (int k = 1; k < 14; k++) t += (i >= pt.offset[k]) ? 1 : 0;
-        const int j = i - pt.offset[t];
-        const float g = grad[i] * clip;
-        const float mi = fmaf(1.f - hp.beta1, g - m[i], m[i]);          // m = b1 m + (1-b1) g
-        const float vi = fmaf(1.f - hp.beta2, g * g - v[i], v[i]);      // v = b2 v + (1-b2) g^2
-        m[i] = mi;
-        v[i] = vi;
-        const float denom = sqrtf(vi) / bc2s + hp.eps;
-        const float p = pt.main[t][j] - (hp.lr / bc1) * (mi / denom);
-        pt.main[t][j] = p;
-        // soft update with the freshly updated main parameter (naf_algorithm.py:213, 225-226)
-        pt.target[t][j] = hp.tau * p + (1.f - hp.tau) * pt.target[t][j];
-    }
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
+        adam_soft_update_element(pt, i, grad[i], c, m, v, hp);
 }
 
 __global__ void __launch_bounds__(256) soft_update_kernel(ParamTable pt, float tau) {
@@ -1284,6 +1264,25 @@ extern "C" int rloa_naf_learn_apply(rloa_naf_ws* ws, const rloa_naf_params* mn, 
                                                              grad_norm);
     RLOA_LAUNCHED();
     return RLOA_OK;
+}
+
+struct rloa_xchg;
+namespace rloa {
+int xchg_exchange_adam(rloa_xchg* x, const float* local_grad, const ParamTable& pt, float* m, float* v, int64_t* step_ptr,
+                       const rloa_naf_hyper& hp, float* grad_norm, cudaStream_t st);
+}
+
+extern "C" int rloa_naf_learn_apply_xchg(rloa_naf_ws* ws, const rloa_naf_params* mn, const rloa_naf_params* tg,
+                                         const rloa_adam_state* adam, const rloa_naf_hyper* hp, rloa_xchg* xchg,
+                                         const float* grad, float* grad_norm, void* stream) {
+    RLOA_REQUIRE(ws && adam && hp && grad && xchg && adam->m && adam->v && adam->step, "rloa_naf_learn_apply_xchg: null argument");
+    int rc = check_params(ws, mn, "rloa_naf_learn_apply_xchg(main)");
+    if (rc != RLOA_OK) return rc;
+    rc = check_params(ws, tg, "rloa_naf_learn_apply_xchg(target)");
+    if (rc != RLOA_OK) return rc;
+    ParamTable pt;
+    fill_param_table(mn, tg, &pt);
+    return xchg_exchange_adam(xchg, grad, pt, adam->m, adam->v, adam->step, *hp, grad_norm, as_stream(stream));
 }
 
 extern "C" int rloa_naf_soft_update(const rloa_naf_params* mn, const rloa_naf_params* tg, float tau, void* stream) {

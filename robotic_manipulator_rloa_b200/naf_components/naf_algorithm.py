@@ -105,6 +105,10 @@ class NAFAgent:
         self.last_loss = None
         self.last_grad_norm = None
         self.rank, self.world_size = rdist.world()
+        # N > 1: 'peer' = NVLink peer-memory exchange fused into the optimiser kernels (csrc/grad_exchange.cu),
+        # 'nccl' = torch.distributed all-reduce between the two native calls (the baseline); RLOA_GRAD_EXCHANGE selects
+        self.grad_exchange_mode = os.environ.get('RLOA_GRAD_EXCHANGE', 'peer')
+        self._xchg: Optional[rdist.GradExchange] = None
 
     # ------------------------------------------------------------------------------------------
     # native plumbing
@@ -238,12 +242,26 @@ class NAFAgent:
         N.check(ws.lib.rloa_naf_learn_grads(ws.handle, C.byref(pm), C.byref(pt), s.data_ptr(), a.data_ptr(),
                                             r.data_ptr(), s2.data_ptr(), d.data_ptr(), B, C.byref(hp),
                                             b['grad'].data_ptr(), b['loss'].data_ptr(), st), 'rloa_naf_learn_grads')
-        if self.world_size > 1:          # the one exchange step of the data-parallel path (NCCL over NVLink)
-            rdist.allreduce_gradient(b['grad'])
         adam = self.optimizer.native()
-        N.check(ws.lib.rloa_naf_learn_apply(ws.handle, C.byref(pm), C.byref(pt), C.byref(adam), C.byref(hp),
-                                            b['grad'].data_ptr(), b['gnorm'].data_ptr(), st), 'rloa_naf_learn_apply')
+        xchg = self._exchange()
+        if xchg is not None:             # the one exchange step of the data-parallel path, inside the optimiser kernels
+            N.check(ws.lib.rloa_naf_learn_apply_xchg(ws.handle, C.byref(pm), C.byref(pt), C.byref(adam), C.byref(hp),
+                                                     xchg.handle, b['grad'].data_ptr(), b['gnorm'].data_ptr(), st),
+                    'rloa_naf_learn_apply_xchg')
+        else:
+            if self.world_size > 1:      # baseline: NCCL all-reduce between the two native calls
+                rdist.allreduce_gradient(b['grad'])
+            N.check(ws.lib.rloa_naf_learn_apply(ws.handle, C.byref(pm), C.byref(pt), C.byref(adam), C.byref(hp),
+                                                b['grad'].data_ptr(), b['gnorm'].data_ptr(), st), 'rloa_naf_learn_apply')
         self.last_loss, self.last_grad_norm = b['loss'], b['gnorm']
+
+    def _exchange(self) -> Optional[rdist.GradExchange]:
+        """The peer-memory exchange when it applies (N > 1 and mode 'peer', or forced with mode 'peer-always');
+        created lazily — collectively — on the first learn()."""
+        if self._xchg is None and (
+                (self.world_size > 1 and self.grad_exchange_mode == 'peer') or self.grad_exchange_mode == 'peer-always'):
+            self._xchg = rdist.GradExchange(self.n_params, self.device)
+        return self._xchg
 
     def soft_update(self, main_nn: NAF, target_nn: NAF) -> None:
         """theta_target = tau theta_main + (1 - tau) theta_target over parameters (naf_algorithm.py:217-226)."""

@@ -45,3 +45,49 @@ def allreduce_gradient(flat_grad: torch.Tensor) -> float:
     if w > 1:
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
     return 1.0 / float(w)
+
+
+class GradExchange:
+    """NVLink peer-memory gradient exchange (csrc/grad_exchange.cu): one exchange block per rank, exported with CUDA
+    IPC, mapped by every peer; the optimiser's own kernels publish, sum (in rank order) and consume the gradient.
+    Construction is collective: every rank of the process group must create it at the same point."""
+
+    def __init__(self, n_params: int, device: torch.device):
+        import ctypes as C
+        from .. import _native as N
+        self.lib = N.lib()
+        self.device = torch.device(device)
+        self.rank, self.world = world()
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(self.lib.rloa_xchg_create(int(n_params), C.byref(self._h)), 'rloa_xchg_create')
+            mine = C.create_string_buffer(64)
+            N.check(self.lib.rloa_xchg_handle(self._h, mine), 'rloa_xchg_handle')
+            handles = None
+            if self.world > 1:
+                local = torch.tensor(list(mine.raw), dtype=torch.uint8, device=self.device)
+                gathered = [torch.empty_like(local) for _ in range(self.world)]
+                dist.all_gather(gathered, local)
+                handles = bytes(torch.cat(gathered).cpu().numpy().tobytes())
+            N.check(self.lib.rloa_xchg_connect(self._h, self.rank, self.world, handles), 'rloa_xchg_connect')
+            if self.world > 1:
+                dist.barrier()
+
+    @property
+    def handle(self):
+        return self._h
+
+    def timed_out(self) -> bool:
+        """True after a device-side wait for a peer gave up (~2 s): the ranks have diverged."""
+        return self.lib.rloa_xchg_status(self._h) == 1
+
+    def close(self) -> None:
+        if self._h:
+            self.lib.rloa_xchg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

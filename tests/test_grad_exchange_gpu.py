@@ -1,0 +1,92 @@
+"""
+GPU tests of the NVLink peer-memory gradient exchange (csrc/grad_exchange.cu, rloa_naf_learn_apply_xchg).
+  * world = 1 (any box): publish + reduce + Adam must reproduce rloa_naf_learn_apply bit for bit;
+  * world = 2 (needs two GPUs; skipped otherwise — run with `gpurun --gpus 2`): three data-parallel updates with
+    the peer exchange against the same updates with an NCCL all-reduce between the two native calls: parameters
+    identical across ranks (bit-exact, no broadcast) and equal between the two exchange modes.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.naf_restatement import NAFRef
+
+pytestmark = pytest.mark.gpu
+S, A, H, B = 21, 6, 256, 256
+
+
+def _batch(seed):
+    g = torch.Generator().manual_seed(seed)
+    s = torch.randn(B, S, generator=g)
+    return (s, torch.clamp(torch.randn(B, A, generator=g) * 1.5, -1, 1).long(), -torch.rand(B, 1, generator=g),
+            s + 0.1 * torch.randn(B, S, generator=g), torch.zeros(B, 1))
+
+
+def _agent(mode, dev):
+    from robotic_manipulator_rloa_b200.naf_components.naf_algorithm import NAFAgent
+    ref_main, ref_target = NAFRef(S, A, H, seed=1), NAFRef(S, A, H, seed=2)
+    agent = NAFAgent(None, S, A, H, B, 1000, 1e-3, 1e-3, 0.99, 1, 1, 500, dev, 0)
+    agent.qnetwork_main.load_state_dict(ref_main.state_dict())
+    agent.qnetwork_target.load_state_dict(ref_target.state_dict())
+    agent.grad_exchange_mode = mode
+    return agent
+
+
+def _params(agent):
+    return torch.cat([p.detach().reshape(-1) for p in list(agent.qnetwork_main.parameters()) +
+                      list(agent.qnetwork_target.parameters())])
+
+
+def test_single_rank_exchange_is_bit_identical_to_plain_apply():
+    dev = torch.device('cuda:0')
+    plain, peer = _agent('nccl', dev), _agent('peer-always', dev)
+    for step in range(3):
+        plain.learn(_batch(step)); peer.learn(_batch(step))
+    torch.cuda.synchronize()
+    assert peer._xchg is not None and not peer._xchg.timed_out()
+    assert torch.equal(_params(plain), _params(peer))
+    assert float(plain.last_grad_norm.item()) == float(peer.last_grad_norm.item())
+    assert int(peer.optimizer.step_count.item()) == 3
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    out = {}
+    for mode in ('peer', 'nccl'):
+        agent = _agent(mode, dev)
+        assert agent.world_size == world
+        for step in range(3):
+            agent.learn(_batch(100 * rank + step))          # every rank learns from its own replay shard
+        torch.cuda.synchronize()
+        if mode == 'peer':
+            assert agent._xchg is not None and not agent._xchg.timed_out()
+        vec = _params(agent)
+        gathered = [torch.empty_like(vec) for _ in range(world)]
+        dist.all_gather(gathered, vec)
+        out[mode] = torch.stack(gathered).cpu().numpy()
+    if rank == 0:
+        np.savez(os.path.join(out_dir, 'out.npz'), **out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs (gpurun --gpus 2)')
+def test_two_rank_peer_exchange_matches_nccl(tmp_path):
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    out = np.load(tmp_path / 'out.npz')
+    for mode in ('peer', 'nccl'):
+        assert np.array_equal(out[mode][0], out[mode][1]), f'{mode}: ranks diverged'
+    # both modes add the two ranks' gradients in rank order (a two-operand sum has one rounding): same bits expected;
+    # allow the last ulp of an lr-sized Adam step in case NCCL reduces in the other order
+    assert np.abs(out['peer'][0] - out['nccl'][0]).max() <= 1e-6
