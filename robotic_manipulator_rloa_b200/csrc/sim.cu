@@ -444,6 +444,72 @@ __global__ void episode_update_kernel(int n, int frames, const float* __restrict
     }
 }
 
+// Episode bookkeeping and the lock-step reset of the finished envs in ONE launch (the two are per-env and
+// independent across envs).  The start-pose draw is keyed by the loop counter read at kernel entry; the counter is
+// incremented by whichever block finishes last, so every block sees the same value whatever the scheduling order.
+__global__ void episode_update_reset_kernel(int n, int frames, const float* __restrict__ reward,
+                                            const uint8_t* __restrict__ done, const uint8_t* __restrict__ active,
+                                            float* __restrict__ score, int* __restrict__ frame, uint8_t* __restrict__ reset_mask,
+                                            float* __restrict__ log_score, int* __restrict__ log_frame,
+                                            float* __restrict__ log_last, int* __restrict__ log_env, int log_cap,
+                                            int* __restrict__ log_count, unsigned long long* __restrict__ transitions,
+                                            unsigned long long* __restrict__ tick, SimArrays S, const float* __restrict__ pos,
+                                            const float* __restrict__ var, int n_init, int nsub, float pos_maximp,
+                                            unsigned long long seed, unsigned* __restrict__ ticket) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long t = tick != nullptr ? *tick + 1ull : 0ull;     // the value begin_reset would have seen
+    const bool live = e < n && (active == nullptr || active[e] != 0);
+    const int nlive = __syncthreads_count(live);
+    if (threadIdx.x == 0 && transitions != nullptr && nlive > 0) atomicAdd(transitions, (unsigned long long)nlive);
+    bool fin = false;
+    if (e < n) {
+        if (live) {
+            const float sc = score[e] + reward[e];
+            const int fr = frame[e] + 1;
+            fin = done[e] != 0 || fr >= frames;
+            if (fin) {
+                const int slot = atomicAdd(log_count, 1);
+                if (slot < log_cap) {
+                    log_score[slot] = sc;
+                    log_frame[slot] = fr;
+                    log_last[slot] = reward[e];
+                    log_env[slot] = e;
+                }
+                score[e] = 0.f;
+                frame[e] = 0;
+            } else {
+                score[e] = sc;
+                frame[e] = fr;
+            }
+        }
+        reset_mask[e] = fin ? 1 : 0;
+        if (fin) {        // sim_begin_reset_random_kernel for this env
+            const size_t N = (size_t)S.n_envs;
+            for (int j0 = 0; j0 < n_init; j0 += 4) {
+                uint32_t c[4] = {(uint32_t)e, (uint32_t)(j0 >> 2), (uint32_t)t, (uint32_t)(t >> 32)};
+                philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x52455345u);
+                for (int k = 0; k < 4 && j0 + k < n_init; k++) {
+                    const int j = j0 + k;
+                    const size_t at = (size_t)j * N + e;
+                    const float v = var != nullptr ? var[j] : 0.f;
+                    S.kp[at] = 0.1f;
+                    S.tpos[at] = fmaf(v, 2.f * u01(c[k]) - 1.f, pos != nullptr ? pos[j] : 0.f);
+                    S.tvel[at] = 0.f;
+                    S.maximp[at] = pos_maximp;
+                }
+            }
+            S.reset_left[e] = nsub;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && tick != nullptr) {
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1u) {
+            *ticket = 0u;
+            *tick += 1ull;
+        }
+    }
+}
+
 }  // namespace rloa
 
 // ------------------------------------------------------------------------------------------------
@@ -460,6 +526,7 @@ struct rloa_sim {
     const rloa_model* model = nullptr;
     SimArrays a{};
     float* block = nullptr;
+    unsigned* ticket = nullptr;      // last-block-done counter of rloa_episode_update_reset (zero at rest)
     int device = 0;
 };
 
@@ -598,6 +665,7 @@ extern "C" int rloa_sim_create(const rloa_model* m, int32_t n_envs, rloa_sim** o
     s->a.target = s->a.minv + N * ndof * ndof; s->a.obstacle = s->a.target + 3 * N;
     s->a.iters = reinterpret_cast<int*>(s->a.obstacle + 3 * N);
     s->a.reset_left = s->a.iters + n_envs;
+    if (cudaMalloc(&s->ticket, sizeof(unsigned)) == cudaSuccess) cudaMemset(s->ticket, 0, sizeof(unsigned));
     cudaFuncSetAttribute(sim_minv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxLinks * kFRec * 32 * (int)sizeof(float));
     cudaMemset(s->block, 0, floats * sizeof(float));
     sim_clear_kernel<<<(unsigned)((n + 255) / 256), 256>>>(s->a);
@@ -615,6 +683,7 @@ extern "C" int rloa_sim_create(const rloa_model* m, int32_t n_envs, rloa_sim** o
 extern "C" void rloa_sim_destroy(rloa_sim* s) {
     if (s == nullptr) return;
     if (s->block) cudaFree(s->block);
+    if (s->ticket) cudaFree(s->ticket);
     delete s;
 }
 
@@ -820,6 +889,26 @@ extern "C" int rloa_episode_update(int32_t n_envs, int32_t frames, const float* 
         n_envs, frames, reward, done, active, score, frame, reset_mask, log_score, log_frame, log_last_reward, log_env,
         log_capacity, log_count, reinterpret_cast<unsigned long long*>(transitions),
         reinterpret_cast<unsigned long long*>(tick));
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
+extern "C" int rloa_episode_update_reset(rloa_sim* s, int32_t frames, const float* reward, const uint8_t* done,
+                                         const uint8_t* active, float* score, int32_t* frame, uint8_t* reset_mask,
+                                         float* log_score, int32_t* log_frame, float* log_last_reward, int32_t* log_env,
+                                         int32_t log_capacity, int32_t* log_count, int64_t* transitions, uint64_t* tick,
+                                         const float* pos, const float* var, int32_t n_init, int32_t n_substeps,
+                                         uint64_t seed, void* stream) {
+    RLOA_REQUIRE(s != nullptr && s->ticket != nullptr, "rloa_episode_update_reset: null sim");
+    RLOA_REQUIRE(reward && done && score && frame && reset_mask && log_score && log_frame && log_last_reward &&
+                     log_env && log_count, "rloa_episode_update_reset: null argument");
+    RLOA_REQUIRE(n_init >= 0 && n_init <= s->a.nl && n_substeps >= 0, "rloa_episode_update_reset: n_init / n_substeps out of range");
+    const int n = s->a.n_envs;
+    episode_update_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+        n, frames, reward, done, active, score, frame, reset_mask, log_score, log_frame, log_last_reward, log_env,
+        log_capacity, log_count, reinterpret_cast<unsigned long long*>(transitions),
+        reinterpret_cast<unsigned long long*>(tick), s->a, pos, var, n_init, n_substeps, 100000.f * s->model->host.dt, seed,
+        s->ticket);
     RLOA_LAUNCHED();
     return RLOA_OK;
 }

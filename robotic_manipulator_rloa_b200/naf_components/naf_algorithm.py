@@ -188,10 +188,13 @@ class NAFAgent:
         if out is None:
             out = torch.empty(n, self.action_size, dtype=torch.float32, device=self.device)
         p = self.qnetwork_main.native_params()
-        N.check(ws.lib.rloa_naf_act(ws.handle, C.byref(p), states.data_ptr(), n, self.seed, self._act_calls,
-                                    N.ptr(tick), float(self.noise_scale), out.data_ptr(), self._stream()),
-                'rloa_naf_act')
-        self._act_calls += 1
+        # Philox step: the host call counter, or — inside the vectorised loop — the device counter alone, so that an
+        # eager launch and a replay of the captured graph draw the same noise
+        N.check(ws.lib.rloa_naf_act(ws.handle, C.byref(p), states.data_ptr(), n, self.seed,
+                                    self._act_calls if tick is None else 0, N.ptr(tick), float(self.noise_scale),
+                                    out.data_ptr(), self._stream()), 'rloa_naf_act')
+        if tick is None:
+            self._act_calls += 1
         return out
 
     def act(self, state):
@@ -395,15 +398,17 @@ class VectorLoop:
             for u in range(a.num_updates):
                 a.learn_from_memory(tick=self.tick, sub=u)
         self._mark(parity, 4)
-        N.check(self.lib.rloa_episode_update(self.n, self.frames, self.reward.data_ptr(), self.done.data_ptr(),
-                                             self.valid.data_ptr(), self.score.data_ptr(), self.frame.data_ptr(),
-                                             self.reset_mask.data_ptr(), self.log_score.data_ptr(),
-                                             self.log_frame.data_ptr(), self.log_last.data_ptr(),
-                                             self.log_env.data_ptr(), self.cap, self.log_count.data_ptr(),
-                                             self.transitions.data_ptr(), self.tick.data_ptr(), a._stream()),
-                'rloa_episode_update')
-        if auto_reset:      # finished envs start their 50 reset sub-steps, one per following step() (lock step)
-            env.begin_reset_masked(self.reset_mask, tick=self.tick)
+        common = (self.reward.data_ptr(), self.done.data_ptr(), self.valid.data_ptr(), self.score.data_ptr(),
+                  self.frame.data_ptr(), self.reset_mask.data_ptr(), self.log_score.data_ptr(), self.log_frame.data_ptr(),
+                  self.log_last.data_ptr(), self.log_env.data_ptr(), self.cap, self.log_count.data_ptr(),
+                  self.transitions.data_ptr(), self.tick.data_ptr())
+        if auto_reset:      # bookkeeping + the finished envs start their 50 reset sub-steps (one per following step)
+            N.check(self.lib.rloa_episode_update_reset(env.sim._h_sim, self.frames, *common, env._d_pos.data_ptr(),
+                                                       env._d_var.data_ptr(), env._n_init(), 50,
+                                                       (env.seed + 0x5EED) & 0xFFFFFFFFFFFFFFFF, a._stream()),
+                    'rloa_episode_update_reset')
+        else:
+            N.check(self.lib.rloa_episode_update(self.n, self.frames, *common, a._stream()), 'rloa_episode_update')
         self._mark(parity, 5)
         self.state, self.next_state = self.next_state, self.state
 
