@@ -321,30 +321,16 @@ def ours(args):
     h_state = torch.zeros(n, S).pin_memory(); h_act = torch.zeros(n, A).pin_memory()
     h_rew = torch.zeros(n).pin_memory(); h_done = torch.zeros(n, dtype=torch.uint8).pin_memory()
     h_state.copy_(loop.state)
+    loop.bind_host_buffers(h_state, h_act, h_rew, h_done)
     e2e_steps = max(10, args.steps // 4)
+    for _ in range(3):                     # warm-up of the host-facing path (captures its two graphs)
+        loop.step_host(use_graph=use_graph)
     loop.transitions.zero_()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(e2e_steps):
-        loop.state.copy_(h_state, non_blocking=True)                      # H2D: this step's states
-        agent.act_batch(loop.state, out=loop.actions, tick=loop.tick)
-        h_act.copy_(loop.actions, non_blocking=True)                      # D2H: actions to the caller
-        torch.cuda.current_stream().synchronize()
-        loop.actions.copy_(h_act, non_blocking=True)                      # H2D: actions into Environment.step
-        env.sim.step(loop.actions, out=(loop.next_state, loop.reward, loop.done), valid=loop.valid)
-        h_state.copy_(loop.next_state, non_blocking=True)                 # D2H: (state, reward, done)
-        h_rew.copy_(loop.reward, non_blocking=True)
-        h_done.copy_(loop.done, non_blocking=True)
-        agent.memory.add_batch(loop.state, loop.actions, loop.reward, loop.next_state, loop.done, valid=loop.valid)
-        agent._maybe_learn(tick=loop.tick)
-        _native.check(lib.rloa_episode_update(n, FRAMES, loop.reward.data_ptr(), loop.done.data_ptr(), loop.valid.data_ptr(),
-                                              loop.score.data_ptr(), loop.frame.data_ptr(), loop.reset_mask.data_ptr(),
-                                              loop.log_score.data_ptr(), loop.log_frame.data_ptr(), loop.log_last.data_ptr(),
-                                              loop.log_env.data_ptr(), loop.cap, loop.log_count.data_ptr(),
-                                              loop.transitions.data_ptr(), loop.tick.data_ptr(), agent._stream()))
-        env.begin_reset_masked(loop.reset_mask, tick=loop.tick)
-        torch.cuda.current_stream().synchronize()
+        loop.step_host(use_graph=use_graph)        # the public call: host states in, host actions / results out
     e1.record()
     barrier()
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)

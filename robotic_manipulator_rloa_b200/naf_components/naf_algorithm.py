@@ -368,6 +368,8 @@ class VectorLoop:
         self._graph_learn = False
         self.graph_kernels = 0
         self.graph_error: Optional[str] = None
+        self._host = None               # pinned host buffers bound by bind_host_buffers
+        self._host_graphs = None
 
     def reset_all(self, verbose: bool = False) -> None:
         """Synchronous Environment.reset of every env (50 sub-steps) -> self.state."""
@@ -454,6 +456,78 @@ class VectorLoop:
         self._graph.replay()
         m = self.agent.memory
         m._len = min(m.buffer_size, m._len + 2 * self.n)
+
+    # ---- host-facing iteration: states / actions / results cross pinned HOST buffers every step ---------------
+    def bind_host_buffers(self, h_state: torch.Tensor, h_action: torch.Tensor, h_reward: torch.Tensor,
+                          h_done: torch.Tensor) -> None:
+        """Pinned host tensors [n,S] f32, [n,A] f32, [n] f32, [n] u8 that `step_host` reads and writes: the caller
+        owns the observations and sees every action, reward and done flag, as with the reference's
+        ``env.step(agent.act(state))`` (naf_algorithm.py:249-262), for all envs at once."""
+        for t in (h_state, h_action, h_reward, h_done):
+            if not t.is_pinned():
+                raise ValueError('step_host needs pinned host tensors')
+        self._host = (h_state, h_action, h_reward, h_done)
+        self._host_graphs = None
+
+    def _host_phase_act(self) -> None:
+        h_state, h_action, _, _ = self._host
+        self.state.copy_(h_state, non_blocking=True)                      # H2D: this step's states
+        self.agent.act_batch(self.state, out=self.actions, tick=self.tick)
+        h_action.copy_(self.actions, non_blocking=True)                   # D2H: the actions, for the caller
+
+    def _host_phase_step(self, learn_now: bool) -> None:
+        h_state, h_action, h_reward, h_done = self._host
+        a, env = self.agent, self.env
+        self.actions.copy_(h_action, non_blocking=True)                   # H2D: actions into Environment.step
+        env.sim.step(self.actions, out=(self.next_state, self.reward, self.done), valid=self.valid)
+        h_state.copy_(self.next_state, non_blocking=True)                 # D2H: (state, reward, done)
+        h_reward.copy_(self.reward, non_blocking=True)
+        h_done.copy_(self.done, non_blocking=True)
+        a.memory.add_batch(self.state, self.actions, self.reward, self.next_state, self.done, valid=self.valid)
+        if learn_now:
+            for u in range(a.num_updates):
+                a.learn_from_memory(tick=self.tick, sub=u)
+        N.check(self.lib.rloa_episode_update_reset(
+            env.sim._h_sim, self.frames, self.reward.data_ptr(), self.done.data_ptr(), self.valid.data_ptr(),
+            self.score.data_ptr(), self.frame.data_ptr(), self.reset_mask.data_ptr(), self.log_score.data_ptr(),
+            self.log_frame.data_ptr(), self.log_last.data_ptr(), self.log_env.data_ptr(), self.cap,
+            self.log_count.data_ptr(), self.transitions.data_ptr(), self.tick.data_ptr(), env._d_pos.data_ptr(),
+            env._d_var.data_ptr(), env._n_init(), 50, (env.seed + 0x5EED) & 0xFFFFFFFFFFFFFFFF, a._stream()),
+            'rloa_episode_update_reset')
+
+    def step_host(self, use_graph: bool = True) -> None:
+        """One iteration through the bound host buffers: [H2D states, act, D2H actions] sync
+        [H2D actions, Environment.step, D2H state/reward/done, store, learn, bookkeeping] sync.  In steady state the
+        two halves are CUDA graphs (copies included)."""
+        a = self.agent
+        stream = torch.cuda.current_stream(a.device)
+        if use_graph and self._host_graphs is None and self._graphable() and a._ws is not None and \
+                (not self.learn or a._bufs is not None):
+            host_len = a.memory._len
+            try:
+                torch.cuda.synchronize(a.device)
+                g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1, capture_error_mode='thread_local'):
+                    self._host_phase_act()
+                with torch.cuda.graph(g2, capture_error_mode='thread_local'):
+                    self._host_phase_step(self.learn)
+                self._host_graphs = (g1, g2)
+            except Exception as err:      # pragma: no cover
+                self.graph_error = f'{type(err).__name__}: {err}'
+                self._host_graphs = False
+                torch.cuda.synchronize(a.device)
+            a.memory._len = host_len
+        if use_graph and self._host_graphs:
+            self._host_graphs[0].replay()
+            stream.synchronize()
+            self._host_graphs[1].replay()
+            a.memory._len = min(a.memory.buffer_size, a.memory._len + self.n)
+            stream.synchronize()
+        else:
+            self._host_phase_act()
+            stream.synchronize()
+            self._host_phase_step(self.learn and a._learn_due(pending=self.n))
+            stream.synchronize()
 
     def run_steps(self, k: int, use_graph: bool = True) -> None:
         """k iterations with auto-reset; pairs go through the CUDA graph when it is (or can be) captured."""

@@ -158,3 +158,27 @@ def test_short_training_run_learns_something():
     print(f'greedy mean |ee - target| after 40 steps: untrained {d0:.3f} m -> after 150 updates {d1:.3f} m; '
           f'last loss {float(agent.last_loss.item()):.4f}')
     assert np.isfinite(d1)
+
+
+def test_step_host_moves_every_step_through_pinned_buffers():
+    """step_host: the caller's pinned buffers carry states in and actions / states / rewards / dones out; the graph
+    replays and the eager launches of the same path produce the same trajectory."""
+    n = 256
+    outs = []
+    for use_graph in (False, True):
+        env, agent, loop = _twin(n)
+        hs, ha = torch.zeros(n, 21).pin_memory(), torch.zeros(n, 6).pin_memory()
+        hr, hd = torch.zeros(n).pin_memory(), torch.zeros(n, dtype=torch.uint8).pin_memory()
+        hs.copy_(loop.state)
+        loop.bind_host_buffers(hs, ha, hr, hd)
+        for _ in range(12):
+            loop.step_host(use_graph=use_graph)
+        assert (loop._host_graphs not in (None, False)) == use_graph
+        assert torch.equal(hs, loop.next_state.cpu()) and torch.equal(ha, loop.actions.cpu())
+        assert torch.equal(hr, loop.reward.cpu()) and torch.equal(hd, loop.done.cpu())
+        assert ha.abs().max() <= 1.0 and int(loop.tick.item()) == 12
+        outs.append((hs.clone(), ha.clone(), hr.clone(), int(agent.memory.cursor.item())))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][2], outs[1][2]) and outs[0][3] == outs[1][3]
+    with pytest.raises(ValueError):
+        loop.bind_host_buffers(torch.zeros(n, 21), ha, hr, hd)
