@@ -28,10 +28,15 @@ inline int fail(int code, const char* what) {
         }                                                                                          \
     } while (0)
 
+// developer trace (RLOA_TRACE=1, eager launches only): one CUDA event after every launch, intervals printed by
+// rloa_trace_dump() — warm per-kernel times inside the real loop, which ncu (cold, serialised) cannot give
+void trace_mark(const char* file, int line);
+
 // after a <<<>>> launch: count it and surface launch-configuration errors
 #define RLOA_LAUNCHED()                                                                            \
     do {                                                                                           \
         ::rloa::g_launches.fetch_add(1, std::memory_order_relaxed);                                \
+        ::rloa::trace_mark(__FILE__, __LINE__);                                                    \
         cudaError_t err__ = cudaPeekAtLastError();                                                 \
         if (err__ != cudaSuccess) {                                                                \
             ::rloa::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(err__),       \

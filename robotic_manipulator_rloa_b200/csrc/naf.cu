@@ -14,14 +14,13 @@
 #include <new>
 
 #include "common.cuh"
+#include "bn_fuse.cuh"
 #include "naf_trunk_tc.cuh"
 #include "optim.cuh"
 #include "philox.cuh"
 
 namespace rloa {
 
-constexpr float kBnEps = 1e-5f;        // nn.BatchNorm1d defaults
-constexpr float kBnMomentum = 0.1f;
 
 // ------------------------------------------------------------------------------------------------
 // generic tiled SGEMM  C[i][j] = sum_k Aop(i,k) Bop(k,j)
@@ -44,7 +43,66 @@ struct GemmArgs {
 };
 struct GemmBatch {
     GemmArgs a[2];
+    BnFuse bn[2];               // NT layout only: BatchNorm statistics of the output fused into the epilogue
 };
+
+// Epilogue of an NT tile whose output feeds a train-mode BatchNorm (bn_fuse.cuh): v[i][j] = the 4 x 4 outputs of this
+// thread (rows i0 + 4 ty + i, columns j0 + 4 tx + j).  red: [16][BM + kPad] shared scratch, cm: [BN] shared scratch.
+__device__ __forceinline__ void gemm_bn_epilogue(const BnFuse& f, float (*red)[BM + kPad], float* cm, const float (&v)[4][4],
+                                                 int i0, int j0, int M, int H, int tx, int ty, int tid) {
+    __shared__ unsigned s_last;
+    const int rows = min(BM, M - i0);
+    // pass 1: tile mean per column
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) s += (ty * 4 + i < rows) ? v[i][j] : 0.f;
+        red[ty][tx * 4 + j] = s;
+    }
+    __syncthreads();
+    if (tid < BN) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; r++) s += red[r][tid];
+        cm[tid] = s / (float)rows;
+    }
+    __syncthreads();
+    // pass 2: centred second moment
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float m = cm[tx * 4 + j];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float d = (ty * 4 + i < rows) ? v[i][j] - m : 0.f;
+            s = fmaf(d, d, s);
+        }
+        red[ty][tx * 4 + j] = s;
+    }
+    __syncthreads();
+    const int chunks = gridDim.y;
+    if (tid < BN && j0 + tid < H) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; r++) s += red[r][tid];
+        float* P = f.part + (size_t)blockIdx.y * 2 * H;
+        P[j0 + tid] = cm[tid];
+        P[H + j0 + tid] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned t = atomicAdd(&f.ticket[blockIdx.x], 1u);
+        s_last = (t == (unsigned)chunks - 1u) ? 1u : 0u;
+        if (s_last) f.ticket[blockIdx.x] = 0u;
+    }
+    __syncthreads();
+    if (s_last && tid < BN && j0 + tid < H) {
+        __threadfence();
+        bn_finalize_column(f.bn, f.part, chunks, BM, M, H, j0 + tid, blockIdx.x == 0 && tid == 0);
+    }
+}
 
 template <int LAYOUT, bool PRO>
 __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(GemmBatch batch) {
@@ -118,16 +176,15 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(GemmBatch batch) {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int gi = i0 + ty * 4 + i;
-        if (gi >= g.M) continue;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int gj = j0 + tx * 4 + j;
-            if (gj >= g.N) continue;
-            float v = acc[i][j];
-            if (LAYOUT == kNT && g.bias != nullptr) v += g.bias[gj];
-            C[(size_t)gi * g.ldc + gj] = v;
+            if (LAYOUT == kNT && g.bias != nullptr && gj < g.N) acc[i][j] += g.bias[gj];
+            if (gi < g.M && gj < g.N) C[(size_t)gi * g.ldc + gj] = acc[i][j];
         }
     }
+    if (LAYOUT == kNT && batch.bn[blockIdx.z].enabled)
+        gemm_bn_epilogue(batch.bn[blockIdx.z], As, &Bs[0][0], acc, i0, j0, g.M, g.N, tx, ty, tid);
 }
 
 // Vectorised, double-buffered version of the same tile (used whenever lda, ldb, K-range and N are multiples of
@@ -227,18 +284,20 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_vec_kernel(GemmBatch batch)
         __syncthreads();
         buf ^= 1;
     }
+    const int gj = j0 + tx * 4;
+    if (LAYOUT == kNT && g.bias != nullptr && gj < g.N) {
+        const float4 bb = ldg4(g.bias + gj);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { acc[i][0] += bb.x; acc[i][1] += bb.y; acc[i][2] += bb.z; acc[i][3] += bb.w; }
+    }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int gi = i0 + ty * 4 + i;
-        const int gj = j0 + tx * 4;
         if (gi >= g.M || gj >= g.N) continue;
-        float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        if (LAYOUT == kNT && g.bias != nullptr) {
-            const float4 bb = ldg4(g.bias + gj);
-            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-        }
-        *reinterpret_cast<float4*>(C + (size_t)gi * g.ldc + gj) = o;
+        *reinterpret_cast<float4*>(C + (size_t)gi * g.ldc + gj) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     }
+    if (LAYOUT == kNT && batch.bn[blockIdx.z].enabled)
+        gemm_bn_epilogue(batch.bn[blockIdx.z], As[0], &Bs[0][0][0], acc, i0, j0, g.M, g.N, tx, ty, tid);
 }
 
 static bool gemm_vec_ok(const GemmArgs& g, int layout) {
@@ -264,13 +323,6 @@ static void launch_gemm(const GemmBatch& gb, int nbatch, dim3 grid, cudaStream_t
 // train: scale = w / sqrt(var_b + eps), shift = b - mean_b scale; running stats updated with momentum 0.1
 // and the unbiased variance; num_batches_tracked += 1.   eval: the same from the running statistics.
 // ------------------------------------------------------------------------------------------------
-struct BnArgs {
-    const float* z;             // [B][H]
-    const float *w, *b;
-    float *run_mean, *run_var;
-    int64_t* batches;
-    float *scale, *shift, *mean, *rstd;
-};
 struct BnBatch {
     BnArgs a[2];
 };
@@ -372,27 +424,7 @@ bn_stats_split_kernel(BnBatch batch, int B, int H, float* __restrict__ part, uns
     __syncthreads();
     if (!s_last || r != 0) return;
     __threadfence();
-    const float* Q = part + (size_t)blockIdx.z * R * 2 * H;
-    float n = 0.f, mean = 0.f, M2 = 0.f;
-    for (int k = 0; k < R; k++) {
-        const float nb = (float)min(8 * kBnRowsPerThread, B - k * 8 * kBnRowsPerThread);
-        const float mb = __ldcg(Q + (size_t)k * 2 * H + f), Mb = __ldcg(Q + (size_t)k * 2 * H + H + f);
-        const float nn = n + nb, delta = mb - mean;
-        mean = fmaf(delta, nb / nn, mean);
-        M2 = M2 + Mb + delta * delta * (n * nb / nn);
-        n = nn;
-    }
-    const float var = M2 / (float)B;
-    const float unbiased = B > 1 ? M2 / (float)(B - 1) : var;
-    a.run_mean[f] = fmaf(kBnMomentum, mean - a.run_mean[f], a.run_mean[f]);
-    a.run_var[f] = fmaf(kBnMomentum, unbiased - a.run_var[f], a.run_var[f]);
-    if (blockIdx.x == 0 && c == 0 && a.batches != nullptr) *a.batches += 1;
-    const float rstd = 1.f / sqrtf(var + kBnEps);
-    const float sc = a.w[f] * rstd;
-    a.scale[f] = sc;
-    a.shift[f] = fmaf(-mean, sc, a.b[f]);
-    a.mean[f] = mean;
-    a.rstd[f] = rstd;
+    bn_finalize_column(a, part + (size_t)blockIdx.z * R * 2 * H, R, 8 * kBnRowsPerThread, B, H, f, blockIdx.x == 0 && c == 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -992,21 +1024,30 @@ static int check_params(const rloa_naf_ws* ws, const rloa_naf_params* p, const c
 static int trunk_forward(rloa_naf_ws* ws, int nets, const rloa_naf_params* const* P, const float* const* x, int B,
                          int train, cudaStream_t st) {
     const int H = ws->H, S = ws->S;
+    // train-mode statistics ride in the epilogue of the producing kernel (bn_fuse.cuh) once the batch is large
+    // enough to be split over row tiles; eval mode (and tiny batches) use the stand-alone column kernel
+    const bool fuse = train && B >= kBnSplitMinBatch;
+    const int chunks = bn_chunks(B);
     GemmBatch gb{};
     BnBatch bb{};
     for (int n = 0; n < nets; n++) {
         gb.a[n] = GemmArgs{x[n], S, P[n]->w1, S, ws->z1[n], H, P[n]->b1, nullptr, nullptr, B, H, S, 0};
         bb.a[n] = BnArgs{ws->z1[n], P[n]->bn1_w, P[n]->bn1_b, P[n]->bn1_mean, P[n]->bn1_var, P[n]->bn1_batches,
                          ws->scale[n][0], ws->shift[n][0], ws->mean[n][0], ws->rstd[n][0]};
+        gb.bn[n] = BnFuse{bb.a[n], ws->bn_part + (size_t)n * chunks * 2 * H, ws->tickets + n * (H / 32), fuse ? 1 : 0};
     }
     dim3 grid((H + BN - 1) / BN, (B + BM - 1) / BM, nets);
     launch_gemm<kNT, false>(gb, nets, grid, st);
     RLOA_LAUNCHED();
-    if (train && B >= kBnSplitMinBatch)
-        bn_stats_split_kernel<<<dim3(H / 32, bn_chunks(B), nets), 256, 0, st>>>(bb, B, H, ws->bn_part, ws->tickets);
-    else
+    if (!fuse) {
         bn_stats_kernel<<<dim3(H / 32, nets), 256, 0, st>>>(bb, B, H, train);
-    RLOA_LAUNCHED();
+        RLOA_LAUNCHED();
+    }
+    for (int n = 0; n < nets; n++) {
+        bb.a[n] = BnArgs{ws->z2[n], P[n]->bn2_w, P[n]->bn2_b, P[n]->bn2_mean, P[n]->bn2_var, P[n]->bn2_batches,
+                         ws->scale[n][1], ws->shift[n][1], ws->mean[n][1], ws->rstd[n][1]};
+        gb.bn[n].bn = bb.a[n];
+    }
     if (ws->trunk_mode == 1) {
         const float *z1p[2], *scp[2], *shp[2], *w2p[2], *b2p[2];
         float* z2p[2];
@@ -1014,7 +1055,7 @@ static int trunk_forward(rloa_naf_ws* ws, int nets, const rloa_naf_params* const
             z1p[n] = ws->z1[n]; scp[n] = ws->scale[n][0]; shp[n] = ws->shift[n][0];
             w2p[n] = P[n]->w2; b2p[n] = P[n]->b2; z2p[n] = ws->z2[n];
         }
-        const int rc = trunk_tc_layer2(&ws->tc, nets, z1p, scp, shp, w2p, b2p, z2p, B, H, st);
+        const int rc = trunk_tc_layer2(&ws->tc, nets, z1p, scp, shp, w2p, b2p, z2p, B, H, fuse ? gb.bn : nullptr, st);
         if (rc != RLOA_OK) return rc;
     } else {
         for (int n = 0; n < nets; n++)
@@ -1022,14 +1063,10 @@ static int trunk_forward(rloa_naf_ws* ws, int nets, const rloa_naf_params* const
         launch_gemm<kNT, true>(gb, nets, grid, st);
         RLOA_LAUNCHED();
     }
-    for (int n = 0; n < nets; n++)
-        bb.a[n] = BnArgs{ws->z2[n], P[n]->bn2_w, P[n]->bn2_b, P[n]->bn2_mean, P[n]->bn2_var, P[n]->bn2_batches,
-                         ws->scale[n][1], ws->shift[n][1], ws->mean[n][1], ws->rstd[n][1]};
-    if (train && B >= kBnSplitMinBatch)
-        bn_stats_split_kernel<<<dim3(H / 32, bn_chunks(B), nets), 256, 0, st>>>(bb, B, H, ws->bn_part, ws->tickets);
-    else
+    if (!fuse) {
         bn_stats_kernel<<<dim3(H / 32, nets), 256, 0, st>>>(bb, B, H, train);
-    RLOA_LAUNCHED();
+        RLOA_LAUNCHED();
+    }
     return RLOA_OK;
 }
 
@@ -1039,7 +1076,7 @@ extern "C" int rloa_naf_hidden_layer(rloa_naf_ws* ws, const float* z1, const flo
     RLOA_REQUIRE(batch >= 1, "rloa_naf_hidden_layer: batch >= 1 required");
     cudaStream_t st = as_stream(stream);
     const int H = ws->H;
-    if (ws->trunk_mode == 1) return trunk_tc_layer2(&ws->tc, 1, &z1, &scale, &shift, &w2, &b2, &z2, batch, H, st);
+    if (ws->trunk_mode == 1) return trunk_tc_layer2(&ws->tc, 1, &z1, &scale, &shift, &w2, &b2, &z2, batch, H, nullptr, st);
     GemmBatch gb{};
     gb.a[0] = GemmArgs{z1, H, w2, H, z2, H, b2, scale, shift, batch, H, H, 0};
     launch_gemm<kNT, true>(gb, 1, dim3((H + BN - 1) / BN, (batch + BM - 1) / BM, 1), st);

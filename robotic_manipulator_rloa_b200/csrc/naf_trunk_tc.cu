@@ -45,6 +45,7 @@ struct TcNet {
 };
 struct TcBatch {
     TcNet n[2];
+    BnFuse bn[2];               // train-mode BatchNorm statistics of z2, fused into the epilogue (bn_fuse.cuh)
 };
 
 // 8 consecutive fp32 -> one 16-byte chunk of bf16
@@ -201,17 +202,65 @@ __global__ void __launch_bounds__(kTcThreads) trunk_tc_layer2_kernel(const __gri
               "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < B) {
+        const bool fuse = batch.bn[blockIdx.z].enabled != 0;
+        float* tile = reinterpret_cast<float*>(sm_a);          // [128][65] fp32: the operand tiles are dead after the MMAs
+        const int trow = (warp & 3) * 32 + lane;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 bias = *reinterpret_cast<const float4*>(g.b2 + n0 + half * 32 + j);
-                float4 o;
-                o.x = __uint_as_float(v[j]) + bias.x;
-                o.y = __uint_as_float(v[j + 1]) + bias.y;
-                o.z = __uint_as_float(v[j + 2]) + bias.z;
-                o.w = __uint_as_float(v[j + 3]) + bias.w;
-                *reinterpret_cast<float4*>(dst + half * 32 + j) = o;
+        for (int j = 0; j < 32; j += 4) {
+            const float4 bias = *reinterpret_cast<const float4*>(g.b2 + n0 + half * 32 + j);
+            float4 o;
+            o.x = __uint_as_float(v[j]) + bias.x;
+            o.y = __uint_as_float(v[j + 1]) + bias.y;
+            o.z = __uint_as_float(v[j + 2]) + bias.z;
+            o.w = __uint_as_float(v[j + 3]) + bias.w;
+            if (row < B) *reinterpret_cast<float4*>(dst + half * 32 + j) = o;
+            if (fuse) {
+                float* tr = tile + trow * 65 + half * 32 + j;
+                tr[0] = o.x; tr[1] = o.y; tr[2] = o.z; tr[3] = o.w;
             }
+        }
+    }
+    if (batch.bn[blockIdx.z].enabled) {
+        // ---- BatchNorm statistics of this 128 x 64 tile: column mean and centred second moment over its valid rows,
+        // then the last row tile of the column group merges all partials and finalises (bn_fuse.cuh) ----
+        const BnFuse& f = batch.bn[blockIdx.z];
+        const float* tile = reinterpret_cast<const float*>(sm_a);
+        float* red = reinterpret_cast<float*>(sm_a) + 128 * 65;     // [4][64] + [64]
+        __shared__ unsigned s_last;
+        const int rows = min(kTcM, B - m0), c = tid & 63, grp = tid >> 6;
+        __syncthreads();
+        float s = 0.f;
+        for (int r = grp * 32; r < grp * 32 + 32; r++) s += r < rows ? tile[r * 65 + c] : 0.f;
+        red[grp * 64 + c] = s;
+        __syncthreads();
+        if (tid < 64) red[256 + tid] = (red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid]) / (float)rows;
+        __syncthreads();
+        const float mean_c = red[256 + c];
+        s = 0.f;
+        for (int r = grp * 32; r < grp * 32 + 32; r++) {
+            const float d = r < rows ? tile[r * 65 + c] - mean_c : 0.f;
+            s = fmaf(d, d, s);
+        }
+        __syncthreads();
+        red[grp * 64 + c] = s;
+        __syncthreads();
+        const int chunks = gridDim.x;
+        if (tid < 64) {
+            float* P = f.part + (size_t)blockIdx.x * 2 * kTcK;
+            P[n0 + tid] = mean_c;
+            P[kTcK + n0 + tid] = red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid];
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned t = atomicAdd(&f.ticket[blockIdx.y], 1u);
+            s_last = (t == (unsigned)chunks - 1u) ? 1u : 0u;
+            if (s_last) f.ticket[blockIdx.y] = 0u;
+        }
+        __syncthreads();
+        if (s_last && tid < 64) {
+            __threadfence();
+            bn_finalize_column(f.bn, f.part, chunks, kTcM, B, kTcK, n0 + tid, blockIdx.y == 0 && tid == 0);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -240,11 +289,15 @@ int trunk_tc_prepare(TrunkTC* t, int max_batch, int H) {
 }
 
 int trunk_tc_layer2(TrunkTC* t, int nets, const float* const* z1, const float* const* scale, const float* const* shift,
-                    const float* const* w2, const float* const* b2, float* const* z2, int B, int H, cudaStream_t st) {
+                    const float* const* w2, const float* const* b2, float* const* z2, int B, int H, const BnFuse* bn,
+                    cudaStream_t st) {
     RLOA_REQUIRE(t->ready, "tcgen05 trunk: rloa_naf_ws_set_trunk(1) was not called");
     RLOA_REQUIRE(H == kTcK && nets >= 1 && nets <= 2, "tcgen05 trunk: hidden = 256 and 1..2 networks per launch");
     TcBatch tb{};
-    for (int n = 0; n < nets; n++) tb.n[n] = TcNet{z1[n], scale[n], shift[n], w2[n], b2[n], z2[n]};
+    for (int n = 0; n < nets; n++) {
+        tb.n[n] = TcNet{z1[n], scale[n], shift[n], w2[n], b2[n], z2[n]};
+        if (bn != nullptr) tb.bn[n] = bn[n];
+    }
     dim3 grid((B + kTcM - 1) / kTcM, kTcK / kTcN, nets);
     trunk_tc_layer2_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(tb, B);
     RLOA_LAUNCHED();

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "bn_fuse.cuh"
 #include "rloa_b200.h"
 
 namespace rloa {
@@ -17,9 +18,11 @@ void trunk_tc_init(TrunkTC* t);
 void trunk_tc_free(TrunkTC* t);
 // checks the device, opts the kernel into its dynamic shared memory size
 int trunk_tc_prepare(TrunkTC* t, int max_batch, int H);
-// for each of `nets` networks: z2[B][H] = bf16(relu(z1 * scale + shift)) @ bf16(w2)^T + b2, fp32 accumulation in TMEM
+// for each of `nets` networks: z2[B][H] = bf16(relu(z1 * scale + shift)) @ bf16(w2)^T + b2, fp32 accumulation in TMEM;
+// bn (one BnFuse per net, or NULL): train-mode BatchNorm statistics of z2 fused into the epilogue (128-row chunks)
 int trunk_tc_layer2(TrunkTC* t, int nets, const float* const* z1, const float* const* scale, const float* const* shift,
-                    const float* const* w2, const float* const* b2, float* const* z2, int B, int H, cudaStream_t st);
+                    const float* const* w2, const float* const* b2, float* const* z2, int B, int H, const BnFuse* bn,
+                    cudaStream_t st);
 
 // fused eval-mode policy (naf_policy_tc.cu): supported shapes, one-time setup, and NAFAgent.act for `batch` rows
 bool policy_tc_supported(int S, int A, int H);
