@@ -271,6 +271,14 @@ int rloa_naf_learn_grads(rloa_naf_ws* ws, const rloa_naf_params* main_net, const
 int rloa_naf_learn_apply(rloa_naf_ws* ws, const rloa_naf_params* main_net, const rloa_naf_params* target_net,
                          const rloa_adam_state* adam, const rloa_naf_hyper* hp, float* grad,
                          float* grad_norm, void* stream);
+/* NAFAgent.learn in one call for a single rank (naf_algorithm.py:180-226): _grads followed by _apply, with the
+ * split-K reduction, the gradient norm and clip + Adam + soft update fused into one kernel.  Same results
+ * as the two calls, bit for bit; `grad` still receives the flat gradient. */
+int rloa_naf_learn_step(rloa_naf_ws* ws, const rloa_naf_params* main_net, const rloa_naf_params* target_net,
+                        const rloa_adam_state* adam, const float* states, const float* actions,
+                        const float* rewards, const float* next_states, const float* dones, int32_t batch,
+                        const rloa_naf_hyper* hp, float* grad, float* loss, float* grad_norm, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Gradient exchange over NVLink peer memory (N > 1 ranks on one node, one process per GPU).  Replaces the
  * NCCL all-reduce between _grads and _apply: every rank owns an exchange block exported with CUDA IPC and

@@ -114,6 +114,8 @@ SIGNATURES = {
                                        C.POINTER(NafHyper), _fp, _fp, _VP]),
     'rloa_naf_learn_apply': (C.c_int, [_VP, C.POINTER(NafParams), C.POINTER(NafParams), C.POINTER(AdamState),
                                        C.POINTER(NafHyper), _fp, _fp, _VP]),
+    'rloa_naf_learn_step': (C.c_int, [_VP, C.POINTER(NafParams), C.POINTER(NafParams), C.POINTER(AdamState), _fp, _fp, _fp,
+                                      _fp, _fp, _I, C.POINTER(NafHyper), _fp, _fp, _fp, _VP]),
     'rloa_xchg_create': (C.c_int, [_I, C.POINTER(_VP)]),
     'rloa_xchg_handle': (C.c_int, [_VP, C.c_char_p]),
     'rloa_xchg_connect': (C.c_int, [_VP, _I, _I, C.c_char_p]),

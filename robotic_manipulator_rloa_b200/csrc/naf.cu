@@ -772,6 +772,7 @@ head_bias_grad_kernel(const float* __restrict__ dzh, int B, int NH, int A, float
 // sums the split-K partials of up to 3 weight gradients in a fixed order (deterministic)
 struct ReduceSeg {
     const float* part; float* out; int n; int nsplit; size_t pstride;
+    int off;                    // offset of `out` in the flat gradient
 };
 struct ReduceArgs {
     ReduceSeg s[5];
@@ -830,6 +831,83 @@ adam_soft_update_kernel(ParamTable pt, const float* __restrict__ grad, const flo
         adam_soft_update_element(pt, i, grad[i], c, m, v, hp);
 }
 
+// The single-GPU tail of NAFAgent.learn in ONE launch (kNormBlocks co-resident blocks): fixed-order sum of the
+// split-K partials into the flat gradient, squared-norm partials, a device-wide barrier, then clip + Adam + soft
+// update of the same elements.  Element-to-thread mapping, summation order and arithmetic are those of
+// splitk_reduce_kernel + grad_sqsum_kernel + adam_soft_update_kernel, so the result is bit-identical to the three.
+__device__ __forceinline__ float splitk_element(const ReduceArgs& r, int e, float current) {
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+        const ReduceSeg& sg = r.s[q];
+        const int j = e - sg.off;
+        if (j >= 0 && j < sg.n) {
+            float t = 0.f;
+            for (int k = 0; k < sg.nsplit; k++) t += sg.part[k * sg.pstride + j];
+            return t;
+        }
+    }
+    return current;
+}
+
+__global__ void __launch_bounds__(256)
+splitk_adam_kernel(ReduceArgs r, float* __restrict__ grad, ParamTable pt, float* __restrict__ m, float* __restrict__ v,
+                   int64_t* __restrict__ step_ptr, rloa_naf_hyper hp, float* __restrict__ sq_partial,
+                   unsigned* __restrict__ barrier, float* __restrict__ grad_norm_out) {
+    __shared__ float red[256];
+    __shared__ AdamCoef s_c;
+    const int n = pt.offset[14];
+    const int n4 = ((reinterpret_cast<uintptr_t>(grad) & 15u) == 0) ? (n >> 2) : 0;
+    float s = 0.f;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n4; i += gridDim.x * 256) {
+        float4 g = reinterpret_cast<float4*>(grad)[i];
+        g.x = splitk_element(r, 4 * i, g.x); g.y = splitk_element(r, 4 * i + 1, g.y);
+        g.z = splitk_element(r, 4 * i + 2, g.z); g.w = splitk_element(r, 4 * i + 3, g.w);
+        reinterpret_cast<float4*>(grad)[i] = g;
+        const float x0 = g.x * hp.grad_scale, x1 = g.y * hp.grad_scale, x2 = g.z * hp.grad_scale, x3 = g.w * hp.grad_scale;
+        s = fmaf(x0, x0, s); s = fmaf(x1, x1, s); s = fmaf(x2, x2, s); s = fmaf(x3, x3, s);
+    }
+    for (int i = 4 * n4 + blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const float g = splitk_element(r, i, grad[i]);
+        grad[i] = g;
+        const float x = g * hp.grad_scale;
+        s = fmaf(x, x, s);
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {       // device-wide barrier: arrival count + generation (all blocks are co-resident)
+        volatile unsigned* gen = barrier + 1;
+        const unsigned gen0 = *gen;
+        sq_partial[blockIdx.x] = red[0];
+        if (blockIdx.x == 0) *step_ptr += 1;                     // optimizer.step() counter
+        __threadfence();
+        if (atomicAdd(barrier, 1u) == gridDim.x - 1u) {
+            barrier[0] = 0u;
+            __threadfence();
+            atomicAdd(barrier + 1, 1u);
+        } else {
+            while (*gen == gen0) { }
+        }
+        __threadfence();
+        s_c = adam_coefficients(sq_partial, *reinterpret_cast<volatile int64_t*>(step_ptr), hp);
+        if (blockIdx.x == 0 && grad_norm_out != nullptr) *grad_norm_out = s_c.norm;
+    }
+    __syncthreads();
+    const AdamCoef c = s_c;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n4; i += gridDim.x * 256) {
+        const float4 g = reinterpret_cast<const float4*>(grad)[i];
+        adam_soft_update_element(pt, 4 * i, g.x, c, m, v, hp);
+        adam_soft_update_element(pt, 4 * i + 1, g.y, c, m, v, hp);
+        adam_soft_update_element(pt, 4 * i + 2, g.z, c, m, v, hp);
+        adam_soft_update_element(pt, 4 * i + 3, g.w, c, m, v, hp);
+    }
+    for (int i = 4 * n4 + blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
+        adam_soft_update_element(pt, i, grad[i], c, m, v, hp);
+}
+
 __global__ void __launch_bounds__(256) soft_update_kernel(ParamTable pt, float tau) {
     const int n = pt.offset[14];
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
@@ -870,7 +948,7 @@ struct rloa_naf_ws {
     float *v_tmp;
     float *bn_part;              // [2 nets][R][2][H] chunk statistics / [R][3][H] backward partial sums
     float *bwd_coef;             // [3][H] k1, cB, cC of the BatchNorm backward
-    unsigned* tickets;           // [2 * H / 32] last-block-done counters (always return to 0)
+    unsigned* tickets;           // [2 * H / 32] last-block-done counters (always return to 0) + [2] device barrier
     size_t splitk_floats;
     int n_loss_parts;
     cudaStream_t side[2] = {nullptr, nullptr};   // weight-gradient contractions run beside the critical path
@@ -938,7 +1016,7 @@ extern "C" int rloa_naf_ws_create(int32_t S, int32_t A, int32_t H, int32_t max_b
                    + 16 * (size_t)H  // scale/shift/mean/rstd [2][2]
                    + (size_t)max_batch * ws->NH + BH + 2 * (size_t)max_batch + ws->n_loss_parts + ws->splitk_floats +
                    kNormBlocks + (size_t)ws->NH * H +
-                   (size_t)bn_chunks(max_batch) * 4 * H + 3 * (size_t)H + 2 * (size_t)(H / 32);
+                   (size_t)bn_chunks(max_batch) * 4 * H + 3 * (size_t)H + 2 * (size_t)(H / 32) + 2;
     if (cudaMalloc(&ws->block, total * sizeof(float)) != cudaSuccess) {
         set_error("rloa_naf_ws_create: cudaMalloc of %zu bytes failed: %s", total * sizeof(float),
                   cudaGetErrorString(cudaGetLastError()));
@@ -961,8 +1039,8 @@ extern "C" int rloa_naf_ws_create(int32_t S, int32_t A, int32_t H, int32_t max_b
     ws->wh_pack = p; p += (size_t)ws->NH * H;
     ws->bn_part = p; p += (size_t)bn_chunks(max_batch) * 4 * H;
     ws->bwd_coef = p; p += 3 * (size_t)H;
-    ws->tickets = reinterpret_cast<unsigned*>(p); p += 2 * (size_t)(H / 32);
-    cudaMemset(ws->tickets, 0, 2 * (size_t)(H / 32) * sizeof(unsigned));
+    ws->tickets = reinterpret_cast<unsigned*>(p); p += 2 * (size_t)(H / 32) + 2;     // + arrival count, generation
+    cudaMemset(ws->tickets, 0, (2 * (size_t)(H / 32) + 2) * sizeof(unsigned));
     const int hb = (ws->NH * (H + 1) + ((ws->NH + 31) & ~31) + kHeadWarps * H + H) * (int)sizeof(float);
     if (hb > 48 * 1024) cudaFuncSetAttribute(naf_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
     trunk_tc_init(&ws->tc);
@@ -1162,10 +1240,12 @@ static int bn_relu_backward(rloa_naf_ws* ws, float* da, const float* z, const fl
     return RLOA_OK;
 }
 
-extern "C" int rloa_naf_learn_grads(rloa_naf_ws* ws, const rloa_naf_params* mn, const rloa_naf_params* tg,
-                                    const float* states, const float* actions, const float* rewards,
-                                    const float* next_states, const float* dones, int32_t batch,
-                                    const rloa_naf_hyper* hp, float* grad, float* loss, void* stream) {
+// forward of both nets, loss, backward.  With defer != NULL the final split-K reduction is NOT launched: its
+// description is returned instead, for the fused tail kernel of rloa_naf_learn_step.
+static int learn_grads_impl(rloa_naf_ws* ws, const rloa_naf_params* mn, const rloa_naf_params* tg,
+                            const float* states, const float* actions, const float* rewards,
+                            const float* next_states, const float* dones, int32_t batch,
+                            const rloa_naf_hyper* hp, float* grad, float* loss, ReduceArgs* defer, void* stream) {
     RLOA_REQUIRE(ws && states && actions && rewards && next_states && hp && grad, "rloa_naf_learn_grads: null argument");
     RLOA_REQUIRE(batch >= 2 && batch <= ws->max_batch, "rloa_naf_learn_grads: 2 <= batch <= workspace max_batch required");
     RLOA_REQUIRE(!(hp->use_done_mask && dones == nullptr), "rloa_naf_learn_grads: use_done_mask needs dones");
@@ -1256,14 +1336,25 @@ extern "C" int rloa_naf_learn_grads(rloa_naf_ws* ws, const rloa_naf_params* mn, 
     RLOA_CUDA(cudaStreamWaitEvent(st, ws->join_ev[0], 0));
     RLOA_CUDA(cudaStreamWaitEvent(st, ws->join_ev[1], 0));
     ReduceArgs ra{};
-    ra.s[0] = ReduceSeg{part_w2, grad + fl.w2, H * H, nsplit, (size_t)H * H};
-    ra.s[1] = ReduceSeg{part_w1, grad + fl.w1, H * S, nsplit, (size_t)H * S};
-    ra.s[2] = ReduceSeg{part_wh, grad + fl.wmu, A * H, nsplit, (size_t)NH * H};
-    ra.s[3] = ReduceSeg{part_wh + (size_t)A * H, grad + fl.wv, H, nsplit, (size_t)NH * H};
-    ra.s[4] = ReduceSeg{part_wh + (size_t)(A + 1) * H, grad + fl.wl, NL * H, nsplit, (size_t)NH * H};
+    ra.s[0] = ReduceSeg{part_w2, grad + fl.w2, H * H, nsplit, (size_t)H * H, fl.w2};
+    ra.s[1] = ReduceSeg{part_w1, grad + fl.w1, H * S, nsplit, (size_t)H * S, fl.w1};
+    ra.s[2] = ReduceSeg{part_wh, grad + fl.wmu, A * H, nsplit, (size_t)NH * H, fl.wmu};
+    ra.s[3] = ReduceSeg{part_wh + (size_t)A * H, grad + fl.wv, H, nsplit, (size_t)NH * H, fl.wv};
+    ra.s[4] = ReduceSeg{part_wh + (size_t)(A + 1) * H, grad + fl.wl, NL * H, nsplit, (size_t)NH * H, fl.wl};
+    if (defer != nullptr) {
+        *defer = ra;
+        return RLOA_OK;
+    }
     splitk_reduce_kernel<<<dim3(64, 5), 256, 0, st>>>(ra);
     RLOA_LAUNCHED();
     return RLOA_OK;
+}
+
+extern "C" int rloa_naf_learn_grads(rloa_naf_ws* ws, const rloa_naf_params* mn, const rloa_naf_params* tg,
+                                    const float* states, const float* actions, const float* rewards,
+                                    const float* next_states, const float* dones, int32_t batch,
+                                    const rloa_naf_hyper* hp, float* grad, float* loss, void* stream) {
+    return learn_grads_impl(ws, mn, tg, states, actions, rewards, next_states, dones, batch, hp, grad, loss, nullptr, stream);
 }
 
 static void fill_param_table(const rloa_naf_params* mn, const rloa_naf_params* tg, ParamTable* pt) {
@@ -1299,6 +1390,22 @@ extern "C" int rloa_naf_learn_apply(rloa_naf_ws* ws, const rloa_naf_params* mn, 
     RLOA_LAUNCHED();
     adam_soft_update_kernel<<<(n + 1023) / 1024, 256, 0, st>>>(pt, grad, ws->sq_partial, adam->m, adam->v, adam->step, *hp,
                                                              grad_norm);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
+extern "C" int rloa_naf_learn_step(rloa_naf_ws* ws, const rloa_naf_params* mn, const rloa_naf_params* tg,
+                                   const rloa_adam_state* adam, const float* states, const float* actions,
+                                   const float* rewards, const float* next_states, const float* dones, int32_t batch,
+                                   const rloa_naf_hyper* hp, float* grad, float* loss, float* grad_norm, void* stream) {
+    RLOA_REQUIRE(adam && adam->m && adam->v && adam->step, "rloa_naf_learn_step: null optimiser state");
+    ReduceArgs ra{};
+    int rc = learn_grads_impl(ws, mn, tg, states, actions, rewards, next_states, dones, batch, hp, grad, loss, &ra, stream);
+    if (rc != RLOA_OK) return rc;
+    ParamTable pt;
+    fill_param_table(mn, tg, &pt);
+    splitk_adam_kernel<<<kNormBlocks, 256, 0, as_stream(stream)>>>(ra, grad, pt, adam->m, adam->v, adam->step, *hp,
+                                                                  ws->sq_partial, ws->tickets + 2 * (ws->H / 32), grad_norm);
     RLOA_LAUNCHED();
     return RLOA_OK;
 }

@@ -35,13 +35,22 @@ replay_append_kernel(rloa_replay rb, int n, const float* __restrict__ states, co
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row0 = blockIdx.x * kAppendRows;
     const long long cur = *reinterpret_cast<const volatile long long*>(rb.cursor);
-    // valid rows of the earlier blocks / of all blocks
+    // valid rows of the earlier blocks / of all blocks: from the per-block counts of replay_count_kernel, or — for
+    // the batch sizes of a training loop (n <= 16384) — counted here straight from the mask, which saves the launch
     int before = 0, total = 0;
     if (valid != nullptr) {
-        for (int b = tid; b < (int)gridDim.x; b += kAppendThreads) {
-            const int cnt = block_counts[b];
-            total += cnt;
-            if (b < (int)blockIdx.x) before += cnt;
+        if (block_counts != nullptr) {
+            for (int b = tid; b < (int)gridDim.x; b += kAppendThreads) {
+                const int cnt = block_counts[b];
+                total += cnt;
+                if (b < (int)blockIdx.x) before += cnt;
+            }
+        } else {
+            for (int i = tid; i < n; i += kAppendThreads) {
+                const int vv = valid[i] != 0 ? 1 : 0;
+                total += vv;
+                if (i < row0) before += vv;
+            }
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
@@ -191,13 +200,15 @@ extern "C" int rloa_replay_append(const rloa_replay* rb, int32_t n, const float*
     cudaStream_t st = as_stream(stream);
     const int nblocks = (n + kAppendRows - 1) / kAppendRows;
     RLOA_REQUIRE(rb->scratch != nullptr, "rloa_replay_append: rb->scratch is required");
-    if (valid != nullptr) {
+    const bool count_pass = valid != nullptr && n > 16384;
+    if (count_pass) {
         replay_count_kernel<<<nblocks, kAppendRows, 0, st>>>(valid, n, rb->scratch + 1);
         RLOA_LAUNCHED();
     }
-    // scratch[0] = ticket counter (zero at rest), scratch[1..] = per-block valid counts
+    // scratch[0] = ticket counter (zero at rest), scratch[1..] = per-block valid counts (large appends only)
     replay_append_kernel<<<nblocks, kAppendThreads, 0, st>>>(*rb, n, states, actions, rewards, next_states, dones, valid,
-                                                         rb->scratch + 1, reinterpret_cast<unsigned*>(rb->scratch));
+                                                            count_pass ? rb->scratch + 1 : nullptr,
+                                                            reinterpret_cast<unsigned*>(rb->scratch));
     RLOA_LAUNCHED();
     return RLOA_OK;
 }

@@ -109,6 +109,7 @@ class NAFAgent:
         # 'nccl' = torch.distributed all-reduce between the two native calls (the baseline); RLOA_GRAD_EXCHANGE selects
         self.grad_exchange_mode = os.environ.get('RLOA_GRAD_EXCHANGE', 'peer')
         self._xchg: Optional[rdist.GradExchange] = None
+        self.fused_learn = True                     # single rank: one-call learn (rloa_naf_learn_step)
 
     # ------------------------------------------------------------------------------------------
     # native plumbing
@@ -242,11 +243,19 @@ class NAFAgent:
         hp = self._hyper()
         pm, pt = self.qnetwork_main.native_params(), self.qnetwork_target.native_params()
         st = self._stream()
+        adam = self.optimizer.native()
+        xchg = self._exchange()
+        if xchg is None and self.world_size == 1 and self.fused_learn:
+            # single rank: backward tail, gradient norm and the optimiser in one kernel (rloa_naf_learn_step)
+            N.check(ws.lib.rloa_naf_learn_step(ws.handle, C.byref(pm), C.byref(pt), C.byref(adam), s.data_ptr(),
+                                               a.data_ptr(), r.data_ptr(), s2.data_ptr(), d.data_ptr(), B, C.byref(hp),
+                                               b['grad'].data_ptr(), b['loss'].data_ptr(), b['gnorm'].data_ptr(), st),
+                    'rloa_naf_learn_step')
+            self.last_loss, self.last_grad_norm = b['loss'], b['gnorm']
+            return
         N.check(ws.lib.rloa_naf_learn_grads(ws.handle, C.byref(pm), C.byref(pt), s.data_ptr(), a.data_ptr(),
                                             r.data_ptr(), s2.data_ptr(), d.data_ptr(), B, C.byref(hp),
                                             b['grad'].data_ptr(), b['loss'].data_ptr(), st), 'rloa_naf_learn_grads')
-        adam = self.optimizer.native()
-        xchg = self._exchange()
         if xchg is not None:             # the one exchange step of the data-parallel path, inside the optimiser kernels
             N.check(ws.lib.rloa_naf_learn_apply_xchg(ws.handle, C.byref(pm), C.byref(pt), C.byref(adam), C.byref(hp),
                                                      xchg.handle, b['grad'].data_ptr(), b['gnorm'].data_ptr(), st),

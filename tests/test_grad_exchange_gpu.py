@@ -42,12 +42,14 @@ def _params(agent):
 
 def test_single_rank_exchange_is_bit_identical_to_plain_apply():
     dev = torch.device('cuda:0')
-    plain, peer = _agent('nccl', dev), _agent('peer-always', dev)
+    plain, peer, two_call = _agent('nccl', dev), _agent('peer-always', dev), _agent('nccl', dev)
+    two_call.fused_learn = False        # rloa_naf_learn_grads + rloa_naf_learn_apply instead of rloa_naf_learn_step
     for step in range(3):
-        plain.learn(_batch(step)); peer.learn(_batch(step))
+        plain.learn(_batch(step)); peer.learn(_batch(step)); two_call.learn(_batch(step))
     torch.cuda.synchronize()
     assert peer._xchg is not None and not peer._xchg.timed_out()
     assert torch.equal(_params(plain), _params(peer))
+    assert torch.equal(_params(plain), _params(two_call))       # the fused tail kernel == the three separate kernels
     assert float(plain.last_grad_norm.item()) == float(peer.last_grad_norm.item())
     assert int(peer.optimizer.step_count.item()) == 3
 
