@@ -261,7 +261,7 @@ def ours(args):
             use_graph = False
     if phase_ev is None:
         phase_ev = mk()
-    loop.phase_events = phase_ev
+    loop.phase_events = None
     for _ in range(max(args.warmup, 3)):
         loop.step()
     graphed = bool(use_graph and loop.capture())
@@ -269,40 +269,44 @@ def ours(args):
         loop.replay_pair()                        # one untimed replay
     barrier()
 
-    # ---- timed region: K steps in pairs (the state buffers ping-pong), CUDA events per pair, L2 flushed between pairs ----
+    def run_pairs(count, odd, collect, use_g):
+        """`count` pairs (+ `odd` single iteration) of the loop, one CUDA-event pair and one L2 flush per pair."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(count + odd)]
+        for i in range(count + odd):
+            if flush is not None:
+                flush.fill_(i & 0xff)
+            evs[i][0].record()
+            if i < count:
+                if use_g:
+                    loop.replay_pair()
+                else:
+                    loop._body(True, True, 0)
+                    loop._body(True, True, 1)
+            else:
+                loop._body(True, True, 0)
+            evs[i][1].record()
+            if collect is not None:
+                # the phase events are re-recorded by every pair: read them before the next pair overwrites them
+                evs[i][1].synchronize()
+                for par in range(2 if i < count else 1):
+                    for k in range(5):
+                        collect[0][k].append(phase_ev[par][k].elapsed_time(phase_ev[par][k + 1]))
+                    collect[1][par].append(phase_ev[par][0].elapsed_time(phase_ev[par][5]))
+        return evs
+
+    # ---- timed region: K steps in pairs (the state buffers ping-pong), CUDA events per pair, L2 flushed between pairs.
+    # No event nodes inside the loop here: six of them per iteration cost ~25 us, 11 % of the step ----
     npairs, odd = args.steps // 2, args.steps % 2
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(npairs + odd)]
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     loop.transitions.zero_()
     launches0 = lib.rloa_launch_count()
-    phase_ms = [[] for _ in range(5)]
     barrier()
     t_wall = time.perf_counter()
-    for i in range(npairs + odd):
-        if flush is not None:
-            flush.fill_(i & 0xff)
-        ev[i][0].record()
-        if i < npairs:
-            if graphed:
-                loop.replay_pair()
-            else:
-                loop._body(True, True, 0)
-                loop._body(True, True, 1)
-        else:
-            loop._body(True, True, 0)
-        ev[i][1].record()
-        if graphed or i % 8 == 7 or i == npairs + odd - 1:
-            # the phase events are re-recorded by every pair: read them before the next pair overwrites them
-            ev[i][1].synchronize()
-            for par in range(2 if i < npairs else 1):
-                for k in range(5):
-                    phase_ms[k].append(phase_ev[par][k].elapsed_time(phase_ev[par][k + 1]))
+    ev = run_pairs(npairs, odd, None, graphed)
     barrier()
     t_wall = time.perf_counter() - t_wall
-    loop.phase_events = None
-    sim_ms = phase_ms[1]
     launches = lib.rloa_launch_count() - launches0
     if graphed:      # a graph replay re-launches the kernels recorded at capture: count them per replay
         launches = loop.graph_kernels * npairs + launches
@@ -315,6 +319,21 @@ def ours(args):
         dist.all_reduce(trans, op=dist.ReduceOp.SUM)
     total_ms, trans = float(total_ms.item()), float(trans.item())
     value = trans / (total_ms * 1e-3)
+
+    # ---- second pass, same loop and state, WITH the phase-boundary events recorded inside it (re-captured graph):
+    # where the step goes, and the live launch time of the simulator step for the roofline ----
+    phase_ms = [[] for _ in range(5)]
+    parity_ms = [[], []]                   # whole iteration right after the L2 flush / the one after it
+    loop.phase_events = phase_ev
+    graphed_phases = False
+    if graphed:
+        loop._graph = None
+        graphed_phases = loop.capture()
+    run_pairs(max(8, min(npairs, 50)), 0, (phase_ms, parity_ms), graphed_phases)
+    barrier()
+    loop.phase_events = None
+    loop._graph = None
+    sim_ms = phase_ms[1]
 
     # ---- e2e: same loop, every step's states/actions/results cross pinned host buffers -----------------------
     n, S, A = args.envs, 21, 6
@@ -372,8 +391,10 @@ def ours(args):
             'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n * (S + A) * 4,
                     'd2h_bytes_per_step': n * (A * 4 + S * 4 + 4 + 1), 'steps': e2e_steps},
+            'phases_note': 'second pass with event nodes inside the loop (each node costs ~4 us, so phases sum to more than ms_per_step)',
             'phases_ms': dict(zip(('act', 'env_step', 'replay_append', 'sample_learn', 'bookkeeping_reset'),
                                   [round(sum(x) / len(x), 5) for x in phase_ms])),
+            'iteration_ms_after_flush_then_warm': [round(sum(x) / max(len(x), 1), 5) for x in parity_ms],
             'gpu_launches': int(launches),
             'graphed': graphed, 'graph_error': loop.graph_error,
             'clocks': clocks,

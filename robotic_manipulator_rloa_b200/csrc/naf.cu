@@ -520,11 +520,19 @@ bn_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict__ z, 
     __syncthreads();
     if (!s_last || r != 0) return;
     __threadfence();
+    // partials requested in batches of 16 chunks before they are added (in chunk order): the loads overlap
     float tg = 0.f, tgx = 0.f, tz = 0.f;
-    for (int k = 0; k < R; k++) {
-        tg += __ldcg(part + (size_t)k * 3 * H + f);
-        tgx += __ldcg(part + (size_t)k * 3 * H + H + f);
-        tz += __ldcg(part + (size_t)k * 3 * H + 2 * H + f);
+    for (int k0 = 0; k0 < R; k0 += 16) {
+        float a0[16], a1[16], a2[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const bool ok = k0 + k < R;
+            a0[k] = ok ? __ldcg(part + (size_t)(k0 + k) * 3 * H + f) : 0.f;
+            a1[k] = ok ? __ldcg(part + (size_t)(k0 + k) * 3 * H + H + f) : 0.f;
+            a2[k] = ok ? __ldcg(part + (size_t)(k0 + k) * 3 * H + 2 * H + f) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++) { tg += a0[k]; tgx += a1[k]; tz += a2[k]; }
     }
     const float k1 = w[f] * rs, c1 = tg / (float)B, c2 = tgx / (float)B;
     coef.k1[f] = k1;
@@ -842,7 +850,15 @@ __device__ __forceinline__ float splitk_element(const ReduceArgs& r, int e, floa
         const int j = e - sg.off;
         if (j >= 0 && j < sg.n) {
             float t = 0.f;
-            for (int k = 0; k < sg.nsplit; k++) t += sg.part[k * sg.pstride + j];
+            int k = 0;
+            for (; k + 8 <= sg.nsplit; k += 8) {          // 8 partials in flight, added in split order
+                float x[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) x[u] = sg.part[(k + u) * sg.pstride + j];
+#pragma unroll
+                for (int u = 0; u < 8; u++) t += x[u];
+            }
+            for (; k < sg.nsplit; k++) t += sg.part[k * sg.pstride + j];
             return t;
         }
     }
