@@ -488,14 +488,22 @@ bn_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict__ z, 
     const int R = gridDim.y;
     const int row0 = blockIdx.y * (8 * kBnRowsPerThread);
     const float sc = scale[f], sh = shift[f], mu = mean[f], rs = rstd[f];
-    float sg = 0.f, sgx = 0.f, sz = 0.f;
+    // every operand is requested before the first use and the ReLU mask is a select, not a guarded load: one memory
+    // round trip for the block instead of two dependent ones per row
+    float zv[kBnRowsPerThread], dv_[kBnRowsPerThread];
 #pragma unroll
     for (int k = 0; k < kBnRowsPerThread; k++) {
         const int row = row0 + r + 8 * k;
-        if (row < B) {
-            const size_t idx = (size_t)row * H + f;
-            const float zz = z[idx];
-            const float g = fmaf(zz, sc, sh) > 0.f ? da[idx] : 0.f;
+        const size_t idx = (size_t)(row < B ? row : 0) * H + f;
+        zv[k] = z[idx];
+        dv_[k] = da[idx];
+    }
+    float sg = 0.f, sgx = 0.f, sz = 0.f;
+#pragma unroll
+    for (int k = 0; k < kBnRowsPerThread; k++) {
+        if (row0 + r + 8 * k < B) {
+            const float zz = zv[k];
+            const float g = fmaf(zz, sc, sh) > 0.f ? dv_[k] : 0.f;
             sg += g;
             sgx = fmaf(g, (zz - mu) * rs, sgx);
             sz += zz - mu;
@@ -565,6 +573,69 @@ bn_bwd_apply_kernel(float* __restrict__ da, const float* __restrict__ z, const f
         o.z = fmaf(k1.z, g.z, -cB.z) - cC.z * (zz.z - mu.z);
         o.w = fmaf(k1.w, g.w, -cB.w) - cC.w * (zz.w - mu.w);
         reinterpret_cast<float4*>(da)[i] = o;
+    }
+}
+
+// Layer-1 BatchNorm backward fused with the input-layer weight gradient: dz1 = k1 g - cB - cC (z1 - mean) is only
+// ever consumed by dW1 = dz1^T x (and by the bias gradient, which bn_bwd_reduce_kernel already produced), so it is
+// never written: block = 32 batch rows, thread = hidden column h, accumulates dW1[h][0..S) over the block's rows with
+// the x tile broadcast from shared memory, and leaves one split-K partial per block (summed in chunk order by the tail).
+constexpr int kDw1Rows = 64, kDw1MaxS = 24, kDw1Cols = 128;
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_dw1_kernel(const float* __restrict__ da, const float* __restrict__ z, const float* __restrict__ scale,
+                        const float* __restrict__ shift, const float* __restrict__ mean, BnBwdCoef coef,
+                        const float* __restrict__ x, int B, int H, int S, float* __restrict__ part) {
+    // block = (64-row chunk, 128 columns); thread = (column h, half of the chunk's rows): 32 rows each, all 64 operand
+    // loads in flight at once, then the two halves are added through shared memory
+    __shared__ __align__(16) float xs[kDw1Rows][kDw1MaxS];
+    __shared__ float half_acc[kDw1Cols][kDw1MaxS + 1];
+    const int row0 = blockIdx.x * kDw1Rows, rows = min(kDw1Rows, B - row0);
+    const int hl = threadIdx.x & (kDw1Cols - 1), rh = threadIdx.x >> 7;
+    const int h = blockIdx.y * kDw1Cols + hl;
+    constexpr int kHalf = kDw1Rows / 2;
+    float zz[kHalf], gg[kHalf];
+#pragma unroll
+    for (int u = 0; u < kHalf; u++) {
+        const int r = rh * kHalf + u;
+        const size_t idx = (size_t)(row0 + (r < rows ? r : 0)) * H + (h < H ? h : 0);
+        zz[u] = z[idx];
+        gg[u] = da[idx];
+    }
+    for (int e = threadIdx.x; e < kDw1Rows * kDw1MaxS; e += 256) {
+        const int r = e / kDw1MaxS, k = e - r * kDw1MaxS;
+        xs[r][k] = (r < rows && k < S) ? x[(size_t)(row0 + r) * S + k] : 0.f;
+    }
+    __syncthreads();
+    float acc[kDw1MaxS];
+#pragma unroll
+    for (int k = 0; k < kDw1MaxS; k++) acc[k] = 0.f;
+    if (h < H) {
+        const float sc = scale[h], sh = shift[h], mu = mean[h], k1 = coef.k1[h], cB = coef.cB[h], cC = coef.cC[h];
+#pragma unroll
+        for (int u = 0; u < kHalf; u++) {
+            const int r = rh * kHalf + u;
+            const float g = fmaf(zz[u], sc, sh) > 0.f ? gg[u] : 0.f;
+            const float dz = r < rows ? fmaf(k1, g, -cB) - cC * (zz[u] - mu) : 0.f;
+#pragma unroll
+            for (int k4 = 0; k4 < kDw1MaxS / 4; k4++) {
+                const float4 xv = *reinterpret_cast<const float4*>(&xs[r][4 * k4]);
+                acc[4 * k4] = fmaf(dz, xv.x, acc[4 * k4]);
+                acc[4 * k4 + 1] = fmaf(dz, xv.y, acc[4 * k4 + 1]);
+                acc[4 * k4 + 2] = fmaf(dz, xv.z, acc[4 * k4 + 2]);
+                acc[4 * k4 + 3] = fmaf(dz, xv.w, acc[4 * k4 + 3]);
+            }
+        }
+    }
+    if (rh == 1) {
+#pragma unroll
+        for (int k = 0; k < kDw1MaxS; k++) half_acc[hl][k] = acc[k];
+    }
+    __syncthreads();
+    if (rh == 0 && h < H) {
+        float* out = part + (size_t)blockIdx.x * H * S + (size_t)h * S;
+#pragma unroll
+        for (int k = 0; k < kDw1MaxS; k++)
+            if (k < S) out[k] = acc[k] + half_acc[hl][k];       // first half of the rows, then the second: fixed order
     }
 }
 
@@ -851,12 +922,12 @@ __device__ __forceinline__ float splitk_element(const ReduceArgs& r, int e, floa
         if (j >= 0 && j < sg.n) {
             float t = 0.f;
             int k = 0;
-            for (; k + 8 <= sg.nsplit; k += 8) {          // 8 partials in flight, added in split order
-                float x[8];
+            for (; k + 16 <= sg.nsplit; k += 16) {        // 16 partials in flight, added in split order
+                float x[16];
 #pragma unroll
-                for (int u = 0; u < 8; u++) x[u] = sg.part[(k + u) * sg.pstride + j];
+                for (int u = 0; u < 16; u++) x[u] = sg.part[(k + u) * sg.pstride + j];
 #pragma unroll
-                for (int u = 0; u < 8; u++) t += x[u];
+                for (int u = 0; u < 16; u++) t += x[u];
             }
             for (; k < sg.nsplit; k++) t += sg.part[k * sg.pstride + j];
             return t;
@@ -963,6 +1034,7 @@ struct rloa_naf_ws {
     float *dzh, *da, *y, *loss_part, *splitk, *sq_partial, *wh_pack;
     float *v_tmp;
     float *bn_part;              // [2 nets][R][2][H] chunk statistics / [R][3][H] backward partial sums
+    float *w1_part;              // [<= 64 chunks of 64 rows][H][S] partials of dW1 (bn_bwd_apply_dw1_kernel)
     float *bwd_coef;             // [3][H] k1, cB, cC of the BatchNorm backward
     unsigned* tickets;           // [2 * H / 32] last-block-done counters (always return to 0) + [2] device barrier
     size_t splitk_floats;
@@ -1009,6 +1081,8 @@ extern "C" int rloa_naf_num_params(int32_t S, int32_t A, int32_t H) {
 }
 
 static int splitk_len(int B) { return 128; }
+// dW1 partials: one per 64 batch rows, kept for batches up to 4096 rows
+static int dw1_chunks(int B) { const int c = (B + kDw1Rows - 1) / kDw1Rows; return c < 64 ? c : 64; }
 static int bn_chunks(int B) { return (B + 8 * kBnRowsPerThread - 1) / (8 * kBnRowsPerThread); }
 constexpr int kBnSplitMinBatch = 128;    // below this the single-block-per-column kernels are already short
 static int splitk_count(int B) { return (B + splitk_len(B) - 1) / splitk_len(B); }
@@ -1032,7 +1106,8 @@ extern "C" int rloa_naf_ws_create(int32_t S, int32_t A, int32_t H, int32_t max_b
                    + 16 * (size_t)H  // scale/shift/mean/rstd [2][2]
                    + (size_t)max_batch * ws->NH + BH + 2 * (size_t)max_batch + ws->n_loss_parts + ws->splitk_floats +
                    kNormBlocks + (size_t)ws->NH * H +
-                   (size_t)bn_chunks(max_batch) * 4 * H + 3 * (size_t)H + 2 * (size_t)(H / 32) + 2;
+                   (size_t)bn_chunks(max_batch) * 4 * H + 3 * (size_t)H + 2 * (size_t)(H / 32) + 2 +
+                   (size_t)dw1_chunks(max_batch) * H * S;
     if (cudaMalloc(&ws->block, total * sizeof(float)) != cudaSuccess) {
         set_error("rloa_naf_ws_create: cudaMalloc of %zu bytes failed: %s", total * sizeof(float),
                   cudaGetErrorString(cudaGetLastError()));
@@ -1055,6 +1130,7 @@ extern "C" int rloa_naf_ws_create(int32_t S, int32_t A, int32_t H, int32_t max_b
     ws->wh_pack = p; p += (size_t)ws->NH * H;
     ws->bn_part = p; p += (size_t)bn_chunks(max_batch) * 4 * H;
     ws->bwd_coef = p; p += 3 * (size_t)H;
+    ws->w1_part = p; p += (size_t)dw1_chunks(max_batch) * H * S;
     ws->tickets = reinterpret_cast<unsigned*>(p); p += 2 * (size_t)(H / 32) + 2;     // + arrival count, generation
     cudaMemset(ws->tickets, 0, (2 * (size_t)(H / 32) + 2) * sizeof(unsigned));
     const int hb = (ws->NH * (H + 1) + ((ws->NH + 31) & ~31) + kHeadWarps * H + H) * (int)sizeof(float);
@@ -1321,6 +1397,14 @@ static int learn_grads_impl(rloa_naf_ws* ws, const rloa_naf_params* mn, const rl
     gb.a[0] = GemmArgs{ws->dzh, NH, ws->z2[0], H, part_wh, H, nullptr, ws->scale[0][1], ws->shift[0][1], NH, H, B, klen};
     launch_gemm<kTN, true>(gb, 1, dim3((H + BN - 1) / BN, (NH + BM - 1) / BM, nsplit), ws->side[0]);
     RLOA_LAUNCHED();
+    {   // the head-weight partials are summed on the side stream too (fixed split order), off the critical path
+        ReduceArgs rh{};
+        rh.s[0] = ReduceSeg{part_wh, grad + fl.wmu, A * H, nsplit, (size_t)NH * H, fl.wmu};
+        rh.s[1] = ReduceSeg{part_wh + (size_t)A * H, grad + fl.wv, H, nsplit, (size_t)NH * H, fl.wv};
+        rh.s[2] = ReduceSeg{part_wh + (size_t)(A + 1) * H, grad + fl.wl, NL * H, nsplit, (size_t)NH * H, fl.wl};
+        splitk_reduce_kernel<<<dim3(16, 3), 256, 0, ws->side[0]>>>(rh);
+        RLOA_LAUNCHED();
+    }
     RLOA_CUDA(cudaEventRecord(ws->join_ev[0], ws->side[0]));
     if (!fused) {   // da2 [B][H] = dZh Wh
         gb.a[0] = GemmArgs{ws->dzh, NH, ws->wh_pack, H, ws->da, H, nullptr, nullptr, nullptr, B, H, NH, 0};
@@ -1336,32 +1420,57 @@ static int learn_grads_impl(rloa_naf_ws* ws, const rloa_naf_params* mn, const rl
     RLOA_CUDA(cudaStreamWaitEvent(ws->side[1], ws->fork_ev[1], 0));
     launch_gemm<kTN, true>(gb, 1, dim3((H + BN - 1) / BN, (H + BM - 1) / BM, nsplit), ws->side[1]);
     RLOA_LAUNCHED();
+    {
+        ReduceArgs r2{};
+        r2.s[0] = ReduceSeg{part_w2, grad + fl.w2, H * H, nsplit, (size_t)H * H, fl.w2};
+        splitk_reduce_kernel<<<dim3(64, 1), 256, 0, ws->side[1]>>>(r2);
+        RLOA_LAUNCHED();
+    }
     RLOA_CUDA(cudaEventRecord(ws->join_ev[1], ws->side[1]));
     // da1 [B][H] = dz2 W2 -> reuse z2[1] (the target's z2 is no longer needed) as the output buffer
     float* da1 = ws->z2[1];
-    gb.a[0] = GemmArgs{ws->da, H, mn->w2, H, da1, H, nullptr, nullptr, nullptr, B, H, H, 0};
-    launch_gemm<kNN, false>(gb, 1, dim3((H + BN - 1) / BN, (B + BM - 1) / BM, 1), st);
-    RLOA_LAUNCHED();
-    rc = bn_relu_backward(ws, da1, ws->z1[0], mn->bn1_w, 0, B, grad + fl.bn1w, grad + fl.bn1b, grad + fl.b1, st);
-    if (rc != RLOA_OK) return rc;
-    // dW1 [H][S] = dz1^T x
-    gb.a[0] = GemmArgs{da1, H, states, S, part_w1, S, nullptr, nullptr, nullptr, H, S, B, klen};
-    launch_gemm<kTN, false>(gb, 1, dim3((S + BN - 1) / BN, (H + BM - 1) / BM, nsplit), st);
-    RLOA_LAUNCHED();
+    if (ws->trunk_mode == 1) {          // tcgen05: bf16 operands, fp32 accumulate (the bound is stated in the tests)
+        rc = trunk_tc_input_grad(&ws->tc, ws->da, mn->w2, da1, B, H, st);
+        if (rc != RLOA_OK) return rc;
+    } else {
+        gb.a[0] = GemmArgs{ws->da, H, mn->w2, H, da1, H, nullptr, nullptr, nullptr, B, H, H, 0};
+        launch_gemm<kNN, false>(gb, 1, dim3((H + BN - 1) / BN, (B + BM - 1) / BM, 1), st);
+        RLOA_LAUNCHED();
+    }
+    int w1_split = nsplit;
+    if (B >= kBnSplitMinBatch && B <= 4096 && S <= kDw1MaxS) {
+        // layer-1 BatchNorm backward: column sums -> coefficients, then dz1 is formed on the fly inside the dW1
+        // contraction (it has no other consumer) and never written
+        BnBwdCoef coef{ws->bwd_coef, ws->bwd_coef + H, ws->bwd_coef + 2 * H};
+        bn_bwd_reduce_kernel<<<dim3(H / 32, bn_chunks(B)), 256, 0, st>>>(da1, ws->z1[0], mn->bn1_w, ws->scale[0][0],
+                                                                         ws->shift[0][0], ws->mean[0][0], ws->rstd[0][0], B, H,
+                                                                         ws->bn_part, ws->tickets, coef, grad + fl.bn1w,
+                                                                         grad + fl.bn1b, grad + fl.b1);
+        RLOA_LAUNCHED();
+        w1_split = (B + kDw1Rows - 1) / kDw1Rows;
+        part_w1 = ws->w1_part;
+        bn_bwd_apply_dw1_kernel<<<dim3(w1_split, (H + kDw1Cols - 1) / kDw1Cols), 256, 0, st>>>(da1, ws->z1[0], ws->scale[0][0], ws->shift[0][0], ws->mean[0][0],
+                                                         coef, states, B, H, S, part_w1);
+        RLOA_LAUNCHED();
+    } else {
+        rc = bn_relu_backward(ws, da1, ws->z1[0], mn->bn1_w, 0, B, grad + fl.bn1w, grad + fl.bn1b, grad + fl.b1, st);
+        if (rc != RLOA_OK) return rc;
+        // dW1 [H][S] = dz1^T x
+        gb.a[0] = GemmArgs{da1, H, states, S, part_w1, S, nullptr, nullptr, nullptr, H, S, B, klen};
+        launch_gemm<kTN, false>(gb, 1, dim3((S + BN - 1) / BN, (H + BM - 1) / BM, nsplit), st);
+        RLOA_LAUNCHED();
+    }
     // join the side branches, then the fixed-order reduction of the split-K partials into the flat gradient
     RLOA_CUDA(cudaStreamWaitEvent(st, ws->join_ev[0], 0));
     RLOA_CUDA(cudaStreamWaitEvent(st, ws->join_ev[1], 0));
+    // only the input-layer partials are left for the main stream (the others were summed on the side streams)
     ReduceArgs ra{};
-    ra.s[0] = ReduceSeg{part_w2, grad + fl.w2, H * H, nsplit, (size_t)H * H, fl.w2};
-    ra.s[1] = ReduceSeg{part_w1, grad + fl.w1, H * S, nsplit, (size_t)H * S, fl.w1};
-    ra.s[2] = ReduceSeg{part_wh, grad + fl.wmu, A * H, nsplit, (size_t)NH * H, fl.wmu};
-    ra.s[3] = ReduceSeg{part_wh + (size_t)A * H, grad + fl.wv, H, nsplit, (size_t)NH * H, fl.wv};
-    ra.s[4] = ReduceSeg{part_wh + (size_t)(A + 1) * H, grad + fl.wl, NL * H, nsplit, (size_t)NH * H, fl.wl};
+    ra.s[0] = ReduceSeg{part_w1, grad + fl.w1, H * S, w1_split, (size_t)H * S, fl.w1};
     if (defer != nullptr) {
         *defer = ra;
         return RLOA_OK;
     }
-    splitk_reduce_kernel<<<dim3(64, 5), 256, 0, st>>>(ra);
+    splitk_reduce_kernel<<<dim3(16, 1), 256, 0, st>>>(ra);
     RLOA_LAUNCHED();
     return RLOA_OK;
 }

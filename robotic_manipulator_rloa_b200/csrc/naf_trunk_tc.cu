@@ -64,6 +64,10 @@ __device__ __forceinline__ uint4 pack8(const float4 a, const float4 b, const flo
     return r;
 }
 
+// MODE 0 (forward):  C = bf16(relu(A * scale + shift)) @ bf16(W)^T + bias,  W given as [n][k]  (+ fused BN statistics)
+// MODE 1 (backward): C = bf16(A) @ bf16(W),                                 W given as [k][n]: the input gradient
+//                    da1 = dz2 W2 of reference naf_algorithm.py:208 (autograd of hidden_layer), no bias
+template <int MODE>
 __global__ void __launch_bounds__(kTcThreads) trunk_tc_layer2_kernel(const __grid_constant__ TcBatch batch, int B) {
     extern __shared__ uint8_t tc_smem_raw[];
     const TcNet& g = batch.n[blockIdx.z];
@@ -95,8 +99,8 @@ __global__ void __launch_bounds__(kTcThreads) trunk_tc_layer2_kernel(const __gri
     float sc[8], sh[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        sc[i] = g.scale[lane * 8 + i];
-        sh[i] = g.shift[lane * 8 + i];
+        sc[i] = MODE == 0 ? g.scale[lane * 8 + i] : 1.f;
+        sh[i] = MODE == 0 ? g.shift[lane * 8 + i] : 0.f;
     }
     // 8 rows per warp per batch, every load of a batch issued before the first conversion (memory-level
     // parallelism: the kernel is one L2 round trip per batch, not per row)
@@ -118,12 +122,12 @@ __global__ void __launch_bounds__(kTcThreads) trunk_tc_layer2_kernel(const __gri
         for (int b = 0; b < kBatch; b++) {
             const int r = r0 + b * kWarps;
             uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-            if (m0 + r < B) packed = pack8<true>(lo[b], hi[b], sc, sh);
+            if (m0 + r < B) packed = pack8<MODE == 0>(lo[b], hi[b], sc, sh);
             const uint32_t off = kb * kABlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4);
             *reinterpret_cast<uint4*>(sm_a + off) = packed;
         }
     }
-    {
+    if (MODE == 0) {
         float4 lo[kTcN / kWarps], hi[kTcN / kWarps];
 #pragma unroll
         for (int b = 0; b < kTcN / kWarps; b++) {
@@ -136,6 +140,28 @@ __global__ void __launch_bounds__(kTcThreads) trunk_tc_layer2_kernel(const __gri
             const int r = warp + b * kWarps;
             const uint32_t off = kb * kBBlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4);
             *reinterpret_cast<uint4*>(sm_b + off) = pack8<false>(lo[b], hi[b], nullptr, nullptr);
+        }
+    } else {
+        // W is [k][n]: the UMMA B operand wants (n, k) K-major, so the slice W[0..255][n0..n0+63] is transposed while
+        // it is staged — half a warp reads one k row (64 floats), each lane scatters its 4 n values as bf16
+        const int nq = (lane & 15) * 4;
+#pragma unroll 1
+        for (int k0 = warp * 2 + (lane >> 4); k0 < kTcK; k0 += 8 * 16) {
+            float4 w[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) w[u] = *reinterpret_cast<const float4*>(g.w2 + (size_t)(k0 + 16 * u) * kTcK + n0 + nq);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int k = k0 + 16 * u;
+                const float vals[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int n = nq + c;
+                    const uint32_t off = (k >> 6) * kBBlockBytes + (n >> 3) * 1024 + (n & 7) * 128 +
+                                         ((((k & 63) >> 3) ^ (n & 7)) << 4) + (k & 7) * 2;
+                    *reinterpret_cast<__nv_bfloat16*>(sm_b + off) = __float2bfloat16_rn(vals[c]);
+                }
+            }
         }
     }
     // generic-proxy writes -> visible to the async proxy (tensor core operand fetch)
@@ -202,12 +228,13 @@ __global__ void __launch_bounds__(kTcThreads) trunk_tc_layer2_kernel(const __gri
               "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const bool fuse = batch.bn[blockIdx.z].enabled != 0;
+        const bool fuse = MODE == 0 && batch.bn[blockIdx.z].enabled != 0;
         float* tile = reinterpret_cast<float*>(sm_a);          // [128][65] fp32: the operand tiles are dead after the MMAs
         const int trow = (warp & 3) * 32 + lane;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-            const float4 bias = *reinterpret_cast<const float4*>(g.b2 + n0 + half * 32 + j);
+            const float4 bias = MODE == 0 ? *reinterpret_cast<const float4*>(g.b2 + n0 + half * 32 + j)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 o;
             o.x = __uint_as_float(v[j]) + bias.x;
             o.y = __uint_as_float(v[j + 1]) + bias.y;
@@ -220,7 +247,7 @@ __global__ void __launch_bounds__(kTcThreads) trunk_tc_layer2_kernel(const __gri
             }
         }
     }
-    if (batch.bn[blockIdx.z].enabled) {
+    if (MODE == 0 && batch.bn[blockIdx.z].enabled) {
         // ---- BatchNorm statistics of this 128 x 64 tile: column mean and centred second moment over its valid rows,
         // then the last row tile of the column group merges all partials and finalises (bn_fuse.cuh) ----
         const BnFuse& f = batch.bn[blockIdx.z];
@@ -282,7 +309,8 @@ int trunk_tc_prepare(TrunkTC* t, int max_batch, int H) {
     RLOA_CUDA(cudaGetDevice(&dev));
     RLOA_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     RLOA_REQUIRE(major == 10, "tcgen05 trunk: needs an sm_100 device");
-    RLOA_CUDA(cudaFuncSetAttribute(trunk_tc_layer2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    RLOA_CUDA(cudaFuncSetAttribute(trunk_tc_layer2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    RLOA_CUDA(cudaFuncSetAttribute(trunk_tc_layer2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     t->max_batch = max_batch;
     t->ready = true;
     return RLOA_OK;
@@ -299,7 +327,19 @@ int trunk_tc_layer2(TrunkTC* t, int nets, const float* const* z1, const float* c
         if (bn != nullptr) tb.bn[n] = bn[n];
     }
     dim3 grid((B + kTcM - 1) / kTcM, kTcK / kTcN, nets);
-    trunk_tc_layer2_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(tb, B);
+    trunk_tc_layer2_kernel<0><<<grid, kTcThreads, kTcSmemBytes, st>>>(tb, B);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
+
+int trunk_tc_input_grad(TrunkTC* t, const float* dz, const float* w, float* da, int B, int H, cudaStream_t st) {
+    RLOA_REQUIRE(t->ready, "tcgen05 trunk: rloa_naf_ws_set_trunk(1) was not called");
+    RLOA_REQUIRE(H == kTcK, "tcgen05 trunk: hidden = 256");
+    TcBatch tb{};
+    tb.n[0] = TcNet{dz, nullptr, nullptr, w, nullptr, da};
+    dim3 grid((B + kTcM - 1) / kTcM, kTcK / kTcN, 1);
+    trunk_tc_layer2_kernel<1><<<grid, kTcThreads, kTcSmemBytes, st>>>(tb, B);
     RLOA_LAUNCHED();
     return RLOA_OK;
 }

@@ -24,6 +24,9 @@ int trunk_tc_layer2(TrunkTC* t, int nets, const float* const* z1, const float* c
                     const float* const* w2, const float* const* b2, float* const* z2, int B, int H, const BnFuse* bn,
                     cudaStream_t st);
 
+// input gradient of the hidden layer on the tensor core: da[B][H] = bf16(dz[B][H]) @ bf16(w[H][H]) (w = [out][in])
+int trunk_tc_input_grad(TrunkTC* t, const float* dz, const float* w, float* da, int B, int H, cudaStream_t st);
+
 // fused eval-mode policy (naf_policy_tc.cu): supported shapes, one-time setup, and NAFAgent.act for `batch` rows
 bool policy_tc_supported(int S, int A, int H);
 int policy_tc_prepare(TrunkTC* t);
