@@ -679,13 +679,33 @@ __global__ void __launch_bounds__(kHeadWarps * 32) naf_head_kernel(HeadArgs h) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (h.t_z2 != nullptr)
         for (int k = tid; k < H; k += blockDim.x) twv[k] = h.t_wv[k];
-    for (int idx = tid; idx < NH * H; idx += blockDim.x) {
-        const int o = idx / H, k = idx - o * H;
-        float w;
-        if (o < A) w = h.w_mu[o * H + k];
-        else if (o == A) w = h.w_v[k];
-        else w = h.w_l[(o - A - 1) * H + k];
-        Wh[o * HS + k] = w;
+    // head weights -> shared memory: the three tensors are copied as flat float4 streams, 8 loads in flight per thread
+    // (a per-element loop with the tensor select inside cost one dependent L2 round trip per iteration)
+    {
+        const int H4 = H >> 2;                       // H is a multiple of 32
+        auto stage = [&](const float* __restrict__ src, int rows, int first_row) {
+            const int n4 = rows * H4;
+            for (int i0 = tid; i0 < n4; i0 += 8 * blockDim.x) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = i0 + u * blockDim.x;
+                    v[u] = i < n4 ? reinterpret_cast<const float4*>(src)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = i0 + u * blockDim.x;
+                    if (i < n4) {
+                        const int o = i / H4, k = 4 * (i - o * H4);
+                        float* d = Wh + (first_row + o) * HS + k;
+                        d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+                    }
+                }
+            }
+        };
+        stage(h.w_mu, A, 0);
+        stage(h.w_v, 1, A);
+        stage(h.w_l, NL, A + 1);
     }
     for (int o = tid; o < NH; o += blockDim.x) bh[o] = o < A ? h.b_mu[o] : (o == A ? h.b_v[0] : h.b_l[o - A - 1]);
     __syncthreads();

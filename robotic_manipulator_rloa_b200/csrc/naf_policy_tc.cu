@@ -156,14 +156,15 @@ policy_act_tc_kernel(const uint8_t* __restrict__ image, const float* __restrict_
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const float4* wr = reinterpret_cast<const float4*>(w1 + (j0 + i) * kPolSP);
-                float acc = 0.f;
+                // packed FFMA2 (fma.rn.f32x2): two partial dot products per instruction, halves the FMA issue count
+                float2 acc2 = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int k4 = 0; k4 < kPolSP / 4; k4++) {
                     const float4 w = wr[k4];
-                    acc = fmaf(x[4 * k4], w.x, acc); acc = fmaf(x[4 * k4 + 1], w.y, acc);
-                    acc = fmaf(x[4 * k4 + 2], w.z, acc); acc = fmaf(x[4 * k4 + 3], w.w, acc);
+                    acc2 = __ffma2_rn(make_float2(x[4 * k4], x[4 * k4 + 1]), make_float2(w.x, w.y), acc2);
+                    acc2 = __ffma2_rn(make_float2(x[4 * k4 + 2], x[4 * k4 + 3]), make_float2(w.z, w.w), acc2);
                 }
-                a[i] = fmaxf(fmaf(acc, sc1[j0 + i], sh1[j0 + i]), 0.f);
+                a[i] = fmaxf(fmaf(acc2.x + acc2.y, sc1[j0 + i], sh1[j0 + i]), 0.f);
             }
             const int chunk = j0 >> 3;                   // 0..31 over K = 256
             *reinterpret_cast<uint4*>(sm_a + (chunk >> 3) * (128 * 128) + sw128_chunk_offset(r, chunk & 7)) = pack8_bf16(a);
