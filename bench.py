@@ -164,10 +164,13 @@ class CpuLoop:
             self.frame[k] = 0
 
 
+CPU_MIN_WARMUP = 3       # three NAF updates: the first torch-CPU backward / OpenMP team start-up are not steady state
+
+
 def run_cpu(steps: int, warmup: int, n_envs: int, batch: int, update_every: int):
     cores = os.cpu_count() or 1
     loop = CpuLoop(n_envs, batch, update_every, cores)
-    for _ in range(warmup):
+    for _ in range(max(warmup, CPU_MIN_WARMUP)):
         loop.step()
     loop.transitions = 0
     t0 = time.perf_counter()
@@ -181,10 +184,10 @@ def reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    n_cpu, every = 512, 8        # 512 envs per step, one B=1024 update per 8 steps = 1 update per 4096 env-steps
-    value, ms, cores = run_cpu(args.steps, args.warmup, n_cpu, args.batch, every)
-    sample = (f'{n_cpu} envs per step (1/8 of the 4096-env workload), one batch-{args.batch} NAF update every {every} '
-              f'steps (same update:data ratio), {args.steps} steps')
+    # one CPU step = the whole per-GPU workload of one GPU step: args.envs arms stepped + one batch-B NAF update
+    value, ms, cores = run_cpu(args.steps, args.warmup, args.envs, args.batch, 1)
+    sample = (f'the full per-GPU workload per step ({args.envs} envs stepped, one batch-{args.batch} NAF update), {args.steps} timed '
+              f'steps after {max(args.warmup, CPU_MIN_WARMUP)} warm-up steps')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
@@ -370,10 +373,11 @@ def ours(args):
         cpu_value, cpu_ms, cores = (None, None, os.cpu_count())
         cpu = None
         if world == 1 and not args.no_cpu:
-            cpu_value, cpu_ms, cores = run_cpu(48, 4, 512, args.batch, 8)
+            cpu_value, cpu_ms, cores = run_cpu(40, 3, args.envs, args.batch, 1)
             cpu = {'value': cpu_value, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
-                   'sample': '48 steps x 512 envs (1/8 of the workload per step), one batch-%d NAF update every 8 steps; '
-                             'fp64 C restatement of the Bullet step (OpenMP, all cores) + torch-CPU NAF' % args.batch}
+                   'sample': '40 steps of the full per-GPU workload (%d envs stepped + one batch-%d NAF update) after 3 warm-up '
+                             'steps; fp64 C restatement of the Bullet step (OpenMP, all cores) + torch-CPU NAF'
+                             % (args.envs, args.batch)}
         line = {
             'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
