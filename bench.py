@@ -201,6 +201,61 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+def naf_update_leg(agent, dev, batch):
+    """NAF updates/s (the second half of BASELINE.json's metric) on this GPU: NAFAgent.learn through librloa_b200
+    against the reference's learn() arithmetic run by torch eager on the SAME GPU (oracle/naf_restatement.py on CUDA —
+    the real incumbent for a user of the reference who owns a B200).  CUDA events, L2 not flushed, 50 updates each."""
+    import torch
+    from oracle.naf_restatement import NAFRef
+    g = torch.Generator().manual_seed(0)
+    s = torch.randn(batch, 21, generator=g).to(dev)
+    s2 = (s + 0.1 * torch.randn(batch, 21, generator=g).to(dev))
+    a = torch.clamp(torch.randn(batch, 6, generator=g) * 1.5, -1, 1).to(dev)
+    r = -torch.rand(batch, 1, generator=g).to(dev)
+    d = torch.zeros(batch, 1, device=dev)
+    out = {'batch': batch}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, n=50):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n * 1e3
+
+    rr, dd = r.reshape(-1).contiguous(), d.reshape(-1).contiguous()
+    out['ours_us_per_update'] = timed(lambda: agent._learn_device(s, a, rr, s2, dd))
+    g1 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g1, capture_error_mode='thread_local'):
+        agent._learn_device(s, a, rr, s2, dd)
+    out['ours_graph_us_per_update'] = timed(g1.replay)
+    main, target = NAFRef(21, 6, 256, seed=0).to(dev), NAFRef(21, 6, 256, seed=0).to(dev)
+    opt = torch.optim.Adam(main.parameters(), lr=1e-3)
+    al = a.long()
+    main.train(); target.train()
+
+    def ref_learn():             # naf_algorithm.py:180-226 without any host read (the reference's learn() has none either)
+        opt.zero_grad()
+        with torch.no_grad():
+            v_next = target.heads(s2)[3]
+        q = main.heads(s, al)[2]
+        torch.nn.functional.mse_loss(q, r + 0.99 * v_next).backward()
+        torch.nn.utils.clip_grad_norm_(main.parameters(), 1)
+        opt.step()
+        with torch.no_grad():
+            for pt, pm in zip(target.parameters(), main.parameters()):
+                pt.copy_(1e-3 * pm + (1.0 - 1e-3) * pt)
+
+    out['torch_eager_us_per_update'] = timed(ref_learn, n=20)
+    out['updates_per_s'] = 1e6 / out['ours_graph_us_per_update']
+    out['speedup_vs_torch_eager_same_gpu'] = out['torch_eager_us_per_update'] / out['ours_graph_us_per_update']
+    return out
+
+
 def workload_config(args, where):
     return {'workload': 'BASELINE.json configs[1]: KUKA IIWA kuka_with_gripper2 (stand-in asset), fixed target/obstacle, '
                         f'{args.envs} envs per GPU, {FRAMES}-step episodes, NAF batch {args.batch}, 1 update per '
@@ -372,7 +427,12 @@ def ours(args):
         tflops = FLOP_PER_ENV_STEP * args.envs / (sim_avg_ms * 1e-3) / 1e12
         cpu_value, cpu_ms, cores = (None, None, os.cpu_count())
         cpu = None
+        naf = None
         if world == 1 and not args.no_cpu:
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                naf = naf_update_leg(agent, dev, args.batch)
             cpu_value, cpu_ms, cores = run_cpu(40, 3, args.envs, args.batch, 1)
             cpu = {'value': cpu_value, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
                    'sample': '40 steps of the full per-GPU workload (%d envs stepped + one batch-%d NAF update) after 3 warm-up '
@@ -399,6 +459,7 @@ def ours(args):
             'phases_ms': dict(zip(('act', 'env_step', 'replay_append', 'sample_learn', 'bookkeeping_reset'),
                                   [round(sum(x) / len(x), 5) for x in phase_ms])),
             'iteration_ms_after_flush_then_warm': [round(sum(x) / max(len(x), 1), 5) for x in parity_ms],
+            'naf_update': naf,
             'gpu_launches': int(launches),
             'graphed': graphed, 'graph_error': loop.graph_error,
             'clocks': clocks,

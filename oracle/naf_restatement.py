@@ -50,7 +50,7 @@ class NAFRef(nn.Module):
         entries = torch.tanh(self.matrix_entries(x))              # :84
         V = self.value(x)                                         # :87
         B, A = states.shape[0], self.action_size
-        L = torch.zeros(B, A, A, dtype=states.dtype)
+        L = torch.zeros(B, A, A, dtype=states.dtype).to(states.device)   # :95 host allocation + copy, as the reference
         rows, cols = torch.tril_indices(A, A)                     # :98 row-major lower-triangular order
         L[:, rows, cols] = entries
         diag = torch.arange(A)
