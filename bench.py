@@ -383,6 +383,11 @@ def ours(args):
     phase_ms = [[] for _ in range(5)]
     parity_ms = [[], []]                   # whole iteration right after the L2 flush / the one after it
     loop.phase_events = phase_ev
+    loop.pipeline_sim = False              # the three kernels of the simulator step back to back, so that they can be timed
+    loop.phase_events = None
+    loop._body(True, True, 0)              # consumes the half-step the pipelined loop left prepared
+    loop._body(True, True, 1)
+    loop.phase_events = phase_ev
     graphed_phases = False
     if graphed:
         loop._graph = None
@@ -390,6 +395,7 @@ def ours(args):
     run_pairs(max(8, min(npairs, 50)), 0, (phase_ms, parity_ms), graphed_phases)
     barrier()
     loop.phase_events = None
+    loop.pipeline_sim = True
     loop._graph = None
     sim_ms = phase_ms[1]
 
@@ -446,16 +452,19 @@ def ours(args):
             'naf_updates_per_s': args.steps / (total_ms * 1e-3),
             'sim_substeps_per_s': world * args.envs * args.steps / (total_ms * 1e-3),
             'wall_ms_per_step_incl_flush': t_wall / args.steps * 1e3,
-            'roofline': {'kernel': 'sim_step_kernel', 'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
-                         'frac': gbs / hbm_peak, 'traffic': None, 'peak_source': which,
-                         'avg_launch_ms': sim_avg_ms, 'share_of_step': sim_avg_ms * args.steps / total_ms,
+            'roofline': {'kernel': 'rloa_sim_step = sim_dynamics_kernel + sim_minv_kernel + sim_solve_kernel', 'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                         'frac': gbs / hbm_peak, 'traffic': 8.07e6, 'traffic_source': 'ncu --set full at 4096 arms, dram read+write of '
+                         'the three kernels per launch (profiles/r1e_sim_kernels_4096_ncu_full.md)', 'peak_source': which,
+                         'avg_launch_ms': sim_avg_ms,
+                         'share_of_step': sim_avg_ms / max(sum(sum(x) / len(x) for x in phase_ms), 1e-9),
                          'note': 'the kernel is FP32-issue / latency bound, not HBM bound (SURVEY 8d): see fp32',
                          'fp32': {'achieved': tflops, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': tflops / fp32_peak,
                                   'flop_per_env_step': FLOP_PER_ENV_STEP, 'sm_mhz': sm_mhz}},
             'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n * (S + A) * 4,
                     'd2h_bytes_per_step': n * (A * 4 + S * 4 + 4 + 1), 'steps': e2e_steps},
-            'phases_note': 'second pass with event nodes inside the loop (each node costs ~4 us, so phases sum to more than ms_per_step)',
+            'phases_note': 'second pass over the same loop with event nodes inside it (each costs ~4 us) and WITHOUT the software pipelining of the '
+                           'simulator step, so its three kernels run back to back and can be timed: phases sum to more than ms_per_step',
             'phases_ms': dict(zip(('act', 'env_step', 'replay_append', 'sample_learn', 'bookkeeping_reset'),
                                   [round(sum(x) / len(x), 5) for x in phase_ms])),
             'iteration_ms_after_flush_then_warm': [round(sum(x) / max(len(x), 1), 5) for x in parity_ms],

@@ -137,6 +137,16 @@ typedef struct {
 int rloa_sim_step(rloa_sim* s, const rloa_step_config* cfg, const float* actions, const uint8_t* active,
                   float* obs, float* reward, uint8_t* done, uint8_t* valid, void* stream);
 
+/* Software pipelining of the step.  A stepSimulation has an action-independent half (forward kinematics,
+ * articulated-body factorisation, free accelerations, M^-1: two of the three kernels) that only needs the
+ * joint state the PREVIOUS step left behind.  rloa_sim_prepare runs that half for the next step on a stream
+ * owned by the simulator, forked from `stream` at the call and joined by the next rloa_sim_step (or by
+ * rloa_sim_join, e.g. before the end of a CUDA-graph capture), which then launches the solve only.  Same
+ * arithmetic, same results; anything that changes (q, qd) in between (set_state, reset, clear) drops the
+ * prepared half. */
+int rloa_sim_prepare(rloa_sim* s, void* stream);
+int rloa_sim_join(rloa_sim* s, void* stream);
+
 /* Lock-step asynchronous Environment.reset for the vectorised loop: arms the POSITION_CONTROL motors of
  * the masked envs (joints 0..n_init-1 -> init_targets) and schedules n_substeps (50) reset sub-steps,
  * executed one per rloa_sim_step launch, so envs that keep acting never wait for a resetting one

@@ -95,6 +95,8 @@ SIGNATURES = {
     'rloa_sim_set_motors': (C.c_int, [_VP, _fp, _fp, _fp, _fp, _VP]),
     'rloa_sim_clear': (C.c_int, [_VP, _VP]),
     'rloa_sim_step': (C.c_int, [_VP, C.POINTER(StepConfig), _fp, _fp, _fp, _fp, _fp, _fp, _VP]),
+    'rloa_sim_prepare': (C.c_int, [_VP, _VP]),
+    'rloa_sim_join': (C.c_int, [_VP, _VP]),
     'rloa_sim_begin_reset': (C.c_int, [_VP, _fp, _fp, _I, _I, _VP]),
     'rloa_sim_begin_reset_random': (C.c_int, [_VP, _fp, _fp, _fp, _I, _I, _U64, _fp, _VP]),
     'rloa_sim_reset': (C.c_int, [_VP, _fp, _fp, _I, _I, _fp, _VP]),

@@ -528,7 +528,23 @@ struct rloa_sim {
     float* block = nullptr;
     unsigned* ticket = nullptr;      // last-block-done counter of rloa_episode_update_reset (zero at rest)
     int device = 0;
+    // software pipelining of the step (rloa_sim_prepare): the action-independent half (dynamics + M^-1) of the NEXT
+    // step runs on this side stream while the caller's stream does something else
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+    bool prepared = false;           // F / qs / M^-1 hold the current (q, qd): rloa_sim_step launches the solve only
+    bool join_pending = false;       // the caller's stream has not yet waited for the side stream
 };
+
+// the caller's stream waits for an outstanding rloa_sim_prepare; with invalidate the prepared half is dropped
+static int sim_sync_prepared(rloa_sim* s, cudaStream_t st, bool invalidate) {
+    if (s->join_pending) {
+        RLOA_CUDA(cudaStreamWaitEvent(st, s->join_ev, 0));
+        s->join_pending = false;
+    }
+    if (invalidate) s->prepared = false;
+    return RLOA_OK;
+}
 
 static void mat3_mul(const double* A, const double* B, double* C) {
     for (int i = 0; i < 3; i++)
@@ -666,6 +682,9 @@ extern "C" int rloa_sim_create(const rloa_model* m, int32_t n_envs, rloa_sim** o
     s->a.iters = reinterpret_cast<int*>(s->a.obstacle + 3 * N);
     s->a.reset_left = s->a.iters + n_envs;
     if (cudaMalloc(&s->ticket, sizeof(unsigned)) == cudaSuccess) cudaMemset(s->ticket, 0, sizeof(unsigned));
+    cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s->join_ev, cudaEventDisableTiming);
     cudaFuncSetAttribute(sim_minv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxLinks * kFRec * 32 * (int)sizeof(float));
     cudaMemset(s->block, 0, floats * sizeof(float));
     sim_clear_kernel<<<(unsigned)((n + 255) / 256), 256>>>(s->a);
@@ -684,6 +703,9 @@ extern "C" void rloa_sim_destroy(rloa_sim* s) {
     if (s == nullptr) return;
     if (s->block) cudaFree(s->block);
     if (s->ticket) cudaFree(s->ticket);
+    if (s->side) cudaStreamDestroy(s->side);
+    if (s->fork_ev) cudaEventDestroy(s->fork_ev);
+    if (s->join_ev) cudaEventDestroy(s->join_ev);
     delete s;
 }
 
@@ -714,7 +736,8 @@ static int gather(const rloa_sim* s, const float* src, float* dst, void* stream)
 
 extern "C" int rloa_sim_set_state(rloa_sim* s, const float* q, const float* qd, void* stream) {
     RLOA_REQUIRE(s != nullptr, "rloa_sim_set_state: null sim");
-    int rc = RLOA_OK;
+    int rc = sim_sync_prepared(s, as_stream(stream), true);
+    if (rc != RLOA_OK) return rc;
     if (q && (rc = scatter(s, q, s->a.q, stream)) != RLOA_OK) return rc;
     if (qd && (rc = scatter(s, qd, s->a.qd, stream)) != RLOA_OK) return rc;
     return RLOA_OK;
@@ -741,6 +764,10 @@ extern "C" int rloa_sim_set_motors(rloa_sim* s, const float* kp, const float* tp
 
 extern "C" int rloa_sim_clear(rloa_sim* s, void* stream) {
     RLOA_REQUIRE(s != nullptr, "rloa_sim_clear: null sim");
+    {
+        const int rcp = sim_sync_prepared(s, as_stream(stream), true);
+        if (rcp != RLOA_OK) return rcp;
+    }
     const size_t n = (size_t)s->a.n_envs * s->a.nl;
     sim_clear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(s->a);
     RLOA_LAUNCHED();
@@ -796,8 +823,8 @@ static int launch_solve(const rloa_sim* s, const StepCfgDev& c, int mode, const 
 }
 
 // one stepSimulation for every env = three launches on the caller's stream
-static int launch_substep(const rloa_sim* s, const StepCfgDev& c, int mode, const float* actions, const uint8_t* active,
-                          float* obs, float* reward, uint8_t* done, uint8_t* valid, cudaStream_t st) {
+// the action-independent half of a stepSimulation: dynamics + M^-1 columns for the current (q, qd)
+static int launch_dynamics(const rloa_sim* s, cudaStream_t st) {
     const ModelDev& h = s->model->host;
     const unsigned blocks = (unsigned)((s->a.n_envs + kTpb - 1) / kTpb);
     if (h.nl <= 16) sim_dynamics_kernel<16><<<blocks, kTpb, 0, st>>>(h, s->a);
@@ -805,17 +832,51 @@ static int launch_substep(const rloa_sim* s, const StepCfgDev& c, int mode, cons
     RLOA_LAUNCHED();
     sim_minv_kernel<<<blocks, dim3(32, h.ndof), (size_t)h.nl * kFRec * 32 * sizeof(float), st>>>(h, s->a);
     RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
+// one stepSimulation for every env = three launches on the caller's stream
+static int launch_substep(const rloa_sim* s, const StepCfgDev& c, int mode, const float* actions, const uint8_t* active,
+                          float* obs, float* reward, uint8_t* done, uint8_t* valid, cudaStream_t st, bool skip_dynamics = false) {
+    const ModelDev& h = s->model->host;
+    if (!skip_dynamics) {
+        const int rc = launch_dynamics(s, st);
+        if (rc != RLOA_OK) return rc;
+    }
     if (h.nl <= 16) return launch_solve<16>(s, c, mode, actions, active, obs, reward, done, valid, st);
     return launch_solve<32>(s, c, mode, actions, active, obs, reward, done, valid, st);
+}
+
+extern "C" int rloa_sim_prepare(rloa_sim* s, void* stream) {
+    RLOA_REQUIRE(s != nullptr && s->side != nullptr, "rloa_sim_prepare: null sim");
+    cudaStream_t st = as_stream(stream);
+    int rc = sim_sync_prepared(s, st, true);
+    if (rc != RLOA_OK) return rc;
+    RLOA_CUDA(cudaEventRecord(s->fork_ev, st));
+    RLOA_CUDA(cudaStreamWaitEvent(s->side, s->fork_ev, 0));
+    rc = launch_dynamics(s, s->side);
+    if (rc != RLOA_OK) return rc;
+    RLOA_CUDA(cudaEventRecord(s->join_ev, s->side));
+    s->prepared = true;
+    s->join_pending = true;
+    return RLOA_OK;
+}
+
+extern "C" int rloa_sim_join(rloa_sim* s, void* stream) {
+    RLOA_REQUIRE(s != nullptr, "rloa_sim_join: null sim");
+    return sim_sync_prepared(s, as_stream(stream), false);
 }
 
 extern "C" int rloa_sim_step(rloa_sim* s, const rloa_step_config* cfg, const float* actions, const uint8_t* active,
                              float* obs, float* reward, uint8_t* done, uint8_t* valid, void* stream) {
     RLOA_REQUIRE(s && cfg && actions && obs && reward && done, "rloa_sim_step: null argument");
     StepCfgDev c;
-    const int rc = make_step_cfg(s, cfg, &c);
+    int rc = make_step_cfg(s, cfg, &c);
     if (rc != RLOA_OK) return rc;
-    return launch_substep(s, c, kModeStep, actions, active, obs, reward, done, valid, as_stream(stream));
+    const bool prepared = s->prepared;
+    rc = sim_sync_prepared(s, as_stream(stream), true);     // the step consumes (and ends) the prepared state
+    if (rc != RLOA_OK) return rc;
+    return launch_substep(s, c, kModeStep, actions, active, obs, reward, done, valid, as_stream(stream), prepared);
 }
 
 extern "C" int rloa_sim_begin_reset(rloa_sim* s, const uint8_t* mask, const float* init_targets, int32_t n_init,
@@ -845,7 +906,10 @@ extern "C" int rloa_sim_begin_reset_random(rloa_sim* s, const uint8_t* mask, con
 
 extern "C" int rloa_sim_reset(rloa_sim* s, const uint8_t* mask, const float* init_targets, int32_t n_init,
                               int32_t n_substeps, float* obs, void* stream) {
-    const int rc = rloa_sim_begin_reset(s, mask, init_targets, n_init, n_substeps, stream);
+    RLOA_REQUIRE(s != nullptr, "rloa_sim_reset: null sim");
+    int rc = sim_sync_prepared(s, as_stream(stream), true);
+    if (rc != RLOA_OK) return rc;
+    rc = rloa_sim_begin_reset(s, mask, init_targets, n_init, n_substeps, stream);
     if (rc != RLOA_OK) return rc;
     StepCfgDev c;
     std::memset(&c, 0, sizeof(c));

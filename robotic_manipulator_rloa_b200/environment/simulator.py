@@ -121,6 +121,14 @@ class BatchedSimulator:
                 'rloa_sim_step')
         return obs, reward, done
 
+    def prepare(self) -> None:
+        """Start the action-independent half of the NEXT step (dynamics + M^-1) on the simulator's side stream."""
+        N.check(self.lib.rloa_sim_prepare(self._h_sim, self._stream()), 'rloa_sim_prepare')
+
+    def join(self) -> None:
+        """Make the current stream wait for an outstanding prepare() (no-op when there is none)."""
+        N.check(self.lib.rloa_sim_join(self._h_sim, self._stream()), 'rloa_sim_join')
+
     def begin_reset(self, init_targets: torch.Tensor, mask: Optional[torch.Tensor] = None,
                     substeps: int = RESET_SUBSTEPS) -> None:
         """Schedule a lock-step asynchronous reset of the masked envs (one sub-step per step() call)."""

@@ -377,6 +377,7 @@ class VectorLoop:
         self._graph_learn = False
         self.graph_kernels = 0
         self.graph_error: Optional[str] = None
+        self.pipeline_sim = True        # rloa_sim_prepare: the next step's dynamics run beside this step's learn
         self._host = None               # pinned host buffers bound by bind_host_buffers
         self._host_graphs = None
 
@@ -401,6 +402,8 @@ class VectorLoop:
         a.act_batch(self.state, out=self.actions, tick=self.tick)
         self._mark(parity, 1)
         env.sim.step(self.actions, out=(self.next_state, self.reward, self.done), valid=self.valid)
+        if self.pipeline_sim:     # dynamics + M^-1 of the NEXT step overlap the replay / learn phase of this one
+            env.sim.prepare()
         self._mark(parity, 2)
         a.memory.add_batch(self.state, self.actions, self.reward, self.next_state, self.done,
                            valid=self.valid if auto_reset else None)
@@ -420,6 +423,8 @@ class VectorLoop:
                     'rloa_episode_update_reset')
         else:
             N.check(self.lib.rloa_episode_update(self.n, self.frames, *common, a._stream()), 'rloa_episode_update')
+        if self.pipeline_sim:
+            env.sim.join()
         self._mark(parity, 5)
         self.state, self.next_state = self.next_state, self.state
 
@@ -489,6 +494,8 @@ class VectorLoop:
         a, env = self.agent, self.env
         self.actions.copy_(h_action, non_blocking=True)                   # H2D: actions into Environment.step
         env.sim.step(self.actions, out=(self.next_state, self.reward, self.done), valid=self.valid)
+        if self.pipeline_sim:
+            env.sim.prepare()
         h_state.copy_(self.next_state, non_blocking=True)                 # D2H: (state, reward, done)
         h_reward.copy_(self.reward, non_blocking=True)
         h_done.copy_(self.done, non_blocking=True)
@@ -503,6 +510,8 @@ class VectorLoop:
             self.log_count.data_ptr(), self.transitions.data_ptr(), self.tick.data_ptr(), env._d_pos.data_ptr(),
             env._d_var.data_ptr(), env._n_init(), 50, (env.seed + 0x5EED) & 0xFFFFFFFFFFFFFFFF, a._stream()),
             'rloa_episode_update_reset')
+        if self.pipeline_sim:
+            env.sim.join()
 
     def step_host(self, use_graph: bool = True) -> None:
         """One iteration through the bound host buffers: [H2D states, act, D2H actions] sync
