@@ -379,6 +379,7 @@ class VectorLoop:
         self.graph_error: Optional[str] = None
         self.pipeline_sim = True        # rloa_sim_prepare: the next step's dynamics run beside this step's learn
         self._host = None               # pinned host buffers bound by bind_host_buffers
+        self._copy_stream = None
         self._host_graphs = None
 
     def reset_all(self, verbose: bool = False) -> None:
@@ -496,9 +497,15 @@ class VectorLoop:
         env.sim.step(self.actions, out=(self.next_state, self.reward, self.done), valid=self.valid)
         if self.pipeline_sim:
             env.sim.prepare()
-        h_state.copy_(self.next_state, non_blocking=True)                 # D2H: (state, reward, done)
-        h_reward.copy_(self.reward, non_blocking=True)
-        h_done.copy_(self.done, non_blocking=True)
+        # D2H of (state, reward, done) on a copy stream: it overlaps the store / learn phase and is joined at the end
+        cur = torch.cuda.current_stream(a.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(a.device)
+        self._copy_stream.wait_stream(cur)
+        with torch.cuda.stream(self._copy_stream):
+            h_state.copy_(self.next_state, non_blocking=True)
+            h_reward.copy_(self.reward, non_blocking=True)
+            h_done.copy_(self.done, non_blocking=True)
         a.memory.add_batch(self.state, self.actions, self.reward, self.next_state, self.done, valid=self.valid)
         if learn_now:
             for u in range(a.num_updates):
@@ -512,6 +519,7 @@ class VectorLoop:
             'rloa_episode_update_reset')
         if self.pipeline_sim:
             env.sim.join()
+        cur.wait_stream(self._copy_stream)
 
     def step_host(self, use_graph: bool = True) -> None:
         """One iteration through the bound host buffers: [H2D states, act, D2H actions] sync
