@@ -307,7 +307,13 @@ int rloa_xchg_status(const rloa_xchg* x);
 void rloa_xchg_destroy(rloa_xchg* x);
 int rloa_naf_learn_apply_xchg(rloa_naf_ws* ws, const rloa_naf_params* main_net, const rloa_naf_params* target_net,
                               const rloa_adam_state* adam, const rloa_naf_hyper* hp, rloa_xchg* xchg,
-                              const float* grad, float* grad_norm, void* stream);
+                              float* grad, float* grad_norm, void* stream);
+/* rloa_naf_learn_grads + rloa_naf_learn_apply_xchg in one call: the last split-K sum of the backward pass is
+ * folded into the publish kernel (one launch less on every rank's critical path); same results. */
+int rloa_naf_learn_step_xchg(rloa_naf_ws* ws, const rloa_naf_params* main_net, const rloa_naf_params* target_net,
+                             const rloa_adam_state* adam, rloa_xchg* xchg, const float* states, const float* actions,
+                             const float* rewards, const float* next_states, const float* dones, int32_t batch,
+                             const rloa_naf_hyper* hp, float* grad, float* loss, float* grad_norm, void* stream);
 
 /* NAFAgent.soft_update alone (naf_algorithm.py:217-226) */
 int rloa_naf_soft_update(const rloa_naf_params* main_net, const rloa_naf_params* target_net, float tau,

@@ -125,6 +125,8 @@ SIGNATURES = {
     'rloa_xchg_destroy': (None, [_VP]),
     'rloa_naf_learn_apply_xchg': (C.c_int, [_VP, C.POINTER(NafParams), C.POINTER(NafParams), C.POINTER(AdamState),
                                             C.POINTER(NafHyper), _VP, _fp, _fp, _VP]),
+    'rloa_naf_learn_step_xchg': (C.c_int, [_VP, C.POINTER(NafParams), C.POINTER(NafParams), C.POINTER(AdamState), _VP, _fp, _fp,
+                                           _fp, _fp, _fp, _I, C.POINTER(NafHyper), _fp, _fp, _fp, _VP]),
     'rloa_naf_soft_update': (C.c_int, [C.POINTER(NafParams), C.POINTER(NafParams), _F, _VP]),
     'rloa_replay_append': (C.c_int, [C.POINTER(Replay), _I, _fp, _fp, _fp, _fp, _fp, _fp, _VP]),
     'rloa_replay_sample': (C.c_int, [C.POINTER(Replay), _I, _U64, _U64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _VP]),

@@ -81,15 +81,32 @@ __device__ __forceinline__ bool wait_peers(const unsigned long long* local_flags
 }
 
 __global__ void __launch_bounds__(256)
-xchg_publish_kernel(XchgPeers P, const float* __restrict__ local_grad, float* __restrict__ my_grad, int n,
+xchg_publish_kernel(XchgPeers P, ReduceArgs r, float* __restrict__ local_grad, float* __restrict__ my_grad, int n,
                     int64_t* __restrict__ step_ptr, unsigned* __restrict__ ticket,
                     int* __restrict__ status) {
     const unsigned long long t = (unsigned long long)(*step_ptr) + 1ull;      // this update's number
     wait_peers(P.done[P.rank], P.world, P.rank, t - 1ull, status);
-    const int n4 = n >> 2;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < n4; i += gridDim.x * 256)
-        reinterpret_cast<float4*>(my_grad)[i] = reinterpret_cast<const float4*>(local_grad)[i];
-    for (int i = 4 * n4 + blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) my_grad[i] = local_grad[i];
+    // copy the local gradient into the exchange block; segments whose split-K partials were left unsummed by
+    // rloa_naf_learn_step_xchg are summed here (fixed order) and written back to the local gradient as well
+    const bool deferred = r.s[0].n > 0;
+    const int n4 = ((reinterpret_cast<uintptr_t>(local_grad) & 15u) == 0) ? (n >> 2) : 0;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n4; i += gridDim.x * 256) {
+        float4 g = reinterpret_cast<const float4*>(local_grad)[i];
+        if (deferred) {
+            g.x = splitk_element(r, 4 * i, g.x); g.y = splitk_element(r, 4 * i + 1, g.y);
+            g.z = splitk_element(r, 4 * i + 2, g.z); g.w = splitk_element(r, 4 * i + 3, g.w);
+            reinterpret_cast<float4*>(local_grad)[i] = g;
+        }
+        reinterpret_cast<float4*>(my_grad)[i] = g;
+    }
+    for (int i = 4 * n4 + blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        float g = local_grad[i];
+        if (deferred) {
+            g = splitk_element(r, i, g);
+            local_grad[i] = g;
+        }
+        my_grad[i] = g;
+    }
     // one system-scope fence per block, after the CTA barrier: fences are cumulative, so the block's stores (ordered
     // before thread 0 by bar.sync) are visible system-wide before the ticket / the ready flag (20k per-thread
     // fence.sc.sys would cost more than the copy itself)
@@ -279,12 +296,13 @@ extern "C" void rloa_xchg_destroy(rloa_xchg* x) {
 
 // used by rloa_naf_learn_apply_xchg (naf.cu): publish, then exchange + clip + Adam + soft update in one kernel
 namespace rloa {
-int xchg_exchange_adam(rloa_xchg* x, const float* local_grad, const ParamTable& pt, float* m, float* v, int64_t* step_ptr,
-                       const rloa_naf_hyper& hp, float* grad_norm, cudaStream_t st) {
+int xchg_exchange_adam(rloa_xchg* x, float* local_grad, const ReduceArgs& deferred, const ParamTable& pt, float* m, float* v,
+                       int64_t* step_ptr, const rloa_naf_hyper& hp, float* grad_norm, cudaStream_t st) {
     RLOA_REQUIRE(x != nullptr && x->connected, "gradient exchange: rloa_xchg_connect was not called");
     const int n = pt.offset[14];
     RLOA_REQUIRE(n == x->n, "gradient exchange: gradient length does not match the exchange buffer");
-    xchg_publish_kernel<<<kXchgBlocks, 256, 0, st>>>(x->peers, local_grad, x->block, n, step_ptr, x->tickets, x->status);
+    xchg_publish_kernel<<<kXchgBlocks, 256, 0, st>>>(x->peers, deferred, local_grad, x->block, n, step_ptr, x->tickets,
+                                                     x->status);
     RLOA_LAUNCHED();
     xchg_reduce_adam_kernel<<<kXchgBlocks, 256, 0, st>>>(x->peers, x->sum, pt, m, v, hp, x->sq_partial, step_ptr,
                                                          x->tickets + 1, grad_norm, x->status);

@@ -868,14 +868,6 @@ head_bias_grad_kernel(const float* __restrict__ dzh, int B, int NH, int A, float
     }
 }
 
-// sums the split-K partials of up to 3 weight gradients in a fixed order (deterministic)
-struct ReduceSeg {
-    const float* part; float* out; int n; int nsplit; size_t pstride;
-    int off;                    // offset of `out` in the flat gradient
-};
-struct ReduceArgs {
-    ReduceSeg s[5];
-};
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(ReduceArgs r) {
     const ReduceSeg& s = r.s[blockIdx.y];
     for (int i = blockIdx.x * 256 + threadIdx.x; i < s.n; i += gridDim.x * 256) {
@@ -934,28 +926,6 @@ adam_soft_update_kernel(ParamTable pt, const float* __restrict__ grad, const flo
 // split-K partials into the flat gradient, squared-norm partials, a device-wide barrier, then clip + Adam + soft
 // update of the same elements.  Element-to-thread mapping, summation order and arithmetic are those of
 // splitk_reduce_kernel + grad_sqsum_kernel + adam_soft_update_kernel, so the result is bit-identical to the three.
-__device__ __forceinline__ float splitk_element(const ReduceArgs& r, int e, float current) {
-#pragma unroll
-    for (int q = 0; q < 5; q++) {
-        const ReduceSeg& sg = r.s[q];
-        const int j = e - sg.off;
-        if (j >= 0 && j < sg.n) {
-            float t = 0.f;
-            int k = 0;
-            for (; k + 16 <= sg.nsplit; k += 16) {        // 16 partials in flight, added in split order
-                float x[16];
-#pragma unroll
-                for (int u = 0; u < 16; u++) x[u] = sg.part[(k + u) * sg.pstride + j];
-#pragma unroll
-                for (int u = 0; u < 16; u++) t += x[u];
-            }
-            for (; k < sg.nsplit; k++) t += sg.part[k * sg.pstride + j];
-            return t;
-        }
-    }
-    return current;
-}
-
 __global__ void __launch_bounds__(256)
 splitk_adam_kernel(ReduceArgs r, float* __restrict__ grad, ParamTable pt, float* __restrict__ m, float* __restrict__ v,
                    int64_t* __restrict__ step_ptr, rloa_naf_hyper hp, float* __restrict__ sq_partial,
@@ -1557,13 +1527,13 @@ extern "C" int rloa_naf_learn_step(rloa_naf_ws* ws, const rloa_naf_params* mn, c
 
 struct rloa_xchg;
 namespace rloa {
-int xchg_exchange_adam(rloa_xchg* x, const float* local_grad, const ParamTable& pt, float* m, float* v, int64_t* step_ptr,
-                       const rloa_naf_hyper& hp, float* grad_norm, cudaStream_t st);
+int xchg_exchange_adam(rloa_xchg* x, float* local_grad, const ReduceArgs& deferred, const ParamTable& pt, float* m, float* v,
+                       int64_t* step_ptr, const rloa_naf_hyper& hp, float* grad_norm, cudaStream_t st);
 }
 
 extern "C" int rloa_naf_learn_apply_xchg(rloa_naf_ws* ws, const rloa_naf_params* mn, const rloa_naf_params* tg,
                                          const rloa_adam_state* adam, const rloa_naf_hyper* hp, rloa_xchg* xchg,
-                                         const float* grad, float* grad_norm, void* stream) {
+                                         float* grad, float* grad_norm, void* stream) {
     RLOA_REQUIRE(ws && adam && hp && grad && xchg && adam->m && adam->v && adam->step, "rloa_naf_learn_apply_xchg: null argument");
     int rc = check_params(ws, mn, "rloa_naf_learn_apply_xchg(main)");
     if (rc != RLOA_OK) return rc;
@@ -1571,7 +1541,21 @@ extern "C" int rloa_naf_learn_apply_xchg(rloa_naf_ws* ws, const rloa_naf_params*
     if (rc != RLOA_OK) return rc;
     ParamTable pt;
     fill_param_table(mn, tg, &pt);
-    return xchg_exchange_adam(xchg, grad, pt, adam->m, adam->v, adam->step, *hp, grad_norm, as_stream(stream));
+    return xchg_exchange_adam(xchg, grad, ReduceArgs{}, pt, adam->m, adam->v, adam->step, *hp, grad_norm, as_stream(stream));
+}
+
+extern "C" int rloa_naf_learn_step_xchg(rloa_naf_ws* ws, const rloa_naf_params* mn, const rloa_naf_params* tg,
+                                        const rloa_adam_state* adam, rloa_xchg* xchg, const float* states,
+                                        const float* actions, const float* rewards, const float* next_states,
+                                        const float* dones, int32_t batch, const rloa_naf_hyper* hp, float* grad, float* loss,
+                                        float* grad_norm, void* stream) {
+    RLOA_REQUIRE(adam && xchg && adam->m && adam->v && adam->step, "rloa_naf_learn_step_xchg: null argument");
+    ReduceArgs ra{};
+    int rc = learn_grads_impl(ws, mn, tg, states, actions, rewards, next_states, dones, batch, hp, grad, loss, &ra, stream);
+    if (rc != RLOA_OK) return rc;
+    ParamTable pt;
+    fill_param_table(mn, tg, &pt);
+    return xchg_exchange_adam(xchg, grad, ra, pt, adam->m, adam->v, adam->step, *hp, grad_norm, as_stream(stream));
 }
 
 extern "C" int rloa_naf_soft_update(const rloa_naf_params* mn, const rloa_naf_params* tg, float tau, void* stream) {

@@ -56,4 +56,38 @@ __device__ __forceinline__ void adam_soft_update_element(const ParamTable& pt, i
     pt.target[t][j] = hp.tau * p + (1.f - hp.tau) * pt.target[t][j];
 }
 
+// sums the split-K partials of up to 3 weight gradients in a fixed order (deterministic)
+struct ReduceSeg {
+    const float* part; float* out; int n; int nsplit; size_t pstride;
+    int off;                    // offset of `out` in the flat gradient
+};
+struct ReduceArgs {
+    ReduceSeg s[5];
+};
+
+// element e of the flat gradient: the fixed-order sum of its split-K partials when e lies in a deferred segment,
+// `current` otherwise
+__device__ __forceinline__ float splitk_element(const ReduceArgs& r, int e, float current) {
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+        const ReduceSeg& sg = r.s[q];
+        const int j = e - sg.off;
+        if (j >= 0 && j < sg.n) {
+            float t = 0.f;
+            int k = 0;
+            for (; k + 16 <= sg.nsplit; k += 16) {        // 16 partials in flight, added in split order
+                float x[16];
+#pragma unroll
+                for (int u = 0; u < 16; u++) x[u] = sg.part[(k + u) * sg.pstride + j];
+#pragma unroll
+                for (int u = 0; u < 16; u++) t += x[u];
+            }
+            for (; k < sg.nsplit; k++) t += sg.part[k * sg.pstride + j];
+            return t;
+        }
+    }
+    return current;
+}
+
+
 }  // namespace rloa

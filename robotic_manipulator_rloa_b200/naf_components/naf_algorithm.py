@@ -253,6 +253,14 @@ class NAFAgent:
                     'rloa_naf_learn_step')
             self.last_loss, self.last_grad_norm = b['loss'], b['gnorm']
             return
+        if xchg is not None and self.fused_learn:
+            # N ranks: backward, then the gradient exchange over NVLink peer memory inside the optimiser kernels
+            N.check(ws.lib.rloa_naf_learn_step_xchg(ws.handle, C.byref(pm), C.byref(pt), C.byref(adam), xchg.handle,
+                                                    s.data_ptr(), a.data_ptr(), r.data_ptr(), s2.data_ptr(), d.data_ptr(), B,
+                                                    C.byref(hp), b['grad'].data_ptr(), b['loss'].data_ptr(),
+                                                    b['gnorm'].data_ptr(), st), 'rloa_naf_learn_step_xchg')
+            self.last_loss, self.last_grad_norm = b['loss'], b['gnorm']
+            return
         N.check(ws.lib.rloa_naf_learn_grads(ws.handle, C.byref(pm), C.byref(pt), s.data_ptr(), a.data_ptr(),
                                             r.data_ptr(), s2.data_ptr(), d.data_ptr(), B, C.byref(hp),
                                             b['grad'].data_ptr(), b['loss'].data_ptr(), st), 'rloa_naf_learn_grads')

@@ -153,3 +153,36 @@ def test_reset_and_trajectory_divergence(cfg):
     print('trajectory divergence max|dqd| at t=1,10,100,400:', ['%.2e' % x for x in worst_qd])
     assert worst_q[0] <= 3e-4
     assert worst_q[-1] <= 5e-2      # reported, loose: chaotic growth of fp32 / early-exit differences
+
+
+def test_prepared_step_is_bit_identical():
+    """rloa_sim_prepare (dynamics + M^-1 of the next step on the side stream) + rloa_sim_step (solve only) is the same
+    computation as the plain three-kernel step; a set_state in between drops the prepared half."""
+    cfg = KUKA
+    model, _ = make_oracle(cfg)
+    n = 1024
+    q, qd = random_states(model, n, seed=21, held=cfg['fixed'])
+    rng = np.random.default_rng(22)
+    acts = [torch.as_tensor(rng.uniform(-1, 1, (n, 6)), dtype=torch.float32, device='cuda') for _ in range(6)]
+    outs = []
+    for pipelined in (False, True):
+        sim = make_sim(model, cfg, n)
+        sim.set_state(q, qd)
+        traj = []
+        for k, a in enumerate(acts):
+            if pipelined and k == 3:                 # invalidation path: same state written back -> must recompute
+                qq, qqd = sim.get_state()
+                sim.prepare()
+                sim.set_state(qq, qqd)
+            obs, rew, done = sim.step(a)
+            if pipelined:
+                sim.prepare()
+            traj.append((obs.clone(), rew.clone(), done.clone()))
+        if pipelined:
+            sim.join()
+        qg, qdg = sim.get_state()
+        outs.append((traj, qg.clone(), qdg.clone()))
+        sim.close()
+    for (o0, r0, d0), (o1, r1, d1) in zip(outs[0][0], outs[1][0]):
+        assert torch.equal(o0, o1) and torch.equal(r0, r1) and torch.equal(d0, d1)
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
