@@ -182,3 +182,25 @@ def test_step_host_moves_every_step_through_pinned_buffers():
     assert torch.equal(outs[0][2], outs[1][2]) and outs[0][3] == outs[1][3]
     with pytest.raises(ValueError):
         loop.bind_host_buffers(torch.zeros(n, 21), ha, hr, hd)
+
+
+def test_config4_rollouts_with_per_env_targets():
+    """BASELINE configs[3] at test scale: test_trained_model on the demo KUKA weights with per-env randomised target /
+    obstacle positions, several waves of envs (n_episodes > n_envs), results in the reference's (completed, frame) form."""
+    from robotic_manipulator_rloa_b200 import ManipulatorFramework
+    n = 512
+    mf = ManipulatorFramework()
+    mf.initialize_environment(**KUKA, n_envs=n)
+    mf.initialize_naf_agent()
+    mf.load_pretrained_parameters_from_weights_file(os.path.join(
+        os.path.dirname(os.path.abspath(__file__)), '..', 'robotic_manipulator_rloa_b200', 'naf_components', 'demo_weights',
+        'weights_kuka.p'))
+    g = torch.Generator().manual_seed(4321)
+    tgt = torch.tensor([0.4, 0.85, 0.71]) + 0.2 * (torch.rand(n, 3, generator=g) - 0.5)
+    obs = torch.tensor([0.45, 0.55, 0.55]) + 0.2 * (torch.rand(n, 3, generator=g) - 0.5)
+    mf.env.set_task_positions(tgt.to(DEV), obs.to(DEV))
+    state = mf.env.get_state()
+    assert torch.allclose(state[:, 15:18].cpu(), tgt, atol=1e-6) and torch.allclose(state[:, 18:21].cpu(), obs, atol=1e-6)
+    mf.test_trained_model(n + 100, 60)                        # two waves
+    res = mf.last_test_results
+    assert len(res) == n + 100 and all(isinstance(r[0], bool) and 0 <= r[1] <= 59 for r in res)
