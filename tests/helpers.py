@@ -11,6 +11,11 @@ PANDA = dict(file='franka_panda/panda.urdf', ee=11, involved=[0, 1, 2, 3, 4, 5, 
              target=[0.4, 0.3, 0.5], obstacle=[0.3, 0.0, 0.6], start=[0, 0, 0, -1.5, 0, 1.5, 0])
 
 
+# the reference's xarm6 demo (rl_framework.py:571-580): involved joints 1-6, joint 0 is the fixed world joint
+XARM6 = dict(file='xarm/xarm6_with_gripper.urdf', ee=12, involved=[1, 2, 3, 4, 5, 6], fixed=[0, 7, 8, 9, 10, 11, 12, 13],
+             target=[0.3, 0.47, 0.61], obstacle=[0.25, 0.27, 0.5], start=[0., 1., 0., -2.3, 0., 0., 0.])
+
+
 def make_oracle(cfg):
     model = load_manipulator(cfg['file'])
     return model, BulletOracle(model, cfg['ee'], len(cfg['involved']))

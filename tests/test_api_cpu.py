@@ -95,6 +95,8 @@ def test_model_files():
     assert kuka.nl == 14 and len(kuka.joint_names) == 14
     panda = load_manipulator('franka_panda/panda.urdf')
     assert panda.nl == 12 and sorted(set(int(t) for t in panda.jtype)) == [0, 1, 2]   # fixed, revolute, prismatic
+    xarm = load_manipulator('xarm/xarm6_with_gripper.urdf')                       # the reference's second demo asset
+    assert xarm.nl == 14 and int(xarm.jtype[0]) == 0 and int(xarm.jtype[7]) == 0   # world joint and gripper mount fixed
     with pytest.raises(ModelError):
         load_manipulator('no/such/file.urdf')
     mf = ManipulatorFramework()

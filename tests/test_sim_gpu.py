@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import KUKA, PANDA, make_oracle, random_states, step_motors
+from helpers import KUKA, PANDA, XARM6, make_oracle, random_states, step_motors
 
 pytestmark = pytest.mark.gpu
 
@@ -21,7 +21,7 @@ def make_sim(model, cfg, n):
     return sim
 
 
-@pytest.mark.parametrize('cfg', [KUKA, PANDA], ids=['kuka', 'panda'])
+@pytest.mark.parametrize('cfg', [KUKA, PANDA, XARM6], ids=['kuka', 'panda', 'xarm6'])
 def test_fk_and_distances_match_oracle(cfg):
     model, orc = make_oracle(cfg)
     n = 512
@@ -42,8 +42,8 @@ def test_fk_and_distances_match_oracle(cfg):
 
 @pytest.mark.parametrize('cfg,vel,near,stress', [(KUKA, 2.0, 0.0, False), (KUKA, 0.3, 0.0, False),
                                                   (KUKA, 2.0, 0.25, False), (PANDA, 2.0, 0.0, False),
-                                                  (PANDA, 1.0, 0.25, False), (KUKA, 2.0, 0.1, True)],
-                         ids=['kuka-saturated', 'kuka-gentle', 'kuka-limits', 'panda', 'panda-limits', 'kuka-stress'])
+                                                  (PANDA, 1.0, 0.25, False), (KUKA, 2.0, 0.1, True), (XARM6, 2.0, 0.1, False)],
+                         ids=['kuka-saturated', 'kuka-gentle', 'kuka-limits', 'panda', 'panda-limits', 'kuka-stress', 'xarm6'])
 def test_single_step_matches_oracle(cfg, vel, near, stress):
     """4096 seeded (q, qd, action) per case.  Normal cases keep the POSITION_CONTROL-held joints near 0 as
     the reference does (velocities of a few rad/s): absolute tolerance.  The stress case puts the held

@@ -94,6 +94,41 @@ PANDA = [
      0.0, (0, 0, 0), (0, 0, 0), [('sphere', (0, 0, 0), (0, 0, 0), (0.01,))]),
 ]
 
+# UFACTORY xArm 6 + gripper, joint order of pybullet_data/xarm/xarm6_with_gripper.urdf as the reference's demo uses it
+# (rl_framework.py:571-580: endeffector 12, involved joints 1-6, fixed [0, 7..13]): joint 0 is the fixed world joint,
+# 1-6 the arm, 7 the fixed gripper mount, 8-13 the six revolute gripper joints.  Arm kinematics / masses from the
+# xArm 6 description (medium confidence), gripper low confidence.
+XARM6 = [
+    ('link_base', 'world', 'world_joint', 'fixed', (0, 0, 0), (0, 0, 0), (0, 0, 1), None, 0.0,
+     2.7, (0, 0, 0.07), (0.005, 0.005, 0.003), [('capsule', (0, 0, 0.07), (0, 0, 0), (0.06, 0.08))]),
+    ('link1', 'link_base', 'joint1', 'revolute', (0, 0, 0.267), (0, 0, 0), (0, 0, 1), (-6.28318, 6.28318), 1.0,
+     2.16, (0.0002, 0.0270, -0.0135), (0.0054, 0.0049, 0.0032), [('capsule', (0, 0, -0.06), (0, 0, 0), (0.055, 0.12))]),
+    ('link2', 'link1', 'joint2', 'revolute', (0, 0, 0), (-PI / 2, 0, 0), (0, 0, 1), (-2.059, 2.0944), 1.0,
+     1.71, (0.0367, -0.2209, 0.0335), (0.0271, 0.0041, 0.0263), [('capsule', (0.03, -0.14, 0.02), (PI / 2, 0, 0), (0.05, 0.26))]),
+    ('link3', 'link2', 'joint3', 'revolute', (0.0535, -0.2845, 0), (0, 0, 0), (0, 0, 1), (-3.927, 0.19198), 1.0,
+     1.384, (0.0680, 0.2278, 0.0108), (0.0064, 0.0016, 0.0067), [('capsule', (0.07, 0.12, 0), (PI / 2, 0, 0), (0.045, 0.16))]),
+    ('link4', 'link3', 'joint4', 'revolute', (0.0775, 0.3425, 0), (-PI / 2, 0, 0), (0, 0, 1), (-6.28318, 6.28318), 1.0,
+     1.115, (-0.0002, 0.0205, -0.0264), (0.0046, 0.0043, 0.0012), [('capsule', (0, 0, -0.10), (0, 0, 0), (0.04, 0.16))]),
+    ('link5', 'link4', 'joint5', 'revolute', (0, 0, 0), (PI / 2, 0, 0), (0, 0, 1), (-1.69297, 3.14159), 1.0,
+     1.275, (0.0646, 0.0290, 0.0064), (0.0014, 0.0023, 0.0029), [('capsule', (0.05, 0.04, 0), (0, PI / 2, 0), (0.04, 0.08))]),
+    ('link6', 'link5', 'joint6', 'revolute', (0.076, 0.097, 0), (-PI / 2, 0, 0), (0, 0, 1), (-6.28318, 6.28318), 1.0,
+     0.1096, (0, -0.0025, -0.0166), (5e-5, 5e-5, 8e-5), [('sphere', (0, 0, -0.01), (0, 0, 0), (0.04,))]),
+    ('xarm_gripper_base_link', 'link6', 'gripper_fix', 'fixed', (0, 0, 0), (0, 0, 0), (0, 0, 1), None, 0.0,
+     0.54, (-0.0003, 0.0002, 0.0538), (4.7e-4, 3.0e-4, 3.7e-4), [('box', (0, 0, 0.045), (0, 0, 0), (0.06, 0.09, 0.09))]),
+    ('left_outer_knuckle', 'xarm_gripper_base_link', 'drive_joint', 'revolute', (0, 0.035, 0.059098), (0, 0, 0), (1, 0, 0),
+     (0.0, 0.85), 0.0, 0.033, (0, 0.021, 0.016), (1.9e-5, 6.7e-6, 1.3e-5), [('capsule', (0, 0.02, 0.015), (0, 0, 0), (0.008, 0.03))]),
+    ('left_finger', 'left_outer_knuckle', 'left_finger_joint', 'revolute', (0, 0.035465, 0.042039), (0, 0, 0), (-1, 0, 0),
+     (0.0, 0.85), 0.0, 0.048, (0, -0.016, 0.014), (2.1e-5, 1.7e-5, 1.1e-5), [('capsule', (0, -0.015, 0.02), (0, 0, 0), (0.008, 0.04))]),
+    ('left_inner_knuckle', 'xarm_gripper_base_link', 'left_inner_knuckle_joint', 'revolute', (0, 0.02, 0.074098), (0, 0, 0),
+     (1, 0, 0), (0.0, 0.85), 0.0, 0.033, (0, 0.017, 0.019), (1.3e-5, 8.7e-6, 8.3e-6), [('capsule', (0, 0.017, 0.019), (0, 0, 0), (0.007, 0.03))]),
+    ('right_outer_knuckle', 'xarm_gripper_base_link', 'right_outer_knuckle_joint', 'revolute', (0, -0.035, 0.059098), (0, 0, 0),
+     (-1, 0, 0), (0.0, 0.85), 0.0, 0.033, (0, -0.021, 0.016), (1.9e-5, 6.7e-6, 1.3e-5), [('capsule', (0, -0.02, 0.015), (0, 0, 0), (0.008, 0.03))]),
+    ('right_finger', 'right_outer_knuckle', 'right_finger_joint', 'revolute', (0, -0.035465, 0.042039), (0, 0, 0), (1, 0, 0),
+     (0.0, 0.85), 0.0, 0.048, (0, 0.016, 0.014), (2.1e-5, 1.7e-5, 1.1e-5), [('capsule', (0, 0.015, 0.02), (0, 0, 0), (0.008, 0.04))]),
+    ('right_inner_knuckle', 'xarm_gripper_base_link', 'right_inner_knuckle_joint', 'revolute', (0, -0.02, 0.074098), (0, 0, 0),
+     (-1, 0, 0), (0.0, 0.85), 0.0, 0.033, (0, -0.017, 0.019), (1.3e-5, 8.7e-6, 8.3e-6), [('capsule', (0, -0.017, 0.019), (0, 0, 0), (0.007, 0.03))]),
+]
+
 NOTE = ('STAND-IN ASSET written by tools/make_standin_assets.py: pybullet_data is not available in this image. '
         'Kinematics/inertials recalled from pybullet_data (SURVEY.md Appendix C), primitive collision shapes '
         'instead of convex-hulled meshes. Replace with the real file when available.')
@@ -186,4 +221,5 @@ if __name__ == '__main__':
     write_urdf(os.path.join(DATA, 'kuka_iiwa', 'model_standin.urdf'), 'lbr_iiwa_with_gripper_standin',
                'lbr_iiwa_link_0', KUKA)
     write_urdf(os.path.join(DATA, 'franka_panda', 'panda.urdf'), 'panda_standin', 'panda_link0', PANDA)
+    write_urdf(os.path.join(DATA, 'xarm', 'xarm6_with_gripper.urdf'), 'xarm6_with_gripper_standin', 'world', XARM6)
     print('written under', DATA)
