@@ -33,7 +33,7 @@ constexpr int kMaxShapes = 32;
 constexpr int kMaxDof = 16;
 constexpr int kMaxSlots = 3;
 constexpr int kFRec = 16;                // factor record per link: s_a s_l h_a h_l r invD (F[link][k][env])
-constexpr int kLRec = 37;                // per-link local record of the dynamics kernel
+constexpr int kLRec = 28;                // per-link local record of the dynamics kernel (forward-sweep results + u)
 constexpr int kTpb = 32;                 // threads (= arms) per block of the thread-per-arm kernels
 
 // fp32 device copy of rloa_model_desc plus the tree tables the kernels need; passed BY VALUE as a
@@ -394,8 +394,6 @@ __device__ __forceinline__ void arm_dynamics(const ModelDev& M, const SimArrays&
             Li[24] = fmaf(R.m[3] * R.m[3], I.x, fmaf(R.m[4] * R.m[4], I.y, R.m[5] * R.m[5] * I.z));
             Li[25] = fmaf(R.m[3] * R.m[6], I.x, fmaf(R.m[4] * R.m[7], I.y, R.m[5] * R.m[8] * I.z));
             Li[26] = fmaf(R.m[6] * R.m[6], I.x, fmaf(R.m[7] * R.m[7], I.y, R.m[8] * R.m[8] * I.z));
-            Li[27] = mass;
-            Li[28] = -M.damping[i] * qd;       // explicit joint damping (PhysicsServerCommandProcessor)
             const int sv = M.fwsave[i];
             if (sv >= 0) {
                 float* sl = slot + sv * 27;
@@ -418,7 +416,8 @@ __device__ __forceinline__ void arm_dynamics(const ModelDev& M, const SimArrays&
             const V3 s_a = ld3(Li), s_l = ld3(Li + 3), r = ld3(Li + 6), c_a = ld3(Li + 9), c_l = ld3(Li + 12);
             V3 pA_a = ld3(Li + 15), pA_l = ld3(Li + 18);
             S3 A{Li[21], Li[22], Li[23], Li[24], Li[25], Li[26]};
-            const float mass = Li[27], tau = Li[28];
+            const float mass = M.mass[i];
+            const float tau = -M.damping[i] * qdv[i];       // explicit joint damping (PhysicsServerCommandProcessor)
             S3 C{mass, 0.f, 0.f, mass, 0.f, mass};
             M3 B;
 #pragma unroll
@@ -446,9 +445,7 @@ __device__ __forceinline__ void arm_dynamics(const ModelDev& M, const SimArrays&
             const float D = dot(s_a, h_a) + dot(s_l, h_l);
             const float invD = (M.jtype[i] != RLOA_JOINT_FIXED) ? 1.f / D : 0.f;
             const float u = tau - (dot(s_a, pA_a) + dot(s_l, pA_l)) - (dot(c_a, h_a) + dot(c_l, h_l));
-            st3(Li + 29, h_a); st3(Li + 32, h_l);
-            Li[35] = invD;
-            Li[36] = u;
+            Li[27] = u;         // h, 1/D, s and r are read back from the factor record F by the third sweep
             {
                 float* Fi = S.F + (size_t)i * kFRec * N + env;
                 Fi[0] = s_a.x; Fi[(size_t)N] = s_a.y; Fi[(size_t)2 * N] = s_a.z;
@@ -521,12 +518,17 @@ __device__ __forceinline__ void arm_dynamics(const ModelDev& M, const SimArrays&
                 p_a = ld3(slot + (src - 2) * 27);
                 p_l = ld3(slot + (src - 2) * 27 + 3);
             }
-            const V3 r = ld3(Li + 6);
+            const float* Fi = S.F + (size_t)i * kFRec * N + env;      // written by this thread in the second sweep
+            const V3 s_a = v3(Fi[0], Fi[(size_t)N], Fi[(size_t)2 * N]);
+            const V3 s_l = v3(Fi[(size_t)3 * N], Fi[(size_t)4 * N], Fi[(size_t)5 * N]);
+            const V3 h_a = v3(Fi[(size_t)6 * N], Fi[(size_t)7 * N], Fi[(size_t)8 * N]);
+            const V3 h_l = v3(Fi[(size_t)9 * N], Fi[(size_t)10 * N], Fi[(size_t)11 * N]);
+            const V3 r = v3(Fi[(size_t)12 * N], Fi[(size_t)13 * N], Fi[(size_t)14 * N]);
+            const float invD = Fi[(size_t)15 * N];
             const V3 x_a = p_a, x_l = p_l + cross(p_a, r);
-            const V3 h_a = ld3(Li + 29), h_l = ld3(Li + 32);
-            const float qdd = (Li[36] - (dot(h_a, x_a) + dot(h_l, x_l))) * Li[35];
-            a_a = fma3(qdd, ld3(Li), x_a + ld3(Li + 9));
-            a_l = fma3(qdd, ld3(Li + 3), x_l + ld3(Li + 12));
+            const float qdd = (Li[27] - (dot(h_a, x_a) + dot(h_l, x_l))) * invD;
+            a_a = fma3(qdd, s_a, x_a + ld3(Li + 9));
+            a_l = fma3(qdd, s_l, x_l + ld3(Li + 12));
             const int sv = M.fwsave[i];
             if (sv >= 0) {
                 st3(slot + sv * 27, a_a);
