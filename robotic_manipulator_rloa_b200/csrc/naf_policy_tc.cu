@@ -9,7 +9,7 @@
 //     0. one thread issues three 1-D TMA bulk copies (cp.async.bulk, mbarrier complete_tx): W2 image 128 KB,
 //        W1 + vectors 28 KB now, head image 16 KB later into the W1 region;
 //     1. layer 1 (K = S = 21: too thin for the tensor core, and the observation carries raw joint angles, so it
-//        stays fp32) on the CUDA cores while the W2 copy is in flight: thread = (row, half of the 256 columns),
+//        stays fp32) on the CUDA cores while the W2 copy is in flight: thread = (row, quarter of the 256 columns),
 //        W1 broadcast from shared memory; relu(bn1(.)) -> bf16 -> A operand tile, hand-swizzled;
 //     2. layer 2: 16 x tcgen05.mma 128x256x16 (bf16 -> fp32 TMEM, 256 columns), commit -> mbarrier;
 //     3. epilogue 2: tcgen05.ld, relu(bn2(.)) -> bf16 -> the same A tile (layer-2 operands are dead);
@@ -29,7 +29,7 @@ using namespace tc;
 constexpr int kPolH = 256;                     // hidden width the kernel is built for
 constexpr int kPolSP = 24;                     // padded state width (S <= 24: KUKA 21, Panda 23)
 constexpr int kPolNH = 32;                     // head rows in the image: [0,A) mu, [A,2A) diag L, rest zero
-constexpr int kPolThreads = 256;
+constexpr int kPolThreads = 512;               // 16 warps: thread = (tile row, quarter of the 256 hidden columns)
 constexpr uint32_t kPolW2Bytes = kPolH * kPolH * 2;            // 131072
 constexpr uint32_t kPolWhBytes = kPolNH * kPolH * 2;           // 16384
 constexpr uint32_t kPolVecFloats = 4 * kPolH + kPolNH;         // sc1 sh1 sc2 sh2 bh
@@ -112,7 +112,7 @@ policy_act_tc_kernel(const uint8_t* __restrict__ image, const float* __restrict_
                      float noise_scale, float* __restrict__ actions) {
     extern __shared__ uint8_t pol_smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int r = tid & 127, half = tid >> 7;            // tile row, which 128 of the 256 hidden columns
+    const int r = tid & 127, half = tid >> 7;            // tile row, which 64 of the 256 hidden columns (0..3)
     const int row = blockIdx.x * 128 + r;
 
     const uint32_t raw = smem_u32(pol_smem_raw);
@@ -150,8 +150,8 @@ policy_act_tc_kernel(const uint8_t* __restrict__ image, const float* __restrict_
         const float* w1 = reinterpret_cast<const float*>(sm_r);
         const float *sc1 = sm_vec, *sh1 = sm_vec + kPolH;
 #pragma unroll 1
-        for (int c8 = 0; c8 < 16; c8++) {                // 16 chunks of 8 columns
-            const int j0 = half * 128 + c8 * 8;
+        for (int c8 = 0; c8 < 8; c8++) {                 // 8 chunks of 8 columns
+            const int j0 = half * 64 + c8 * 8;
             float a[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) {
@@ -191,12 +191,13 @@ policy_act_tc_kernel(const uint8_t* __restrict__ image, const float* __restrict_
     mbar_wait(&bars[3], 0);
     fence_after_sync();
 
-    // ---- epilogue 2: relu(bn2(.)) -> bf16 -> the A tile again (TMEM lane = row; warps 4-7 take columns 128-255) ----
+    // ---- epilogue 2: relu(bn2(.)) -> bf16 -> the A tile again (TMEM lane = row = 32 (warp % 4) + lane; warp / 4 picks
+    // the 64-column quarter) ----
     {
         const float *sc2 = sm_vec + 2 * kPolH, *sh2 = sm_vec + 3 * kPolH;
 #pragma unroll 1
-        for (int q = 0; q < 4; q++) {
-            const int c0 = half * 128 + q * 32;
+        for (int q = 0; q < 2; q++) {
+            const int c0 = half * 64 + q * 32;
             uint32_t v[32];
             tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
 #pragma unroll
