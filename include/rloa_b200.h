@@ -28,8 +28,8 @@
 extern "C" {
 #endif
 
-#define RLOA_MAX_LINKS 32      /* links == PyBullet getNumJoints(); one warp lane per link */
-#define RLOA_MAX_SHAPES 32     /* collision primitives; one warp lane per primitive */
+#define RLOA_MAX_LINKS 32      /* links == PyBullet getNumJoints() */
+#define RLOA_MAX_SHAPES 32     /* collision primitives (sphere / capsule / box) */
 #define RLOA_MAX_DOF 16        /* movable joints (PGS rows = dof + active limit rows <= 32) */
 
 typedef enum {
@@ -93,7 +93,8 @@ int rloa_model_create(const rloa_model_desc* desc, rloa_model** out);
 void rloa_model_destroy(rloa_model* m);
 
 /* ------------------------------------------------------------------------------------------------
- * Batched simulator: n_envs independent arms, one warp per arm.
+ * Batched simulator: n_envs independent arms, one THREAD per arm (struct-of-arrays state, coalesced across the
+ * warp); one step = dynamics, M^-1 columns (warp = 32 arms x one dof) and solve kernels — DESIGN.md section 3.
  * Replaces the PyBullet world owned by Environment (environment.py:207-210) and
  * p.setJointMotorControl2 / p.stepSimulation / p.getJointState / p.getLinkState /
  * p.getClosestPoints on Environment.step / reset / get_state / get_reward / is_terminal_state
