@@ -454,7 +454,7 @@ def ours(args):
             'wall_ms_per_step_incl_flush': t_wall / args.steps * 1e3,
             'roofline': {'kernel': 'rloa_sim_step = sim_dynamics_kernel + sim_minv_kernel + sim_solve_kernel', 'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                          'frac': gbs / hbm_peak, 'traffic': 8.07e6, 'traffic_source': 'ncu --set full at 4096 arms, dram read+write of '
-                         'the three kernels per launch (profiles/r1e_sim_kernels_4096_ncu_full.md)', 'peak_source': which,
+                         'the three kernels per launch, caches flushed by ncu (profiles/r1m_sim4096_ncu_full.md)', 'peak_source': which,
                          'avg_launch_ms': sim_avg_ms,
                          'share_of_step': sim_avg_ms / max(sum(sum(x) / len(x) for x in phase_ms), 1e-9),
                          'note': 'the kernel is FP32-issue / latency bound, not HBM bound (SURVEY 8d): see fp32',
