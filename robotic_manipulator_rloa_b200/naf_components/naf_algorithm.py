@@ -280,7 +280,10 @@ class NAFAgent:
         created lazily — collectively — on the first learn()."""
         if self._xchg is None and (
                 (self.world_size > 1 and self.grad_exchange_mode == 'peer') or self.grad_exchange_mode == 'peer-always'):
-            self._xchg = rdist.GradExchange(self.n_params, self.device)
+            self._xchg = rdist.GradExchange.create(self.n_params, self.device)
+            if self._xchg is None:      # some rank cannot export / map the blocks: every rank falls back together
+                logger.warning('NVLink peer-memory gradient exchange unavailable, using the NCCL all-reduce')
+                self.grad_exchange_mode = 'nccl'
         return self._xchg
 
     def soft_update(self, main_nn: NAF, target_nn: NAF) -> None:

@@ -50,7 +50,9 @@ def allreduce_gradient(flat_grad: torch.Tensor) -> float:
 class GradExchange:
     """NVLink peer-memory gradient exchange (csrc/grad_exchange.cu): one exchange block per rank, exported with CUDA
     IPC, mapped by every peer; the optimiser's own kernels publish, sum (in rank order) and consume the gradient.
-    Construction is collective: every rank of the process group must create it at the same point."""
+    Construction is collective: every rank of the process group must create it at the same point.  `create`
+    returns None on EVERY rank when any rank cannot export or map the blocks (IPC disabled, no peer access), so the
+    callers fall back to the NCCL all-reduce together."""
 
     def __init__(self, n_params: int, device: torch.device):
         import ctypes as C
@@ -59,19 +61,46 @@ class GradExchange:
         self.device = torch.device(device)
         self.rank, self.world = world()
         self._h = C.c_void_p()
+        self.error = None
         with torch.cuda.device(self.device):
-            N.check(self.lib.rloa_xchg_create(int(n_params), C.byref(self._h)), 'rloa_xchg_create')
             mine = C.create_string_buffer(64)
-            N.check(self.lib.rloa_xchg_handle(self._h, mine), 'rloa_xchg_handle')
+            ok = True
+            try:
+                N.check(self.lib.rloa_xchg_create(int(n_params), C.byref(self._h)), 'rloa_xchg_create')
+                N.check(self.lib.rloa_xchg_handle(self._h, mine), 'rloa_xchg_handle')
+            except N.NativeLibraryError as err:
+                ok, self.error = False, str(err)
+            if not self._all_ok(ok):
+                self.close()
+                return
             handles = None
             if self.world > 1:
                 local = torch.tensor(list(mine.raw), dtype=torch.uint8, device=self.device)
                 gathered = [torch.empty_like(local) for _ in range(self.world)]
                 dist.all_gather(gathered, local)
                 handles = bytes(torch.cat(gathered).cpu().numpy().tobytes())
-            N.check(self.lib.rloa_xchg_connect(self._h, self.rank, self.world, handles), 'rloa_xchg_connect')
+            try:
+                N.check(self.lib.rloa_xchg_connect(self._h, self.rank, self.world, handles), 'rloa_xchg_connect')
+            except N.NativeLibraryError as err:
+                ok, self.error = False, str(err)
+            if not self._all_ok(ok):
+                self.close()
+                return
             if self.world > 1:
                 dist.barrier()
+
+    def _all_ok(self, ok: bool) -> bool:
+        """Logical AND of `ok` over the ranks (one tiny all-reduce), so that every rank takes the same branch."""
+        if self.world == 1:
+            return ok
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return bool(flag.item())
+
+    @classmethod
+    def create(cls, n_params: int, device: torch.device):
+        x = cls(n_params, device)
+        return x if x._h else None
 
     @property
     def handle(self):
@@ -84,7 +113,7 @@ class GradExchange:
     def close(self) -> None:
         if self._h:
             self.lib.rloa_xchg_destroy(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         try:
