@@ -29,7 +29,8 @@ extern "C" {
 #endif
 
 #define RLOA_MAX_LINKS 32      /* links == PyBullet getNumJoints() */
-#define RLOA_MAX_SHAPES 32     /* collision primitives (sphere / capsule / box) */
+#define RLOA_MAX_SHAPES 32     /* collision shapes (sphere / capsule / box / convex hull) */
+#define RLOA_MAX_HULL_VERTS 16384 /* vertices of all convex-hull shapes of a model together */
 #define RLOA_MAX_DOF 16        /* movable joints (PGS rows = dof + active limit rows <= 32) */
 
 typedef enum {
@@ -40,7 +41,7 @@ typedef enum {
 } rloa_status;
 
 enum { RLOA_JOINT_FIXED = 0, RLOA_JOINT_REVOLUTE = 1, RLOA_JOINT_PRISMATIC = 2 };
-enum { RLOA_SHAPE_SPHERE = 1, RLOA_SHAPE_CAPSULE = 2, RLOA_SHAPE_BOX = 3 };
+enum { RLOA_SHAPE_SPHERE = 1, RLOA_SHAPE_CAPSULE = 2, RLOA_SHAPE_BOX = 3, RLOA_SHAPE_HULL = 4 };
 
 const char* rloa_last_error(void);
 int rloa_version(void);
@@ -81,11 +82,20 @@ typedef struct {
     const int32_t* s_type;      /* [ns] RLOA_SHAPE_* */
     const double* s_R;          /* [ns][9] link COM frame <- shape frame */
     const double* s_p;          /* [ns][3] */
-    const double* s_dim;        /* [ns][3] sphere r,-,- | capsule r,half_len,- (local z) | box half extents */
+    const double* s_dim;        /* [ns][3] sphere r,-,- | capsule r,half_len,- (local z) | box half extents |
+                                   hull: collision margin,-,- (pybullet's importer: 0.001) */
     double obstacle_radius;     /* sphere_small.urdf x 2.5 -> 0.075 */
     double target_half[3];      /* cube_small.urdf -> 0.025 each */
     int32_t ee_link;            /* endeffector_index */
     int32_t n_obs_joints;       /* len(involved_joints); get_state reads joints 0..n-1 (environment.py:442-444) */
+    /* RLOA_SHAPE_HULL: mesh / cylinder collision geometry, which p.loadURDF / p.loadSDF keep as the convex hull of
+     * the vertices (environment.py:228-233).  Shape s owns verts[s_vert_first[s] .. + s_vert_count[s]), given in
+     * the shape frame; closest distances come from GJK over the vertex cloud (p.getClosestPoints,
+     * utils/collision_detector.py:47-52).  n_verts = 0: the three pointers are ignored. */
+    int32_t n_verts;
+    const int32_t* s_vert_first;  /* [ns] */
+    const int32_t* s_vert_count;  /* [ns] */
+    const double* verts;          /* [n_verts][3] */
 } rloa_model_desc;
 
 typedef struct rloa_model rloa_model;

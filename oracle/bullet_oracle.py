@@ -13,7 +13,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, '_build', 'liborc_bullet.so')
-MAXL, MAXS = 32, 64
+MAXL, MAXS, MAXV = 32, 64, 16384
 
 
 class OrcModel(C.Structure):
@@ -30,6 +30,7 @@ class OrcModel(C.Structure):
         ('s_R', (C.c_double * 9) * MAXS), ('s_p', (C.c_double * 3) * MAXS), ('s_dim', (C.c_double * 3) * MAXS),
         ('obstacle_radius', C.c_double), ('target_half', C.c_double * 3), ('ee_link', C.c_int),
         ('n_obs_joints', C.c_int),
+        ('s_v0', C.c_int * MAXS), ('s_vn', C.c_int * MAXS), ('nv', C.c_int), ('verts', (C.c_double * 3) * MAXV),
     ]
 
 
@@ -56,6 +57,7 @@ def lib():
         assert _lib.orc_sizeof_model() == C.sizeof(OrcModel), 'orc_model layout mismatch'
         assert _lib.orc_sizeof_motors() == C.sizeof(OrcMotors), 'orc_motors layout mismatch'
         _lib.orc_substep.restype = C.c_int
+        _lib.orc_gjk_hull_box.restype = C.c_double
     return _lib
 
 
@@ -65,6 +67,17 @@ def _dp(a):
 
 def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def gjk_hull_box(verts, R, p, box_centre, box_half):
+    """Distance between hull(verts) posed by (R, p) and an axis-aligned box (half = 0: a point); (distance, iterations)."""
+    verts = np.ascontiguousarray(verts, np.float64).reshape(-1, 3)
+    it = C.c_int(0)
+    d = lib().orc_gjk_hull_box(_dp(verts), C.c_int(verts.shape[0]), _dp(np.ascontiguousarray(R, np.float64)),
+                               _dp(np.ascontiguousarray(p, np.float64)),
+                               _dp(np.ascontiguousarray(box_centre, np.float64)),
+                               _dp(np.ascontiguousarray(box_half, np.float64)), C.byref(it))
+    return float(d), it.value
 
 
 class BulletOracle:
@@ -100,6 +113,13 @@ class BulletOracle:
                 m.s_R[s][k] = float(model.s_R[s][k])
             for k in range(3):
                 m.s_p[s][k] = float(model.s_p[s][k]); m.s_dim[s][k] = float(model.s_dim[s][k])
+        verts = np.asarray(getattr(model, 'verts', np.zeros((0, 3))), np.float64).reshape(-1, 3)
+        assert verts.shape[0] <= MAXV, 'too many hull vertices for the oracle'
+        m.nv = verts.shape[0]
+        if m.nv:
+            C.memmove(m.verts, np.ascontiguousarray(verts).ctypes.data, verts.nbytes)
+            for s in range(model.ns):
+                m.s_v0[s] = int(model.s_v0[s]); m.s_vn[s] = int(model.s_vn[s])
         m.obstacle_radius = obstacle_radius
         m.ee_link = ee_link
         m.n_obs_joints = n_obs_joints

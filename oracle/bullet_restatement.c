@@ -508,6 +508,151 @@ static double segment_box(const double* a, const double* b, const double* h) {
     return sqrt(best);
 }
 
+/* ---------- GJK distance between convex cores (btGjkPairDetector::getClosestPoints with
+ * btVoronoiSimplexSolver restated; no EPA: a consumer on the path only compares the distance with a
+ * threshold, so overlapping cores report 0 and the margins / radii make the result negative) ---------- */
+typedef struct {
+    int type;                    /* ORC_SHAPE_BOX or ORC_SHAPE_HULL */
+    const double* dim;           /* box half extents */
+    const double (*verts)[3];    /* hull vertices, shape frame */
+    int nv;
+    const double* R;             /* world <- shape */
+    const double* p;
+} orc_convex;
+
+static void support_shape(const orc_convex* A, const double* dir_w, double* out_w) {
+    double dl[3], loc[3], t[3];
+    m3tv(A->R, dir_w, dl);
+    if (A->type == ORC_SHAPE_BOX) {
+        for (int a = 0; a < 3; a++) loc[a] = dl[a] >= 0 ? A->dim[a] : -A->dim[a];
+    } else {
+        double best = -1e300;
+        int bi = 0;
+        for (int i = 0; i < A->nv; i++) {
+            double d = dot3(dl, A->verts[i]);
+            if (d > best) { best = d; bi = i; }
+        }
+        for (int a = 0; a < 3; a++) loc[a] = A->verts[bi][a];
+    }
+    m3v(A->R, loc, t);
+    for (int a = 0; a < 3; a++) out_w[a] = A->p[a] + t[a];
+}
+
+/* closest point of triangle (a, b, c) to the origin; mask = which of the three vertices support it
+ * (Voronoi regions, Ericson "Real-Time Collision Detection" 5.1.5 == btVoronoiSimplexSolver::closestPtPointTriangle) */
+static void tri_closest(const double* a, const double* b, const double* c, double* out, int* mask) {
+    double ab[3], ac[3];
+    for (int x = 0; x < 3; x++) { ab[x] = b[x] - a[x]; ac[x] = c[x] - a[x]; }
+    double d1 = -dot3(ab, a), d2 = -dot3(ac, a);
+    if (d1 <= 0 && d2 <= 0) { for (int x = 0; x < 3; x++) out[x] = a[x]; *mask = 1; return; }
+    double d3 = -dot3(ab, b), d4 = -dot3(ac, b);
+    if (d3 >= 0 && d4 <= d3) { for (int x = 0; x < 3; x++) out[x] = b[x]; *mask = 2; return; }
+    double vc = d1 * d4 - d3 * d2;
+    if (vc <= 0 && d1 >= 0 && d3 <= 0) {
+        double v = d1 / (d1 - d3);
+        for (int x = 0; x < 3; x++) out[x] = a[x] + v * ab[x];
+        *mask = 3; return;
+    }
+    double d5 = -dot3(ab, c), d6 = -dot3(ac, c);
+    if (d6 >= 0 && d5 <= d6) { for (int x = 0; x < 3; x++) out[x] = c[x]; *mask = 4; return; }
+    double vb = d5 * d2 - d1 * d6;
+    if (vb <= 0 && d2 >= 0 && d6 <= 0) {
+        double w = d2 / (d2 - d6);
+        for (int x = 0; x < 3; x++) out[x] = a[x] + w * ac[x];
+        *mask = 5; return;
+    }
+    double va = d3 * d6 - d5 * d4;
+    if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
+        double w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        for (int x = 0; x < 3; x++) out[x] = b[x] + w * (c[x] - b[x]);
+        *mask = 6; return;
+    }
+    double den = 1.0 / (va + vb + vc), v = vb * den, w = vc * den;
+    for (int x = 0; x < 3; x++) out[x] = a[x] + ab[x] * v + ac[x] * w;
+    *mask = 7;
+}
+
+/* closest point of the simplex P[0..n) to the origin; P is reduced to the supporting sub-simplex.
+ * Returns 1 when the origin lies inside a tetrahedron (the cores overlap). */
+static int simplex_closest(double P[4][3], int* n, double* v) {
+    if (*n == 1) { for (int x = 0; x < 3; x++) v[x] = P[0][x]; return 0; }
+    if (*n == 2) {
+        double ab[3];
+        for (int x = 0; x < 3; x++) ab[x] = P[1][x] - P[0][x];
+        double t = -dot3(P[0], ab), L2 = dot3(ab, ab);
+        if (t <= 0 || L2 <= 0) { for (int x = 0; x < 3; x++) v[x] = P[0][x]; *n = 1; return 0; }
+        if (t >= L2) { for (int x = 0; x < 3; x++) { v[x] = P[1][x]; P[0][x] = P[1][x]; } *n = 1; return 0; }
+        for (int x = 0; x < 3; x++) v[x] = P[0][x] + (t / L2) * ab[x];
+        return 0;
+    }
+    int mask = 0;
+    if (*n == 3) {
+        tri_closest(P[0], P[1], P[2], v, &mask);
+    } else {
+        /* tetrahedron: the closest point lies on a face whose plane separates the origin from the fourth vertex */
+        static const int face[4][4] = {{0, 1, 2, 3}, {0, 2, 3, 1}, {0, 3, 1, 2}, {1, 3, 2, 0}};
+        double best = 1e300;
+        int any = 0;
+        for (int f = 0; f < 4; f++) {
+            const double *a = P[face[f][0]], *b = P[face[f][1]], *c = P[face[f][2]], *d = P[face[f][3]];
+            double ab[3], ac[3], nrm[3], ad[3];
+            for (int x = 0; x < 3; x++) { ab[x] = b[x] - a[x]; ac[x] = c[x] - a[x]; ad[x] = d[x] - a[x]; }
+            cross3(ab, ac, nrm);
+            double sp = -dot3(a, nrm), sd = dot3(ad, nrm);      /* origin side, fourth-vertex side */
+            if (sp * sd < 0 || sd * sd <= 1e-30 * dot3(nrm, nrm) * dot3(ad, ad)) {   /* outside, or a flat tetrahedron */
+                double c3[3];
+                int m3;
+                tri_closest(a, b, c, c3, &m3);
+                double dd = dot3(c3, c3);
+                if (dd < best) {
+                    best = dd;
+                    any = 1;
+                    for (int x = 0; x < 3; x++) v[x] = c3[x];
+                    mask = 0;
+                    for (int k = 0; k < 3; k++) if ((m3 >> k) & 1) mask |= 1 << face[f][k];
+                }
+            }
+        }
+        if (!any) { v[0] = v[1] = v[2] = 0; return 1; }
+    }
+    int k = 0;
+    for (int i = 0; i < *n; i++)
+        if ((mask >> i) & 1) { if (k != i) for (int x = 0; x < 3; x++) P[k][x] = P[i][x]; k++; }
+    *n = k;
+    return 0;
+}
+
+static double gjk_distance(const orc_convex* A, const double* bc, const double* bh, int* iters_out) {
+    double P[4][3], v[3], w[3], sa[3], nd[3];
+    int n = 0, it;
+    for (int x = 0; x < 3; x++) v[x] = A->p[x] - bc[x];
+    if (dot3(v, v) < 1e-24) { v[0] = 1; v[1] = v[2] = 0; }
+    for (it = 0; it < 64; it++) {
+        for (int x = 0; x < 3; x++) nd[x] = -v[x];
+        support_shape(A, nd, sa);
+        for (int x = 0; x < 3; x++) w[x] = sa[x] - (bc[x] + (v[x] >= 0 ? bh[x] : -bh[x]));   /* support of A - B along -v */
+        if (it > 0) {
+            double vv = dot3(v, v);
+            if (vv - dot3(v, w) <= 1e-13 * vv) break;          /* no vertex of A - B is closer: v is the closest point */
+            int dup = 0;
+            for (int i = 0; i < n; i++)
+                if (P[i][0] == w[0] && P[i][1] == w[1] && P[i][2] == w[2]) dup = 1;
+            if (dup) break;
+        }
+        for (int x = 0; x < 3; x++) P[n][x] = w[x];
+        n++;
+        if (simplex_closest(P, &n, v) || dot3(v, v) < 1e-24) { if (iters_out) *iters_out = it + 1; return 0.0; }
+    }
+    if (iters_out) *iters_out = it;
+    return sqrt(dot3(v, v));
+}
+
+double orc_gjk_hull_box(const double* verts, int nv, const double* R, const double* p, const double* bc,
+                        const double* bh, int* iters_out) {
+    orc_convex A = {ORC_SHAPE_HULL, 0, (const double (*)[3])verts, nv, R, p};
+    return gjk_distance(&A, bc, bh, iters_out);
+}
+
 void orc_distances(const orc_model* m, const double* q, const double* obstacle, const double* target,
                    double* link_obst, double* ee_target, double* ee_pos) {
     double Rw[ORC_MAXL * 9], pw[ORC_MAXL * 3];
@@ -528,7 +673,12 @@ void orc_distances(const orc_model* m, const double* q, const double* obstacle, 
         else if (m->s_type[s] == ORC_SHAPE_CAPSULE) {
             double a0[3] = {0, 0, -m->s_dim[s][1]}, b0[3] = {0, 0, m->s_dim[s][1]};
             dist = point_segment(o_s, a0, b0) - m->s_dim[s][0];
-        } else dist = point_box_signed(o_s, m->s_dim[s]);
+        } else if (m->s_type[s] == ORC_SHAPE_BOX) dist = point_box_signed(o_s, m->s_dim[s]);
+        else { /* convex hull of a mesh: GJK between the hull and the sphere centre, minus the hull margin */
+            static const double zero3[3] = {0, 0, 0};
+            orc_convex A = {ORC_SHAPE_HULL, 0, m->verts + m->s_v0[s], m->s_vn[s], Rs, ps};
+            dist = gjk_distance(&A, obstacle, zero3, 0) - m->s_dim[s][0];
+        }
         dist -= m->obstacle_radius;
         if (dist < link_obst[l]) link_obst[l] = dist;
         if (l == m->ee_link) { /* vs axis-aligned target cube, in the cube frame */
@@ -543,8 +693,12 @@ void orc_distances(const orc_model* m, const double* q, const double* obstacle, 
                 }
                 double sd = segment_box(a1, b1, m->target_half);
                 dt_ = sd - m->s_dim[s][0];
-            } else { /* box ee shapes: bounding-sphere-free conservative stand-in is NOT used; unsupported */
-                dt_ = 10.0;
+            } else if (m->s_type[s] == ORC_SHAPE_BOX) { /* box vs cube: GJK on the two boxes */
+                orc_convex A = {ORC_SHAPE_BOX, m->s_dim[s], 0, 0, Rs, ps};
+                dt_ = gjk_distance(&A, target, m->target_half, 0);
+            } else {
+                orc_convex A = {ORC_SHAPE_HULL, 0, m->verts + m->s_v0[s], m->s_vn[s], Rs, ps};
+                dt_ = gjk_distance(&A, target, m->target_half, 0) - m->s_dim[s][0];
             }
             if (dt_ < ee) ee = dt_;
         }

@@ -18,15 +18,19 @@
  *   btMultiBodyJointMotor / btMultiBodyJointLimitConstraint rows       -> orc_substep()
  *   btMultiBodyConstraintSolver::solveSingleIteration (PGS)            -> orc_substep()
  *   btMultiBody::stepPositionsMultiDof                                 -> orc_substep()
+ * and, for getClosestPoints on mesh (convex hull) shapes and box end-effector shapes
+ * (src/BulletCollision/NarrowPhaseCollision):
+ *   btGjkPairDetector::getClosestPoints + btVoronoiSimplexSolver       -> orc_gjk_distance()
  */
 #ifndef ORC_BULLET_RESTATEMENT_H
 #define ORC_BULLET_RESTATEMENT_H
 
 #define ORC_MAXL 32   /* links (== pybullet getNumJoints) */
-#define ORC_MAXS 64   /* collision primitives */
+#define ORC_MAXS 64   /* collision shapes */
+#define ORC_MAXV 16384 /* convex-hull vertices, all hull shapes together */
 
 enum { ORC_FIXED = 0, ORC_REVOLUTE = 1, ORC_PRISMATIC = 2 };
-enum { ORC_SHAPE_SPHERE = 1, ORC_SHAPE_CAPSULE = 2, ORC_SHAPE_BOX = 3 };
+enum { ORC_SHAPE_SPHERE = 1, ORC_SHAPE_CAPSULE = 2, ORC_SHAPE_BOX = 3, ORC_SHAPE_HULL = 4 };
 
 typedef struct {
     int nl;
@@ -56,11 +60,17 @@ typedef struct {
     int s_type[ORC_MAXS];
     double s_R[ORC_MAXS][9];       /* link COM frame <- shape frame */
     double s_p[ORC_MAXS][3];
-    double s_dim[ORC_MAXS][3];     /* sphere: r,-,- ; capsule (local z): r, half_len,- ; box: half extents */
+    double s_dim[ORC_MAXS][3];     /* sphere: r,-,- ; capsule (local z): r, half_len,- ; box: half extents ;
+                                      hull: collision margin (pybullet's URDF importer sets 0.001),-,- */
     double obstacle_radius;
     double target_half[3];
     int ee_link;
     int n_obs_joints;              /* len(involved_joints): get_state reads joints 0..n-1 */
+    /* convex-hull shapes (mesh collision geometry: Bullet keeps the convex hull of the mesh vertices,
+     * SURVEY.md A.5): vertices in the shape frame, shape s owns verts[s_v0[s] .. s_v0[s] + s_vn[s]) */
+    int s_v0[ORC_MAXS], s_vn[ORC_MAXS];
+    int nv;
+    double verts[ORC_MAXV][3];
 } orc_model;
 
 /* per-joint motor settings (persist across steps, like btMultiBodyJointMotor) */
@@ -82,6 +92,10 @@ void orc_distances(const orc_model* m, const double* q, const double* obstacle, 
                    double* link_obst /*[nl]*/, double* ee_target /*[1]*/, double* ee_pos /*[3]*/);
 void orc_observe(const orc_model* m, const double* q, const double* qd, const double* obstacle,
                  const double* target, double* obs, double* reward, int* done);
+/* distance between the convex hull of nv points (pose world <- shape: R row-major, p) and an axis-aligned box
+ * (centre bc, half extents bh; bh = 0 -> a point); 0 when they overlap */
+double orc_gjk_hull_box(const double* verts /*[nv][3]*/, int nv, const double* R, const double* p,
+                        const double* bc, const double* bh, int* iters_out);
 /* batched helpers (OpenMP over envs); q, qd are [n][nl] */
 void orc_batch_step(const orc_model* m, const orc_motors* mot_template, const int* act_joint, int n_act,
                     int n, double* q, double* qd, const double* actions /*[n][n_act]*/, double max_force,

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(HERE, 'librloa_b200.so')
 MAX_LINKS = 32
 MAX_SHAPES = 32
 MAX_DOF = 16
+MAX_HULL_VERTS = 16384
 
 
 class NativeLibraryError(RuntimeError):
@@ -39,6 +40,7 @@ class ModelDesc(C.Structure):
         ('ns', C.c_int32), ('s_link', _ip), ('s_type', _ip), ('s_R', _dp), ('s_p', _dp), ('s_dim', _dp),
         ('obstacle_radius', C.c_double), ('target_half', C.c_double * 3), ('ee_link', C.c_int32),
         ('n_obs_joints', C.c_int32),
+        ('n_verts', C.c_int32), ('s_vert_first', _ip), ('s_vert_count', _ip), ('verts', _dp),
     ]
 
 
@@ -213,4 +215,9 @@ def make_model_desc(model, ee_link: int, n_obs_joints: int, obstacle_radius: flo
     d.obstacle_radius = obstacle_radius
     d.ee_link = ee_link
     d.n_obs_joints = n_obs_joints
+    verts = np.asarray(getattr(model, 'verts', np.zeros((0, 3))), np.float64).reshape(-1, 3)
+    d.n_verts = verts.shape[0]
+    if d.n_verts:
+        d.s_vert_first, d.s_vert_count = ip('s_v0', model.s_v0), ip('s_vn', model.s_vn)
+        d.verts = dp('verts', verts)
     return d, keep

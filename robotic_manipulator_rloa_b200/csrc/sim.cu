@@ -1,4 +1,5 @@
 // librloa_b200: batched manipulator simulator — kernels and C ABI (include/rloa_b200.h).
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -103,7 +104,7 @@ struct PgsState<D, true> {
 
 // launch 3: thread = arm.  Environment.step (reference environment.py:453-485) from the free velocity on:
 // motor / limit rows, projected Gauss-Seidel, integration, get_state, get_reward, is_terminal_state.
-template <int D, int NLMAX, bool PACKED, bool EXACT>
+template <int D, int NLMAX, bool PACKED, bool EXACT, bool GJK>
 __global__ void __launch_bounds__(kTpb)
 sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_constant__ StepCfgDev cfg, int mode,
                  const float* __restrict__ actions, const uint8_t* __restrict__ active, float* __restrict__ obs,
@@ -271,7 +272,7 @@ sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_c
 
         // ---- state / reward / done from the post-step configuration ----
         const V3 tg = ld3(S.target + 3 * (size_t)env), ob = ld3(S.obstacle + 3 * (size_t)env);
-        const ObsOut o = fk_and_distances<NLMAX>(M, S.q + env, N, ob, tg, cfg.obstacle_thr, !is_reset, nullptr, 0);
+        const ObsOut o = fk_and_distances<NLMAX, GJK>(M, S.q + env, N, ob, tg, cfg.obstacle_thr, !is_reset, nullptr, 0);
         if (obs != nullptr) {
             const int n = M.n_obs;
             for (int i = 0; i < n; i++) {
@@ -315,7 +316,7 @@ sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_c
 }
 
 // get_state + the distances behind get_reward / is_terminal_state, without stepping
-template <int NLMAX>
+template <int NLMAX, bool GJK>
 __global__ void __launch_bounds__(kTpb)
 sim_observe_kernel(const __grid_constant__ ModelDev M, SimArrays S, float* __restrict__ obs,
                    float* __restrict__ link_obst, float* __restrict__ ee_target) {
@@ -323,7 +324,7 @@ sim_observe_kernel(const __grid_constant__ ModelDev M, SimArrays S, float* __res
     const int N = S.n_envs;
     if (env >= N) return;
     const V3 tg = ld3(S.target + 3 * (size_t)env), ob = ld3(S.obstacle + 3 * (size_t)env);
-    const ObsOut o = fk_and_distances<NLMAX>(M, S.q + env, N, ob, tg, 0.f, true,
+    const ObsOut o = fk_and_distances<NLMAX, GJK>(M, S.q + env, N, ob, tg, 0.f, true,
                                              link_obst ? link_obst + (size_t)env * M.nl : nullptr, 1);
     if (obs != nullptr) {
         const int n = M.n_obs;
@@ -520,6 +521,10 @@ using namespace rloa;
 struct rloa_model {
     ModelDev host;
     int device = 0;
+    float4* verts = nullptr;     // device copy of the hull vertices (host.verts points here)
+    ~rloa_model() {
+        if (verts) cudaFree(verts);
+    }
 };
 
 struct rloa_sim {
@@ -558,7 +563,9 @@ static void mat3_mul(const double* A, const double* B, double* C) {
 extern "C" int rloa_model_create(const rloa_model_desc* d, rloa_model** out) {
     RLOA_REQUIRE(d != nullptr && out != nullptr, "rloa_model_create: null argument");
     RLOA_REQUIRE(d->nl >= 1 && d->nl <= kMaxLinks, "rloa_model_create: 1 <= nl <= 32 links supported");
-    RLOA_REQUIRE(d->ns >= 0 && d->ns <= kMaxShapes, "rloa_model_create: at most 32 collision primitives supported");
+    RLOA_REQUIRE(d->ns >= 0 && d->ns <= kMaxShapes, "rloa_model_create: at most 32 collision shapes supported");
+    RLOA_REQUIRE(d->n_verts >= 0 && d->n_verts <= RLOA_MAX_HULL_VERTS, "rloa_model_create: too many convex-hull vertices");
+    RLOA_REQUIRE(d->n_verts == 0 || (d->s_vert_first && d->s_vert_count && d->verts), "rloa_model_create: hull vertex arrays missing");
     RLOA_REQUIRE(d->ee_link >= 0 && d->ee_link < d->nl, "rloa_model_create: endeffector index out of range");
     RLOA_REQUIRE(d->n_obs_joints >= 0 && d->n_obs_joints <= d->nl, "rloa_model_create: n_obs_joints out of range");
     RLOA_REQUIRE(d->dt > 0 && d->iters >= 1, "rloa_model_create: dt > 0 and iters >= 1 required");
@@ -644,10 +651,44 @@ extern "C" int rloa_model_create(const rloa_model_desc* d, rloa_model** out) {
         h.s_type[s] = d->s_type[s];
         for (int k = 0; k < 9; k++) h.s_R[s][k] = (float)d->s_R[9 * s + k];
         for (int k = 0; k < 3; k++) { h.s_p[s][k] = (float)d->s_p[3 * s + k]; h.s_dim[s][k] = (float)d->s_dim[3 * s + k]; }
+        const int t = d->s_type[s];
+        if (!(t >= RLOA_SHAPE_SPHERE && t <= RLOA_SHAPE_HULL)) { delete m; return fail(RLOA_ERR_INVALID, "rloa_model_create: unknown shape type"); }
+        if (t == RLOA_SHAPE_HULL) {
+            const int v0 = d->n_verts ? d->s_vert_first[s] : 0, vn = d->n_verts ? d->s_vert_count[s] : 0;
+            if (!(vn >= 1 && v0 >= 0 && v0 + vn <= d->n_verts)) { delete m; return fail(RLOA_ERR_INVALID, "rloa_model_create: hull shape without vertices / vertex range out of bounds"); }
+            h.s_v0[s] = v0;
+            h.s_vn[s] = vn;
+            // bounding sphere in the shape frame (centre = box centre of the cloud): the broad phase of the obstacle query
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, c[3], r2 = 0;
+            for (int i = v0; i < v0 + vn; i++)
+                for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], d->verts[3 * i + k]); hi[k] = std::max(hi[k], d->verts[3 * i + k]); }
+            for (int k = 0; k < 3; k++) c[k] = 0.5 * (lo[k] + hi[k]);
+            for (int i = v0; i < v0 + vn; i++) {
+                double q = 0;
+                for (int k = 0; k < 3; k++) q += (d->verts[3 * i + k] - c[k]) * (d->verts[3 * i + k] - c[k]);
+                r2 = std::max(r2, q);
+            }
+            for (int k = 0; k < 3; k++) h.s_bs[s][k] = (float)c[k];
+            h.s_bs[s][3] = (float)(std::sqrt(r2) * (1.0 + 1e-6) + 1e-7);
+            h.use_gjk = 1;
+        }
+        if (t == RLOA_SHAPE_BOX && d->s_link[s] == d->ee_link) h.use_gjk = 1;   // box vs target cube needs the narrow phase
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { delete m; cudaGetLastError(); return fail(RLOA_ERR_NO_DEVICE, "rloa_model_create: no CUDA device visible"); }
     if (cudaGetDevice(&m->device) != cudaSuccess) { delete m; return fail(RLOA_ERR_CUDA, "rloa_model_create: cudaGetDevice failed"); }
+    if (d->n_verts > 0) {
+        std::vector<float4> hv((size_t)d->n_verts);
+        for (int i = 0; i < d->n_verts; i++)
+            hv[i] = make_float4((float)d->verts[3 * i], (float)d->verts[3 * i + 1], (float)d->verts[3 * i + 2], 0.f);
+        if (cudaMalloc(&m->verts, hv.size() * sizeof(float4)) != cudaSuccess ||
+            cudaMemcpy(m->verts, hv.data(), hv.size() * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("rloa_model_create: uploading the hull vertices failed: %s", cudaGetErrorString(cudaGetLastError()));
+            delete m;
+            return RLOA_ERR_CUDA;
+        }
+        h.verts = m->verts;
+    }
     *out = m;
     return RLOA_OK;
 }
@@ -806,9 +847,15 @@ static int launch_solve(const rloa_sim* s, const StepCfgDev& c, int mode, const 
     const ModelDev& h = s->model->host;
     const unsigned blocks = (unsigned)((s->a.n_envs + kTpb - 1) / kTpb);
     const int so = 9 + 2 * h.n_obs;
-#define RLOA_SOLVE(D, EXACT)                                                                                       \
-    sim_solve_kernel<D, NLMAX, (D <= 12), EXACT><<<blocks, kTpb, (size_t)(kTpb * so + 4 * D * kTpb) * sizeof(float), st>>>( \
+#define RLOA_SOLVE_G(D, EXACT, GJK)                                                                                \
+    sim_solve_kernel<D, NLMAX, (D <= 12), EXACT, GJK><<<blocks, kTpb, (size_t)(kTpb * so + 4 * D * kTpb) * sizeof(float), st>>>( \
         h, s->a, c, mode, actions, active, obs, reward, done, valid)
+#define RLOA_SOLVE(D, EXACT) RLOA_SOLVE_G(D, EXACT, false)
+    if (h.use_gjk) {               // mesh-hull shapes or box end-effector shapes: the GJK narrow phase is compiled in
+        if (h.ndof <= 8) RLOA_SOLVE_G(8, false, true);
+        else if (h.ndof <= 12) RLOA_SOLVE_G(12, false, true);
+        else RLOA_SOLVE_G(16, false, true);
+    } else
     if (h.ndof == 12 && NLMAX == 16) RLOA_SOLVE(12, true);         // KUKA iiwa + gripper
     else if (h.ndof == 9 && NLMAX == 16) RLOA_SOLVE(9, true);      // Panda
     else if (h.ndof == 7 && NLMAX == 16) RLOA_SOLVE(7, true);      // bare 7-dof arm
@@ -818,6 +865,7 @@ static int launch_solve(const rloa_sim* s, const StepCfgDev& c, int mode, const 
     else if (h.ndof <= 12) RLOA_SOLVE(12, false);
     else RLOA_SOLVE(16, false);
 #undef RLOA_SOLVE
+#undef RLOA_SOLVE_G
     RLOA_LAUNCHED();
     return RLOA_OK;
 }
@@ -928,8 +976,11 @@ extern "C" int rloa_sim_observe(const rloa_sim* s, float* obs, float* link_obsta
     RLOA_REQUIRE(s != nullptr, "rloa_sim_observe: null sim");
     const ModelDev& h = s->model->host;
     const unsigned blocks = (unsigned)((s->a.n_envs + kTpb - 1) / kTpb);
-    if (h.nl <= 16) sim_observe_kernel<16><<<blocks, kTpb, 0, as_stream(stream)>>>(h, s->a, obs, link_obstacle, ee_target);
-    else sim_observe_kernel<32><<<blocks, kTpb, 0, as_stream(stream)>>>(h, s->a, obs, link_obstacle, ee_target);
+    if (h.use_gjk) {
+        if (h.nl <= 16) sim_observe_kernel<16, true><<<blocks, kTpb, 0, as_stream(stream)>>>(h, s->a, obs, link_obstacle, ee_target);
+        else sim_observe_kernel<32, true><<<blocks, kTpb, 0, as_stream(stream)>>>(h, s->a, obs, link_obstacle, ee_target);
+    } else if (h.nl <= 16) sim_observe_kernel<16, false><<<blocks, kTpb, 0, as_stream(stream)>>>(h, s->a, obs, link_obstacle, ee_target);
+    else sim_observe_kernel<32, false><<<blocks, kTpb, 0, as_stream(stream)>>>(h, s->a, obs, link_obstacle, ee_target);
     RLOA_LAUNCHED();
     return RLOA_OK;
 }

@@ -58,6 +58,12 @@ struct ModelDev {
     float mass[kMaxLinks], inertia[kMaxLinks][3], damping[kMaxLinks], lower[kMaxLinks], upper[kMaxLinks];
     int s_link[kMaxShapes], s_type[kMaxShapes];
     float s_R[kMaxShapes][9], s_p[kMaxShapes][3], s_dim[kMaxShapes][3];
+    // convex-hull shapes (mesh / cylinder collision geometry): vertex range in verts, bounding sphere in the shape frame
+    int s_v0[kMaxShapes], s_vn[kMaxShapes];
+    float s_bs[kMaxShapes][4];
+    const float4* verts;                 // device, owned by rloa_model; xyz = vertex in the shape frame
+    int use_gjk;                         // the model has hull shapes or box shapes on the end-effector link
+    int pad2;
 };
 
 struct SimArrays {
@@ -226,6 +232,8 @@ __device__ __noinline__ float segment_box(V3 a, V3 b, V3 h) {
     return sqrtf(best);
 }
 
+#include "gjk.cuh"
+
 struct ObsOut {
     float ee_target;     // closest distance end-effector link <-> target cube (10 when no shape)
     bool hit;            // any link <-> obstacle distance < obstacle_threshold
@@ -235,7 +243,7 @@ struct ObsOut {
 // FK of the whole tree for one arm (q read from the SoA column qcol[i * N]) followed by the distance
 // queries.  Rw / pw: per-thread scratch [NLMAX][9] / [NLMAX][3].  link_dist (optional, [nl] with stride
 // ld_stride) receives the per-link minimum over the link's shapes (diagnostics path).
-template <int NLMAX>
+template <int NLMAX, bool GJK>
 __device__ __forceinline__ ObsOut fk_and_distances(const ModelDev& M, const float* __restrict__ qcol, int N,
                                                    V3 obstacle, V3 target, float obstacle_thr, bool want_dist,
                                                    float* __restrict__ link_dist, int ld_stride) {
@@ -290,8 +298,18 @@ __device__ __forceinline__ ObsOut fk_and_distances(const ModelDev& M, const floa
             const float tz = fminf(fmaxf(o_s.z, -dim.y), dim.y);   // closest point of the local-z segment
             const float ez = o_s.z - tz;
             dist = sqrtf(fmaf(o_s.x, o_s.x, fmaf(o_s.y, o_s.y, ez * ez))) - dim.x;
-        } else {
+        } else if (!GJK || type == RLOA_SHAPE_BOX) {
             dist = point_box_signed(o_s, dim);
+        } else {
+            // mesh hull: the bounding sphere decides most queries (only d < threshold is consumed on the step path)
+            const V3 bc = o_s - v3(M.s_bs[s][0], M.s_bs[s][1], M.s_bs[s][2]);
+            const float lower = sqrtf(dot(bc, bc)) - M.s_bs[s][3] - dim.x;
+            if (link_dist == nullptr && lower - M.obstacle_radius >= fmaxf(obstacle_thr, 0.f)) {
+                dist = lower;
+            } else {
+                const GjkShape A{M.verts + M.s_v0[s], M.s_vn[s], dim, Rs, ps};
+                dist = gjk_distance(A, obstacle, v3(0.f, 0.f, 0.f)) - dim.x;
+            }
         }
         const float d_obst = dist - M.obstacle_radius;
         o.hit = o.hit || (d_obst < obstacle_thr);
@@ -304,7 +322,11 @@ __device__ __forceinline__ ObsOut fk_and_distances(const ModelDev& M, const floa
             } else if (type == RLOA_SHAPE_CAPSULE) {
                 const V3 axw = v3(Rs.m[2], Rs.m[5], Rs.m[8]);
                 d_tgt = segment_box(c_t - dim.y * axw, c_t + dim.y * axw, th) - dim.x;
-            }                                    // box end-effector shapes: no narrow phase -> saturate (10)
+            } else if (GJK) {                    // box or hull vs the cube: GJK (instantiated only for such models)
+                const bool box = type == RLOA_SHAPE_BOX;
+                const GjkShape A{box ? nullptr : M.verts + M.s_v0[s], M.s_vn[s], dim, Rs, ps};
+                d_tgt = gjk_distance(A, target, th) - (box ? 0.f : dim.x);
+            }
             o.ee_target = fminf(o.ee_target, d_tgt);
         }
     }

@@ -11,7 +11,9 @@ is moved to its centre of mass (principal axes), and the result is a set of flat
 ``robotic_manipulator_rloa_b200/data`` (same relative names as pybullet_data) and
 :func:`resolve_manipulator_file` searches that directory the way
 ``p.setAdditionalSearchPath(pybullet_data.getDataPath())`` (environment.py:210) does.
-Mesh collision geometry is not supported (no meshes exist here): primitives only.
+Collision geometry: ``<sphere>``, ``<capsule>``, ``<box>`` primitives, and — like pybullet's importer —
+``<mesh>`` (binary / ASCII STL, OBJ) and ``<cylinder>`` elements as convex vertex clouds with a 0.001 margin
+(:mod:`mesh_io`).
 """
 from __future__ import annotations
 
@@ -23,10 +25,13 @@ from typing import List, Optional, Tuple
 
 import numpy as np
 
+from . import mesh_io
+
 FIXED, REVOLUTE, PRISMATIC = 0, 1, 2
-SHAPE_SPHERE, SHAPE_CAPSULE, SHAPE_BOX = 1, 2, 3
+SHAPE_SPHERE, SHAPE_CAPSULE, SHAPE_BOX, SHAPE_HULL = 1, 2, 3, 4
 MAX_LINKS = 32
-MAX_SHAPES = 64
+MAX_SHAPES = 32
+MAX_VERTS = 16384              # hull vertices per model (RLOA_MAX_HULL_VERTS)
 
 DATA_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'data')
 
@@ -58,6 +63,7 @@ class _Shape:
     R: np.ndarray          # link frame <- shape frame
     p: np.ndarray
     dim: Tuple[float, float, float]
+    verts: Optional[np.ndarray] = None     # SHAPE_HULL: [n][3] in the shape frame
 
 
 @dataclass
@@ -120,6 +126,10 @@ class RobotModel:
     erp: float = 0.2
     max_vel: float = 100.0
     limit_max_impulse: float = 100.0
+    # convex vertex clouds of the SHAPE_HULL shapes: shape s owns verts[s_v0[s] : s_v0[s] + s_vn[s]]
+    s_v0: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    s_vn: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    verts: np.ndarray = field(default_factory=lambda: np.zeros((0, 3)))
 
     @property
     def ns(self) -> int:
@@ -180,8 +190,11 @@ def _compile(links: dict, joints: List[_Joint], base_R: np.ndarray, base_p: np.n
              has_limit=np.zeros(nl, np.int32))
     axis_link = np.zeros((nl, 3))
     s_link, s_type, s_R, s_p, s_dim = [], [], [], [], []
+    s_v0, s_vn, verts = [], [], []
+    nverts = 0
 
     def add_shapes(link_name: str, index: int) -> None:
+        nonlocal nverts
         R_lc, c, _ = frames[link_name]
         for sh in links[link_name].shapes:
             s_link.append(index)
@@ -189,6 +202,12 @@ def _compile(links: dict, joints: List[_Joint], base_R: np.ndarray, base_p: np.n
             s_R.append((R_lc.T @ sh.R).reshape(9))
             s_p.append(R_lc.T @ (sh.p - c))
             s_dim.append(sh.dim)
+            n = 0 if sh.verts is None else int(sh.verts.shape[0])
+            s_v0.append(nverts)
+            s_vn.append(n)
+            if n:
+                verts.append(np.asarray(sh.verts, float))
+                nverts += n
 
     Rb_lc, cb, _ = frames[root]
     base_R_com = base_R @ Rb_lc
@@ -218,8 +237,12 @@ def _compile(links: dict, joints: List[_Joint], base_R: np.ndarray, base_p: np.n
 
     ns = len(s_link)
     if ns > MAX_SHAPES:
-        raise ModelError(f'too many collision primitives: {ns} > {MAX_SHAPES}')
+        raise ModelError(f'too many collision shapes: {ns} > {MAX_SHAPES}')
+    if nverts > MAX_VERTS:
+        raise ModelError(f'too many convex-hull vertices: {nverts} > {MAX_VERTS}; simplify the collision meshes')
     return RobotModel(
+        s_v0=np.asarray(s_v0, np.int32).reshape(ns), s_vn=np.asarray(s_vn, np.int32).reshape(ns),
+        verts=np.concatenate(verts, axis=0) if verts else np.zeros((0, 3)),
         nl=nl, base_R=base_R_com.reshape(9), base_p=base_p_com,
         s_link=np.asarray(s_link, np.int32).reshape(ns), s_type=np.asarray(s_type, np.int32).reshape(ns),
         s_R=np.asarray(s_R, float).reshape(ns, 9), s_p=np.asarray(s_p, float).reshape(ns, 3),
@@ -229,7 +252,7 @@ def _compile(links: dict, joints: List[_Joint], base_R: np.ndarray, base_p: np.n
 
 
 # ----------------------------------------------------------------------------------------- geometry
-def _parse_geometry(geom: ET.Element, R: np.ndarray, p: np.ndarray, sdf: bool) -> Optional[_Shape]:
+def _parse_geometry(geom: ET.Element, R: np.ndarray, p: np.ndarray, sdf: bool, model_dir: str) -> Optional[_Shape]:
     if geom is None:
         return None
     node = geom.find('sphere')
@@ -245,9 +268,23 @@ def _parse_geometry(geom: ET.Element, R: np.ndarray, p: np.ndarray, sdf: bool) -
     if node is not None:
         size = _floats(node.findtext('size') if sdf else node.get('size'), 3)
         return _Shape(SHAPE_BOX, R, p, (0.5 * size[0], 0.5 * size[1], 0.5 * size[2]))
-    if geom.find('mesh') is not None or geom.find('cylinder') is not None:
-        raise ModelError('mesh/cylinder collision geometry is not supported by the B200 simulator '
-                         '(primitives only: sphere, capsule, box)')
+    node = geom.find('cylinder')
+    if node is not None:                               # imported as the hull of 2 x 32 rim points, like pybullet
+        r = float(node.findtext('radius')) if sdf else float(node.get('radius'))
+        ln = float(node.findtext('length')) if sdf else float(node.get('length'))
+        return _Shape(SHAPE_HULL, R, p, (mesh_io.HULL_MARGIN, 0.0, 0.0), mesh_io.cylinder_vertex_cloud(r, ln))
+    node = geom.find('mesh')
+    if node is not None:
+        uri = node.findtext('uri') if sdf else node.get('filename')
+        scale = _floats((node.findtext('scale') if sdf else node.get('scale')) or '1 1 1', 3)
+        if not uri:
+            raise ModelError('<mesh> collision element without a file name')
+        try:
+            v = mesh_io.load_mesh_vertices(mesh_io.resolve_mesh_file(uri.strip(), model_dir, [DATA_PATH]))
+            v = mesh_io.convex_vertex_cloud(v * np.asarray(scale))
+        except mesh_io.MeshError as err:
+            raise ModelError(str(err))
+        return _Shape(SHAPE_HULL, R, p, (mesh_io.HULL_MARGIN, 0.0, 0.0), v)
     return None
 
 
@@ -282,7 +319,7 @@ def load_urdf(path: str) -> RobotModel:
             if org is not None:
                 p = np.array(_floats(org.get('xyz'), 3))
                 R = rpy_to_R(*_floats(org.get('rpy'), 3))
-            sh = _parse_geometry(col.find('geometry'), R, p, sdf=False)
+            sh = _parse_geometry(col.find('geometry'), R, p, False, os.path.dirname(os.path.abspath(path)))
             if sh is not None:
                 l.shapes.append(sh)
         links[l.name] = l
@@ -341,7 +378,7 @@ def load_sdf(path: str) -> RobotModel:
                                       [g('ixz'), g('iyz'), g('izz')]])
         for col in ln.findall('collision'):
             Rc, pc = pose(col.find('pose'))
-            sh = _parse_geometry(col.find('geometry'), Rc, pc, sdf=True)
+            sh = _parse_geometry(col.find('geometry'), Rc, pc, True, os.path.dirname(os.path.abspath(path)))
             if sh is not None:
                 l.shapes.append(sh)
         links[l.name] = l

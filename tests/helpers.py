@@ -64,3 +64,94 @@ def assert_params_close(got, want, name, rtol=2e-4, atol=2e-6, lr=1e-3, max_frac
     bad = np.abs(got - want) > atol + rtol * np.abs(want)
     assert bad.mean() <= max_frac, f'{name}: {bad.sum()} of {bad.size} elements differ'
     assert np.abs(got - want).max() <= 3.1 * lr, f'{name}: max diff {np.abs(got - want).max():.3e}'
+
+
+# ---- mesh (convex hull) variants of the shipped models -----------------------------------------------------------
+def _fibonacci_sphere(n):
+    k = np.arange(n) + 0.5
+    phi = np.arccos(1 - 2 * k / n)
+    th = np.pi * (1 + 5 ** 0.5) * k
+    return np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], axis=1)
+
+
+def hull_cloud(kind, dim, n=40):
+    """Vertex cloud standing in for a primitive: box -> its 8 corners (the same shape), sphere / capsule -> n points
+    on the surface (a polytope inscribed in the primitive)."""
+    dim = np.asarray(dim, float)
+    if kind == 3:
+        return np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], float) * dim
+    pts = _fibonacci_sphere(n) * dim[0]
+    if kind == 2:
+        pts[:, 2] += np.where(pts[:, 2] >= 0, dim[1], -dim[1])
+    return pts
+
+
+def hullified(model, margin=0.001, n=40, only_links=None):
+    """Copy of a RobotModel whose collision primitives became SHAPE_HULL vertex clouds (what a file with <mesh>
+    collision elements loads as)."""
+    import dataclasses
+    s_type, s_dim = model.s_type.copy(), model.s_dim.copy()
+    v0, vn, verts, at = [], [], [], 0
+    for s in range(model.ns):
+        if only_links is not None and int(model.s_link[s]) not in only_links:
+            v0.append(at); vn.append(0)
+            continue
+        cloud = hull_cloud(int(model.s_type[s]), model.s_dim[s], n)
+        s_type[s], s_dim[s] = 4, (margin, 0.0, 0.0)
+        v0.append(at); vn.append(len(cloud)); verts.append(cloud); at += len(cloud)
+    return dataclasses.replace(model, s_type=s_type, s_dim=s_dim, s_v0=np.asarray(v0, np.int32),
+                               s_vn=np.asarray(vn, np.int32), verts=np.concatenate(verts, axis=0))
+
+
+BOX_CORNERS = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], float)
+BOX_TRIS = [(0, 1, 3), (0, 3, 2), (4, 6, 7), (4, 7, 5), (0, 4, 5), (0, 5, 1), (2, 3, 7), (2, 7, 6), (0, 2, 6), (0, 6, 4),
+            (1, 5, 7), (1, 7, 3)]
+
+
+def write_box_mesh(path, half, fmt):
+    """A box as binary STL / ASCII STL / OBJ (12 triangles)."""
+    import struct
+    v = BOX_CORNERS * np.asarray(half, float)
+    if fmt == 'obj':
+        with open(path, 'w') as f:
+            f.write('# box\n')
+            for p in v:
+                f.write('v %.9g %.9g %.9g\n' % tuple(p))
+            for t in BOX_TRIS:
+                f.write('f %d %d %d\n' % (t[0] + 1, t[1] + 1, t[2] + 1))
+    elif fmt == 'stl_ascii':
+        with open(path, 'w') as f:
+            f.write('solid box\n')
+            for t in BOX_TRIS:
+                f.write(' facet normal 0 0 0\n  outer loop\n')
+                for i in t:
+                    f.write('   vertex %.9g %.9g %.9g\n' % tuple(v[i]))
+                f.write('  endloop\n endfacet\n')
+            f.write('endsolid box\n')
+    else:
+        with open(path, 'wb') as f:
+            f.write(b'solid binary box'.ljust(80, b' '))       # starts with "solid" like many exporters' files
+            f.write(struct.pack('<I', len(BOX_TRIS)))
+            for t in BOX_TRIS:
+                f.write(struct.pack('<3f', 0, 0, 0))
+                for i in t:
+                    f.write(struct.pack('<3f', *v[i]))
+                f.write(struct.pack('<H', 0))
+
+
+def write_test_arm(dirname, geometry):
+    """A 3-joint arm as URDF; geometry(link index) -> the inner XML of each link's <collision><geometry>."""
+    links, joints = [], []
+    for i in range(4):
+        col = '' if i == 0 else f'<collision><origin xyz="0 0 0.1" rpy="0.1 0.2 0.3"/><geometry>{geometry(i)}</geometry></collision>'
+        links.append(f'<link name="l{i}"><inertial><origin xyz="0 0 0.1"/><mass value="1.5"/>'
+                     f'<inertia ixx="0.01" iyy="0.012" izz="0.005" ixy="0" ixz="0" iyz="0"/></inertial>{col}</link>')
+    axes = ['0 0 1', '0 1 0', '1 0 0']
+    for i in range(3):
+        joints.append(f'<joint name="j{i}" type="revolute"><parent link="l{i}"/><child link="l{i + 1}"/>'
+                      f'<origin xyz="0 0 0.2" rpy="0 0 0"/><axis xyz="{axes[i]}"/>'
+                      f'<limit lower="-2.5" upper="2.5" effort="100" velocity="10"/></joint>')
+    path = f'{dirname}/arm.urdf'
+    with open(path, 'w') as f:
+        f.write('<?xml version="1.0"?><robot name="arm">' + ''.join(links) + ''.join(joints) + '</robot>')
+    return path

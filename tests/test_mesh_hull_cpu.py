@@ -1,0 +1,169 @@
+"""
+CPU tests of the mesh front end and of the oracle's GJK restatement: STL / OBJ readers,
+<mesh> / <cylinder> collision elements as convex vertex clouds, and the hull / box distance queries against an
+independent quadratic-programming solution and against the closed-form primitives.
+"""
+import numpy as np
+import pytest
+from scipy.optimize import minimize
+from scipy.spatial.transform import Rotation
+
+from helpers import BOX_CORNERS, hullified, make_oracle, write_box_mesh, write_test_arm, KUKA, random_states
+from oracle import bullet_oracle as bo
+from robotic_manipulator_rloa_b200.environment import mesh_io
+from robotic_manipulator_rloa_b200.environment.robot_model import ModelError, SHAPE_BOX, SHAPE_HULL, load_urdf
+
+
+@pytest.mark.parametrize('fmt,ext', [('stl_binary', 'stl'), ('stl_ascii', 'stl'), ('obj', 'obj')])
+def test_mesh_readers_return_the_vertices(tmp_path, fmt, ext):
+    path = str(tmp_path / f'box.{ext}')
+    half = (0.03, 0.05, 0.11)
+    write_box_mesh(path, half, fmt)
+    raw = mesh_io.load_mesh_vertices(path)
+    assert raw.shape == ((8, 3) if fmt == 'obj' else (36, 3))
+    cloud = mesh_io.convex_vertex_cloud(raw)
+    want = np.unique(BOX_CORNERS * np.asarray(half), axis=0)
+    assert cloud.shape == (8, 3) and np.allclose(np.unique(cloud, axis=0), want, atol=1e-7)
+
+
+def test_hull_reduction_drops_interior_points_and_keeps_flat_clouds():
+    rng = np.random.default_rng(0)
+    inner = rng.uniform(-0.5, 0.5, (200, 3)) * 0.9
+    cloud = mesh_io.convex_vertex_cloud(np.concatenate([BOX_CORNERS, inner]))
+    assert cloud.shape == (8, 3)
+    flat = np.concatenate([rng.uniform(-1, 1, (20, 2)), np.zeros((20, 1))], axis=1)     # Qhull refuses: kept as is
+    assert mesh_io.convex_vertex_cloud(flat).shape == (20, 3)
+
+
+def test_cylinder_cloud_is_two_rims():
+    c = mesh_io.cylinder_vertex_cloud(0.04, 0.3)
+    assert c.shape == (64, 3)
+    assert np.allclose(np.hypot(c[:, 0], c[:, 1]), 0.04) and np.allclose(np.abs(c[:, 2]), 0.15)
+
+
+def test_bad_mesh_files_raise(tmp_path):
+    with pytest.raises(mesh_io.MeshError):
+        mesh_io.load_mesh_vertices(str(tmp_path / 'missing.stl'))
+    p = tmp_path / 'x.dae'
+    p.write_text('<COLLADA/>')
+    with pytest.raises(mesh_io.MeshError):
+        mesh_io.load_mesh_vertices(str(p))
+    with pytest.raises(ModelError):
+        load_urdf(write_test_arm(str(tmp_path), lambda i: '<mesh filename="meshes/nope.stl"/>'))
+
+
+def _load_arm_pair(tmp_path):
+    half = {1: (0.04, 0.05, 0.1), 2: (0.03, 0.03, 0.09), 3: (0.02, 0.06, 0.05)}
+    (tmp_path / 'prim').mkdir()
+    (tmp_path / 'mesh' / 'meshes').mkdir(parents=True)
+    fmts = {1: ('stl_binary', 'stl'), 2: ('stl_ascii', 'stl'), 3: ('obj', 'obj')}
+    for i, (fmt, ext) in fmts.items():
+        write_box_mesh(str(tmp_path / 'mesh' / 'meshes' / f'l{i}.{ext}'), (0.5, 0.5, 0.5), fmt)   # unit cube, scaled below
+    prim = load_urdf(write_test_arm(str(tmp_path / 'prim'),
+                                    lambda i: '<box size="%g %g %g"/>' % tuple(2 * np.asarray(half[i]))))
+    mesh = load_urdf(write_test_arm(str(tmp_path / 'mesh'),
+                                    lambda i: '<mesh filename="package://arm/meshes/l%d.%s" scale="%g %g %g"/>'
+                                    % ((i, fmts[i][1]) + tuple(2 * np.asarray(half[i])))))
+    return prim, mesh
+
+
+def test_urdf_mesh_elements_load_as_hulls(tmp_path):
+    prim, mesh = _load_arm_pair(tmp_path)
+    assert list(prim.s_type) == [SHAPE_BOX] * 3 and list(mesh.s_type) == [SHAPE_HULL] * 3
+    assert mesh.verts.shape == (24, 3) and list(mesh.s_vn) == [8, 8, 8] and list(mesh.s_v0) == [0, 8, 16]
+    assert np.allclose(mesh.s_dim[:, 0], mesh_io.HULL_MARGIN)
+    for s in range(3):                       # scale applied: the cloud spans the primitive's half extents
+        assert np.allclose(np.abs(mesh.verts[8 * s:8 * s + 8]).max(axis=0), prim.s_dim[s])
+    assert np.allclose(mesh.s_R, prim.s_R) and np.allclose(mesh.s_p, prim.s_p)
+
+
+def test_urdf_cylinder_loads_as_hull(tmp_path):
+    m = load_urdf(write_test_arm(str(tmp_path), lambda i: '<cylinder radius="0.05" length="0.2"/>'))
+    assert list(m.s_type) == [SHAPE_HULL] * 3 and m.verts.shape == (192, 3)
+
+
+def test_oracle_distances_box_mesh_equals_box_primitive(tmp_path):
+    """The same arm with <box> primitives and with box meshes: link distances differ by the hull margin only, and the
+    end-effector/target distance (box vs cube and hull vs cube, both GJK) by the margin."""
+    prim, mesh = _load_arm_pair(tmp_path)
+    op, om = bo.BulletOracle(prim, 2, 3), bo.BulletOracle(mesh, 2, 3)
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        q = rng.uniform(-2.4, 2.4, 3)
+        ob, tg = rng.uniform(-0.5, 0.5, 3) + [0, 0, 0.4], rng.uniform(-0.5, 0.5, 3) + [0, 0, 0.4]
+        lp, ep, _ = op.distances(q, ob, tg)
+        lm, em, _ = om.distances(q, ob, tg)
+        inside = lp < -0.075 + 1e-9            # sphere centre inside the box: the hull path reports the overlap bound
+        assert np.abs((lm + mesh_io.HULL_MARGIN - lp)[~inside]).max() <= 1e-9
+        assert np.all(lm[inside] <= -0.075)
+        if ep > 1e-6:
+            assert abs(em + mesh_io.HULL_MARGIN - ep) <= 1e-9
+
+
+def _qp_distance(W, bc, bh, rng):
+    n = len(W)
+
+    def f(x):
+        d = x[:n] @ W - x[n:]
+        return d @ d
+    cons = [{'type': 'eq', 'fun': lambda x: x[:n].sum() - 1}]
+    bnds = [(0, 1)] * n + [(bc[i] - bh[i], bc[i] + bh[i]) for i in range(3)]
+    best = np.inf
+    for _ in range(3):
+        x0 = np.concatenate([rng.dirichlet(np.ones(n)), bc])
+        best = min(best, minimize(f, x0, method='SLSQP', bounds=bnds, constraints=cons,
+                                  options={'ftol': 1e-16, 'maxiter': 500}).fun)
+    return np.sqrt(max(best, 0.0))
+
+
+def test_oracle_gjk_against_quadratic_program():
+    rng = np.random.default_rng(0)
+    for trial in range(60):
+        V = rng.normal(size=(rng.integers(4, 24), 3)) * rng.uniform(0.02, 0.3, size=3)
+        R = Rotation.random(random_state=trial).as_matrix()
+        p, bc = rng.normal(size=3) * 0.3, rng.normal(size=3) * 0.4
+        bh = np.full(3, 0.025) if trial % 2 else np.zeros(3)
+        d, it = bo.gjk_hull_box(V, R.reshape(9), p, bc, bh)
+        assert it <= 20
+        assert abs(d - _qp_distance((R @ V.T).T + p, bc, bh, rng)) <= 1e-6
+
+
+def test_oracle_gjk_closed_forms():
+    rng = np.random.default_rng(1)
+    h = np.array([0.1, 0.05, 0.2])
+    eye = np.eye(3).reshape(9)
+    for _ in range(500):
+        pt = rng.normal(size=3) * 0.3
+        o = np.abs(pt) - h
+        want = np.sqrt((np.maximum(o, 0) ** 2).sum())          # 0 inside
+        d, _ = bo.gjk_hull_box(BOX_CORNERS * h, eye, np.zeros(3), pt, np.zeros(3))
+        assert abs(d - want) <= 1e-12
+    # two axis-aligned boxes: per-axis gaps
+    for _ in range(500):
+        c = rng.normal(size=3) * 0.4
+        gap = np.maximum(np.abs(c) - h - 0.025, 0)
+        d, _ = bo.gjk_hull_box(BOX_CORNERS * h, eye, np.zeros(3), c, np.full(3, 0.025))
+        assert abs(d - np.sqrt((gap ** 2).sum())) <= 1e-12
+    # rigid motion invariance
+    V = rng.normal(size=(30, 3)) * 0.1
+    for k in range(50):
+        R = Rotation.random(random_state=k).as_matrix()
+        p, pt = rng.normal(size=3), rng.normal(size=3) * 0.5
+        d0, _ = bo.gjk_hull_box(V, eye, np.zeros(3), pt, np.zeros(3))
+        d1, _ = bo.gjk_hull_box(V, R.reshape(9), p, R @ pt + p, np.zeros(3))
+        assert abs(d0 - d1) <= 1e-10
+
+
+def test_hullified_kuka_tracks_the_primitive_model():
+    """An inscribed 40-point polytope per primitive: distances can only grow, by less than the sagitta of the cloud."""
+    cfg = KUKA
+    model, orc = make_oracle(cfg)
+    hm = hullified(model, margin=0.0)
+    oh = bo.BulletOracle(hm, cfg['ee'], len(cfg['involved']))
+    q, _ = random_states(model, 40, seed=5)
+    for e in range(40):
+        lp, ep, _ = orc.distances(q[e], cfg['obstacle'], cfg['target'])
+        lh, eh, _ = oh.distances(q[e], cfg['obstacle'], cfg['target'])
+        sep = lp > -0.075                       # the overlap bound replaces the depth when the centre is inside
+        assert np.all(lh[sep] >= lp[sep] - 1e-9) and np.all(lh[sep] <= lp[sep] + 0.02)
+        assert eh >= ep - 1e-9 and eh <= ep + 0.02

@@ -1,4 +1,5 @@
-"""Quick simulator throughput probe (sim-only, U(-1,1) actions); prints env-steps/s for a few N."""
+"""Quick simulator throughput probe (sim-only, U(-1,1) actions); prints env-steps/s for a few N.
+usage: bench_sim_quick.py [panda] [mesh[=VERTS]] [N ...]   (mesh: every collision primitive as a VERTS-point hull, GJK path)"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -9,8 +10,17 @@ args = sys.argv[1:]
 panda = bool(args) and args[0] == 'panda'
 if panda:
     args = args[1:]
+mesh = 0
+if args and args[0].startswith('mesh'):
+    mesh = int(args[0].split('=')[1]) if '=' in args[0] else 40
+    args = args[1:]
 model = load_manipulator('franka_panda/panda.urdf' if panda else 'kuka_iiwa/kuka_with_gripper2.sdf')
 na = 7 if panda else 6
+if mesh:
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
+    from helpers import hullified
+    model = hullified(model, n=mesh)
+    print(f'collision shapes: convex hulls, {model.verts.shape[0]} vertices in {model.ns} shapes')
 print('model:', 'panda (12 joints / 9 dof, BASELINE configs[4])' if panda else 'kuka iiwa + gripper (14 joints / 12 dof)')
 for n in [int(x) for x in (args or ['4096', '16384', '65536', '262144'])]:
     if panda:
