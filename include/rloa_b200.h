@@ -185,6 +185,13 @@ int rloa_sim_reset(rloa_sim* s, const uint8_t* mask, const float* init_targets, 
  * shape, collision_detector.py:56-57) and ee_target [n_envs].  Any output may be NULL. */
 int rloa_sim_observe(const rloa_sim* s, float* obs, float* link_obstacle, float* ee_target, void* stream);
 
+/* get_manipulator_collisions_with_itself (environment.py:394-412 -> CollisionDetector.compute_collisions_in_manipulator,
+ * utils/collision_detector.py:63-98): link_link [n_envs][nl][nl], entry [i][j] = closest distance between link i and
+ * link j (p.getClosestPoints(body, body, 10, linkIndexA=i, linkIndexB=j), minimum over the shape pairs).  Entries the
+ * reference does not query — the diagonal and adjacent indices |i - j| = 1 — and pairs with a shapeless link hold 10.0.
+ * Not on the step path (Environment.step never passes consider_autocollision=True). */
+int rloa_sim_self_distances(const rloa_sim* s, float* link_link, void* stream);
+
 /* diagnostics: PGS iterations used by the last substep of every env, [n_envs] int32 */
 int rloa_sim_last_iterations(const rloa_sim* s, int32_t* iters, void* stream);
 

@@ -184,6 +184,12 @@ class BulletOracle:
                             _dp(np.ascontiguousarray(target, np.float64)), _dp(lo), _dp(ee), _dp(eep))
         return lo, float(ee[0]), eep
 
+    def self_distances(self, q):
+        """[nl][nl] link-link closest distances (environment.py:394-412); 10 where the reference does not query."""
+        out = np.zeros((self.nl, self.nl))
+        lib().orc_self_distances(C.byref(self.m), _dp(np.ascontiguousarray(q, np.float64)), _dp(out))
+        return out
+
     def observe(self, q, qd, obstacle, target):
         obs, rew, done = np.zeros(self.S), np.zeros(1), np.zeros(1, np.int32)
         lib().orc_observe(C.byref(self.m), _dp(np.ascontiguousarray(q, np.float64)),

@@ -622,15 +622,17 @@ static int simplex_closest(double P[4][3], int* n, double* v) {
     return 0;
 }
 
-static double gjk_distance(const orc_convex* A, const double* bc, const double* bh, int* iters_out) {
-    double P[4][3], v[3], w[3], sa[3], nd[3];
+/* distance between the cores of two posed convex shapes; 0 when they overlap */
+static double gjk_pair(const orc_convex* A, const orc_convex* B, int* iters_out) {
+    double P[4][3], v[3], w[3], sa[3], sb[3], nd[3];
     int n = 0, it;
-    for (int x = 0; x < 3; x++) v[x] = A->p[x] - bc[x];
+    for (int x = 0; x < 3; x++) v[x] = A->p[x] - B->p[x];
     if (dot3(v, v) < 1e-24) { v[0] = 1; v[1] = v[2] = 0; }
     for (it = 0; it < 64; it++) {
         for (int x = 0; x < 3; x++) nd[x] = -v[x];
         support_shape(A, nd, sa);
-        for (int x = 0; x < 3; x++) w[x] = sa[x] - (bc[x] + (v[x] >= 0 ? bh[x] : -bh[x]));   /* support of A - B along -v */
+        support_shape(B, v, sb);
+        for (int x = 0; x < 3; x++) w[x] = sa[x] - sb[x];      /* support of A - B along -v */
         if (it > 0) {
             double vv = dot3(v, v);
             if (vv - dot3(v, w) <= 1e-13 * vv) break;          /* no vertex of A - B is closer: v is the closest point */
@@ -645,6 +647,54 @@ static double gjk_distance(const orc_convex* A, const double* bc, const double* 
     }
     if (iters_out) *iters_out = it;
     return sqrt(dot3(v, v));
+}
+
+/* shape A against an axis-aligned box (centre bc, half extents bh; bh = 0: a point) */
+static double gjk_distance(const orc_convex* A, const double* bc, const double* bh, int* iters_out) {
+    static const double eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    orc_convex B = {ORC_SHAPE_BOX, bh, 0, 0, eye, bc};
+    return gjk_pair(A, &B, iters_out);
+}
+
+/* core + radius of model shape s posed by (Rs, ps): sphere = point, capsule = segment (a box with two zero
+ * half extents), box, hull (radius = margin) */
+static double shape_core(const orc_model* m, int s, const double* Rs, const double* ps, double* half, orc_convex* out) {
+    int t = m->s_type[s];
+    double radius = 0;
+    half[0] = half[1] = half[2] = 0;
+    out->type = ORC_SHAPE_BOX; out->dim = half; out->verts = 0; out->nv = 0; out->R = Rs; out->p = ps;
+    if (t == ORC_SHAPE_SPHERE) radius = m->s_dim[s][0];
+    else if (t == ORC_SHAPE_CAPSULE) { half[2] = m->s_dim[s][1]; radius = m->s_dim[s][0]; }
+    else if (t == ORC_SHAPE_BOX) { for (int a = 0; a < 3; a++) half[a] = m->s_dim[s][a]; }
+    else { out->type = ORC_SHAPE_HULL; out->verts = m->verts + m->s_v0[s]; out->nv = m->s_vn[s]; radius = m->s_dim[s][0]; }
+    return radius;
+}
+
+/* environment.py:394-412 + collision_detector.py:63-98: closest distance between every pair of links (min over
+ * their shape pairs, saturated at 10); adjacent links and the diagonal are not queried by the reference: 10 */
+void orc_self_distances(const orc_model* m, const double* q, double* out /*[nl][nl]*/) {
+    double Rw[ORC_MAXL * 9], pw[ORC_MAXL * 3];
+    double Rs[ORC_MAXS][9], ps[ORC_MAXS][3];
+    int nl = m->nl;
+    orc_fk(m, q, Rw, pw);
+    for (int s = 0; s < m->ns; s++) {
+        int l = m->s_link[s];
+        double t[3];
+        m3m(Rw + 9 * l, m->s_R[s], Rs[s]);
+        m3v(Rw + 9 * l, m->s_p[s], t);
+        for (int a = 0; a < 3; a++) ps[s][a] = pw[3 * l + a] + t[a];
+    }
+    for (int i = 0; i < nl * nl; i++) out[i] = 10.0;
+    for (int sa = 0; sa < m->ns; sa++)
+        for (int sb = sa + 1; sb < m->ns; sb++) {
+            int i = m->s_link[sa], j = m->s_link[sb];
+            if (i == j || i == j + 1 || j == i + 1) continue;
+            double ha[3], hb[3];
+            orc_convex A, B;
+            double ra = shape_core(m, sa, Rs[sa], ps[sa], ha, &A), rb = shape_core(m, sb, Rs[sb], ps[sb], hb, &B);
+            double d = gjk_pair(&A, &B, 0) - ra - rb;
+            if (d < out[i * nl + j]) out[i * nl + j] = out[j * nl + i] = d;
+        }
 }
 
 double orc_gjk_hull_box(const double* verts, int nv, const double* R, const double* p, const double* bc,

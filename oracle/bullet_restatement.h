@@ -96,6 +96,8 @@ void orc_observe(const orc_model* m, const double* q, const double* qd, const do
  * (centre bc, half extents bh; bh = 0 -> a point); 0 when they overlap */
 double orc_gjk_hull_box(const double* verts /*[nv][3]*/, int nv, const double* R, const double* p,
                         const double* bc, const double* bh, int* iters_out);
+/* link <-> link closest distances, [nl][nl] (10 on the diagonal, for adjacent links and for links without shapes) */
+void orc_self_distances(const orc_model* m, const double* q, double* out);
 /* batched helpers (OpenMP over envs); q, qd are [n][nl] */
 void orc_batch_step(const orc_model* m, const orc_motors* mot_template, const int* act_joint, int n_act,
                     int n, double* q, double* qd, const double* actions /*[n][n_act]*/, double max_force,

@@ -103,6 +103,7 @@ SIGNATURES = {
     'rloa_sim_begin_reset_random': (C.c_int, [_VP, _fp, _fp, _fp, _I, _I, _U64, _fp, _VP]),
     'rloa_sim_reset': (C.c_int, [_VP, _fp, _fp, _I, _I, _fp, _VP]),
     'rloa_sim_observe': (C.c_int, [_VP, _fp, _fp, _fp, _VP]),
+    'rloa_sim_self_distances': (C.c_int, [_VP, _fp, _VP]),
     'rloa_sim_last_iterations': (C.c_int, [_VP, _fp, _VP]),
     'rloa_episode_update': (C.c_int, [_I, _I, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _I, _fp, _fp, _fp, _VP]),
     'rloa_episode_update_reset': (C.c_int, [_VP, _I, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _I, _fp, _fp, _fp,

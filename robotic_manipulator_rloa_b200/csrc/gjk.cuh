@@ -101,16 +101,30 @@ __device__ __forceinline__ bool gjk_simplex_closest(V3* P, int& n, V3& v) {
     return false;
 }
 
-// distance between shape A and the axis-aligned box (centre bc, half extents bh; bh = 0: a point); 0 on overlap
-__device__ __noinline__ float gjk_distance(const GjkShape& A, V3 bc, V3 bh) {
+// support mapping of the second shape: an axis-aligned box / point (obstacle sphere centre, target cube) ...
+struct GjkAabb {
+    V3 c, h;
+    __device__ __forceinline__ V3 operator()(V3 d) const {
+        return v3(c.x + (d.x >= 0.f ? h.x : -h.x), c.y + (d.y >= 0.f ? h.y : -h.y), c.z + (d.z >= 0.f ? h.z : -h.z));
+    }
+    __device__ __forceinline__ V3 centre() const { return c; }
+};
+// ... or another posed shape (link vs link)
+struct GjkPosed {
+    const GjkShape& S;
+    __device__ __forceinline__ V3 operator()(V3 d) const { return gjk_support(S, d); }
+    __device__ __forceinline__ V3 centre() const { return S.p; }
+};
+
+// distance between the cores of shape A and shape B (given by its support mapping); 0 on overlap
+template <class SupportB>
+__device__ __forceinline__ float gjk_run(const GjkShape& A, const SupportB& B) {
     V3 P[4];
     int n = 0;
-    V3 v = A.p - bc;
+    V3 v = A.p - B.centre();
     if (dot(v, v) < 1e-20f) v = v3(1.f, 0.f, 0.f);
     for (int it = 0; it < 32; it++) {
-        const V3 sa = gjk_support(A, v3(-v.x, -v.y, -v.z));
-        const V3 w = sa - v3(bc.x + (v.x >= 0.f ? bh.x : -bh.x), bc.y + (v.y >= 0.f ? bh.y : -bh.y),
-                             bc.z + (v.z >= 0.f ? bh.z : -bh.z));
+        const V3 w = gjk_support(A, v3(-v.x, -v.y, -v.z)) - B(v);      // support of A - B along -v
         if (it > 0) {
             const float vv = dot(v, v);
             if (vv - dot(v, w) <= 2e-6f * vv) break;      // no vertex of A - B is closer: v is the closest point
@@ -123,3 +137,8 @@ __device__ __noinline__ float gjk_distance(const GjkShape& A, V3 bc, V3 bh) {
     }
     return sqrtf(dot(v, v));
 }
+
+// shape A against the axis-aligned box (centre bc, half extents bh; bh = 0: a point)
+__device__ __noinline__ float gjk_distance(const GjkShape& A, V3 bc, V3 bh) { return gjk_run(A, GjkAabb{bc, bh}); }
+// shape A against shape B
+__device__ __noinline__ float gjk_distance_pair(const GjkShape& A, const GjkShape& B) { return gjk_run(A, GjkPosed{B}); }

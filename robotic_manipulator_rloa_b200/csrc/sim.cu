@@ -341,6 +341,69 @@ sim_observe_kernel(const __grid_constant__ ModelDev M, SimArrays S, float* __res
     if (ee_target != nullptr) ee_target[env] = o.ee_target;
 }
 
+// get_manipulator_collisions_with_itself (environment.py:394-412, collision_detector.py:63-98): closest distance
+// between every pair of non-adjacent links = min over their shape pairs of GJK(core A, core B) - radius A - radius B
+// (sphere core = point, capsule core = segment, hull radius = margin); thread = arm.  Not on the step path.
+template <int NLMAX>
+__global__ void __launch_bounds__(kTpb)
+sim_self_distances_kernel(const __grid_constant__ ModelDev M, SimArrays S, float* __restrict__ out) {
+    const int env = blockIdx.x * kTpb + threadIdx.x;
+    const int N = S.n_envs, nl = M.nl;
+    if (env >= N) return;
+    float Rw[NLMAX * 9], pw[NLMAX * 3];
+    for (int i = 0; i < nl; i++) {
+        const int par = M.parent[i];
+        M3 Rl;
+        V3 pl, dd;
+        joint_transform(M, i, S.q[(size_t)i * N + env], Rl, pl, dd);
+        M3 R = Rl;
+        V3 p = pl;
+        if (par >= 0) {
+            M3 Rp;
+#pragma unroll
+            for (int k = 0; k < 9; k++) Rp.m[k] = Rw[par * 9 + k];
+            p = ld3(pw + par * 3) + mul(Rp, pl);
+            R = mul(Rp, Rl);
+        }
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rw[i * 9 + k] = R.m[k];
+        st3(pw + i * 3, p);
+    }
+    float* o = out + (size_t)env * nl * nl;
+    for (int k = 0; k < nl * nl; k++) o[k] = 10.f;
+    auto posed = [&](int s, GjkShape& A) -> float {      // returns the radius around the core
+        const int l = M.s_link[s], t = M.s_type[s];
+        M3 Rl, sR;
+#pragma unroll
+        for (int k = 0; k < 9; k++) { Rl.m[k] = Rw[l * 9 + k]; sR.m[k] = M.s_R[s][k]; }
+        A.R = mul(Rl, sR);
+        A.p = ld3(pw + l * 3) + mul(Rl, v3(M.s_p[s][0], M.s_p[s][1], M.s_p[s][2]));
+        A.verts = nullptr;
+        A.nv = 0;
+        A.half = v3(0.f, 0.f, 0.f);
+        if (t == RLOA_SHAPE_SPHERE) return M.s_dim[s][0];
+        if (t == RLOA_SHAPE_CAPSULE) { A.half.z = M.s_dim[s][1]; return M.s_dim[s][0]; }
+        if (t == RLOA_SHAPE_BOX) { A.half = v3(M.s_dim[s][0], M.s_dim[s][1], M.s_dim[s][2]); return 0.f; }
+        A.verts = M.verts + M.s_v0[s];
+        A.nv = M.s_vn[s];
+        return M.s_dim[s][0];
+    };
+    const int ns = M.ns;
+    for (int sa = 0; sa < ns; sa++) {
+        GjkShape A;
+        const float ra = posed(sa, A);
+        const int i = M.s_link[sa];
+        for (int sb = sa + 1; sb < ns; sb++) {
+            const int j = M.s_link[sb];
+            if (i == j || i == j + 1 || j == i + 1) continue;
+            GjkShape B;
+            const float rb = posed(sb, B);
+            const float d = gjk_distance_pair(A, B) - ra - rb;
+            if (d < o[i * nl + j]) { o[i * nl + j] = d; o[j * nl + i] = d; }
+        }
+    }
+}
+
 // lock-step asynchronous Environment.reset: arm the POSITION_CONTROL motors of the masked envs and let
 // the next n_substeps step launches run their reset sub-steps (environment.py:295-301)
 __global__ void sim_begin_reset_kernel(SimArrays S, const uint8_t* __restrict__ mask,
@@ -981,6 +1044,16 @@ extern "C" int rloa_sim_observe(const rloa_sim* s, float* obs, float* link_obsta
         else sim_observe_kernel<32, true><<<blocks, kTpb, 0, as_stream(stream)>>>(h, s->a, obs, link_obstacle, ee_target);
     } else if (h.nl <= 16) sim_observe_kernel<16, false><<<blocks, kTpb, 0, as_stream(stream)>>>(h, s->a, obs, link_obstacle, ee_target);
     else sim_observe_kernel<32, false><<<blocks, kTpb, 0, as_stream(stream)>>>(h, s->a, obs, link_obstacle, ee_target);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
+extern "C" int rloa_sim_self_distances(const rloa_sim* s, float* link_link, void* stream) {
+    RLOA_REQUIRE(s != nullptr && link_link != nullptr, "rloa_sim_self_distances: null argument");
+    const ModelDev& h = s->model->host;
+    const unsigned blocks = (unsigned)((s->a.n_envs + kTpb - 1) / kTpb);
+    if (h.nl <= 16) sim_self_distances_kernel<16><<<blocks, kTpb, 0, as_stream(stream)>>>(h, s->a, link_link);
+    else sim_self_distances_kernel<32><<<blocks, kTpb, 0, as_stream(stream)>>>(h, s->a, link_link);
     RLOA_LAUNCHED();
     return RLOA_OK;
 }

@@ -215,8 +215,19 @@ class Environment:
         return bool((link_obstacle[0] < threshold).any().item())
 
     def get_manipulator_collisions_with_itself(self) -> dict:
-        raise NotImplementedError('self-collision queries are out of scope of the B200 hot path '
-                                  '(Environment.step never enables consider_autocollision)')
+        """``{'joint_i': distances from link i to every link except i-1, i, i+1}`` like the reference
+        (environment.py:394-412); arrays are [k] for one env and [n_envs][k] tensors for a batch."""
+        d = self.sim.self_distances()
+        nl = self.num_joints
+        out = {}
+        for i in range(nl):
+            others = [j for j in range(nl) if abs(j - i) > 1]
+            sel = d[:, i, others]
+            out[f'joint_{i}'] = sel[0].cpu().numpy().astype(float) if self.n_envs == 1 else sel
+        return out
+
+    def _self_collision(self) -> bool:
+        return any(bool((v < 0).any()) for v in self.get_manipulator_collisions_with_itself().values())
 
     def get_endeffector_target_collision(self, threshold: float) -> Tuple[bool, NDArray]:
         ee = CollisionObject(body=self.sim, link=self.endeffector_index)
@@ -225,23 +236,23 @@ class Environment:
 
     def is_terminal_state(self, target_threshold: float = 0.05, obstacle_threshold: float = 0.,
                           consider_autocollision: bool = False) -> int:
-        if consider_autocollision:
-            self.get_manipulator_collisions_with_itself()
         if self.get_manipulator_obstacle_collisions(threshold=obstacle_threshold):
             logger.info('Collision detected, terminating episode...')
             return 1
         if self.get_endeffector_target_collision(threshold=target_threshold)[0]:
             logger.info('The goal state has been reached, terminating episode...')
             return 1
+        if consider_autocollision and self._self_collision():
+            logger.info('Auto-Collision detected, terminating episode...')
+            return 1
         return 0
 
     def get_reward(self, consider_autocollision: bool = False) -> float:
-        if consider_autocollision:
-            self.get_manipulator_collisions_with_itself()
+        self_collision = consider_autocollision and self._self_collision()
         hit_target, dist = self.get_endeffector_target_collision(threshold=0.05)
         if hit_target:
             return 250
-        if self.get_manipulator_obstacle_collisions(threshold=0):
+        if self.get_manipulator_obstacle_collisions(threshold=0) or self_collision:
             return -1000
         return -1 * float(dist[0])
 

@@ -168,6 +168,12 @@ class BatchedSimulator:
                 'rloa_sim_observe')
         return obs, link, ee
 
+    def self_distances(self) -> torch.Tensor:
+        """[n_envs][nl][nl] link-link closest distances (10 on the diagonal / adjacent links / shapeless links)."""
+        out = torch.empty(self.n_envs, self.nl, self.nl, dtype=torch.float32, device=self.device)
+        N.check(self.lib.rloa_sim_self_distances(self._h_sim, out.data_ptr(), self._stream()), 'rloa_sim_self_distances')
+        return out
+
     def last_iterations(self) -> torch.Tensor:
         it = torch.empty(self.n_envs, dtype=torch.int32, device=self.device)
         N.check(self.lib.rloa_sim_last_iterations(self._h_sim, it.data_ptr(), self._stream()), 'rloa_sim_last_iterations')

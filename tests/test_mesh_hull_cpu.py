@@ -167,3 +167,38 @@ def test_hullified_kuka_tracks_the_primitive_model():
         sep = lp > -0.075                       # the overlap bound replaces the depth when the centre is inside
         assert np.all(lh[sep] >= lp[sep] - 1e-9) and np.all(lh[sep] <= lp[sep] + 0.02)
         assert eh >= ep - 1e-9 and eh <= ep + 0.02
+
+
+# ---- link-link distances (get_manipulator_collisions_with_itself) ---------------------------
+def _segment_segment(p1, q1, p2, q2):
+    f = lambda x: np.sum((p1 + x[0] * (q1 - p1) - p2 - x[1] * (q2 - p2)) ** 2)
+    starts = ([.5, .5], [0, 0], [1, 1], [0, 1], [1, 0])
+    return np.sqrt(min(minimize(f, x0, bounds=[(0, 1), (0, 1)], method='L-BFGS-B',
+                                options={'ftol': 1e-18, 'gtol': 1e-14}).fun for x0 in starts))
+
+
+def test_oracle_self_distances_structure_and_capsule_pairs():
+    cfg = KUKA
+    model, orc = make_oracle(cfg)
+    q, _ = random_states(model, 30, seed=3)
+    nl = model.nl
+    separated = 0
+    for e in range(30):
+        D = orc.self_distances(q[e])
+        assert np.array_equal(D, D.T)
+        for i in range(nl):
+            assert D[i, i] == 10.0 and (i == 0 or D[i, i - 1] == 10.0)
+        Rw, pw = orc.fk(q[e])
+
+        def seg(s):
+            l = model.s_link[s]
+            R = Rw[l] @ model.s_R[s].reshape(3, 3)
+            p = pw[l] + Rw[l] @ model.s_p[s]
+            return p - model.s_dim[s][1] * R[:, 2], p + model.s_dim[s][1] * R[:, 2], model.s_dim[s][0]
+        for a, b in [(0, 2), (0, 3), (1, 4), (2, 5), (0, 5), (1, 3)]:        # links 0-5 carry one capsule each
+            a0, a1, ra = seg(a)
+            b0, b1, rb = seg(b)
+            core = _segment_segment(a0, a1, b0, b1)
+            separated += core > 1e-3
+            assert abs(D[a, b] - (core - ra - rb)) <= 1e-7
+    assert separated > 100

@@ -143,3 +143,54 @@ def test_urdf_with_mesh_files_end_to_end(tmp_path):
     for e in range(0, n, 4):
         lo, eet, _ = orc.distances(q32[e], ob[e], tg[e])
         assert np.abs(lm[e] - lo).max() <= 2e-5 and abs(em[e] - eet) <= 2e-5
+
+
+# ---- link-link distances (get_manipulator_collisions_with_itself) ------------------------------------------------
+@pytest.mark.parametrize('meshed', [False, True], ids=['primitives', 'hulls'])
+def test_self_distances_match_oracle(meshed):
+    cfg = KUKA
+    model, orc = make_oracle(cfg)
+    if meshed:
+        model = hullified(model, n=24)
+        orc = BulletOracle(model, cfg['ee'], len(cfg['involved']))
+    n = 256
+    q, qd = random_states(model, n, seed=61)
+    sim = make_sim(model, cfg, n)
+    sim.set_state(q, qd)
+    got = sim.self_distances().cpu().numpy()
+    q32 = q.astype(np.float32).astype(np.float64)
+    worst = 0.0
+    for e in range(n):
+        want = orc.self_distances(q32[e])
+        assert np.array_equal(got[e] == 10.0, want == 10.0)
+        worst = max(worst, np.abs(got[e] - want).max())
+    print(f'self distances ({"hulls" if meshed else "primitives"}): max err {worst:.2e}')
+    assert worst <= 2e-5
+
+
+def test_environment_autocollision_api():
+    """get_manipulator_collisions_with_itself / consider_autocollision through the drop-in Environment (reference
+    environment.py:311-371, 394-412)."""
+    from robotic_manipulator_rloa_b200.environment.environment import Environment, EnvironmentConfiguration
+    cfg = KUKA
+    env = Environment(cfg['file'], EnvironmentConfiguration(
+        endeffector_index=cfg['ee'], fixed_joints=cfg['fixed'], involved_joints=cfg['involved'],
+        target_position=cfg['target'], obstacle_position=cfg['obstacle'], initial_joint_positions=cfg['start'],
+        initial_positions_variation_range=[0] * 6, max_force=200., visualize=False))
+    env.reset(verbose=False)
+    d = env.get_manipulator_collisions_with_itself()
+    nl = env.num_joints
+    assert sorted(d) == sorted(f'joint_{i}' for i in range(nl))
+    for i in range(nl):
+        assert d[f'joint_{i}'].shape == (len([j for j in range(nl) if abs(j - i) > 1]),)
+    _, orc = make_oracle(cfg)
+    q, _ = env.sim.get_state()
+    want = orc.self_distances(q[0].double().cpu().numpy())
+    for i in range(nl):
+        others = [j for j in range(nl) if abs(j - i) > 1]
+        assert np.abs(d[f'joint_{i}'] - want[i, others]).max() <= 2e-5
+    hit = any((v < 0).any() for v in d.values())
+    base_r, base_t = env.get_reward(), env.is_terminal_state()
+    assert env.get_reward(consider_autocollision=True) == (-1000 if hit and base_r != 250 else base_r)
+    assert env.is_terminal_state(consider_autocollision=True) == (1 if hit else base_t)
+    env.close()
