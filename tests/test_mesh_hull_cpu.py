@@ -202,3 +202,35 @@ def test_oracle_self_distances_structure_and_capsule_pairs():
             separated += core > 1e-3
             assert abs(D[a, b] - (core - ra - rb)) <= 1e-7
     assert separated > 100
+
+
+def test_sdf_mesh_element_with_uri_and_scale(tmp_path):
+    """The shipped KUKA SDF with its gripper-base <box> swapped for a unit-cube mesh + <scale>: same model otherwise,
+    the box becomes an 8-vertex hull with the box's half extents, and the oracle distances move by the margin."""
+    import os
+    import shutil
+    from robotic_manipulator_rloa_b200.environment.robot_model import DATA_PATH, load_sdf
+    src = os.path.join(DATA_PATH, 'kuka_iiwa', 'kuka_with_gripper2.sdf')
+    text = open(src).read()
+    box = '<geometry><box><size>0.05 0.1 0.04</size></box></geometry>'
+    assert text.count(box) == 1
+    text = text.replace(box, '<geometry><mesh><uri>model://kuka/meshes/cube.obj</uri><scale>0.05 0.1 0.04</scale></mesh></geometry>')
+    (tmp_path / 'meshes').mkdir()
+    write_box_mesh(str(tmp_path / 'meshes' / 'cube.obj'), (0.5, 0.5, 0.5), 'obj')
+    (tmp_path / 'kuka.sdf').write_text(text)
+    prim, mesh = load_sdf(src), load_sdf(str(tmp_path / 'kuka.sdf'))
+    s = int(np.flatnonzero(prim.s_type == SHAPE_BOX)[0])
+    assert mesh.s_type[s] == SHAPE_HULL and mesh.s_vn[s] == 8 and mesh.verts.shape == (8, 3)
+    assert np.allclose(np.abs(mesh.verts).max(axis=0), prim.s_dim[s])
+    keep = np.arange(prim.ns) != s
+    assert np.array_equal(mesh.s_type[keep], prim.s_type[keep]) and np.allclose(mesh.E0, prim.E0)
+    op, om = bo.BulletOracle(prim, 13, 6), bo.BulletOracle(mesh, 13, 6)
+    q, _ = random_states(prim, 50, seed=9)
+    link = int(prim.s_link[s])
+    for e in range(50):
+        lp, ep, _ = op.distances(q[e], KUKA['obstacle'], KUKA['target'])
+        lm, em, _ = om.distances(q[e], KUKA['obstacle'], KUKA['target'])
+        other = np.arange(prim.nl) != link
+        assert np.array_equal(lp[other], lm[other]) and ep == em
+        if lp[link] > -0.075:
+            assert abs(lm[link] + mesh_io.HULL_MARGIN - lp[link]) <= 1e-9
