@@ -100,6 +100,7 @@ class NAFAgent:
                                    action_size if self.device.type == 'cuda' else None, max_append=n_envs)
         self.update_t_step = 0
         self._act_calls = 0
+        self._tick_base = 0                         # where the next loop's device counter starts (resume)
         self._ws: Optional[NafWorkspace] = None
         self._bufs = None
         self.last_loss = None
@@ -177,6 +178,38 @@ class NAFAgent:
 
     def _cpu_state_dict(self):
         return {k: v.detach().cpu() for k, v in self.qnetwork_main.state_dict().items()}
+
+    # ------------------------------------------------------------------------------------------
+    # true resume (an addition; the reference's checkpoints hold the main network's weights only — SURVEY.md
+    # section 5: "Not saved: optimizer state, replay buffer, target net, RNG, episode counter")
+    def save_training_state(self, path: str) -> None:
+        """Everything ``learn`` / ``act`` depend on: both networks, the Adam moments and step, the replay ring, the
+        update gate and the counters that key the device RNG streams."""
+        self._require_cuda()
+        cpu = lambda sd: {k: v.detach().cpu() for k, v in sd.items()}
+        torch.save({'format': 1, 'state_size': self.state_size, 'action_size': self.action_size,
+                    'layer_size': self.layer_size, 'seed': self.seed,
+                    'main': cpu(self.qnetwork_main.state_dict()), 'target': cpu(self.qnetwork_target.state_dict()),
+                    'adam': {'exp_avg': self.optimizer.exp_avg.cpu(), 'exp_avg_sq': self.optimizer.exp_avg_sq.cpu(),
+                             'step': int(self.optimizer.step_count.item())},
+                    'replay': self.memory.state_dict(), 'update_t_step': self.update_t_step,
+                    'act_calls': self._act_calls, 'tick_base': self._tick_base}, path)
+
+    def load_training_state(self, path: str) -> None:
+        self._require_cuda()
+        if not os.path.isfile(path):
+            raise MissingWeightsFile
+        sd = torch.load(path, map_location='cpu')
+        if (sd['state_size'], sd['action_size'], sd['layer_size']) != (self.state_size, self.action_size, self.layer_size):
+            raise ValueError('training state was saved for a different network shape')
+        self.qnetwork_main.load_state_dict(sd['main'])
+        self.qnetwork_target.load_state_dict(sd['target'])
+        self.optimizer.exp_avg.copy_(sd['adam']['exp_avg'])
+        self.optimizer.exp_avg_sq.copy_(sd['adam']['exp_avg_sq'])
+        self.optimizer.step_count.fill_(int(sd['adam']['step']))
+        self.memory.load_state_dict(sd['replay'])
+        self.update_t_step, self._act_calls = int(sd['update_t_step']), int(sd['act_calls'])
+        self._tick_base = int(sd['tick_base'])
 
     # ------------------------------------------------------------------------------------------
     def act_batch(self, states: torch.Tensor, out: Optional[torch.Tensor] = None,
@@ -346,6 +379,7 @@ class NAFAgent:
             if completed < episodes and n == 1:
                 logger.info(f'Running Episode {completed + 1}')
                 loop.reset_all(verbose)
+        self._tick_base = int(loop.tick.item())      # a later run() / a resumed agent continues the RNG streams
         torch.save(self._cpu_state_dict(), self.MODEL_PATH)
         logger.info(f'Model has been successfully saved in {self.MODEL_PATH}')
         return scores
@@ -381,7 +415,7 @@ class VectorLoop:
         self.log_env = torch.zeros(self.cap, **i32)
         self.log_count = torch.zeros(1, **i32)
         self.transitions = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.tick = torch.zeros(1, dtype=torch.int64, device=dev)      # device loop counter (uint64 bits)
+        self.tick = torch.full((1,), int(agent._tick_base), dtype=torch.int64, device=dev)   # device loop counter (uint64 bits)
         self.lib = N.lib()
         self.phase_events = None        # optional [6 events] x 2 iterations: act | sim | append | learn | tail
         self._graph = None              # CUDA graph of two consecutive iterations

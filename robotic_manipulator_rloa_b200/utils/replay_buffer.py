@@ -119,3 +119,31 @@ class ReplayBuffer:
 
     def __len__(self) -> int:
         return self._len
+
+    # ---- resume (an addition: the reference does not persist its deque) ------------------------------
+    def state_dict(self) -> dict:
+        """Live rows, write cursor and draw counter as CPU tensors (NAFAgent.save_training_state)."""
+        if self._rb is None:
+            return {'allocated': False, 'draws': self._draws}
+        n = self.sync_len()
+        rows = lambda t: t[:n].detach().cpu()
+        return {'allocated': True, 'state_size': self.state_size, 'action_size': self.action_size,
+                'buffer_size': self.buffer_size, 'len': n, 'cursor': int(self.cursor.item()), 'draws': self._draws,
+                'states': rows(self.states), 'next_states': rows(self.next_states), 'actions': rows(self.actions),
+                'rewards': rows(self.rewards), 'dones': rows(self.dones)}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self._draws = int(sd['draws'])
+        if not sd['allocated']:
+            return
+        if int(sd['buffer_size']) != self.buffer_size:
+            raise ValueError(f"replay capacity mismatch: saved {sd['buffer_size']}, this buffer {self.buffer_size}")
+        if self._rb is None:
+            self._allocate(int(sd['state_size']), int(sd['action_size']))
+        if (self.state_size, self.action_size) != (int(sd['state_size']), int(sd['action_size'])):
+            raise ValueError('replay row layout mismatch')
+        n = int(sd['len'])
+        for name in ('states', 'next_states', 'actions', 'rewards', 'dones'):
+            getattr(self, name)[:n].copy_(sd[name].to(self.device))
+        self.cursor.fill_(int(sd['cursor']))
+        self._len = n

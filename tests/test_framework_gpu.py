@@ -204,3 +204,49 @@ def test_config4_rollouts_with_per_env_targets():
     mf.test_trained_model(n + 100, 60)                        # two waves
     res = mf.last_test_results
     assert len(res) == n + 100 and all(isinstance(r[0], bool) and 0 <= r[1] <= 59 for r in res)
+
+
+def test_training_state_resume_is_bit_identical(tmp_path):
+    """save_training_state / load_training_state (an addition over the reference's weights-only checkpoints): a fresh
+    agent restored from the file continues appends, samples, updates and noisy actions bit-for-bit."""
+    from robotic_manipulator_rloa_b200.naf_components.naf_algorithm import NAFAgent
+
+    def make():
+        return NAFAgent(None, 21, 6, 256, 64, 1024, 1e-3, 1e-3, 0.99, 1, 1, 500, DEV, seed=0)
+
+    g = torch.Generator().manual_seed(5)
+    chunks = [(torch.randn(300, 21, generator=g).to(DEV), torch.rand(300, 6, generator=g).to(DEV) * 2 - 1,
+               torch.randn(300, generator=g).to(DEV), torch.randn(300, 21, generator=g).to(DEV),
+               (torch.rand(300, generator=g) < 0.05).to(torch.uint8).to(DEV)) for _ in range(6)]
+    probe = torch.randn(128, 21, generator=g).to(DEV)
+
+    def advance(agent, lo, hi):
+        for k in range(lo, hi):
+            agent.memory.add_batch(*chunks[k])                 # 6 x 300 rows wrap the 1024-row ring
+            tick = torch.tensor([k], dtype=torch.int64, device=DEV)
+            agent.learn_from_memory(tick=tick)
+        tick = torch.tensor([hi], dtype=torch.int64, device=DEV)
+        return agent.act_batch(probe, tick=tick).clone()
+
+    straight = make()
+    act_a = advance(straight, 0, 6)
+    first = make()
+    advance(first, 0, 3)
+    path = str(tmp_path / 'resume.p')
+    first.save_training_state(path)
+    resumed = make()
+    resumed.load_training_state(path)
+    act_b = advance(resumed, 3, 6)
+    torch.cuda.synchronize()
+    assert torch.equal(act_a, act_b)
+    for net in ('qnetwork_main', 'qnetwork_target'):
+        sa, sb = getattr(straight, net).state_dict(), getattr(resumed, net).state_dict()
+        assert all(torch.equal(sa[k], sb[k]) for k in sa), net
+    assert torch.equal(straight.optimizer.exp_avg, resumed.optimizer.exp_avg)
+    assert torch.equal(straight.optimizer.exp_avg_sq, resumed.optimizer.exp_avg_sq)
+    assert int(straight.optimizer.step_count.item()) == int(resumed.optimizer.step_count.item()) == 6
+    for name in ('states', 'next_states', 'actions', 'rewards', 'dones', 'cursor'):
+        assert torch.equal(getattr(straight.memory, name), getattr(resumed.memory, name)), name
+    assert len(straight.memory) == len(resumed.memory) == 1024
+    with pytest.raises(ValueError):
+        NAFAgent(None, 23, 7, 256, 64, 1024, 1e-3, 1e-3, 0.99, 1, 1, 500, DEV, seed=0).load_training_state(path)
