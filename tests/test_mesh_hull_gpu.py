@@ -194,3 +194,31 @@ def test_environment_autocollision_api():
     assert env.get_reward(consider_autocollision=True) == (-1000 if hit and base_r != 250 else base_r)
     assert env.is_terminal_state(consider_autocollision=True) == (1 if hit else base_t)
     env.close()
+
+
+def test_cylinder_and_dense_hulls_against_oracle(tmp_path):
+    """Vertex clouds with many coplanar / cocircular points (pybullet's 2 x 32-point cylinders) and a dense 300-point
+    hull: the degenerate simplices GJK meets there must not cost accuracy."""
+    arm = load_urdf(write_test_arm(str(tmp_path), lambda i: '<cylinder radius="%g" length="%g"/>' % (0.03 + 0.01 * i, 0.12 + 0.03 * i)))
+    cfg = dict(ee=2, involved=[0, 1, 2], fixed=[], target=[0.2, 0.1, 0.5], obstacle=[-0.1, 0.2, 0.4])
+    dense = hullified(make_oracle(KUKA)[0], n=300)
+    for model, c, seed in ((arm, cfg, 71), (dense, KUKA, 72)):
+        orc = BulletOracle(model, c['ee'], len(c['involved']))
+        n = 512
+        if model is arm:
+            q = np.random.default_rng(seed).uniform(-2.4, 2.4, (n, 3))
+        else:
+            q, _ = random_states(model, n, seed=seed)
+        ob, tg = spread_tasks(c, n, seed + 10, orc, q)
+        sim = make_sim(model, c, n)
+        sim.set_task(torch.as_tensor(tg, dtype=torch.float32), torch.as_tensor(ob, dtype=torch.float32))
+        sim.set_state(q, np.zeros_like(q))
+        _, link, ee = sim.observe(want_distances=True)
+        link, ee = link.cpu().numpy(), ee.cpu().numpy()
+        q32 = q.astype(np.float32).astype(np.float64)
+        worst = 0.0
+        for e in range(0, n, 2):
+            lo, eet, _ = orc.distances(q32[e], ob[e], tg[e])
+            worst = max(worst, np.abs(link[e] - lo).max(), abs(ee[e] - eet))
+        print(f'{"cylinders" if model is arm else "300-point hulls"}: max distance err {worst:.2e}')
+        assert worst <= 2e-5

@@ -9,6 +9,10 @@ from robotic_manipulator_rloa_b200.environment.simulator import BatchedSimulator
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 model = load_manipulator('kuka_iiwa/kuka_with_gripper2.sdf')
+if len(sys.argv) > 3:       # mesh=<verts>: every collision primitive as a convex vertex cloud (the GJK instantiation)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
+    from helpers import hullified
+    model = hullified(model, n=int(sys.argv[3].split('=')[1]))
 sim = BatchedSimulator(model, n, 13, [0, 1, 2, 3, 4, 5], list(range(6, 14)))
 sim.set_task([0.4, 0.85, 0.71], [0.45, 0.55, 0.55])
 q = torch.zeros(n, model.nl, device='cuda')
