@@ -716,13 +716,17 @@ extern "C" int rloa_model_create(const rloa_model_desc* d, rloa_model** out) {
         for (int k = 0; k < 3; k++) { h.s_p[s][k] = (float)d->s_p[3 * s + k]; h.s_dim[s][k] = (float)d->s_dim[3 * s + k]; }
         const int t = d->s_type[s];
         if (!(t >= RLOA_SHAPE_SPHERE && t <= RLOA_SHAPE_HULL)) { delete m; return fail(RLOA_ERR_INVALID, "rloa_model_create: unknown shape type"); }
-        if (t == RLOA_SHAPE_HULL) {
+        // bounding sphere: centre c (shape frame) and radius, then the centre moved to the link frame
+        double c[3] = {0, 0, 0}, rb = 0;
+        if (t == RLOA_SHAPE_SPHERE) rb = d->s_dim[3 * s];
+        else if (t == RLOA_SHAPE_CAPSULE) rb = d->s_dim[3 * s] + d->s_dim[3 * s + 1];
+        else if (t == RLOA_SHAPE_BOX) rb = std::sqrt(d->s_dim[3 * s] * d->s_dim[3 * s] + d->s_dim[3 * s + 1] * d->s_dim[3 * s + 1] + d->s_dim[3 * s + 2] * d->s_dim[3 * s + 2]);
+        else {
             const int v0 = d->n_verts ? d->s_vert_first[s] : 0, vn = d->n_verts ? d->s_vert_count[s] : 0;
             if (!(vn >= 1 && v0 >= 0 && v0 + vn <= d->n_verts)) { delete m; return fail(RLOA_ERR_INVALID, "rloa_model_create: hull shape without vertices / vertex range out of bounds"); }
             h.s_v0[s] = v0;
             h.s_vn[s] = vn;
-            // bounding sphere in the shape frame (centre = box centre of the cloud): the broad phase of the obstacle query
-            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, c[3], r2 = 0;
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, r2 = 0;
             for (int i = v0; i < v0 + vn; i++)
                 for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], d->verts[3 * i + k]); hi[k] = std::max(hi[k], d->verts[3 * i + k]); }
             for (int k = 0; k < 3; k++) c[k] = 0.5 * (lo[k] + hi[k]);
@@ -731,10 +735,12 @@ extern "C" int rloa_model_create(const rloa_model_desc* d, rloa_model** out) {
                 for (int k = 0; k < 3; k++) q += (d->verts[3 * i + k] - c[k]) * (d->verts[3 * i + k] - c[k]);
                 r2 = std::max(r2, q);
             }
-            for (int k = 0; k < 3; k++) h.s_bs[s][k] = (float)c[k];
-            h.s_bs[s][3] = (float)(std::sqrt(r2) * (1.0 + 1e-6) + 1e-7);
+            rb = std::sqrt(r2) + d->s_dim[3 * s];         // + the collision margin
             h.use_gjk = 1;
         }
+        for (int k = 0; k < 3; k++)
+            h.s_bs[s][k] = (float)(d->s_p[3 * s + k] + d->s_R[9 * s + 3 * k] * c[0] + d->s_R[9 * s + 3 * k + 1] * c[1] + d->s_R[9 * s + 3 * k + 2] * c[2]);
+        h.s_bs[s][3] = (float)(rb * (1.0 + 1e-5) + 1e-6);
         if (t == RLOA_SHAPE_BOX && d->s_link[s] == d->ee_link) h.use_gjk = 1;   // box vs target cube needs the narrow phase
     }
     int ndev = 0;

@@ -58,9 +58,10 @@ struct ModelDev {
     float mass[kMaxLinks], inertia[kMaxLinks][3], damping[kMaxLinks], lower[kMaxLinks], upper[kMaxLinks];
     int s_link[kMaxShapes], s_type[kMaxShapes];
     float s_R[kMaxShapes][9], s_p[kMaxShapes][3], s_dim[kMaxShapes][3];
-    // convex-hull shapes (mesh / cylinder collision geometry): vertex range in verts, bounding sphere in the shape frame
-    int s_v0[kMaxShapes], s_vn[kMaxShapes];
+    // bounding sphere of every shape: centre in the LINK frame, radius (margins / radii included, rounded up)
     float s_bs[kMaxShapes][4];
+    // convex-hull shapes (mesh / cylinder collision geometry): vertex range in verts
+    int s_v0[kMaxShapes], s_vn[kMaxShapes];
     const float4* verts;                 // device, owned by rloa_model; xyz = vertex in the shape frame
     int use_gjk;                         // the model has hull shapes or box shapes on the end-effector link
     int pad2;
@@ -276,15 +277,25 @@ __device__ __forceinline__ ObsOut fk_and_distances(const ModelDev& M, const floa
         for (int i = 0; i < nl; i++) link_dist[i * ld_stride] = 10.f;
     const int ns = M.ns;
     const V3 th = v3(M.target_half[0], M.target_half[1], M.target_half[2]);
+    const float reach = M.obstacle_radius + fmaxf(obstacle_thr, 0.f);
     for (int s = 0; s < ns; s++) {
         const int l = M.s_link[s];
         M3 Rl, sR;
 #pragma unroll
-        for (int k = 0; k < 9; k++) {
-            Rl.m[k] = Rw[l * 9 + k];
-            sR.m[k] = M.s_R[s][k];
-        }
+        for (int k = 0; k < 9; k++) Rl.m[k] = Rw[l * 9 + k];
         const V3 pl = ld3(pw + l * 3);
+        // broad phase, exact for the decision the step consumes (d < threshold): the shape lies inside its bounding
+        // sphere (centre given in the link frame), so a sphere that far from the obstacle cannot be a hit
+        // (SURVEY.md 7.3-4).  The diagnostics path (link_dist) and the end-effector link keep the narrow phase.
+        bool far = false;
+        if (link_dist == nullptr) {
+            const V3 rel = obstacle - (pl + mul(Rl, v3(M.s_bs[s][0], M.s_bs[s][1], M.s_bs[s][2])));
+            const float rr = M.s_bs[s][3] + reach;
+            far = dot(rel, rel) >= rr * rr;
+            if (far && l != M.ee_link) continue;
+        }
+#pragma unroll
+        for (int k = 0; k < 9; k++) sR.m[k] = M.s_R[s][k];
         const V3 sp = v3(M.s_p[s][0], M.s_p[s][1], M.s_p[s][2]);
         const V3 dim = v3(M.s_dim[s][0], M.s_dim[s][1], M.s_dim[s][2]);
         const int type = M.s_type[s];
@@ -292,7 +303,9 @@ __device__ __forceinline__ ObsOut fk_and_distances(const ModelDev& M, const floa
         const V3 ps = pl + mul(Rl, sp);
         const V3 o_s = mulT(Rs, obstacle - ps);  // obstacle centre in the shape frame
         float dist;
-        if (type == RLOA_SHAPE_SPHERE) {
+        if (far) {
+            dist = reach;                        // any value that is not a hit: d_obst = max(threshold, 0)
+        } else if (type == RLOA_SHAPE_SPHERE) {
             dist = sqrtf(dot(o_s, o_s)) - dim.x;
         } else if (type == RLOA_SHAPE_CAPSULE) {
             const float tz = fminf(fmaxf(o_s.z, -dim.y), dim.y);   // closest point of the local-z segment
@@ -301,15 +314,8 @@ __device__ __forceinline__ ObsOut fk_and_distances(const ModelDev& M, const floa
         } else if (!GJK || type == RLOA_SHAPE_BOX) {
             dist = point_box_signed(o_s, dim);
         } else {
-            // mesh hull: the bounding sphere decides most queries (only d < threshold is consumed on the step path)
-            const V3 bc = o_s - v3(M.s_bs[s][0], M.s_bs[s][1], M.s_bs[s][2]);
-            const float lower = sqrtf(dot(bc, bc)) - M.s_bs[s][3] - dim.x;
-            if (link_dist == nullptr && lower - M.obstacle_radius >= fmaxf(obstacle_thr, 0.f)) {
-                dist = lower;
-            } else {
-                const GjkShape A{M.verts + M.s_v0[s], M.s_vn[s], dim, Rs, ps};
-                dist = gjk_distance(A, obstacle, v3(0.f, 0.f, 0.f)) - dim.x;
-            }
+            const GjkShape A{M.verts + M.s_v0[s], M.s_vn[s], dim, Rs, ps};
+            dist = gjk_distance(A, obstacle, v3(0.f, 0.f, 0.f)) - dim.x;
         }
         const float d_obst = dist - M.obstacle_radius;
         o.hit = o.hit || (d_obst < obstacle_thr);
