@@ -213,13 +213,19 @@ int rloa_episode_update(int32_t n_envs, int32_t frames, const float* reward, con
                         void* stream);
 
 /* rloa_episode_update followed by rloa_sim_begin_reset_random(mask = the envs that just finished) in one
- * launch: the steady-state tail of the vectorised loop (naf_algorithm.py:263-277 + environment.py:284-301). */
+ * launch: the steady-state tail of the vectorised loop (naf_algorithm.py:263-277 + environment.py:284-301).
+ * tick_next (device uint64): NULL or == tick -> *tick is incremented in place, as in rloa_episode_update.
+ * A different pointer -> *tick_next = *tick + 1 and *tick is left alone (a ping-pong pair of counters), so the
+ * readers of *tick on the caller's stream (rloa_replay_sample, ...) may run concurrently: while a rloa_sim_prepare
+ * is in flight the launch then goes behind it on the simulator's side stream and completes no later than
+ * rloa_sim_join / the next rloa_sim_step; its outputs (score, frame, logs, reset_mask, *tick_next) must not be read
+ * before that. */
 int rloa_episode_update_reset(rloa_sim* s, int32_t frames, const float* reward, const uint8_t* done,
                               const uint8_t* active, float* score, int32_t* frame, uint8_t* reset_mask,
                               float* log_score, int32_t* log_frame, float* log_last_reward, int32_t* log_env,
                               int32_t log_capacity, int32_t* log_count, int64_t* transitions, uint64_t* tick,
-                              const float* pos, const float* var, int32_t n_init, int32_t n_substeps,
-                              uint64_t seed, void* stream);
+                              uint64_t* tick_next, const float* pos, const float* var, int32_t n_init,
+                              int32_t n_substeps, uint64_t seed, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * NAF network (naf_components/naf_neural_network.py:8-123).  Parameters live in caller-owned

@@ -107,7 +107,7 @@ SIGNATURES = {
     'rloa_sim_last_iterations': (C.c_int, [_VP, _fp, _VP]),
     'rloa_episode_update': (C.c_int, [_I, _I, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _I, _fp, _fp, _fp, _VP]),
     'rloa_episode_update_reset': (C.c_int, [_VP, _I, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _I, _fp, _fp, _fp,
-                                            _fp, _fp, _I, _I, _U64, _VP]),
+                                            _fp, _fp, _fp, _I, _I, _U64, _VP]),
     'rloa_naf_ws_create': (C.c_int, [_I, _I, _I, _I, C.POINTER(_VP)]),
     'rloa_naf_ws_destroy': (None, [_VP]),
     'rloa_naf_ws_set_trunk': (C.c_int, [_VP, _I]),

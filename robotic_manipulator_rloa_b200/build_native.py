@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
-    cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-cudart', 'static']
+    cmd = [NVCC, '-shared', '-Wno-deprecated-gpu-targets', '-o', LIB] + objs + ['-cudart', 'static']
     subprocess.check_call(cmd)
     return LIB
 

@@ -517,7 +517,8 @@ __global__ void episode_update_reset_kernel(int n, int frames, const float* __re
                                             float* __restrict__ log_score, int* __restrict__ log_frame,
                                             float* __restrict__ log_last, int* __restrict__ log_env, int log_cap,
                                             int* __restrict__ log_count, unsigned long long* __restrict__ transitions,
-                                            unsigned long long* __restrict__ tick, SimArrays S, const float* __restrict__ pos,
+                                            unsigned long long* __restrict__ tick, unsigned long long* __restrict__ tick_next,
+                                            SimArrays S, const float* __restrict__ pos,
                                             const float* __restrict__ var, int n_init, int nsub, float pos_maximp,
                                             unsigned long long seed, unsigned* __restrict__ ticket) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -567,7 +568,9 @@ __global__ void episode_update_reset_kernel(int n, int frames, const float* __re
     }
     __syncthreads();
     if (threadIdx.x == 0 && tick != nullptr) {
-        if (atomicAdd(ticket, 1u) == gridDim.x - 1u) {
+        if (tick_next != nullptr && tick_next != tick) {
+            if (blockIdx.x == 0) *tick_next = t;         // ping-pong counter: *tick is not written, readers may run beside
+        } else if (atomicAdd(ticket, 1u) == gridDim.x - 1u) {
             *ticket = 0u;
             *tick += 1ull;
         }
@@ -1091,18 +1094,23 @@ extern "C" int rloa_episode_update_reset(rloa_sim* s, int32_t frames, const floa
                                          const uint8_t* active, float* score, int32_t* frame, uint8_t* reset_mask,
                                          float* log_score, int32_t* log_frame, float* log_last_reward, int32_t* log_env,
                                          int32_t log_capacity, int32_t* log_count, int64_t* transitions, uint64_t* tick,
-                                         const float* pos, const float* var, int32_t n_init, int32_t n_substeps,
-                                         uint64_t seed, void* stream) {
+                                         uint64_t* tick_next, const float* pos, const float* var, int32_t n_init,
+                                         int32_t n_substeps, uint64_t seed, void* stream) {
     RLOA_REQUIRE(s != nullptr && s->ticket != nullptr, "rloa_episode_update_reset: null sim");
     RLOA_REQUIRE(reward && done && score && frame && reset_mask && log_score && log_frame && log_last_reward &&
                      log_env && log_count, "rloa_episode_update_reset: null argument");
     RLOA_REQUIRE(n_init >= 0 && n_init <= s->a.nl && n_substeps >= 0, "rloa_episode_update_reset: n_init / n_substeps out of range");
     const int n = s->a.n_envs;
-    episode_update_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+    // with a ping-pong counter nothing this kernel writes is read by the caller's stream before rloa_sim_join, so while
+    // a rloa_sim_prepare is in flight it runs behind it on the simulator's side stream (beside the NAF update)
+    const bool beside = tick != nullptr && tick_next != nullptr && tick_next != tick && s->join_pending;
+    cudaStream_t st = beside ? s->side : as_stream(stream);
+    episode_update_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
         n, frames, reward, done, active, score, frame, reset_mask, log_score, log_frame, log_last_reward, log_env,
         log_capacity, log_count, reinterpret_cast<unsigned long long*>(transitions),
-        reinterpret_cast<unsigned long long*>(tick), s->a, pos, var, n_init, n_substeps, 100000.f * s->model->host.dt, seed,
-        s->ticket);
+        reinterpret_cast<unsigned long long*>(tick), reinterpret_cast<unsigned long long*>(tick_next), s->a, pos, var,
+        n_init, n_substeps, 100000.f * s->model->host.dt, seed, s->ticket);
     RLOA_LAUNCHED();
+    if (beside) RLOA_CUDA(cudaEventRecord(s->join_ev, s->side));
     return RLOA_OK;
 }

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import json
+import logging
 import os
 import random
 import time
@@ -344,14 +345,18 @@ class NAFAgent:
         if n == 1:
             logger.info(f'Running Episode {completed + 1}')
         loop.reset_all(verbose)
-        sync_every = 1 if n == 1 else 4
+        sync_every = 1 if n == 1 else (16 if n >= 256 else 4)      # iterations between host reads of the episode log
         it = 0
         while completed < episodes:
             if n == 1 and verbose:
                 logger.info(f'Running frame {int(loop.frame.item()) + 1} in episode {completed + 1}')
                 logger.info(f'Current State: {loop.state[0].cpu().numpy()}')
-            loop.step(auto_reset=(n > 1))
-            it += 1
+            if n == 1:
+                loop.step(auto_reset=False)
+                it += 1
+            else:               # pairs of iterations replay the captured CUDA graph once the loop is in steady state
+                loop.run_steps(sync_every)
+                it += sync_every
             if n == 1 and verbose:
                 logger.info(f'Action chosen for the given state is: {loop.actions[0].cpu().numpy()}')
                 logger.info(f'Reward: {float(loop.reward.item())}\n')
@@ -362,13 +367,15 @@ class NAFAgent:
                 continue
             hi = min(n_done, episodes)
             ls, lf = loop.log_score[completed:hi].cpu().numpy(), loop.log_frame[completed:hi].cpu().numpy()
+            info = logger.isEnabledFor(logging.INFO)
             for k in range(hi - completed):
                 ep = completed + k + 1
                 scores[ep] = (float(ls[k]), int(lf[k]))
-                logger.info(f'Reward:                             {float(ls[k])}')
-                logger.info(f'Number of frames:                   {int(lf[k])}')
-                logger.info(f'Mean of rewards on this episode:    {float(ls[k]) / frames}')
-                logger.info(f'Time taken for this episode:        {round(time.time() - start, 3)} secs\n')
+                if info:
+                    logger.info(f'Reward:                             {float(ls[k])}')
+                    logger.info(f'Number of frames:                   {int(lf[k])}')
+                    logger.info(f'Mean of rewards on this episode:    {float(ls[k]) / frames}')
+                    logger.info(f'Time taken for this episode:        {round(time.time() - start, 3)} secs\n')
                 if ep % self.checkpoint_frequency == 0:
                     os.makedirs(f'checkpoints/{ep}/', exist_ok=True)
                     torch.save(self._cpu_state_dict(), f'checkpoints/{ep}/weights.p')
@@ -415,10 +422,16 @@ class VectorLoop:
         self.log_env = torch.zeros(self.cap, **i32)
         self.log_count = torch.zeros(1, **i32)
         self.transitions = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.tick = torch.full((1,), int(agent._tick_base), dtype=torch.int64, device=dev)   # device loop counter (uint64 bits)
+        # device loop counter (uint64 bits) as a ping-pong pair: iteration p reads _ticks[p] and its bookkeeping kernel
+        # writes _ticks[1 - p] = _ticks[p] + 1, so that kernel can run beside the update that still reads _ticks[p]
+        self._ticks = torch.full((2,), int(agent._tick_base), dtype=torch.int64, device=dev)
+        self._par = 0                   # which counter is current
+        self._odd = 0                   # iterations since the state buffers last matched the captured graph (mod 2)
+        self._graph_par = 0
         self.lib = N.lib()
         self.phase_events = None        # optional [6 events] x 2 iterations: act | sim | append | learn | tail
         self._graph = None              # CUDA graph of two consecutive iterations
+        self._graph_failed = False      # a capture attempt raised: stay on eager launches
         self._graph_learn = False
         self.graph_kernels = 0
         self.graph_error: Optional[str] = None
@@ -426,6 +439,11 @@ class VectorLoop:
         self._host = None               # pinned host buffers bound by bind_host_buffers
         self._copy_stream = None
         self._host_graphs = None
+
+    @property
+    def tick(self) -> torch.Tensor:
+        """The current loop counter (a 1-element view; pass it as `tick=` / read it with .item())."""
+        return self._ticks[self._par:self._par + 1]
 
     def reset_all(self, verbose: bool = False) -> None:
         """Synchronous Environment.reset of every env (50 sub-steps) -> self.state."""
@@ -454,25 +472,39 @@ class VectorLoop:
         a.memory.add_batch(self.state, self.actions, self.reward, self.next_state, self.done,
                            valid=self.valid if auto_reset else None)
         self._mark(parity, 3)
-        if learn_now:
-            for u in range(a.num_updates):
-                a.learn_from_memory(tick=self.tick, sub=u)
-        self._mark(parity, 4)
+        tick = self.tick
         common = (self.reward.data_ptr(), self.done.data_ptr(), self.valid.data_ptr(), self.score.data_ptr(),
                   self.frame.data_ptr(), self.reset_mask.data_ptr(), self.log_score.data_ptr(), self.log_frame.data_ptr(),
                   self.log_last.data_ptr(), self.log_env.data_ptr(), self.cap, self.log_count.data_ptr(),
-                  self.transitions.data_ptr(), self.tick.data_ptr())
-        if auto_reset:      # bookkeeping + the finished envs start their 50 reset sub-steps (one per following step)
-            N.check(self.lib.rloa_episode_update_reset(env.sim._h_sim, self.frames, *common, env._d_pos.data_ptr(),
-                                                       env._d_var.data_ptr(), env._n_init(), 50,
+                  self.transitions.data_ptr(), tick.data_ptr())
+
+        def bookkeeping_reset():
+            # bookkeeping + the finished envs start their 50 reset sub-steps (one per following step); the counter
+            # for the next iteration goes to the other slot (see _ticks)
+            nxt = self._ticks[1 - self._par:2 - self._par]
+            N.check(self.lib.rloa_episode_update_reset(env.sim._h_sim, self.frames, *common, nxt.data_ptr(),
+                                                       env._d_pos.data_ptr(), env._d_var.data_ptr(), env._n_init(), 50,
                                                        (env.seed + 0x5EED) & 0xFFFFFFFFFFFFFFFF, a._stream()),
                     'rloa_episode_update_reset')
-        else:
+
+        early = auto_reset and self.pipeline_sim      # beside the update, on the simulator's side stream
+        if early:
+            bookkeeping_reset()
+        if learn_now:
+            for u in range(a.num_updates):
+                a.learn_from_memory(tick=tick, sub=u)
+        self._mark(parity, 4)
+        if auto_reset and not early:
+            bookkeeping_reset()
+        elif not auto_reset:
             N.check(self.lib.rloa_episode_update(self.n, self.frames, *common, a._stream()), 'rloa_episode_update')
         if self.pipeline_sim:
             env.sim.join()
         self._mark(parity, 5)
         self.state, self.next_state = self.next_state, self.state
+        self._odd ^= 1
+        if auto_reset:
+            self._par ^= 1
 
     def step(self, auto_reset: bool = True) -> None:
         learn_now = self.learn and self.agent._learn_due(pending=self.n)
@@ -501,18 +533,22 @@ class VectorLoop:
                 self._body(True, self.learn, 0)
                 self._body(True, self.learn, 1)
             self._graph, self._graph_learn = g, self.learn
+            self._odd, self._graph_par = 0, self._par
             self.graph_kernels = int(self.lib.rloa_launch_count() - launched)    # librloa kernels per replay
             a.memory._len = host_len          # capturing does not execute: roll the host mirror back
             return True
         except Exception as err:          # pragma: no cover - depends on driver / NCCL capture support
             self.graph_error = f'{type(err).__name__}: {err}'
             self._graph = None
+            self._graph_failed = True
             a.memory._len = host_len
             torch.cuda.synchronize(self.agent.device)
             return False
 
     def replay_pair(self) -> None:
         """Two iterations through the captured graph."""
+        if self._odd or self._par != self._graph_par:
+            raise RuntimeError('the loop buffers are not in the phase the graph was captured in; use run_steps')
         self._graph.replay()
         m = self.agent.memory
         m._len = min(m.buffer_size, m._len + 2 * self.n)
@@ -559,7 +595,7 @@ class VectorLoop:
             env.sim._h_sim, self.frames, self.reward.data_ptr(), self.done.data_ptr(), self.valid.data_ptr(),
             self.score.data_ptr(), self.frame.data_ptr(), self.reset_mask.data_ptr(), self.log_score.data_ptr(),
             self.log_frame.data_ptr(), self.log_last.data_ptr(), self.log_env.data_ptr(), self.cap,
-            self.log_count.data_ptr(), self.transitions.data_ptr(), self.tick.data_ptr(), env._d_pos.data_ptr(),
+            self.log_count.data_ptr(), self.transitions.data_ptr(), self.tick.data_ptr(), None, env._d_pos.data_ptr(),
             env._d_var.data_ptr(), env._n_init(), 50, (env.seed + 0x5EED) & 0xFFFFFFFFFFFFFFFF, a._stream()),
             'rloa_episode_update_reset')
         if self.pipeline_sim:
@@ -602,7 +638,10 @@ class VectorLoop:
 
     def run_steps(self, k: int, use_graph: bool = True) -> None:
         """k iterations with auto-reset; pairs go through the CUDA graph when it is (or can be) captured."""
-        if use_graph and k >= 2 and self.capture():
+        if use_graph and self._graph is not None and k >= 1 and (self._odd or self._par != self._graph_par):
+            self.step()                    # an odd number of eager iterations since the capture: realign the buffers
+            k -= 1
+        if use_graph and k >= 2 and not self._graph_failed and self.capture():
             while k >= 2:
                 self.replay_pair()
                 k -= 2

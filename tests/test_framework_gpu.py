@@ -250,3 +250,38 @@ def test_training_state_resume_is_bit_identical(tmp_path):
     assert len(straight.memory) == len(resumed.memory) == 1024
     with pytest.raises(ValueError):
         NAFAgent(None, 23, 7, 256, 64, 1024, 1e-3, 1e-3, 0.99, 1, 1, 500, DEV, seed=0).load_training_state(path)
+
+
+def test_run_steps_realigns_graph_after_odd_eager_steps():
+    """run_steps mixes graph replays (pairs) with eager iterations; after an odd number of eager iterations the state
+    buffers and the ping-pong loop counter are out of phase with the captured graph and one eager iteration realigns
+    them.  The mixed schedule must equal 24 eager iterations bit-for-bit."""
+    n = 256
+
+    def snapshot(env, agent, loop):
+        torch.cuda.synchronize()
+        q, qd = env.sim.get_state()
+        return dict(state=loop.state.clone(), q=q.clone(), qd=qd.clone(), tick=int(loop.tick.item()),
+                    cursor=int(agent.memory.cursor.item()), episodes=int(loop.log_count.item()),
+                    params=torch.cat([p.detach().reshape(-1) for p in agent.qnetwork_main.parameters()]).clone())
+
+    env, agent, loop = _twin(n)
+    for _ in range(24):
+        loop.step()
+    want = snapshot(env, agent, loop)
+    env, agent, loop = _twin(n)
+    for _ in range(4):
+        loop.step()
+    loop.run_steps(6)                    # capture + 3 replays
+    assert loop._graph is not None, loop.graph_error
+    loop.step()                          # odd
+    with pytest.raises(RuntimeError):
+        loop.replay_pair()
+    loop.run_steps(7)                    # 1 eager (realign) + 3 replays
+    loop.run_steps(5)                    # 2 replays + 1 eager
+    loop.run_steps(1)                    # eager (realign only)
+    got = snapshot(env, agent, loop)
+    assert got['tick'] == want['tick'] == 24
+    assert got['cursor'] == want['cursor'] and got['episodes'] == want['episodes']
+    for k in ('state', 'q', 'qd', 'params'):
+        assert torch.equal(got[k], want[k]), k
