@@ -186,3 +186,39 @@ def test_prepared_step_is_bit_identical():
     for (o0, r0, d0), (o1, r1, d1) in zip(outs[0][0], outs[1][0]):
         assert torch.equal(o0, o1) and torch.equal(r0, r1) and torch.equal(d0, d1)
     assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+
+
+@pytest.mark.parametrize('n', [1, 31, 77, 1000])
+def test_ragged_env_counts_and_active_mask(n):
+    """Env counts that do not fill the last warp / block, and an `active` mask: inactive envs keep their state and
+    outputs, active ones match the oracle; nothing is written past the end of the output buffers."""
+    cfg = KUKA
+    model, orc = make_oracle(cfg)
+    q, qd = random_states(model, n, seed=100 + n, held=cfg['fixed'])
+    rng = np.random.default_rng(n)
+    actions = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+    active = (rng.uniform(size=n) < 0.7).astype(np.uint8)
+    active[0] = 1
+    sim = make_sim(model, cfg, n)
+    sim.set_state(q, qd)
+    pad = 64
+    obs = torch.full((n + pad, sim.obs_size), -7.0, device='cuda')
+    rew = torch.full((n + pad,), -7.0, device='cuda')
+    done = torch.full((n + pad,), 9, dtype=torch.uint8, device='cuda')
+    sim.step(torch.as_tensor(actions, device='cuda'), active=torch.as_tensor(active, device='cuda'),
+             out=(obs, rew, done))
+    qg, qdg = sim.get_state()
+    qg, qdg = qg.cpu().numpy(), qdg.cpu().numpy()
+    assert (obs[n:] == -7.0).all() and (rew[n:] == -7.0).all() and (done[n:] == 9).all()
+    step_motors(orc, cfg)
+    q32, qd32 = q.astype(np.float32).astype(np.float64), qd.astype(np.float32).astype(np.float64)
+    q_in, qd_in = q32.copy(), qd32.copy()
+    obs_o, rew_o, done_o, _ = orc.batch_step(q32, qd32, actions.astype(np.float64), cfg['involved'], 200.0,
+                                             cfg['obstacle'], cfg['target'], nthreads=4)
+    on = active.astype(bool)
+    assert np.abs(qg[on] - q32[on]).max() <= TOL_Q and np.abs(qdg[on] - qd32[on]).max() <= 2e-3
+    assert np.abs(obs[:n].cpu().numpy()[on][:, 12:15] - obs_o[on][:, 12:15]).max() <= TOL_EE
+    if (~on).any():
+        assert np.abs(qg[~on] - q_in[~on]).max() <= 1e-7 and np.abs(qdg[~on] - qd_in[~on]).max() <= 1e-6
+        assert (obs[:n][torch.as_tensor(~on)] == -7.0).all() and (done[:n][torch.as_tensor(~on)] == 9).all()
+    sim.close()
