@@ -87,7 +87,7 @@ def learn_ref(main: NAFRef, target: NAFRef, opt: torch.optim.Adam, batch, gamma:
     with torch.no_grad():                                         # :225-226 parameters only, no BN buffers
         for pt, pm in zip(target.parameters(), main.parameters()):
             pt.copy_(tau * pm + (1.0 - tau) * pt)
-    return float(loss), float(norm), flat
+    return float(loss.detach()), float(norm), flat
 
 
 def load_reference_classes():
