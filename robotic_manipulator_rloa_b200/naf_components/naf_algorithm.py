@@ -437,6 +437,7 @@ class VectorLoop:
         self.graph_error: Optional[str] = None
         self.pipeline_sim = True        # rloa_sim_prepare: the next step's dynamics run beside this step's learn
         self._host = None               # pinned host buffers bound by bind_host_buffers
+        self._host_ready = None         # event behind the D2H of (state, reward, done) in the host-facing iteration
         self._copy_stream = None
         self._host_graphs = None
 
@@ -564,6 +565,10 @@ class VectorLoop:
                 raise ValueError('step_host needs pinned host tensors')
         self._host = (h_state, h_action, h_reward, h_done)
         self._host_graphs = None
+        try:        # `external`: the record can sit inside the captured graph as an event-record node
+            self._host_ready = torch.cuda.Event(external=True)
+        except TypeError:      # pragma: no cover - older torch: fall back to a full stream synchronisation
+            self._host_ready = None
 
     def _host_phase_act(self) -> None:
         h_state, h_action, _, _ = self._host
@@ -587,6 +592,8 @@ class VectorLoop:
             h_state.copy_(self.next_state, non_blocking=True)
             h_reward.copy_(self.reward, non_blocking=True)
             h_done.copy_(self.done, non_blocking=True)
+            if self._host_ready is not None:      # what step_host waits for: the caller's buffers are complete here
+                self._host_ready.record(self._copy_stream)
         a.memory.add_batch(self.state, self.actions, self.reward, self.next_state, self.done, valid=self.valid)
         if learn_now:
             for u in range(a.num_updates):
@@ -604,8 +611,10 @@ class VectorLoop:
 
     def step_host(self, use_graph: bool = True) -> None:
         """One iteration through the bound host buffers: [H2D states, act, D2H actions] sync
-        [H2D actions, Environment.step, D2H state/reward/done, store, learn, bookkeeping] sync.  In steady state the
-        two halves are CUDA graphs (copies included)."""
+        [H2D actions, Environment.step, D2H state/reward/done | store, learn, bookkeeping] wait for the D2H.  In steady
+        state the two halves are CUDA graphs (copies included).  The call returns as soon as the caller's buffers hold
+        this step's (state, reward, done): store / learn / bookkeeping of this step may still be running, and the next
+        call's work queues behind them on the same stream (torch.cuda.synchronize() to drain)."""
         a = self.agent
         stream = torch.cuda.current_stream(a.device)
         if use_graph and self._host_graphs is None and self._graphable() and a._ws is not None and \
@@ -629,11 +638,13 @@ class VectorLoop:
             stream.synchronize()
             self._host_graphs[1].replay()
             a.memory._len = min(a.memory.buffer_size, a.memory._len + self.n)
-            stream.synchronize()
         else:
             self._host_phase_act()
             stream.synchronize()
             self._host_phase_step(self.learn and a._learn_due(pending=self.n))
+        if self._host_ready is not None:
+            self._host_ready.synchronize()
+        else:
             stream.synchronize()
 
     def run_steps(self, k: int, use_graph: bool = True) -> None:

@@ -171,8 +171,14 @@ def test_step_host_moves_every_step_through_pinned_buffers():
         hr, hd = torch.zeros(n).pin_memory(), torch.zeros(n, dtype=torch.uint8).pin_memory()
         hs.copy_(loop.state)
         loop.bind_host_buffers(hs, ha, hr, hd)
-        for _ in range(12):
+        for k in range(12):
             loop.step_host(use_graph=use_graph)
+            if k >= 6:      # the call returns once the caller's buffers are complete, possibly before the update ends:
+                early = (hs.clone(), hr.clone(), hd.clone())      # what the host sees at return ...
+                torch.cuda.synchronize()
+                assert torch.equal(early[0], loop.next_state.cpu()) and torch.equal(early[1], loop.reward.cpu())
+                assert torch.equal(early[2], loop.done.cpu())     # ... is this step's device result
+        torch.cuda.synchronize()
         assert (loop._host_graphs not in (None, False)) == use_graph
         assert torch.equal(hs, loop.next_state.cpu()) and torch.equal(ha, loop.actions.cpu())
         assert torch.equal(hr, loop.reward.cpu()) and torch.equal(hd, loop.done.cpu())
