@@ -1,0 +1,81 @@
+"""
+Records golden vectors of the reference's PyBullet path — the piece this repository cannot produce itself: the image it
+is built in has neither the `pybullet` wheel nor `pybullet_data` ("parity unpinned").  Run it on any
+machine that has them, next to a checkout of the reference and of this repository:
+
+    pip install pybullet numpy            # plus the reference: pip install robotic-manipulator-rloa (or PYTHONPATH)
+    python tests/golden/make_bullet_golden.py [kuka|xarm6] [n_records=256]
+
+It drives the UNMODIFIED reference `Environment` (PyBullet DIRECT): for every record the joints are put into a seeded
+state with `p.resetJointState`, one `Environment.step(action)` runs, and joint states, observation, reward, done, the
+per-link obstacle distances and the end-effector / target distance are stored — together with the model THIS repository's
+loader builds from the very same asset file, so the checks need no asset at test time.  The output,
+tests/golden/bullet_<robot>.npz, is picked up by tests/test_bullet_golden.py (oracle on CPU, CUDA simulator with -m gpu),
+which skip while the file is absent.  NOT runnable in the build image; written against the PyBullet API the reference
+itself uses (environment.py:207-255, 431-485; utils/collision_detector.py:33-61).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))                       # tests/ (helpers)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))      # repository root
+
+import pybullet as p                                            # noqa: E402
+import pybullet_data                                            # noqa: E402
+from robotic_manipulator_rloa.environment.environment import Environment, EnvironmentConfiguration   # noqa: E402
+from robotic_manipulator_rloa.utils.collision_detector import CollisionDetector, CollisionObject      # noqa: E402
+
+from helpers import KUKA, XARM6, model_to_entries               # noqa: E402
+from robotic_manipulator_rloa_b200.environment.robot_model import load_manipulator                    # noqa: E402
+
+robot = sys.argv[1] if len(sys.argv) > 1 else 'kuka'
+n_rec = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+cfg = {'kuka': KUKA, 'xarm6': XARM6}[robot]
+path = os.path.join(pybullet_data.getDataPath(), cfg['file'])
+
+env = Environment(path, EnvironmentConfiguration(
+    endeffector_index=cfg['ee'], fixed_joints=cfg['fixed'], involved_joints=cfg['involved'],
+    target_position=cfg['target'], obstacle_position=cfg['obstacle'], initial_joint_positions=cfg['start'],
+    initial_positions_variation_range=[0.0] * len(cfg['start']), max_force=200., visualize=False))
+uid, nl = env.manipulator_uid, env.num_joints
+model = load_manipulator(path)                                  # this repository's front end on the same file
+assert model.nl == nl, f'joint count: loader {model.nl}, PyBullet {nl}'
+
+rng = np.random.default_rng(0)
+lo = np.array([p.getJointInfo(uid, j)[8] for j in range(nl)])
+hi = np.array([p.getJointInfo(uid, j)[9] for j in range(nl)])
+movable = np.array([p.getJointInfo(uid, j)[2] != p.JOINT_FIXED for j in range(nl)])
+rec = {k: [] for k in ('q0', 'qd0', 'action', 'q1', 'qd1', 'obs', 'reward', 'done', 'link_obstacle', 'ee_target', 'com')}
+env.step(np.zeros(len(cfg['involved'])))                        # the motors every later step re-arms are in place
+for k in range(n_rec):
+    q0, qd0 = np.zeros(nl), np.zeros(nl)
+    for j in range(nl):
+        if not movable[j]:
+            continue
+        a, b = (lo[j], hi[j]) if lo[j] < hi[j] else (-np.pi, np.pi)
+        if j in cfg['fixed']:                                   # the reference holds these at 0
+            q0[j], qd0[j] = rng.uniform(-0.02, 0.02), rng.uniform(-0.2, 0.2)
+        else:
+            q0[j], qd0[j] = 0.5 * (a + b) + 0.45 * (b - a) * rng.uniform(-1, 1), rng.uniform(-1, 1)
+        p.resetJointState(uid, j, q0[j], qd0[j])
+    action = rng.uniform(-1, 1, len(cfg['involved']))
+    obs, reward, done = env.step(action)
+    js = [p.getJointState(uid, j) for j in range(nl)]
+    rec['q0'].append(q0); rec['qd0'].append(qd0); rec['action'].append(action)
+    rec['q1'].append([s[0] for s in js]); rec['qd1'].append([s[1] for s in js])
+    rec['obs'].append(np.asarray(obs, float)); rec['reward'].append(float(reward)); rec['done'].append(int(done))
+    rec['link_obstacle'].append([CollisionDetector(CollisionObject(uid, l), [env.obstacle]).compute_distances()[0]
+                                 for l in range(nl)])
+    rec['ee_target'].append(CollisionDetector(CollisionObject(uid, cfg['ee']), [env.target]).compute_distances()[0])
+    rec['com'].append([p.getLinkState(uid, l)[0] for l in range(nl)])
+
+out = {k: np.asarray(v) for k, v in rec.items()}
+out.update(model_to_entries(model))
+out['pybullet_api_version'] = np.asarray(p.getAPIVersion())
+out['robot'] = np.asarray(robot)
+dst = os.path.join(HERE, f'bullet_{robot}.npz')
+np.savez_compressed(dst, **out)
+print(f'wrote {dst}: {n_rec} records, {nl} joints, {int(np.sum(out["done"]))} terminal steps')

@@ -155,3 +155,29 @@ def write_test_arm(dirname, geometry):
     with open(path, 'w') as f:
         f.write('<?xml version="1.0"?><robot name="arm">' + ''.join(links) + ''.join(joints) + '</robot>')
     return path
+
+
+# ---- RobotModel <-> flat npz entries (tests/golden/make_bullet_golden.py stores the model PyBullet loaded) -------
+_MODEL_ARRAYS = ('parent', 'jtype', 'E0', 'e', 'd', 'axis', 'mass', 'inertia', 'damping', 'lower', 'upper', 'has_limit',
+                 'base_R', 'base_p', 's_link', 's_type', 's_R', 's_p', 's_dim', 'joint_axis_link', 's_v0', 's_vn', 'verts')
+_MODEL_SCALARS = ('lin_damp', 'ang_damp', 'dt', 'iters', 'resid_thresh', 'erp', 'max_vel', 'limit_max_impulse')
+
+
+def model_to_entries(model, prefix='model_'):
+    out = {prefix + k: np.asarray(getattr(model, k)) for k in _MODEL_ARRAYS}
+    out.update({prefix + k: np.asarray(getattr(model, k)) for k in _MODEL_SCALARS})
+    out[prefix + 'gravity'] = np.asarray(model.gravity, float)
+    out[prefix + 'joint_names'] = np.asarray(model.joint_names)
+    out[prefix + 'link_names'] = np.asarray(model.link_names)
+    return out
+
+
+def model_from_entries(z, prefix='model_'):
+    from robotic_manipulator_rloa_b200.environment.robot_model import RobotModel
+    kw = {k: np.asarray(z[prefix + k]) for k in _MODEL_ARRAYS}
+    for k in ('parent', 'jtype', 'has_limit', 's_link', 's_type', 's_v0', 's_vn'):
+        kw[k] = kw[k].astype(np.int32)
+    kw.update({k: (int if k == 'iters' else float)(z[prefix + k]) for k in _MODEL_SCALARS})
+    return RobotModel(nl=int(kw['parent'].shape[0]), gravity=tuple(float(v) for v in z[prefix + 'gravity']),
+                      joint_names=[str(s) for s in z[prefix + 'joint_names']],
+                      link_names=[str(s) for s in z[prefix + 'link_names']], **kw)
