@@ -4,19 +4,23 @@
 //
 //   policy_pack_kernel   folds the eval-mode BatchNorms into per-column (scale, shift) vectors and writes the
 //                        "weight image": hidden_layer.weight and the 2A head rows that act() needs (mu, diag L)
-//                        as bf16 in the exact shared-memory byte order of a K-major SWIZZLE_128B UMMA operand.
+//                        as bf16, input_layer.weight as tf32, all in the exact shared-memory byte order of a K-major
+//                        SWIZZLE_128B UMMA operand.
 //   policy_act_tc_kernel per 128-row tile:
-//     0. one thread issues three 1-D TMA bulk copies (cp.async.bulk, mbarrier complete_tx): W2 image 128 KB,
-//        W1 + vectors 28 KB now, head image 16 KB later into the W1 region;
-//     1. layer 1 (K = S = 21: too thin for the tensor core, and the observation carries raw joint angles, so it
-//        stays fp32) on the CUDA cores while the W2 copy is in flight: thread = (row, quarter of the 256 columns),
-//        W1 broadcast from shared memory; relu(bn1(.)) -> bf16 -> A operand tile, hand-swizzled;
-//     2. layer 2: 16 x tcgen05.mma 128x256x16 (bf16 -> fp32 TMEM, 256 columns), commit -> mbarrier;
-//     3. epilogue 2: tcgen05.ld, relu(bn2(.)) -> bf16 -> the same A tile (layer-2 operands are dead);
-//     4. heads: 16 x tcgen05.mma 128x32x16 into TMEM columns 0-31 (the layer-2 accumulator is dead);
-//     5. epilogue: mu = tanh, l_kk = tanh, action = clamp(mu + noise_scale exp(-l_kk) eps, -1, 1) with the same
+//     0. one thread issues the 1-D TMA bulk copies (cp.async.bulk, mbarrier complete_tx): W1 image 32 KB + vectors,
+//        W2 image 128 KB, head image 16 KB;
+//     1. layer 1 on the tensor core as kind::tf32 (K = S <= 24 -> three 128x256x8 steps).  The observation carries raw
+//        joint angles, so it is NOT rounded to tf32: every thread splits its values into x = hi + lo (both tf32,
+//        |x - hi - lo| <= 2^-22 |x|) and the MMA runs twice into the same accumulator; only the weights see the 10-bit
+//        mantissa.  (The first version did this layer in fp32 on the CUDA cores: 50 % of the kernel's time in ncu.)
+//     2. epilogue 1: tcgen05.ld, relu(bn1(.)) -> bf16 -> A operand tile, hand-swizzled (it overwrites the layer-1
+//        operands, which are dead);
+//     3. layer 2: 16 x tcgen05.mma 128x256x16 (bf16 -> fp32 TMEM, the same 256 columns), commit -> mbarrier;
+//     4. epilogue 2: relu(bn2(.)) -> bf16 -> the same A tile;
+//     5. heads: 16 x tcgen05.mma 128x32x16 into TMEM columns 0-31;
+//     6. epilogue: mu = tanh, l_kk = tanh, action = clamp(mu + noise_scale exp(-l_kk) eps, -1, 1) with the same
 //        Philox4x32-10 keying as the fp32 head kernel (seed, step + *step_offset, row, k).
-// Shared memory: A tile 64 KB + W2 128 KB + W1/head region 24 KB + vectors 4.2 KB = 220.2 KB of the 227 KB.
+// Shared memory: A tile 64 KB (first: W1 32 KB | x_hi 16 KB | x_lo 16 KB) + W2 128 KB + heads 16 KB + vectors 4.2 KB.
 #include "common.cuh"
 #include "naf_trunk_tc.cuh"
 #include "philox.cuh"
@@ -27,20 +31,23 @@ namespace rloa {
 using namespace tc;
 
 constexpr int kPolH = 256;                     // hidden width the kernel is built for
-constexpr int kPolSP = 24;                     // padded state width (S <= 24: KUKA 21, Panda 23)
+constexpr int kPolSP = 24;                     // largest state width (KUKA 21, Panda 23): three tf32 k-steps of 8
+constexpr int kPolKP = 32;                     // K of the layer-1 operand tiles: one 128-byte swizzle row of fp32
 constexpr int kPolNH = 32;                     // head rows in the image: [0,A) mu, [A,2A) diag L, rest zero
 constexpr int kPolThreads = 512;               // 16 warps: thread = (tile row, quarter of the 256 hidden columns)
 constexpr uint32_t kPolW2Bytes = kPolH * kPolH * 2;            // 131072
 constexpr uint32_t kPolWhBytes = kPolNH * kPolH * 2;           // 16384
 constexpr uint32_t kPolVecFloats = 4 * kPolH + kPolNH;         // sc1 sh1 sc2 sh2 bh
 constexpr uint32_t kPolVecBytes = kPolVecFloats * 4;           // 4224
-constexpr uint32_t kPolW1Bytes = kPolH * kPolSP * 4;           // 24576 (fp32 [256][24])
+constexpr uint32_t kPolW1Bytes = kPolH * kPolKP * 4;           // 32768 (tf32 [256 rows][128 B], swizzled)
+constexpr uint32_t kPolXBytes = 128 * kPolKP * 4;              // 16384 per observation tile (hi, lo)
 constexpr uint32_t kPolOffWh = kPolW2Bytes;
 constexpr uint32_t kPolOffW1 = kPolOffWh + kPolWhBytes;        // W1 and the vectors are contiguous: one bulk copy
 constexpr uint32_t kPolOffVec = kPolOffW1 + kPolW1Bytes;
 constexpr uint32_t kPolImageBytes = kPolOffVec + kPolVecBytes;
 constexpr uint32_t kPolABytes = 128 * kPolH * 2;               // 65536
-constexpr uint32_t kPolSmemBytes = kPolABytes + kPolW2Bytes + kPolW1Bytes + kPolVecBytes + 64 + 1024;
+constexpr uint32_t kPolSmemBytes = kPolABytes + kPolW2Bytes + kPolWhBytes + kPolVecBytes + 64 + 1024;
+static_assert(kPolW1Bytes + 2 * kPolXBytes <= kPolABytes, "layer-1 operands live in the A tile");
 constexpr uint32_t kPolTmemCols = 256;
 
 size_t policy_image_bytes() { return kPolImageBytes; }
@@ -80,13 +87,20 @@ __global__ void __launch_bounds__(256) policy_pack_kernel(rloa_naf_params p, uin
         return;
     }
     u -= kPolNH * kPolH / 8;
-    // (c) W1 fp32, rows padded to 24
-    if (u < kPolH * kPolSP) {
-        const int j = u / kPolSP, k = u - j * kPolSP;
-        reinterpret_cast<float*>(image + kPolOffW1)[u] = k < S ? p.w1[(size_t)j * S + k] : 0.f;
+    // (c) W1 as tf32: one thread per 16-byte chunk (4 consecutive k of output row j), K padded to 32 with zeros
+    if (u < kPolH * kPolKP / 4) {
+        const int j = u >> 3, kc = u & 7;
+        float4 v;
+        float* vv = reinterpret_cast<float*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int k = kc * 4 + i;
+            vv[i] = k < S ? to_tf32(p.w1[(size_t)j * S + k]) : 0.f;
+        }
+        *reinterpret_cast<float4*>(image + kPolOffW1 + sw128_chunk_offset(j, kc)) = v;
         return;
     }
-    u -= kPolH * kPolSP;
+    u -= kPolH * kPolKP / 4;
     // (d) eval-mode BatchNorm folded with the linear bias: a = relu(acc * sc + sh)
     float* vec = reinterpret_cast<float*>(image + kPolOffVec);
     if (u < kPolH) {
@@ -120,81 +134,53 @@ policy_act_tc_kernel(const uint8_t* __restrict__ image, const float* __restrict_
     uint8_t* sm = pol_smem_raw + (base - raw);
     uint8_t* sm_a = sm;                                  // [4 k-blocks][128 rows][128 B]
     uint8_t* sm_w2 = sm + kPolABytes;                    // [4 k-blocks][256 rows][128 B]
-    uint8_t* sm_r = sm_w2 + kPolW2Bytes;                 // W1 fp32 [256][24], later the head image [4][32 rows][128 B]
-    float* sm_vec = reinterpret_cast<float*>(sm_r + kPolW1Bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_r + kPolW1Bytes + kPolVecBytes);   // w2, w1, wh, mma
+    uint8_t* sm_r = sm_w2 + kPolW2Bytes;                 // head image [4][32 rows][128 B]
+    float* sm_vec = reinterpret_cast<float*>(sm_r + kPolWhBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_r + kPolWhBytes + kPolVecBytes);   // w2, w1 + vectors, wh, mma
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
     const uint32_t a_base = base, w2_base = base + kPolABytes, r_base = w2_base + kPolW2Bytes;
+    // layer-1 operands inside the A tile (dead before epilogue 1 writes the tile): W1 | x_hi | x_lo
+    uint8_t *sm_xh = sm_a + kPolW1Bytes, *sm_xl = sm_xh + kPolXBytes;
+    const uint32_t xh_base = a_base + kPolW1Bytes, xl_base = xh_base + kPolXBytes;
 
     if (warp == 0) tmem_alloc(tmem_slot, kPolTmemCols);
     if (tid == 0) {
         mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);
         mbar_init_fence();
         mbar_expect_tx(&bars[1], kPolW1Bytes + kPolVecBytes);
-        bulk_g2s(sm_r, image + kPolOffW1, kPolW1Bytes + kPolVecBytes, &bars[1]);
+        bulk_g2s(sm_a, image + kPolOffW1, kPolW1Bytes, &bars[1]);
+        bulk_g2s(sm_vec, image + kPolOffVec, kPolVecBytes, &bars[1]);
         mbar_expect_tx(&bars[0], kPolW2Bytes);
         bulk_g2s(sm_w2, image, kPolW2Bytes, &bars[0]);
+        mbar_expect_tx(&bars[2], kPolWhBytes);
+        bulk_g2s(sm_r, image + kPolOffWh, kPolWhBytes, &bars[2]);
     }
-    // this thread's observation row, fp32 registers
-    float x[kPolSP];
+    // this thread's 8 observation values (row r, k = 8 half .. 8 half + 7) as tf32 hi / lo pairs, swizzled
+    {
+        float xh[8], xl[8];
 #pragma unroll
-    for (int k = 0; k < kPolSP; k++) x[k] = (k < S && row < n_rows) ? states[(size_t)row * S + k] : 0.f;
+        for (int i = 0; i < 8; i++) {
+            const int k = half * 8 + i;
+            const float x = (k < S && row < n_rows) ? states[(size_t)row * S + k] : 0.f;
+            xh[i] = to_tf32(x);
+            xl[i] = to_tf32(x - xh[i]);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const uint32_t off = sw128_chunk_offset(r, half * 2 + c);
+            *reinterpret_cast<float4*>(sm_xh + off) = make_float4(xh[4 * c], xh[4 * c + 1], xh[4 * c + 2], xh[4 * c + 3]);
+            *reinterpret_cast<float4*>(sm_xl + off) = make_float4(xl[4 * c], xl[4 * c + 1], xl[4 * c + 2], xl[4 * c + 3]);
+        }
+    }
+    fence_proxy_async();                                 // observation tiles -> async proxy
     fence_before_sync();
     __syncthreads();                                     // barrier inits + TMEM address visible
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    // ---- layer 1 on the CUDA cores (fp32), 128 columns per thread, straight into the bf16 A tile ----
-    mbar_wait(&bars[1], 0);
-    {
-        const float* w1 = reinterpret_cast<const float*>(sm_r);
-        const float *sc1 = sm_vec, *sh1 = sm_vec + kPolH;
-#pragma unroll 1
-        for (int c8 = 0; c8 < 8; c8++) {                 // 8 chunks of 8 columns
-            const int j0 = half * 64 + c8 * 8;
-            float a[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const float4* wr = reinterpret_cast<const float4*>(w1 + (j0 + i) * kPolSP);
-                // packed FFMA2 (fma.rn.f32x2): two partial dot products per instruction, halves the FMA issue count
-                float2 acc2 = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int k4 = 0; k4 < kPolSP / 4; k4++) {
-                    const float4 w = wr[k4];
-                    acc2 = __ffma2_rn(make_float2(x[4 * k4], x[4 * k4 + 1]), make_float2(w.x, w.y), acc2);
-                    acc2 = __ffma2_rn(make_float2(x[4 * k4 + 2], x[4 * k4 + 3]), make_float2(w.z, w.w), acc2);
-                }
-                a[i] = fmaxf(fmaf(acc2.x + acc2.y, sc1[j0 + i], sh1[j0 + i]), 0.f);
-            }
-            const int chunk = j0 >> 3;                   // 0..31 over K = 256
-            *reinterpret_cast<uint4*>(sm_a + (chunk >> 3) * (128 * 128) + sw128_chunk_offset(r, chunk & 7)) = pack8_bf16(a);
-        }
-    }
-    fence_proxy_async();                                 // A tile -> async proxy; also orders the W1 reads before the head copy
-    __syncthreads();
-
-    // ---- layer 2 on the tensor core ----
-    if (tid == 0) {
-        // the W1 region is free now: fetch the head image into it while layer 2 runs
-        mbar_expect_tx(&bars[2], kPolWhBytes);
-        bulk_g2s(sm_r, image + kPolOffWh, kPolWhBytes, &bars[2]);
-        mbar_wait(&bars[0], 0);                          // W2 image landed
-        fence_after_sync();
-        constexpr uint32_t idesc = idesc_bf16_f32(128, kPolH);
-#pragma unroll
-        for (int k = 0; k < kPolH / 16; k++)
-            mma_bf16(tmem, umma_desc_sw128(a_base + (k >> 2) * (128 * 128) + (k & 3) * 32),
-                     umma_desc_sw128(w2_base + (k >> 2) * (kPolH * 128) + (k & 3) * 32), idesc, k > 0);
-        mma_commit(&bars[3]);
-    }
-    __syncwarp();
-    mbar_wait(&bars[3], 0);
-    fence_after_sync();
-
-    // ---- epilogue 2: relu(bn2(.)) -> bf16 -> the A tile again (TMEM lane = row = 32 (warp % 4) + lane; warp / 4 picks
-    // the 64-column quarter) ----
-    {
-        const float *sc2 = sm_vec + 2 * kPolH, *sh2 = sm_vec + 3 * kPolH;
+    // relu(acc * scale + shift) of this thread's 64 accumulator columns -> bf16 -> the A tile (TMEM lane = row =
+    // 32 (warp % 4) + lane; warp / 4 picks the 64-column quarter)
+    auto bn_relu_to_a = [&](const float* sc, const float* sh) {
 #pragma unroll 1
         for (int q = 0; q < 2; q++) {
             const int c0 = half * 64 + q * 32;
@@ -206,13 +192,50 @@ policy_act_tc_kernel(const uint8_t* __restrict__ image, const float* __restrict_
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int j = c0 + g * 8 + i;
-                    a[i] = fmaxf(fmaf(__uint_as_float(v[g * 8 + i]), sc2[j], sh2[j]), 0.f);
+                    a[i] = fmaxf(fmaf(__uint_as_float(v[g * 8 + i]), sc[j], sh[j]), 0.f);
                 }
                 const int chunk = (c0 >> 3) + g;
                 *reinterpret_cast<uint4*>(sm_a + (chunk >> 3) * (128 * 128) + sw128_chunk_offset(r, chunk & 7)) = pack8_bf16(a);
             }
         }
+    };
+
+    // ---- layer 1 on the tensor core: D = (x_hi + x_lo) W1^T, tf32 operands, fp32 accumulate ----
+    if (tid == 0) {
+        mbar_wait(&bars[1], 0);                          // W1 image + vectors landed
+        fence_after_sync();
+        constexpr uint32_t idesc = idesc_tf32_f32(128, kPolH);
+#pragma unroll
+        for (int k = 0; k < kPolSP / 8; k++) {
+            mma_tf32(tmem, umma_desc_sw128(xh_base + k * 32), umma_desc_sw128(a_base + k * 32), idesc, k > 0);
+            mma_tf32(tmem, umma_desc_sw128(xl_base + k * 32), umma_desc_sw128(a_base + k * 32), idesc, true);
+        }
+        mma_commit(&bars[3]);
     }
+    __syncwarp();
+    mbar_wait(&bars[1], 0);                              // the vectors, for every thread
+    mbar_wait(&bars[3], 0);
+    fence_after_sync();
+    bn_relu_to_a(sm_vec, sm_vec + kPolH);                // epilogue 1: relu(bn1(.)) over the dead layer-1 operands
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+
+    // ---- layer 2 on the tensor core ----
+    if (tid == 0) {
+        mbar_wait(&bars[0], 0);                          // W2 image landed
+        fence_after_sync();
+        constexpr uint32_t idesc = idesc_bf16_f32(128, kPolH);
+#pragma unroll
+        for (int k = 0; k < kPolH / 16; k++)
+            mma_bf16(tmem, umma_desc_sw128(a_base + (k >> 2) * (128 * 128) + (k & 3) * 32),
+                     umma_desc_sw128(w2_base + (k >> 2) * (kPolH * 128) + (k & 3) * 32), idesc, k > 0);
+        mma_commit(&bars[3]);
+    }
+    __syncwarp();
+    mbar_wait(&bars[3], 1);
+    fence_after_sync();
+    bn_relu_to_a(sm_vec + 2 * kPolH, sm_vec + 3 * kPolH);    // epilogue 2: relu(bn2(.)) -> the A tile again
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
@@ -230,7 +253,7 @@ policy_act_tc_kernel(const uint8_t* __restrict__ image, const float* __restrict_
     }
     __syncwarp();
     if (warp < 4) {
-        mbar_wait(&bars[3], 1);
+        mbar_wait(&bars[3], 0);                          // third completion of the MMA barrier
         fence_after_sync();
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
@@ -274,7 +297,7 @@ int policy_tc_act(TrunkTC* t, const rloa_naf_params* p, const float* states, int
                   const uint64_t* step_offset, float noise_scale, float* actions, cudaStream_t st) {
     RLOA_REQUIRE(t->policy_image != nullptr, "tcgen05 policy: rloa_naf_ws_set_trunk(1) was not called");
     uint8_t* image = static_cast<uint8_t*>(t->policy_image);
-    const int pack_threads = kPolH * kPolH / 8 + kPolNH * kPolH / 8 + kPolH * kPolSP + kPolH;
+    const int pack_threads = kPolH * kPolH / 8 + kPolNH * kPolH / 8 + kPolH * kPolKP / 4 + kPolH;
     policy_pack_kernel<<<(pack_threads + 255) / 256, 256, 0, st>>>(*p, image);
     RLOA_LAUNCHED();
     policy_act_tc_kernel<<<(batch + 127) / 128, kPolThreads, kPolSmemBytes, st>>>(

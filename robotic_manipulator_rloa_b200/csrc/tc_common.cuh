@@ -16,6 +16,11 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// instruction descriptor, kind::tf32: D = F32, A = B = TF32 (format code 2), both K-major; K = 8 per instruction
+__host__ __device__ constexpr uint32_t idesc_tf32_f32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // shared memory matrix descriptor, K-major SWIZZLE_128B: start address >> 4 (bits 0-13), leading byte offset
 // (unused for swizzled K-major, canonical value 1) at bits 16-29, stride byte offset = 1024 B between 8-row
 // atoms at bits 32-45, descriptor version 1 at bits 46-47, layout type 2 (SWIZZLE_128B) at bits 61-63
@@ -41,6 +46,23 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
         "}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    const uint32_t acc = accumulate ? 1u : 0u;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// fp32 -> the nearest tf32 value (10-bit mantissa, ties away from zero), kept in an fp32 container
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
 }
 // the mbarrier completes when every MMA issued so far by this thread has finished (implies before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
