@@ -1197,8 +1197,16 @@ static int trunk_forward(rloa_naf_ws* ws, int nets, const rloa_naf_params* const
         gb.bn[n] = BnFuse{bb.a[n], ws->bn_part + (size_t)n * chunks * 2 * H, ws->tickets + n * (H / 32), fuse ? 1 : 0};
     }
     dim3 grid((H + BN - 1) / BN, (B + BM - 1) / BM, nets);
-    launch_gemm<kNT, false>(gb, nets, grid, st);
-    RLOA_LAUNCHED();
+    if (ws->trunk_mode == 1 && trunk_tc_layer1_supported(S, H) && B >= 128) {    // tcgen05 kind::tf32 (naf_trunk_tc.cu)
+        const float *xp[2], *w1p[2], *b1p[2];
+        float* z1p[2];
+        for (int n = 0; n < nets; n++) { xp[n] = x[n]; w1p[n] = P[n]->w1; b1p[n] = P[n]->b1; z1p[n] = ws->z1[n]; }
+        const int rc = trunk_tc_layer1(&ws->tc, nets, xp, w1p, b1p, z1p, B, S, H, fuse ? gb.bn : nullptr, st);
+        if (rc != RLOA_OK) return rc;
+    } else {
+        launch_gemm<kNT, false>(gb, nets, grid, st);
+        RLOA_LAUNCHED();
+    }
     if (!fuse) {
         bn_stats_kernel<<<dim3(H / 32, nets), 256, 0, st>>>(bb, B, H, train);
         RLOA_LAUNCHED();

@@ -67,8 +67,12 @@ __device__ __forceinline__ uint4 pack8(const float4 a, const float4 b, const flo
 // MODE 0 (forward):  C = bf16(relu(A * scale + shift)) @ bf16(W)^T + bias,  W given as [n][k]  (+ fused BN statistics)
 // MODE 1 (backward): C = bf16(A) @ bf16(W),                                 W given as [k][n]: the input gradient
 //                    da1 = dz2 W2 of reference naf_algorithm.py:208 (autograd of hidden_layer), no bias
+// MODE 2 (layer 1):  C = (tf32_hi(A) + tf32_lo(A)) @ tf32(W)^T + bias with A = the S-wide observations (S <= 24),
+//                    W = input_layer.weight [n][S]  (+ fused BN statistics).  kind::tf32, 2 x 3 MMAs of K = 8: the
+//                    inputs keep 2^-22 relative precision through the hi / lo split, the weights are rounded to tf32.
+//                    Field use: z1 = observations, w2 = W1, b2 = b1, z2 = the layer-1 pre-activations.
 template <int MODE>
-__global__ void __launch_bounds__(kTcThreads) trunk_tc_layer2_kernel(const __grid_constant__ TcBatch batch, int B) {
+__global__ void __launch_bounds__(kTcThreads) trunk_tc_layer2_kernel(const __grid_constant__ TcBatch batch, int B, int S) {
     extern __shared__ uint8_t tc_smem_raw[];
     const TcNet& g = batch.n[blockIdx.z];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -93,6 +97,45 @@ __global__ void __launch_bounds__(kTcThreads) trunk_tc_layer2_kernel(const __gri
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
 
+    if (MODE == 2) {
+        // ---- layer-1 operands (tf32, K-major, one 128-byte swizzle row = 32 fp32 per matrix row): x_hi | x_lo | W1 ----
+        uint8_t *sm_xh = sm_a, *sm_xl = sm_a + kABlockBytes;
+        {
+            const int r = tid & 127, h = tid >> 7;             // row, which 16 of the 32 k
+            const int row = m0 + r;
+            float x[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int k = h * 16 + i;
+                x[i] = (k < S && row < B) ? g.z1[(size_t)row * S + k] : 0.f;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                float hi[4], lo[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    hi[i] = tc::to_tf32(x[4 * c + i]);
+                    lo[i] = tc::to_tf32(x[4 * c + i] - hi[i]);
+                }
+                const uint32_t off = tc::sw128_chunk_offset(r, h * 4 + c);
+                *reinterpret_cast<float4*>(sm_xh + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(sm_xl + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+        {
+            const int n = tid & 63, q = tid >> 6;              // weight row, which 8 of the 32 k
+            float w[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int k = q * 8 + i;
+                w[i] = k < S ? tc::to_tf32(g.w2[(size_t)(n0 + n) * S + k]) : 0.f;
+            }
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+                *reinterpret_cast<float4*>(sm_b + tc::sw128_chunk_offset(n, q * 2 + c)) =
+                    make_float4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+        }
+    } else {
     // ---- operands -> shared memory (bf16, K-major, 128-byte swizzle) ----
     // lane owns the 16-byte chunk (8 bf16) k = 8 lane .. 8 lane + 7 of a row: k-block lane / 8, chunk lane % 8
     const int kb = lane >> 3, ch = lane & 7;
@@ -164,6 +207,7 @@ __global__ void __launch_bounds__(kTcThreads) trunk_tc_layer2_kernel(const __gri
             }
         }
     }
+    }
     // generic-proxy writes -> visible to the async proxy (tensor core operand fetch)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -172,7 +216,16 @@ __global__ void __launch_bounds__(kTcThreads) trunk_tc_layer2_kernel(const __gri
     const uint32_t tmem = *tmem_slot;
 
     // ---- one thread issues the 16 MMAs of the tile, then commits to the mbarrier ----
-    if (tid == 0) {
+    if (tid == 0 && MODE == 2) {
+        constexpr uint32_t idesc = tc::idesc_tf32_f32(kTcM, kTcN);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {                          // K = 24 in steps of 8 (32 bytes inside the swizzle row)
+            tc::mma_tf32(tmem, umma_desc_sw128(a_base + k * 32), umma_desc_sw128(b_base + k * 32), idesc, k > 0);
+            tc::mma_tf32(tmem, umma_desc_sw128(a_base + kABlockBytes + k * 32), umma_desc_sw128(b_base + k * 32), idesc, true);
+        }
+        tc::mma_commit(bar);
+    }
+    if (tid == 0 && MODE != 2) {
 #pragma unroll
         for (int k = 0; k < kTcK / 16; k++) {
             // k-block k / 4 (64 bf16 = one 128-byte swizzle row), 32-byte step k % 4 inside the swizzle atom
@@ -228,12 +281,12 @@ __global__ void __launch_bounds__(kTcThreads) trunk_tc_layer2_kernel(const __gri
               "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const bool fuse = MODE == 0 && batch.bn[blockIdx.z].enabled != 0;
+        const bool fuse = MODE != 1 && batch.bn[blockIdx.z].enabled != 0;
         float* tile = reinterpret_cast<float*>(sm_a);          // [128][65] fp32: the operand tiles are dead after the MMAs
         const int trow = (warp & 3) * 32 + lane;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-            const float4 bias = MODE == 0 ? *reinterpret_cast<const float4*>(g.b2 + n0 + half * 32 + j)
+            const float4 bias = MODE != 1 ? *reinterpret_cast<const float4*>(g.b2 + n0 + half * 32 + j)
                                           : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 o;
             o.x = __uint_as_float(v[j]) + bias.x;
@@ -247,7 +300,7 @@ __global__ void __launch_bounds__(kTcThreads) trunk_tc_layer2_kernel(const __gri
             }
         }
     }
-    if (MODE == 0 && batch.bn[blockIdx.z].enabled) {
+    if (MODE != 1 && batch.bn[blockIdx.z].enabled) {
         // ---- BatchNorm statistics of this 128 x 64 tile: column mean and centred second moment over its valid rows,
         // then the last row tile of the column group merges all partials and finalises (bn_fuse.cuh) ----
         const BnFuse& f = batch.bn[blockIdx.z];
@@ -311,6 +364,7 @@ int trunk_tc_prepare(TrunkTC* t, int max_batch, int H) {
     RLOA_REQUIRE(major == 10, "tcgen05 trunk: needs an sm_100 device");
     RLOA_CUDA(cudaFuncSetAttribute(trunk_tc_layer2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     RLOA_CUDA(cudaFuncSetAttribute(trunk_tc_layer2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    RLOA_CUDA(cudaFuncSetAttribute(trunk_tc_layer2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     t->max_batch = max_batch;
     t->ready = true;
     return RLOA_OK;
@@ -327,11 +381,27 @@ int trunk_tc_layer2(TrunkTC* t, int nets, const float* const* z1, const float* c
         if (bn != nullptr) tb.bn[n] = bn[n];
     }
     dim3 grid((B + kTcM - 1) / kTcM, kTcK / kTcN, nets);
-    trunk_tc_layer2_kernel<0><<<grid, kTcThreads, kTcSmemBytes, st>>>(tb, B);
+    trunk_tc_layer2_kernel<0><<<grid, kTcThreads, kTcSmemBytes, st>>>(tb, B, 0);
     RLOA_LAUNCHED();
     return RLOA_OK;
 }
 
+bool trunk_tc_layer1_supported(int S, int H) { return H == kTcK && S >= 1 && S <= 24; }
+
+int trunk_tc_layer1(TrunkTC* t, int nets, const float* const* x, const float* const* w1, const float* const* b1,
+                    float* const* z1, int B, int S, int H, const BnFuse* bn, cudaStream_t st) {
+    RLOA_REQUIRE(t->ready, "tcgen05 trunk: rloa_naf_ws_set_trunk(1) was not called");
+    RLOA_REQUIRE(trunk_tc_layer1_supported(S, H) && nets >= 1 && nets <= 2, "tcgen05 layer 1: hidden = 256, S <= 24, 1..2 networks");
+    TcBatch tb{};
+    for (int n = 0; n < nets; n++) {
+        tb.n[n] = TcNet{x[n], nullptr, nullptr, w1[n], b1[n], z1[n]};
+        if (bn != nullptr) tb.bn[n] = bn[n];
+    }
+    dim3 grid((B + kTcM - 1) / kTcM, kTcK / kTcN, nets);
+    trunk_tc_layer2_kernel<2><<<grid, kTcThreads, kTcSmemBytes, st>>>(tb, B, S);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
 
 int trunk_tc_input_grad(TrunkTC* t, const float* dz, const float* w, float* da, int B, int H, cudaStream_t st) {
     RLOA_REQUIRE(t->ready, "tcgen05 trunk: rloa_naf_ws_set_trunk(1) was not called");
@@ -339,7 +409,7 @@ int trunk_tc_input_grad(TrunkTC* t, const float* dz, const float* w, float* da, 
     TcBatch tb{};
     tb.n[0] = TcNet{dz, nullptr, nullptr, w, nullptr, da};
     dim3 grid((B + kTcM - 1) / kTcM, kTcK / kTcN, 1);
-    trunk_tc_layer2_kernel<1><<<grid, kTcThreads, kTcSmemBytes, st>>>(tb, B);
+    trunk_tc_layer2_kernel<1><<<grid, kTcThreads, kTcSmemBytes, st>>>(tb, B, 0);
     RLOA_LAUNCHED();
     return RLOA_OK;
 }

@@ -24,6 +24,12 @@ int trunk_tc_layer2(TrunkTC* t, int nets, const float* const* z1, const float* c
                     const float* const* w2, const float* const* b2, float* const* z2, int B, int H, const BnFuse* bn,
                     cudaStream_t st);
 
+// layer 1 on the tensor core (kind::tf32, observations split hi + lo): z1[B][H] = x[B][S] @ tf32(w1[H][S])^T + b1, with the
+// train-mode BatchNorm statistics of z1 fused like in trunk_tc_layer2
+bool trunk_tc_layer1_supported(int S, int H);
+int trunk_tc_layer1(TrunkTC* t, int nets, const float* const* x, const float* const* w1, const float* const* b1,
+                    float* const* z1, int B, int S, int H, const BnFuse* bn, cudaStream_t st);
+
 // input gradient of the hidden layer on the tensor core: da[B][H] = bf16(dz[B][H]) @ bf16(w[H][H]) (w = [out][in])
 int trunk_tc_input_grad(TrunkTC* t, const float* dz, const float* w, float* da, int B, int H, cudaStream_t st);
 
