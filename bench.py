@@ -262,7 +262,7 @@ def workload_config(args, where):
                         'vectorised step, live-policy actions',
             'envs_per_gpu': args.envs, 'replay_batch': args.batch, 'frames': FRAMES, 'parallelism': f'env-dp{args.gpus}',
             'l2': 'flushed between timed step pairs (256 MiB fill, untimed)' if where == 'gpu' else 'n/a',
-            'naf_trunk': ('tcgen05: bf16 operands, fp32 TMEM accumulate (fused policy kernel + hidden layer); heads, BatchNorm, '
+            'naf_trunk': ('tcgen05: bf16 operands (tf32 for the S-wide input layer), fp32 TMEM accumulate (fused policy kernel + trunk); heads, BatchNorm, '
                           'backward and optimiser fp32' if getattr(args, 'trunk', 'tc') == 'tc' and where == 'gpu' else 'fp32'),
             'launch': 'eager' if getattr(args, 'no_graph', False) or where == 'cpu' else 'cuda-graph of 2 loop iterations'}
 

@@ -2,7 +2,7 @@
 BatchedSimulator — torch-tensor front end of the native batched simulator (rloa_sim_* in
 include/rloa_b200.h).  It plays the role of the PyBullet physics client the reference's Environment
 owns (/root/reference/robotic_manipulator_rloa/environment/environment.py:207-210): N independent
-arms, one warp each, state resident in HBM.  PyTorch is plumbing here (device memory + streams).
+arms, one thread each (struct-of-arrays state resident in HBM).  PyTorch is plumbing here (device memory + streams).
 """
 from __future__ import annotations
 

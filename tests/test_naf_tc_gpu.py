@@ -93,7 +93,7 @@ def test_forward_and_learn_with_tensor_core_trunk():
 @pytest.mark.parametrize('S,A,n', [(21, 6, 1), (21, 6, 100), (21, 6, 128), (23, 7, 4096), (21, 6, 5000)])
 def test_fused_policy_kernel_matches_fp32_act(S, A, n):
     """NAFAgent.act through the fused tcgen05 policy kernel (trunk mode 1: one launch, W2 / heads in bf16, layer 1
-    fp32) against the fp32 kernels (mode 0) on the same states, weights, running BatchNorm statistics and Philox
+    in tf32 with the observations split hi + lo) against the fp32 kernels (mode 0) on the same states, weights, running BatchNorm statistics and Philox
     keys.  Bound: bf16 operand rounding through two 256-long contractions ahead of a tanh — |d mu| <= 1e-2; with
     noise the same eps is drawn, so clamped actions agree to 2e-2."""
     from robotic_manipulator_rloa_b200.naf_components.naf_algorithm import NAFAgent
