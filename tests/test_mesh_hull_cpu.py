@@ -234,3 +234,62 @@ def test_sdf_mesh_element_with_uri_and_scale(tmp_path):
         assert np.array_equal(lp[other], lm[other]) and ep == em
         if lp[link] > -0.075:
             assert abs(lm[link] + mesh_io.HULL_MARGIN - lp[link]) <= 1e-9
+
+
+def test_oracle_gjk_degenerate_clouds():
+    """Single vertex, segment, planar polygon, duplicated vertices, query point inside / on the hull."""
+    eye, z3 = np.eye(3).reshape(9), np.zeros(3)
+    # one vertex: plain point distances
+    d, _ = bo.gjk_hull_box(np.array([[0.1, 0.2, 0.3]]), eye, z3, np.array([0.1, 0.2, 1.3]), z3)
+    assert abs(d - 1.0) <= 1e-12
+    # two vertices: point-segment
+    seg = np.array([[0.0, 0, 0], [1.0, 0, 0]])
+    for pt, want in (([0.5, 0.3, 0], 0.3), ([-0.4, 0.3, 0], 0.5), ([2.0, 0, 0], 1.0), ([0.25, 0, 0], 0.0)):
+        d, _ = bo.gjk_hull_box(seg, eye, z3, np.array(pt, float), z3)
+        assert abs(d - want) <= 1e-9
+    # planar square (a flat "hull"): distance to the plate, from above and from the side
+    sq = np.array([[-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0]], float)
+    for pt, want in (([0.2, 0.3, 0.7], 0.7), ([2.0, 0, 0], 1.0), ([2.0, 2.0, 0], 2 ** 0.5), ([0.3, -0.2, 0], 0.0)):
+        d, _ = bo.gjk_hull_box(sq, eye, z3, np.array(pt, float), z3)
+        assert abs(d - want) <= 1e-9
+    # duplicated / interior vertices do not change the answer
+    rng = np.random.default_rng(4)
+    cube = BOX_CORNERS * 0.5
+    noisy = np.concatenate([cube, cube, rng.uniform(-0.4, 0.4, (50, 3))])
+    for _ in range(100):
+        pt = rng.normal(size=3)
+        a, _ = bo.gjk_hull_box(cube, eye, z3, pt, z3)
+        b, it = bo.gjk_hull_box(noisy, eye, z3, pt, z3)
+        assert abs(a - b) <= 1e-12 and it <= 16
+    # the same cube against a box that touches it, overlaps it, and sits inside it
+    for c, want in (([1.0, 0, 0], 0.25), ([0.75, 0, 0], 0.0), ([0.6, 0.1, 0], 0.0), ([0.0, 0, 0], 0.0)):
+        d, _ = bo.gjk_hull_box(cube, eye, z3, np.array(c, float), np.full(3, 0.25))
+        assert abs(d - want) <= 1e-12
+
+
+def test_loader_mesh_edge_cases(tmp_path):
+    """Non-uniform and negative mesh scales, a mesh referenced by an absolute path, and a link with two collision
+    elements (mesh + primitive): shape order, vertex ranges and bounding data stay consistent."""
+    (tmp_path / 'm').mkdir()
+    cube = str(tmp_path / 'm' / 'cube.stl')
+    write_box_mesh(cube, (0.5, 0.5, 0.5), 'stl_binary')
+
+    def geom(i):
+        if i == 1:
+            return f'<mesh filename="{cube}" scale="0.1 -0.2 0.3"/>'          # absolute path, mirrored in y
+        if i == 2:
+            return '<mesh filename="m/cube.stl" scale="0.05 0.05 0.05"/>'
+        return '<sphere radius="0.04"/>'
+    path = write_test_arm(str(tmp_path), geom)
+    text = open(path).read().replace(
+        '</link><link name="l3">', '<collision><origin xyz="0 0 0.2"/><geometry><box size="0.02 0.02 0.02"/></geometry>'
+                                   '</collision></link><link name="l3">')
+    open(path, 'w').write(text)
+    m = load_urdf(path)
+    assert list(m.s_link) == [0, 1, 1, 2] and list(m.s_type) == [SHAPE_HULL, SHAPE_HULL, SHAPE_BOX, 1]
+    assert list(m.s_vn) == [8, 8, 0, 0] and list(m.s_v0) == [0, 8, 16, 16] and m.verts.shape == (16, 3)
+    assert np.allclose(np.abs(m.verts[:8]).max(axis=0), [0.05, 0.1, 0.15])
+    assert np.allclose(np.abs(m.verts[8:]).max(axis=0), [0.025, 0.025, 0.025])
+    orc = bo.BulletOracle(m, 2, 3)
+    lo, ee, _ = orc.distances(np.zeros(3), [0.5, 0.5, 0.5], [0.0, 0.0, 1.2])
+    assert np.all(np.isfinite(lo)) and lo.max() < 10.0 and np.isfinite(ee)
