@@ -10,15 +10,18 @@ importable (an optimisation of the support loop, not a change of the shape).
 """
 from __future__ import annotations
 
+import logging
 import os
 import struct
-from typing import List, Optional
+from typing import List, Optional, Tuple
 
 import numpy as np
 
 HULL_MARGIN = 0.001            # gUrdfDefaultCollisionMargin of pybullet's importer
 CYLINDER_STEPS = 32            # rim points per end cap of an imported <cylinder>
-MAX_SHAPE_VERTS = 4096         # per shape, after hull reduction
+MAX_SHAPE_VERTS = 512          # per shape: hulls with more vertices are thinned to their support points (below)
+
+logger = logging.getLogger(__name__)
 
 
 class MeshError(Exception):
@@ -83,8 +86,35 @@ def convex_vertex_cloud(verts: np.ndarray) -> np.ndarray:
         except ImportError:
             pass
     if v.shape[0] > MAX_SHAPE_VERTS:
-        raise MeshError(f'convex hull with {v.shape[0]} vertices (limit {MAX_SHAPE_VERTS}): simplify the collision mesh')
+        n_full = v.shape[0]
+        v, dev = thin_vertex_cloud(v, MAX_SHAPE_VERTS)
+        logger.warning(f'collision hull with {n_full} vertices thinned to {v.shape[0]} support points '
+                       f'(the thinned hull lies inside the original, at most {dev * 1e3:.3f} mm from it)')
     return v
+
+
+def _fibonacci_directions(n: int) -> np.ndarray:
+    k = np.arange(n) + 0.5
+    phi = np.arccos(1.0 - 2.0 * k / n)
+    th = np.pi * (1.0 + 5.0 ** 0.5) * k
+    return np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], axis=1)
+
+
+def thin_vertex_cloud(verts: np.ndarray, budget: int) -> Tuple[np.ndarray, float]:
+    """At most ``budget`` vertices of a convex cloud: the support points of ``budget`` evenly spread directions plus the
+    six axis extremes (scaled to the cloud's bounding box so that thin shapes are sampled evenly too).  The result is a
+    subset of the hull's vertices, so its hull lies inside the original; the second return value is the largest gap
+    between the two support functions over a dense direction set (the Hausdorff distance of the hulls, sampled)."""
+    v = np.asarray(verts, np.float64)
+    c = 0.5 * (v.min(axis=0) + v.max(axis=0))
+    ext = np.maximum(0.5 * (v.max(axis=0) - v.min(axis=0)), 1e-12)
+    dirs = _fibonacci_directions(max(budget - 6, 8)) / ext          # even coverage of the normalised shape
+    dirs = np.concatenate([dirs, np.eye(3), -np.eye(3)])
+    keep = np.unique(np.argmax((v - c) @ dirs.T, axis=0))
+    thin = v[np.sort(keep)][:budget]
+    probe = _fibonacci_directions(8192)
+    gap = (v @ probe.T).max(axis=0) - (thin @ probe.T).max(axis=0)
+    return thin, float(gap.max())
 
 
 def cylinder_vertex_cloud(radius: float, length: float) -> np.ndarray:

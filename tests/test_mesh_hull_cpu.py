@@ -293,3 +293,26 @@ def test_loader_mesh_edge_cases(tmp_path):
     orc = bo.BulletOracle(m, 2, 3)
     lo, ee, _ = orc.distances(np.zeros(3), [0.5, 0.5, 0.5], [0.0, 0.0, 1.2])
     assert np.all(np.isfinite(lo)) and lo.max() < 10.0 and np.isfinite(ee)
+
+
+def test_large_hulls_are_thinned_to_support_points():
+    """Hulls above MAX_SHAPE_VERTS keep only support points: a subset of the original vertices (so the thinned hull is
+    inside the original), within the reported deviation, and GJK distances move by no more than that deviation."""
+    rng = np.random.default_rng(7)
+    k = np.arange(20000) + 0.5
+    phi, th = np.arccos(1 - 2 * k / 20000), np.pi * (1 + 5 ** 0.5) * k
+    pts = np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], axis=1) * [0.05, 0.07, 0.16]
+    thin, dev = mesh_io.thin_vertex_cloud(pts, mesh_io.MAX_SHAPE_VERTS)
+    # an inscribed 512-vertex polytope of a smooth body with a 0.16 m half axis cannot be closer than ~0.8 mm (sagitta)
+    assert thin.shape[0] <= mesh_io.MAX_SHAPE_VERTS and dev <= 1.5e-3
+    full_set = {tuple(p) for p in pts}
+    assert all(tuple(p) in full_set for p in thin)
+    cloud = mesh_io.convex_vertex_cloud(pts)                 # the loader's entry point applies the same thinning
+    assert cloud.shape[0] <= mesh_io.MAX_SHAPE_VERTS
+    eye, z3 = np.eye(3).reshape(9), np.zeros(3)
+    for _ in range(50):
+        q = rng.normal(size=3)
+        q *= rng.uniform(0.2, 0.5) / np.linalg.norm(q)
+        a, _ = bo.gjk_hull_box(pts, eye, z3, q, z3)
+        b, _ = bo.gjk_hull_box(thin, eye, z3, q, z3)
+        assert -1e-12 <= b - a <= dev + 1e-9
