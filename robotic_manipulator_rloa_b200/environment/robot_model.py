@@ -17,6 +17,7 @@ Collision geometry: ``<sphere>``, ``<capsule>``, ``<box>`` primitives, and — l
 """
 from __future__ import annotations
 
+import logging
 import math
 import os
 import xml.etree.ElementTree as ET
@@ -32,6 +33,8 @@ SHAPE_SPHERE, SHAPE_CAPSULE, SHAPE_BOX, SHAPE_HULL = 1, 2, 3, 4
 MAX_LINKS = 32
 MAX_SHAPES = 32
 MAX_VERTS = 16384              # hull vertices per model (RLOA_MAX_HULL_VERTS)
+
+logger = logging.getLogger(__name__)
 
 DATA_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'data')
 
@@ -343,6 +346,13 @@ def load_urdf(path: str) -> RobotModel:
         if dyn is not None:
             j.damping = float(dyn.get('damping', 0.0))
         joints.append(j)
+    children = {j.child for j in joints}
+    for name, l in links.items():
+        if name not in children and l.mass > 0:
+            # the reference calls p.loadURDF(file) without useFixedBase (environment.py:229): a root link with mass
+            # would be a free-floating base there and fall under gravity; this simulator keeps every base fixed
+            logger.warning(f'root link "{name}" has mass {l.mass}: PyBullet would treat it as a free-floating base '
+                           f'(loadURDF without useFixedBase); the B200 simulator keeps the base fixed')
     return _compile(links, joints, np.eye(3), np.zeros(3))
 
 
