@@ -283,7 +283,7 @@ def _parse_geometry(geom: ET.Element, R: np.ndarray, p: np.ndarray, sdf: bool, m
         if not uri:
             raise ModelError('<mesh> collision element without a file name')
         try:
-            v = mesh_io.load_mesh_vertices(mesh_io.resolve_mesh_file(uri.strip(), model_dir, [DATA_PATH]))
+            v = mesh_io.load_mesh_vertices(mesh_io.resolve_mesh_file(uri.strip(), model_dir, [d for d in (_pybullet_data_path(), DATA_PATH) if d]))
             v = mesh_io.convex_vertex_cloud(v * np.asarray(scale))
         except mesh_io.MeshError as err:
             raise ModelError(str(err))
@@ -429,19 +429,37 @@ def load_sdf(path: str) -> RobotModel:
     return _compile(links, joints, Rb, pb)
 
 
+def _pybullet_data_path() -> Optional[str]:
+    """The real asset directory when the user's machine has it (the reference adds it to PyBullet's search path,
+    environment.py:210); RLOA_ASSETS=standin forces the models shipped with this package."""
+    if os.environ.get('RLOA_ASSETS', '').lower() == 'standin':
+        return None
+    try:
+        import pybullet_data
+        return pybullet_data.getDataPath()
+    except Exception:       # not installed (the build image), or a broken install
+        return None
+
+
 def resolve_manipulator_file(manipulator_file: str) -> str:
-    """File lookup: as given, else relative to the package data dir (pybullet_data stand-in)."""
+    """File lookup: as given, else relative to pybullet_data when it is installed, else relative to the package data
+    dir (the stand-in assets)."""
     if os.path.isfile(manipulator_file):
         return manipulator_file
-    cand = os.path.join(DATA_PATH, manipulator_file)
-    if os.path.isfile(cand):
-        return cand
-    # a path that ends in a known pybullet_data relative name, e.g. <pybullet_data>/kuka_iiwa/x.sdf
-    parts = manipulator_file.replace('\\', '/').split('/')
-    for k in range(len(parts) - 1, 0, -1):
-        cand = os.path.join(DATA_PATH, *parts[k - 1:])
+    roots = [d for d in (_pybullet_data_path(), DATA_PATH) if d]
+    for root in roots:
+        cand = os.path.join(root, manipulator_file)
         if os.path.isfile(cand):
+            if root is not DATA_PATH:
+                logger.info(f'loading {manipulator_file} from pybullet_data ({root})')
             return cand
+    # a path that ends in a known relative name, e.g. <somewhere>/pybullet_data/kuka_iiwa/x.sdf
+    parts = manipulator_file.replace('\\', '/').split('/')
+    for root in roots:
+        for k in range(len(parts) - 1, 0, -1):
+            cand = os.path.join(root, *parts[k - 1:])
+            if os.path.isfile(cand):
+                return cand
     raise ModelError(f'file not found: {manipulator_file}')
 
 

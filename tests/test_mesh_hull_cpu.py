@@ -3,6 +3,8 @@ CPU tests of the mesh front end and of the oracle's GJK res
 <mesh> / <cylinder> collision elements as convex vertex clouds, and the hull / box distance queries against an
 independent quadratic-programming solution and against the closed-form primitives.
 """
+import os
+
 import numpy as np
 import pytest
 from scipy.optimize import minimize
@@ -316,3 +318,24 @@ def test_large_hulls_are_thinned_to_support_points():
         a, _ = bo.gjk_hull_box(pts, eye, z3, q, z3)
         b, _ = bo.gjk_hull_box(thin, eye, z3, q, z3)
         assert -1e-12 <= b - a <= dev + 1e-9
+
+
+def test_real_pybullet_data_is_preferred_when_installed(tmp_path, monkeypatch):
+    """With pybullet_data importable, relative names resolve there first (the reference's search path,
+    environment.py:210); RLOA_ASSETS=standin keeps the shipped models."""
+    import sys
+    import types
+    from robotic_manipulator_rloa_b200.environment import robot_model as rm
+    data = tmp_path / 'pbdata'                   # not the CWD: a relative name must not resolve "as given"
+    (data / 'kuka_iiwa').mkdir(parents=True)
+    fake_file = data / 'kuka_iiwa' / 'kuka_with_gripper2.sdf'
+    fake_file.write_text(open(os.path.join(rm.DATA_PATH, 'kuka_iiwa', 'kuka_with_gripper2.sdf')).read())
+    fake = types.ModuleType('pybullet_data')
+    fake.getDataPath = lambda: str(data)
+    monkeypatch.setitem(sys.modules, 'pybullet_data', fake)
+    monkeypatch.delenv('RLOA_ASSETS', raising=False)
+    assert rm.resolve_manipulator_file('kuka_iiwa/kuka_with_gripper2.sdf') == str(fake_file)
+    assert rm.resolve_manipulator_file('franka_panda/panda.urdf').startswith(rm.DATA_PATH)     # not in the fake dir
+    monkeypatch.setenv('RLOA_ASSETS', 'standin')
+    assert rm.resolve_manipulator_file('kuka_iiwa/kuka_with_gripper2.sdf').startswith(rm.DATA_PATH)
+    assert rm.load_manipulator('kuka_iiwa/kuka_with_gripper2.sdf').nl == 14
