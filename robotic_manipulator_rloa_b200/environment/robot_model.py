@@ -463,10 +463,22 @@ def resolve_manipulator_file(manipulator_file: str) -> str:
     raise ModelError(f'file not found: {manipulator_file}')
 
 
-def load_manipulator(manipulator_file: str) -> RobotModel:
-    path = resolve_manipulator_file(manipulator_file)
+def _load_file(path: str) -> RobotModel:
     if path.endswith('.urdf'):
         return load_urdf(path)
     if path.endswith('.sdf'):
         return load_sdf(path)
     raise ModelError('The file extension is neither .sdf nor .urdf')
+
+
+def load_manipulator(manipulator_file: str) -> RobotModel:
+    path = resolve_manipulator_file(manipulator_file)
+    try:
+        return _load_file(path)
+    except ModelError as err:
+        # a pybullet_data file this front end cannot digest: fall back to the shipped stand-in of the same name, loudly
+        standin = os.path.join(DATA_PATH, manipulator_file)
+        if not path.startswith(DATA_PATH) and not os.path.isfile(manipulator_file) and os.path.isfile(standin):
+            logger.warning(f'{path} could not be loaded ({err}); using the stand-in model {standin} instead')
+            return _load_file(standin)
+        raise

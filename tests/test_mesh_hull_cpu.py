@@ -339,3 +339,20 @@ def test_real_pybullet_data_is_preferred_when_installed(tmp_path, monkeypatch):
     monkeypatch.setenv('RLOA_ASSETS', 'standin')
     assert rm.resolve_manipulator_file('kuka_iiwa/kuka_with_gripper2.sdf').startswith(rm.DATA_PATH)
     assert rm.load_manipulator('kuka_iiwa/kuka_with_gripper2.sdf').nl == 14
+
+
+def test_unloadable_pybullet_data_file_falls_back_to_the_stand_in(tmp_path, monkeypatch):
+    import sys
+    import types
+    from robotic_manipulator_rloa_b200.environment import robot_model as rm
+    data = tmp_path / 'pbdata'
+    (data / 'kuka_iiwa').mkdir(parents=True)
+    (data / 'kuka_iiwa' / 'kuka_with_gripper2.sdf').write_text('<sdf version="1.6"><model name="m"><link name="a"/>'
+                                                              '<link name="b"/></model></sdf>')       # two roots
+    fake = types.ModuleType('pybullet_data')
+    fake.getDataPath = lambda: str(data)
+    monkeypatch.setitem(sys.modules, 'pybullet_data', fake)
+    monkeypatch.delenv('RLOA_ASSETS', raising=False)
+    assert rm.load_manipulator('kuka_iiwa/kuka_with_gripper2.sdf').nl == 14          # the stand-in
+    with pytest.raises(ModelError):                                                   # an explicit path gets no fallback
+        rm.load_manipulator(str(data / 'kuka_iiwa' / 'kuka_with_gripper2.sdf'))
