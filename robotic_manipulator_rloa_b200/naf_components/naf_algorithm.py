@@ -649,9 +649,13 @@ class VectorLoop:
 
     def run_steps(self, k: int, use_graph: bool = True) -> None:
         """k iterations with auto-reset; pairs go through the CUDA graph when it is (or can be) captured."""
-        if use_graph and self._graph is not None and k >= 1 and (self._odd or self._par != self._graph_par):
-            self.step()                    # an odd number of eager iterations since the capture: realign the buffers
-            k -= 1
+        if use_graph and self._graph is not None:
+            off_state, off_tick = bool(self._odd), self._par != self._graph_par
+            if off_state != off_tick:      # step(auto_reset=False) calls since the capture moved only one of the two
+                self._graph = None         # phases: no eager iteration can realign them, capture again instead
+            elif off_state and k >= 1:
+                self.step()                # an odd number of eager iterations since the capture: realign the buffers
+                k -= 1
         if use_graph and k >= 2 and not self._graph_failed and self.capture():
             while k >= 2:
                 self.replay_pair()
