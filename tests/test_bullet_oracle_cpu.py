@@ -122,3 +122,43 @@ def test_joint_limits_hold():
     for _ in range(40):
         orc.batch_step(q, qd, a, cfg['involved'], 200.0, [5, 5, 5], [5, 5, 6])
     assert q[0, 1] <= model.upper[1] + 2e-3 and abs(qd[0, 1]) <= 5e-2
+
+
+def test_saturated_step_satisfies_the_lcp_optimality_conditions():
+    """Whatever sweep order the solver uses, the solution of one step must satisfy the complementarity conditions of the
+    motor rows (no joint limit active here).  The joint-space impulse is recovered independently of the solver from
+    lambda = M (qd' - qd_free), with M from the CRBA and the free velocity from the ABA; then per motor row
+      |lambda| <  max impulse  ->  the joint moves at its target velocity  v* = kp (q_des - q) / dt + qd_des
+      |lambda| == max impulse  ->  the impulse pushes towards the target (sign(lambda) = sign(v* - qd'))
+    up to the solver's own stopping residual (1e-7 on the squared velocity change)."""
+    cfg = KUKA
+    model, orc = make_oracle(cfg)
+    step_motors(orc, cfg)
+    dt, nl = orc.m.dt, model.nl
+    mov = np.nonzero(np.asarray(model.jtype) != 0)[0]
+    n = 200
+    q0, qd0 = random_states(model, n, seed=17, vel=2.0, frac_limit=0.8, held=cfg['fixed'])
+    rng = np.random.default_rng(18)
+    actions = rng.uniform(-1, 1, (n, 6))
+    q, qd = q0.copy(), qd0.copy()
+    _, _, _, iters = orc.batch_step(q, qd, actions, cfg['involved'], 200.0, cfg['obstacle'], cfg['target'], nthreads=4)
+    sat_rows = free_rows = 0
+    for e in range(n):
+        if iters[e] >= 50:                                    # not converged within Bullet's cap: nothing to check
+            continue
+        qs = qd0[e] + dt * orc.aba(q0[e], qd0[e])             # free velocity (no clamp reached at these speeds)
+        M = orc.crba(q0[e])[np.ix_(mov, mov)]
+        lam = M @ (qd[e] - qs)[mov]
+        for r, j in enumerate(mov):
+            if j in cfg['involved']:
+                vstar, mx = actions[e, cfg['involved'].index(j)], 200.0 * dt
+            else:                                             # POSITION_CONTROL target 0: kp 0.1, force 1e5
+                vstar, mx = 0.1 * (0.0 - q0[e, j]) / dt, 100000.0 * dt
+            assert abs(lam[r]) <= mx * (1 + 1e-6) + 1e-9
+            if abs(lam[r]) < mx * (1 - 1e-6):
+                free_rows += 1
+                assert abs(qd[e, j] - vstar) <= 3e-3
+            else:
+                sat_rows += 1
+                assert np.sign(lam[r]) == np.sign(vstar - qd[e, j])
+    assert sat_rows > 50 and free_rows > 500
