@@ -162,3 +162,47 @@ def test_saturated_step_satisfies_the_lcp_optimality_conditions():
                 sat_rows += 1
                 assert np.sign(lam[r]) == np.sign(vstar - qd[e, j])
     assert sat_rows > 50 and free_rows > 500
+
+
+def test_closed_form_distances_against_gjk():
+    """The closed forms behind get_reward / is_terminal_state (capsule-vs-cube = exact segment/box distance, box-vs-sphere
+    = signed point/box distance, capsule-vs-sphere = point/segment) against the GJK restatement, which is itself
+    pinned to a quadratic-programming solution (tests/test_mesh_hull_cpu.py)."""
+    from helpers import BOX_CORNERS
+    from oracle.bullet_oracle import gjk_hull_box
+    cfg = KUKA
+    model, orc = make_oracle(cfg)
+    rng = np.random.default_rng(23)
+    q, _ = random_states(model, 150, seed=23)
+    eye, z3 = np.eye(3).reshape(9), np.zeros(3)
+    half = np.full(3, 0.025)
+    checked_box = 0
+    for e in range(150):
+        Rw, pw = orc.fk(q[e])
+        ee_pos = pw[cfg['ee']]
+        target = ee_pos + rng.uniform(-0.15, 0.15, 3)
+        obstacle = pw[rng.integers(0, model.nl)] + rng.uniform(-0.2, 0.2, 3)
+        lo, ee, _ = orc.distances(q[e], obstacle, target)
+        for s in range(model.ns):
+            l, kind = int(model.s_link[s]), int(model.s_type[s])
+            R = Rw[l] @ model.s_R[s].reshape(3, 3)
+            p = pw[l] + Rw[l] @ model.s_p[s]
+            if kind == 2:                                    # capsule: a segment with a radius
+                ends = np.stack([p - model.s_dim[s][1] * R[:, 2], p + model.s_dim[s][1] * R[:, 2]])
+                core, _ = gjk_hull_box(ends, eye, z3, obstacle, z3)
+                want = core - model.s_dim[s][0] - 0.075
+                if l == cfg['ee']:
+                    core_t, _ = gjk_hull_box(ends, eye, z3, target, half)
+                    assert abs(ee - (core_t - model.s_dim[s][0])) <= 1e-9
+            elif kind == 1:
+                want = np.linalg.norm(obstacle - p) - model.s_dim[s][0] - 0.075
+            else:                                            # box: compare where the sphere centre is outside the box
+                core, _ = gjk_hull_box(BOX_CORNERS * model.s_dim[s], R.reshape(9), p, obstacle, z3)
+                if core <= 1e-9:
+                    continue
+                want = core - 0.075
+                checked_box += 1
+            only = [t for t in range(model.ns) if int(model.s_link[t]) == l]
+            if len(only) == 1:                               # the per-link value is the minimum over the link's shapes
+                assert abs(lo[l] - want) <= 1e-9, (l, kind)
+    assert checked_box > 20
