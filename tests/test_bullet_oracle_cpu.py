@@ -206,3 +206,45 @@ def test_closed_form_distances_against_gjk():
             if len(only) == 1:                               # the per-link value is the minimum over the link's shapes
                 assert abs(lo[l] - want) <= 1e-9, (l, kind)
     assert checked_box > 20
+
+
+@pytest.mark.parametrize('cfg', [KUKA, PANDA], ids=['kuka', 'panda'])
+def test_aba_against_the_euler_lagrange_equations(cfg):
+    """Independent of the Newton-Euler recursions: with Bullet's velocity drag and the joint damping switched off, the
+    ABA accelerations must solve  M qdd + Mdot qd - dT/dq + dV/dq = tau  where M(q) is the CRBA mass matrix,
+    T = 1/2 qd^T M qd and V = -sum_i m_i g . p_i(q) comes from the forward kinematics; derivatives by central
+    differences.  This pins the Coriolis / centrifugal and gravity terms (signs, frames, COM offsets)."""
+    model, orc = make_oracle(cfg)                         # KUKA: SDF, base pose, gripper tree; Panda: prismatic fingers
+    m = orc.m
+    m.lin_damp, m.ang_damp = 0.0, 0.0
+    for i in range(model.nl):
+        m.damping[i] = 0.0
+    mov = np.nonzero(np.asarray(model.jtype) != 0)[0]
+    g = np.array([m.gravity[0], m.gravity[1], m.gravity[2]])
+    mass = np.asarray(model.mass, float)
+
+    def M_of(q):
+        return orc.crba(q)[np.ix_(mov, mov)]
+
+    def V_of(q):
+        return -float(sum(mass[i] * (g @ orc.fk(q)[1][i]) for i in range(model.nl)))
+
+    q_all, qd_all = random_states(model, 5, seed=29, vel=1.5, frac_limit=0.7)
+    rng = np.random.default_rng(30)
+    h = 1e-5
+    for e in range(5):
+        q, qd = q_all[e], qd_all[e]
+        tau = np.zeros(model.nl); tau[mov] = rng.uniform(-3, 3, len(mov))
+        v = qd[mov]
+        dM = []
+        dV = np.zeros(len(mov))
+        for r, j in enumerate(mov):
+            qp, qm = q.copy(), q.copy()
+            qp[j] += h; qm[j] -= h
+            dM.append((M_of(qp) - M_of(qm)) / (2 * h))
+            dV[r] = (V_of(qp) - V_of(qm)) / (2 * h)
+        Mdot_v = sum(dM[r] * v[r] for r in range(len(mov))) @ v
+        dT = np.array([0.5 * v @ dM[r] @ v for r in range(len(mov))])
+        want = np.linalg.solve(M_of(q), tau[mov] - Mdot_v + dT - dV)
+        got = orc.aba(q, qd, tau)[mov]
+        assert np.abs(got - want).max() <= 2e-5 * max(1.0, np.abs(want).max()), (e, np.abs(got - want).max())
