@@ -10,7 +10,7 @@ DESIGN.md section 2), so the restatement is held to what CAN be checked without 
 import numpy as np
 import pytest
 
-from helpers import KUKA, PANDA, make_oracle, random_states, step_motors
+from helpers import KUKA, PANDA, XARM6, make_oracle, random_states, step_motors
 
 
 @pytest.mark.parametrize('cfg', [KUKA, PANDA], ids=['kuka', 'panda'])
@@ -248,3 +248,83 @@ def test_aba_against_the_euler_lagrange_equations(cfg):
         want = np.linalg.solve(M_of(q), tau[mov] - Mdot_v + dT - dV)
         got = orc.aba(q, qd, tau)[mov]
         assert np.abs(got - want).max() <= 2e-5 * max(1.0, np.abs(want).max()), (e, np.abs(got - want).max())
+
+
+def _direct_urdf_com_positions(path, q_by_joint):
+    """Link COM world positions straight from the URDF semantics (joint origin, then the joint motion about / along the
+    axis given in the child frame, inertial origin) with scipy rotations — no COM-frame algebra, no loader code."""
+    import xml.etree.ElementTree as ET
+    from scipy.spatial.transform import Rotation as Rot
+    root = ET.parse(path).getroot()
+
+    def origin(node):
+        o = node.find('origin') if node is not None else None
+        xyz = np.array([float(v) for v in (o.get('xyz', '0 0 0') if o is not None else '0 0 0').split()])
+        rpy = [float(v) for v in (o.get('rpy', '0 0 0') if o is not None else '0 0 0').split()]
+        return Rot.from_euler('xyz', rpy).as_matrix(), xyz          # extrinsic x, y, z = URDF fixed-axis rpy
+
+    com = {l.get('name'): origin(l.find('inertial'))[1] for l in root.findall('link')}
+    children = {}
+    for j in root.findall('joint'):
+        children.setdefault(j.find('parent').get('link'), []).append(j)
+    child_links = {j.find('child').get('link') for j in root.findall('joint')}
+    base = [l.get('name') for l in root.findall('link') if l.get('name') not in child_links][0]
+    out = {}
+
+    def walk(link, R, p):
+        out[link] = p + R @ com[link]
+        for j in children.get(link, []):
+            Rj, pj = origin(j)
+            Rc, pc = R @ Rj, p + R @ pj
+            ax = j.find('axis')
+            axis = np.array([float(v) for v in ax.get('xyz').split()]) if ax is not None else np.array([1.0, 0, 0])
+            axis = axis / np.linalg.norm(axis)
+            qj = q_by_joint.get(j.get('name'), 0.0)
+            if j.get('type') in ('revolute', 'continuous'):
+                Rc = Rc @ Rot.from_rotvec(axis * qj).as_matrix()
+            elif j.get('type') == 'prismatic':
+                pc = pc + Rc @ (axis * qj)
+            walk(j.find('child').get('link'), Rc, pc)
+
+    walk(base, np.eye(3), np.zeros(3))
+    return out
+
+
+@pytest.mark.parametrize('cfg', [PANDA, XARM6], ids=['panda', 'xarm6'])
+def test_loader_and_fk_against_direct_urdf_kinematics(cfg):
+    """The loader moves every link frame to its centre of mass with principal axes and the oracle's FK works in those
+    frames (Bullet's btMultiBody layout); the COM world positions must equal a direct walk of the URDF tree."""
+    from robotic_manipulator_rloa_b200.environment.robot_model import resolve_manipulator_file
+    model, orc = make_oracle(cfg)
+    path = resolve_manipulator_file(cfg['file'])
+    q_all, _ = random_states(model, 6, seed=31, frac_limit=0.9)
+    for e in range(6):
+        want = _direct_urdf_com_positions(path, {model.joint_names[i]: q_all[e, i] for i in range(model.nl)})
+        _, pw = orc.fk(q_all[e])
+        for i in range(model.nl):
+            assert np.abs(pw[i] - want[model.link_names[i]]).max() <= 1e-9, (model.link_names[i], pw[i], want[model.link_names[i]])
+
+
+@pytest.mark.parametrize('cfg', [KUKA, PANDA], ids=['kuka', 'panda'])
+def test_mass_matrix_against_the_kinetic_energy_of_the_links(cfg):
+    """1/2 qd^T M(q) qd (CRBA) must equal sum_i 1/2 m_i |v_i|^2 + 1/2 w_i^T R_i I_i R_i^T w_i with the link COM
+    velocities and angular velocities taken by central differences of the forward kinematics along qd."""
+    model, orc = make_oracle(cfg)
+    mov = np.nonzero(np.asarray(model.jtype) != 0)[0]
+    mass, I = np.asarray(model.mass, float), np.asarray(model.inertia, float)
+    q_all, qd_all = random_states(model, 6, seed=37, vel=1.0, frac_limit=0.8)
+    h = 1e-6
+    for e in range(6):
+        q, qd = q_all[e], qd_all[e]
+        Rp, pp = orc.fk(q + h * qd)
+        Rm, pm = orc.fk(q - h * qd)
+        R0, _ = orc.fk(q)
+        T = 0.0
+        for i in range(model.nl):
+            v = (pp[i] - pm[i]) / (2 * h)
+            W = (Rp[i] - Rm[i]) / (2 * h) @ R0[i].T                       # [w]x = Rdot R^T
+            w = np.array([W[2, 1] - W[1, 2], W[0, 2] - W[2, 0], W[1, 0] - W[0, 1]]) * 0.5
+            wl = R0[i].T @ w
+            T += 0.5 * mass[i] * (v @ v) + 0.5 * (wl * I[i]) @ wl
+        M = orc.crba(q)[np.ix_(mov, mov)]
+        assert abs(0.5 * qd[mov] @ M @ qd[mov] - T) <= 1e-7 * max(1.0, T)
