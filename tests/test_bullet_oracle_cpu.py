@@ -328,3 +328,60 @@ def test_mass_matrix_against_the_kinetic_energy_of_the_links(cfg):
             T += 0.5 * mass[i] * (v @ v) + 0.5 * (wl * I[i]) @ wl
         M = orc.crba(q)[np.ix_(mov, mov)]
         assert abs(0.5 * qd[mov] @ M @ qd[mov] - T) <= 1e-7 * max(1.0, T)
+
+
+def test_sdf_loader_and_fk_against_direct_sdf_kinematics():
+    """The same pin for the SDF front end (the KUKA asset): SDF gives absolute link poses at q = 0 and joint axes in
+    the child frame; the COM world positions from a direct walk must equal the loader + oracle FK."""
+    import xml.etree.ElementTree as ET
+    from scipy.spatial.transform import Rotation as Rot
+    from robotic_manipulator_rloa_b200.environment.robot_model import resolve_manipulator_file
+    cfg = KUKA
+    model, orc = make_oracle(cfg)
+    sdf = ET.parse(resolve_manipulator_file(cfg['file'])).getroot().find('.//model')
+
+    def pose(node):
+        v = [float(x) for x in (node.text if node is not None else '0 0 0 0 0 0').split()]
+        return Rot.from_euler('xyz', v[3:]).as_matrix(), np.array(v[:3])
+
+    Rm, pm = pose(sdf.find('pose'))
+    zero, com = {}, {}
+    for l in sdf.findall('link'):
+        Rl, pl = pose(l.find('pose'))
+        zero[l.get('name')] = (Rm @ Rl, pm + Rm @ pl)
+        com[l.get('name')] = pose(l.find('inertial').find('pose'))[1] if l.find('inertial') is not None else np.zeros(3)
+    joints = {j.findtext('child'): j for j in sdf.findall('joint') if j.findtext('parent') != 'world'}
+    q_all, _ = random_states(model, 6, seed=41, frac_limit=0.9)
+    for e in range(6):
+        qj = {model.joint_names[i]: q_all[e, i] for i in range(model.nl)}
+        world = {}
+
+        def place(link):
+            if link in world:
+                return world[link]
+            if link not in joints:
+                world[link] = zero[link]
+                return world[link]
+            j = joints[link]
+            Rp, pp = place(j.findtext('parent'))
+            Rp0, pp0 = zero[j.findtext('parent')]
+            Rc0, pc0 = zero[link]
+            R = Rp @ (Rp0.T @ Rc0)
+            p = pp + Rp @ (Rp0.T @ (pc0 - pp0))
+            ax = j.find('axis')
+            if ax is not None and j.get('type') != 'fixed':
+                axis = np.array([float(x) for x in ax.findtext('xyz').split()])
+                if ax.findtext('use_parent_model_frame', '0').strip() in ('1', 'true'):
+                    axis = Rc0.T @ (Rm @ axis)
+                axis = axis / np.linalg.norm(axis)
+                if j.get('type') == 'prismatic':
+                    p = p + R @ (axis * qj[j.get('name')])
+                else:
+                    R = R @ Rot.from_rotvec(axis * qj[j.get('name')]).as_matrix()
+            world[link] = (R, p)
+            return world[link]
+
+        _, pw = orc.fk(q_all[e])
+        for i in range(model.nl):
+            R, p = place(model.link_names[i])
+            assert np.abs(pw[i] - (p + R @ com[model.link_names[i]])).max() <= 1e-9, model.link_names[i]
