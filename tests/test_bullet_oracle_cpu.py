@@ -385,3 +385,55 @@ def test_sdf_loader_and_fk_against_direct_sdf_kinematics():
         for i in range(model.nl):
             R, p = place(model.link_names[i])
             assert np.abs(pw[i] - (p + R @ com[model.link_names[i]])).max() <= 1e-9, model.link_names[i]
+
+
+def test_non_diagonal_inertia_tensors_survive_the_principal_axes_transform(tmp_path):
+    """A URDF whose links have full inertia tensors and rotated inertial frames: the loader diagonalises them into the
+    COM frame Bullet wants.  1/2 qd^T M qd from the loaded model must equal the kinetic energy computed directly from
+    the URDF quantities (mass, COM offset, R_inertial I R_inertial^T) on a direct walk of the tree."""
+    from scipy.spatial.transform import Rotation as Rot
+    from oracle.bullet_oracle import BulletOracle
+    from robotic_manipulator_rloa_b200.environment.robot_model import load_urdf
+    rng = np.random.default_rng(43)
+    links, joints, spec = ['<link name="l0"/>'], [], {}
+    axes = ['0 0 1', '0 1 0', '1 0 0', '0.6 0 0.8']
+    for i in range(1, 5):
+        A = rng.normal(size=(3, 3))
+        I = A @ A.T * 0.01 + np.eye(3) * 0.005                       # a full SPD tensor
+        com, rpy = rng.uniform(-0.05, 0.05, 3), rng.uniform(-0.8, 0.8, 3)
+        spec[f'l{i}'] = (1.0 + i * 0.3, com, Rot.from_euler('xyz', rpy).as_matrix(), I)
+        links.append(f'<link name="l{i}"><inertial><origin xyz="{com[0]} {com[1]} {com[2]}" rpy="{rpy[0]} {rpy[1]} {rpy[2]}"/>'
+                     f'<mass value="{1.0 + i * 0.3}"/><inertia ixx="{I[0, 0]}" ixy="{I[0, 1]}" ixz="{I[0, 2]}" iyy="{I[1, 1]}" '
+                     f'iyz="{I[1, 2]}" izz="{I[2, 2]}"/></inertial></link>')
+        o, r = rng.uniform(-0.2, 0.2, 3), rng.uniform(-0.5, 0.5, 3)
+        spec[f'j{i}'] = (o, Rot.from_euler('xyz', r).as_matrix(), np.array([float(v) for v in axes[i - 1].split()]))
+        joints.append(f'<joint name="j{i}" type="revolute"><parent link="l{i - 1}"/><child link="l{i}"/>'
+                      f'<origin xyz="{o[0]} {o[1]} {o[2]}" rpy="{r[0]} {r[1]} {r[2]}"/><axis xyz="{axes[i - 1]}"/>'
+                      f'<limit lower="-3" upper="3" effort="10" velocity="10"/></joint>')
+    path = str(tmp_path / 'arm.urdf')
+    open(path, 'w').write('<?xml version="1.0"?><robot name="a">' + ''.join(links) + ''.join(joints) + '</robot>')
+    model = load_urdf(path)
+    orc = BulletOracle(model, 3, 4)
+
+    def frames(q):                                   # URDF link frames and COM positions by a direct chain walk
+        R, p, out = np.eye(3), np.zeros(3), []
+        for i in range(1, 5):
+            o, Rj, ax = spec[f'j{i}']
+            p = p + R @ o
+            R = R @ Rj @ Rot.from_rotvec(ax / np.linalg.norm(ax) * q[i - 1]).as_matrix()
+            out.append((R.copy(), p + R @ spec[f'l{i}'][1]))
+        return out
+
+    h = 1e-6
+    for _ in range(5):
+        q, qd = rng.uniform(-2, 2, 4), rng.uniform(-1, 1, 4)
+        f0, fp, fm = frames(q), frames(q + h * qd), frames(q - h * qd)
+        T = 0.0
+        for i in range(4):
+            m, _, Ri, I = spec[f'l{i + 1}']
+            v = (fp[i][1] - fm[i][1]) / (2 * h)
+            W = (fp[i][0] - fm[i][0]) / (2 * h) @ f0[i][0].T
+            w = 0.5 * np.array([W[2, 1] - W[1, 2], W[0, 2] - W[2, 0], W[1, 0] - W[0, 1]])
+            Iw = f0[i][0] @ Ri @ I @ Ri.T @ f0[i][0].T
+            T += 0.5 * m * (v @ v) + 0.5 * w @ Iw @ w
+        assert abs(0.5 * qd @ orc.crba(q) @ qd - T) <= 1e-7 * max(1.0, T)
