@@ -43,3 +43,22 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
         assert 'no CPU fallback' in str(err)
     else:
         raise AssertionError('expected NativeLibraryError')
+
+
+def test_ctypes_structs_match_the_header_as_a_c_compiler_sees_it(tmp_path):
+    """sizeof / offsetof of the ABI structs from gcc on include/rloa_b200.h against the ctypes mirrors in _native.py."""
+    import subprocess
+    src = tmp_path / 'probe.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rloa_b200.h"\n'
+                   'int main(void) {\n'
+                   '  printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(rloa_model_desc), offsetof(rloa_model_desc, base_R),\n'
+                   '         offsetof(rloa_model_desc, ns), offsetof(rloa_model_desc, ee_link), offsetof(rloa_model_desc, n_verts),\n'
+                   '         offsetof(rloa_model_desc, verts), sizeof(rloa_step_config), sizeof(rloa_naf_hyper));\n'
+                   '  return 0;\n}\n')
+    exe = tmp_path / 'probe'
+    subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    M = _native.ModelDesc
+    want = [ctypes.sizeof(M), M.base_R.offset, M.ns.offset, M.ee_link.offset, M.n_verts.offset, M.verts.offset,
+            ctypes.sizeof(_native.StepConfig), ctypes.sizeof(_native.NafHyper)]
+    assert got == want
