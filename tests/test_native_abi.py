@@ -62,3 +62,26 @@ def test_ctypes_structs_match_the_header_as_a_c_compiler_sees_it(tmp_path):
     want = [ctypes.sizeof(M), M.base_R.offset, M.ns.offset, M.ee_link.offset, M.n_verts.offset, M.verts.offset,
             ctypes.sizeof(_native.StepConfig), ctypes.sizeof(_native.NafHyper)]
     assert got == want
+
+
+def test_binding_table_has_the_header_s_parameter_counts():
+    """Every prototype in include/rloa_b200.h against the ctypes table: same number of parameters, and pointer /
+    integer / float kinds in the same positions (a changed C signature must not go unnoticed on a machine without a GPU)."""
+    text = open(os.path.join(ROOT, 'include', 'rloa_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    protos = re.findall(r'\b(rloa_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', text, flags=re.S)
+    assert len(protos) >= 30
+    for name, params in protos:
+        params = ' '.join(params.split())
+        plist = [] if params in ('', 'void') else [p.strip() for p in params.split(',')]
+        restype, argtypes = _native.SIGNATURES[name]
+        assert len(argtypes) == len(plist), f'{name}: header has {len(plist)} parameters, the binding {len(argtypes)}'
+        for p, a in zip(plist, argtypes):
+            is_ptr = '*' in p
+            ptype = p.rsplit(' ', 1)[0]                      # drop the parameter name
+            if is_ptr:
+                assert a in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(a, 'contents') or hasattr(a, '_type_'), (name, p, a)
+            elif 'float' in ptype or 'double' in ptype:
+                assert a in (ctypes.c_float, ctypes.c_double), (name, p, a)
+            else:
+                assert a in (ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_size_t), (name, p, a)
