@@ -437,3 +437,57 @@ def test_non_diagonal_inertia_tensors_survive_the_principal_axes_transform(tmp_p
             Iw = f0[i][0] @ Ri @ I @ Ri.T @ f0[i][0].T
             T += 0.5 * m * (v @ v) + 0.5 * w @ Iw @ w
         assert abs(0.5 * qd @ orc.crba(q) @ qd - T) <= 1e-7 * max(1.0, T)
+
+
+def test_joint_limit_rows_satisfy_their_complementarity_conditions():
+    """Joints pushed a little past a limit (the velocity-level limit row of Bullet: target velocity
+    v_l = -penetration * erp / dt, impulse >= 0 towards the inside) together with the motor of the same joint.
+    With the total joint impulse tau = M (qd' - qd_free) recovered independently of the solver:
+      qd' > v_l  ->  the limit is inactive and tau is the motor's impulse (|tau| <= max)
+      qd' = v_l  ->  the limit impulse tau - lambda_motor is non-negative (towards the inside), the motor being saturated
+                     towards its own target
+      qd' < v_l  ->  never (the limit impulse cap of 100 is out of reach here)."""
+    cfg = KUKA
+    model, orc = make_oracle(cfg)
+    step_motors(orc, cfg)
+    dt, erp = orc.m.dt, orc.m.erp
+    mov = np.nonzero(np.asarray(model.jtype) != 0)[0]
+    lower, upper = np.asarray(model.lower), np.asarray(model.upper)
+    rng = np.random.default_rng(47)
+    n = 300
+    q0, qd0 = random_states(model, n, seed=47, vel=0.3, frac_limit=0.5, held=cfg['fixed'])
+    over = np.zeros((n, model.nl), int)                      # -1: below the lower limit, +1: above the upper one
+    for e in range(n):
+        for j in rng.choice(cfg['involved'], size=2, replace=False):
+            side = rng.choice([-1, 1])
+            q0[e, j] = (lower[j] if side < 0 else upper[j]) + side * rng.uniform(1e-4, 3e-3)
+            over[e, j] = side
+    actions = rng.uniform(-1, 1, (n, 6))
+    q, qd = q0.copy(), qd0.copy()
+    _, _, _, iters = orc.batch_step(q, qd, actions, cfg['involved'], 200.0, cfg['obstacle'], cfg['target'], nthreads=4)
+    active = inactive = 0
+    tol = 5e-3
+    for e in range(n):
+        if iters[e] >= 50:
+            continue
+        qs = qd0[e] + dt * orc.aba(q0[e], qd0[e])
+        tau = orc.crba(q0[e])[np.ix_(mov, mov)] @ (qd[e] - qs)[mov]
+        for r, j in enumerate(mov):
+            if over[e, j] == 0:
+                continue
+            s = -over[e, j]                                   # +1: the limit pushes towards +q (lower limit), -1 the other way
+            pen = (q0[e, j] - lower[j]) if over[e, j] < 0 else (upper[j] - q0[e, j])      # negative
+            v_l = -pen * erp / dt                             # >= 0, in the limit's own (inward) direction
+            v_in = s * qd[e, j]                               # joint velocity in that direction
+            assert v_in >= v_l - tol, (e, j, v_in, v_l)
+            mx = 200.0 * dt
+            vstar = actions[e, cfg['involved'].index(j)]
+            if v_in > v_l + tol:
+                inactive += 1
+                assert abs(tau[r]) <= mx * (1 + 1e-6) + 1e-9
+            else:
+                active += 1
+                lam_motor = mx * np.sign(vstar - qd[e, j]) if abs(vstar - qd[e, j]) > tol else None
+                if lam_motor is not None:
+                    assert s * (tau[r] - lam_motor) >= -1e-6, (e, j, tau[r], lam_motor)
+    assert active > 30 and inactive > 10, (active, inactive)
