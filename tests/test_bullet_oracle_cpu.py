@@ -270,9 +270,11 @@ def _direct_urdf_com_positions(path, q_by_joint):
     child_links = {j.find('child').get('link') for j in root.findall('joint')}
     base = [l.get('name') for l in root.findall('link') if l.get('name') not in child_links][0]
     out = {}
+    frames = {}
 
     def walk(link, R, p):
         out[link] = p + R @ com[link]
+        frames[link] = (R, p)
         for j in children.get(link, []):
             Rj, pj = origin(j)
             Rc, pc = R @ Rj, p + R @ pj
@@ -287,6 +289,11 @@ def _direct_urdf_com_positions(path, q_by_joint):
             walk(j.find('child').get('link'), Rc, pc)
 
     walk(base, np.eye(3), np.zeros(3))
+    shapes = {}                                   # link -> [(world rotation, world position) of every collision origin]
+    for l in root.findall('link'):
+        R, p = frames[l.get('name')]
+        shapes[l.get('name')] = [(R @ origin(c)[0], p + R @ origin(c)[1]) for c in l.findall('collision')]
+    out['__shapes__'] = shapes
     return out
 
 
@@ -300,9 +307,18 @@ def test_loader_and_fk_against_direct_urdf_kinematics(cfg):
     q_all, _ = random_states(model, 6, seed=31, frac_limit=0.9)
     for e in range(6):
         want = _direct_urdf_com_positions(path, {model.joint_names[i]: q_all[e, i] for i in range(model.nl)})
-        _, pw = orc.fk(q_all[e])
+        Rw, pw = orc.fk(q_all[e])
         for i in range(model.nl):
             assert np.abs(pw[i] - want[model.link_names[i]]).max() <= 1e-9, (model.link_names[i], pw[i], want[model.link_names[i]])
+        # collision shapes: the loader re-expresses every <collision><origin> in the link's COM frame
+        seen = {}
+        for s in range(model.ns):
+            l = int(model.s_link[s])
+            k = seen.get(l, 0)
+            seen[l] = k + 1
+            R_want, p_want = want['__shapes__'][model.link_names[l]][k]
+            assert np.abs(pw[l] + Rw[l] @ model.s_p[s] - p_want).max() <= 1e-9
+            assert np.abs(Rw[l] @ model.s_R[s].reshape(3, 3) - R_want).max() <= 1e-9
 
 
 @pytest.mark.parametrize('cfg', [KUKA, PANDA], ids=['kuka', 'panda'])
