@@ -107,7 +107,8 @@ def thin_vertex_cloud(verts: np.ndarray, budget: int) -> Tuple[np.ndarray, float
     between the two support functions over a dense direction set (the Hausdorff distance of the hulls, sampled)."""
     v = np.asarray(verts, np.float64)
     c = 0.5 * (v.min(axis=0) + v.max(axis=0))
-    ext = np.maximum(0.5 * (v.max(axis=0) - v.min(axis=0)), 1e-12)
+    ext = 0.5 * (v.max(axis=0) - v.min(axis=0))
+    ext = np.maximum(ext, max(1e-3 * float(ext.max()), 1e-12))     # flat clouds: keep the direction set balanced
     dirs = _fibonacci_directions(max(budget - 6, 8)) / ext          # even coverage of the normalised shape
     dirs = np.concatenate([dirs, np.eye(3), -np.eye(3)])
     keep = np.unique(np.argmax((v - c) @ dirs.T, axis=0))
