@@ -72,7 +72,27 @@ for k in range(n_rec):
     rec['ee_target'].append(CollisionDetector(CollisionObject(uid, cfg['ee']), [env.target]).compute_distances()[0])
     rec['com'].append([p.getLinkState(uid, l)[0] for l in range(nl)])
 
+# ---- 400-step trajectories (north_star: "400-step trajectory divergence reported") -----------------------------
+n_traj, T = 8, 400
+traj_q0 = np.zeros((n_traj, nl)); traj_qd0 = np.zeros((n_traj, nl))
+traj_actions = rng.uniform(-1, 1, (n_traj, T, len(cfg['involved'])))
+traj_q = np.zeros((n_traj, T, nl)); traj_qd = np.zeros((n_traj, T, nl))
+traj_done = np.zeros((n_traj, T), int)
+for k in range(n_traj):
+    for j in range(nl):
+        if movable[j] and j not in cfg['fixed']:
+            a, b = (lo[j], hi[j]) if lo[j] < hi[j] else (-np.pi, np.pi)
+            traj_q0[k, j] = 0.5 * (a + b) + 0.3 * (b - a) * rng.uniform(-1, 1)
+        p.resetJointState(uid, j, traj_q0[k, j], 0.0)
+    for t in range(T):
+        _, _, done = env.step(traj_actions[k, t])          # the recording does not stop at done: physics only
+        js = [p.getJointState(uid, j) for j in range(nl)]
+        traj_q[k, t] = [s[0] for s in js]; traj_qd[k, t] = [s[1] for s in js]
+        traj_done[k, t] = int(done)
+
 out = {k: np.asarray(v) for k, v in rec.items()}
+out.update(traj_q0=traj_q0, traj_qd0=traj_qd0, traj_actions=traj_actions, traj_q=traj_q, traj_qd=traj_qd,
+           traj_done=traj_done)
 out.update(model_to_entries(model))
 out['pybullet_api_version'] = np.asarray(p.getAPIVersion())
 out['robot'] = np.asarray(robot)
