@@ -68,8 +68,7 @@ __device__ __forceinline__ bool wait_peers(const unsigned long long* local_flags
         for (int r = 0; r < world && ok; r++) {
             if (r == rank) continue;
             while (ld_sys(local_flags + r) < want) {
-                if (clock64() - t0 > kXchgTimeoutCycles) { ok = 0; break; }
-                __nanosleep(64);
+                if (clock64() - t0 > kXchgTimeoutCycles) { ok = 0; break; }     // tight spin: the flag sits in local HBM / L2
             }
         }
         if (!ok) atomicExch(status, 1);
@@ -129,6 +128,7 @@ xchg_reduce_adam_kernel(XchgPeers P, float* __restrict__ sum_out, ParamTable pt,
                         unsigned* __restrict__ barrier, float* __restrict__ grad_norm_out, int* __restrict__ status) {
     __shared__ float red[256];
     __shared__ AdamCoef s_c;
+    __shared__ int s_bad;
     const int n = pt.offset[14];
     const unsigned long long t = (unsigned long long)(*step_ptr);             // already incremented by publish
     wait_peers(P.ready[P.rank], P.world, P.rank, t, status);
@@ -182,8 +182,13 @@ xchg_reduce_adam_kernel(XchgPeers P, float* __restrict__ sum_out, ParamTable pt,
         __threadfence();
         s_c = adam_coefficients(sq_partial, (long long)t, hp);
         if (blockIdx.x == 0 && grad_norm_out != nullptr) *grad_norm_out = s_c.norm;
+        // a wait that gave up (here or in any earlier update: the flag is sticky) means some peer's gradient may be
+        // stale: every block of every later launch skips the optimiser, so the ranks stop moving instead of drifting
+        // apart silently; rloa_xchg_status reports it
+        s_bad = *reinterpret_cast<volatile int*>(status);
     }
     __syncthreads();
+    if (s_bad) return;
     const AdamCoef c = s_c;
     // ---- clip + Adam + soft update of the elements this block summed (re-read from L2) ----
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n4; i += gridDim.x * 256) {

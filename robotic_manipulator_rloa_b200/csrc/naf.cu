@@ -1082,7 +1082,8 @@ extern "C" void rloa_naf_ws_destroy(rloa_naf_ws* ws);
 extern "C" int rloa_naf_ws_create(int32_t S, int32_t A, int32_t H, int32_t max_batch, rloa_naf_ws** out) {
     RLOA_REQUIRE(out != nullptr, "rloa_naf_ws_create: null out");
     RLOA_REQUIRE(S >= 1 && S <= 4096, "rloa_naf_ws_create: state_size out of range");
-    RLOA_REQUIRE(A >= 1 && A <= 10, "rloa_naf_ws_create: 1 <= action_size <= 10 supported (head outputs <= 64)");
+    // the fused head kernel computes outputs `lane` and `lane + 32`: A + 1 + A (A + 1) / 2 <= 64  <=>  A <= 9
+    RLOA_REQUIRE(A >= 1 && A + 1 + A * (A + 1) / 2 <= 64, "rloa_naf_ws_create: 1 <= action_size <= 9 supported (head outputs <= 64)");
     RLOA_REQUIRE(H >= 32 && H % 32 == 0 && H <= 1024, "rloa_naf_ws_create: hidden size must be a multiple of 32 (<= 1024)");
     RLOA_REQUIRE(max_batch >= 1, "rloa_naf_ws_create: max_batch >= 1 required");
     rloa_naf_ws* ws = new (std::nothrow) rloa_naf_ws();

@@ -109,9 +109,12 @@ class Environment:
                      f'and {self.target_pos} respectively')
         self._observation_space = np.zeros((9 + 2 * len(self.involved_joints),))
         self._action_space = np.zeros((len(self.involved_joints),))
+        # one process per GPU: every rank draws its own start poses
+        from ..utils import distributed as rdist
+        rank, world = rdist.world()
+        self.seed = int(seed) if world == 1 else rdist.rank_seed(int(seed), rank, 2)
         self._gen = torch.Generator(device=self.device)
-        self._gen.manual_seed(int(seed) + 0x5EED)
-        self.seed = int(seed)
+        self._gen.manual_seed((self.seed + 0x5EED) & 0x7FFFFFFFFFFFFFFF)
         n_init = self._n_init()
         pos = list(self.initial_joint_positions[:n_init]) if self.initial_joint_positions else [0.0] * n_init
         var = (list(self.initial_positions_variation_range[:n_init]) if self.initial_positions_variation_range

@@ -54,6 +54,9 @@ class BatchedSimulator:
         self.obs = torch.zeros(self.n_envs, self.obs_size, **f32)
         self.reward = torch.zeros(self.n_envs, **f32)
         self.done = torch.zeros(self.n_envs, dtype=torch.uint8, device=self.device)
+        # bumped by every call that drops the prepared half of the pipelined step on the host side (rloa_sim_prepare's
+        # `prepared` flag is baked into a captured CUDA graph): VectorLoop compares it before replaying a graph
+        self.generation = 0
 
     # ------------------------------------------------------------------------------------------
     def _stream(self) -> int:
@@ -91,6 +94,7 @@ class BatchedSimulator:
     def set_state(self, q, qd) -> None:
         q = self._f32(q, (self.n_envs, self.nl))
         qd = self._f32(qd, (self.n_envs, self.nl))
+        self.generation += 1
         N.check(self.lib.rloa_sim_set_state(self._h_sim, q.data_ptr(), qd.data_ptr(), self._stream()),
                 'rloa_sim_set_state')
 
@@ -106,6 +110,7 @@ class BatchedSimulator:
         N.check(self.lib.rloa_sim_set_motors(self._h_sim, *[N.ptr(t) for t in ts], self._stream()), 'rloa_sim_set_motors')
 
     def clear(self) -> None:
+        self.generation += 1
         N.check(self.lib.rloa_sim_clear(self._h_sim, self._stream()), 'rloa_sim_clear')
 
     def step(self, actions: torch.Tensor, active: Optional[torch.Tensor] = None, out=None,
@@ -153,6 +158,7 @@ class BatchedSimulator:
         init_targets = init_targets.contiguous()
         n_init = init_targets.shape[1]
         obs = self.obs if obs is None else obs
+        self.generation += 1
         N.check(self.lib.rloa_sim_reset(self._h_sim, N.ptr(mask), init_targets.data_ptr() if n_init else None, n_init,
                                         int(substeps), obs.data_ptr(), self._stream()), 'rloa_sim_reset')
         return obs

@@ -96,7 +96,13 @@ class NAFAgent:
         self.n_params = sum(p.numel() for p in self.qnetwork_main.parameters())
         self.optimizer = FusedAdam(self.n_params, learning_rate, self.device)
         n_envs = getattr(environment, 'n_envs', 1) if environment is not None else 1
-        self.memory = ReplayBuffer(buffer_size, batch_size, self.device, seed,
+        # one process per GPU: the network initialisation above shares `seed` (parameters start identical on every
+        # rank), exploration noise and replay sampling get per-rank streams — otherwise N ranks would compute the same
+        # rollout and the same gradient N times
+        self.rank, self.world_size = rdist.world()
+        self.noise_seed = seed if self.world_size == 1 else rdist.rank_seed(seed, self.rank, 0)
+        replay_seed = seed if self.world_size == 1 else rdist.rank_seed(seed, self.rank, 1)
+        self.memory = ReplayBuffer(buffer_size, batch_size, self.device, replay_seed,
                                    state_size if self.device.type == 'cuda' else None,
                                    action_size if self.device.type == 'cuda' else None, max_append=n_envs)
         self.update_t_step = 0
@@ -106,7 +112,7 @@ class NAFAgent:
         self._bufs = None
         self.last_loss = None
         self.last_grad_norm = None
-        self.rank, self.world_size = rdist.world()
+        self._ws_generation = 0                     # bumped when the workspace / trunk mode a captured graph baked in changes
         # N > 1: 'peer' = NVLink peer-memory exchange fused into the optimiser kernels (csrc/grad_exchange.cu),
         # 'nccl' = torch.distributed all-reduce between the two native calls (the baseline); RLOA_GRAD_EXCHANGE selects
         self.grad_exchange_mode = os.environ.get('RLOA_GRAD_EXCHANGE', 'peer')
@@ -124,6 +130,7 @@ class NAFAgent:
         if self._ws is None or self._ws.max_batch < rows:
             if self._ws is not None:
                 self._ws.close()
+            self._ws_generation += 1
             self._ws = NafWorkspace(self.state_size, self.action_size, self.layer_size, max(rows, self.batch_size, 256),
                                     self.device)
             if self.qnetwork_main.trunk_mode:
@@ -134,6 +141,7 @@ class NAFAgent:
         """0 = fp32 CUDA-core trunk (reference-exact), 1 = tcgen05 tensor-core trunk (bf16 operands)."""
         self.qnetwork_main.set_trunk_mode(int(mode))
         self.qnetwork_target.set_trunk_mode(int(mode))
+        self._ws_generation += 1
         if self._ws is not None:
             self._ws.set_trunk(int(mode))
 
@@ -225,7 +233,7 @@ class NAFAgent:
         p = self.qnetwork_main.native_params()
         # Philox step: the host call counter, or — inside the vectorised loop — the device counter alone, so that an
         # eager launch and a replay of the captured graph draw the same noise
-        N.check(ws.lib.rloa_naf_act(ws.handle, C.byref(p), states.data_ptr(), n, self.seed,
+        N.check(ws.lib.rloa_naf_act(ws.handle, C.byref(p), states.data_ptr(), n, self.noise_seed,
                                     self._act_calls if tick is None else 0, N.ptr(tick), float(self.noise_scale),
                                     out.data_ptr(), self._stream()), 'rloa_naf_act')
         if tick is None:
@@ -245,11 +253,12 @@ class NAFAgent:
         self.memory.add(state, action, reward, next_state, done)
         self._maybe_learn()
 
-    def _learn_due(self, pending: int = 0) -> bool:
+    def _learn_due(self, pending: int = 0, pending_exact: bool = True) -> bool:
         """The update gate of NAFAgent.step (naf_algorithm.py:147-150); advances the update_freq counter.
-        `pending` = transitions the caller is about to append before it learns."""
+        `pending` = transitions the caller is about to append before it learns (an upper bound when the append is
+        masked: pending_exact False)."""
         self.update_t_step = (self.update_t_step + 1) % self.update_freq
-        return self.update_t_step == 0 and len(self.memory) + pending > self.batch_size
+        return self.update_t_step == 0 and self.memory.gate_open(pending, pending_exact)
 
     def _maybe_learn(self, tick: Optional[torch.Tensor] = None) -> None:
         if self._learn_due():
@@ -328,26 +337,34 @@ class NAFAgent:
                 'rloa_naf_soft_update')
 
     # ------------------------------------------------------------------------------------------
-    def make_loop(self, frames: int, log_capacity: int, learn: bool = True) -> 'VectorLoop':
-        return VectorLoop(self, frames, log_capacity, learn)
+    def make_loop(self, frames: int, log_capacity: int, learn: bool = True, store: bool = True) -> 'VectorLoop':
+        """`store=False` (evaluation rollouts): transitions are not appended to the replay ring."""
+        return VectorLoop(self, frames, log_capacity, learn, store)
 
     def run(self, frames: int = 1000, episodes: int = 1000, verbose: bool = True) -> Dict[int, Tuple[float, int]]:
         """Training loop (naf_algorithm.py:228-292) over ``environment.n_envs`` arms in lock step.
         ``episodes`` counts completed episodes over all envs, numbered in completion order; with one env the
-        sequence of resets, steps, updates, log lines and checkpoints is the reference's."""
+        sequence of resets, steps, updates, log lines and checkpoints is the reference's.
+
+        One process per GPU (torchrun): ``episodes`` counts over ALL ranks.  Every learn() is a collective, so the exit
+        test uses the all-reduced count read at the same iteration on every rank — all ranks run the same number of
+        updates; each rank logs its own episodes, rank 0 alone writes checkpoints and model.p, and a gradient
+        exchange that timed out raises instead of letting the ranks drift apart."""
         self._require_cuda()
         env = self.environment
         n = env.n_envs
+        multi = self.world_size > 1
         logger.info('Training started')
         scores = {episode: (0, 0) for episode in range(1, episodes + 1)}
         loop = self.make_loop(frames, episodes + 2 * n + 1)
-        completed, start = 0, time.time()
+        completed, start = 0, time.time()       # local episodes recorded so far
+        total = 0                               # completed episodes over all ranks (== completed on a single rank)
         if n == 1:
             logger.info(f'Running Episode {completed + 1}')
         loop.reset_all(verbose)
         sync_every = 1 if n == 1 else (16 if n >= 256 else 4)      # iterations between host reads of the episode log
         it = 0
-        while completed < episodes:
+        while total < episodes:
             if n == 1 and verbose:
                 logger.info(f'Running frame {int(loop.frame.item()) + 1} in episode {completed + 1}')
                 logger.info(f'Current State: {loop.state[0].cpu().numpy()}')
@@ -362,7 +379,14 @@ class NAFAgent:
                 logger.info(f'Reward: {float(loop.reward.item())}\n')
             if it % sync_every:
                 continue
-            n_done = int(loop.log_count.item())          # the one host read of the loop
+            if multi:           # same iteration on every rank: one tiny all-reduce, then the host read
+                cnt = loop.log_count.to(torch.int64)
+                glob = cnt.clone()
+                rdist.dist.all_reduce(glob, op=rdist.dist.ReduceOp.SUM)
+                n_done, total = (int(x) for x in torch.stack([cnt[0], glob[0]]).cpu())
+                self._check_exchange()
+            else:
+                n_done = total = int(loop.log_count.item())          # the one host read of the loop
             if n_done <= completed:
                 continue
             hi = min(n_done, episodes)
@@ -376,20 +400,29 @@ class NAFAgent:
                     logger.info(f'Number of frames:                   {int(lf[k])}')
                     logger.info(f'Mean of rewards on this episode:    {float(ls[k]) / frames}')
                     logger.info(f'Time taken for this episode:        {round(time.time() - start, 3)} secs\n')
-                if ep % self.checkpoint_frequency == 0:
+                if ep % self.checkpoint_frequency == 0 and self.rank == 0:
                     os.makedirs(f'checkpoints/{ep}/', exist_ok=True)
                     torch.save(self._cpu_state_dict(), f'checkpoints/{ep}/weights.p')
                     with open(f'checkpoints/{ep}/scores.txt', 'w') as f:
                         f.write(json.dumps(scores))
             completed = hi
             start = time.time()
-            if completed < episodes and n == 1:
+            if total < episodes and n == 1:
                 logger.info(f'Running Episode {completed + 1}')
                 loop.reset_all(verbose)
         self._tick_base = int(loop.tick.item())      # a later run() / a resumed agent continues the RNG streams
-        torch.save(self._cpu_state_dict(), self.MODEL_PATH)
-        logger.info(f'Model has been successfully saved in {self.MODEL_PATH}')
+        self._check_exchange()
+        if self.rank == 0:
+            torch.save(self._cpu_state_dict(), self.MODEL_PATH)
+            logger.info(f'Model has been successfully saved in {self.MODEL_PATH}')
         return scores
+
+    def _check_exchange(self) -> None:
+        """Raise when a device-side wait of the peer-memory gradient exchange gave up: from that update on the
+        optimiser kernels skip their update (grad_exchange.cu), so parameters are stale, not divergent."""
+        if self._xchg is not None and self._xchg.timed_out():
+            raise RuntimeError(f'rank {self.rank}: the NVLink gradient exchange timed out waiting for a peer '
+                               '(a rank left the training loop or died); parameters stopped updating at that point')
 
 
 class VectorLoop:
@@ -398,9 +431,10 @@ class VectorLoop:
     every random draw is keyed by the device counter ``tick``, and two consecutive iterations (the state buffers
     ping-pong) can therefore be captured once into a CUDA graph and replayed (``run_steps``)."""
 
-    def __init__(self, agent: NAFAgent, frames: int, log_capacity: int, learn: bool = True):
+    def __init__(self, agent: NAFAgent, frames: int, log_capacity: int, learn: bool = True, store: bool = True):
         self.agent, self.env = agent, agent.environment
         self.frames, self.learn = int(frames), learn
+        self.store = bool(store) or bool(learn)
         n, dev = self.env.n_envs, agent.device
         self.n = n
         f32 = dict(dtype=torch.float32, device=dev)
@@ -431,6 +465,8 @@ class VectorLoop:
         self.lib = N.lib()
         self.phase_events = None        # optional [6 events] x 2 iterations: act | sim | append | learn | tail
         self._graph = None              # CUDA graph of two consecutive iterations
+        self._graph_gen = None          # _generation() at capture time
+        self._host_gen = None
         self._graph_failed = False      # a capture attempt raised: stay on eager launches
         self._graph_learn = False
         self.graph_kernels = 0
@@ -470,8 +506,9 @@ class VectorLoop:
         if self.pipeline_sim:     # dynamics + M^-1 of the NEXT step overlap the replay / learn phase of this one
             env.sim.prepare()
         self._mark(parity, 2)
-        a.memory.add_batch(self.state, self.actions, self.reward, self.next_state, self.done,
-                           valid=self.valid if auto_reset else None)
+        if self.store:
+            a.memory.add_batch(self.state, self.actions, self.reward, self.next_state, self.done,
+                               valid=self.valid if auto_reset else None)
         self._mark(parity, 3)
         tick = self.tick
         common = (self.reward.data_ptr(), self.done.data_ptr(), self.valid.data_ptr(), self.score.data_ptr(),
@@ -508,13 +545,18 @@ class VectorLoop:
             self._par ^= 1
 
     def step(self, auto_reset: bool = True) -> None:
-        learn_now = self.learn and self.agent._learn_due(pending=self.n)
+        learn_now = self.learn and self.agent._learn_due(pending=self.n, pending_exact=not auto_reset)
         self._body(auto_reset, learn_now, 0)
 
     # ---- CUDA graph of two iterations ---------------------------------------------------------------------
     def _graphable(self) -> bool:
         a = self.agent
-        return (not self.learn) or (a.update_freq == 1 and len(a.memory) > a.batch_size)
+        return (not self.learn) or (a.update_freq == 1 and a.memory.gate_open())
+
+    def _generation(self):
+        """Host-side state a captured graph bakes in: the simulator's prepared flag (dropped by reset / set_state /
+        clear) and the NAF workspace pointers / trunk mode."""
+        return (self.env.sim.generation, self.agent._ws_generation, id(self.agent._ws))
 
     def capture(self) -> bool:
         """Capture two consecutive auto-reset iterations (eager warm-up must have happened: workspaces exist).
@@ -535,6 +577,7 @@ class VectorLoop:
                 self._body(True, self.learn, 1)
             self._graph, self._graph_learn = g, self.learn
             self._odd, self._graph_par = 0, self._par
+            self._graph_gen = self._generation()
             self.graph_kernels = int(self.lib.rloa_launch_count() - launched)    # librloa kernels per replay
             a.memory._len = host_len          # capturing does not execute: roll the host mirror back
             return True
@@ -550,9 +593,13 @@ class VectorLoop:
         """Two iterations through the captured graph."""
         if self._odd or self._par != self._graph_par:
             raise RuntimeError('the loop buffers are not in the phase the graph was captured in; use run_steps')
+        if self._graph_gen != self._generation():
+            raise RuntimeError('the simulator state or the NAF workspace changed since the graph was captured '
+                               '(reset / set_state / set_trunk_mode / a larger batch); use run_steps, which re-captures')
         self._graph.replay()
         m = self.agent.memory
-        m._len = min(m.buffer_size, m._len + 2 * self.n)
+        if self.store:
+            m._len = min(m.buffer_size, m._len + 2 * self.n)
 
     # ---- host-facing iteration: states / actions / results cross pinned HOST buffers every step ---------------
     def bind_host_buffers(self, h_state: torch.Tensor, h_action: torch.Tensor, h_reward: torch.Tensor,
@@ -617,6 +664,8 @@ class VectorLoop:
         call's work queues behind them on the same stream (torch.cuda.synchronize() to drain)."""
         a = self.agent
         stream = torch.cuda.current_stream(a.device)
+        if self._host_graphs and self._host_gen != self._generation():
+            self._host_graphs = None
         if use_graph and self._host_graphs is None and self._graphable() and a._ws is not None and \
                 (not self.learn or a._bufs is not None):
             host_len = a.memory._len
@@ -628,6 +677,7 @@ class VectorLoop:
                 with torch.cuda.graph(g2, capture_error_mode='thread_local'):
                     self._host_phase_step(self.learn)
                 self._host_graphs = (g1, g2)
+                self._host_gen = self._generation()
             except Exception as err:      # pragma: no cover
                 self.graph_error = f'{type(err).__name__}: {err}'
                 self._host_graphs = False
@@ -641,7 +691,7 @@ class VectorLoop:
         else:
             self._host_phase_act()
             stream.synchronize()
-            self._host_phase_step(self.learn and a._learn_due(pending=self.n))
+            self._host_phase_step(self.learn and a._learn_due(pending=self.n, pending_exact=False))
         if self._host_ready is not None:
             self._host_ready.synchronize()
         else:
@@ -649,6 +699,8 @@ class VectorLoop:
 
     def run_steps(self, k: int, use_graph: bool = True) -> None:
         """k iterations with auto-reset; pairs go through the CUDA graph when it is (or can be) captured."""
+        if self._graph is not None and self._graph_gen != self._generation():
+            self._graph = None             # stale: baked-in prepared flag / workspace pointers; capture again below
         if use_graph and self._graph is not None:
             off_state, off_tick = bool(self._odd), self._par != self._graph_par
             if off_state != off_tick:      # step(auto_reset=False) calls since the capture moved only one of the two

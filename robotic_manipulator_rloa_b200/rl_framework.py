@@ -99,7 +99,7 @@ class ManipulatorFramework:
     @staticmethod
     def set_log_level(log_level: int) -> None:
         names = {10: 'DEBUG', 20: 'INFO', 30: 'WARNING', 40: 'ERROR', 50: 'CRITICAL'}
-        if log_level in names:
+        if isinstance(log_level, int) and log_level in names:
             logger.info(f'Log Level has been set to {logger.level} ({names[logger.level]})')
             logger.setLevel(log_level)
         else:

@@ -26,6 +26,8 @@ class ReplayBuffer:
         self.seed = int(seed)
         self._draws = 0
         self._len = 0                       # host mirror of min(cursor, capacity)
+        self._len_exact = True              # False after a masked append of unknown size (the mirror is an upper bound)
+        self._gate_open = False             # sticky: the ring holds more than batch_size rows (it never shrinks)
         self._max_append = int(max_append)
         self._rb: Optional[N.Replay] = None
         self.state_size, self.action_size = state_size, action_size
@@ -93,7 +95,26 @@ class ReplayBuffer:
         # host mirror of the live count; with a valid mask and no n_valid it is an upper bound (exact value:
         # sync_len()) — the `len(memory) > batch_size` gate only matters before the ring first fills a batch
         added = n if (valid is None or n_valid is None) else int(n_valid)
+        if valid is not None and n_valid is None:
+            self._len_exact = False
         self._len = min(self.buffer_size, self._len + added)
+
+    def gate_open(self, pending: int = 0, pending_exact: bool = True) -> bool:
+        """The `len(memory) > batch_size` gate of NAFAgent.step (naf_algorithm.py:150), evaluated on the EXACT live count:
+        `pending` rows are about to be appended before the update samples; with a masked append of unknown size
+        (pending_exact False) only rows already in the ring count, so learning can start one vectorised step later than
+        the upper bound would allow, never earlier — the sampler never sees fewer than batch_size live rows.  Costs
+        one device read the first time the host mirror crosses the threshold, nothing afterwards."""
+        if self._gate_open:
+            return True
+        if self._len + pending <= self.batch_size:
+            return False
+        if not (self._len_exact and pending_exact):
+            self.sync_len()
+            self._len_exact = True
+        live = self._len + (pending if pending_exact else 0)
+        self._gate_open = live > self.batch_size
+        return self._gate_open
 
     def sync_len(self) -> int:
         """Exact live count read back from the device cursor (synchronises)."""
@@ -111,7 +132,7 @@ class ReplayBuffer:
         self._draws += 1
 
     def sample(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-        if self._rb is None or self._len < self.batch_size:
+        if self._rb is None or (self._len if self._len_exact else self.sync_len()) < self.batch_size:
             raise ValueError('Sample larger than population or is negative')     # what random.sample raises
         s, a, r, s2, d = self._out
         self.sample_into(s, a, r, s2, d, self._idx)
@@ -146,4 +167,4 @@ class ReplayBuffer:
         for name in ('states', 'next_states', 'actions', 'rewards', 'dones'):
             getattr(self, name)[:n].copy_(sd[name].to(self.device))
         self.cursor.fill_(int(sd['cursor']))
-        self._len = n
+        self._len, self._len_exact, self._gate_open = n, True, n > self.batch_size

@@ -16,6 +16,28 @@ XARM6 = dict(file='xarm/xarm6_with_gripper.urdf', ee=12, involved=[1, 2, 3, 4, 5
              target=[0.3, 0.47, 0.61], obstacle=[0.25, 0.27, 0.5], start=[0., 1., 0., -2.3, 0., 0., 0.])
 
 
+def parity_report(case, dq_e, dqd_e, tol_q=1e-4, tol_qd=1e-4, **extra):
+    """Counts against the FLAT north_star bounds (1e-4 rad, 1e-4 rad/s): how many envs exceed them and the worst case.
+    Printed (so the driver's log shows them) and appended to gpurun_out/parity_counts.jsonl when that directory exists;
+    the callers assert the counts against a stated budget instead of widening the bound."""
+    import json
+    import os
+    dq_e, dqd_e = np.asarray(dq_e, float), np.asarray(dqd_e, float)
+    rep = dict(case=case, n=int(dq_e.size), n_over_q=int((dq_e > tol_q).sum()), n_over_qd=int((dqd_e > tol_qd).sum()),
+               worst_q=float(dq_e.max()), worst_qd=float(dqd_e.max()), p99_qd=float(np.quantile(dqd_e, 0.99)),
+               median_qd=float(np.median(dqd_e)))
+    rep.update({k: (float(v) if isinstance(v, (float, np.floating)) else int(v)) for k, v in extra.items()})
+    print('PARITY', json.dumps(rep))
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    if os.path.isdir(out):
+        try:
+            with open(os.path.join(out, 'parity_counts.jsonl'), 'a') as f:
+                f.write(json.dumps(rep) + '\n')
+        except OSError:
+            pass
+    return rep
+
+
 def make_oracle(cfg):
     model = load_manipulator(cfg['file'])
     return model, BulletOracle(model, cfg['ee'], len(cfg['involved']))

@@ -8,11 +8,11 @@ import os
 import numpy as np
 import pytest
 
-from helpers import KUKA, XARM6, make_oracle, model_from_entries, model_to_entries, step_motors
+from helpers import KUKA, PANDA, XARM6, make_oracle, model_from_entries, model_to_entries, step_motors
 from oracle.bullet_oracle import BulletOracle
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-CFG = {'kuka': KUKA, 'xarm6': XARM6}
+CFG = {'kuka': KUKA, 'xarm6': XARM6, 'panda': PANDA}
 
 
 def _load(robot):
@@ -35,7 +35,32 @@ def test_model_entries_round_trip():
     assert np.array_equal(orc.fk(q)[1], o2.fk(q)[1])
 
 
-@pytest.mark.parametrize('robot', ['kuka', 'xarm6'])
+@pytest.mark.parametrize('robot', ['kuka', 'xarm6', 'panda'])
+def test_model_constants_against_recorded_pybullet(robot):
+    """What Bullet reports about the loaded model and its world against what this repository's loader / restatement
+    assume (SURVEY.md Appendix A and C were written from memory): masses, principal inertias, joint damping, limits, and
+    the world defaults the restatement hard-codes (dt 1/240, 50 solver iterations, ERP 0.2, residual threshold 1e-7)."""
+    z = _load(robot)
+    if 'bt_mass' not in z:
+        pytest.skip('recorded with an older make_bullet_golden.py (no getDynamicsInfo entries)')
+    model = model_from_entries(z)
+    assert np.abs(model.mass - z['bt_mass']).max() <= 1e-9
+    got = np.sort(np.asarray(model.inertia).reshape(model.nl, -1)[:, :3], axis=1)
+    assert np.abs(got - np.sort(z['bt_local_inertia_diag'], axis=1)).max() <= 1e-7      # principal moments, any axis order
+    assert np.abs(model.damping - z['bt_joint_damping']).max() <= 1e-9
+    lim = model.has_limit.astype(bool)
+    assert np.abs(model.lower[lim] - z['bt_joint_lower'][lim]).max() <= 1e-9
+    assert np.abs(model.upper[lim] - z['bt_joint_upper'][lim]).max() <= 1e-9
+    assert abs(float(z['bt_world_fixedTimeStep']) - model.dt) <= 1e-12
+    assert int(z['bt_world_numSolverIterations']) == model.iters
+    if 'bt_world_erp' in z:
+        assert abs(float(z['bt_world_erp']) - model.erp) <= 1e-12
+    if 'bt_world_solverResidualThreshold' in z:
+        assert abs(float(z['bt_world_solverResidualThreshold']) - model.resid_thresh) <= 1e-15
+    assert abs(float(z['bt_obstacle_shape'][1]) * (1.0 if float(z['bt_obstacle_shape'][1]) > 0.05 else 2.5) - 0.075) <= 1e-9
+
+
+@pytest.mark.parametrize('robot', ['kuka', 'xarm6', 'panda'])
 def test_oracle_against_recorded_pybullet(robot):
     z, cfg = _load(robot), CFG[robot]
     model = model_from_entries(z)
@@ -54,7 +79,7 @@ def test_oracle_against_recorded_pybullet(robot):
     assert np.abs(ee - z['ee_target']).max() <= 2e-3
 
 
-@pytest.mark.parametrize('robot', ['kuka', 'xarm6'])
+@pytest.mark.parametrize('robot', ['kuka', 'xarm6', 'panda'])
 def test_oracle_trajectory_divergence_from_recorded_pybullet(robot):
     """400 steps from the recorded start states with the recorded actions: the divergence is REPORTED (north_star) and
     sanity-bounded; contact response is not modelled, so steps after the first recorded contact are left out."""
@@ -77,7 +102,7 @@ def test_oracle_trajectory_divergence_from_recorded_pybullet(robot):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('robot', ['kuka', 'xarm6'])
+@pytest.mark.parametrize('robot', ['kuka', 'xarm6', 'panda'])
 def test_cuda_simulator_against_recorded_pybullet(robot):
     import torch
     from robotic_manipulator_rloa_b200.environment.simulator import BatchedSimulator

@@ -189,6 +189,16 @@ def test_environment_autocollision_api():
     for i in range(nl):
         others = [j for j in range(nl) if abs(j - i) > 1]
         assert np.abs(d[f'joint_{i}'] - want[i, others]).max() <= 2e-5
+    # CollisionDetector.compute_collisions_in_manipulator (reference utils/collision_detector.py:63-98): the same
+    # distances per link, neighbours skipped, saturated at max_distance
+    from robotic_manipulator_rloa_b200.utils.collision_detector import CollisionDetector, CollisionObject
+    for link in (0, 5, nl - 1):
+        det = CollisionDetector(CollisionObject(body=env.sim, link=link), obstacle_ids=[])
+        got = det.compute_collisions_in_manipulator(list(range(nl)))
+        others = [j for j in range(nl) if abs(j - link) > 1]
+        assert got.shape == (len(others),) and np.abs(got - want[link, others]).max() <= 2e-5
+        capped = det.compute_collisions_in_manipulator(list(range(nl)), max_distance=0.05)
+        assert capped.max() <= 0.05 and np.array_equal(capped < 0.05, got < 0.05)
     hit = any((v < 0).any() for v in d.values())
     base_r, base_t = env.get_reward(), env.is_terminal_state()
     assert env.get_reward(consider_autocollision=True) == (-1000 if hit and base_r != 250 else base_r)

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import KUKA, PANDA, XARM6, make_oracle, random_states, step_motors
+from helpers import KUKA, PANDA, XARM6, make_oracle, parity_report, random_states, step_motors
 
 pytestmark = pytest.mark.gpu
 
@@ -40,15 +40,32 @@ def test_fk_and_distances_match_oracle(cfg):
         assert np.abs(obs[e, na:2 * na] - qd[e, :na]).max() <= 1e-6
 
 
-@pytest.mark.parametrize('cfg,vel,near,stress', [(KUKA, 2.0, 0.0, False), (KUKA, 0.3, 0.0, False),
-                                                  (KUKA, 2.0, 0.25, False), (PANDA, 2.0, 0.0, False),
-                                                  (PANDA, 1.0, 0.25, False), (KUKA, 2.0, 0.1, True), (XARM6, 2.0, 0.1, False)],
-                         ids=['kuka-saturated', 'kuka-gentle', 'kuka-limits', 'panda', 'panda-limits', 'kuka-stress', 'xarm6'])
-def test_single_step_matches_oracle(cfg, vel, near, stress):
-    """4096 seeded (q, qd, action) per case.  Normal cases keep the POSITION_CONTROL-held joints near 0 as
-    the reference does (velocities of a few rad/s): absolute tolerance.  The stress case puts the held
-    joints anywhere in their range, so the motors command up to 24*|q| = 70 rad/s: the tolerance gets a
-    relative term 2e-5*|qd| (fp32 after 50 Gauss-Seidel sweeps)."""
+# Budgets of envs allowed OVER the flat north_star bound of 1e-4 rad/s after one step (of 4096), with the hard cap on the
+# worst one.  Measured on B200 (gpurun_out/parity_counts.jsonl of round 2, copied into DESIGN.md section 2); where they are not
+# zero the cause is physical and named:
+#   flips  — the Gauss-Seidel early exit (max row update^2 <= 1e-7) fires one sweep apart in fp32 and fp64: the two iterates
+#            then differ by the solver's own residual (<= 3e-4 rad/s typical);
+#   limits — a joint pushed past its limit couples its limit row with the saturating motor row; after the 50-sweep cap the
+#            iterate is still moving and fp32 rounding shows at ~1.1e-4;
+#   stress — held joints anywhere in their range: motors command up to 24 |q| = 70 rad/s, so 1e-4 absolute is 1.4e-6
+#            relative — at the resolution of fp32 after 50 sweeps.
+SINGLE_STEP_CASES = [
+    # id,               cfg,   vel, near, stress, budget_over_qd, cap_qd
+    ('kuka-saturated', KUKA, 2.0, 0.0, False, 24, 2e-3),
+    ('kuka-gentle', KUKA, 0.3, 0.0, False, 24, 2e-3),
+    ('kuka-limits', KUKA, 2.0, 0.25, False, 64, 2e-3),
+    ('panda', PANDA, 2.0, 0.0, False, 24, 2e-3),
+    ('panda-limits', PANDA, 1.0, 0.25, False, 64, 2e-3),
+    ('kuka-stress', KUKA, 2.0, 0.1, True, 1024, 5e-3),
+    ('xarm6', XARM6, 2.0, 0.1, False, 64, 2e-3),
+]
+
+
+@pytest.mark.parametrize('name,cfg,vel,near,stress,budget,cap', SINGLE_STEP_CASES, ids=[c[0] for c in SINGLE_STEP_CASES])
+def test_single_step_matches_oracle(name, cfg, vel, near, stress, budget, cap):
+    """4096 seeded (q, qd, action) per case against the fp64 restatement at the FLAT north_star bounds: |dq| <= 1e-4 rad on
+    every env, |dqd| <= 1e-4 rad/s with the envs over the bound COUNTED against the case's budget (see the table above),
+    |d ee| <= 1e-5 m, flags exact away from contact boundaries."""
     model, orc = make_oracle(cfg)
     n = 4096
     q, qd = random_states(model, n, seed=7, vel=vel, near_limit=near, held=None if stress else cfg['fixed'])
@@ -65,24 +82,19 @@ def test_single_step_matches_oracle(cfg, vel, near, stress):
     a32 = actions.astype(np.float32).astype(np.float64)
     obs_o, rew_o, done_o, it_o = orc.batch_step(q32, qd32, a32, cfg['involved'], 200.0, cfg['obstacle'],
                                                 cfg['target'], nthreads=8)
-    scale = 1.0 + 0.2 * np.abs(qd32).max(axis=1)          # 1e-4 * scale = 1e-4 + 2e-5 |qd|_max
-    dq = np.abs(qg.cpu().numpy() - q32).max(axis=1) / scale
-    dqd = np.abs(qdg.cpu().numpy() - qd32).max(axis=1) / scale
+    dq = np.abs(qg.cpu().numpy() - q32).max(axis=1)
+    dqd = np.abs(qdg.cpu().numpy() - qd32).max(axis=1)
     same_it = it_g == it_o
-    # an early-exit decision of the PGS sweep that flips between fp32 and fp64 changes the result by up
-    # to the solver's own residual (3e-4 rad/s); those envs are counted, everything else must be tight
-    print(f'max|dq|={dq.max():.3e} max|dqd|={dqd.max():.3e} iteration mismatches={np.count_nonzero(~same_it)} '
-          f'mean iters={it_o.mean():.1f}')
-    # with a joint pushed past its limit the limit row and the (saturating) motor row of that joint share one
-    # Jacobian; after the 50-sweep cap the iterate is still moving and fp32 rounding shows at 1.1e-4: 2e-4 there
-    tol_qd = 2e-4 if near > 0 else TOL_QD
-    assert dq[same_it].max() <= TOL_Q
-    assert dqd[same_it].max() <= tol_qd
+    rep = parity_report('single_step/' + name, dq, dqd, n_exit_flips=np.count_nonzero(~same_it),
+                        n_over_qd_same_exit=np.count_nonzero(dqd[same_it] > TOL_QD),
+                        worst_qd_same_exit=dqd[same_it].max(), mean_sweeps=it_o.mean())
+    assert rep['worst_q'] <= TOL_Q                           # flat, every env
+    assert rep['n_over_qd'] <= budget, rep                   # counted exceptions, never a wider bound
+    assert rep['worst_qd'] <= cap, rep
     assert np.count_nonzero(~same_it) <= n // 200
-    assert dqd.max() <= 2e-3 and dq.max() <= 1e-4
     na = len(cfg['involved'])
     dee = np.abs(obs.cpu().numpy()[:, 2 * na:2 * na + 3] - obs_o[:, 2 * na:2 * na + 3]).max(axis=1)
-    assert dee[same_it].max() <= TOL_EE
+    assert dee.max() <= TOL_EE
     # flags exact away from contact boundaries; rewards equal where flags agree
     lo = np.stack([orc.distances(q32[e], cfg['obstacle'], cfg['target'])[0].min() for e in range(0, n, 8)])
     eet = np.stack([orc.distances(q32[e], cfg['obstacle'], cfg['target'])[1] for e in range(0, n, 8)])
@@ -134,9 +146,13 @@ def test_reset_and_trajectory_divergence(cfg):
     qg, qdg = sim.get_state()
     q = np.zeros((n, model.nl)); qd = np.zeros((n, model.nl))
     orc.batch_reset(q, qd, init.astype(np.float32).astype(np.float64), 50, nthreads=8)
-    dq0 = np.abs(qg.cpu().numpy() - q).max(); dqd0 = np.abs(qdg.cpu().numpy() - qd).max()
-    print(f'after reset: max|dq|={dq0:.3e} max|dqd|={dqd0:.3e}')
-    assert dq0 <= 2e-4 and dqd0 <= 2e-3
+    dq_e, dqd_e = np.abs(qg.cpu().numpy() - q).max(axis=1), np.abs(qdg.cpu().numpy() - qd).max(axis=1)
+    # 50 chained sub-steps from the load state: flat 1e-4 bounds, envs over them counted (fp32 error accumulates over the
+    # 50 steps while the position motors pull 24 (q* - q) rad/s; the first reset also runs joints 6-13 on the load-time
+    # velocity motors)
+    rep = parity_report('reset50/' + cfg['file'], dq_e, dqd_e)
+    assert rep['worst_q'] <= 2e-4 and rep['n_over_q'] <= n // 4, rep
+    assert rep['worst_qd'] <= 2e-3 and rep['n_over_qd'] <= n, rep
     for j in range(len(cfg['start'])):
         orc.set_position_control(j, 0.0)      # template only; batch_step overrides the involved joints
     step_motors(orc, cfg)
@@ -216,7 +232,9 @@ def test_ragged_env_counts_and_active_mask(n):
     obs_o, rew_o, done_o, _ = orc.batch_step(q32, qd32, actions.astype(np.float64), cfg['involved'], 200.0,
                                              cfg['obstacle'], cfg['target'], nthreads=4)
     on = active.astype(bool)
-    assert np.abs(qg[on] - q32[on]).max() <= TOL_Q and np.abs(qdg[on] - qd32[on]).max() <= 2e-3
+    rep = parity_report(f'ragged/n={n}', np.abs(qg[on] - q32[on]).max(axis=1), np.abs(qdg[on] - qd32[on]).max(axis=1))
+    assert rep['worst_q'] <= TOL_Q
+    assert rep['n_over_qd'] <= max(1, n // 100) and rep['worst_qd'] <= 2e-3, rep      # PGS exit flips, counted
     assert np.abs(obs[:n].cpu().numpy()[on][:, 12:15] - obs_o[on][:, 12:15]).max() <= TOL_EE
     if (~on).any():
         assert np.abs(qg[~on] - q_in[~on]).max() <= 1e-7 and np.abs(qdg[~on] - qd_in[~on]).max() <= 1e-6
