@@ -327,7 +327,9 @@ class Ctx:
         self.lib = _native.lib()
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev) if not args.no_flush else None
         import logging
+        from robotic_manipulator_rloa_b200.utils.logger import get_global_logger
         logging.getLogger().setLevel(logging.ERROR)
+        get_global_logger().setLevel(logging.ERROR)
 
     def barrier(self):
         if self.world > 1:
@@ -533,12 +535,25 @@ def release(rec):
         env.close()
 
 
+def quiet_framework():
+    """ManipulatorFramework with the package logger at ERROR: the reference logs every test episode at INFO on stdout,
+    which must carry the one JSON line only."""
+    import logging
+    from robotic_manipulator_rloa_b200 import ManipulatorFramework
+    from robotic_manipulator_rloa_b200.utils.logger import get_global_logger
+    get_global_logger().setLevel(logging.ERROR)
+    mf = ManipulatorFramework()
+    get_global_logger().setLevel(logging.ERROR)
+    logging.getLogger().setLevel(logging.ERROR)
+    return mf
+
+
 def rollout_workload(ctx, n_envs=16384, frames=750):
     """Config 4: test_trained_model on weights_kuka.p, per-env randomised target / obstacle, through the public facade."""
     torch = ctx.torch
     import numpy as np
     from robotic_manipulator_rloa_b200 import ManipulatorFramework
-    mf = ManipulatorFramework()
+    mf = quiet_framework()
     mf.initialize_environment(manipulator_file=KUKA['file'], endeffector_index=13, fixed_joints=KUKA['fixed'],
                               involved_joints=KUKA['involved'], target_position=KUKA['target'],
                               obstacle_position=KUKA['obstacle'], initial_joint_positions=KUKA['start'],
@@ -608,7 +623,7 @@ def demo_workload(ctx):
     """Config 1: the reference's kuka_training demo shape (1 env, batch 128, 10 episodes x 400 frames) through the facade."""
     torch = ctx.torch
     from robotic_manipulator_rloa_b200 import ManipulatorFramework
-    mf = ManipulatorFramework()
+    mf = quiet_framework()
     mf.initialize_environment(manipulator_file=KUKA['file'], endeffector_index=13, fixed_joints=KUKA['fixed'],
                               involved_joints=KUKA['involved'], target_position=KUKA['target'],
                               obstacle_position=KUKA['obstacle'], initial_joint_positions=KUKA['start'],

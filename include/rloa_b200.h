@@ -260,6 +260,12 @@ int rloa_naf_ws_set_trunk(rloa_naf_ws* ws, int32_t mode);
 int rloa_naf_hidden_layer(rloa_naf_ws* ws, const float* z1, const float* scale, const float* shift,
                           const float* w2, const float* b2, float* z2, int32_t batch, void* stream);
 
+/* Self-test of the tcgen05 operand layouts the tensor-core learn path relies on (csrc/umma_probe.cu): one 128-row bf16
+ * tile in the K-major SWIZZLE_128B layout read both K-major and, untransposed, MN-major.  a, b, c are fp32 row-major
+ * device arrays:  mode 0: c[128][256] = a[128][256] b[256][256]^T;  1: c[128][256] = a[128][256] b[256][256];
+ * 2: c[256][256] = a[128][256]^T b[128][256];  3: c[256][64] = a[128][256]^T b[128][64]  (operands rounded to bf16). */
+int rloa_umma_probe(int32_t mode, const float* a, const float* b, float* c, void* stream);
+
 /* NAF.forward (naf_neural_network.py:56-123) without the sampling tail:
  * mu [B][A], pdiag [B][A] (= diag of P = L o L^T, i.e. exp(2 tanh z_kk)), V [B], and when
  * action != NULL, Q [B] = -1/2 sum_k P_kk (u_k - mu_k)^2 + V.  train_mode != 0 uses batch

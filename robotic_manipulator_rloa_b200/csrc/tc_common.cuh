@@ -29,6 +29,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
            (2ull << 61);
 }
 
+// The same SWIZZLE_128B bytes read as an MN-major operand (the contraction runs over the tile's ROWS): canonical form
+// ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in elements — 64 MN-contiguous elements x 8 K rows per 1024-byte atom; atoms
+// along MN (the next 64 columns = the next k-block of the K-major view) are LBO bytes apart, atoms along K (the next 8
+// rows) SBO = 1024 bytes apart.  One K = 16 instruction consumes two atoms along K: advance the start address by 2048.
+// Selected per operand by bits 15 (A) / 16 (B) of the instruction descriptor.
+constexpr uint32_t kIdescAMajorMN = 1u << 15, kIdescBMajorMN = 1u << 16;
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
 // byte offset of the 16-byte chunk `chunk` (8 bf16) of row `row` inside one k-block (64 bf16 per row) of a
 // K-major SWIZZLE_128B operand tile: 8-row atoms of 1 KB, chunk index XOR row % 8
 __host__ __device__ __forceinline__ uint32_t sw128_chunk_offset(int row, int chunk) {

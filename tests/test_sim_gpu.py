@@ -51,13 +51,15 @@ def test_fk_and_distances_match_oracle(cfg):
 #            relative — at the resolution of fp32 after 50 sweeps.
 SINGLE_STEP_CASES = [
     # id,               cfg,   vel, near, stress, budget_over_qd, cap_qd
-    ('kuka-saturated', KUKA, 2.0, 0.0, False, 24, 2e-3),
-    ('kuka-gentle', KUKA, 0.3, 0.0, False, 24, 2e-3),
-    ('kuka-limits', KUKA, 2.0, 0.25, False, 64, 2e-3),
-    ('panda', PANDA, 2.0, 0.0, False, 24, 2e-3),
-    ('panda-limits', PANDA, 1.0, 0.25, False, 64, 2e-3),
-    ('kuka-stress', KUKA, 2.0, 0.1, True, 1024, 5e-3),
-    ('xarm6', XARM6, 2.0, 0.1, False, 64, 2e-3),
+    # measured in round 2 (envs over 1e-4 rad/s of 4096, worst |dqd|): 0 / 9.8e-6; 4 / 1.1e-3 (all 4 are exit flips);
+    # 1 / 4.4e-4 (flip); 0 / 7.3e-6; 5 / 1.09e-4 (limits); 6 / 8.9e-4 (5 flips + 1 at 1.17e-4); 2 / 1.64e-4 (limits)
+    ('kuka-saturated', KUKA, 2.0, 0.0, False, 4, 2e-3),
+    ('kuka-gentle', KUKA, 0.3, 0.0, False, 12, 2e-3),
+    ('kuka-limits', KUKA, 2.0, 0.25, False, 8, 2e-3),
+    ('panda', PANDA, 2.0, 0.0, False, 4, 2e-3),
+    ('panda-limits', PANDA, 1.0, 0.25, False, 12, 2e-3),
+    ('kuka-stress', KUKA, 2.0, 0.1, True, 16, 2e-3),
+    ('xarm6', XARM6, 2.0, 0.1, False, 8, 2e-3),
 ]
 
 
@@ -151,8 +153,7 @@ def test_reset_and_trajectory_divergence(cfg):
     # 50 steps while the position motors pull 24 (q* - q) rad/s; the first reset also runs joints 6-13 on the load-time
     # velocity motors)
     rep = parity_report('reset50/' + cfg['file'], dq_e, dqd_e)
-    assert rep['worst_q'] <= 2e-4 and rep['n_over_q'] <= n // 4, rep
-    assert rep['worst_qd'] <= 2e-3 and rep['n_over_qd'] <= n, rep
+    assert rep['worst_q'] <= TOL_Q and rep['worst_qd'] <= TOL_QD, rep      # measured: 2.0e-7 rad, 4.4e-5 rad/s
     for j in range(len(cfg['start'])):
         orc.set_position_control(j, 0.0)      # template only; batch_step overrides the involved joints
     step_motors(orc, cfg)
@@ -234,7 +235,7 @@ def test_ragged_env_counts_and_active_mask(n):
     on = active.astype(bool)
     rep = parity_report(f'ragged/n={n}', np.abs(qg[on] - q32[on]).max(axis=1), np.abs(qdg[on] - qd32[on]).max(axis=1))
     assert rep['worst_q'] <= TOL_Q
-    assert rep['n_over_qd'] <= max(1, n // 100) and rep['worst_qd'] <= 2e-3, rep      # PGS exit flips, counted
+    assert rep['n_over_qd'] <= max(1, n // 250) and rep['worst_qd'] <= 2e-3, rep      # PGS exit flips, counted (measured: 0)
     assert np.abs(obs[:n].cpu().numpy()[on][:, 12:15] - obs_o[on][:, 12:15]).max() <= TOL_EE
     if (~on).any():
         assert np.abs(qg[~on] - q_in[~on]).max() <= 1e-7 and np.abs(qdg[~on] - qd_in[~on]).max() <= 1e-6
