@@ -327,6 +327,7 @@ class Ctx:
         self.lib = _native.lib()
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev) if not args.no_flush else None
         import logging
+        import robotic_manipulator_rloa_b200  # noqa: F401  (importing the package installs its logger at INFO, like the reference)
         from robotic_manipulator_rloa_b200.utils.logger import get_global_logger
         logging.getLogger().setLevel(logging.ERROR)
         get_global_logger().setLevel(logging.ERROR)

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 LIB = os.path.join(HERE, 'librloa_b200.so')
-SOURCES = ['core.cu', 'sim.cu', 'naf.cu', 'naf_trunk_tc.cu', 'naf_policy_tc.cu', 'grad_exchange.cu', 'replay.cu', 'umma_probe.cu']
+SOURCES = ['core.cu', 'sim.cu', 'naf.cu', 'naf_trunk_tc.cu', 'naf_policy_tc.cu', 'grad_exchange.cu', 'replay.cu', 'umma_probe.cu', 'naf_learn_cluster.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--use_fast_math=false',
          '-Xcompiler', '-fPIC', '-I', INCLUDE, '-I', CSRC]

@@ -10,12 +10,14 @@
 // (two-pass, no atomics), one fused head kernel (mu, V, diag L, advantage, TD error, head gradients),
 // deterministic split-K weight gradients, fused clip-norm + Adam + soft target update.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
 #include "common.cuh"
 #include "bn_fuse.cuh"
 #include "naf_trunk_tc.cuh"
+#include "naf_learn_cluster.cuh"
 #include "optim.cuh"
 #include "philox.cuh"
 
@@ -1032,6 +1034,8 @@ struct rloa_naf_ws {
     cudaStream_t side[2] = {nullptr, nullptr};   // weight-gradient contractions run beside the critical path
     cudaEvent_t fork_ev[2] = {nullptr, nullptr}, join_ev[2] = {nullptr, nullptr};
     TrunkTC tc;                  // tcgen05 trunk state
+    LearnCluster lc;             // fused learn on two thread-block clusters (naf_learn_cluster.cu); used in trunk mode 1
+    bool use_cluster = true;     // RLOA_LEARN_CLUSTER=0 keeps the multi-launch tcgen05 path (A/B measurements)
 };
 
 static int naf_nparams(int S, int A, int H) {
@@ -1127,6 +1131,10 @@ extern "C" int rloa_naf_ws_create(int32_t S, int32_t A, int32_t H, int32_t max_b
     const int hb = (ws->NH * (H + 1) + ((ws->NH + 31) & ~31) + kHeadWarps * H + H) * (int)sizeof(float);
     if (hb > 48 * 1024) cudaFuncSetAttribute(naf_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
     trunk_tc_init(&ws->tc);
+    {
+        const char* e = getenv("RLOA_LEARN_CLUSTER");
+        ws->use_cluster = !(e != nullptr && e[0] == '0');
+    }
     for (int i = 0; i < 2; i++) {
         if (cudaStreamCreateWithFlags(&ws->side[i], cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&ws->fork_ev[i], cudaEventDisableTiming) != cudaSuccess ||
@@ -1143,6 +1151,7 @@ extern "C" int rloa_naf_ws_create(int32_t S, int32_t A, int32_t H, int32_t max_b
 extern "C" void rloa_naf_ws_destroy(rloa_naf_ws* ws) {
     if (ws == nullptr) return;
     trunk_tc_free(&ws->tc);
+    learn_cluster_free(&ws->lc);
     for (int i = 0; i < 2; i++) {
         if (ws->side[i]) cudaStreamDestroy(ws->side[i]);
         if (ws->fork_ev[i]) cudaEventDestroy(ws->fork_ev[i]);
@@ -1163,8 +1172,18 @@ extern "C" int rloa_naf_ws_set_trunk(rloa_naf_ws* ws, int32_t mode) {
             rc = policy_tc_prepare(&ws->tc);
             if (rc != RLOA_OK) return rc;
         }
+        if (ws->use_cluster && learn_cluster_supported(ws->S, ws->A, ws->H, 2)) {
+            rc = learn_cluster_prepare(&ws->lc, ws->S, ws->A);
+            if (rc != RLOA_OK) return rc;
+        }
     }
     ws->trunk_mode = mode;
+    return RLOA_OK;
+}
+
+extern "C" int rloa_naf_ws_set_debug(rloa_naf_ws* ws, float* buffer) {
+    RLOA_REQUIRE(ws != nullptr, "rloa_naf_ws_set_debug: null workspace");
+    ws->lc.dbg = buffer;
     return RLOA_OK;
 }
 
@@ -1331,6 +1350,30 @@ static int bn_relu_backward(rloa_naf_ws* ws, float* da, const float* z, const fl
     return RLOA_OK;
 }
 
+static void fill_param_table(const rloa_naf_params* mn, const rloa_naf_params* tg, ParamTable* pt);
+
+// trunk mode 1 and a batch of at most 1024 rows: the whole of learn() in one cluster launch (naf_learn_cluster.cu)
+static bool cluster_learn_applies(const rloa_naf_ws* ws, int batch) {
+    return ws->trunk_mode == 1 && ws->use_cluster && ws->lc.images != nullptr && learn_cluster_supported(ws->S, ws->A, ws->H, batch);
+}
+static int cluster_learn(rloa_naf_ws* ws, const rloa_naf_params* mn, const rloa_naf_params* tg, const rloa_adam_state* adam,
+                         const float* states, const float* actions, const float* rewards, const float* next_states,
+                         const float* dones, int32_t batch, const rloa_naf_hyper* hp, float* grad, float* loss, float* gnorm,
+                         int do_adam, void* stream) {
+    RLOA_REQUIRE(ws && states && actions && rewards && next_states && hp && grad, "rloa_naf_learn: null argument");
+    RLOA_REQUIRE(!(hp->use_done_mask && dones == nullptr), "rloa_naf_learn: use_done_mask needs dones");
+    int rc = check_params(ws, mn, "rloa_naf_learn(main)");
+    if (rc != RLOA_OK) return rc;
+    rc = check_params(ws, tg, "rloa_naf_learn(target)");
+    if (rc != RLOA_OK) return rc;
+    const FlatLayout fl = flat_layout(ws->S, ws->A, ws->H);
+    const int offs[15] = {fl.w1, fl.b1, fl.bn1w, fl.bn1b, fl.w2, fl.b2, fl.bn2w, fl.bn2b, fl.wmu, fl.bmu, fl.wv, fl.bv, fl.wl, fl.bl, fl.total};
+    ParamTable pt;
+    fill_param_table(mn, tg, &pt);
+    return learn_cluster_step(&ws->lc, mn, tg, adam, states, actions, rewards, next_states, dones, batch, hp, pt, offs, grad, loss,
+                              gnorm, do_adam, as_stream(stream));
+}
+
 // forward of both nets, loss, backward.  With defer != NULL the final split-K reduction is NOT launched: its
 // description is returned instead, for the fused tail kernel of rloa_naf_learn_step.
 static int learn_grads_impl(rloa_naf_ws* ws, const rloa_naf_params* mn, const rloa_naf_params* tg,
@@ -1478,6 +1521,8 @@ extern "C" int rloa_naf_learn_grads(rloa_naf_ws* ws, const rloa_naf_params* mn, 
                                     const float* states, const float* actions, const float* rewards,
                                     const float* next_states, const float* dones, int32_t batch,
                                     const rloa_naf_hyper* hp, float* grad, float* loss, void* stream) {
+    if (ws != nullptr && cluster_learn_applies(ws, batch))
+        return cluster_learn(ws, mn, tg, nullptr, states, actions, rewards, next_states, dones, batch, hp, grad, loss, nullptr, 0, stream);
     return learn_grads_impl(ws, mn, tg, states, actions, rewards, next_states, dones, batch, hp, grad, loss, nullptr, stream);
 }
 
@@ -1523,6 +1568,8 @@ extern "C" int rloa_naf_learn_step(rloa_naf_ws* ws, const rloa_naf_params* mn, c
                                    const float* rewards, const float* next_states, const float* dones, int32_t batch,
                                    const rloa_naf_hyper* hp, float* grad, float* loss, float* grad_norm, void* stream) {
     RLOA_REQUIRE(adam && adam->m && adam->v && adam->step, "rloa_naf_learn_step: null optimiser state");
+    if (ws != nullptr && cluster_learn_applies(ws, batch))
+        return cluster_learn(ws, mn, tg, adam, states, actions, rewards, next_states, dones, batch, hp, grad, loss, grad_norm, 1, stream);
     ReduceArgs ra{};
     int rc = learn_grads_impl(ws, mn, tg, states, actions, rewards, next_states, dones, batch, hp, grad, loss, &ra, stream);
     if (rc != RLOA_OK) return rc;
@@ -1559,6 +1606,13 @@ extern "C" int rloa_naf_learn_step_xchg(rloa_naf_ws* ws, const rloa_naf_params* 
                                         const float* dones, int32_t batch, const rloa_naf_hyper* hp, float* grad, float* loss,
                                         float* grad_norm, void* stream) {
     RLOA_REQUIRE(adam && xchg && adam->m && adam->v && adam->step, "rloa_naf_learn_step_xchg: null argument");
+    if (ws != nullptr && cluster_learn_applies(ws, batch)) {     // the cluster kernel leaves the complete local gradient
+        int rcc = cluster_learn(ws, mn, tg, nullptr, states, actions, rewards, next_states, dones, batch, hp, grad, loss, nullptr, 0, stream);
+        if (rcc != RLOA_OK) return rcc;
+        ParamTable ptc;
+        fill_param_table(mn, tg, &ptc);
+        return xchg_exchange_adam(xchg, grad, ReduceArgs{}, ptc, adam->m, adam->v, adam->step, *hp, grad_norm, as_stream(stream));
+    }
     ReduceArgs ra{};
     int rc = learn_grads_impl(ws, mn, tg, states, actions, rewards, next_states, dones, batch, hp, grad, loss, &ra, stream);
     if (rc != RLOA_OK) return rc;

@@ -1,0 +1,1006 @@
+// NAFAgent.learn in ONE launch on the 5th-generation tensor cores (reference naf_components/naf_algorithm.py:180-226:
+// target forward, TD target, main forward, MSE loss, backward, clip_grad_norm_, Adam, soft update).
+//
+// Two thread-block clusters of 8 CTAs — cluster 0 = target network on next_states, cluster 1 = main network on states —
+// 128 replay rows per CTA (batch <= 1024), 512 threads per CTA.  Nothing but the weights, the batch and the split-K partials
+// of the weight gradients touches global memory: pre-activations live in TMEM (z1 in columns 0-255, z2 in 256-511), the
+// bf16 operand tiles in shared memory, and the train-mode BatchNorm couples the rows through DISTRIBUTED SHARED MEMORY:
+// every CTA leaves its per-column partial statistics in its own shared memory, one barrier.cluster later every CTA reads
+// the eight partials of each column over DSMEM and merges them in rank order (Chan's update), so all eight hold the same
+// batch statistics without a global round trip.  Four such exchanges (BN1 / BN2 forward, BN2 / BN1 backward), two more for
+// the gradient-norm and the final hand-over, replace nine kernel boundaries of the multi-launch path.
+//
+// Every contraction runs as tcgen05.mma with fp32 TMEM accumulators:
+//   z1 = x W1^T            kind::tf32, observations split hi + lo (2^-22), K = 24
+//   z2 = a1 W2^T           bf16 128x256x256                      heads = a2 Wh^T        bf16 128x64x256
+//   dWh^T = a2^T dzh       A and B read MN-major (contraction over the 128 batch rows of both tiles, nothing transposed)
+//   da2 = dzh Wh           B = the forward head image read MN-major
+//   da1 = dz2 W2           B = the forward W2 image read MN-major (TMA-reloaded: its slot held the head tiles meanwhile)
+//   dW2 = dz2^T a1         A and B MN-major, 256 x 256 fp32 = all 512 TMEM columns
+//   dW1 = dz1^T [x_hi|x_lo] A and B MN-major, bf16 hi / lo split of the observations
+// (csrc/umma_probe.cu pins the MN-major views).  z1 is not kept across the backward: its TMEM columns are needed, and
+// recomputing it is six K = 8 instructions.  The TD target of a row needs V'(s') of the same row from the other cluster:
+// the target CTA of rank r writes y for its 128 rows and raises a flag, the main CTA of rank r waits for it in its head
+// phase (the target never waits for the main, so the pair cannot deadlock; the flag returns to 0: graph-replay safe).
+// Tail: every CTA dumps its partial weight gradients, one cluster barrier, then each CTA sums an eighth of the flat
+// gradient over the 8 partials in rank order, the squared-norm partials meet over DSMEM, and clip + Adam + soft target
+// update are applied to the same elements (optim.cuh arithmetic).  Deterministic: no atomics on data, fixed orders.
+//
+// Numerics: bf16 operands (tf32 for W1), fp32 accumulation and fp32 BatchNorm statistics from the TMEM accumulators; the
+// bound against the all-fp32 path is stated in tests/test_naf_learn_cluster_gpu.py.  sm_100a only.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "bn_fuse.cuh"
+#include "naf_learn_cluster.cuh"
+#include "optim.cuh"
+#include "tc_common.cuh"
+
+namespace rloa {
+
+using namespace tc;
+
+namespace lc {
+constexpr int H = 256, KP = 32, NHP = 64, ROWS = 128, THREADS = 512, CL = 8;
+// weight image of one network (global memory, written by learn_pack_kernel in shared-memory byte order)
+constexpr uint32_t W2_BYTES = H * H * 2;                 // 131072: 4 k-blocks x [256 rows][128 B]
+constexpr uint32_t WH_BYTES = NHP * H * 2;               // 32768: 4 k-blocks x [64 rows][128 B]
+constexpr uint32_t W1_BYTES = H * KP * 4;                // 32768: tf32 [256 rows][128 B]
+constexpr uint32_t VEC_FLOATS = 2 * H + NHP;             // b1 | b2 | bh
+constexpr uint32_t VEC_BYTES = VEC_FLOATS * 4;           // 2304
+constexpr uint32_t OFF_W2 = 0, OFF_WH = W2_BYTES, OFF_W1 = OFF_WH + WH_BYTES, OFF_VEC = OFF_W1 + W1_BYTES;
+constexpr uint32_t IMAGE_BYTES = OFF_VEC + VEC_BYTES;    // 198912
+// shared memory map (offsets from the 1024-byte aligned base)
+constexpr uint32_t R1 = 0;                               // 64 KB  A-operand tile [4 k-blocks][128 rows][128 B]
+constexpr uint32_t R0 = 65536;                           // 128 KB W2 image | head image + scratch | a1 + dz1
+constexpr uint32_t S1 = R0 + 131072;                     // 16 KB  dzh tile | reduction scratch + coefficients | x tile
+constexpr uint32_t COEF = S1 + 16384;                    // [2 layers][sc | sh | mean | rstd][256] fp32 = 8 KB
+constexpr uint32_t XBUF = COEF + 8192;                   // [2][3][256] fp32 = 6 KB: this CTA's partial statistics (DSMEM)
+constexpr uint32_t VEC = XBUF + 6144;                    // b1 | b2 | bh
+constexpr uint32_t MISC = VEC + VEC_BYTES;               // mbarriers, TMEM slot, small reductions
+constexpr uint32_t SMEM_BYTES = MISC + 512 + 1024;       // + alignment slack
+static_assert(SMEM_BYTES <= 232448, "shared memory budget of one SM");
+constexpr uint32_t A_BLK = ROWS * 128;                   // k-block stride of a 128-row tile
+constexpr uint32_t HEAD_SCRATCH = R0 + 32768;            // fp32 [128][65] head pre-activations / gradients (33,280 B)
+}  // namespace lc
+
+size_t learn_cluster_image_bytes() { return 2 * (size_t)lc::IMAGE_BYTES; }
+
+// ---------------------------------------------------------------------------------------------------
+// weight images of both networks (net 0 = target, 1 = main)
+__global__ void __launch_bounds__(256) learn_pack_kernel(rloa_naf_params pt, rloa_naf_params pm, uint8_t* __restrict__ images) {
+    using namespace lc;
+    const rloa_naf_params& p = blockIdx.y == 0 ? pt : pm;
+    uint8_t* image = images + (size_t)blockIdx.y * IMAGE_BYTES;
+    const int S = p.state_size, A = p.action_size, NL = A * (A + 1) / 2, NH = A + 1 + NL;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t < H * H / 8) {                                  // W2: one 16-byte chunk (8 consecutive k of row n)
+        const int n = t >> 5, kc = t & 31;
+        const float4 a = *reinterpret_cast<const float4*>(p.w2 + (size_t)n * H + kc * 8);
+        const float4 b = *reinterpret_cast<const float4*>(p.w2 + (size_t)n * H + kc * 8 + 4);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        *reinterpret_cast<uint4*>(image + OFF_W2 + (uint32_t)(kc >> 3) * (H * 128) + sw128_chunk_offset(n, kc & 7)) = pack8_bf16(v);
+        return;
+    }
+    int u = t - H * H / 8;
+    if (u < NHP * H / 8) {                                // head rows: [0,A) mu, A value, A+1.. matrix entries, rest zero
+        const int o = u >> 5, kc = u & 31;
+        const float* src = o < A ? p.w_mu + (size_t)o * H : (o == A ? p.w_v : (o < NH ? p.w_l + (size_t)(o - A - 1) * H : nullptr));
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = src != nullptr ? src[kc * 8 + i] : 0.f;
+        *reinterpret_cast<uint4*>(image + OFF_WH + (uint32_t)(kc >> 3) * (NHP * 128) + sw128_chunk_offset(o, kc & 7)) = pack8_bf16(v);
+        return;
+    }
+    u -= NHP * H / 8;
+    if (u < H * KP / 4) {                                 // W1 as tf32, K padded to 32
+        const int j = u >> 3, kc = u & 7;
+        float4 v;
+        float* vv = reinterpret_cast<float*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int k = kc * 4 + i;
+            vv[i] = k < S ? to_tf32(p.w1[(size_t)j * S + k]) : 0.f;
+        }
+        *reinterpret_cast<float4*>(image + OFF_W1 + sw128_chunk_offset(j, kc)) = v;
+        return;
+    }
+    u -= H * KP / 4;
+    float* vec = reinterpret_cast<float*>(image + OFF_VEC);
+    if (u < H) {
+        vec[u] = p.b1[u];
+        vec[H + u] = p.b2[u];
+        if (u < NHP) vec[2 * H + u] = u < A ? p.b_mu[u] : (u == A ? p.b_v[0] : (u < NH ? p.b_l[u - A - 1] : 0.f));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct LearnClusterArgs {
+    const uint8_t* images;                  // [2][IMAGE_BYTES]
+    rloa_naf_params p[2];                   // 0 = target, 1 = main
+    const float *states, *actions, *rewards, *next_states, *dones;
+    int B, S, A, NL, NH;
+    rloa_naf_hyper hp;
+    float* y;                               // [1024] TD targets, target cluster -> main cluster
+    unsigned* yflag;                        // [8], zero at rest
+    float *part_w2, *part_w1, *part_wh;     // [8][256*256], [8][256*S], [8][NH][256]
+    float *part_hb, *part_loss;             // [8][64], [8]
+    float *grad, *loss, *gnorm;             // outputs
+    ParamTable pt;
+    float *m, *v;
+    int64_t* step;
+    int do_adam;
+    int off_w1, off_b1, off_bn1w, off_bn1b, off_w2, off_b2, off_bn2w, off_bn2b, off_wmu, off_bmu, off_wv, off_bv, off_wl, off_bl, n_params;
+    float* dbg;                             // optional: z1 | z2 | dzh | dz2 | da1 | dz1 as fp32 [1024][256] each (dzh [1024][64])
+};
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem(const float* local, uint32_t rank) {
+    uint32_t ra;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
+}
+
+// mbarrier wait that cannot hang the GPU: a barrier that does not complete within ~2 s aborts the launch (a bug, never a
+// legitimate wait: every barrier here is fed by this CTA's own TMA copies or MMAs)
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+
+// column sums over the 32 rows of a warp: lane l enters with v[i] = (row l, column i), leaves with the sum of column l
+__device__ __forceinline__ float colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; i++) {
+            const float send = up ? v[i] : v[i + s];
+            const float keep = up ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
+__device__ __forceinline__ void store_chunks32(uint8_t* tile, int r, int c0, const float (&a)[32]) {
+    // 32 consecutive columns c0.. of row r -> four 16-byte bf16 chunks of a K-major SWIZZLE_128B tile (128 rows per k-block)
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const float x[8] = {a[8 * g], a[8 * g + 1], a[8 * g + 2], a[8 * g + 3], a[8 * g + 4], a[8 * g + 5], a[8 * g + 6], a[8 * g + 7]};
+        const int chunk = (c0 >> 3) + g;
+        *reinterpret_cast<uint4*>(tile + (chunk >> 3) * lc::A_BLK + sw128_chunk_offset(r, chunk & 7)) = pack8_bf16(x);
+    }
+}
+
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(lc::THREADS, 1)
+naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
+    using namespace lc;
+    extern __shared__ uint8_t lc_smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r = tid & 127, q = tid >> 7, wq = warp & 3;           // tile row (= TMEM lane), 64-column quarter, lane quarter
+    const int net = blockIdx.x >> 3;                                  // 0 = target (scheduled first), 1 = main
+    const int rank = (int)cluster_rank();
+    const int B = g.B, S = g.S, A = g.A, NH = g.NH;
+    const int row0 = rank * ROWS, row = row0 + r;
+    const bool valid = row < B;
+    const int nrows = min(max(B - row0, 0), ROWS);
+    const rloa_naf_params& P = g.p[net];
+    const uint8_t* image = g.images + (size_t)net * IMAGE_BYTES;
+
+    const uint32_t raw = smem_u32(lc_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* sm = lc_smem_raw + (base - raw);
+    float* coef = reinterpret_cast<float*>(sm + COEF);               // [layer][4][256]
+    float* xbuf = reinterpret_cast<float*>(sm + XBUF);               // [2][3][256]
+    float* vec = reinterpret_cast<float*>(sm + VEC);
+    float* scratch = reinterpret_cast<float*>(sm + S1);              // [3][4][256] + [3][256] (12 KB + 3 KB)
+    float* bcoef = scratch + 3 * 4 * 256;                            // k1 | cB | cC
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + MISC);         // 0: W1 (+vec), 1: W2, 2: Wh, 3: MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    float* red = reinterpret_cast<float*>(bars + 6);                 // [16] + [1]
+    uint32_t mma_phase = 0;
+
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);
+        mbar_init_fence();
+        mbar_expect_tx(&bars[0], W1_BYTES + VEC_BYTES);
+        bulk_g2s(sm + R1, image + OFF_W1, W1_BYTES, &bars[0]);
+        bulk_g2s(sm + VEC, image + OFF_VEC, VEC_BYTES, &bars[0]);
+        mbar_expect_tx(&bars[1], W2_BYTES);
+        bulk_g2s(sm + R0, image + OFF_W2, W2_BYTES, &bars[1]);
+    }
+    // this thread's 8 observation values (row r, k = 8 q .. 8 q + 7); kept in registers for the z1 recompute and dW1
+    float xk[8];
+    {
+        const float* x = net == 0 ? g.next_states : g.states;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int k = q * 8 + i;
+            xk[i] = (k < S && valid) ? x[(size_t)row * S + k] : 0.f;
+        }
+    }
+    auto stage_x_tf32 = [&](uint8_t* xh, uint8_t* xl) {
+        float h[8], l[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { h[i] = to_tf32(xk[i]); l[i] = to_tf32(xk[i] - h[i]); }
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const uint32_t off = sw128_chunk_offset(r, q * 2 + c);
+            *reinterpret_cast<float4*>(xh + off) = make_float4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+            *reinterpret_cast<float4*>(xl + off) = make_float4(l[4 * c], l[4 * c + 1], l[4 * c + 2], l[4 * c + 3]);
+        }
+    };
+    stage_x_tf32(sm + R1 + W1_BYTES, sm + R1 + W1_BYTES + 16384);
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);        // this warp's 32 TMEM lanes
+
+    auto mma_wait = [&]() {
+        __syncwarp();
+        mbar_wait_bounded(&bars[3], mma_phase);
+        mma_phase ^= 1u;
+        fence_after_sync();
+    };
+    auto issue_layer1 = [&](uint32_t w1_addr, uint32_t xh_addr, uint32_t xl_addr, uint32_t bar_phase) {
+        if (tid == 0) {
+            mbar_wait_bounded(&bars[0], bar_phase);
+            fence_after_sync();
+            constexpr uint32_t idesc = idesc_tf32_f32(128, H);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                mma_tf32(tmem, umma_desc_sw128(xh_addr + k * 32), umma_desc_sw128(w1_addr + k * 32), idesc, k > 0);
+                mma_tf32(tmem, umma_desc_sw128(xl_addr + k * 32), umma_desc_sw128(w1_addr + k * 32), idesc, true);
+            }
+            mma_commit(&bars[3]);
+        }
+    };
+
+    // ---- train-mode BatchNorm statistics of the pre-activations in TMEM columns tcol.. (+ bias): CTA partial (mean, M2),
+    // cluster exchange over DSMEM, merged batch statistics -> coef[layer] = sc | sh | mean | rstd; running statistics by rank 0
+    auto forward_stats = [&](int layer, uint32_t tcol, const float* bias, const float* bn_w, const float* bn_b,
+                             float* run_mean, float* run_var, int64_t* batches) {
+        float* part = scratch;                 // [4][256]
+        float* meanc = scratch + 4 * 256;      // [256]
+        float* xb = xbuf + (layer & 1) * 3 * 256;
+#pragma unroll 1
+        for (int p = 0; p < 2; p++) {
+            const int c0 = q * 64 + p * 32;
+            uint32_t v[32];
+            tmem_ld32(tlane + tcol + c0, v);
+            float z[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) z[i] = valid ? __uint_as_float(v[i]) + bias[c0 + i] : 0.f;
+            const float s = colsum32(z, lane);
+            part[wq * 256 + c0 + lane] = s;
+        }
+        __syncthreads();
+        if (tid < 256) {
+            const float tot = (part[tid] + part[256 + tid]) + (part[512 + tid] + part[768 + tid]);
+            meanc[tid] = nrows > 0 ? tot / (float)nrows : 0.f;
+        }
+        __syncthreads();
+        float* part2 = scratch + 5 * 256;      // [4][256]
+#pragma unroll 1
+        for (int p = 0; p < 2; p++) {
+            const int c0 = q * 64 + p * 32;
+            uint32_t v[32];
+            tmem_ld32(tlane + tcol + c0, v);
+            float d[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+                const float e = valid ? (__uint_as_float(v[i]) + bias[c0 + i]) - meanc[c0 + i] : 0.f;
+                d[i] = e * e;
+            }
+            const float s = colsum32(d, lane);
+            part2[wq * 256 + c0 + lane] = s;
+        }
+        __syncthreads();
+        if (tid < 256) {
+            xb[tid] = meanc[tid];
+            xb[256 + tid] = (part2[tid] + part2[256 + tid]) + (part2[512 + tid] + part2[768 + tid]);
+        }
+        cluster_sync_all();
+        if (tid < 256) {
+            float pm[CL], pM[CL];
+#pragma unroll
+            for (int c = 0; c < CL; c++) { pm[c] = ld_dsmem(xb + tid, c); pM[c] = ld_dsmem(xb + 256 + tid, c); }
+            float n = 0.f, mean = 0.f, M2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < CL; c++) {
+                const float nb = (float)min(max(B - c * ROWS, 0), ROWS);
+                if (nb > 0.f) {
+                    const float nn = n + nb, delta = pm[c] - mean;
+                    mean = fmaf(delta, nb / nn, mean);
+                    M2 = M2 + pM[c] + delta * delta * (n * nb / nn);
+                    n = nn;
+                }
+            }
+            const float var = M2 / (float)B;
+            const float rstd = 1.f / sqrtf(var + kBnEps);
+            const float sc = bn_w[tid] * rstd;
+            float* cf = coef + layer * 4 * 256;
+            cf[tid] = sc;
+            cf[256 + tid] = fmaf(-mean, sc, bn_b[tid]);
+            cf[512 + tid] = mean;
+            cf[768 + tid] = rstd;
+            if (rank == 0) {
+                const float unbiased = B > 1 ? M2 / (float)(B - 1) : var;
+                run_mean[tid] = fmaf(kBnMomentum, mean - run_mean[tid], run_mean[tid]);
+                run_var[tid] = fmaf(kBnMomentum, unbiased - run_var[tid], run_var[tid]);
+                if (tid == 0 && batches != nullptr) *batches += 1;
+            }
+        }
+        __syncthreads();
+    };
+    // relu(bn(z)) of TMEM columns tcol.. -> bf16 K-major tile (rows past the batch are zero)
+    auto activation_to_tile = [&](int layer, uint32_t tcol, const float* bias, uint8_t* tile) {
+        const float* cf = coef + layer * 4 * 256;
+#pragma unroll 1
+        for (int p = 0; p < 2; p++) {
+            const int c0 = q * 64 + p * 32;
+            uint32_t v[32];
+            tmem_ld32(tlane + tcol + c0, v);
+            float a[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++)
+                a[i] = valid ? fmaxf(fmaf(__uint_as_float(v[i]) + bias[c0 + i], cf[c0 + i], cf[256 + c0 + i]), 0.f) : 0.f;
+            store_chunks32(tile, r, c0, a);
+        }
+    };
+    auto dbg_rows32 = [&](int section, int width, int c0, const float (&a)[32]) {
+        if (g.dbg != nullptr && net == 1 && valid) {
+            float* d = g.dbg + (size_t)section * 1024 * 256 + (size_t)row * width + c0;
+#pragma unroll
+            for (int i = 0; i < 32; i++) d[i] = a[i];
+        }
+    };
+
+    // =========================== forward ===========================
+    issue_layer1(base + R1, base + R1 + W1_BYTES, base + R1 + W1_BYTES + 16384, 0);
+    mbar_wait_bounded(&bars[0], 0);                       // biases, for every thread
+    mma_wait();
+    forward_stats(0, 0, vec, P.bn1_w, P.bn1_b, P.bn1_mean, P.bn1_var, P.bn1_batches);
+    if (g.dbg != nullptr && net == 1) {
+#pragma unroll 1
+        for (int p = 0; p < 2; p++) {
+            uint32_t v[32];
+            float a[32];
+            tmem_ld32(tlane + q * 64 + p * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; i++) a[i] = __uint_as_float(v[i]) + vec[q * 64 + p * 32 + i];
+            dbg_rows32(0, 256, q * 64 + p * 32, a);
+        }
+    }
+    activation_to_tile(0, 0, vec, sm + R1);               // a1 over the dead layer-1 operands
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (tid == 0) {                                       // z2 = a1 W2^T -> TMEM columns 256-511
+        mbar_wait_bounded(&bars[1], 0);
+        fence_after_sync();
+        constexpr uint32_t idesc = idesc_bf16_f32(128, H);
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            mma_bf16(tmem + 256, umma_desc_sw128(base + R1 + (k >> 2) * A_BLK + (k & 3) * 32),
+                     umma_desc_sw128(base + R0 + (k >> 2) * (H * 128) + (k & 3) * 32), idesc, k > 0);
+        mma_commit(&bars[3]);
+    }
+    mma_wait();
+    if (tid == 0) {                                       // the W2 slot is free: head image -> its first 32 KB
+        mbar_expect_tx(&bars[2], WH_BYTES);
+        bulk_g2s(sm + R0, image + OFF_WH, WH_BYTES, &bars[2]);
+    }
+    forward_stats(1, 256, vec + H, P.bn2_w, P.bn2_b, P.bn2_mean, P.bn2_var, P.bn2_batches);
+    if (g.dbg != nullptr && net == 1) {
+#pragma unroll 1
+        for (int p = 0; p < 2; p++) {
+            uint32_t v[32];
+            float a[32];
+            tmem_ld32(tlane + 256 + q * 64 + p * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; i++) a[i] = __uint_as_float(v[i]) + vec[H + q * 64 + p * 32 + i];
+            dbg_rows32(1, 256, q * 64 + p * 32, a);
+        }
+    }
+    activation_to_tile(1, 256, vec + H, sm + R1);         // a2
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (tid == 0) {                                       // heads = a2 Wh^T -> TMEM columns 0-63
+        mbar_wait_bounded(&bars[2], 0);
+        fence_after_sync();
+        constexpr uint32_t idesc = idesc_bf16_f32(128, NHP);
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            mma_bf16(tmem, umma_desc_sw128(base + R1 + (k >> 2) * A_BLK + (k & 3) * 32),
+                     umma_desc_sw128(base + R0 + (k >> 2) * (NHP * 128) + (k & 3) * 32), idesc, k > 0);
+        mma_commit(&bars[3]);
+    }
+    mma_wait();
+
+    // =========================== head ===========================
+    float* hrow = reinterpret_cast<float*>(sm + HEAD_SCRATCH) + r * 65;      // this row's 64 head values (q == 0 threads)
+    const float* bh = vec + 2 * H;
+    if (q == 0) {
+#pragma unroll 1
+        for (int p = 0; p < 2; p++) {
+            uint32_t v[32];
+            tmem_ld32(tlane + p * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; i++) hrow[p * 32 + i] = __uint_as_float(v[i]) + bh[p * 32 + i];
+        }
+    }
+    if (net == 0) {
+        // ---- target network: y = r + gamma V'(s') for this CTA's rows, then hand over to the main CTA of the same rank
+        if (q == 0 && valid) {
+            float vv = hrow[A];
+            if (g.hp.use_done_mask && g.dones != nullptr) vv *= (1.f - g.dones[row]);
+            g.y[row] = fmaf(g.hp.gamma, vv, g.rewards[row]);
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            unsigned one = 1u;
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(g.yflag + rank), "r"(one) : "memory");
+        }
+    } else {
+        // ---- main network: TD error, loss, gradients of the head pre-activations ----
+        if (tid == 0) {
+            unsigned f = 0u;
+            const long long t0 = clock64();
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(g.yflag + rank) : "memory");
+                if (f == 0u && clock64() - t0 > 4000000000ll) __trap();      // the target cluster never ran: abort, do not hang
+            } while (f == 0u);
+        }
+        __syncthreads();
+        float err2 = 0.f;
+        if (q == 0) {
+            float dzh[64];
+#pragma unroll
+            for (int i = 0; i < 64; i++) dzh[i] = 0.f;
+            if (valid) {
+                const float yrow = __ldcg(g.y + row);
+                const float vval = hrow[A];
+                float adv = 0.f;
+                float gmu[10], gl[10];
+                for (int k = 0; k < A; k++) {
+                    const float mu = tanhf(hrow[k]);
+                    const float t = tanhf(hrow[A + 1 + (k * (k + 3)) / 2]);
+                    const float Pk = expf(2.f * t);
+                    float u = g.actions[(size_t)row * A + k];
+                    if (g.hp.trunc_action) u = truncf(u);
+                    const float diff = u - mu;
+                    adv = fmaf(-0.5f * Pk * diff, diff, adv);
+                    gmu[k] = Pk * diff * (1.f - mu * mu);
+                    gl[k] = -Pk * diff * diff * (1.f - t * t);
+                }
+                const float err = (vval + adv) - yrow;
+                err2 = err * err;
+                const float dq = 2.f * err / (float)B;             // MSE over the batch (naf_algorithm.py:204)
+                // static indexing of dzh: walk the outputs once
+#pragma unroll
+                for (int o = 0; o < 64; o++) {
+                    float gv = 0.f;
+                    if (o < A) gv = dq * gmu[o < 10 ? o : 0];
+                    else if (o == A) gv = dq;
+                    else {
+                        const int e = o - A - 1;
+                        for (int k = 0; k < A; k++)
+                            if ((k * (k + 3)) / 2 == e) gv = dq * gl[k];
+                    }
+                    dzh[o] = o < NH ? gv : 0.f;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 64; i++) hrow[i] = dzh[i];
+            // bf16 tile [128 rows][64 columns] (one k-block) for dWh^T and da2
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const float x[8] = {dzh[8 * c], dzh[8 * c + 1], dzh[8 * c + 2], dzh[8 * c + 3],
+                                    dzh[8 * c + 4], dzh[8 * c + 5], dzh[8 * c + 6], dzh[8 * c + 7]};
+                *reinterpret_cast<uint4*>(sm + S1 + sw128_chunk_offset(r, c)) = pack8_bf16(x);
+            }
+            if (g.dbg != nullptr && valid) {
+                float* d = g.dbg + (size_t)2 * 1024 * 256 + (size_t)row * 64;
+#pragma unroll
+                for (int i = 0; i < 64; i++) d[i] = dzh[i];
+            }
+        }
+        // loss partial of this CTA (fixed order: lanes, then warps 0-3)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, off);
+        if (q == 0 && lane == 0) red[wq] = err2;
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            g.part_loss[rank] = (red[0] + red[1]) + (red[2] + red[3]);
+            g.yflag[rank] = 0u;                                  // consumed: zero at rest
+        }
+        if (tid < 64) {                                          // head bias gradients: column sums of dzh over this CTA's rows
+            const float* hs = reinterpret_cast<const float*>(sm + HEAD_SCRATCH);
+            float s = 0.f;
+            for (int rr = 0; rr < ROWS; rr++) s += hs[rr * 65 + tid];
+            g.part_hb[rank * 64 + tid] = s;
+        }
+        fence_proxy_async();     // the generic reads of the head scratch precede the TMA write that reuses its slot
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+
+        // =========================== backward ===========================
+        if (tid == 0) {          // dWh^T [256 f][64 o] = a2^T dzh: both tiles MN-major, contraction over the 128 rows
+            constexpr uint32_t idesc = idesc_bf16_f32(128, NHP) | kIdescAMajorMN | kIdescBMajorMN;
+#pragma unroll
+            for (int half = 0; half < 2; half++)
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    mma_bf16(tmem + 64 + half * 64, umma_desc_sw128_mn(base + R1 + half * 2 * A_BLK + k * 2048, A_BLK),
+                             umma_desc_sw128_mn(base + S1 + k * 2048, A_BLK), idesc, k > 0);
+            mma_commit(&bars[3]);
+        }
+        mma_wait();
+        if (q < 2) {             // partial head-weight gradient of this CTA: part_wh[rank][o][f], f = 128 q + r
+            float* dst = g.part_wh + (size_t)rank * NH * H + (q * 128 + r);
+#pragma unroll 1
+            for (int p = 0; p < 2; p++) {
+                uint32_t v[32];
+                tmem_ld32(tlane + 64 + q * 64 + p * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; i++)
+                    if (p * 32 + i < NH) dst[(size_t)(p * 32 + i) * H] = __uint_as_float(v[i]);
+            }
+        }
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+        if (tid == 0) {          // da2 [128][256] = dzh Wh: B = the head image read MN-major (contraction over its 64 rows)
+            constexpr uint32_t idesc = idesc_bf16_f32(128, H) | kIdescBMajorMN;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                mma_bf16(tmem, umma_desc_sw128(base + S1 + k * 32), umma_desc_sw128_mn(base + R0 + k * 2048, NHP * 128), idesc, k > 0);
+            mma_commit(&bars[3]);
+        }
+        mma_wait();
+        if (tid == 0) {          // head image and scratch are dead: W2 image back into its slot for da1
+            mbar_expect_tx(&bars[1], W2_BYTES);
+            bulk_g2s(sm + R0, image + OFF_W2, W2_BYTES, &bars[1]);
+        }
+
+        // ReLU + BatchNorm backward of one layer: da in TMEM columns dcol.., z in zcol.. (+ bias).  Pass 1: column sums of
+        // g = da [bn(z) > 0], g xhat and (z - mean) over the whole batch through the cluster; pass 2 (by the caller):
+        // dz = k1 g - cB - cC (z - mean).  gamma / beta / linear-bias gradients are totals: rank 0 writes them.
+        auto backward_stats = [&](int layer, uint32_t dcol, uint32_t zcol, const float* bias, const float* bn_w, int xslot,
+                                  float* d_w, float* d_b, float* d_lin) {
+            const float* cf = coef + layer * 4 * 256;
+            float* xb = xbuf + xslot * 3 * 256;
+#pragma unroll 1
+            for (int p = 0; p < 2; p++) {
+                const int c0 = q * 64 + p * 32;
+                // one quantity at a time (the accumulators are re-read from TMEM: 16 TB/s, cheaper than 96 live registers)
+#pragma unroll 1
+                for (int k = 0; k < 3; k++) {
+                    uint32_t vd[32], vz[32];
+                    tmem_ld32(tlane + zcol + c0, vz);
+                    if (k < 2) tmem_ld32(tlane + dcol + c0, vd);
+                    float a[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        const float z = __uint_as_float(vz[i]) + bias[c0 + i];
+                        const float zc = valid ? z - cf[512 + c0 + i] : 0.f;
+                        if (k == 2) {
+                            a[i] = zc;
+                        } else {
+                            const float gg = (valid && fmaf(z, cf[c0 + i], cf[256 + c0 + i]) > 0.f) ? __uint_as_float(vd[i]) : 0.f;
+                            a[i] = k == 0 ? gg : gg * (zc * cf[768 + c0 + i]);
+                        }
+                    }
+                    const float sres = colsum32(a, lane);
+                    scratch[k * 1024 + wq * 256 + c0 + lane] = sres;
+                }
+            }
+            __syncthreads();
+            if (tid < 256) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const float* pp = scratch + k * 1024;
+                    xb[k * 256 + tid] = (pp[tid] + pp[256 + tid]) + (pp[512 + tid] + pp[768 + tid]);
+                }
+            }
+            cluster_sync_all();
+            if (tid < 256) {
+                float t[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    float pv[CL];
+#pragma unroll
+                    for (int c = 0; c < CL; c++) pv[c] = ld_dsmem(xb + k * 256 + tid, c);
+#pragma unroll
+                    for (int c = 0; c < CL; c++) t[k] += pv[c];
+                }
+                const float rs = cf[768 + tid];
+                const float k1 = bn_w[tid] * rs, c1 = t[0] / (float)B, c2 = t[1] / (float)B;
+                bcoef[tid] = k1;
+                bcoef[256 + tid] = k1 * c1;
+                bcoef[512 + tid] = k1 * c2 * rs;
+                if (rank == 0) {
+                    d_w[tid] = t[1];
+                    d_b[tid] = t[0];
+                    d_lin[tid] = k1 * (t[0] - (float)B * c1) - k1 * c2 * rs * t[2];
+                }
+            }
+            __syncthreads();
+        };
+
+        backward_stats(1, 0, 256, vec + H, P.bn2_w, 0, g.grad + g.off_bn2w, g.grad + g.off_bn2b, g.grad + g.off_b2);
+        {   // dz2 -> bf16 tile in R1 (a2 is dead: dWh^T finished)
+            const float* cf = coef + 1 * 4 * 256;
+#pragma unroll 1
+            for (int p = 0; p < 2; p++) {
+                const int c0 = q * 64 + p * 32;
+                uint32_t vd[32], vz[32];
+                tmem_ld32(tlane + c0, vd);
+                tmem_ld32(tlane + 256 + c0, vz);
+                float a[32];
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    const float z = __uint_as_float(vz[i]) + vec[H + c0 + i];
+                    const float gg = fmaf(z, cf[c0 + i], cf[256 + c0 + i]) > 0.f ? __uint_as_float(vd[i]) : 0.f;
+                    a[i] = valid ? fmaf(bcoef[c0 + i], gg, -bcoef[256 + c0 + i]) - bcoef[512 + c0 + i] * (z - cf[512 + c0 + i]) : 0.f;
+                }
+                store_chunks32(sm + R1, r, c0, a);
+                dbg_rows32(3, 256, c0, a);
+            }
+        }
+        fence_proxy_async();
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+        if (tid == 0) {          // da1 [128][256] = dz2 W2: B = the forward W2 image read MN-major -> TMEM columns 256-511
+            mbar_wait_bounded(&bars[1], 1);
+            fence_after_sync();
+            constexpr uint32_t idesc = idesc_bf16_f32(128, H) | kIdescBMajorMN;
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                mma_bf16(tmem + 256, umma_desc_sw128(base + R1 + (k >> 2) * A_BLK + (k & 3) * 32),
+                         umma_desc_sw128_mn(base + R0 + k * 2048, H * 128), idesc, k > 0);
+            mma_commit(&bars[3]);
+        }
+        mma_wait();
+        if (tid == 0) {          // W2 is dead: layer-1 operands back (W1 image by TMA, observations from registers)
+            mbar_expect_tx(&bars[0], W1_BYTES);
+            bulk_g2s(sm + R0, image + OFF_W1, W1_BYTES, &bars[0]);
+        }
+        stage_x_tf32(sm + R0 + W1_BYTES, sm + R0 + W1_BYTES + 16384);
+        fence_proxy_async();
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+        issue_layer1(base + R0, base + R0 + W1_BYTES, base + R0 + W1_BYTES + 16384, 1);      // z1 again -> TMEM columns 0-255
+        mma_wait();
+        backward_stats(0, 256, 0, vec, P.bn1_w, 1, g.grad + g.off_bn1w, g.grad + g.off_bn1b, g.grad + g.off_b1);
+        {   // dz1 -> R0 + 64 KB, a1 -> R0 (the layer-1 operands there are dead: z1 is in TMEM)
+            const float* cf = coef;
+#pragma unroll 1
+            for (int p = 0; p < 2; p++) {
+                const int c0 = q * 64 + p * 32;
+                {
+                    uint32_t vd[32], vz[32];
+                    tmem_ld32(tlane + 256 + c0, vd);
+                    tmem_ld32(tlane + c0, vz);
+                    float d[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        const float z = __uint_as_float(vz[i]) + vec[c0 + i];
+                        const float gg = fmaf(z, cf[c0 + i], cf[256 + c0 + i]) > 0.f ? __uint_as_float(vd[i]) : 0.f;
+                        d[i] = valid ? fmaf(bcoef[c0 + i], gg, -bcoef[256 + c0 + i]) - bcoef[512 + c0 + i] * (z - cf[512 + c0 + i]) : 0.f;
+                    }
+                    store_chunks32(sm + R0 + 65536, r, c0, d);
+                    dbg_rows32(5, 256, c0, d);
+                    if (g.dbg != nullptr) {
+                        float da[32];
+#pragma unroll
+                        for (int i = 0; i < 32; i++) da[i] = __uint_as_float(vd[i]);
+                        dbg_rows32(4, 256, c0, da);
+                    }
+                }
+                {
+                    uint32_t vz[32];
+                    tmem_ld32(tlane + c0, vz);
+                    float a[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i++)
+                        a[i] = valid ? fmaxf(fmaf(__uint_as_float(vz[i]) + vec[c0 + i], cf[c0 + i], cf[256 + c0 + i]), 0.f) : 0.f;
+                    store_chunks32(sm + R0, r, c0, a);
+                }
+            }
+        }
+        __syncthreads();         // the backward coefficients in S1 are dead: the observation tile takes their place
+        {   // [x_hi | x_lo] as bf16, 64 columns: hi(k) at column k, lo(k) at column 32 + k
+            float h[8], l[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                h[i] = __bfloat162float(__float2bfloat16_rn(xk[i]));
+                l[i] = xk[i] - h[i];
+            }
+            *reinterpret_cast<uint4*>(sm + S1 + sw128_chunk_offset(r, q)) = pack8_bf16(h);
+            *reinterpret_cast<uint4*>(sm + S1 + sw128_chunk_offset(r, 4 + q)) = pack8_bf16(l);
+        }
+        fence_proxy_async();
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+        if (tid == 0) {          // dW2 [256 n][256 k] = dz2^T a1 -> all 512 TMEM columns (n half h in columns 256 h ..)
+            constexpr uint32_t idesc = idesc_bf16_f32(128, H) | kIdescAMajorMN | kIdescBMajorMN;
+#pragma unroll
+            for (int half = 0; half < 2; half++)
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    mma_bf16(tmem + half * 256, umma_desc_sw128_mn(base + R1 + half * 2 * A_BLK + k * 2048, A_BLK),
+                             umma_desc_sw128_mn(base + R0 + k * 2048, A_BLK), idesc, k > 0);
+            mma_commit(&bars[3]);
+        }
+        mma_wait();
+        {   // partial dW2 of this CTA: row n = 128 half + r, columns 64 q ..
+            float* dst = g.part_w2 + (size_t)rank * H * H;
+#pragma unroll 1
+            for (int half = 0; half < 2; half++)
+#pragma unroll 1
+                for (int p = 0; p < 2; p++) {
+                    const int c0 = q * 64 + p * 32;
+                    uint32_t v[32];
+                    tmem_ld32(tlane + half * 256 + c0, v);
+                    float4* o = reinterpret_cast<float4*>(dst + (size_t)(half * 128 + r) * H + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                           __uint_as_float(v[4 * j + 3]));
+                }
+        }
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+        if (tid == 0) {          // dW1 [256 h][hi 32 | lo 32] = dz1^T [x_hi | x_lo]
+            constexpr uint32_t idesc = idesc_bf16_f32(128, 64) | kIdescAMajorMN | kIdescBMajorMN;
+#pragma unroll
+            for (int half = 0; half < 2; half++)
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    mma_bf16(tmem + half * 64, umma_desc_sw128_mn(base + R0 + 65536 + half * 2 * A_BLK + k * 2048, A_BLK),
+                             umma_desc_sw128_mn(base + S1 + k * 2048, A_BLK), idesc, k > 0);
+            mma_commit(&bars[3]);
+        }
+        mma_wait();
+        if (q < 2) {
+            float* dst = g.part_w1 + (size_t)rank * H * S + (size_t)(q * 128 + r) * S;
+            uint32_t v0[32], v1[32];
+            tmem_ld32(tlane + q * 64, v0);
+            tmem_ld32(tlane + q * 64 + 32, v1);
+#pragma unroll
+            for (int i = 0; i < 24; i++)
+                if (i < S) dst[i] = __uint_as_float(v0[i]) + __uint_as_float(v1[i]);
+        }
+
+        // =========================== optimiser tail ===========================
+        __threadfence();
+        cluster_sync_all();                                    // every CTA's partials (and rank 0's totals) are visible
+        const int n = g.n_params;
+        const float gs = g.hp.grad_scale;
+        // (a) this CTA's eighth of dW2, float4; (b) its share of everything else, scalar
+        float4 gw[4];
+        float sq = 0.f;
+        {
+            const float4* pw = reinterpret_cast<const float4*>(g.part_w2);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int i4 = rank * 2048 + j * 512 + tid;                  // 16384 float4 in W2, 2048 per CTA
+                float4 pv[CL];
+#pragma unroll
+                for (int c = 0; c < CL; c++) pv[c] = __ldcg(pw + (size_t)c * (H * H / 4) + i4);
+                float4 s4 = pv[0];
+#pragma unroll
+                for (int c = 1; c < CL; c++) { s4.x += pv[c].x; s4.y += pv[c].y; s4.z += pv[c].z; s4.w += pv[c].w; }
+                gw[j] = s4;
+                reinterpret_cast<float4*>(g.grad + g.off_w2)[i4] = s4;
+                const float x0 = s4.x * gs, x1 = s4.y * gs, x2 = s4.z * gs, x3 = s4.w * gs;
+                sq = fmaf(x0, x0, sq); sq = fmaf(x1, x1, sq); sq = fmaf(x2, x2, sq); sq = fmaf(x3, x3, sq);
+            }
+        }
+        // the remaining n - 65536 elements, compacted (W2 skipped): element e of that list, CTA c takes e in [c m, (c+1) m)
+        const int rest = n - H * H, per = (rest + CL - 1) / CL;
+        float gr[8];
+        int gi[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int e = rank * per + j * THREADS + tid;
+            gi[j] = -1;
+            gr[j] = 0.f;
+            if (j * THREADS + tid < per && e < rest) {
+                const int i = e < g.off_w2 ? e : e + H * H;                   // flat index
+                float s = 0.f;
+                if (i < g.off_b1) {                                           // dW1: 8 partials
+                    float pv[CL];
+#pragma unroll
+                    for (int c = 0; c < CL; c++) pv[c] = __ldcg(g.part_w1 + (size_t)c * H * S + i);
+#pragma unroll
+                    for (int c = 0; c < CL; c++) s += pv[c];
+                } else if (i < g.off_wmu) {                                   // b1, bn1, b2, bn2: totals left by rank 0
+                    s = __ldcg(g.grad + i);
+                } else {                                                      // heads
+                    int o = -1, f = 0;
+                    if (i < g.off_bmu) { o = (i - g.off_wmu) / H; f = (i - g.off_wmu) - o * H; }
+                    else if (i < g.off_wv) { o = i - g.off_bmu; f = -1; }
+                    else if (i < g.off_bv) { o = A; f = i - g.off_wv; }
+                    else if (i < g.off_wl) { o = A; f = -1; }
+                    else if (i < g.off_bl) { const int oo = (i - g.off_wl) / H; o = A + 1 + oo; f = (i - g.off_wl) - oo * H; }
+                    else { o = A + 1 + (i - g.off_bl); f = -1; }
+                    float pv[CL];
+#pragma unroll
+                    for (int c = 0; c < CL; c++)
+                        pv[c] = f >= 0 ? __ldcg(g.part_wh + (size_t)c * NH * H + (size_t)o * H + f) : __ldcg(g.part_hb + c * 64 + o);
+#pragma unroll
+                    for (int c = 0; c < CL; c++) s += pv[c];
+                }
+                gi[j] = i;
+                gr[j] = s;
+                g.grad[i] = s;
+                const float x = s * gs;
+                sq = fmaf(x, x, sq);
+            }
+        }
+        // squared norm: warp tree, warps in order, CTAs in rank order over DSMEM
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+        if (lane == 0) red[warp] = sq;
+        __syncthreads();
+        float* normslot = xbuf;                                 // DSMEM-visible slot (the statistics buffers are dead)
+        if (tid == 0) {
+            float t = 0.f;
+            for (int w = 0; w < THREADS / 32; w++) t += red[w];
+            normslot[0] = t;
+        }
+        cluster_sync_all();
+        if (g.do_adam) {
+            if (tid == 0) {
+                float t = 0.f;
+                for (int c = 0; c < CL; c++) t += ld_dsmem(normslot, c);
+                const long long step = (long long)(*g.step) + 1;            // optimizer.step() count of this update
+                AdamCoef c;
+                c.norm = sqrtf(t);
+                c.clip = fminf(g.hp.clip_norm / (c.norm + 1e-6f), 1.f) * g.hp.grad_scale;
+                c.bc1 = 1.f - powf(g.hp.beta1, (float)step);
+                c.bc2s = sqrtf(1.f - powf(g.hp.beta2, (float)step));
+                *reinterpret_cast<AdamCoef*>(red + 20) = c;
+                if (rank == 0) {
+                    if (g.gnorm != nullptr) *g.gnorm = c.norm;
+                    if (g.loss != nullptr) {
+                        float l = 0.f;
+                        for (int cc = 0; cc < CL; cc++) l += __ldcg(g.part_loss + cc);
+                        *g.loss = l / (float)B;
+                    }
+                }
+            }
+            __syncthreads();
+            const AdamCoef c = *reinterpret_cast<const AdamCoef*>(red + 20);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int i = g.off_w2 + 4 * (rank * 2048 + j * 512 + tid);
+                adam_soft_update_element(g.pt, i, gw[j].x, c, g.m, g.v, g.hp);
+                adam_soft_update_element(g.pt, i + 1, gw[j].y, c, g.m, g.v, g.hp);
+                adam_soft_update_element(g.pt, i + 2, gw[j].z, c, g.m, g.v, g.hp);
+                adam_soft_update_element(g.pt, i + 3, gw[j].w, c, g.m, g.v, g.hp);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (gi[j] >= 0) adam_soft_update_element(g.pt, gi[j], gr[j], c, g.m, g.v, g.hp);
+        } else if (rank == 0 && tid == 0 && g.loss != nullptr) {
+            float l = 0.f;
+            for (int cc = 0; cc < CL; cc++) l += __ldcg(g.part_loss + cc);
+            *g.loss = l / (float)B;
+        }
+    }
+    // a CTA's shared memory must outlive every DSMEM read of it; the step counter moves after everybody has read it
+    cluster_sync_all();
+    if (net == 1 && g.do_adam && rank == 0 && tid == 0) *g.step += 1;
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------
+bool learn_cluster_supported(int S, int A, int H, int B) {
+    const int NH = A + 1 + A * (A + 1) / 2;
+    return H == lc::H && S >= 1 && S <= 24 && A >= 1 && A <= 9 && NH <= lc::NHP && B >= 2 && B <= lc::CL * lc::ROWS;
+}
+
+int learn_cluster_prepare(LearnCluster* lcw, int S, int A) {
+    if (lcw->images != nullptr) return RLOA_OK;
+    const int NH = A + 1 + A * (A + 1) / 2;
+    RLOA_CUDA(cudaFuncSetAttribute(naf_learn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc::SMEM_BYTES));
+    const size_t floats = 1024 + (size_t)lc::CL * (lc::H * lc::H + lc::H * S + (size_t)NH * lc::H + 64 + 1) + 16;
+    RLOA_CUDA(cudaMalloc(&lcw->images, learn_cluster_image_bytes()));
+    if (cudaMalloc(&lcw->block, floats * sizeof(float)) != cudaSuccess) {
+        cudaFree(lcw->images);
+        lcw->images = nullptr;
+        set_error("learn cluster: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return RLOA_ERR_CUDA;
+    }
+    RLOA_CUDA(cudaMemset(lcw->block, 0, floats * sizeof(float)));
+    float* p = lcw->block;
+    lcw->y = p; p += 1024;
+    lcw->part_w2 = p; p += (size_t)lc::CL * lc::H * lc::H;
+    lcw->part_w1 = p; p += (size_t)lc::CL * lc::H * S;
+    lcw->part_wh = p; p += (size_t)lc::CL * NH * lc::H;
+    lcw->part_hb = p; p += lc::CL * 64;
+    lcw->part_loss = p; p += lc::CL;
+    lcw->yflag = reinterpret_cast<unsigned*>(p);
+    return RLOA_OK;
+}
+
+void learn_cluster_free(LearnCluster* lcw) {
+    if (lcw->images) cudaFree(lcw->images);
+    if (lcw->block) cudaFree(lcw->block);
+    *lcw = LearnCluster{};
+}
+
+int learn_cluster_step(LearnCluster* lcw, const rloa_naf_params* mn, const rloa_naf_params* tg, const rloa_adam_state* adam,
+                       const float* states, const float* actions, const float* rewards, const float* next_states,
+                       const float* dones, int B, const rloa_naf_hyper* hp, const ParamTable& pt, const int* flat_offsets,
+                       float* grad, float* loss, float* gnorm, int do_adam, cudaStream_t st) {
+    RLOA_REQUIRE(lcw->images != nullptr, "learn cluster: not prepared");
+    const int S = mn->state_size, A = mn->action_size;
+    const int pack_threads = lc::H * lc::H / 8 + lc::NHP * lc::H / 8 + lc::H * lc::KP / 4 + lc::H;
+    learn_pack_kernel<<<dim3((pack_threads + 255) / 256, 2), 256, 0, st>>>(*tg, *mn, static_cast<uint8_t*>(lcw->images));
+    RLOA_LAUNCHED();
+    LearnClusterArgs a{};
+    a.images = static_cast<const uint8_t*>(lcw->images);
+    a.p[0] = *tg; a.p[1] = *mn;
+    a.states = states; a.actions = actions; a.rewards = rewards; a.next_states = next_states; a.dones = dones;
+    a.B = B; a.S = S; a.A = A; a.NL = A * (A + 1) / 2; a.NH = A + 1 + a.NL;
+    a.hp = *hp;
+    a.y = lcw->y; a.yflag = lcw->yflag;
+    a.part_w2 = lcw->part_w2; a.part_w1 = lcw->part_w1; a.part_wh = lcw->part_wh; a.part_hb = lcw->part_hb; a.part_loss = lcw->part_loss;
+    a.grad = grad; a.loss = loss; a.gnorm = gnorm;
+    a.pt = pt;
+    a.m = adam != nullptr ? adam->m : nullptr; a.v = adam != nullptr ? adam->v : nullptr; a.step = adam != nullptr ? adam->step : nullptr;
+    a.do_adam = do_adam;
+    a.off_w1 = flat_offsets[0]; a.off_b1 = flat_offsets[1]; a.off_bn1w = flat_offsets[2]; a.off_bn1b = flat_offsets[3];
+    a.off_w2 = flat_offsets[4]; a.off_b2 = flat_offsets[5]; a.off_bn2w = flat_offsets[6]; a.off_bn2b = flat_offsets[7];
+    a.off_wmu = flat_offsets[8]; a.off_bmu = flat_offsets[9]; a.off_wv = flat_offsets[10]; a.off_bv = flat_offsets[11];
+    a.off_wl = flat_offsets[12]; a.off_bl = flat_offsets[13]; a.n_params = flat_offsets[14];
+    a.dbg = lcw->dbg;
+    naf_learn_cluster_kernel<<<2 * lc::CL, lc::THREADS, lc::SMEM_BYTES, st>>>(a);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
+}  // namespace rloa

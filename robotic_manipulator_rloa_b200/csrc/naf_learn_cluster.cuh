@@ -1,0 +1,28 @@
+// Fused NAFAgent.learn on two thread-block clusters (naf_learn_cluster.cu) — declarations for naf.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "optim.cuh"
+#include "rloa_b200.h"
+
+namespace rloa {
+
+struct LearnCluster {
+    void* images = nullptr;          // bf16 / tf32 weight images of both networks (shared-memory byte order)
+    float* block = nullptr;          // y | partial weight gradients | head-bias / loss partials | hand-over flags
+    float *y = nullptr, *part_w2 = nullptr, *part_w1 = nullptr, *part_wh = nullptr, *part_hb = nullptr, *part_loss = nullptr;
+    unsigned* yflag = nullptr;
+    float* dbg = nullptr;            // optional intermediate dump (tests)
+};
+
+bool learn_cluster_supported(int S, int A, int H, int B);
+int learn_cluster_prepare(LearnCluster* lc, int S, int A);
+void learn_cluster_free(LearnCluster* lc);
+// flat_offsets: the 14 segment offsets of the flat gradient in nn.Module.parameters() order + the total
+int learn_cluster_step(LearnCluster* lc, const rloa_naf_params* mn, const rloa_naf_params* tg, const rloa_adam_state* adam,
+                       const float* states, const float* actions, const float* rewards, const float* next_states,
+                       const float* dones, int B, const rloa_naf_hyper* hp, const ParamTable& pt, const int* flat_offsets,
+                       float* grad, float* loss, float* gnorm, int do_adam, cudaStream_t st);
+
+}  // namespace rloa
