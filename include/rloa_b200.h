@@ -252,10 +252,12 @@ void rloa_naf_ws_destroy(rloa_naf_ws* ws);
 /* 0 = fp32 CUDA-core trunk (reference-exact numerics), 1 = tcgen05 tensor-core trunk
  * (bf16 operands, fp32 TMEM accumulation; looser bound) */
 int rloa_naf_ws_set_trunk(rloa_naf_ws* ws, int32_t mode);
-/* Diagnostics of the fused tensor-core learn kernel (csrc/naf_learn_cluster.cu, trunk mode 1, batch <= 1024): when
- * buffer != NULL the next learn calls dump their intermediates as fp32 — six sections of 1024 x 256 floats:
- * z1 | z2 | dzh (row stride 64) | dz2 | da1 | dz1 — so each stage can be checked against autograd.  NULL switches it off. */
-int rloa_naf_ws_set_debug(rloa_naf_ws* ws, float* buffer);
+/* Diagnostics of the fused tensor-core learn kernel (csrc/naf_learn_cluster.cu, trunk mode 1, batch <= 1024).
+ * buffer != NULL: the next learn calls dump their intermediates as fp32 — six sections of 1024 x 256 floats:
+ * z1 | z2 | dzh (row stride 64) | dz2 | da1 | dz1 — so each stage can be checked against autograd.
+ * stamps != NULL: 16 x 32 int64 clock64() phase stamps, one row per CTA (tools/learn_cluster_profile.py).
+ * NULL switches either off. */
+int rloa_naf_ws_set_debug(rloa_naf_ws* ws, float* buffer, int64_t* stamps);
 
 /* The trunk's hidden layer on its own (naf_neural_network.py:77-78):
  *   z2 [B][H] = relu(z1 * scale + shift) @ w2^T + b2,   scale / shift [H] = folded BatchNorm1 coefficients.

@@ -113,7 +113,7 @@ SIGNATURES = {
     'rloa_naf_ws_set_trunk': (C.c_int, [_VP, _I]),
     'rloa_naf_hidden_layer': (C.c_int, [_VP, _fp, _fp, _fp, _fp, _fp, _fp, _I, _VP]),
     'rloa_umma_probe': (C.c_int, [_I, _fp, _fp, _fp, _VP]),
-    'rloa_naf_ws_set_debug': (C.c_int, [_VP, _fp]),
+    'rloa_naf_ws_set_debug': (C.c_int, [_VP, _fp, _fp]),
     'rloa_naf_forward': (C.c_int, [_VP, C.POINTER(NafParams), _fp, _fp, _I, _I, _I, _fp, _fp, _fp, _fp, _VP]),
     'rloa_naf_act': (C.c_int, [_VP, C.POINTER(NafParams), _fp, _I, _U64, _U64, _fp, _F, _fp, _VP]),
     'rloa_naf_num_params': (C.c_int, [_I, _I, _I]),

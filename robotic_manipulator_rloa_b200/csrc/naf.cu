@@ -1181,9 +1181,10 @@ extern "C" int rloa_naf_ws_set_trunk(rloa_naf_ws* ws, int32_t mode) {
     return RLOA_OK;
 }
 
-extern "C" int rloa_naf_ws_set_debug(rloa_naf_ws* ws, float* buffer) {
+extern "C" int rloa_naf_ws_set_debug(rloa_naf_ws* ws, float* buffer, int64_t* stamps) {
     RLOA_REQUIRE(ws != nullptr, "rloa_naf_ws_set_debug: null workspace");
     ws->lc.dbg = buffer;
+    ws->lc.prof = reinterpret_cast<long long*>(stamps);
     return RLOA_OK;
 }
 

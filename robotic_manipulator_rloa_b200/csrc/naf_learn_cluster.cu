@@ -132,6 +132,7 @@ struct LearnClusterArgs {
     int do_adam;
     int off_w1, off_b1, off_bn1w, off_bn1b, off_w2, off_b2, off_bn2w, off_bn2b, off_wmu, off_bmu, off_wv, off_bv, off_wl, off_bl, n_params;
     float* dbg;                             // optional: z1 | z2 | dzh | dz2 | da1 | dz1 as fp32 [1024][256] each (dzh [1024][64])
+    long long* prof;                        // optional: [16 CTAs][32] clock64 phase stamps
 };
 
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -146,7 +147,7 @@ __device__ __forceinline__ float ld_dsmem(const float* local, uint32_t rank) {
     uint32_t ra;
     float v;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
-    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra));
     return v;
 }
 
@@ -169,6 +170,20 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
         if (!done && clock64() - t0 > 4000000000ll) __trap();
     }
 }
+
+// 32 accumulator columns without the wait: several loads can be in flight before one tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // column sums over the 32 rows of a warp: lane l enters with v[i] = (row l, column i), leaves with the sum of column l
 __device__ __forceinline__ float colsum32(float (&v)[32], int lane) {
@@ -195,6 +210,21 @@ __device__ __forceinline__ void store_chunks32(uint8_t* tile, int r, int c0, con
     }
 }
 
+// one element of clip + Adam + soft target update: the arithmetic of adam_soft_update_element (optim.cuh) on operands that
+// are already in registers
+__device__ __forceinline__ void adam_math(float grad_i, const AdamCoef& c, const rloa_naf_hyper& hp, float& m, float& v, float& p,
+                                          float& pt) {
+    const float gq = grad_i * c.clip;
+    m = fmaf(1.f - hp.beta1, gq - m, m);
+    v = fmaf(1.f - hp.beta2, gq * gq - v, v);
+    const float denom = sqrtf(v) / c.bc2s + hp.eps;
+    p = p - (hp.lr / c.bc1) * (m / denom);
+    pt = hp.tau * p + (1.f - hp.tau) * pt;
+}
+
+struct TrueT { static constexpr bool value = true; };
+struct FalseT { static constexpr bool value = false; };
+
 __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(lc::THREADS, 1)
 naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
     using namespace lc;
@@ -207,20 +237,22 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
     const int row0 = rank * ROWS, row = row0 + r;
     const bool valid = row < B;
     const int nrows = min(max(B - row0, 0), ROWS);
+    const bool full = nrows == ROWS;
     const rloa_naf_params& P = g.p[net];
     const uint8_t* image = g.images + (size_t)net * IMAGE_BYTES;
 
     const uint32_t raw = smem_u32(lc_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* sm = lc_smem_raw + (base - raw);
-    float* coef = reinterpret_cast<float*>(sm + COEF);               // [layer][4][256]
+    float* coef = reinterpret_cast<float*>(sm + COEF);               // [layer][sc | shb | rstd | xo][256]
     float* xbuf = reinterpret_cast<float*>(sm + XBUF);               // [2][3][256]
     float* vec = reinterpret_cast<float*>(sm + VEC);
-    float* scratch = reinterpret_cast<float*>(sm + S1);              // [3][4][256] + [3][256] (12 KB + 3 KB)
-    float* bcoef = scratch + 3 * 4 * 256;                            // k1 | cB | cC
+    float* scratch = reinterpret_cast<float*>(sm + S1);              // [2][4][256] partial column sums + [256] + [3][256]
+    float* colaux = scratch + 2 * 4 * 256;                           // per-column operand of the current statistics pass
+    float* bcoef = scratch + 2 * 4 * 256 + 256;                      // k1 | k1 c1 | k1 c2
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + MISC);         // 0: W1 (+vec), 1: W2, 2: Wh, 3: MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-    float* red = reinterpret_cast<float*>(bars + 6);                 // [16] + [1]
+    float* red = reinterpret_cast<float*>(bars + 6);                 // [16] + AdamCoef at [20]
     uint32_t mma_phase = 0;
 
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -261,6 +293,11 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);        // this warp's 32 TMEM lanes
+    long long* prof = g.prof != nullptr ? g.prof + blockIdx.x * 32 : nullptr;
+    auto stamp = [&](int i) {
+        if (prof != nullptr && tid == 0) prof[i] = clock64();
+    };
+    stamp(0);
 
     auto mma_wait = [&]() {
         __syncwarp();
@@ -282,49 +319,51 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
         }
     };
 
-    // ---- train-mode BatchNorm statistics of the pre-activations in TMEM columns tcol.. (+ bias): CTA partial (mean, M2),
-    // cluster exchange over DSMEM, merged batch statistics -> coef[layer] = sc | sh | mean | rstd; running statistics by rank 0
+    // ---- train-mode BatchNorm statistics of the pre-activations acc + bias (acc = TMEM columns tcol..) in ONE pass over
+    // the accumulator: per column sum and sum of squares of (z - K), K = the layer's running mean (a pivot near the batch
+    // mean keeps the one-pass variance as accurate as the two-pass form); CTA partial (mean, M2) -> cluster exchange over
+    // DSMEM -> Chan merge in rank order -> coef[layer] = sc | shb | rstd | xo with the linear bias folded in:
+    //   relu(bn(z)) = max(acc sc + shb, 0),   xhat = acc rstd + xo.   Running statistics are updated by rank 0.
     auto forward_stats = [&](int layer, uint32_t tcol, const float* bias, const float* bn_w, const float* bn_b,
                              float* run_mean, float* run_var, int64_t* batches) {
-        float* part = scratch;                 // [4][256]
-        float* meanc = scratch + 4 * 256;      // [256]
         float* xb = xbuf + (layer & 1) * 3 * 256;
-#pragma unroll 1
-        for (int p = 0; p < 2; p++) {
-            const int c0 = q * 64 + p * 32;
-            uint32_t v[32];
-            tmem_ld32(tlane + tcol + c0, v);
-            float z[32];
-#pragma unroll
-            for (int i = 0; i < 32; i++) z[i] = valid ? __uint_as_float(v[i]) + bias[c0 + i] : 0.f;
-            const float s = colsum32(z, lane);
-            part[wq * 256 + c0 + lane] = s;
-        }
+        if (tid < 256) colaux[tid] = bias[tid] - run_mean[tid];
         __syncthreads();
-        if (tid < 256) {
-            const float tot = (part[tid] + part[256 + tid]) + (part[512 + tid] + part[768 + tid]);
-            meanc[tid] = nrows > 0 ? tot / (float)nrows : 0.f;
-        }
-        __syncthreads();
-        float* part2 = scratch + 5 * 256;      // [4][256]
+        auto body = [&](auto full_t) {
+            constexpr bool kFull = decltype(full_t)::value;
 #pragma unroll 1
-        for (int p = 0; p < 2; p++) {
-            const int c0 = q * 64 + p * 32;
-            uint32_t v[32];
-            tmem_ld32(tlane + tcol + c0, v);
-            float d[32];
+            for (int p = 0; p < 2; p++) {
+                const int c0 = q * 64 + p * 32;
+                uint32_t v[32];
+                tmem_ld32(tlane + tcol + c0, v);
+                float d[32], e[32];
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
-                const float e = valid ? (__uint_as_float(v[i]) + bias[c0 + i]) - meanc[c0 + i] : 0.f;
-                d[i] = e * e;
+                for (int j = 0; j < 8; j++) {
+                    const float4 k4 = *reinterpret_cast<const float4*>(colaux + c0 + 4 * j);
+                    d[4 * j] = __uint_as_float(v[4 * j]) + k4.x;
+                    d[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + k4.y;
+                    d[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + k4.z;
+                    d[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + k4.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    if (!kFull) d[i] = valid ? d[i] : 0.f;
+                    e[i] = d[i] * d[i];
+                }
+                const float s1 = colsum32(d, lane), s2 = colsum32(e, lane);
+                scratch[wq * 256 + c0 + lane] = s1;
+                scratch[1024 + wq * 256 + c0 + lane] = s2;
             }
-            const float s = colsum32(d, lane);
-            part2[wq * 256 + c0 + lane] = s;
-        }
+        };
+        if (full) body(TrueT{}); else body(FalseT{});
         __syncthreads();
         if (tid < 256) {
-            xb[tid] = meanc[tid];
-            xb[256 + tid] = (part2[tid] + part2[256 + tid]) + (part2[512 + tid] + part2[768 + tid]);
+            const float S1 = (scratch[tid] + scratch[256 + tid]) + (scratch[512 + tid] + scratch[768 + tid]);
+            const float S2 = (scratch[1024 + tid] + scratch[1280 + tid]) + (scratch[1536 + tid] + scratch[1792 + tid]);
+            const float n = (float)nrows;
+            const float md = nrows > 0 ? S1 / n : 0.f;
+            xb[tid] = md + run_mean[tid];                          // CTA mean of z
+            xb[256 + tid] = fmaxf(S2 - md * S1, 0.f);              // CTA centred second moment
         }
         cluster_sync_all();
         if (tid < 256) {
@@ -345,11 +384,12 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
             const float var = M2 / (float)B;
             const float rstd = 1.f / sqrtf(var + kBnEps);
             const float sc = bn_w[tid] * rstd;
+            const float sh = fmaf(-mean, sc, bn_b[tid]);
             float* cf = coef + layer * 4 * 256;
             cf[tid] = sc;
-            cf[256 + tid] = fmaf(-mean, sc, bn_b[tid]);
-            cf[512 + tid] = mean;
-            cf[768 + tid] = rstd;
+            cf[256 + tid] = fmaf(bias[tid], sc, sh);
+            cf[512 + tid] = rstd;
+            cf[768 + tid] = (bias[tid] - mean) * rstd;
             if (rank == 0) {
                 const float unbiased = B > 1 ? M2 / (float)(B - 1) : var;
                 run_mean[tid] = fmaf(kBnMomentum, mean - run_mean[tid], run_mean[tid]);
@@ -359,8 +399,28 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
         }
         __syncthreads();
     };
+    auto dbg_rows32 = [&](int section, int width, int c0, const float (&a)[32]) {
+        if (g.dbg != nullptr && net == 1 && valid) {
+            float* d = g.dbg + (size_t)section * 1024 * 256 + (size_t)row * width + c0;
+#pragma unroll
+            for (int i = 0; i < 32; i++) d[i] = a[i];
+        }
+    };
+    auto dbg_preact = [&](int section, uint32_t tcol, const float* bias) {
+        if (g.dbg != nullptr && net == 1) {
+#pragma unroll 1
+            for (int p = 0; p < 2; p++) {
+                uint32_t v[32];
+                float a[32];
+                tmem_ld32(tlane + tcol + q * 64 + p * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; i++) a[i] = __uint_as_float(v[i]) + bias[q * 64 + p * 32 + i];
+                dbg_rows32(section, 256, q * 64 + p * 32, a);
+            }
+        }
+    };
     // relu(bn(z)) of TMEM columns tcol.. -> bf16 K-major tile (rows past the batch are zero)
-    auto activation_to_tile = [&](int layer, uint32_t tcol, const float* bias, uint8_t* tile) {
+    auto activation_to_tile = [&](int layer, uint32_t tcol, uint8_t* tile) {
         const float* cf = coef + layer * 4 * 256;
 #pragma unroll 1
         for (int p = 0; p < 2; p++) {
@@ -369,16 +429,19 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
             tmem_ld32(tlane + tcol + c0, v);
             float a[32];
 #pragma unroll
-            for (int i = 0; i < 32; i++)
-                a[i] = valid ? fmaxf(fmaf(__uint_as_float(v[i]) + bias[c0 + i], cf[c0 + i], cf[256 + c0 + i]), 0.f) : 0.f;
-            store_chunks32(tile, r, c0, a);
-        }
-    };
-    auto dbg_rows32 = [&](int section, int width, int c0, const float (&a)[32]) {
-        if (g.dbg != nullptr && net == 1 && valid) {
-            float* d = g.dbg + (size_t)section * 1024 * 256 + (size_t)row * width + c0;
+            for (int j = 0; j < 8; j++) {
+                const float4 sc = *reinterpret_cast<const float4*>(cf + c0 + 4 * j);
+                const float4 sh = *reinterpret_cast<const float4*>(cf + 256 + c0 + 4 * j);
+                a[4 * j] = fmaxf(fmaf(__uint_as_float(v[4 * j]), sc.x, sh.x), 0.f);
+                a[4 * j + 1] = fmaxf(fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y), 0.f);
+                a[4 * j + 2] = fmaxf(fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z), 0.f);
+                a[4 * j + 3] = fmaxf(fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w), 0.f);
+            }
+            if (!full) {
 #pragma unroll
-            for (int i = 0; i < 32; i++) d[i] = a[i];
+                for (int i = 0; i < 32; i++) a[i] = valid ? a[i] : 0.f;
+            }
+            store_chunks32(tile, r, c0, a);
         }
     };
 
@@ -386,19 +449,11 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
     issue_layer1(base + R1, base + R1 + W1_BYTES, base + R1 + W1_BYTES + 16384, 0);
     mbar_wait_bounded(&bars[0], 0);                       // biases, for every thread
     mma_wait();
+    stamp(1);
     forward_stats(0, 0, vec, P.bn1_w, P.bn1_b, P.bn1_mean, P.bn1_var, P.bn1_batches);
-    if (g.dbg != nullptr && net == 1) {
-#pragma unroll 1
-        for (int p = 0; p < 2; p++) {
-            uint32_t v[32];
-            float a[32];
-            tmem_ld32(tlane + q * 64 + p * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; i++) a[i] = __uint_as_float(v[i]) + vec[q * 64 + p * 32 + i];
-            dbg_rows32(0, 256, q * 64 + p * 32, a);
-        }
-    }
-    activation_to_tile(0, 0, vec, sm + R1);               // a1 over the dead layer-1 operands
+    stamp(2);
+    dbg_preact(0, 0, vec);
+    activation_to_tile(0, 0, sm + R1);                    // a1 over the dead layer-1 operands
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
@@ -418,19 +473,11 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
         mbar_expect_tx(&bars[2], WH_BYTES);
         bulk_g2s(sm + R0, image + OFF_WH, WH_BYTES, &bars[2]);
     }
+    stamp(3);
     forward_stats(1, 256, vec + H, P.bn2_w, P.bn2_b, P.bn2_mean, P.bn2_var, P.bn2_batches);
-    if (g.dbg != nullptr && net == 1) {
-#pragma unroll 1
-        for (int p = 0; p < 2; p++) {
-            uint32_t v[32];
-            float a[32];
-            tmem_ld32(tlane + 256 + q * 64 + p * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; i++) a[i] = __uint_as_float(v[i]) + vec[H + q * 64 + p * 32 + i];
-            dbg_rows32(1, 256, q * 64 + p * 32, a);
-        }
-    }
-    activation_to_tile(1, 256, vec + H, sm + R1);         // a2
+    stamp(4);
+    dbg_preact(1, 256, vec + H);
+    activation_to_tile(1, 256, sm + R1);                  // a2
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
@@ -448,21 +495,27 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
     mma_wait();
 
     // =========================== head ===========================
-    float* hrow = reinterpret_cast<float*>(sm + HEAD_SCRATCH) + r * 65;      // this row's 64 head values (q == 0 threads)
+    stamp(5);
+    // every thread moves 16 of its row's 64 head values TMEM -> shared (zo) and clears the same 16 slots of the gradient row
+    float* zo = reinterpret_cast<float*>(sm + HEAD_SCRATCH) + r * 65;
+    float* dzr = reinterpret_cast<float*>(sm + HEAD_SCRATCH + 33280) + r * 65;
+    float* hpart = reinterpret_cast<float*>(sm + HEAD_SCRATCH + 2 * 33280);     // [128][4] advantage partials, then [8][64]
     const float* bh = vec + 2 * H;
-    if (q == 0) {
-#pragma unroll 1
-        for (int p = 0; p < 2; p++) {
-            uint32_t v[32];
-            tmem_ld32(tlane + p * 32, v);
+    {
+        uint32_t v[32];
+        tmem_ld32(tlane + (q >> 1) * 32, v);               // two threads share a 32-column load, each keeps 16
 #pragma unroll
-            for (int i = 0; i < 32; i++) hrow[p * 32 + i] = __uint_as_float(v[i]) + bh[p * 32 + i];
+        for (int i = 0; i < 16; i++) {
+            const int o = q * 16 + i;
+            zo[o] = __uint_as_float((q & 1) ? v[16 + i] : v[i]) + bh[o];
+            dzr[o] = 0.f;
         }
     }
+    __syncthreads();
     if (net == 0) {
         // ---- target network: y = r + gamma V'(s') for this CTA's rows, then hand over to the main CTA of the same rank
         if (q == 0 && valid) {
-            float vv = hrow[A];
+            float vv = zo[A];
             if (g.hp.use_done_mask && g.dones != nullptr) vv *= (1.f - g.dones[row]);
             g.y[row] = fmaf(g.hp.gamma, vv, g.rewards[row]);
         }
@@ -473,7 +526,24 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(g.yflag + rank), "r"(one) : "memory");
         }
     } else {
-        // ---- main network: TD error, loss, gradients of the head pre-activations ----
+        // ---- main network: TD error, loss, gradients of the head pre-activations; thread (r, q) owns actions k = q, q + 4, q + 8
+        float mu_[3], t_[3], P_[3], df_[3];
+        float advp = 0.f;
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const int k = q + 4 * u;
+            mu_[u] = t_[u] = P_[u] = df_[u] = 0.f;
+            if (k < A && valid) {
+                mu_[u] = tanhf(zo[k]);
+                t_[u] = tanhf(zo[A + 1 + (k * (k + 3)) / 2]);
+                P_[u] = expf(2.f * t_[u]);
+                float act = g.actions[(size_t)row * A + k];
+                if (g.hp.trunc_action) act = truncf(act);
+                df_[u] = act - mu_[u];
+                advp = fmaf(-0.5f * P_[u] * df_[u], df_[u], advp);
+            }
+        }
+        hpart[r * 4 + q] = advp;
         if (tid == 0) {
             unsigned f = 0u;
             const long long t0 = clock64();
@@ -483,81 +553,72 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
             } while (f == 0u);
         }
         __syncthreads();
+        stamp(6);
         float err2 = 0.f;
-        if (q == 0) {
-            float dzh[64];
-#pragma unroll
-            for (int i = 0; i < 64; i++) dzh[i] = 0.f;
-            if (valid) {
-                const float yrow = __ldcg(g.y + row);
-                const float vval = hrow[A];
-                float adv = 0.f;
-                float gmu[10], gl[10];
-                for (int k = 0; k < A; k++) {
-                    const float mu = tanhf(hrow[k]);
-                    const float t = tanhf(hrow[A + 1 + (k * (k + 3)) / 2]);
-                    const float Pk = expf(2.f * t);
-                    float u = g.actions[(size_t)row * A + k];
-                    if (g.hp.trunc_action) u = truncf(u);
-                    const float diff = u - mu;
-                    adv = fmaf(-0.5f * Pk * diff, diff, adv);
-                    gmu[k] = Pk * diff * (1.f - mu * mu);
-                    gl[k] = -Pk * diff * diff * (1.f - t * t);
-                }
-                const float err = (vval + adv) - yrow;
+        if (valid) {
+            const float adv = (hpart[r * 4] + hpart[r * 4 + 1]) + (hpart[r * 4 + 2] + hpart[r * 4 + 3]);
+            const float err = (zo[A] + adv) - __ldcg(g.y + row);
+            const float dq = 2.f * err / (float)B;                 // MSE over the batch (naf_algorithm.py:204)
+            if (q == 0) {
                 err2 = err * err;
-                const float dq = 2.f * err / (float)B;             // MSE over the batch (naf_algorithm.py:204)
-                // static indexing of dzh: walk the outputs once
+                dzr[A] = dq;
+            }
 #pragma unroll
-                for (int o = 0; o < 64; o++) {
-                    float gv = 0.f;
-                    if (o < A) gv = dq * gmu[o < 10 ? o : 0];
-                    else if (o == A) gv = dq;
-                    else {
-                        const int e = o - A - 1;
-                        for (int k = 0; k < A; k++)
-                            if ((k * (k + 3)) / 2 == e) gv = dq * gl[k];
-                    }
-                    dzh[o] = o < NH ? gv : 0.f;
+            for (int u = 0; u < 3; u++) {
+                const int k = q + 4 * u;
+                if (k < A) {
+                    dzr[k] = dq * P_[u] * df_[u] * (1.f - mu_[u] * mu_[u]);
+                    dzr[A + 1 + (k * (k + 3)) / 2] = dq * (-P_[u] * df_[u] * df_[u]) * (1.f - t_[u] * t_[u]);
                 }
-            }
-#pragma unroll
-            for (int i = 0; i < 64; i++) hrow[i] = dzh[i];
-            // bf16 tile [128 rows][64 columns] (one k-block) for dWh^T and da2
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const float x[8] = {dzh[8 * c], dzh[8 * c + 1], dzh[8 * c + 2], dzh[8 * c + 3],
-                                    dzh[8 * c + 4], dzh[8 * c + 5], dzh[8 * c + 6], dzh[8 * c + 7]};
-                *reinterpret_cast<uint4*>(sm + S1 + sw128_chunk_offset(r, c)) = pack8_bf16(x);
-            }
-            if (g.dbg != nullptr && valid) {
-                float* d = g.dbg + (size_t)2 * 1024 * 256 + (size_t)row * 64;
-#pragma unroll
-                for (int i = 0; i < 64; i++) d[i] = dzh[i];
             }
         }
-        // loss partial of this CTA (fixed order: lanes, then warps 0-3)
+        __syncthreads();
+        {   // bf16 tile [128 rows][64 columns] (one k-block) for dWh^T and da2: 16 columns = 2 chunks per thread
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                float x[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) x[i] = dzr[q * 16 + c * 8 + i];
+                *reinterpret_cast<uint4*>(sm + S1 + sw128_chunk_offset(r, q * 2 + c)) = pack8_bf16(x);
+            }
+            if (g.dbg != nullptr && valid) {
+                float* d = g.dbg + (size_t)2 * 1024 * 256 + (size_t)row * 64 + q * 16;
+#pragma unroll
+                for (int i = 0; i < 16; i++) d[i] = dzr[q * 16 + i];
+            }
+        }
+        // loss partial of this CTA (fixed order: lanes, then warps 0-3); head bias gradients: column sums of dzh over the rows
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, off);
         if (q == 0 && lane == 0) red[wq] = err2;
+        {
+            const int o = tid & 63, part = tid >> 6;                // 8 parts of 16 rows
+            const float* ds = reinterpret_cast<const float*>(sm + HEAD_SCRATCH + 33280);
+            float sacc = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 16; rr++) sacc += ds[(part * 16 + rr) * 65 + o];
+            __syncthreads();                                        // the advantage partials in hpart are dead
+            hpart[part * 64 + o] = sacc;
+        }
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
             g.part_loss[rank] = (red[0] + red[1]) + (red[2] + red[3]);
             g.yflag[rank] = 0u;                                  // consumed: zero at rest
         }
-        if (tid < 64) {                                          // head bias gradients: column sums of dzh over this CTA's rows
-            const float* hs = reinterpret_cast<const float*>(sm + HEAD_SCRATCH);
-            float s = 0.f;
-            for (int rr = 0; rr < ROWS; rr++) s += hs[rr * 65 + tid];
-            g.part_hb[rank * 64 + tid] = s;
+        if (tid < 64) {
+            float sacc = 0.f;
+#pragma unroll
+            for (int part = 0; part < 8; part++) sacc += hpart[part * 64 + tid];
+            g.part_hb[rank * 64 + tid] = sacc;
         }
-        fence_proxy_async();     // the generic reads of the head scratch precede the TMA write that reuses its slot
+        fence_proxy_async();     // the generic accesses of the head scratch precede the TMA write that reuses its slot
         fence_before_sync();
         __syncthreads();
         fence_after_sync();
 
         // =========================== backward ===========================
+        stamp(7);
         if (tid == 0) {          // dWh^T [256 f][64 o] = a2^T dzh: both tiles MN-major, contraction over the 128 rows
             constexpr uint32_t idesc = idesc_bf16_f32(128, NHP) | kIdescAMajorMN | kIdescBMajorMN;
 #pragma unroll
@@ -583,6 +644,7 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
         fence_before_sync();
         __syncthreads();
         fence_after_sync();
+        stamp(8);
         if (tid == 0) {          // da2 [128][256] = dzh Wh: B = the head image read MN-major (contraction over its 64 rows)
             constexpr uint32_t idesc = idesc_bf16_f32(128, H) | kIdescBMajorMN;
 #pragma unroll
@@ -596,95 +658,120 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
             bulk_g2s(sm + R0, image + OFF_W2, W2_BYTES, &bars[1]);
         }
 
-        // ReLU + BatchNorm backward of one layer: da in TMEM columns dcol.., z in zcol.. (+ bias).  Pass 1: column sums of
-        // g = da [bn(z) > 0], g xhat and (z - mean) over the whole batch through the cluster; pass 2 (by the caller):
-        // dz = k1 g - cB - cC (z - mean).  gamma / beta / linear-bias gradients are totals: rank 0 writes them.
-        auto backward_stats = [&](int layer, uint32_t dcol, uint32_t zcol, const float* bias, const float* bn_w, int xslot,
+        // ReLU + BatchNorm backward of one layer in ONE pass over the two accumulators (da in TMEM columns dcol.., the
+        // layer's pre-activations in zcol..): column sums of g = da [bn(z) > 0] and g xhat over the whole batch through the
+        // cluster, then dz = k1 (g - c1 - c2 xhat) (second pass, by the caller).  gamma / beta gradients are totals: rank 0
+        // writes them; the linear-bias gradient under a train-mode BatchNorm is the rounding residue k1 (sum g - B c1).
+        auto backward_stats = [&](int layer, uint32_t dcol, uint32_t zcol, const float* bn_w, int xslot,
                                   float* d_w, float* d_b, float* d_lin) {
             const float* cf = coef + layer * 4 * 256;
             float* xb = xbuf + xslot * 3 * 256;
+            auto body = [&](auto full_t) {
+                constexpr bool kFull = decltype(full_t)::value;
 #pragma unroll 1
-            for (int p = 0; p < 2; p++) {
-                const int c0 = q * 64 + p * 32;
-                // one quantity at a time (the accumulators are re-read from TMEM: 16 TB/s, cheaper than 96 live registers)
-#pragma unroll 1
-                for (int k = 0; k < 3; k++) {
+                for (int p = 0; p < 2; p++) {
+                    const int c0 = q * 64 + p * 32;
                     uint32_t vd[32], vz[32];
-                    tmem_ld32(tlane + zcol + c0, vz);
-                    if (k < 2) tmem_ld32(tlane + dcol + c0, vd);
-                    float a[32];
+                    tmem_ld32_nowait(tlane + zcol + c0, vz);
+                    tmem_ld32_nowait(tlane + dcol + c0, vd);
+                    tmem_ld_wait();
+                    float a0[32], a1[32];
 #pragma unroll
-                    for (int i = 0; i < 32; i++) {
-                        const float z = __uint_as_float(vz[i]) + bias[c0 + i];
-                        const float zc = valid ? z - cf[512 + c0 + i] : 0.f;
-                        if (k == 2) {
-                            a[i] = zc;
-                        } else {
-                            const float gg = (valid && fmaf(z, cf[c0 + i], cf[256 + c0 + i]) > 0.f) ? __uint_as_float(vd[i]) : 0.f;
-                            a[i] = k == 0 ? gg : gg * (zc * cf[768 + c0 + i]);
+                    for (int j = 0; j < 8; j++) {
+                        const float4 sc = *reinterpret_cast<const float4*>(cf + c0 + 4 * j);
+                        const float4 sh = *reinterpret_cast<const float4*>(cf + 256 + c0 + 4 * j);
+                        const float4 rs = *reinterpret_cast<const float4*>(cf + 512 + c0 + 4 * j);
+                        const float4 xo = *reinterpret_cast<const float4*>(cf + 768 + c0 + 4 * j);
+                        const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+                        const float rsv[4] = {rs.x, rs.y, rs.z, rs.w}, xov[4] = {xo.x, xo.y, xo.z, xo.w};
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int i = 4 * j + u;
+                            const float acc = __uint_as_float(vz[i]);
+                            bool on = fmaf(acc, scv[u], shv[u]) > 0.f;
+                            if (!kFull) on = on && valid;
+                            const float gg = on ? __uint_as_float(vd[i]) : 0.f;
+                            a0[i] = gg;
+                            a1[i] = gg * fmaf(acc, rsv[u], xov[u]);
                         }
                     }
-                    const float sres = colsum32(a, lane);
-                    scratch[k * 1024 + wq * 256 + c0 + lane] = sres;
+                    const float s0 = colsum32(a0, lane), s1 = colsum32(a1, lane);
+                    scratch[wq * 256 + c0 + lane] = s0;
+                    scratch[1024 + wq * 256 + c0 + lane] = s1;
                 }
-            }
+            };
+            if (full) body(TrueT{}); else body(FalseT{});
             __syncthreads();
             if (tid < 256) {
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    const float* pp = scratch + k * 1024;
-                    xb[k * 256 + tid] = (pp[tid] + pp[256 + tid]) + (pp[512 + tid] + pp[768 + tid]);
-                }
+                xb[tid] = (scratch[tid] + scratch[256 + tid]) + (scratch[512 + tid] + scratch[768 + tid]);
+                xb[256 + tid] = (scratch[1024 + tid] + scratch[1280 + tid]) + (scratch[1536 + tid] + scratch[1792 + tid]);
             }
             cluster_sync_all();
             if (tid < 256) {
-                float t[3] = {0.f, 0.f, 0.f};
+                float p0[CL], p1[CL];
 #pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    float pv[CL];
+                for (int c = 0; c < CL; c++) { p0[c] = ld_dsmem(xb + tid, c); p1[c] = ld_dsmem(xb + 256 + tid, c); }
+                float tg = 0.f, tgx = 0.f;
 #pragma unroll
-                    for (int c = 0; c < CL; c++) pv[c] = ld_dsmem(xb + k * 256 + tid, c);
-#pragma unroll
-                    for (int c = 0; c < CL; c++) t[k] += pv[c];
-                }
-                const float rs = cf[768 + tid];
-                const float k1 = bn_w[tid] * rs, c1 = t[0] / (float)B, c2 = t[1] / (float)B;
+                for (int c = 0; c < CL; c++) { tg += p0[c]; tgx += p1[c]; }
+                const float k1 = bn_w[tid] * cf[512 + tid], c1 = tg / (float)B, c2 = tgx / (float)B;
                 bcoef[tid] = k1;
                 bcoef[256 + tid] = k1 * c1;
-                bcoef[512 + tid] = k1 * c2 * rs;
+                bcoef[512 + tid] = k1 * c2;
                 if (rank == 0) {
-                    d_w[tid] = t[1];
-                    d_b[tid] = t[0];
-                    d_lin[tid] = k1 * (t[0] - (float)B * c1) - k1 * c2 * rs * t[2];
+                    d_w[tid] = tgx;
+                    d_b[tid] = tg;
+                    d_lin[tid] = k1 * (tg - (float)B * c1);
                 }
             }
             __syncthreads();
         };
-
-        backward_stats(1, 0, 256, vec + H, P.bn2_w, 0, g.grad + g.off_bn2w, g.grad + g.off_bn2b, g.grad + g.off_b2);
-        {   // dz2 -> bf16 tile in R1 (a2 is dead: dWh^T finished)
-            const float* cf = coef + 1 * 4 * 256;
-#pragma unroll 1
-            for (int p = 0; p < 2; p++) {
-                const int c0 = q * 64 + p * 32;
-                uint32_t vd[32], vz[32];
-                tmem_ld32(tlane + c0, vd);
-                tmem_ld32(tlane + 256 + c0, vz);
-                float a[32];
+        // dz = k1 g - k1 c1 - k1 c2 xhat of 32 columns (accumulators vd = da, vz = the layer's pre-activations)
+        auto dz32 = [&](int layer, int c0, const uint32_t (&vd)[32], const uint32_t (&vz)[32], float (&d)[32]) {
+            const float* cf = coef + layer * 4 * 256;
 #pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    const float z = __uint_as_float(vz[i]) + vec[H + c0 + i];
-                    const float gg = fmaf(z, cf[c0 + i], cf[256 + c0 + i]) > 0.f ? __uint_as_float(vd[i]) : 0.f;
-                    a[i] = valid ? fmaf(bcoef[c0 + i], gg, -bcoef[256 + c0 + i]) - bcoef[512 + c0 + i] * (z - cf[512 + c0 + i]) : 0.f;
+            for (int j = 0; j < 8; j++) {
+                const float4 sc = *reinterpret_cast<const float4*>(cf + c0 + 4 * j);
+                const float4 sh = *reinterpret_cast<const float4*>(cf + 256 + c0 + 4 * j);
+                const float4 rs = *reinterpret_cast<const float4*>(cf + 512 + c0 + 4 * j);
+                const float4 xo = *reinterpret_cast<const float4*>(cf + 768 + c0 + 4 * j);
+                const float4 k1 = *reinterpret_cast<const float4*>(bcoef + c0 + 4 * j);
+                const float4 kc1 = *reinterpret_cast<const float4*>(bcoef + 256 + c0 + 4 * j);
+                const float4 kc2 = *reinterpret_cast<const float4*>(bcoef + 512 + c0 + 4 * j);
+                const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+                const float rsv[4] = {rs.x, rs.y, rs.z, rs.w}, xov[4] = {xo.x, xo.y, xo.z, xo.w};
+                const float k1v[4] = {k1.x, k1.y, k1.z, k1.w}, c1v[4] = {kc1.x, kc1.y, kc1.z, kc1.w}, c2v[4] = {kc2.x, kc2.y, kc2.z, kc2.w};
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = 4 * j + u;
+                    const float acc = __uint_as_float(vz[i]);
+                    const float gg = fmaf(acc, scv[u], shv[u]) > 0.f ? __uint_as_float(vd[i]) : 0.f;
+                    const float dzv = fmaf(-c2v[u], fmaf(acc, rsv[u], xov[u]), fmaf(k1v[u], gg, -c1v[u]));
+                    d[i] = valid ? dzv : 0.f;
                 }
-                store_chunks32(sm + R1, r, c0, a);
-                dbg_rows32(3, 256, c0, a);
             }
+        };
+
+        stamp(9);
+        backward_stats(1, 0, 256, P.bn2_w, 0, g.grad + g.off_bn2w, g.grad + g.off_bn2b, g.grad + g.off_b2);
+        stamp(10);
+#pragma unroll 1
+        for (int p = 0; p < 2; p++) {          // dz2 -> bf16 tile in R1 (a2 is dead: dWh^T finished)
+            const int c0 = q * 64 + p * 32;
+            uint32_t vd[32], vz[32];
+            tmem_ld32_nowait(tlane + c0, vd);
+            tmem_ld32_nowait(tlane + 256 + c0, vz);
+            tmem_ld_wait();
+            float d[32];
+            dz32(1, c0, vd, vz, d);
+            store_chunks32(sm + R1, r, c0, d);
+            dbg_rows32(3, 256, c0, d);
         }
         fence_proxy_async();
         fence_before_sync();
         __syncthreads();
         fence_after_sync();
+        stamp(11);
         if (tid == 0) {          // da1 [128][256] = dz2 W2: B = the forward W2 image read MN-major -> TMEM columns 256-511
             mbar_wait_bounded(&bars[1], 1);
             fence_after_sync();
@@ -705,43 +792,45 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
         fence_before_sync();
         __syncthreads();
         fence_after_sync();
+        stamp(12);
         issue_layer1(base + R0, base + R0 + W1_BYTES, base + R0 + W1_BYTES + 16384, 1);      // z1 again -> TMEM columns 0-255
         mma_wait();
-        backward_stats(0, 256, 0, vec, P.bn1_w, 1, g.grad + g.off_bn1w, g.grad + g.off_bn1b, g.grad + g.off_b1);
-        {   // dz1 -> R0 + 64 KB, a1 -> R0 (the layer-1 operands there are dead: z1 is in TMEM)
-            const float* cf = coef;
+        stamp(13);
+        backward_stats(0, 256, 0, P.bn1_w, 1, g.grad + g.off_bn1w, g.grad + g.off_bn1b, g.grad + g.off_b1);
+        stamp(14);
 #pragma unroll 1
-            for (int p = 0; p < 2; p++) {
-                const int c0 = q * 64 + p * 32;
-                {
-                    uint32_t vd[32], vz[32];
-                    tmem_ld32(tlane + 256 + c0, vd);
-                    tmem_ld32(tlane + c0, vz);
-                    float d[32];
+        for (int p = 0; p < 2; p++) {          // dz1 -> R0 + 64 KB, a1 -> R0 (the layer-1 operands there are dead: z1 is in TMEM)
+            const int c0 = q * 64 + p * 32;
+            uint32_t vd[32], vz[32];
+            tmem_ld32_nowait(tlane + 256 + c0, vd);
+            tmem_ld32_nowait(tlane + c0, vz);
+            tmem_ld_wait();
+            {
+                float d[32];
+                dz32(0, c0, vd, vz, d);
+                store_chunks32(sm + R0 + 65536, r, c0, d);
+                dbg_rows32(5, 256, c0, d);
+                if (g.dbg != nullptr) {
+                    float da[32];
 #pragma unroll
-                    for (int i = 0; i < 32; i++) {
-                        const float z = __uint_as_float(vz[i]) + vec[c0 + i];
-                        const float gg = fmaf(z, cf[c0 + i], cf[256 + c0 + i]) > 0.f ? __uint_as_float(vd[i]) : 0.f;
-                        d[i] = valid ? fmaf(bcoef[c0 + i], gg, -bcoef[256 + c0 + i]) - bcoef[512 + c0 + i] * (z - cf[512 + c0 + i]) : 0.f;
-                    }
-                    store_chunks32(sm + R0 + 65536, r, c0, d);
-                    dbg_rows32(5, 256, c0, d);
-                    if (g.dbg != nullptr) {
-                        float da[32];
-#pragma unroll
-                        for (int i = 0; i < 32; i++) da[i] = __uint_as_float(vd[i]);
-                        dbg_rows32(4, 256, c0, da);
-                    }
+                    for (int i = 0; i < 32; i++) da[i] = __uint_as_float(vd[i]);
+                    dbg_rows32(4, 256, c0, da);
                 }
-                {
-                    uint32_t vz[32];
-                    tmem_ld32(tlane + c0, vz);
-                    float a[32];
+            }
+            {
+                float a[32];
 #pragma unroll
-                    for (int i = 0; i < 32; i++)
-                        a[i] = valid ? fmaxf(fmaf(__uint_as_float(vz[i]) + vec[c0 + i], cf[c0 + i], cf[256 + c0 + i]), 0.f) : 0.f;
-                    store_chunks32(sm + R0, r, c0, a);
+                for (int j = 0; j < 8; j++) {
+                    const float4 sc = *reinterpret_cast<const float4*>(coef + c0 + 4 * j);
+                    const float4 sh = *reinterpret_cast<const float4*>(coef + 256 + c0 + 4 * j);
+                    a[4 * j] = fmaxf(fmaf(__uint_as_float(vz[4 * j]), sc.x, sh.x), 0.f);
+                    a[4 * j + 1] = fmaxf(fmaf(__uint_as_float(vz[4 * j + 1]), sc.y, sh.y), 0.f);
+                    a[4 * j + 2] = fmaxf(fmaf(__uint_as_float(vz[4 * j + 2]), sc.z, sh.z), 0.f);
+                    a[4 * j + 3] = fmaxf(fmaf(__uint_as_float(vz[4 * j + 3]), sc.w, sh.w), 0.f);
                 }
+#pragma unroll
+                for (int i = 0; i < 32; i++) a[i] = valid ? a[i] : 0.f;
+                store_chunks32(sm + R0, r, c0, a);
             }
         }
         __syncthreads();         // the backward coefficients in S1 are dead: the observation tile takes their place
@@ -759,37 +848,8 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
         fence_before_sync();
         __syncthreads();
         fence_after_sync();
-        if (tid == 0) {          // dW2 [256 n][256 k] = dz2^T a1 -> all 512 TMEM columns (n half h in columns 256 h ..)
-            constexpr uint32_t idesc = idesc_bf16_f32(128, H) | kIdescAMajorMN | kIdescBMajorMN;
-#pragma unroll
-            for (int half = 0; half < 2; half++)
-#pragma unroll
-                for (int k = 0; k < 8; k++)
-                    mma_bf16(tmem + half * 256, umma_desc_sw128_mn(base + R1 + half * 2 * A_BLK + k * 2048, A_BLK),
-                             umma_desc_sw128_mn(base + R0 + k * 2048, A_BLK), idesc, k > 0);
-            mma_commit(&bars[3]);
-        }
-        mma_wait();
-        {   // partial dW2 of this CTA: row n = 128 half + r, columns 64 q ..
-            float* dst = g.part_w2 + (size_t)rank * H * H;
-#pragma unroll 1
-            for (int half = 0; half < 2; half++)
-#pragma unroll 1
-                for (int p = 0; p < 2; p++) {
-                    const int c0 = q * 64 + p * 32;
-                    uint32_t v[32];
-                    tmem_ld32(tlane + half * 256 + c0, v);
-                    float4* o = reinterpret_cast<float4*>(dst + (size_t)(half * 128 + r) * H + c0);
-#pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                           __uint_as_float(v[4 * j + 3]));
-                }
-        }
-        fence_before_sync();
-        __syncthreads();
-        fence_after_sync();
-        if (tid == 0) {          // dW1 [256 h][hi 32 | lo 32] = dz1^T [x_hi | x_lo]
+        stamp(15);
+        if (tid == 0) {          // dW1 [256 h][hi 32 | lo 32] = dz1^T [x_hi | x_lo] -> TMEM columns 0-127
             constexpr uint32_t idesc = idesc_bf16_f32(128, 64) | kIdescAMajorMN | kIdescBMajorMN;
 #pragma unroll
             for (int half = 0; half < 2; half++)
@@ -803,16 +863,64 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
         if (q < 2) {
             float* dst = g.part_w1 + (size_t)rank * H * S + (size_t)(q * 128 + r) * S;
             uint32_t v0[32], v1[32];
-            tmem_ld32(tlane + q * 64, v0);
-            tmem_ld32(tlane + q * 64 + 32, v1);
+            tmem_ld32_nowait(tlane + q * 64, v0);
+            tmem_ld32_nowait(tlane + q * 64 + 32, v1);
+            tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 24; i++)
                 if (i < S) dst[i] = __uint_as_float(v0[i]) + __uint_as_float(v1[i]);
         }
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+        stamp(16);
+        if (tid == 0) {          // dW2 [256 n][256 k] = dz2^T a1 -> all 512 TMEM columns (n half h in columns 256 h ..)
+            constexpr uint32_t idesc = idesc_bf16_f32(128, H) | kIdescAMajorMN | kIdescBMajorMN;
+#pragma unroll
+            for (int half = 0; half < 2; half++)
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    mma_bf16(tmem + half * 256, umma_desc_sw128_mn(base + R1 + half * 2 * A_BLK + k * 2048, A_BLK),
+                             umma_desc_sw128_mn(base + R0 + k * 2048, A_BLK), idesc, k > 0);
+            mma_commit(&bars[3]);
+        }
+        mma_wait();
+        {   // partial dW2 of this CTA, staged through shared memory (every operand tile is dead) so that the global stores
+            // are 512 contiguous bytes per warp instruction: fp32 [128 rows][260] per half (pitch 260: conflict-free STS.128)
+            float* stg = reinterpret_cast<float*>(sm + R1);
+            float* dst = g.part_w2 + (size_t)rank * H * H;
+#pragma unroll 1
+            for (int half = 0; half < 2; half++) {
+#pragma unroll 1
+                for (int p = 0; p < 2; p++) {
+                    const int c0 = q * 64 + p * 32;
+                    uint32_t v[32];
+                    tmem_ld32(tlane + half * 256 + c0, v);
+                    float4* o = reinterpret_cast<float4*>(stg + r * 260 + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                           __uint_as_float(v[4 * j + 3]));
+                }
+                __syncthreads();
+#pragma unroll
+                for (int rr = 0; rr < 8; rr++) {           // warp w stores rows w, w + 16, ...: 2 x 512 B per row
+                    const int srow = warp + 16 * rr;
+                    const float4 lo = *reinterpret_cast<const float4*>(stg + srow * 260 + lane * 4);
+                    const float4 hi = *reinterpret_cast<const float4*>(stg + srow * 260 + 128 + lane * 4);
+                    float4* o = reinterpret_cast<float4*>(dst + (size_t)(half * 128 + srow) * H);
+                    o[lane] = lo;
+                    o[32 + lane] = hi;
+                }
+                __syncthreads();
+            }
+        }
 
         // =========================== optimiser tail ===========================
+        stamp(17);
         __threadfence();
         cluster_sync_all();                                    // every CTA's partials (and rank 0's totals) are visible
+        stamp(18);
         const int n = g.n_params;
         const float gs = g.hp.grad_scale;
         // (a) this CTA's eighth of dW2, float4; (b) its share of everything else, scalar
@@ -821,62 +929,107 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
         {
             const float4* pw = reinterpret_cast<const float4*>(g.part_w2);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int i4 = rank * 2048 + j * 512 + tid;                  // 16384 float4 in W2, 2048 per CTA
-                float4 pv[CL];
+            for (int jj = 0; jj < 2; jj++) {                   // two rounds of 16 loads in flight
+                float4 pv[2][CL];
 #pragma unroll
-                for (int c = 0; c < CL; c++) pv[c] = __ldcg(pw + (size_t)c * (H * H / 4) + i4);
-                float4 s4 = pv[0];
+                for (int u = 0; u < 2; u++)
 #pragma unroll
-                for (int c = 1; c < CL; c++) { s4.x += pv[c].x; s4.y += pv[c].y; s4.z += pv[c].z; s4.w += pv[c].w; }
-                gw[j] = s4;
-                reinterpret_cast<float4*>(g.grad + g.off_w2)[i4] = s4;
-                const float x0 = s4.x * gs, x1 = s4.y * gs, x2 = s4.z * gs, x3 = s4.w * gs;
-                sq = fmaf(x0, x0, sq); sq = fmaf(x1, x1, sq); sq = fmaf(x2, x2, sq); sq = fmaf(x3, x3, sq);
+                    for (int c = 0; c < CL; c++) pv[u][c] = __ldcg(pw + (size_t)c * (H * H / 4) + rank * 2048 + (2 * jj + u) * 512 + tid);
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    float4 s4 = pv[u][0];
+#pragma unroll
+                    for (int c = 1; c < CL; c++) { s4.x += pv[u][c].x; s4.y += pv[u][c].y; s4.z += pv[u][c].z; s4.w += pv[u][c].w; }
+                    gw[2 * jj + u] = s4;
+                    reinterpret_cast<float4*>(g.grad + g.off_w2)[rank * 2048 + (2 * jj + u) * 512 + tid] = s4;
+                    const float x0 = s4.x * gs, x1 = s4.y * gs, x2 = s4.z * gs, x3 = s4.w * gs;
+                    sq = fmaf(x0, x0, sq); sq = fmaf(x1, x1, sq); sq = fmaf(x2, x2, sq); sq = fmaf(x3, x3, sq);
+                }
             }
         }
         // the remaining n - 65536 elements, compacted (W2 skipped): element e of that list, CTA c takes e in [c m, (c+1) m)
         const int rest = n - H * H, per = (rest + CL - 1) / CL;
-        float gr[8];
-        int gi[8];
+        constexpr int kSlots = 6;                              // per <= 2727 (A = 9, S = 24) < 6 x 512
+        float gr[kSlots];
+        int gi[kSlots];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int e = rank * per + j * THREADS + tid;
-            gi[j] = -1;
-            gr[j] = 0.f;
-            if (j * THREADS + tid < per && e < rest) {
-                const int i = e < g.off_w2 ? e : e + H * H;                   // flat index
-                float s = 0.f;
-                if (i < g.off_b1) {                                           // dW1: 8 partials
-                    float pv[CL];
+        for (int grp = 0; grp < 2; grp++) {                    // three elements x 8 partials in flight per round
+            float pvs[3][CL];
 #pragma unroll
-                    for (int c = 0; c < CL; c++) pv[c] = __ldcg(g.part_w1 + (size_t)c * H * S + i);
+            for (int u = 0; u < 3; u++) {
+                const int j = 3 * grp + u;
+                const int e = rank * per + j * THREADS + tid;
+                gi[j] = -1;
 #pragma unroll
-                    for (int c = 0; c < CL; c++) s += pv[c];
-                } else if (i < g.off_wmu) {                                   // b1, bn1, b2, bn2: totals left by rank 0
-                    s = __ldcg(g.grad + i);
-                } else {                                                      // heads
-                    int o = -1, f = 0;
-                    if (i < g.off_bmu) { o = (i - g.off_wmu) / H; f = (i - g.off_wmu) - o * H; }
-                    else if (i < g.off_wv) { o = i - g.off_bmu; f = -1; }
-                    else if (i < g.off_bv) { o = A; f = i - g.off_wv; }
-                    else if (i < g.off_wl) { o = A; f = -1; }
-                    else if (i < g.off_bl) { const int oo = (i - g.off_wl) / H; o = A + 1 + oo; f = (i - g.off_wl) - oo * H; }
-                    else { o = A + 1 + (i - g.off_bl); f = -1; }
-                    float pv[CL];
+                for (int c = 0; c < CL; c++) pvs[u][c] = 0.f;
+                if (j * THREADS + tid < per && e < rest) {
+                    const int i = e < g.off_w2 ? e : e + H * H;               // flat index
+                    gi[j] = i;
+                    if (i < g.off_b1) {                                       // dW1: 8 partials
 #pragma unroll
-                    for (int c = 0; c < CL; c++)
-                        pv[c] = f >= 0 ? __ldcg(g.part_wh + (size_t)c * NH * H + (size_t)o * H + f) : __ldcg(g.part_hb + c * 64 + o);
+                        for (int c = 0; c < CL; c++) pvs[u][c] = __ldcg(g.part_w1 + (size_t)c * H * S + i);
+                    } else if (i < g.off_wmu) {                               // b1, bn1, b2, bn2: totals left by rank 0
+                        pvs[u][0] = __ldcg(g.grad + i);
+                    } else {                                                  // heads
+                        int o = -1, f = 0;
+                        if (i < g.off_bmu) { o = (i - g.off_wmu) / H; f = (i - g.off_wmu) - o * H; }
+                        else if (i < g.off_wv) { o = i - g.off_bmu; f = -1; }
+                        else if (i < g.off_bv) { o = A; f = i - g.off_wv; }
+                        else if (i < g.off_wl) { o = A; f = -1; }
+                        else if (i < g.off_bl) { const int oo = (i - g.off_wl) / H; o = A + 1 + oo; f = (i - g.off_wl) - oo * H; }
+                        else { o = A + 1 + (i - g.off_bl); f = -1; }
 #pragma unroll
-                    for (int c = 0; c < CL; c++) s += pv[c];
+                        for (int c = 0; c < CL; c++)
+                            pvs[u][c] = f >= 0 ? __ldcg(g.part_wh + (size_t)c * NH * H + (size_t)o * H + f) : __ldcg(g.part_hb + c * 64 + o);
+                    }
                 }
-                gi[j] = i;
-                gr[j] = s;
-                g.grad[i] = s;
-                const float x = s * gs;
-                sq = fmaf(x, x, sq);
+            }
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                const int j = 3 * grp + u;
+                float ssum = 0.f;
+#pragma unroll
+                for (int c = 0; c < CL; c++) ssum += pvs[u][c];
+                gr[j] = ssum;
+                if (gi[j] >= 0) {
+                    g.grad[gi[j]] = ssum;
+                    const float x = ssum * gs;
+                    sq = fmaf(x, x, sq);
+                }
             }
         }
+        // operands of the optimiser (m, v, theta, theta_target) for this CTA's elements: requested now, they arrive while the
+        // squared-norm partials cross the cluster
+        float4 am[4], av[4], ap[4], at[4];
+        float rm[kSlots], rv[kSlots], rp[kSlots], rt[kSlots];
+        int rtn[kSlots], rj[kSlots];
+        if (g.do_adam) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int i4 = rank * 2048 + j * 512 + tid;
+                am[j] = reinterpret_cast<const float4*>(g.m + g.off_w2)[i4];
+                av[j] = reinterpret_cast<const float4*>(g.v + g.off_w2)[i4];
+                ap[j] = reinterpret_cast<const float4*>(g.pt.main[4])[i4];
+                at[j] = reinterpret_cast<const float4*>(g.pt.target[4])[i4];
+            }
+#pragma unroll
+            for (int j = 0; j < kSlots; j++) {
+                rm[j] = rv[j] = rp[j] = rt[j] = 0.f;
+                rtn[j] = rj[j] = 0;
+                if (gi[j] >= 0) {
+                    int t = 0;
+#pragma unroll
+                    for (int k = 1; k < 14; k++) t += (gi[j] >= g.pt.offset[k]) ? 1 : 0;
+                    rtn[j] = t;
+                    rj[j] = gi[j] - g.pt.offset[t];
+                    rm[j] = g.m[gi[j]];
+                    rv[j] = g.v[gi[j]];
+                    rp[j] = g.pt.main[t][rj[j]];
+                    rt[j] = g.pt.target[t][rj[j]];
+                }
+            }
+        }
+        stamp(19);
         // squared norm: warp tree, warps in order, CTAs in rank order over DSMEM
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
@@ -889,6 +1042,7 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
             normslot[0] = t;
         }
         cluster_sync_all();
+        stamp(20);
         if (g.do_adam) {
             if (tid == 0) {
                 float t = 0.f;
@@ -913,26 +1067,38 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
             const AdamCoef c = *reinterpret_cast<const AdamCoef*>(red + 20);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int i = g.off_w2 + 4 * (rank * 2048 + j * 512 + tid);
-                adam_soft_update_element(g.pt, i, gw[j].x, c, g.m, g.v, g.hp);
-                adam_soft_update_element(g.pt, i + 1, gw[j].y, c, g.m, g.v, g.hp);
-                adam_soft_update_element(g.pt, i + 2, gw[j].z, c, g.m, g.v, g.hp);
-                adam_soft_update_element(g.pt, i + 3, gw[j].w, c, g.m, g.v, g.hp);
+                const int i4 = rank * 2048 + j * 512 + tid;
+                adam_math(gw[j].x, c, g.hp, am[j].x, av[j].x, ap[j].x, at[j].x);
+                adam_math(gw[j].y, c, g.hp, am[j].y, av[j].y, ap[j].y, at[j].y);
+                adam_math(gw[j].z, c, g.hp, am[j].z, av[j].z, ap[j].z, at[j].z);
+                adam_math(gw[j].w, c, g.hp, am[j].w, av[j].w, ap[j].w, at[j].w);
+                reinterpret_cast<float4*>(g.m + g.off_w2)[i4] = am[j];
+                reinterpret_cast<float4*>(g.v + g.off_w2)[i4] = av[j];
+                reinterpret_cast<float4*>(g.pt.main[4])[i4] = ap[j];
+                reinterpret_cast<float4*>(g.pt.target[4])[i4] = at[j];
             }
 #pragma unroll
-            for (int j = 0; j < 8; j++)
-                if (gi[j] >= 0) adam_soft_update_element(g.pt, gi[j], gr[j], c, g.m, g.v, g.hp);
+            for (int j = 0; j < kSlots; j++)
+                if (gi[j] >= 0) {
+                    adam_math(gr[j], c, g.hp, rm[j], rv[j], rp[j], rt[j]);
+                    g.m[gi[j]] = rm[j];
+                    g.v[gi[j]] = rv[j];
+                    g.pt.main[rtn[j]][rj[j]] = rp[j];
+                    g.pt.target[rtn[j]][rj[j]] = rt[j];
+                }
         } else if (rank == 0 && tid == 0 && g.loss != nullptr) {
             float l = 0.f;
             for (int cc = 0; cc < CL; cc++) l += __ldcg(g.part_loss + cc);
             *g.loss = l / (float)B;
         }
     }
+    stamp(21);
     // a CTA's shared memory must outlive every DSMEM read of it; the step counter moves after everybody has read it
     cluster_sync_all();
     if (net == 1 && g.do_adam && rank == 0 && tid == 0) *g.step += 1;
     fence_before_sync();
     __syncthreads();
+    stamp(22);
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
@@ -998,6 +1164,7 @@ int learn_cluster_step(LearnCluster* lcw, const rloa_naf_params* mn, const rloa_
     a.off_wmu = flat_offsets[8]; a.off_bmu = flat_offsets[9]; a.off_wv = flat_offsets[10]; a.off_bv = flat_offsets[11];
     a.off_wl = flat_offsets[12]; a.off_bl = flat_offsets[13]; a.n_params = flat_offsets[14];
     a.dbg = lcw->dbg;
+    a.prof = lcw->prof;
     naf_learn_cluster_kernel<<<2 * lc::CL, lc::THREADS, lc::SMEM_BYTES, st>>>(a);
     RLOA_LAUNCHED();
     return RLOA_OK;

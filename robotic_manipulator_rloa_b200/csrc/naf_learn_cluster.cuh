@@ -14,6 +14,7 @@ struct LearnCluster {
     float *y = nullptr, *part_w2 = nullptr, *part_w1 = nullptr, *part_wh = nullptr, *part_hb = nullptr, *part_loss = nullptr;
     unsigned* yflag = nullptr;
     float* dbg = nullptr;            // optional intermediate dump (tests)
+    long long* prof = nullptr;       // optional clock64 phase stamps
 };
 
 bool learn_cluster_supported(int S, int A, int H, int B);

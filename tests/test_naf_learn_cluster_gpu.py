@@ -128,11 +128,11 @@ def test_cluster_learn_stages_and_gradient(B):
     # a first call creates the workspace; the debug buffer is attached to it afterwards
     dbg = torch.full((6, 1024, 256), float('nan'), device=DEV)
     agent._workspace(B)
-    N.check(agent._ws.lib.rloa_naf_ws_set_debug(agent._ws.handle, dbg.data_ptr()), 'set_debug')
+    N.check(agent._ws.lib.rloa_naf_ws_set_debug(agent._ws.handle, dbg.data_ptr(), None), 'set_debug')
     pm_before = {k: v.detach().clone() for k, v in agent.qnetwork_main.state_dict().items()}
     agent.learn((s, a.long(), r, s2, d))
     torch.cuda.synchronize()
-    N.check(agent._ws.lib.rloa_naf_ws_set_debug(agent._ws.handle, None), 'set_debug')
+    N.check(agent._ws.lib.rloa_naf_ws_set_debug(agent._ws.handle, None, None), 'set_debug')
     dcpu = dbg.cpu()
     stage = {'z1': dcpu[0, :B], 'z2': dcpu[1, :B], 'dzh': dcpu[2].reshape(-1)[:1024 * 64].reshape(1024, 64)[:B, :A + 1 + 21],
              'dz2': dcpu[3, :B], 'da1': dcpu[4, :B], 'dz1': dcpu[5, :B]}
