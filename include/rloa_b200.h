@@ -379,6 +379,20 @@ int rloa_replay_sample(const rloa_replay* rb, int32_t batch, uint64_t seed, uint
                        const uint64_t* draw_offset, float* states, float* actions, float* rewards,
                        float* next_states, float* dones, int32_t* indices, void* stream);
 
+/* ReplayBuffer.sample + NAFAgent.learn in one call (naf_algorithm.py:152-154: `experiences = self.memory.sample();
+ * self.learn(experiences)`), available when rloa_naf_learn_fused_supported(ws, batch) != 0 (trunk mode 1, batch <= 1024): the
+ * fused learn kernel draws the same slots as rloa_replay_sample(seed, draw + *draw_offset) and reads its rows straight from
+ * the ring, so no sampled copy of the batch is written.  xchg may be NULL (single rank). */
+int rloa_naf_learn_fused_supported(const rloa_naf_ws* ws, int32_t batch);
+int rloa_naf_learn_step_replay(rloa_naf_ws* ws, const rloa_naf_params* main_net, const rloa_naf_params* target_net,
+                               const rloa_adam_state* adam, rloa_xchg* xchg, const rloa_replay* rb, uint64_t seed, uint64_t draw,
+                               const uint64_t* draw_offset, int32_t batch, const rloa_naf_hyper* hyper, float* grad, float* loss,
+                               float* grad_norm, void* stream);
+/* Optional: writes the tensor-core weight images the next rloa_naf_learn_* call of this workspace needs on the workspace's
+ * side stream NOW (the caller promises not to modify the parameters before that call), so that the call itself starts with
+ * the images ready.  A no-op on the other paths. */
+int rloa_naf_learn_prepack(rloa_naf_ws* ws, const rloa_naf_params* main_net, const rloa_naf_params* target_net, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -123,6 +123,10 @@ SIGNATURES = {
                                        C.POINTER(NafHyper), _fp, _fp, _VP]),
     'rloa_naf_learn_step': (C.c_int, [_VP, C.POINTER(NafParams), C.POINTER(NafParams), C.POINTER(AdamState), _fp, _fp, _fp,
                                       _fp, _fp, _I, C.POINTER(NafHyper), _fp, _fp, _fp, _VP]),
+    'rloa_naf_learn_fused_supported': (C.c_int, [_VP, _I]),
+    'rloa_naf_learn_step_replay': (C.c_int, [_VP, C.POINTER(NafParams), C.POINTER(NafParams), C.POINTER(AdamState), _VP,
+                                             C.POINTER(Replay), _U64, _U64, _fp, _I, C.POINTER(NafHyper), _fp, _fp, _fp, _VP]),
+    'rloa_naf_learn_prepack': (C.c_int, [_VP, C.POINTER(NafParams), C.POINTER(NafParams), _VP]),
     'rloa_xchg_create': (C.c_int, [_I, C.POINTER(_VP)]),
     'rloa_xchg_handle': (C.c_int, [_VP, C.c_char_p]),
     'rloa_xchg_connect': (C.c_int, [_VP, _I, _I, C.c_char_p]),

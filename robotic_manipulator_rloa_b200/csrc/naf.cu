@@ -1360,9 +1360,9 @@ static bool cluster_learn_applies(const rloa_naf_ws* ws, int batch) {
 static int cluster_learn(rloa_naf_ws* ws, const rloa_naf_params* mn, const rloa_naf_params* tg, const rloa_adam_state* adam,
                          const float* states, const float* actions, const float* rewards, const float* next_states,
                          const float* dones, int32_t batch, const rloa_naf_hyper* hp, float* grad, float* loss, float* gnorm,
-                         int do_adam, void* stream) {
-    RLOA_REQUIRE(ws && states && actions && rewards && next_states && hp && grad, "rloa_naf_learn: null argument");
-    RLOA_REQUIRE(!(hp->use_done_mask && dones == nullptr), "rloa_naf_learn: use_done_mask needs dones");
+                         int do_adam, void* stream, const LearnClusterReplay* replay = nullptr) {
+    RLOA_REQUIRE(ws && hp && grad && (replay != nullptr || (states && actions && rewards && next_states)), "rloa_naf_learn: null argument");
+    RLOA_REQUIRE(!(hp->use_done_mask && dones == nullptr && replay == nullptr), "rloa_naf_learn: use_done_mask needs dones");
     int rc = check_params(ws, mn, "rloa_naf_learn(main)");
     if (rc != RLOA_OK) return rc;
     rc = check_params(ws, tg, "rloa_naf_learn(target)");
@@ -1372,7 +1372,7 @@ static int cluster_learn(rloa_naf_ws* ws, const rloa_naf_params* mn, const rloa_
     ParamTable pt;
     fill_param_table(mn, tg, &pt);
     return learn_cluster_step(&ws->lc, mn, tg, adam, states, actions, rewards, next_states, dones, batch, hp, pt, offs, grad, loss,
-                              gnorm, do_adam, as_stream(stream));
+                              gnorm, do_adam, replay, as_stream(stream));
 }
 
 // forward of both nets, loss, backward.  With defer != NULL the final split-K reduction is NOT launched: its
@@ -1382,6 +1382,7 @@ static int learn_grads_impl(rloa_naf_ws* ws, const rloa_naf_params* mn, const rl
                             const float* next_states, const float* dones, int32_t batch,
                             const rloa_naf_hyper* hp, float* grad, float* loss, ReduceArgs* defer, void* stream) {
     RLOA_REQUIRE(ws && states && actions && rewards && next_states && hp && grad, "rloa_naf_learn_grads: null argument");
+    ws->lc.prepacked = false;        // a pending rloa_naf_learn_prepack belongs to the fused path; this path changes the weights
     RLOA_REQUIRE(batch >= 2 && batch <= ws->max_batch, "rloa_naf_learn_grads: 2 <= batch <= workspace max_batch required");
     RLOA_REQUIRE(!(hp->use_done_mask && dones == nullptr), "rloa_naf_learn_grads: use_done_mask needs dones");
     int rc = check_params(ws, mn, "rloa_naf_learn_grads(main)");
@@ -1620,6 +1621,46 @@ extern "C" int rloa_naf_learn_step_xchg(rloa_naf_ws* ws, const rloa_naf_params* 
     ParamTable pt;
     fill_param_table(mn, tg, &pt);
     return xchg_exchange_adam(xchg, grad, ra, pt, adam->m, adam->v, adam->step, *hp, grad_norm, as_stream(stream));
+}
+
+extern "C" int rloa_naf_learn_fused_supported(const rloa_naf_ws* ws, int32_t batch) {
+    return (ws != nullptr && cluster_learn_applies(ws, batch)) ? 1 : 0;
+}
+
+extern "C" int rloa_naf_learn_prepack(rloa_naf_ws* ws, const rloa_naf_params* mn, const rloa_naf_params* tg, void* stream) {
+    RLOA_REQUIRE(ws != nullptr && mn != nullptr && tg != nullptr, "rloa_naf_learn_prepack: null argument");
+    if (!(ws->trunk_mode == 1 && ws->use_cluster && ws->lc.images != nullptr)) return RLOA_OK;      // nothing to prepare on the other paths
+    int rc = check_params(ws, mn, "rloa_naf_learn_prepack(main)");
+    if (rc != RLOA_OK) return rc;
+    rc = check_params(ws, tg, "rloa_naf_learn_prepack(target)");
+    if (rc != RLOA_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    RLOA_CUDA(cudaEventRecord(ws->lc.pack_fork, st));
+    RLOA_CUDA(cudaStreamWaitEvent(ws->side[0], ws->lc.pack_fork, 0));
+    rc = learn_cluster_pack(&ws->lc, mn, tg, ws->side[0]);
+    if (rc != RLOA_OK) return rc;
+    RLOA_CUDA(cudaEventRecord(ws->lc.pack_done, ws->side[0]));
+    ws->lc.prepacked = true;
+    return RLOA_OK;
+}
+
+extern "C" int rloa_naf_learn_step_replay(rloa_naf_ws* ws, const rloa_naf_params* mn, const rloa_naf_params* tg,
+                                          const rloa_adam_state* adam, rloa_xchg* xchg, const rloa_replay* rb, uint64_t seed,
+                                          uint64_t draw, const uint64_t* draw_offset, int32_t batch, const rloa_naf_hyper* hp,
+                                          float* grad, float* loss, float* grad_norm, void* stream) {
+    RLOA_REQUIRE(ws && adam && adam->m && adam->v && adam->step && rb && hp, "rloa_naf_learn_step_replay: null argument");
+    RLOA_REQUIRE(cluster_learn_applies(ws, batch),
+                 "rloa_naf_learn_step_replay: needs trunk mode 1 and a batch the fused kernel supports (rloa_naf_learn_fused_supported); "
+                 "use rloa_replay_sample + rloa_naf_learn_step otherwise");
+    RLOA_REQUIRE(rb->state_size == ws->S && rb->action_size == ws->A, "rloa_naf_learn_step_replay: replay row layout does not match the network");
+    const LearnClusterReplay rp{rb, seed, draw, draw_offset};
+    if (xchg == nullptr)
+        return cluster_learn(ws, mn, tg, adam, nullptr, nullptr, nullptr, nullptr, nullptr, batch, hp, grad, loss, grad_norm, 1, stream, &rp);
+    int rc = cluster_learn(ws, mn, tg, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, batch, hp, grad, loss, nullptr, 0, stream, &rp);
+    if (rc != RLOA_OK) return rc;
+    ParamTable pt;
+    fill_param_table(mn, tg, &pt);
+    return xchg_exchange_adam(xchg, grad, ReduceArgs{}, pt, adam->m, adam->v, adam->step, *hp, grad_norm, as_stream(stream));
 }
 
 extern "C" int rloa_naf_soft_update(const rloa_naf_params* mn, const rloa_naf_params* tg, float tau, void* stream) {

@@ -34,6 +34,7 @@
 #include "bn_fuse.cuh"
 #include "naf_learn_cluster.cuh"
 #include "optim.cuh"
+#include "replay_sample.cuh"
 #include "tc_common.cuh"
 
 namespace rloa {
@@ -133,6 +134,12 @@ struct LearnClusterArgs {
     int off_w1, off_b1, off_bn1w, off_bn1b, off_w2, off_b2, off_bn2w, off_bn2b, off_wmu, off_bmu, off_wv, off_bv, off_wl, off_bl, n_params;
     float* dbg;                             // optional: z1 | z2 | dzh | dz2 | da1 | dz1 as fp32 [1024][256] each (dzh [1024][64])
     long long* prof;                        // optional: [16 CTAs][32] clock64 phase stamps
+    // fused ReplayBuffer.sample: row i of the batch is ring slot replay_sample_slot(rb, i, seed, draw + *draw_offset), read
+    // straight from the ring (states / actions / rewards / next_states / dones above are unused then)
+    int use_replay;
+    rloa_replay rb;
+    unsigned long long rs_seed, rs_draw;
+    const unsigned long long* rs_draw_offset;
 };
 
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -222,6 +229,261 @@ __device__ __forceinline__ void adam_math(float grad_i, const AdamCoef& c, const
     pt = hp.tau * p + (1.f - hp.tau) * pt;
 }
 
+
+// ---- per-thread context of the phase functions below.  They are deliberately NOT inlined: every one is called from two or
+// three places (both BatchNorm layers, forward and recompute), and the kernel executes its code exactly once per launch, so
+// instruction FETCH (230 KB of straight-line code when everything was inlined) was a first-order cost, doubled by a cold L2.
+struct LcCtx {
+    uint32_t tlane;                 // TMEM address of this warp's 32 lanes
+    int tid, q, r, lane, wq, rank, B, nrows, row, net;
+    bool valid;
+    float *coef, *xbuf, *scratch, *colaux, *bcoef;
+    float* dbg;
+};
+
+__device__ __forceinline__ void lc_dbg_rows32(const LcCtx& c, int section, int width, int c0, const float (&a)[32]) {
+    if (c.dbg != nullptr && c.net == 1 && c.valid) {
+        float* d = c.dbg + (size_t)section * 1024 * 256 + (size_t)c.row * width + c0;
+#pragma unroll
+        for (int i = 0; i < 32; i++) d[i] = a[i];
+    }
+}
+
+// train-mode BatchNorm statistics of the pre-activations acc + bias (acc = TMEM columns tcol..) in ONE pass over the
+// accumulator: per column sum and sum of squares of (z - K), K = the layer's running mean (a pivot near the batch mean keeps
+// the one-pass variance as accurate as the two-pass form); CTA partial (mean, M2) -> cluster exchange over DSMEM -> Chan
+// merge in rank order -> coef[layer] = sc | shb | rstd | xo with the linear bias folded in:
+//   relu(bn(z)) = max(acc sc + shb, 0),   xhat = acc rstd + xo.   Running statistics are updated by rank 0.
+__device__ __forceinline__ void lc_forward_stats(const LcCtx& c, int layer, uint32_t tcol, const float* bias, const float* bn_w,
+                                              const float* bn_b, float* run_mean, float* run_var, int64_t* batches) {
+    using namespace lc;
+    float* xb = c.xbuf + (layer & 1) * 3 * 256;
+    float* scratch = c.scratch;
+    const int tid = c.tid;
+    if (tid < 256) c.colaux[tid] = bias[tid] - run_mean[tid];
+    __syncthreads();
+#pragma unroll 1
+    for (int p = 0; p < 2; p++) {
+        const int c0 = c.q * 64 + p * 32;
+        uint32_t v[32];
+        tmem_ld32(c.tlane + tcol + c0, v);
+        float d[32], e[32];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float4 k4 = *reinterpret_cast<const float4*>(c.colaux + c0 + 4 * j);
+            d[4 * j] = __uint_as_float(v[4 * j]) + k4.x;
+            d[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + k4.y;
+            d[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + k4.z;
+            d[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + k4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            d[i] = c.valid ? d[i] : 0.f;
+            e[i] = d[i] * d[i];
+        }
+        const float s1 = colsum32(d, c.lane), s2 = colsum32(e, c.lane);
+        scratch[c.wq * 256 + c0 + c.lane] = s1;
+        scratch[1024 + c.wq * 256 + c0 + c.lane] = s2;
+    }
+    __syncthreads();
+    if (tid < 256) {
+        const float S1 = (scratch[tid] + scratch[256 + tid]) + (scratch[512 + tid] + scratch[768 + tid]);
+        const float S2 = (scratch[1024 + tid] + scratch[1280 + tid]) + (scratch[1536 + tid] + scratch[1792 + tid]);
+        const float n = (float)c.nrows;
+        const float md = c.nrows > 0 ? S1 / n : 0.f;
+        xb[tid] = md + run_mean[tid];                          // CTA mean of z
+        xb[256 + tid] = fmaxf(S2 - md * S1, 0.f);              // CTA centred second moment
+    }
+    cluster_sync_all();
+    if (tid < 256) {
+        const int B = c.B;
+        float pm[CL], pM[CL];
+#pragma unroll
+        for (int k = 0; k < CL; k++) { pm[k] = ld_dsmem(xb + tid, k); pM[k] = ld_dsmem(xb + 256 + tid, k); }
+        float n = 0.f, mean = 0.f, M2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < CL; k++) {
+            const float nb = (float)min(max(B - k * ROWS, 0), ROWS);
+            if (nb > 0.f) {
+                const float nn = n + nb, delta = pm[k] - mean;
+                mean = fmaf(delta, nb / nn, mean);
+                M2 = M2 + pM[k] + delta * delta * (n * nb / nn);
+                n = nn;
+            }
+        }
+        const float var = M2 / (float)B;
+        const float rstd = 1.f / sqrtf(var + kBnEps);
+        const float sc = bn_w[tid] * rstd;
+        const float sh = fmaf(-mean, sc, bn_b[tid]);
+        float* cf = c.coef + layer * 4 * 256;
+        cf[tid] = sc;
+        cf[256 + tid] = fmaf(bias[tid], sc, sh);
+        cf[512 + tid] = rstd;
+        cf[768 + tid] = (bias[tid] - mean) * rstd;
+        if (c.rank == 0) {
+            const float unbiased = B > 1 ? M2 / (float)(B - 1) : var;
+            run_mean[tid] = fmaf(kBnMomentum, mean - run_mean[tid], run_mean[tid]);
+            run_var[tid] = fmaf(kBnMomentum, unbiased - run_var[tid], run_var[tid]);
+            if (tid == 0 && batches != nullptr) *batches += 1;
+        }
+    }
+    __syncthreads();
+}
+
+// relu(bn(z)) of TMEM columns tcol.. -> bf16 K-major tile (rows past the batch are zero)
+__device__ __forceinline__ void lc_activation_to_tile(const LcCtx& c, int layer, uint32_t tcol, uint8_t* tile) {
+    const float* cf = c.coef + layer * 4 * 256;
+#pragma unroll 1
+    for (int p = 0; p < 2; p++) {
+        const int c0 = c.q * 64 + p * 32;
+        uint32_t v[32];
+        tmem_ld32(c.tlane + tcol + c0, v);
+        float a[32];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float4 sc = *reinterpret_cast<const float4*>(cf + c0 + 4 * j);
+            const float4 sh = *reinterpret_cast<const float4*>(cf + 256 + c0 + 4 * j);
+            a[4 * j] = fmaxf(fmaf(__uint_as_float(v[4 * j]), sc.x, sh.x), 0.f);
+            a[4 * j + 1] = fmaxf(fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y), 0.f);
+            a[4 * j + 2] = fmaxf(fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z), 0.f);
+            a[4 * j + 3] = fmaxf(fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w), 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i++) a[i] = c.valid ? a[i] : 0.f;
+        store_chunks32(tile, c.r, c0, a);
+    }
+}
+
+// ReLU + BatchNorm backward of one layer in ONE pass over the two accumulators (da in TMEM columns dcol.., the layer's
+// pre-activations in zcol..): column sums of g = da [bn(z) > 0] and g xhat over the whole batch through the cluster, then
+// the coefficients of dz = k1 (g - c1 - c2 xhat).  gamma / beta gradients are totals: rank 0 writes them; the linear-bias
+// gradient under a train-mode BatchNorm is the rounding residue k1 (sum g - B c1).
+__device__ __forceinline__ void lc_backward_stats(const LcCtx& c, int layer, uint32_t dcol, uint32_t zcol, const float* bn_w, int xslot,
+                                               float* d_w, float* d_b, float* d_lin) {
+    using namespace lc;
+    const float* cf = c.coef + layer * 4 * 256;
+    float* xb = c.xbuf + xslot * 3 * 256;
+    float* scratch = c.scratch;
+    const int tid = c.tid;
+#pragma unroll 1
+    for (int p = 0; p < 2; p++) {
+        const int c0 = c.q * 64 + p * 32;
+        uint32_t vd[32], vz[32];
+        tmem_ld32_nowait(c.tlane + zcol + c0, vz);
+        tmem_ld32_nowait(c.tlane + dcol + c0, vd);
+        tmem_ld_wait();
+        float a0[32], a1[32];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float4 sc = *reinterpret_cast<const float4*>(cf + c0 + 4 * j);
+            const float4 sh = *reinterpret_cast<const float4*>(cf + 256 + c0 + 4 * j);
+            const float4 rs = *reinterpret_cast<const float4*>(cf + 512 + c0 + 4 * j);
+            const float4 xo = *reinterpret_cast<const float4*>(cf + 768 + c0 + 4 * j);
+            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+            const float rsv[4] = {rs.x, rs.y, rs.z, rs.w}, xov[4] = {xo.x, xo.y, xo.z, xo.w};
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = 4 * j + u;
+                const float acc = __uint_as_float(vz[i]);
+                const bool on = c.valid && fmaf(acc, scv[u], shv[u]) > 0.f;
+                const float gg = on ? __uint_as_float(vd[i]) : 0.f;
+                a0[i] = gg;
+                a1[i] = gg * fmaf(acc, rsv[u], xov[u]);
+            }
+        }
+        const float s0 = colsum32(a0, c.lane), s1 = colsum32(a1, c.lane);
+        scratch[c.wq * 256 + c0 + c.lane] = s0;
+        scratch[1024 + c.wq * 256 + c0 + c.lane] = s1;
+    }
+    __syncthreads();
+    if (tid < 256) {
+        xb[tid] = (scratch[tid] + scratch[256 + tid]) + (scratch[512 + tid] + scratch[768 + tid]);
+        xb[256 + tid] = (scratch[1024 + tid] + scratch[1280 + tid]) + (scratch[1536 + tid] + scratch[1792 + tid]);
+    }
+    cluster_sync_all();
+    if (tid < 256) {
+        float p0[CL], p1[CL];
+#pragma unroll
+        for (int k = 0; k < CL; k++) { p0[k] = ld_dsmem(xb + tid, k); p1[k] = ld_dsmem(xb + 256 + tid, k); }
+        float tg = 0.f, tgx = 0.f;
+#pragma unroll
+        for (int k = 0; k < CL; k++) { tg += p0[k]; tgx += p1[k]; }
+        const float k1 = bn_w[tid] * cf[512 + tid], c1 = tg / (float)c.B, c2 = tgx / (float)c.B;
+        c.bcoef[tid] = k1;
+        c.bcoef[256 + tid] = k1 * c1;
+        c.bcoef[512 + tid] = k1 * c2;
+        if (c.rank == 0) {
+            d_w[tid] = tgx;
+            d_b[tid] = tg;
+            d_lin[tid] = k1 * (tg - (float)c.B * c1);
+        }
+    }
+    __syncthreads();
+}
+
+// dz = k1 g - k1 c1 - k1 c2 xhat of this thread's 64 columns -> bf16 K-major tile `dz_tile`; with act_tile != NULL also
+// relu(bn(z)) of the same pre-activations -> `act_tile` (layer 1: a1 is recomputed for dW2 while z1 is in registers anyway)
+__device__ __forceinline__ void lc_dz_to_tile(const LcCtx& c, int layer, uint32_t dcol, uint32_t zcol, uint8_t* dz_tile, uint8_t* act_tile,
+                                           int dbg_dz, int dbg_da) {
+    const float* cf = c.coef + layer * 4 * 256;
+    const float* bcoef = c.bcoef;
+#pragma unroll 1
+    for (int p = 0; p < 2; p++) {
+        const int c0 = c.q * 64 + p * 32;
+        uint32_t vd[32], vz[32];
+        tmem_ld32_nowait(c.tlane + dcol + c0, vd);
+        tmem_ld32_nowait(c.tlane + zcol + c0, vz);
+        tmem_ld_wait();
+        float d[32];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float4 sc = *reinterpret_cast<const float4*>(cf + c0 + 4 * j);
+            const float4 sh = *reinterpret_cast<const float4*>(cf + 256 + c0 + 4 * j);
+            const float4 rs = *reinterpret_cast<const float4*>(cf + 512 + c0 + 4 * j);
+            const float4 xo = *reinterpret_cast<const float4*>(cf + 768 + c0 + 4 * j);
+            const float4 k1 = *reinterpret_cast<const float4*>(bcoef + c0 + 4 * j);
+            const float4 kc1 = *reinterpret_cast<const float4*>(bcoef + 256 + c0 + 4 * j);
+            const float4 kc2 = *reinterpret_cast<const float4*>(bcoef + 512 + c0 + 4 * j);
+            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+            const float rsv[4] = {rs.x, rs.y, rs.z, rs.w}, xov[4] = {xo.x, xo.y, xo.z, xo.w};
+            const float k1v[4] = {k1.x, k1.y, k1.z, k1.w}, c1v[4] = {kc1.x, kc1.y, kc1.z, kc1.w}, c2v[4] = {kc2.x, kc2.y, kc2.z, kc2.w};
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = 4 * j + u;
+                const float acc = __uint_as_float(vz[i]);
+                const float gg = fmaf(acc, scv[u], shv[u]) > 0.f ? __uint_as_float(vd[i]) : 0.f;
+                const float dzv = fmaf(-c2v[u], fmaf(acc, rsv[u], xov[u]), fmaf(k1v[u], gg, -c1v[u]));
+                d[i] = c.valid ? dzv : 0.f;
+            }
+        }
+        store_chunks32(dz_tile, c.r, c0, d);
+        if (c.dbg != nullptr) {
+            lc_dbg_rows32(c, dbg_dz, 256, c0, d);
+            if (dbg_da >= 0) {
+                float da[32];
+#pragma unroll
+                for (int i = 0; i < 32; i++) da[i] = __uint_as_float(vd[i]);
+                lc_dbg_rows32(c, dbg_da, 256, c0, da);
+            }
+        }
+        if (act_tile != nullptr) {
+            float a[32];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 sc = *reinterpret_cast<const float4*>(cf + c0 + 4 * j);
+                const float4 sh = *reinterpret_cast<const float4*>(cf + 256 + c0 + 4 * j);
+                a[4 * j] = fmaxf(fmaf(__uint_as_float(vz[4 * j]), sc.x, sh.x), 0.f);
+                a[4 * j + 1] = fmaxf(fmaf(__uint_as_float(vz[4 * j + 1]), sc.y, sh.y), 0.f);
+                a[4 * j + 2] = fmaxf(fmaf(__uint_as_float(vz[4 * j + 2]), sc.z, sh.z), 0.f);
+                a[4 * j + 3] = fmaxf(fmaf(__uint_as_float(vz[4 * j + 3]), sc.w, sh.w), 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i++) a[i] = c.valid ? a[i] : 0.f;
+            store_chunks32(act_tile, c.r, c0, a);
+        }
+    }
+}
+
 struct TrueT { static constexpr bool value = true; };
 struct FalseT { static constexpr bool value = false; };
 
@@ -237,7 +499,6 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
     const int row0 = rank * ROWS, row = row0 + r;
     const bool valid = row < B;
     const int nrows = min(max(B - row0, 0), ROWS);
-    const bool full = nrows == ROWS;
     const rloa_naf_params& P = g.p[net];
     const uint8_t* image = g.images + (size_t)net * IMAGE_BYTES;
 
@@ -267,12 +528,18 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
     }
     // this thread's 8 observation values (row r, k = 8 q .. 8 q + 7); kept in registers for the z1 recompute and dW1
     float xk[8];
+    size_t src_row = (size_t)row;                                     // row of the batch arrays, or ring slot of the sample
+    if (g.use_replay && valid)
+        src_row = replay_sample_slot(g.rb, row, g.rs_seed, g.rs_draw + (g.rs_draw_offset != nullptr ? *g.rs_draw_offset : 0ull));
+    const float* in_actions = g.use_replay ? g.rb.actions : g.actions;
+    const float* in_rewards = g.use_replay ? g.rb.rewards : g.rewards;
+    const float* in_dones = g.use_replay ? g.rb.dones : g.dones;
     {
-        const float* x = net == 0 ? g.next_states : g.states;
+        const float* x = g.use_replay ? (net == 0 ? g.rb.next_states : g.rb.states) : (net == 0 ? g.next_states : g.states);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int k = q * 8 + i;
-            xk[i] = (k < S && valid) ? x[(size_t)row * S + k] : 0.f;
+            xk[i] = (k < S && valid) ? x[src_row * S + k] : 0.f;
         }
     }
     auto stage_x_tf32 = [&](uint8_t* xh, uint8_t* xl) {
@@ -319,93 +586,15 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
         }
     };
 
-    // ---- train-mode BatchNorm statistics of the pre-activations acc + bias (acc = TMEM columns tcol..) in ONE pass over
-    // the accumulator: per column sum and sum of squares of (z - K), K = the layer's running mean (a pivot near the batch
-    // mean keeps the one-pass variance as accurate as the two-pass form); CTA partial (mean, M2) -> cluster exchange over
-    // DSMEM -> Chan merge in rank order -> coef[layer] = sc | shb | rstd | xo with the linear bias folded in:
-    //   relu(bn(z)) = max(acc sc + shb, 0),   xhat = acc rstd + xo.   Running statistics are updated by rank 0.
+    LcCtx ctx;
+    ctx.tlane = tlane; ctx.tid = tid; ctx.q = q; ctx.r = r; ctx.lane = lane; ctx.wq = wq; ctx.rank = rank; ctx.B = B;
+    ctx.nrows = nrows; ctx.row = row; ctx.net = net; ctx.valid = valid;
+    ctx.coef = coef; ctx.xbuf = xbuf; ctx.scratch = scratch; ctx.colaux = colaux; ctx.bcoef = bcoef; ctx.dbg = g.dbg;
     auto forward_stats = [&](int layer, uint32_t tcol, const float* bias, const float* bn_w, const float* bn_b,
                              float* run_mean, float* run_var, int64_t* batches) {
-        float* xb = xbuf + (layer & 1) * 3 * 256;
-        if (tid < 256) colaux[tid] = bias[tid] - run_mean[tid];
-        __syncthreads();
-        auto body = [&](auto full_t) {
-            constexpr bool kFull = decltype(full_t)::value;
-#pragma unroll 1
-            for (int p = 0; p < 2; p++) {
-                const int c0 = q * 64 + p * 32;
-                uint32_t v[32];
-                tmem_ld32(tlane + tcol + c0, v);
-                float d[32], e[32];
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float4 k4 = *reinterpret_cast<const float4*>(colaux + c0 + 4 * j);
-                    d[4 * j] = __uint_as_float(v[4 * j]) + k4.x;
-                    d[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + k4.y;
-                    d[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + k4.z;
-                    d[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + k4.w;
-                }
-#pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    if (!kFull) d[i] = valid ? d[i] : 0.f;
-                    e[i] = d[i] * d[i];
-                }
-                const float s1 = colsum32(d, lane), s2 = colsum32(e, lane);
-                scratch[wq * 256 + c0 + lane] = s1;
-                scratch[1024 + wq * 256 + c0 + lane] = s2;
-            }
-        };
-        if (full) body(TrueT{}); else body(FalseT{});
-        __syncthreads();
-        if (tid < 256) {
-            const float S1 = (scratch[tid] + scratch[256 + tid]) + (scratch[512 + tid] + scratch[768 + tid]);
-            const float S2 = (scratch[1024 + tid] + scratch[1280 + tid]) + (scratch[1536 + tid] + scratch[1792 + tid]);
-            const float n = (float)nrows;
-            const float md = nrows > 0 ? S1 / n : 0.f;
-            xb[tid] = md + run_mean[tid];                          // CTA mean of z
-            xb[256 + tid] = fmaxf(S2 - md * S1, 0.f);              // CTA centred second moment
-        }
-        cluster_sync_all();
-        if (tid < 256) {
-            float pm[CL], pM[CL];
-#pragma unroll
-            for (int c = 0; c < CL; c++) { pm[c] = ld_dsmem(xb + tid, c); pM[c] = ld_dsmem(xb + 256 + tid, c); }
-            float n = 0.f, mean = 0.f, M2 = 0.f;
-#pragma unroll
-            for (int c = 0; c < CL; c++) {
-                const float nb = (float)min(max(B - c * ROWS, 0), ROWS);
-                if (nb > 0.f) {
-                    const float nn = n + nb, delta = pm[c] - mean;
-                    mean = fmaf(delta, nb / nn, mean);
-                    M2 = M2 + pM[c] + delta * delta * (n * nb / nn);
-                    n = nn;
-                }
-            }
-            const float var = M2 / (float)B;
-            const float rstd = 1.f / sqrtf(var + kBnEps);
-            const float sc = bn_w[tid] * rstd;
-            const float sh = fmaf(-mean, sc, bn_b[tid]);
-            float* cf = coef + layer * 4 * 256;
-            cf[tid] = sc;
-            cf[256 + tid] = fmaf(bias[tid], sc, sh);
-            cf[512 + tid] = rstd;
-            cf[768 + tid] = (bias[tid] - mean) * rstd;
-            if (rank == 0) {
-                const float unbiased = B > 1 ? M2 / (float)(B - 1) : var;
-                run_mean[tid] = fmaf(kBnMomentum, mean - run_mean[tid], run_mean[tid]);
-                run_var[tid] = fmaf(kBnMomentum, unbiased - run_var[tid], run_var[tid]);
-                if (tid == 0 && batches != nullptr) *batches += 1;
-            }
-        }
-        __syncthreads();
+        lc_forward_stats(ctx, layer, tcol, bias, bn_w, bn_b, run_mean, run_var, batches);
     };
-    auto dbg_rows32 = [&](int section, int width, int c0, const float (&a)[32]) {
-        if (g.dbg != nullptr && net == 1 && valid) {
-            float* d = g.dbg + (size_t)section * 1024 * 256 + (size_t)row * width + c0;
-#pragma unroll
-            for (int i = 0; i < 32; i++) d[i] = a[i];
-        }
-    };
+    auto dbg_rows32 = [&](int section, int width, int c0, const float (&a)[32]) { lc_dbg_rows32(ctx, section, width, c0, a); };
     auto dbg_preact = [&](int section, uint32_t tcol, const float* bias) {
         if (g.dbg != nullptr && net == 1) {
 #pragma unroll 1
@@ -419,31 +608,7 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
             }
         }
     };
-    // relu(bn(z)) of TMEM columns tcol.. -> bf16 K-major tile (rows past the batch are zero)
-    auto activation_to_tile = [&](int layer, uint32_t tcol, uint8_t* tile) {
-        const float* cf = coef + layer * 4 * 256;
-#pragma unroll 1
-        for (int p = 0; p < 2; p++) {
-            const int c0 = q * 64 + p * 32;
-            uint32_t v[32];
-            tmem_ld32(tlane + tcol + c0, v);
-            float a[32];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const float4 sc = *reinterpret_cast<const float4*>(cf + c0 + 4 * j);
-                const float4 sh = *reinterpret_cast<const float4*>(cf + 256 + c0 + 4 * j);
-                a[4 * j] = fmaxf(fmaf(__uint_as_float(v[4 * j]), sc.x, sh.x), 0.f);
-                a[4 * j + 1] = fmaxf(fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y), 0.f);
-                a[4 * j + 2] = fmaxf(fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z), 0.f);
-                a[4 * j + 3] = fmaxf(fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w), 0.f);
-            }
-            if (!full) {
-#pragma unroll
-                for (int i = 0; i < 32; i++) a[i] = valid ? a[i] : 0.f;
-            }
-            store_chunks32(tile, r, c0, a);
-        }
-    };
+    auto activation_to_tile = [&](int layer, uint32_t tcol, uint8_t* tile) { lc_activation_to_tile(ctx, layer, tcol, tile); };
 
     // =========================== forward ===========================
     issue_layer1(base + R1, base + R1 + W1_BYTES, base + R1 + W1_BYTES + 16384, 0);
@@ -516,8 +681,8 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
         // ---- target network: y = r + gamma V'(s') for this CTA's rows, then hand over to the main CTA of the same rank
         if (q == 0 && valid) {
             float vv = zo[A];
-            if (g.hp.use_done_mask && g.dones != nullptr) vv *= (1.f - g.dones[row]);
-            g.y[row] = fmaf(g.hp.gamma, vv, g.rewards[row]);
+            if (g.hp.use_done_mask && in_dones != nullptr) vv *= (1.f - in_dones[src_row]);
+            g.y[row] = fmaf(g.hp.gamma, vv, in_rewards[src_row]);
         }
         __threadfence();
         __syncthreads();
@@ -537,7 +702,7 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
                 mu_[u] = tanhf(zo[k]);
                 t_[u] = tanhf(zo[A + 1 + (k * (k + 3)) / 2]);
                 P_[u] = expf(2.f * t_[u]);
-                float act = g.actions[(size_t)row * A + k];
+                float act = in_actions[src_row * A + k];
                 if (g.hp.trunc_action) act = truncf(act);
                 df_[u] = act - mu_[u];
                 advp = fmaf(-0.5f * P_[u] * df_[u], df_[u], advp);
@@ -658,115 +823,10 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
             bulk_g2s(sm + R0, image + OFF_W2, W2_BYTES, &bars[1]);
         }
 
-        // ReLU + BatchNorm backward of one layer in ONE pass over the two accumulators (da in TMEM columns dcol.., the
-        // layer's pre-activations in zcol..): column sums of g = da [bn(z) > 0] and g xhat over the whole batch through the
-        // cluster, then dz = k1 (g - c1 - c2 xhat) (second pass, by the caller).  gamma / beta gradients are totals: rank 0
-        // writes them; the linear-bias gradient under a train-mode BatchNorm is the rounding residue k1 (sum g - B c1).
-        auto backward_stats = [&](int layer, uint32_t dcol, uint32_t zcol, const float* bn_w, int xslot,
-                                  float* d_w, float* d_b, float* d_lin) {
-            const float* cf = coef + layer * 4 * 256;
-            float* xb = xbuf + xslot * 3 * 256;
-            auto body = [&](auto full_t) {
-                constexpr bool kFull = decltype(full_t)::value;
-#pragma unroll 1
-                for (int p = 0; p < 2; p++) {
-                    const int c0 = q * 64 + p * 32;
-                    uint32_t vd[32], vz[32];
-                    tmem_ld32_nowait(tlane + zcol + c0, vz);
-                    tmem_ld32_nowait(tlane + dcol + c0, vd);
-                    tmem_ld_wait();
-                    float a0[32], a1[32];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const float4 sc = *reinterpret_cast<const float4*>(cf + c0 + 4 * j);
-                        const float4 sh = *reinterpret_cast<const float4*>(cf + 256 + c0 + 4 * j);
-                        const float4 rs = *reinterpret_cast<const float4*>(cf + 512 + c0 + 4 * j);
-                        const float4 xo = *reinterpret_cast<const float4*>(cf + 768 + c0 + 4 * j);
-                        const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
-                        const float rsv[4] = {rs.x, rs.y, rs.z, rs.w}, xov[4] = {xo.x, xo.y, xo.z, xo.w};
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int i = 4 * j + u;
-                            const float acc = __uint_as_float(vz[i]);
-                            bool on = fmaf(acc, scv[u], shv[u]) > 0.f;
-                            if (!kFull) on = on && valid;
-                            const float gg = on ? __uint_as_float(vd[i]) : 0.f;
-                            a0[i] = gg;
-                            a1[i] = gg * fmaf(acc, rsv[u], xov[u]);
-                        }
-                    }
-                    const float s0 = colsum32(a0, lane), s1 = colsum32(a1, lane);
-                    scratch[wq * 256 + c0 + lane] = s0;
-                    scratch[1024 + wq * 256 + c0 + lane] = s1;
-                }
-            };
-            if (full) body(TrueT{}); else body(FalseT{});
-            __syncthreads();
-            if (tid < 256) {
-                xb[tid] = (scratch[tid] + scratch[256 + tid]) + (scratch[512 + tid] + scratch[768 + tid]);
-                xb[256 + tid] = (scratch[1024 + tid] + scratch[1280 + tid]) + (scratch[1536 + tid] + scratch[1792 + tid]);
-            }
-            cluster_sync_all();
-            if (tid < 256) {
-                float p0[CL], p1[CL];
-#pragma unroll
-                for (int c = 0; c < CL; c++) { p0[c] = ld_dsmem(xb + tid, c); p1[c] = ld_dsmem(xb + 256 + tid, c); }
-                float tg = 0.f, tgx = 0.f;
-#pragma unroll
-                for (int c = 0; c < CL; c++) { tg += p0[c]; tgx += p1[c]; }
-                const float k1 = bn_w[tid] * cf[512 + tid], c1 = tg / (float)B, c2 = tgx / (float)B;
-                bcoef[tid] = k1;
-                bcoef[256 + tid] = k1 * c1;
-                bcoef[512 + tid] = k1 * c2;
-                if (rank == 0) {
-                    d_w[tid] = tgx;
-                    d_b[tid] = tg;
-                    d_lin[tid] = k1 * (tg - (float)B * c1);
-                }
-            }
-            __syncthreads();
-        };
-        // dz = k1 g - k1 c1 - k1 c2 xhat of 32 columns (accumulators vd = da, vz = the layer's pre-activations)
-        auto dz32 = [&](int layer, int c0, const uint32_t (&vd)[32], const uint32_t (&vz)[32], float (&d)[32]) {
-            const float* cf = coef + layer * 4 * 256;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const float4 sc = *reinterpret_cast<const float4*>(cf + c0 + 4 * j);
-                const float4 sh = *reinterpret_cast<const float4*>(cf + 256 + c0 + 4 * j);
-                const float4 rs = *reinterpret_cast<const float4*>(cf + 512 + c0 + 4 * j);
-                const float4 xo = *reinterpret_cast<const float4*>(cf + 768 + c0 + 4 * j);
-                const float4 k1 = *reinterpret_cast<const float4*>(bcoef + c0 + 4 * j);
-                const float4 kc1 = *reinterpret_cast<const float4*>(bcoef + 256 + c0 + 4 * j);
-                const float4 kc2 = *reinterpret_cast<const float4*>(bcoef + 512 + c0 + 4 * j);
-                const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
-                const float rsv[4] = {rs.x, rs.y, rs.z, rs.w}, xov[4] = {xo.x, xo.y, xo.z, xo.w};
-                const float k1v[4] = {k1.x, k1.y, k1.z, k1.w}, c1v[4] = {kc1.x, kc1.y, kc1.z, kc1.w}, c2v[4] = {kc2.x, kc2.y, kc2.z, kc2.w};
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int i = 4 * j + u;
-                    const float acc = __uint_as_float(vz[i]);
-                    const float gg = fmaf(acc, scv[u], shv[u]) > 0.f ? __uint_as_float(vd[i]) : 0.f;
-                    const float dzv = fmaf(-c2v[u], fmaf(acc, rsv[u], xov[u]), fmaf(k1v[u], gg, -c1v[u]));
-                    d[i] = valid ? dzv : 0.f;
-                }
-            }
-        };
-
         stamp(9);
-        backward_stats(1, 0, 256, P.bn2_w, 0, g.grad + g.off_bn2w, g.grad + g.off_bn2b, g.grad + g.off_b2);
+        lc_backward_stats(ctx, 1, 0, 256, P.bn2_w, 0, g.grad + g.off_bn2w, g.grad + g.off_bn2b, g.grad + g.off_b2);
         stamp(10);
-#pragma unroll 1
-        for (int p = 0; p < 2; p++) {          // dz2 -> bf16 tile in R1 (a2 is dead: dWh^T finished)
-            const int c0 = q * 64 + p * 32;
-            uint32_t vd[32], vz[32];
-            tmem_ld32_nowait(tlane + c0, vd);
-            tmem_ld32_nowait(tlane + 256 + c0, vz);
-            tmem_ld_wait();
-            float d[32];
-            dz32(1, c0, vd, vz, d);
-            store_chunks32(sm + R1, r, c0, d);
-            dbg_rows32(3, 256, c0, d);
-        }
+        lc_dz_to_tile(ctx, 1, 0, 256, sm + R1, nullptr, 3, -1);      // dz2 -> bf16 tile in R1 (a2 is dead: dWh^T finished)
         fence_proxy_async();
         fence_before_sync();
         __syncthreads();
@@ -796,43 +856,10 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
         issue_layer1(base + R0, base + R0 + W1_BYTES, base + R0 + W1_BYTES + 16384, 1);      // z1 again -> TMEM columns 0-255
         mma_wait();
         stamp(13);
-        backward_stats(0, 256, 0, P.bn1_w, 1, g.grad + g.off_bn1w, g.grad + g.off_bn1b, g.grad + g.off_b1);
+        lc_backward_stats(ctx, 0, 256, 0, P.bn1_w, 1, g.grad + g.off_bn1w, g.grad + g.off_bn1b, g.grad + g.off_b1);
         stamp(14);
-#pragma unroll 1
-        for (int p = 0; p < 2; p++) {          // dz1 -> R0 + 64 KB, a1 -> R0 (the layer-1 operands there are dead: z1 is in TMEM)
-            const int c0 = q * 64 + p * 32;
-            uint32_t vd[32], vz[32];
-            tmem_ld32_nowait(tlane + 256 + c0, vd);
-            tmem_ld32_nowait(tlane + c0, vz);
-            tmem_ld_wait();
-            {
-                float d[32];
-                dz32(0, c0, vd, vz, d);
-                store_chunks32(sm + R0 + 65536, r, c0, d);
-                dbg_rows32(5, 256, c0, d);
-                if (g.dbg != nullptr) {
-                    float da[32];
-#pragma unroll
-                    for (int i = 0; i < 32; i++) da[i] = __uint_as_float(vd[i]);
-                    dbg_rows32(4, 256, c0, da);
-                }
-            }
-            {
-                float a[32];
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float4 sc = *reinterpret_cast<const float4*>(coef + c0 + 4 * j);
-                    const float4 sh = *reinterpret_cast<const float4*>(coef + 256 + c0 + 4 * j);
-                    a[4 * j] = fmaxf(fmaf(__uint_as_float(vz[4 * j]), sc.x, sh.x), 0.f);
-                    a[4 * j + 1] = fmaxf(fmaf(__uint_as_float(vz[4 * j + 1]), sc.y, sh.y), 0.f);
-                    a[4 * j + 2] = fmaxf(fmaf(__uint_as_float(vz[4 * j + 2]), sc.z, sh.z), 0.f);
-                    a[4 * j + 3] = fmaxf(fmaf(__uint_as_float(vz[4 * j + 3]), sc.w, sh.w), 0.f);
-                }
-#pragma unroll
-                for (int i = 0; i < 32; i++) a[i] = valid ? a[i] : 0.f;
-                store_chunks32(sm + R0, r, c0, a);
-            }
-        }
+        // dz1 -> R0 + 64 KB, a1 -> R0 (the layer-1 operands there are dead: z1 is in TMEM)
+        lc_dz_to_tile(ctx, 0, 256, 0, sm + R0 + 65536, sm + R0, 5, 4);
         __syncthreads();         // the backward coefficients in S1 are dead: the observation tile takes their place
         {   // [x_hi | x_lo] as bf16, 64 columns: hi(k) at column k, lo(k) at column 32 + k
             float h[8], l[8];
@@ -923,13 +950,16 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
         stamp(18);
         const int n = g.n_params;
         const float gs = g.hp.grad_scale;
-        // (a) this CTA's eighth of dW2, float4; (b) its share of everything else, scalar
-        float4 gw[4];
+        // The tail's loops are rolled (their bodies are fetched once and reused) and hand their per-thread results from the
+        // gather pass to the optimiser pass through shared memory — every operand tile is dead by now.
+        float4* t_gw = reinterpret_cast<float4*>(sm + R1);                    // [4][512] summed dW2 elements of this thread
+        float* t_gr = reinterpret_cast<float*>(sm + R1 + 32768);              // [6][512] summed other elements
+        int* t_gi = reinterpret_cast<int*>(sm + R1 + 32768 + 12288);          // [6][512] their flat indices (-1: none)
         float sq = 0.f;
-        {
+        {   // (a) this CTA's eighth of dW2 (16384 float4 in all, 2048 per CTA, 4 per thread): two rounds of 16 loads in flight
             const float4* pw = reinterpret_cast<const float4*>(g.part_w2);
-#pragma unroll
-            for (int jj = 0; jj < 2; jj++) {                   // two rounds of 16 loads in flight
+#pragma unroll 1
+            for (int jj = 0; jj < 2; jj++) {
                 float4 pv[2][CL];
 #pragma unroll
                 for (int u = 0; u < 2; u++)
@@ -940,31 +970,30 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
                     float4 s4 = pv[u][0];
 #pragma unroll
                     for (int c = 1; c < CL; c++) { s4.x += pv[u][c].x; s4.y += pv[u][c].y; s4.z += pv[u][c].z; s4.w += pv[u][c].w; }
-                    gw[2 * jj + u] = s4;
+                    t_gw[(2 * jj + u) * THREADS + tid] = s4;
                     reinterpret_cast<float4*>(g.grad + g.off_w2)[rank * 2048 + (2 * jj + u) * 512 + tid] = s4;
                     const float x0 = s4.x * gs, x1 = s4.y * gs, x2 = s4.z * gs, x3 = s4.w * gs;
                     sq = fmaf(x0, x0, sq); sq = fmaf(x1, x1, sq); sq = fmaf(x2, x2, sq); sq = fmaf(x3, x3, sq);
                 }
             }
         }
-        // the remaining n - 65536 elements, compacted (W2 skipped): element e of that list, CTA c takes e in [c m, (c+1) m)
+        // (b) the remaining n - 65536 elements, compacted (W2 skipped): element e of that list, CTA c takes e in [c m, (c+1) m)
         const int rest = n - H * H, per = (rest + CL - 1) / CL;
         constexpr int kSlots = 6;                              // per <= 2727 (A = 9, S = 24) < 6 x 512
-        float gr[kSlots];
-        int gi[kSlots];
-#pragma unroll
+#pragma unroll 1
         for (int grp = 0; grp < 2; grp++) {                    // three elements x 8 partials in flight per round
             float pvs[3][CL];
+            int gi3[3];
 #pragma unroll
             for (int u = 0; u < 3; u++) {
                 const int j = 3 * grp + u;
                 const int e = rank * per + j * THREADS + tid;
-                gi[j] = -1;
+                gi3[u] = -1;
 #pragma unroll
                 for (int c = 0; c < CL; c++) pvs[u][c] = 0.f;
                 if (j * THREADS + tid < per && e < rest) {
                     const int i = e < g.off_w2 ? e : e + H * H;               // flat index
-                    gi[j] = i;
+                    gi3[u] = i;
                     if (i < g.off_b1) {                                       // dW1: 8 partials
 #pragma unroll
                         for (int c = 0; c < CL; c++) pvs[u][c] = __ldcg(g.part_w1 + (size_t)c * H * S + i);
@@ -990,42 +1019,12 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
                 float ssum = 0.f;
 #pragma unroll
                 for (int c = 0; c < CL; c++) ssum += pvs[u][c];
-                gr[j] = ssum;
-                if (gi[j] >= 0) {
-                    g.grad[gi[j]] = ssum;
+                t_gr[j * THREADS + tid] = ssum;
+                t_gi[j * THREADS + tid] = gi3[u];
+                if (gi3[u] >= 0) {
+                    g.grad[gi3[u]] = ssum;
                     const float x = ssum * gs;
                     sq = fmaf(x, x, sq);
-                }
-            }
-        }
-        // operands of the optimiser (m, v, theta, theta_target) for this CTA's elements: requested now, they arrive while the
-        // squared-norm partials cross the cluster
-        float4 am[4], av[4], ap[4], at[4];
-        float rm[kSlots], rv[kSlots], rp[kSlots], rt[kSlots];
-        int rtn[kSlots], rj[kSlots];
-        if (g.do_adam) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int i4 = rank * 2048 + j * 512 + tid;
-                am[j] = reinterpret_cast<const float4*>(g.m + g.off_w2)[i4];
-                av[j] = reinterpret_cast<const float4*>(g.v + g.off_w2)[i4];
-                ap[j] = reinterpret_cast<const float4*>(g.pt.main[4])[i4];
-                at[j] = reinterpret_cast<const float4*>(g.pt.target[4])[i4];
-            }
-#pragma unroll
-            for (int j = 0; j < kSlots; j++) {
-                rm[j] = rv[j] = rp[j] = rt[j] = 0.f;
-                rtn[j] = rj[j] = 0;
-                if (gi[j] >= 0) {
-                    int t = 0;
-#pragma unroll
-                    for (int k = 1; k < 14; k++) t += (gi[j] >= g.pt.offset[k]) ? 1 : 0;
-                    rtn[j] = t;
-                    rj[j] = gi[j] - g.pt.offset[t];
-                    rm[j] = g.m[gi[j]];
-                    rv[j] = g.v[gi[j]];
-                    rp[j] = g.pt.main[t][rj[j]];
-                    rt[j] = g.pt.target[t][rj[j]];
                 }
             }
         }
@@ -1065,27 +1064,37 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
             }
             __syncthreads();
             const AdamCoef c = *reinterpret_cast<const AdamCoef*>(red + 20);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
+#pragma unroll 2
+            for (int j = 0; j < 4; j++) {                      // W2: operands as float4 straight from the tensors
                 const int i4 = rank * 2048 + j * 512 + tid;
-                adam_math(gw[j].x, c, g.hp, am[j].x, av[j].x, ap[j].x, at[j].x);
-                adam_math(gw[j].y, c, g.hp, am[j].y, av[j].y, ap[j].y, at[j].y);
-                adam_math(gw[j].z, c, g.hp, am[j].z, av[j].z, ap[j].z, at[j].z);
-                adam_math(gw[j].w, c, g.hp, am[j].w, av[j].w, ap[j].w, at[j].w);
-                reinterpret_cast<float4*>(g.m + g.off_w2)[i4] = am[j];
-                reinterpret_cast<float4*>(g.v + g.off_w2)[i4] = av[j];
-                reinterpret_cast<float4*>(g.pt.main[4])[i4] = ap[j];
-                reinterpret_cast<float4*>(g.pt.target[4])[i4] = at[j];
+                float4 am = reinterpret_cast<const float4*>(g.m + g.off_w2)[i4], av = reinterpret_cast<const float4*>(g.v + g.off_w2)[i4];
+                float4 ap = reinterpret_cast<const float4*>(g.pt.main[4])[i4], at = reinterpret_cast<const float4*>(g.pt.target[4])[i4];
+                const float4 gw = t_gw[j * THREADS + tid];
+                adam_math(gw.x, c, g.hp, am.x, av.x, ap.x, at.x);
+                adam_math(gw.y, c, g.hp, am.y, av.y, ap.y, at.y);
+                adam_math(gw.z, c, g.hp, am.z, av.z, ap.z, at.z);
+                adam_math(gw.w, c, g.hp, am.w, av.w, ap.w, at.w);
+                reinterpret_cast<float4*>(g.m + g.off_w2)[i4] = am;
+                reinterpret_cast<float4*>(g.v + g.off_w2)[i4] = av;
+                reinterpret_cast<float4*>(g.pt.main[4])[i4] = ap;
+                reinterpret_cast<float4*>(g.pt.target[4])[i4] = at;
             }
+#pragma unroll 3
+            for (int j = 0; j < kSlots; j++) {
+                const int i = t_gi[j * THREADS + tid];
+                if (i >= 0) {
+                    int t = 0;
 #pragma unroll
-            for (int j = 0; j < kSlots; j++)
-                if (gi[j] >= 0) {
-                    adam_math(gr[j], c, g.hp, rm[j], rv[j], rp[j], rt[j]);
-                    g.m[gi[j]] = rm[j];
-                    g.v[gi[j]] = rv[j];
-                    g.pt.main[rtn[j]][rj[j]] = rp[j];
-                    g.pt.target[rtn[j]][rj[j]] = rt[j];
+                    for (int k = 1; k < 14; k++) t += (i >= g.pt.offset[k]) ? 1 : 0;
+                    const int jj = i - g.pt.offset[t];
+                    float rm = g.m[i], rv = g.v[i], rp = g.pt.main[t][jj], rt = g.pt.target[t][jj];
+                    adam_math(t_gr[j * THREADS + tid], c, g.hp, rm, rv, rp, rt);
+                    g.m[i] = rm;
+                    g.v[i] = rv;
+                    g.pt.main[t][jj] = rp;
+                    g.pt.target[t][jj] = rt;
                 }
+            }
         } else if (rank == 0 && tid == 0 && g.loss != nullptr) {
             float l = 0.f;
             for (int cc = 0; cc < CL; cc++) l += __ldcg(g.part_loss + cc);
@@ -1129,24 +1138,40 @@ int learn_cluster_prepare(LearnCluster* lcw, int S, int A) {
     lcw->part_hb = p; p += lc::CL * 64;
     lcw->part_loss = p; p += lc::CL;
     lcw->yflag = reinterpret_cast<unsigned*>(p);
+    RLOA_CUDA(cudaEventCreateWithFlags(&lcw->pack_done, cudaEventDisableTiming));
+    RLOA_CUDA(cudaEventCreateWithFlags(&lcw->pack_fork, cudaEventDisableTiming));
     return RLOA_OK;
 }
 
 void learn_cluster_free(LearnCluster* lcw) {
+    if (lcw->pack_done) cudaEventDestroy(lcw->pack_done);
+    if (lcw->pack_fork) cudaEventDestroy(lcw->pack_fork);
     if (lcw->images) cudaFree(lcw->images);
     if (lcw->block) cudaFree(lcw->block);
     *lcw = LearnCluster{};
 }
 
-int learn_cluster_step(LearnCluster* lcw, const rloa_naf_params* mn, const rloa_naf_params* tg, const rloa_adam_state* adam,
-                       const float* states, const float* actions, const float* rewards, const float* next_states,
-                       const float* dones, int B, const rloa_naf_hyper* hp, const ParamTable& pt, const int* flat_offsets,
-                       float* grad, float* loss, float* gnorm, int do_adam, cudaStream_t st) {
+int learn_cluster_pack(LearnCluster* lcw, const rloa_naf_params* mn, const rloa_naf_params* tg, cudaStream_t st) {
     RLOA_REQUIRE(lcw->images != nullptr, "learn cluster: not prepared");
-    const int S = mn->state_size, A = mn->action_size;
     const int pack_threads = lc::H * lc::H / 8 + lc::NHP * lc::H / 8 + lc::H * lc::KP / 4 + lc::H;
     learn_pack_kernel<<<dim3((pack_threads + 255) / 256, 2), 256, 0, st>>>(*tg, *mn, static_cast<uint8_t*>(lcw->images));
     RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
+int learn_cluster_step(LearnCluster* lcw, const rloa_naf_params* mn, const rloa_naf_params* tg, const rloa_adam_state* adam,
+                       const float* states, const float* actions, const float* rewards, const float* next_states,
+                       const float* dones, int B, const rloa_naf_hyper* hp, const ParamTable& pt, const int* flat_offsets,
+                       float* grad, float* loss, float* gnorm, int do_adam, const LearnClusterReplay* replay, cudaStream_t st) {
+    RLOA_REQUIRE(lcw->images != nullptr, "learn cluster: not prepared");
+    const int S = mn->state_size, A = mn->action_size;
+    if (lcw->prepacked) {            // rloa_naf_learn_prepack already wrote the images on the side stream: join it
+        RLOA_CUDA(cudaStreamWaitEvent(st, lcw->pack_done, 0));
+        lcw->prepacked = false;
+    } else {
+        const int rc = learn_cluster_pack(lcw, mn, tg, st);
+        if (rc != RLOA_OK) return rc;
+    }
     LearnClusterArgs a{};
     a.images = static_cast<const uint8_t*>(lcw->images);
     a.p[0] = *tg; a.p[1] = *mn;
@@ -1165,6 +1190,12 @@ int learn_cluster_step(LearnCluster* lcw, const rloa_naf_params* mn, const rloa_
     a.off_wl = flat_offsets[12]; a.off_bl = flat_offsets[13]; a.n_params = flat_offsets[14];
     a.dbg = lcw->dbg;
     a.prof = lcw->prof;
+    if (replay != nullptr) {
+        a.use_replay = 1;
+        a.rb = *replay->rb;
+        a.rs_seed = replay->seed; a.rs_draw = replay->draw;
+        a.rs_draw_offset = reinterpret_cast<const unsigned long long*>(replay->draw_offset);
+    }
     naf_learn_cluster_kernel<<<2 * lc::CL, lc::THREADS, lc::SMEM_BYTES, st>>>(a);
     RLOA_LAUNCHED();
     return RLOA_OK;

@@ -15,6 +15,14 @@ struct LearnCluster {
     unsigned* yflag = nullptr;
     float* dbg = nullptr;            // optional intermediate dump (tests)
     long long* prof = nullptr;       // optional clock64 phase stamps
+    bool prepacked = false;          // rloa_naf_learn_prepack wrote the images on a side stream; the next learn joins pack_done
+    cudaEvent_t pack_done = nullptr, pack_fork = nullptr;
+};
+
+struct LearnClusterReplay {          // fused ReplayBuffer.sample: the kernel reads its rows straight from the ring
+    const rloa_replay* rb;
+    uint64_t seed, draw;
+    const uint64_t* draw_offset;
 };
 
 bool learn_cluster_supported(int S, int A, int H, int B);
@@ -24,6 +32,8 @@ void learn_cluster_free(LearnCluster* lc);
 int learn_cluster_step(LearnCluster* lc, const rloa_naf_params* mn, const rloa_naf_params* tg, const rloa_adam_state* adam,
                        const float* states, const float* actions, const float* rewards, const float* next_states,
                        const float* dones, int B, const rloa_naf_hyper* hp, const ParamTable& pt, const int* flat_offsets,
-                       float* grad, float* loss, float* gnorm, int do_adam, cudaStream_t st);
+                       float* grad, float* loss, float* gnorm, int do_adam, const LearnClusterReplay* replay, cudaStream_t st);
+// the weight images of both networks (what learn_cluster_step does first unless a prepack is pending)
+int learn_cluster_pack(LearnCluster* lc, const rloa_naf_params* mn, const rloa_naf_params* tg, cudaStream_t st);
 
 }  // namespace rloa

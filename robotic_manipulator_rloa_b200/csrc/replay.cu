@@ -6,6 +6,7 @@
 // (k distinct slots, no rejection table, no host round trip), and the np.stack / .to(device) copies
 // (replay_buffer.py:57-65) become one gather kernel.
 #include "common.cuh"
+#include "replay_sample.cuh"
 
 namespace rloa {
 
@@ -128,22 +129,6 @@ replay_append_kernel(rloa_replay rb, int n, const float* __restrict__ states, co
     }
 }
 
-__device__ __forceinline__ uint32_t mix32(uint32_t x) {
-    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
-    return x;
-}
-// keyed bijection of [0, 2^bits): 6-round Feistel over (hi: bits - bits/2, lo: bits/2) with alternating halves
-__device__ __forceinline__ uint32_t feistel(uint32_t x, int bits, uint32_t k0, uint32_t k1) {
-    const int lb = bits >> 1, hb = bits - lb;
-    uint32_t lo = x & ((1u << lb) - 1u), hi = x >> lb;
-#pragma unroll
-    for (int r = 0; r < 6; r++) {
-        if ((r & 1) == 0) hi = (hi ^ mix32(lo * 0x9E3779B9u + k0 + r)) & ((1u << hb) - 1u);
-        else lo = (lo ^ mix32(hi * 0x7FEB352Du + k1 + r)) & ((1u << lb) - 1u);
-    }
-    return (hi << lb) | lo;
-}
-
 __global__ void __launch_bounds__(256)
 replay_sample_kernel(rloa_replay rb, int batch, unsigned long long seed, unsigned long long draw0,
                      const unsigned long long* __restrict__ draw_offset, float* __restrict__ states, float* __restrict__ actions, float* __restrict__ rewards,
@@ -151,19 +136,8 @@ replay_sample_kernel(rloa_replay rb, int batch, unsigned long long seed, unsigne
     const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= batch) return;
     const unsigned long long draw = draw0 + (draw_offset != nullptr ? *draw_offset : 0ull);
-    const long long cur = *rb.cursor;
-    const uint32_t live = (uint32_t)(cur < rb.capacity ? cur : rb.capacity);
-    if (live == 0) return;
-    int bits = 1;
-    while ((1u << bits) < live) bits++;
-    if (bits < 2) bits = 2;
-    const uint32_t k0 = mix32((uint32_t)seed ^ mix32((uint32_t)draw)), k1 = mix32((uint32_t)(seed >> 32) + 0x68E31DA4u ^ (uint32_t)(draw >> 32) ^ k0);
-    uint32_t x = (uint32_t)warp % live;
-    do {
-        x = feistel(x, bits, k0, k1);
-    } while (x >= live);                          // cycle walking keeps the map a bijection of [0, live)
-    // x counts from the oldest live transition, like indexing the deque
-    const size_t slot = (size_t)(((cur < rb.capacity ? 0 : cur) + x) % rb.capacity);
+    if (*rb.cursor <= 0) return;
+    const size_t slot = replay_sample_slot(rb, warp, seed, draw);
     const int S = rb.state_size, A = rb.action_size;
     for (int k = lane; k < S; k += 32) {
         states[(size_t)warp * S + k] = rb.states[slot * S + k];

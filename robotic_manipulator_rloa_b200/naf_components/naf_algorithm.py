@@ -266,10 +266,37 @@ class NAFAgent:
                 self.learn_from_memory(tick=tick, sub=u)
 
     def learn_from_memory(self, tick: Optional[torch.Tensor] = None, sub: int = 0) -> None:
-        """sample + learn without leaving the device (replay_buffer.py:47-67 + naf_algorithm.py:180-213)."""
+        """sample + learn without leaving the device (replay_buffer.py:47-67 + naf_algorithm.py:180-213).  With the tensor-core
+        trunk and a batch of at most 1024 rows this is ONE kernel: the fused learn kernel draws the sampler's slots itself
+        and reads its rows straight from the ring (rloa_naf_learn_step_replay)."""
         b = self._learn_buffers()
+        m = self.memory
+        ws = self._workspace(self.batch_size)
+        if self.fused_learn and m._rb is not None and ws.lib.rloa_naf_learn_fused_supported(ws.handle, self.batch_size):
+            hp = self._hyper()
+            pm, pt = self.qnetwork_main.native_params(), self.qnetwork_target.native_params()
+            adam = self.optimizer.native()
+            xchg = self._exchange()
+            draw = m._draws if tick is None else (int(sub) << 32)
+            N.check(ws.lib.rloa_naf_learn_step_replay(ws.handle, C.byref(pm), C.byref(pt), C.byref(adam),
+                                                      xchg.handle if xchg is not None else None, C.byref(m._rb), m.seed, draw,
+                                                      N.ptr(tick), self.batch_size, C.byref(hp), b['grad'].data_ptr(),
+                                                      b['loss'].data_ptr(), b['gnorm'].data_ptr(), self._stream()),
+                    'rloa_naf_learn_step_replay')
+            m._draws += 1
+            self.last_loss, self.last_grad_norm = b['loss'], b['gnorm']
+            return
         self.memory.sample_into(b['s'], b['a'], b['r'], b['s2'], b['d'], tick=tick, sub=sub)
         self._learn_device(b['s'], b['a'], b['r'], b['s2'], b['d'])
+
+    def prepack(self) -> None:
+        """Start writing the tensor-core weight images of the next learn() on the workspace's side stream (a no-op on the
+        fp32 / multi-launch paths).  The parameters must not be modified between this call and that learn()."""
+        if self._ws is None or not self.qnetwork_main.trunk_mode:
+            return
+        pm, pt = self.qnetwork_main.native_params(), self.qnetwork_target.native_params()
+        N.check(self._ws.lib.rloa_naf_learn_prepack(self._ws.handle, C.byref(pm), C.byref(pt), self._stream()),
+                'rloa_naf_learn_prepack')
 
     def learn(self, experiences: Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]) -> None:
         """Reference signature: a 5-tuple of tensors as ReplayBuffer.sample returns them."""
@@ -500,6 +527,8 @@ class VectorLoop:
     def _body(self, auto_reset: bool, learn_now: bool, parity: int) -> None:
         a, env = self.agent, self.env
         self._mark(parity, 0)
+        if learn_now:             # the weights are final since the last update: their images are written beside act / step
+            a.prepack()
         a.act_batch(self.state, out=self.actions, tick=self.tick)
         self._mark(parity, 1)
         env.sim.step(self.actions, out=(self.next_state, self.reward, self.done), valid=self.valid)

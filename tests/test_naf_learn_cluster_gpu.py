@@ -234,3 +234,31 @@ def test_cluster_learn_is_deterministic_and_graph_capturable():
     torch.cuda.synchronize()
     got = torch.cat([p.detach().reshape(-1) for p in agent.qnetwork_main.parameters()])
     assert torch.equal(got, outs[0])
+
+
+def test_fused_replay_sampling_equals_sample_then_learn():
+    """rloa_naf_learn_step_replay (the kernel draws the sampler's slots and reads the ring itself) against
+    ReplayBuffer.sample_into + learn on the sampled copy: same slots, same kernel, bit-identical parameters; a prepack
+    issued before the call changes nothing either."""
+    agents = []
+    for variant in range(3):
+        agent, _, _ = make_agent(batch=256)
+        g = torch.Generator().manual_seed(5)
+        n = 900
+        s = torch.randn(n, S, generator=g); s2 = s + 0.1 * torch.randn(n, S, generator=g)
+        a = torch.clamp(torch.randn(n, A, generator=g) * 1.5, -1, 1); r = -torch.rand(n, generator=g)
+        d = torch.zeros(n, dtype=torch.uint8)
+        agent.memory.add_batch(s.to(DEV), a.to(DEV), r.to(DEV), s2.to(DEV), d.to(DEV))
+        for step in range(3):
+            if variant == 0:                       # fused: one kernel samples and learns
+                agent.learn_from_memory()
+            elif variant == 1:                     # prepack first, then fused
+                agent.prepack()
+                agent.learn_from_memory()
+            else:                                  # sample into buffers, learn on the copy
+                b = agent._learn_buffers()
+                agent.memory.sample_into(b['s'], b['a'], b['r'], b['s2'], b['d'])
+                agent._learn_device(b['s'], b['a'], b['r'], b['s2'], b['d'])
+        torch.cuda.synchronize()
+        agents.append(torch.cat([p.detach().reshape(-1) for p in agent.qnetwork_main.parameters()]).clone())
+    assert torch.equal(agents[0], agents[2]) and torch.equal(agents[1], agents[2])

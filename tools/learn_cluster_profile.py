@@ -9,7 +9,8 @@ import numpy as np, torch
 from robotic_manipulator_rloa_b200 import _native as N
 from test_naf_learn_cluster_gpu import make_agent, make_batch
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+B = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 1024
+FLUSH = 'flush' in sys.argv          # 256 MiB fill before the stamped launch: cold L2, as between bench.py's timed pairs
 agent, _, _ = make_agent(batch=B)
 s, a, r, s2, d = make_batch(B, seed=1)
 f = lambda t: t.to(device='cuda', dtype=torch.float32).contiguous()
@@ -19,6 +20,9 @@ for _ in range(5):
 stamps = torch.zeros(16, 32, dtype=torch.int64, device='cuda')
 N.check(agent._ws.lib.rloa_naf_ws_set_debug(agent._ws.handle, None, stamps.data_ptr()), 'dbg')
 for _ in range(3):
+    agent._learn_device(*args)
+if FLUSH:
+    torch.empty(256 << 20, dtype=torch.uint8, device='cuda').fill_(1)
     agent._learn_device(*args)
 torch.cuda.synchronize()
 N.check(agent._ws.lib.rloa_naf_ws_set_debug(agent._ws.handle, None, None), 'dbg')
