@@ -22,41 +22,12 @@
 #include <new>
 
 #include "common.cuh"
+#include "grad_exchange.cuh"
 #include "optim.cuh"
 
 namespace rloa {
 
-constexpr int kXchgMaxWorld = 16;
 constexpr int kXchgBlocks = kNormBlocks;   // one partial per block feeds adam_coefficients; all blocks co-resident (80 <= 148 SMs)
-constexpr long long kXchgTimeoutCycles = 4000000000ll;      // ~2 s at 1.9 GHz
-
-struct XchgPeers {
-    const float* grad[kXchgMaxWorld];                        // mapped peer blocks (own block at index rank)
-    unsigned long long* ready[kXchgMaxWorld];                // ready[r] = slot array in rank r's block (write slot `rank`)
-    unsigned long long* done[kXchgMaxWorld];
-    int world, rank;
-};
-
-__device__ __forceinline__ unsigned long long ld_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// peer data loads: system-scope (never served from a stale line), volatile so they stay below the flag wait, but
-// without a memory clobber so a batch of them is issued back to back and the NVLink round trips overlap
-__device__ __forceinline__ float ld_peer_f32(const float* p) {
-    float v;
-    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float4 ld_peer_f32x4(const float* p) {
-    float4 v;
-    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
 
 // thread 0 of the block spins until slot r of the LOCAL flag array is >= want for every peer r != rank
 __device__ __forceinline__ bool wait_peers(const unsigned long long* local_flags, int world, int rank,
@@ -218,14 +189,16 @@ struct rloa_xchg {
     bool connected = false;
 };
 
-static size_t xchg_flag_offset(int n) { return (((size_t)n * sizeof(float)) + 255) & ~(size_t)255; }
+// block layout: [ n floats: this rank's gradient, pulled by the peers (whole-gradient kernels) | kXchgPushRegions x n floats:
+// region s = the gradient rank s PUSHED here (fused learn kernel) | ready flags | done flags ]
+static size_t xchg_flag_offset(int n) { return (((size_t)n * (1 + kXchgPushRegions) * sizeof(float)) + 255) & ~(size_t)255; }
 
 extern "C" int rloa_xchg_create(int32_t n_floats, rloa_xchg** out) {
     RLOA_REQUIRE(out != nullptr && n_floats >= 1, "rloa_xchg_create: bad argument");
     rloa_xchg* x = new (std::nothrow) rloa_xchg();
     RLOA_REQUIRE(x != nullptr, "rloa_xchg_create: out of host memory");
     x->n = n_floats;
-    const size_t bytes = xchg_flag_offset(n_floats) + 2 * kXchgMaxWorld * sizeof(unsigned long long);
+    const size_t bytes = xchg_flag_offset(n_floats) + 2 * kXchgSlices * kXchgMaxWorld * sizeof(unsigned long long);
     if (cudaMalloc(&x->block, bytes) != cudaSuccess || cudaMalloc(&x->sum, (size_t)n_floats * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&x->tickets, 4 * sizeof(unsigned)) != cudaSuccess || cudaMalloc(&x->status, sizeof(int)) != cudaSuccess ||
         cudaMalloc(&x->sq_partial, kXchgBlocks * sizeof(float)) != cudaSuccess) {
@@ -271,7 +244,7 @@ extern "C" int rloa_xchg_connect(rloa_xchg* x, int32_t rank, int32_t world, cons
         uint8_t* b = static_cast<uint8_t*>(base);
         x->peers.grad[r] = reinterpret_cast<const float*>(b);
         x->peers.ready[r] = reinterpret_cast<unsigned long long*>(b + fo);
-        x->peers.done[r] = reinterpret_cast<unsigned long long*>(b + fo + kXchgMaxWorld * sizeof(unsigned long long));
+        x->peers.done[r] = reinterpret_cast<unsigned long long*>(b + fo + kXchgSlices * kXchgMaxWorld * sizeof(unsigned long long));
     }
     x->peers.world = world;
     x->peers.rank = rank;
@@ -301,6 +274,12 @@ extern "C" void rloa_xchg_destroy(rloa_xchg* x) {
 
 // used by rloa_naf_learn_apply_xchg (naf.cu): publish, then exchange + clip + Adam + soft update in one kernel
 namespace rloa {
+void xchg_peers(const rloa_xchg* x, XchgPeers* out, int** status) {
+    *out = x->peers;
+    *status = x->status;
+}
+int xchg_connected_world(const rloa_xchg* x) { return (x != nullptr && x->connected) ? x->world : 0; }
+
 int xchg_exchange_adam(rloa_xchg* x, float* local_grad, const ReduceArgs& deferred, const ParamTable& pt, float* m, float* v,
                        int64_t* step_ptr, const rloa_naf_hyper& hp, float* grad_norm, cudaStream_t st) {
     RLOA_REQUIRE(x != nullptr && x->connected, "gradient exchange: rloa_xchg_connect was not called");

@@ -18,6 +18,7 @@
 #include "bn_fuse.cuh"
 #include "naf_trunk_tc.cuh"
 #include "naf_learn_cluster.cuh"
+#include "grad_exchange.cuh"
 #include "optim.cuh"
 #include "philox.cuh"
 
@@ -1360,7 +1361,7 @@ static bool cluster_learn_applies(const rloa_naf_ws* ws, int batch) {
 static int cluster_learn(rloa_naf_ws* ws, const rloa_naf_params* mn, const rloa_naf_params* tg, const rloa_adam_state* adam,
                          const float* states, const float* actions, const float* rewards, const float* next_states,
                          const float* dones, int32_t batch, const rloa_naf_hyper* hp, float* grad, float* loss, float* gnorm,
-                         int do_adam, void* stream, const LearnClusterReplay* replay = nullptr) {
+                         int do_adam, void* stream, const LearnClusterReplay* replay = nullptr, const rloa_xchg* xchg = nullptr) {
     RLOA_REQUIRE(ws && hp && grad && (replay != nullptr || (states && actions && rewards && next_states)), "rloa_naf_learn: null argument");
     RLOA_REQUIRE(!(hp->use_done_mask && dones == nullptr && replay == nullptr), "rloa_naf_learn: use_done_mask needs dones");
     int rc = check_params(ws, mn, "rloa_naf_learn(main)");
@@ -1372,7 +1373,7 @@ static int cluster_learn(rloa_naf_ws* ws, const rloa_naf_params* mn, const rloa_
     ParamTable pt;
     fill_param_table(mn, tg, &pt);
     return learn_cluster_step(&ws->lc, mn, tg, adam, states, actions, rewards, next_states, dones, batch, hp, pt, offs, grad, loss,
-                              gnorm, do_adam, replay, as_stream(stream));
+                              gnorm, do_adam, replay, xchg, as_stream(stream));
 }
 
 // forward of both nets, loss, backward.  With defer != NULL the final split-K reduction is NOT launched: its
@@ -1608,7 +1609,10 @@ extern "C" int rloa_naf_learn_step_xchg(rloa_naf_ws* ws, const rloa_naf_params* 
                                         const float* dones, int32_t batch, const rloa_naf_hyper* hp, float* grad, float* loss,
                                         float* grad_norm, void* stream) {
     RLOA_REQUIRE(adam && xchg && adam->m && adam->v && adam->step, "rloa_naf_learn_step_xchg: null argument");
-    if (ws != nullptr && cluster_learn_applies(ws, batch)) {     // the cluster kernel leaves the complete local gradient
+    if (ws != nullptr && cluster_learn_applies(ws, batch)) {
+        if (xchg_connected_world(xchg) <= kLearnClusterMaxWorld)       // the exchange runs inside the cluster kernel's tail
+            return cluster_learn(ws, mn, tg, adam, states, actions, rewards, next_states, dones, batch, hp, grad, loss, grad_norm, 1,
+                                 stream, nullptr, xchg);
         int rcc = cluster_learn(ws, mn, tg, nullptr, states, actions, rewards, next_states, dones, batch, hp, grad, loss, nullptr, 0, stream);
         if (rcc != RLOA_OK) return rcc;
         ParamTable ptc;
@@ -1654,8 +1658,8 @@ extern "C" int rloa_naf_learn_step_replay(rloa_naf_ws* ws, const rloa_naf_params
                  "use rloa_replay_sample + rloa_naf_learn_step otherwise");
     RLOA_REQUIRE(rb->state_size == ws->S && rb->action_size == ws->A, "rloa_naf_learn_step_replay: replay row layout does not match the network");
     const LearnClusterReplay rp{rb, seed, draw, draw_offset};
-    if (xchg == nullptr)
-        return cluster_learn(ws, mn, tg, adam, nullptr, nullptr, nullptr, nullptr, nullptr, batch, hp, grad, loss, grad_norm, 1, stream, &rp);
+    if (xchg == nullptr || xchg_connected_world(xchg) <= kLearnClusterMaxWorld)
+        return cluster_learn(ws, mn, tg, adam, nullptr, nullptr, nullptr, nullptr, nullptr, batch, hp, grad, loss, grad_norm, 1, stream, &rp, xchg);
     int rc = cluster_learn(ws, mn, tg, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, batch, hp, grad, loss, nullptr, 0, stream, &rp);
     if (rc != RLOA_OK) return rc;
     ParamTable pt;

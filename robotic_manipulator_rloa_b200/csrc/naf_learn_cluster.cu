@@ -32,6 +32,7 @@
 
 #include "common.cuh"
 #include "bn_fuse.cuh"
+#include "grad_exchange.cuh"
 #include "naf_learn_cluster.cuh"
 #include "optim.cuh"
 #include "replay_sample.cuh"
@@ -136,6 +137,13 @@ struct LearnClusterArgs {
     long long* prof;                        // optional: [16 CTAs][32] clock64 phase stamps
     // fused ReplayBuffer.sample: row i of the batch is ring slot replay_sample_slot(rb, i, seed, draw + *draw_offset), read
     // straight from the ring (states / actions / rewards / next_states / dones above are unused then)
+    // N > 1 ranks: the gradient exchange over NVLink peer memory INSIDE the tail — CTA c owns slice c of the flat gradient
+    // on every rank; it STORES its local sums into region (1 + rank) of every rank's exchange block (posted writes through
+    // the mapped peer pointers), pushes a ready flag behind them, waits for the peers' flags, and sums the slice over the
+    // ranks in rank order from its own block — no NVLink read round trip on the critical path
+    int use_xchg;
+    XchgPeers xp;
+    int* xstatus;
     int use_replay;
     rloa_replay rb;
     unsigned long long rs_seed, rs_draw;
@@ -484,6 +492,7 @@ __device__ __forceinline__ void lc_dz_to_tile(const LcCtx& c, int layer, uint32_
     }
 }
 
+constexpr int kXchgInKernelWorld = 8;      // ranks the in-kernel exchange keeps in flight per round (one NVSwitch box)
 struct TrueT { static constexpr bool value = true; };
 struct FalseT { static constexpr bool value = false; };
 
@@ -955,6 +964,37 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
         float4* t_gw = reinterpret_cast<float4*>(sm + R1);                    // [4][512] summed dW2 elements of this thread
         float* t_gr = reinterpret_cast<float*>(sm + R1 + 32768);              // [6][512] summed other elements
         int* t_gi = reinterpret_cast<int*>(sm + R1 + 32768 + 12288);          // [6][512] their flat indices (-1: none)
+        // N > 1: local sums go to this rank's exchange block (peers read them); before the first write every peer must have
+        // finished reading the block for the previous update (normally long true)
+        const bool xch = g.use_xchg != 0;
+        const int me = g.xp.rank, world = g.xp.world;
+        const unsigned long long tstep = xch ? (unsigned long long)(*g.step) + 1ull : 0ull;
+        __shared__ int s_xbad;
+        auto wait_flags = [&](const unsigned long long* local, unsigned long long want) {
+            if (tid == 0) {
+                const long long t0 = clock64();
+                bool ok = true;
+                for (int rr = 0; rr < world && ok; rr++) {
+                    if (rr == me) continue;
+                    while (ld_sys(local + rank * kXchgMaxWorld + rr) < want)
+                        if (clock64() - t0 > kXchgTimeoutCycles) { ok = false; break; }
+                }
+                if (!ok) atomicExch(g.xstatus, 1);
+                __threadfence_system();
+            }
+            __syncthreads();
+        };
+        auto push_flags = [&](unsigned long long* const* remote, unsigned long long val) {      // after a __syncthreads
+            if (tid == 0) {
+                __threadfence_system();
+                for (int rr = 0; rr < world; rr++)
+                    if (rr != me) st_sys(remote[rr] + rank * kXchgMaxWorld + me, val);
+            }
+        };
+        // push model: this rank's local sums are STORED into region (1 + me) of every rank's exchange block (posted NVLink
+        // writes, no round trip); the cross-rank sum then reads only local memory
+        const size_t xreg = (size_t)(1 + me) * (size_t)g.n_params;
+        if (xch) wait_flags(g.xp.done[me], tstep - 1ull);
         float sq = 0.f;
         {   // (a) this CTA's eighth of dW2 (16384 float4 in all, 2048 per CTA, 4 per thread): two rounds of 16 loads in flight
             const float4* pw = reinterpret_cast<const float4*>(g.part_w2);
@@ -971,7 +1011,14 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
 #pragma unroll
                     for (int c = 1; c < CL; c++) { s4.x += pv[u][c].x; s4.y += pv[u][c].y; s4.z += pv[u][c].z; s4.w += pv[u][c].w; }
                     t_gw[(2 * jj + u) * THREADS + tid] = s4;
-                    reinterpret_cast<float4*>(g.grad + g.off_w2)[rank * 2048 + (2 * jj + u) * 512 + tid] = s4;
+                    if (xch) {
+#pragma unroll
+                        for (int rr = 0; rr < kXchgInKernelWorld; rr++)
+                            if (rr < world)
+                                reinterpret_cast<float4*>(const_cast<float*>(g.xp.grad[rr]) + xreg + g.off_w2)[rank * 2048 + (2 * jj + u) * 512 + tid] = s4;
+                    } else {
+                        reinterpret_cast<float4*>(g.grad + g.off_w2)[rank * 2048 + (2 * jj + u) * 512 + tid] = s4;
+                    }
                     const float x0 = s4.x * gs, x1 = s4.y * gs, x2 = s4.z * gs, x3 = s4.w * gs;
                     sq = fmaf(x0, x0, sq); sq = fmaf(x1, x1, sq); sq = fmaf(x2, x2, sq); sq = fmaf(x3, x3, sq);
                 }
@@ -1022,11 +1069,73 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
                 t_gr[j * THREADS + tid] = ssum;
                 t_gi[j * THREADS + tid] = gi3[u];
                 if (gi3[u] >= 0) {
-                    g.grad[gi3[u]] = ssum;
+                    if (xch) {
+#pragma unroll
+                        for (int rr = 0; rr < kXchgInKernelWorld; rr++)
+                            if (rr < world) const_cast<float*>(g.xp.grad[rr])[xreg + gi3[u]] = ssum;
+                    } else {
+                        g.grad[gi3[u]] = ssum;
+                    }
                     const float x = ssum * gs;
                     sq = fmaf(x, x, sq);
                 }
             }
+        }
+        if (xch) {
+            __syncthreads();
+            push_flags(g.xp.ready, tstep);
+            wait_flags(g.xp.ready[me], tstep);
+            sq = 0.f;
+            // all ranks' contributions now sit in THIS rank's block: local loads, all in flight, summed in rank order
+            const float* xl = g.xp.grad[me];
+            const size_t np = (size_t)g.n_params;
+#pragma unroll 1
+            for (int jj = 0; jj < 2; jj++) {
+                float4 pv[2][kXchgInKernelWorld];
+#pragma unroll
+                for (int u = 0; u < 2; u++)
+#pragma unroll
+                    for (int rr = 0; rr < kXchgInKernelWorld; rr++)
+                        if (rr < world)
+                            pv[u][rr] = __ldcg(reinterpret_cast<const float4*>(xl + (size_t)(1 + rr) * np + g.off_w2) + rank * 2048 + (2 * jj + u) * 512 + tid);
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int j = 2 * jj + u, i4 = rank * 2048 + j * 512 + tid;
+                    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int rr = 0; rr < kXchgInKernelWorld; rr++)      // rank order: the same bits on every rank
+                        if (rr < world) { s4.x += pv[u][rr].x; s4.y += pv[u][rr].y; s4.z += pv[u][rr].z; s4.w += pv[u][rr].w; }
+                    t_gw[j * THREADS + tid] = s4;
+                    reinterpret_cast<float4*>(g.grad + g.off_w2)[i4] = s4;
+                    const float x0 = s4.x * gs, x1 = s4.y * gs, x2 = s4.z * gs, x3 = s4.w * gs;
+                    sq = fmaf(x0, x0, sq); sq = fmaf(x1, x1, sq); sq = fmaf(x2, x2, sq); sq = fmaf(x3, x3, sq);
+                }
+            }
+            {
+                float pr[kSlots][kXchgInKernelWorld];
+                int ii[kSlots];
+#pragma unroll
+                for (int j = 0; j < kSlots; j++) {
+                    ii[j] = t_gi[j * THREADS + tid];
+#pragma unroll
+                    for (int rr = 0; rr < kXchgInKernelWorld; rr++)
+                        pr[j][rr] = (ii[j] >= 0 && rr < world) ? __ldcg(xl + (size_t)(1 + rr) * np + ii[j]) : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < kSlots; j++)
+                    if (ii[j] >= 0) {
+                        float ssum = 0.f;
+#pragma unroll
+                        for (int rr = 0; rr < kXchgInKernelWorld; rr++)
+                            if (rr < world) ssum += pr[j][rr];
+                        t_gr[j * THREADS + tid] = ssum;
+                        g.grad[ii[j]] = ssum;
+                        const float x = ssum * gs;
+                        sq = fmaf(x, x, sq);
+                    }
+            }
+            __syncthreads();
+            push_flags(g.xp.done, tstep);                      // the peers' blocks are not read any more for this update
         }
         stamp(19);
         // squared norm: warp tree, warps in order, CTAs in rank order over DSMEM
@@ -1062,10 +1171,13 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
                     }
                 }
             }
+            if (tid == 0) s_xbad = xch ? *reinterpret_cast<volatile int*>(g.xstatus) : 0;
             __syncthreads();
             const AdamCoef c = *reinterpret_cast<const AdamCoef*>(red + 20);
+            // a wait that gave up (now or in an earlier update: the flag is sticky) means a peer's gradient may be stale:
+            // nobody applies the update, so the ranks stop instead of drifting apart; rloa_xchg_status reports it
 #pragma unroll 2
-            for (int j = 0; j < 4; j++) {                      // W2: operands as float4 straight from the tensors
+            for (int j = 0; j < (s_xbad ? 0 : 4); j++) {       // W2: operands as float4 straight from the tensors
                 const int i4 = rank * 2048 + j * 512 + tid;
                 float4 am = reinterpret_cast<const float4*>(g.m + g.off_w2)[i4], av = reinterpret_cast<const float4*>(g.v + g.off_w2)[i4];
                 float4 ap = reinterpret_cast<const float4*>(g.pt.main[4])[i4], at = reinterpret_cast<const float4*>(g.pt.target[4])[i4];
@@ -1081,7 +1193,7 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
             }
 #pragma unroll 3
             for (int j = 0; j < kSlots; j++) {
-                const int i = t_gi[j * THREADS + tid];
+                const int i = s_xbad ? -1 : t_gi[j * THREADS + tid];
                 if (i >= 0) {
                     int t = 0;
 #pragma unroll
@@ -1104,7 +1216,7 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
     stamp(21);
     // a CTA's shared memory must outlive every DSMEM read of it; the step counter moves after everybody has read it
     cluster_sync_all();
-    if (net == 1 && g.do_adam && rank == 0 && tid == 0) *g.step += 1;
+    if (net == 1 && g.do_adam && rank == 0 && tid == 0) *g.step += 1;      // also after a timed-out exchange: the flags count updates
     fence_before_sync();
     __syncthreads();
     stamp(22);
@@ -1162,7 +1274,8 @@ int learn_cluster_pack(LearnCluster* lcw, const rloa_naf_params* mn, const rloa_
 int learn_cluster_step(LearnCluster* lcw, const rloa_naf_params* mn, const rloa_naf_params* tg, const rloa_adam_state* adam,
                        const float* states, const float* actions, const float* rewards, const float* next_states,
                        const float* dones, int B, const rloa_naf_hyper* hp, const ParamTable& pt, const int* flat_offsets,
-                       float* grad, float* loss, float* gnorm, int do_adam, const LearnClusterReplay* replay, cudaStream_t st) {
+                       float* grad, float* loss, float* gnorm, int do_adam, const LearnClusterReplay* replay, const rloa_xchg* xchg,
+                       cudaStream_t st) {
     RLOA_REQUIRE(lcw->images != nullptr, "learn cluster: not prepared");
     const int S = mn->state_size, A = mn->action_size;
     if (lcw->prepacked) {            // rloa_naf_learn_prepack already wrote the images on the side stream: join it
@@ -1190,6 +1303,12 @@ int learn_cluster_step(LearnCluster* lcw, const rloa_naf_params* mn, const rloa_
     a.off_wl = flat_offsets[12]; a.off_bl = flat_offsets[13]; a.n_params = flat_offsets[14];
     a.dbg = lcw->dbg;
     a.prof = lcw->prof;
+    if (xchg != nullptr) {
+        RLOA_REQUIRE(do_adam != 0 && xchg_connected_world(xchg) >= 1 && xchg_connected_world(xchg) <= kXchgInKernelWorld,
+                     "learn cluster: the in-kernel exchange needs a connected handle of at most 8 ranks and the optimiser");
+        a.use_xchg = 1;
+        xchg_peers(xchg, &a.xp, &a.xstatus);
+    }
     if (replay != nullptr) {
         a.use_replay = 1;
         a.rb = *replay->rb;

@@ -6,6 +6,8 @@
 #include "optim.cuh"
 #include "rloa_b200.h"
 
+struct rloa_xchg;
+
 namespace rloa {
 
 struct LearnCluster {
@@ -26,13 +28,15 @@ struct LearnClusterReplay {          // fused ReplayBuffer.sample: the kernel re
 };
 
 bool learn_cluster_supported(int S, int A, int H, int B);
+constexpr int kLearnClusterMaxWorld = 8;     // the in-kernel gradient exchange; larger worlds use the separate exchange kernels
 int learn_cluster_prepare(LearnCluster* lc, int S, int A);
 void learn_cluster_free(LearnCluster* lc);
 // flat_offsets: the 14 segment offsets of the flat gradient in nn.Module.parameters() order + the total
 int learn_cluster_step(LearnCluster* lc, const rloa_naf_params* mn, const rloa_naf_params* tg, const rloa_adam_state* adam,
                        const float* states, const float* actions, const float* rewards, const float* next_states,
                        const float* dones, int B, const rloa_naf_hyper* hp, const ParamTable& pt, const int* flat_offsets,
-                       float* grad, float* loss, float* gnorm, int do_adam, const LearnClusterReplay* replay, cudaStream_t st);
+                       float* grad, float* loss, float* gnorm, int do_adam, const LearnClusterReplay* replay, const rloa_xchg* xchg,
+                       cudaStream_t st);
 // the weight images of both networks (what learn_cluster_step does first unless a prepack is pending)
 int learn_cluster_pack(LearnCluster* lc, const rloa_naf_params* mn, const rloa_naf_params* tg, cudaStream_t st);
 

@@ -25,13 +25,15 @@ def _batch(seed):
             s + 0.1 * torch.randn(B, S, generator=g), torch.zeros(B, 1))
 
 
-def _agent(mode, dev):
+def _agent(mode, dev, trunk=0):
     from robotic_manipulator_rloa_b200.naf_components.naf_algorithm import NAFAgent
     ref_main, ref_target = NAFRef(S, A, H, seed=1), NAFRef(S, A, H, seed=2)
     agent = NAFAgent(None, S, A, H, B, 1000, 1e-3, 1e-3, 0.99, 1, 1, 500, dev, 0)
     agent.qnetwork_main.load_state_dict(ref_main.state_dict())
     agent.qnetwork_target.load_state_dict(ref_target.state_dict())
     agent.grad_exchange_mode = mode
+    if trunk:
+        agent.set_trunk_mode(trunk)      # tensor-core path: the exchange runs inside the fused learn kernel's tail
     return agent
 
 
@@ -40,16 +42,20 @@ def _params(agent):
                       list(agent.qnetwork_target.parameters())])
 
 
-def test_single_rank_exchange_is_bit_identical_to_plain_apply():
+@pytest.mark.parametrize('trunk', [0, 1], ids=['fp32', 'tcgen05-cluster'])
+def test_single_rank_exchange_is_bit_identical_to_plain_apply(trunk):
     dev = torch.device('cuda:0')
-    plain, peer, two_call = _agent('nccl', dev), _agent('peer-always', dev), _agent('nccl', dev)
+    plain, peer, two_call = _agent('nccl', dev, trunk), _agent('peer-always', dev, trunk), _agent('nccl', dev, trunk)
     two_call.fused_learn = False        # rloa_naf_learn_grads + rloa_naf_learn_apply instead of rloa_naf_learn_step
     for step in range(3):
         plain.learn(_batch(step)); peer.learn(_batch(step)); two_call.learn(_batch(step))
     torch.cuda.synchronize()
     assert peer._xchg is not None and not peer._xchg.timed_out()
     assert torch.equal(_params(plain), _params(peer))
-    assert torch.equal(_params(plain), _params(two_call))       # the fused tail kernel == the three separate kernels
+    if trunk == 0:
+        assert torch.equal(_params(plain), _params(two_call))   # the fused tail kernel == the three separate kernels
+    else:       # cluster kernel: in-kernel optimiser (8 norm partials) vs the 80-block apply kernels: last-ulp differences
+        assert float((_params(plain) - _params(two_call)).abs().max()) <= 2e-6
     assert float(plain.last_grad_norm.item()) == float(peer.last_grad_norm.item())
     assert int(peer.optimizer.step_count.item()) == 3
 
@@ -61,13 +67,13 @@ def _worker(rank, world, port, out_dir):
     dev = torch.device('cuda', rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
     out = {}
-    for mode in ('peer', 'nccl'):
-        agent = _agent(mode, dev)
+    for mode in ('peer', 'nccl', 'peer-tc', 'nccl-tc'):
+        agent = _agent(mode.split('-')[0], dev, 1 if mode.endswith('-tc') else 0)
         assert agent.world_size == world
         for step in range(3):
             agent.learn(_batch(100 * rank + step))          # every rank learns from its own replay shard
         torch.cuda.synchronize()
-        if mode == 'peer':
+        if mode.startswith('peer'):
             assert agent._xchg is not None and not agent._xchg.timed_out()
         vec = _params(agent)
         gathered = [torch.empty_like(vec) for _ in range(world)]
@@ -87,8 +93,15 @@ def test_two_rank_peer_exchange_matches_nccl(tmp_path):
         port = s.getsockname()[1]
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     out = np.load(tmp_path / 'out.npz')
-    for mode in ('peer', 'nccl'):
+    for mode in ('peer', 'nccl', 'peer-tc', 'nccl-tc'):
         assert np.array_equal(out[mode][0], out[mode][1]), f'{mode}: ranks diverged'
+    # tensor-core path: the exchange inside the fused learn kernel against NCCL between its two-call form.  The clip
+    # coefficient differs in the last ulp (8 norm partials vs 80), which is enough to re-roll the rounding-noise gradients
+    # of the linear biases under BatchNorm (analytically 0) — Adam turns those into lr-sized steps — so: all but a handful of
+    # elements (measured: 98.4 %) agree to 2e-6, the median difference is below 1e-7, none differs by more than the three
+    # lr-sized steps taken
+    diff = np.abs(out['peer-tc'][0] - out['nccl-tc'][0])
+    assert (diff > 2e-6).mean() <= 3e-2 and diff.max() <= 3.1e-3 and np.median(diff) <= 1e-7
     # both modes add the two ranks' gradients in rank order (a two-operand sum has one rounding): same bits expected;
     # allow the last ulp of an lr-sized Adam step in case NCCL reduces in the other order
     assert np.abs(out['peer'][0] - out['nccl'][0]).max() <= 1e-6
