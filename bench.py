@@ -45,6 +45,7 @@ PANDA = dict(file='franka_panda/panda.urdf', ee=11, involved=[0, 1, 2, 3, 4, 5, 
              target=[0.4, 0.3, 0.5], obstacle=[0.3, 0.0, 0.6], start=[0, 0, 0, -1.5, 0, 1.5, 0])
 VAR3 = [0, 0, .5, .5, .5, .5]      # README.md:49 / rl_framework.py:648-649
 FRAMES = 400
+CONTACT_THRESHOLD = 0.02         # contact rows against obstacle / target on BOTH arms (the product's default, environment/simulator.py)
 PREROLL_PAIRS = 230              # 460 untimed iterations > one 400-step episode + its 50 reset sub-steps
 FLOP_PER_ENV_STEP = 1.0e5        # KUKA 14 links / 12 dof / 34 rows / 50 iterations
 FLOP_PER_SWEEP = 34 * (2 * 12 + 8)   # one Gauss-Seidel sweep over the 34 rows (same table)
@@ -138,7 +139,8 @@ class CpuLoop:
         self.rng = np.random.default_rng(seed)
         nl = self.model.nl
         self.q, self.qd = np.zeros((n_envs, nl)), np.zeros((n_envs, nl))
-        self.orc.batch_reset(self.q, self.qd, self._starts(n_envs), 50, nthreads=cores)
+        self.orc.batch_reset(self.q, self.qd, self._starts(n_envs), 50, nthreads=cores, obstacle=KUKA['obstacle'],
+                             target=KUKA['target'], contact_threshold=CONTACT_THRESHOLD)
         for j in range(len(KUKA['start'])):
             self.orc.set_position_control(j, KUKA['start'][j])
         step_motors(self.orc, KUKA)
@@ -168,7 +170,8 @@ class CpuLoop:
             std = torch.rsqrt(torch.diagonal(P, dim1=1, dim2=2))
             act = torch.clamp(mu + std * torch.randn_like(mu), -1, 1).numpy()
         obs2, rew, done, _ = self.orc.batch_step(self.q, self.qd, act.astype(np.float64), KUKA['involved'], 200.0,
-                                                 KUKA['obstacle'], KUKA['target'], nthreads=self.cores)
+                                                 KUKA['obstacle'], KUKA['target'], nthreads=self.cores,
+                                                 contact_threshold=CONTACT_THRESHOLD)
         idx = (self.cursor + np.arange(self.n)) % self.cap
         self.rs[idx], self.ra[idx], self.rr[idx, 0] = self.obs, act, rew
         self.rs2[idx], self.rd[idx, 0] = obs2, done
@@ -186,7 +189,8 @@ class CpuLoop:
         if fin.any():            # synchronous Environment.reset of the finished envs, as the reference does
             k = np.nonzero(fin)[0]
             q, qd = np.ascontiguousarray(self.q[k]), np.ascontiguousarray(self.qd[k])
-            self.orc.batch_reset(q, qd, self._starts(len(k)), 50, nthreads=self.cores)
+            self.orc.batch_reset(q, qd, self._starts(len(k)), 50, nthreads=self.cores, obstacle=KUKA['obstacle'],
+                                 target=KUKA['target'], contact_threshold=CONTACT_THRESHOLD)
             self.q[k], self.qd[k] = q, qd
             for i, e in enumerate(k):
                 self.obs[e] = self.orc.observe(q[i], qd[i], KUKA['obstacle'], KUKA['target'])[0]
@@ -301,6 +305,7 @@ def workload_config(args, c, where):
                                              gbatch=c['batch'] * gpus),
             'envs_per_gpu': c['envs'], 'replay_batch': c['batch'], 'frames': FRAMES, 'parallelism': f'env-dp{gpus}',
             'initial_positions_variation_range': list(c['var']),
+            'contacts': 'normal contact rows against the obstacle sphere and the target cube (threshold 0.02 m), as in the reference world',
             'l2': 'flushed between timed step pairs (256 MiB fill, untimed)' if where == 'gpu' else 'n/a',
             'steady_state': f'{2 * PREROLL_PAIRS} untimed iterations before the timed region' if where == 'gpu' else 'n/a',
             'naf_trunk': ('tcgen05: bf16 operands (tf32 for the S-wide input layer), fp32 TMEM accumulate (fused policy kernel + trunk); heads, BatchNorm, '

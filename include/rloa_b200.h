@@ -138,6 +138,9 @@ typedef struct {
     float max_force;                        /* environment.py:469 force=max_force */
     float target_threshold;                 /* 0.05  (environment.py:311, 364) */
     float obstacle_threshold;               /* 0.0   (environment.py:311, 368) */
+    float contact_threshold;                /* contact rows against the obstacle sphere / target cube, which the reference
+                                               loads as collidable fixed bodies (environment.py:252-255): Bullet's contact
+                                               breaking threshold 0.02; 0 switches the rows off (free dynamics) */
 } rloa_step_config;
 
 /* Environment.step for every env (environment.py:453-485):
@@ -147,6 +150,10 @@ typedef struct {
  * and reports valid = 0, reward = 0, done = 0; valid (uint8 [n_envs]) may be NULL. */
 int rloa_sim_step(rloa_sim* s, const rloa_step_config* cfg, const float* actions, const uint8_t* active,
                   float* obs, float* reward, uint8_t* done, uint8_t* valid, void* stream);
+
+/* Contact breaking threshold used by rloa_sim_reset's sub-steps (Environment.reset steps the same world as step, contact
+ * rows included; rloa_sim_step takes its threshold from the config).  0 = off. */
+int rloa_sim_set_contacts(rloa_sim* s, float contact_threshold);
 
 /* Software pipelining of the step.  A stepSimulation has an action-independent half (forward kinematics,
  * articulated-body factorisation, free accelerations, M^-1: two of the three kernels) that only needs the

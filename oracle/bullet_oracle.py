@@ -199,7 +199,9 @@ class BulletOracle:
         return obs, float(rew[0]), int(done[0])
 
     # ---- batched (Environment.step / reset over n envs) -----------------------------------------
-    def batch_step(self, q, qd, actions, act_joints, max_force, obstacle, target, nthreads=1):
+    def batch_step(self, q, qd, actions, act_joints, max_force, obstacle, target, nthreads=1, contact_threshold=0.0):
+        """contact_threshold > 0 (Bullet: 0.02) adds the normal contact rows against obstacle and target; the number of
+        contact rows per env is left in self.last_contacts."""
         n = q.shape[0]
         assert q.dtype == np.float64 and qd.dtype == np.float64 and q.flags.c_contiguous
         actions = np.ascontiguousarray(actions, np.float64)
@@ -208,13 +210,28 @@ class BulletOracle:
         target = np.ascontiguousarray(np.broadcast_to(target, (n, 3)), np.float64)
         obs, rew = np.zeros((n, self.S)), np.zeros(n)
         done, iters = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        if contact_threshold > 0.0:
+            nc = np.zeros(n, np.int32)
+            lib().orc_batch_step_contacts(C.byref(self.m), C.byref(self.motors), _ip(aj), C.c_int(len(aj)), C.c_int(n),
+                                          _dp(q), _dp(qd), _dp(actions), C.c_double(max_force), _dp(obstacle), _dp(target),
+                                          C.c_double(contact_threshold), _dp(obs), _dp(rew), _ip(done), _ip(iters), _ip(nc),
+                                          C.c_int(nthreads))
+            self.last_contacts = nc
+            return obs, rew, done, iters
         lib().orc_batch_step(C.byref(self.m), C.byref(self.motors), _ip(aj), C.c_int(len(aj)), C.c_int(n),
                              _dp(q), _dp(qd), _dp(actions), C.c_double(max_force), _dp(obstacle), _dp(target),
                              _dp(obs), _dp(rew), _ip(done), _ip(iters), C.c_int(nthreads))
         return obs, rew, done, iters
 
-    def batch_reset(self, q, qd, init_targets, nsub=50, nthreads=1):
+    def batch_reset(self, q, qd, init_targets, nsub=50, nthreads=1, obstacle=None, target=None, contact_threshold=0.0):
         n = q.shape[0]
         init_targets = np.ascontiguousarray(init_targets, np.float64)
+        if contact_threshold > 0.0:
+            obstacle = np.ascontiguousarray(np.broadcast_to(obstacle, (n, 3)), np.float64)
+            target = np.ascontiguousarray(np.broadcast_to(target, (n, 3)), np.float64)
+            lib().orc_batch_reset_contacts(C.byref(self.m), C.byref(self.motors), C.c_int(init_targets.shape[1]), C.c_int(n),
+                                           _dp(q), _dp(qd), _dp(init_targets), C.c_int(nsub), _dp(obstacle), _dp(target),
+                                           C.c_double(contact_threshold), C.c_int(nthreads))
+            return
         lib().orc_batch_reset(C.byref(self.m), C.byref(self.motors), C.c_int(init_targets.shape[1]), C.c_int(n),
                               _dp(q), _dp(qd), _dp(init_targets), C.c_int(nsub), C.c_int(nthreads))

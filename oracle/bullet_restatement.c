@@ -357,8 +357,110 @@ void orc_crba(const orc_model* m, const double* q, double* M) {
     }
 }
 
+/* ---------- contact rows against the two collidable fixed bodies of the reference (environment.py:252-255: the obstacle
+ * sphere and the target cube are loaded with useFixedBase, so stepSimulation generates contacts between them and the
+ * manipulator's links).  Restated from btMultiBodyConstraintSolver::setupMultiBodyContactConstraint /
+ * resolveSingleConstraintRowGeneric: one NORMAL row per (shape, body) pair closer than the contact breaking threshold
+ * (gContactBreakingThreshold = 0.02), lambda in [0, inf), no split impulse:
+ *     separated  (d > 0): rhs = (-J qs - d / dt) / (J M^-1 J^T)        — acts only if the gap would close within the step
+ *     penetrating (d <= 0): rhs = (-J qs - d erp / dt) / (J M^-1 J^T)  — erp = 0.2 pushes the penetration out
+ * swept after the non-contact rows of every iteration, in contact order.  NOT restated: friction rows (lateral friction of
+ * the two URDFs is not known here), the persistent manifold's multi-point caching (one point per pair), contacts of box /
+ * hull shapes against the cube. ---------- */
+typedef struct {
+    int n;
+    int link[ORC_MAXC];
+    double nrm[ORC_MAXC][3];   /* on the fixed body, pointing at the link */
+    double pA[ORC_MAXC][3];    /* contact point on the link, world */
+    double dist[ORC_MAXC];
+} orc_contact_set;
+
+static double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+/* argmin over t in [0,1] of the distance from a + t (b - a) to the origin-centred box h (same pieces as segment_box) */
+static double segment_box_argmin(const double* a, const double* b, const double* h, double* t_best);
+
+static void add_contact(orc_contact_set* cs, int link, const double* x, double r_shape, const double* from, double r_body,
+                        double thr) {
+    /* core point x of the link's shape against the closest point `from` of the fixed body (sphere centre / cube surface) */
+    double v[3] = {x[0] - from[0], x[1] - from[1], x[2] - from[2]};
+    double L = sqrt(dot3(v, v));
+    if (L < 1e-9 || cs->n >= ORC_MAXC) return;
+    double d = L - r_shape - r_body;
+    if (!(d < thr)) return;
+    int c = cs->n++;
+    cs->link[c] = link;
+    cs->dist[c] = d;
+    for (int a = 0; a < 3; a++) {
+        cs->nrm[c][a] = v[a] / L;
+        cs->pA[c][a] = x[a] - r_shape * v[a] / L;
+    }
+}
+
+static void find_contacts(const orc_model* m, const double* Rw, const double* pw, const double* obstacle,
+                          const double* target, double thr, orc_contact_set* cs) {
+    cs->n = 0;
+    for (int s = 0; s < m->ns; s++) {
+        int l = m->s_link[s], type = m->s_type[s];
+        if (type == ORC_SHAPE_HULL) continue;
+        double Rs[9], ps[3], t[3];
+        m3m(Rw + 9 * l, m->s_R[s], Rs);
+        m3v(Rw + 9 * l, m->s_p[s], t);
+        for (int a = 0; a < 3; a++) ps[a] = pw[3 * l + a] + t[a];
+        double ax[3] = {Rs[2], Rs[5], Rs[8]};
+        double r_s = type == ORC_SHAPE_BOX ? 0.0 : m->s_dim[s][0], hz = m->s_dim[s][1];
+        /* --- obstacle sphere --- */
+        {
+            double x[3];
+            if (type == ORC_SHAPE_SPHERE) { for (int a = 0; a < 3; a++) x[a] = ps[a]; }
+            else if (type == ORC_SHAPE_CAPSULE) {
+                double rel[3] = {obstacle[0] - ps[0], obstacle[1] - ps[1], obstacle[2] - ps[2]};
+                double tz = clampd(dot3(rel, ax), -hz, hz);
+                for (int a = 0; a < 3; a++) x[a] = ps[a] + tz * ax[a];
+            } else { /* box: closest point of the box to the sphere centre */
+                double rel[3] = {obstacle[0] - ps[0], obstacle[1] - ps[1], obstacle[2] - ps[2]}, loc[3], w[3];
+                m3tv(Rs, rel, loc);
+                for (int a = 0; a < 3; a++) loc[a] = clampd(loc[a], -m->s_dim[s][a], m->s_dim[s][a]);
+                m3v(Rs, loc, w);
+                for (int a = 0; a < 3; a++) x[a] = ps[a] + w[a];
+            }
+            add_contact(cs, l, x, r_s, obstacle, m->obstacle_radius, thr);
+        }
+        /* --- target cube (axis-aligned) --- */
+        if (type != ORC_SHAPE_BOX) {
+            double x[3], y[3];
+            if (type == ORC_SHAPE_SPHERE) { for (int a = 0; a < 3; a++) x[a] = ps[a]; }
+            else {
+                double a1[3], b1[3], tb;
+                for (int a = 0; a < 3; a++) { a1[a] = ps[a] - target[a] - hz * ax[a]; b1[a] = ps[a] - target[a] + hz * ax[a]; }
+                segment_box_argmin(a1, b1, m->target_half, &tb);
+                for (int a = 0; a < 3; a++) x[a] = target[a] + a1[a] + tb * (b1[a] - a1[a]);
+            }
+            for (int a = 0; a < 3; a++) y[a] = target[a] + clampd(x[a] - target[a], -m->target_half[a], m->target_half[a]);
+            add_contact(cs, l, x, r_s, y, 0.0, thr);
+        }
+    }
+}
+
+/* row of the point Jacobian: d(n . pA)/dq for every dof (link index), 0 off the contact link's chain */
+static void contact_jacobian(const orc_model* m, const double* Rw, const double* pw, int link, const double* n, const double* pA,
+                             double* J) {
+    for (int i = 0; i < m->nl; i++) J[i] = 0.0;
+    for (int k = link; k >= 0; k = m->parent[k]) {
+        if (m->jtype[k] == ORC_FIXED) continue;
+        double aw[3], dw[3];
+        m3v(Rw + 9 * k, m->axis[k], aw);
+        if (m->jtype[k] == ORC_PRISMATIC) { J[k] = dot3(n, aw); continue; }
+        m3v(Rw + 9 * k, m->d[k], dw);                       /* pivot -> COM of link k, world */
+        double rp[3] = {pA[0] - pw[3 * k] + dw[0], pA[1] - pw[3 * k + 1] + dw[1], pA[2] - pw[3 * k + 2] + dw[2]}, cr[3];
+        cross3(aw, rp, cr);
+        J[k] = dot3(n, cr);
+    }
+}
+
 /* ---------- one stepSimulation: ABA -> rows -> PGS -> integrate ---------- */
-int orc_substep(const orc_model* m, const orc_motors* mot, double* q, double* qd) {
+static int substep_impl(const orc_model* m, const orc_motors* mot, double* q, double* qd, const double* obstacle,
+                        const double* target, double contact_thr, int* n_contacts) {
     int nl = m->nl;
     abawork w;
     double qdd[ORC_MAXL], qs[ORC_MAXL];
@@ -402,6 +504,35 @@ int orc_substep(const orc_model* m, const orc_motors* mot, double* q, double* qd
         rlo[nrows] = -mot->max_imp[i]; rhi[nrows] = mot->max_imp[i]; rapp[nrows] = 0.0;
         nrows++;
     }
+    /* contact rows (collision detection runs on the pre-step pose, like stepSimulation's first phase) */
+    orc_contact_set cs;
+    cs.n = 0;
+    double cJ[ORC_MAXC][ORC_MAXL], cU[ORC_MAXC][ORC_MAXL], crhs[ORC_MAXC], cjdi[ORC_MAXC], capp[ORC_MAXC];
+    if (obstacle != NULL) {
+        double Rw[ORC_MAXL * 9], pw[ORC_MAXL * 3];
+        orc_fk(m, q, Rw, pw);
+        find_contacts(m, Rw, pw, obstacle, target, contact_thr, &cs);
+        for (int c = 0; c < cs.n; c++) {
+            contact_jacobian(m, Rw, pw, cs.link[c], cs.nrm[c], cs.pA[c], cJ[c]);
+            double jmj = 0, rel = 0;
+            for (int i = 0; i < nl; i++) {
+                double u = 0;
+                if (w.hasdof[i])
+                    for (int k = 0; k < nl; k++)
+                        if (w.hasdof[k]) u += col[k][i] * cJ[c][k];        /* (M^-1 J^T)_i, M^-1 symmetric */
+                cU[c][i] = u;
+                jmj += cJ[c][i] * u;
+                rel += cJ[c][i] * qs[i];
+            }
+            cjdi[c] = jmj > 1e-12 ? 1.0 / jmj : 0.0;
+            double d = cs.dist[c];
+            double pos_err = d > 0 ? 0.0 : -d * m->erp / m->dt;
+            double vel_err = -rel - (d > 0 ? d / m->dt : 0.0);
+            crhs[c] = (pos_err + vel_err) * cjdi[c];
+            capp[c] = 0.0;
+        }
+    }
+    if (n_contacts) *n_contacts = cs.n;
     double dv[ORC_MAXL];
     memset(dv, 0, sizeof(dv));
     int it = 0;
@@ -420,6 +551,18 @@ int orc_substep(const orc_model* m, const orc_motors* mot, double* q, double* qd
             double dvel = delta / rjdi[r];
             if (dvel * dvel > resid) resid = dvel * dvel;
         }
+        for (int c = 0; c < cs.n; c++) {                 /* normal contact rows, after the non-contact rows */
+            if (cjdi[c] == 0.0) continue;
+            double jdv = 0;
+            for (int i = 0; i < nl; i++) jdv += cJ[c][i] * dv[i];
+            double delta = crhs[c] - jdv * cjdi[c];
+            double sum = capp[c] + delta;
+            if (sum < 0.0) { delta = -capp[c]; capp[c] = 0.0; }
+            else capp[c] = sum;
+            for (int i = 0; i < nl; i++) dv[i] += delta * cU[c][i];
+            double dvel = delta / cjdi[c];
+            if (dvel * dvel > resid) resid = dvel * dvel;
+        }
         if (resid <= m->resid_thresh || it >= m->iters - 1) { it++; break; }
     }
     for (int i = 0; i < nl; i++) {
@@ -431,6 +574,15 @@ int orc_substep(const orc_model* m, const orc_motors* mot, double* q, double* qd
         q[i] += m->dt * x;                               /* stepPositionsMultiDof */
     }
     return it;
+}
+
+int orc_substep(const orc_model* m, const orc_motors* mot, double* q, double* qd) {
+    return substep_impl(m, mot, q, qd, NULL, NULL, 0.0, NULL);
+}
+
+int orc_substep_contacts(const orc_model* m, const orc_motors* mot, double* q, double* qd, const double* obstacle,
+                         const double* target, double contact_thr, int* n_contacts) {
+    return substep_impl(m, mot, q, qd, obstacle, target, contact_thr, n_contacts);
 }
 
 /* ---------- closest distances (getClosestPoints restated for convex primitives) ---------- */
@@ -505,6 +657,51 @@ static double segment_box(const double* a, const double* b, const double* h) {
             }
         }
     }
+    return sqrt(best);
+}
+
+static double segment_box_argmin(const double* a, const double* b, const double* h, double* t_best) {
+    double dir[3], bp[8];
+    int nb = 0;
+    for (int x = 0; x < 3; x++) dir[x] = b[x] - a[x];
+    bp[nb++] = 0.0;
+    bp[nb++] = 1.0;
+    for (int x = 0; x < 3; x++) {
+        if (fabs(dir[x]) < 1e-300) continue;
+        double t1 = (h[x] - a[x]) / dir[x], t2 = (-h[x] - a[x]) / dir[x];
+        if (t1 > 0 && t1 < 1) bp[nb++] = t1;
+        if (t2 > 0 && t2 < 1) bp[nb++] = t2;
+    }
+    for (int i = 1; i < nb; i++) {
+        double v = bp[i];
+        int j = i - 1;
+        while (j >= 0 && bp[j] > v) { bp[j + 1] = bp[j]; j--; }
+        bp[j + 1] = v;
+    }
+    double best = 1e300, tb = 0.0;
+    for (int i = 0; i < nb; i++) {
+        double f = seg_f(a, dir, h, bp[i]);
+        if (f < best) { best = f; tb = bp[i]; }
+        if (i + 1 < nb) {
+            double tm = 0.5 * (bp[i] + bp[i + 1]), A = 0, B = 0;
+            for (int x = 0; x < 3; x++) {
+                double xm = a[x] + tm * dir[x];
+                if (fabs(xm) > h[x]) {
+                    double sg = xm > 0 ? 1.0 : -1.0;
+                    A += dir[x] * dir[x];
+                    B += 2 * (sg * a[x] - h[x]) * sg * dir[x];
+                }
+            }
+            if (A > 0) {
+                double ts = -B / (2 * A);
+                if (ts > bp[i] && ts < bp[i + 1]) {
+                    double f2 = seg_f(a, dir, h, ts);
+                    if (f2 < best) { best = f2; tb = ts; }
+                }
+            }
+        }
+    }
+    *t_best = tb;
     return sqrt(best);
 }
 
@@ -808,6 +1005,50 @@ void orc_batch_reset(const orc_model* m, const orc_motors* mt, int n_init, int n
             mot.max_imp[j] = 100000.0 * m->dt;
         }
         for (int s = 0; s < nsub; s++) orc_substep(m, &mot, q + e * nl, qd + e * nl);
+    }
+    (void)nthreads;
+}
+
+/* orc_batch_step with the contact rows (contact_thr > 0) */
+void orc_batch_step_contacts(const orc_model* m, const orc_motors* mt, const int* act_joint, int n_act, int n, double* q,
+                             double* qd, const double* actions, double max_force, const double* obstacle, const double* target,
+                             double contact_thr, double* obs, double* reward, int* done, int* iters_out, int* ncontacts_out,
+                             int nthreads) {
+    int nl = m->nl, S = 9 + 2 * m->n_obs_joints;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+#endif
+    for (int e = 0; e < n; e++) {
+        orc_motors mot = *mt;
+        for (int k = 0; k < n_act; k++) {
+            int j = act_joint[k];
+            mot.kp[j] = 0; mot.kd[j] = 1; mot.tpos[j] = 0; mot.tvel[j] = actions[e * n_act + k];
+            mot.max_imp[j] = max_force * m->dt;
+        }
+        int nc = 0;
+        int it = substep_impl(m, &mot, q + e * nl, qd + e * nl, obstacle + 3 * e, target + 3 * e, contact_thr, &nc);
+        if (iters_out) iters_out[e] = it;
+        if (ncontacts_out) ncontacts_out[e] = nc;
+        orc_observe(m, q + e * nl, qd + e * nl, obstacle + 3 * e, target + 3 * e, obs + e * S, reward + e, done + e);
+    }
+    (void)nthreads;
+}
+
+void orc_batch_reset_contacts(const orc_model* m, const orc_motors* mt, int n_init, int n, double* q, double* qd,
+                              const double* init_targets, int nsub, const double* obstacle, const double* target,
+                              double contact_thr, int nthreads) {
+    int nl = m->nl;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+#endif
+    for (int e = 0; e < n; e++) {
+        orc_motors mot = *mt;
+        for (int j = 0; j < n_init; j++) {
+            mot.kp[j] = 0.1; mot.kd[j] = 1.0; mot.tpos[j] = init_targets[e * n_init + j]; mot.tvel[j] = 0;
+            mot.max_imp[j] = 100000.0 * m->dt;
+        }
+        for (int s = 0; s < nsub; s++)
+            substep_impl(m, &mot, q + e * nl, qd + e * nl, obstacle + 3 * e, target + 3 * e, contact_thr, NULL);
     }
     (void)nthreads;
 }

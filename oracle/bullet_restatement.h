@@ -27,6 +27,7 @@
 
 #define ORC_MAXL 32   /* links (== pybullet getNumJoints) */
 #define ORC_MAXS 64   /* collision shapes */
+#define ORC_MAXC 4    /* contact rows per arm: the first four pairs in shape order (== kMaxContacts of the CUDA simulator) */
 #define ORC_MAXV 16384 /* convex-hull vertices, all hull shapes together */
 
 enum { ORC_FIXED = 0, ORC_REVOLUTE = 1, ORC_PRISMATIC = 2 };
@@ -88,6 +89,9 @@ void orc_minv(const orc_model* m, const double* q, double* Minv /*[nl*nl]*/);
 void orc_crba(const orc_model* m, const double* q, double* M /*[nl*nl]*/);
 void orc_rnea_bias(const orc_model* m, const double* q, const double* qd, double* bias);
 int  orc_substep(const orc_model* m, const orc_motors* mot, double* q, double* qd);
+/* the same with NORMAL contact rows against the obstacle sphere and the target cube (friction not restated) */
+int  orc_substep_contacts(const orc_model* m, const orc_motors* mot, double* q, double* qd, const double* obstacle,
+                          const double* target, double contact_thr, int* n_contacts);
 void orc_distances(const orc_model* m, const double* q, const double* obstacle, const double* target,
                    double* link_obst /*[nl]*/, double* ee_target /*[1]*/, double* ee_pos /*[3]*/);
 void orc_observe(const orc_model* m, const double* q, const double* qd, const double* obstacle,

@@ -47,7 +47,7 @@ class ModelDesc(C.Structure):
 class StepConfig(C.Structure):
     _fields_ = [('n_act', C.c_int32), ('act_joint', C.c_int32 * MAX_LINKS), ('n_fixed', C.c_int32),
                 ('fixed_joint', C.c_int32 * MAX_LINKS), ('max_force', C.c_float), ('target_threshold', C.c_float),
-                ('obstacle_threshold', C.c_float)]
+                ('obstacle_threshold', C.c_float), ('contact_threshold', C.c_float)]
 
 
 class NafParams(C.Structure):
@@ -97,6 +97,7 @@ SIGNATURES = {
     'rloa_sim_set_motors': (C.c_int, [_VP, _fp, _fp, _fp, _fp, _VP]),
     'rloa_sim_clear': (C.c_int, [_VP, _VP]),
     'rloa_sim_step': (C.c_int, [_VP, C.POINTER(StepConfig), _fp, _fp, _fp, _fp, _fp, _fp, _VP]),
+    'rloa_sim_set_contacts': (C.c_int, [_VP, _F]),
     'rloa_sim_prepare': (C.c_int, [_VP, _VP]),
     'rloa_sim_join': (C.c_int, [_VP, _VP]),
     'rloa_sim_begin_reset': (C.c_int, [_VP, _fp, _fp, _I, _I, _VP]),

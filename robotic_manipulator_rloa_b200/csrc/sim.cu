@@ -1,6 +1,7 @@
 // librloa_b200: batched manipulator simulator — kernels and C ABI (include/rloa_b200.h).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -63,6 +64,8 @@ struct PgsState<D, false> {
     }
     __device__ __forceinline__ float diag(int d) const { return Mi[tri(d, d)]; }
     __device__ __forceinline__ float get(int d) const { return dv[d]; }
+    __device__ __forceinline__ float mat(int a, int b) const { return Mi[tri(a, b)]; }
+    __device__ __forceinline__ void add(int d, float x) { dv[d] += x; }
     // dv += delta * M^-1[d][:]; the component the next row reads (`first`) is issued first
     __device__ __forceinline__ void axpy(int d, float delta, int first) {
         if (first >= 0 && first < D) dv[first] = fmaf(delta, Mi[tri(d, first)], dv[first]);
@@ -91,6 +94,10 @@ struct PgsState<D, true> {
     }
     __device__ __forceinline__ float diag(int d) const { return (d & 1) ? M[d][d >> 1].y : M[d][d >> 1].x; }
     __device__ __forceinline__ float get(int d) const { return (d & 1) ? dv[d >> 1].y : dv[d >> 1].x; }
+    __device__ __forceinline__ float mat(int a, int b) const { return (b & 1) ? M[a][b >> 1].y : M[a][b >> 1].x; }
+    __device__ __forceinline__ void add(int d, float x) {
+        if (d & 1) dv[d >> 1].y += x; else dv[d >> 1].x += x;
+    }
     // dv += delta * M^-1[d][:]; the pair holding the component the next row reads (`first`) is issued first
     __device__ __forceinline__ void axpy(int d, float delta, int first) {
         const float2 dl = make_float2(delta, delta);
@@ -188,6 +195,51 @@ sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_c
             }
         }
 
+        // ---- contact rows against the obstacle sphere / the target cube (environment.py:252-255 loads both
+        // as collidable fixed bodies).  Only arms flagged `near` by the previous step's distance pass pay for the
+        // collision phase; their rows live in local memory (dynamic contact index) ----
+        int nc = 0;
+        float cJ[kMaxContacts * kMaxDof], cU[kMaxContacts * kMaxDof], crhs[kMaxContacts], cjdi[kMaxContacts], capp[kMaxContacts],
+            cjmj[kMaxContacts];
+        const int nflag = cfg.contact_thr > 0.f ? S.near[env] : 0;
+        if (nflag != 0 && cfg.contact_dbg != 2) {
+            float cd[kMaxContacts];
+            if (nflag > 0) {        // rows left by the previous step's distance pass (same pose)
+                nc = min(nflag, kMaxContacts);
+                const float* row = S.crow + (size_t)env * kMaxContacts * kContactRec;
+                for (int c = 0; c < nc; c++) {
+#pragma unroll
+                    for (int a = 0; a < D; a++) cJ[c * kMaxDof + a] = row[c * kContactRec + a];
+                    cd[c] = row[c * kContactRec + kMaxDof];
+                }
+            } else {                // the pose was set from outside a step: collision phase from scratch
+                const V3 tg0 = ld3(S.target + 3 * (size_t)env), ob0 = ld3(S.obstacle + 3 * (size_t)env);
+                nc = build_contacts<NLMAX>(M, S.q + env, N, ob0, tg0, cfg.contact_thr, cJ, cd);
+            }
+            if (cfg.contact_dbg == 1) nc = 0;          // diagnostics: pay for the collision phase only
+            for (int c = 0; c < nc; c++) {
+                float jmj = 0.f, rel = 0.f;
+#pragma unroll
+                for (int a = 0; a < D; a++) {
+                    float u = 0.f;
+#pragma unroll
+                    for (int b = 0; b < D; b++) u = fmaf(P.mat(a, b), cJ[c * kMaxDof + b], u);     // (M^-1 J^T)_a
+                    cU[c * kMaxDof + a] = u;
+                    jmj = fmaf(cJ[c * kMaxDof + a], u, jmj);
+                    rel = fmaf(cJ[c * kMaxDof + a], qs0[a], rel);
+                }
+                const float jd = jmj > 1e-12f ? 1.f / jmj : 0.f;
+                const float d = cd[c];
+                // separated: the row only acts if the gap would close within the step; penetrating: erp pushes it out
+                const float pos_err = d > 0.f ? 0.f : -d * M.erp * inv_dt;
+                const float vel_err = -rel - (d > 0.f ? d * inv_dt : 0.f);
+                cjdi[c] = jd;
+                cjmj[c] = jmj;
+                crhs[c] = (pos_err + vel_err) * jd;
+                capp[c] = 0.f;
+            }
+        }
+
         // ---- projected Gauss-Seidel, M^-1 in registers; sweep direction alternates like Bullet's ----
         const float limit_hi = M.limit_max_imp, thresh = M.resid_thresh;
         const int iters = M.iters;
@@ -244,6 +296,27 @@ sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_c
                     }
                 }
             }
+            if (nc > 0) {       // normal contact rows, after the non-contact rows of the sweep.  Unrolled over the (at most
+                                // kMaxContacts) rows so that every local-memory address is static: the loads of row c + 1
+                                // are issued while row c's dependent chain runs
+#pragma unroll
+                for (int c = 0; c < kMaxContacts; c++) {
+                    if (c < nc && cjdi[c] != 0.f) {
+                        float jv[3] = {0.f, 0.f, 0.f};        // three chains instead of one of D dependent FMAs
+#pragma unroll
+                        for (int a = 0; a < D; a++) jv[a % 3] = fmaf(cJ[c * kMaxDof + a], P.get(a), jv[a % 3]);
+                        const float jdv = (jv[0] + jv[1]) + jv[2];
+                        float delta = crhs[c] - jdv * cjdi[c];
+                        const float sum = capp[c] + delta;
+                        if (sum < 0.f) { delta = -capp[c]; capp[c] = 0.f; }
+                        else capp[c] = sum;
+#pragma unroll
+                        for (int a = 0; a < D; a++) P.add(a, delta * cU[c * kMaxDof + a]);
+                        const float dvel = delta * cjmj[c];
+                        resid = fmaxf(resid, dvel * dvel);
+                    }
+                }
+            }
             if (!(resid > thresh) || it >= iters - 1) { it++; break; }
         }
 
@@ -272,7 +345,11 @@ sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_c
 
         // ---- state / reward / done from the post-step configuration ----
         const V3 tg = ld3(S.target + 3 * (size_t)env), ob = ld3(S.obstacle + 3 * (size_t)env);
-        const ObsOut o = fk_and_distances<NLMAX, GJK>(M, S.q + env, N, ob, tg, cfg.obstacle_thr, !is_reset, nullptr, 0);
+        const bool contacts_on = cfg.contact_thr > 0.f;
+        const ObsOut o = fk_and_distances<NLMAX, GJK>(M, S.q + env, N, ob, tg, cfg.obstacle_thr, !is_reset, nullptr, 0,
+                                                      cfg.contact_thr, contacts_on,
+                                                      contacts_on ? S.crow + (size_t)env * kMaxContacts * kContactRec : nullptr);
+        if (contacts_on) S.near[env] = o.ncontacts;
         if (obs != nullptr) {
             const int n = M.n_obs;
             for (int i = 0; i < n; i++) {
@@ -605,6 +682,7 @@ struct rloa_sim {
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     bool prepared = false;           // F / qs / M^-1 hold the current (q, qd): rloa_sim_step launches the solve only
     bool join_pending = false;       // the caller's stream has not yet waited for the side stream
+    float contact_thr = 0.f;         // contact rows of the synchronous reset (rloa_sim_set_contacts); steps carry theirs in the config
 };
 
 // the caller's stream waits for an outstanding rloa_sim_prepare; with invalidate the prepared half is dropped
@@ -614,6 +692,11 @@ static int sim_sync_prepared(rloa_sim* s, cudaStream_t st, bool invalidate) {
         s->join_pending = false;
     }
     if (invalidate) s->prepared = false;
+    return RLOA_OK;
+}
+// the pose changed outside a step (set_state / clear): the contact-candidate flags are unknown -> conservative
+static int sim_mark_near(rloa_sim* s, cudaStream_t st) {
+    RLOA_CUDA(cudaMemsetAsync(s->a.near, 0xff, (size_t)s->a.n_envs * sizeof(int), st));        // -1: unknown
     return RLOA_OK;
 }
 
@@ -779,8 +862,8 @@ extern "C" int rloa_sim_create(const rloa_model* m, int32_t n_envs, rloa_sim** o
     s->a.n_envs = n_envs;
     s->a.nl = nl;
     s->a.ndof = ndof;
-    // one allocation: q qd kp tpos tvel maximp qs | F | minv | target obstacle | iters reset_left
-    const size_t floats = 7 * n + n * kFRec + N * ndof * ndof + 6 * N + 2 * N;
+    // one allocation: q qd kp tpos tvel maximp qs | F | minv | target obstacle | iters reset_left near
+    const size_t floats = 7 * n + n * kFRec + N * ndof * ndof + 6 * N + 3 * N;
     if (cudaMalloc(&s->block, floats * sizeof(float)) != cudaSuccess) {
         set_error("rloa_sim_create: cudaMalloc of %zu bytes failed: %s", floats * sizeof(float), cudaGetErrorString(cudaGetLastError()));
         delete s;
@@ -794,12 +877,20 @@ extern "C" int rloa_sim_create(const rloa_model* m, int32_t n_envs, rloa_sim** o
     s->a.target = s->a.minv + N * ndof * ndof; s->a.obstacle = s->a.target + 3 * N;
     s->a.iters = reinterpret_cast<int*>(s->a.obstacle + 3 * N);
     s->a.reset_left = s->a.iters + n_envs;
+    s->a.near = s->a.reset_left + n_envs;
+    if (cudaMalloc(&s->a.crow, N * kMaxContacts * kContactRec * sizeof(float)) != cudaSuccess) {
+        set_error("rloa_sim_create: cudaMalloc of the contact rows failed: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaFree(s->block);
+        delete s;
+        return RLOA_ERR_CUDA;
+    }
     if (cudaMalloc(&s->ticket, sizeof(unsigned)) == cudaSuccess) cudaMemset(s->ticket, 0, sizeof(unsigned));
     cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&s->join_ev, cudaEventDisableTiming);
     cudaFuncSetAttribute(sim_minv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxLinks * kFRec * 32 * (int)sizeof(float));
     cudaMemset(s->block, 0, floats * sizeof(float));
+    cudaMemset(s->a.near, 0xff, N * sizeof(int));        // -1 = unknown pose: every arm runs the collision phase on its first step
     sim_clear_kernel<<<(unsigned)((n + 255) / 256), 256>>>(s->a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (cudaDeviceSynchronize() != cudaSuccess) {
@@ -815,6 +906,7 @@ extern "C" int rloa_sim_create(const rloa_model* m, int32_t n_envs, rloa_sim** o
 extern "C" void rloa_sim_destroy(rloa_sim* s) {
     if (s == nullptr) return;
     if (s->block) cudaFree(s->block);
+    if (s->a.crow) cudaFree(s->a.crow);
     if (s->ticket) cudaFree(s->ticket);
     if (s->side) cudaStreamDestroy(s->side);
     if (s->fork_ev) cudaEventDestroy(s->fork_ev);
@@ -853,7 +945,7 @@ extern "C" int rloa_sim_set_state(rloa_sim* s, const float* q, const float* qd, 
     if (rc != RLOA_OK) return rc;
     if (q && (rc = scatter(s, q, s->a.q, stream)) != RLOA_OK) return rc;
     if (qd && (rc = scatter(s, qd, s->a.qd, stream)) != RLOA_OK) return rc;
-    return RLOA_OK;
+    return sim_mark_near(s, as_stream(stream));
 }
 
 extern "C" int rloa_sim_get_state(const rloa_sim* s, float* q, float* qd, void* stream) {
@@ -884,7 +976,7 @@ extern "C" int rloa_sim_clear(rloa_sim* s, void* stream) {
     const size_t n = (size_t)s->a.n_envs * s->a.nl;
     sim_clear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(s->a);
     RLOA_LAUNCHED();
-    return RLOA_OK;
+    return sim_mark_near(s, as_stream(stream));
 }
 
 static int make_step_cfg(const rloa_sim* s, const rloa_step_config* c, StepCfgDev* out) {
@@ -910,6 +1002,11 @@ static int make_step_cfg(const rloa_sim* s, const rloa_step_config* c, StepCfgDe
     out->pos_maximp = 100000.f * h.dt;
     out->target_thr = c->target_threshold;
     out->obstacle_thr = c->obstacle_threshold;
+    out->contact_thr = c->contact_threshold > 0.f ? c->contact_threshold : 0.f;
+    {
+        const char* e = getenv("RLOA_CONTACT_DEBUG");
+        out->contact_dbg = e != nullptr ? atoi(e) : 0;
+    }
     return RLOA_OK;
 }
 
@@ -965,6 +1062,12 @@ static int launch_substep(const rloa_sim* s, const StepCfgDev& c, int mode, cons
     }
     if (h.nl <= 16) return launch_solve<16>(s, c, mode, actions, active, obs, reward, done, valid, st);
     return launch_solve<32>(s, c, mode, actions, active, obs, reward, done, valid, st);
+}
+
+extern "C" int rloa_sim_set_contacts(rloa_sim* s, float contact_threshold) {
+    RLOA_REQUIRE(s != nullptr && contact_threshold >= 0.f, "rloa_sim_set_contacts: bad argument");
+    s->contact_thr = contact_threshold;
+    return RLOA_OK;
 }
 
 extern "C" int rloa_sim_prepare(rloa_sim* s, void* stream) {
@@ -1034,6 +1137,7 @@ extern "C" int rloa_sim_reset(rloa_sim* s, const uint8_t* mask, const float* ini
     StepCfgDev c;
     std::memset(&c, 0, sizeof(c));
     for (int i = 0; i < kMaxLinks; i++) c.act_index[i] = -1;
+    c.contact_thr = s->contact_thr;          // Environment.reset steps the same world: contacts included
     // the masked envs run their n_substeps reset sub-steps back to back; the last one writes their state
     for (int k = 0; k < n_substeps; k++) {
         const int r = launch_substep(s, c, kModeResetOnly, nullptr, nullptr, k == n_substeps - 1 ? obs : nullptr, nullptr,

@@ -35,6 +35,8 @@ constexpr int kMaxSlots = 3;
 constexpr int kFRec = 16;                // factor record per link: s_a s_l h_a h_l r invD (F[link][k][env])
 constexpr int kLRec = 28;                // per-link local record of the dynamics kernel (forward-sweep results + u)
 constexpr int kTpb = 32;                 // threads (= arms) per block of the thread-per-arm kernels
+constexpr int kMaxContacts = 4;          // normal contact rows per arm (obstacle sphere / target cube vs the link shapes), in
+                                         // shape order; every row costs ~80 dependent cycles per sweep of the thread-per-arm PGS
 
 // fp32 device copy of rloa_model_desc plus the tree tables the kernels need; passed BY VALUE as a
 // __grid_constant__ kernel parameter so every access is a uniform constant-bank load
@@ -74,6 +76,9 @@ struct SimArrays {
     float *target, *obstacle;               // [N][3]
     int* iters;                             // [N]
     int* reset_left;                        // [N] pending reset sub-steps (lock-step asynchronous reset)
+    int* near;                              // [N] contact rows of the CURRENT pose stored in crow (written by the step's distance
+                                            //     pass); -1 = unknown (the pose was set from outside): the step rebuilds them
+    float* crow;                            // [N][kMaxContacts][kMaxDof + 1] J row | signed distance (NULL-safe: only with contacts)
     float* F;                               // [nl][kFRec][N] ABA factor records (dynamics -> minv)
     float* qs;                              // [nl][N] free velocity qd + dt*qdd, clamped
     float* minv;                            // [ndof][ndof][N]
@@ -86,6 +91,8 @@ struct StepCfgDev {
     float vel_maximp;                       // max_force * dt
     float pos_maximp;                       // 1e5 * dt (pybullet POSITION_CONTROL default force)
     float target_thr, obstacle_thr;
+    float contact_thr;                      // contact breaking threshold (Bullet: 0.02); 0 = contact rows off
+    int contact_dbg;                        // RLOA_CONTACT_DEBUG: 1 = collision phase only, 2 = near flags only (timing splits)
 };
 
 struct V3 {
@@ -235,9 +242,110 @@ __device__ __noinline__ float segment_box(V3 a, V3 b, V3 h) {
 
 #include "gjk.cuh"
 
+// ---- contact rows -------------------------------------------------------------
+// Candidates of shape s (world pose Rs, ps) against the obstacle sphere and the axis-aligned target cube: the core point x of
+// the shape (sphere centre / closest point of the capsule axis / closest point of the box) against the closest point of the
+// fixed body; add(link, x, r_shape, from, r_body) keeps the pair when it is closer than the threshold.  Same pairs, same
+// order as oracle/bullet_restatement.c::find_contacts.
+__device__ __noinline__ float segment_box_argmin(V3 a, V3 b, V3 h);
+
+template <class Add>
+__device__ __forceinline__ void shape_contacts(const ModelDev& M, int s, const M3& Rs, V3 ps, V3 obstacle, V3 target, V3 th,
+                                               bool near_o, bool near_t, float M_contact_thr, Add&& add) {
+    const int l = M.s_link[s], type = M.s_type[s];
+    if (type != RLOA_SHAPE_SPHERE && type != RLOA_SHAPE_CAPSULE && type != RLOA_SHAPE_BOX) return;
+    const V3 dim = v3(M.s_dim[s][0], M.s_dim[s][1], M.s_dim[s][2]);
+    const V3 ax = v3(Rs.m[2], Rs.m[5], Rs.m[8]);
+    const float r_s = type == RLOA_SHAPE_BOX ? 0.f : dim.x;
+    if (near_o) {   // obstacle sphere
+        V3 x = ps;
+        if (type == RLOA_SHAPE_CAPSULE) {
+            const float tz = fminf(fmaxf(dot(obstacle - ps, ax), -dim.y), dim.y);
+            x = fma3(tz, ax, ps);
+        } else if (type == RLOA_SHAPE_BOX) {
+            V3 loc = mulT(Rs, obstacle - ps);
+            loc = v3(fminf(fmaxf(loc.x, -dim.x), dim.x), fminf(fmaxf(loc.y, -dim.y), dim.y), fminf(fmaxf(loc.z, -dim.z), dim.z));
+            x = ps + mul(Rs, loc);
+        }
+        add(l, x, r_s, obstacle, M.obstacle_radius);
+    }
+    if (type != RLOA_SHAPE_BOX && near_t) {   // target cube
+        // cheap exact pre-test: the cube lies inside its bounding sphere, so a shape farther than that from the cube's centre
+        // cannot be a contact (for a capsule: distance from the centre to its axis) — the piecewise segment / box routine
+        // below then runs only for shapes within a few centimetres of the cube
+        {
+            const V3 t_s = mulT(Rs, target - ps);
+            const float ez = type == RLOA_SHAPE_CAPSULE ? t_s.z - fminf(fmaxf(t_s.z, -dim.y), dim.y) : t_s.z;
+            const float dc = sqrtf(fmaf(t_s.x, t_s.x, fmaf(t_s.y, t_s.y, ez * ez))) - r_s - sqrtf(dot(th, th));
+            if (!(dc < M_contact_thr)) return;
+        }
+        V3 x = ps;
+        if (type == RLOA_SHAPE_CAPSULE) {
+            const V3 a1 = ps - target - dim.y * ax, b1 = ps - target + dim.y * ax;
+            const float tb = segment_box_argmin(a1, b1, th);
+            x = target + a1 + tb * (b1 - a1);
+        }
+        const V3 c = x - target;
+        const V3 y = target + v3(fminf(fmaxf(c.x, -th.x), th.x), fminf(fmaxf(c.y, -th.y), th.y), fminf(fmaxf(c.z, -th.z), th.z));
+        add(l, x, r_s, y, 0.f);
+    }
+}
+
+// one contact: keep it when closer than thr, write its Jacobian row J[d] = d(n . p_contact)/dq_d (0 off the link's chain) and
+// its distance; Rw / pw = world frames of all links.  Returns 1 when a row was written.
+__device__ __forceinline__ int contact_row(const ModelDev& M, const float* Rw, const float* pw, int link, V3 x, float r_shape, V3 from,
+                                           float r_body, float thr, float* __restrict__ Jc, float* __restrict__ dist_out) {
+    const V3 v = x - from;
+    const float L = sqrtf(dot(v, v));
+    if (L < 1e-9f) return 0;
+    const float d = L - r_shape - r_body;
+    if (!(d < thr)) return 0;
+    const V3 n = (1.f / L) * v;
+    const V3 pA = x - r_shape * n;
+    for (int k = 0; k < kMaxDof; k++) Jc[k] = 0.f;
+    for (int k = link; k >= 0; k = M.parent[k]) {          // the contact link's chain
+        const int di = M.dofidx[k];
+        if (di < 0) continue;
+        M3 Rk;
+#pragma unroll
+        for (int e = 0; e < 9; e++) Rk.m[e] = Rw[k * 9 + e];
+        const V3 aw = mul(Rk, v3(M.axis[k][0], M.axis[k][1], M.axis[k][2]));
+        if (M.jtype[k] == RLOA_JOINT_PRISMATIC) { Jc[di] = dot(n, aw); continue; }
+        const V3 dw = mul(Rk, v3(M.d[k][0], M.d[k][1], M.d[k][2]));      // pivot -> COM of link k, world
+        Jc[di] = dot(n, cross(aw, pA - ld3(pw + k * 3) + dw));
+    }
+    *dist_out = d;
+    return 1;
+}
+
+// the same with the world joint axes aw[k] and pivots pv[k] cached by the kinematics loop (12 instructions per chain link
+// instead of two matrix-vector products)
+__device__ __forceinline__ int contact_row_cached(const ModelDev& M, const float* aw, const float* pv, int link, V3 x, float r_shape,
+                                                  V3 from, float r_body, float thr, float* __restrict__ Jc, float* __restrict__ dist_out) {
+    const V3 v = x - from;
+    const float L = sqrtf(dot(v, v));
+    if (L < 1e-9f) return 0;
+    const float d = L - r_shape - r_body;
+    if (!(d < thr)) return 0;
+    const V3 n = (1.f / L) * v;
+    const V3 pA = x - r_shape * n;
+    for (int k = 0; k < kMaxDof; k++) Jc[k] = 0.f;
+    for (int k = link; k >= 0; k = M.parent[k]) {
+        const int di = M.dofidx[k];
+        if (di < 0) continue;
+        const V3 a = ld3(aw + k * 3);
+        Jc[di] = M.jtype[k] == RLOA_JOINT_PRISMATIC ? dot(n, a) : dot(n, cross(a, pA - ld3(pv + k * 3)));
+    }
+    *dist_out = d;
+    return 1;
+}
+
+constexpr int kContactRec = kMaxDof + 1;      // floats per stored contact row: J[kMaxDof] | signed distance
+
 struct ObsOut {
     float ee_target;     // closest distance end-effector link <-> target cube (10 when no shape)
     bool hit;            // any link <-> obstacle distance < obstacle_threshold
+    int ncontacts;       // contact rows of this pose written to crow (want_near): the NEXT step's collision phase
     V3 ee_pos;           // COM of the end-effector link (getLinkState()[0])
 };
 
@@ -247,8 +355,10 @@ struct ObsOut {
 template <int NLMAX, bool GJK>
 __device__ __forceinline__ ObsOut fk_and_distances(const ModelDev& M, const float* __restrict__ qcol, int N,
                                                    V3 obstacle, V3 target, float obstacle_thr, bool want_dist,
-                                                   float* __restrict__ link_dist, int ld_stride) {
+                                                   float* __restrict__ link_dist, int ld_stride, float contact_thr = 0.f,
+                                                   bool want_near = false, float* __restrict__ crow = nullptr) {
     float Rw[NLMAX * 9], pw[NLMAX * 3];
+    float aw[NLMAX * 3], pv[NLMAX * 3];          // world joint axes / pivots for the contact Jacobians (want_near only)
     const int nl = M.nl;
     for (int i = 0; i < nl; i++) {
         const int par = M.parent[i];
@@ -267,12 +377,17 @@ __device__ __forceinline__ ObsOut fk_and_distances(const ModelDev& M, const floa
 #pragma unroll
         for (int k = 0; k < 9; k++) Rw[i * 9 + k] = R.m[k];
         st3(pw + i * 3, p);
+        if (want_near) {
+            st3(aw + i * 3, mul(R, v3(M.axis[i][0], M.axis[i][1], M.axis[i][2])));
+            st3(pv + i * 3, p - mul(R, dd));
+        }
     }
     ObsOut o;
     o.ee_pos = ld3(pw + M.ee_link * 3);
     o.ee_target = 10.f;
     o.hit = false;
-    if (!want_dist) return o;
+    o.ncontacts = 0;
+    if (!want_dist && !want_near) return o;
     if (link_dist != nullptr)
         for (int i = 0; i < nl; i++) link_dist[i * ld_stride] = 10.f;
     const int ns = M.ns;
@@ -287,12 +402,19 @@ __device__ __forceinline__ ObsOut fk_and_distances(const ModelDev& M, const floa
         // broad phase, exact for the decision the step consumes (d < threshold): the shape lies inside its bounding
         // sphere (centre given in the link frame), so a sphere that far from the obstacle cannot be a hit
         // (SURVEY.md 7.3-4).  The diagnostics path (link_dist) and the end-effector link keep the narrow phase.
-        bool far = false;
+        bool far = false, near_t = false;
         if (link_dist == nullptr) {
-            const V3 rel = obstacle - (pl + mul(Rl, v3(M.s_bs[s][0], M.s_bs[s][1], M.s_bs[s][2])));
-            const float rr = M.s_bs[s][3] + reach;
+            const V3 bc = pl + mul(Rl, v3(M.s_bs[s][0], M.s_bs[s][1], M.s_bs[s][2]));
+            const V3 rel = obstacle - bc;
+            const float rr = M.s_bs[s][3] + reach + (want_near ? contact_thr : 0.f);
             far = dot(rel, rel) >= rr * rr;
-            if (far && l != M.ee_link) continue;
+            if (want_near) {        // bounding sphere against the cube's bounding sphere; refined below
+                const V3 rt = target - bc;
+                const float rc = M.s_bs[s][3] + sqrtf(dot(th, th)) + contact_thr;
+                near_t = dot(rt, rt) < rc * rc;
+            }
+            if (!want_dist && far && !near_t) continue;
+            if (want_dist && far && l != M.ee_link && !near_t) continue;
         }
 #pragma unroll
         for (int k = 0; k < 9; k++) sR.m[k] = M.s_R[s][k];
@@ -302,9 +424,18 @@ __device__ __forceinline__ ObsOut fk_and_distances(const ModelDev& M, const floa
         const M3 Rs = mul(Rl, sR);               // world <- shape
         const V3 ps = pl + mul(Rl, sp);
         const V3 o_s = mulT(Rs, obstacle - ps);  // obstacle centre in the shape frame
+        if (want_near && (near_t || !far)) {
+            // contact rows of THIS pose for the next step's collision phase (stepSimulation detects collisions on the pose
+            // it starts from): written while the world frames are at hand, so that the step does not redo the kinematics
+            shape_contacts(M, s, Rs, ps, obstacle, target, th, !far, near_t, contact_thr, [&](int link, V3 x, float r_shape, V3 from, float r_body) {
+                if (o.ncontacts < kMaxContacts)
+                    o.ncontacts += contact_row_cached(M, aw, pv, link, x, r_shape, from, r_body, contact_thr,
+                                                      crow + o.ncontacts * kContactRec, crow + o.ncontacts * kContactRec + kMaxDof);
+            });
+        }
         float dist;
         if (far) {
-            dist = reach;                        // any value that is not a hit: d_obst = max(threshold, 0)
+            dist = reach + (want_near ? contact_thr : 0.f);     // not a hit and not a contact candidate
         } else if (type == RLOA_SHAPE_SPHERE) {
             dist = sqrtf(dot(o_s, o_s)) - dim.x;
         } else if (type == RLOA_SHAPE_CAPSULE) {
@@ -318,6 +449,7 @@ __device__ __forceinline__ ObsOut fk_and_distances(const ModelDev& M, const floa
             dist = gjk_distance(A, obstacle, v3(0.f, 0.f, 0.f)) - dim.x;
         }
         const float d_obst = dist - M.obstacle_radius;
+        if (!want_dist) continue;
         o.hit = o.hit || (d_obst < obstacle_thr);
         if (link_dist != nullptr) link_dist[l * ld_stride] = fminf(link_dist[l * ld_stride], d_obst);
         if (l == M.ee_link) {                    // vs the axis-aligned target cube, in the cube frame
@@ -633,6 +765,112 @@ __device__ __forceinline__ void arm_minv_column(const ModelDev& M, const SimArra
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Contact rows against the two collidable fixed bodies of the reference (environment.py:252-255: obstacle sphere and
+// target cube, useFixedBase): collision detection on the pre-step pose, one NORMAL row per (shape, body) pair closer than
+// the contact breaking threshold (Bullet gContactBreakingThreshold = 0.02), restated from
+// btMultiBodyConstraintSolver::setupMultiBodyContactConstraint.  Same model as oracle/bullet_restatement.c
+// (find_contacts / contact_jacobian): sphere, capsule and box shapes against the sphere, sphere and capsule shapes against
+// the cube; no friction rows, one point per pair.  Returns the number of contacts; J[c][d] = d(n . p_contact)/dq_d per dof.
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ float segment_box_argmin(V3 a, V3 b, V3 h) {
+    V3 dir = b - a;
+    float bp[8];
+    int nb = 0;
+    bp[nb++] = 0.f;
+    bp[nb++] = 1.f;
+    const float av[3] = {a.x, a.y, a.z}, dv[3] = {dir.x, dir.y, dir.z}, hv[3] = {h.x, h.y, h.z};
+#pragma unroll
+    for (int x = 0; x < 3; x++) {
+        if (fabsf(dv[x]) < 1e-30f) continue;
+        float t1 = (hv[x] - av[x]) / dv[x], t2 = (-hv[x] - av[x]) / dv[x];
+        if (t1 > 0.f && t1 < 1.f) bp[nb++] = t1;
+        if (t2 > 0.f && t2 < 1.f) bp[nb++] = t2;
+    }
+    for (int i = 1; i < nb; i++) {
+        float v = bp[i];
+        int j = i - 1;
+        while (j >= 0 && bp[j] > v) {
+            bp[j + 1] = bp[j];
+            j--;
+        }
+        bp[j + 1] = v;
+    }
+    float best = 3.0e38f, tb = 0.f;
+    for (int i = 0; i < nb; i++) {
+        const float f = seg_box_f(a, dir, h, bp[i]);
+        if (f < best) { best = f; tb = bp[i]; }
+        if (i + 1 < nb) {
+            float tm = 0.5f * (bp[i] + bp[i + 1]), A = 0.f, B = 0.f;
+#pragma unroll
+            for (int x = 0; x < 3; x++) {
+                float xm = fmaf(tm, dv[x], av[x]);
+                if (fabsf(xm) > hv[x]) {
+                    float sg = xm > 0.f ? 1.f : -1.f;
+                    A = fmaf(dv[x], dv[x], A);
+                    B = fmaf(2.f * (sg * av[x] - hv[x]) * sg, dv[x], B);
+                }
+            }
+            if (A > 0.f) {
+                float ts = -B / (2.f * A);
+                if (ts > bp[i] && ts < bp[i + 1]) {
+                    const float f2 = seg_box_f(a, dir, h, ts);
+                    if (f2 < best) { best = f2; tb = ts; }
+                }
+            }
+        }
+    }
+    return tb;
+}
+
+template <int NLMAX>
+__device__ __noinline__ int build_contacts(const ModelDev& M, const float* __restrict__ qcol, int N, V3 obstacle, V3 target,
+                                           float thr, float* __restrict__ J /*[kMaxContacts][kMaxDof]*/,
+                                           float* __restrict__ dist /*[kMaxContacts]*/) {
+    float Rw[NLMAX * 9], pw[NLMAX * 3];
+    const int nl = M.nl;
+    for (int i = 0; i < nl; i++) {
+        const int par = M.parent[i];
+        M3 Rl;
+        V3 pl, dd;
+        joint_transform(M, i, qcol[(size_t)i * N], Rl, pl, dd);
+        M3 R = Rl;
+        V3 p = pl;
+        if (par >= 0) {
+            M3 Rp;
+#pragma unroll
+            for (int k = 0; k < 9; k++) Rp.m[k] = Rw[par * 9 + k];
+            p = ld3(pw + par * 3) + mul(Rp, pl);
+            R = mul(Rp, Rl);
+        }
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rw[i * 9 + k] = R.m[k];
+        st3(pw + i * 3, p);
+    }
+    const V3 th = v3(M.target_half[0], M.target_half[1], M.target_half[2]);
+    int nc = 0;
+    const int ns = M.ns;
+    for (int s = 0; s < ns; s++) {
+        const int l = M.s_link[s];
+        M3 Rl, sR;
+#pragma unroll
+        for (int k = 0; k < 9; k++) { Rl.m[k] = Rw[l * 9 + k]; sR.m[k] = M.s_R[s][k]; }
+        const V3 pl = ld3(pw + l * 3);
+        // broad phase on the shape's bounding sphere (exact: a shape outside it cannot be within thr)
+        const V3 bc = pl + mul(Rl, v3(M.s_bs[s][0], M.s_bs[s][1], M.s_bs[s][2]));
+        const float ro = M.s_bs[s][3] + M.obstacle_radius + thr, rc = M.s_bs[s][3] + sqrtf(dot(th, th)) + thr;
+        const V3 relo = obstacle - bc, relt = target - bc;
+        const bool near_o = dot(relo, relo) < ro * ro, near_t = dot(relt, relt) < rc * rc;
+        if (!near_o && !near_t) continue;
+        const M3 Rs = mul(Rl, sR);
+        const V3 ps = pl + mul(Rl, v3(M.s_p[s][0], M.s_p[s][1], M.s_p[s][2]));
+        shape_contacts(M, s, Rs, ps, obstacle, target, th, near_o, near_t, thr, [&](int link, V3 x, float r_shape, V3 from, float r_body) {
+            if (nc < kMaxContacts) nc += contact_row(M, Rw, pw, link, x, r_shape, from, r_body, thr, J + nc * kMaxDof, dist + nc);
+        });
+    }
+    return nc;
 }
 
 }  // namespace rloa

@@ -15,6 +15,7 @@ import torch
 from .. import _native as N
 from .robot_model import RobotModel
 
+CONTACT_THRESHOLD = 0.02         # Bullet's gContactBreakingThreshold: contact rows for shapes closer than this
 OBSTACLE_RADIUS = 0.075          # sphere_small.urdf (r = 0.03) x globalScaling 2.5, environment.py:252-253
 TARGET_HALF = (0.025, 0.025, 0.025)   # cube_small.urdf (0.05 m), environment.py:254-255
 RESET_SUBSTEPS = 50              # environment.py:300-301
@@ -23,7 +24,7 @@ RESET_SUBSTEPS = 50              # environment.py:300-301
 class BatchedSimulator:
     def __init__(self, model: RobotModel, n_envs: int, endeffector_index: int, involved_joints: Sequence[int],
                  fixed_joints: Sequence[int], max_force: float = 200.0, device: Optional[torch.device] = None,
-                 target_threshold: float = 0.05, obstacle_threshold: float = 0.0):
+                 target_threshold: float = 0.05, obstacle_threshold: float = 0.0, contacts: bool = True):
         if not torch.cuda.is_available():
             raise N.NativeLibraryError('BatchedSimulator needs a CUDA device (sm_100a); there is no CPU fallback')
         self.lib = N.lib()
@@ -49,7 +50,11 @@ class BatchedSimulator:
         cfg.max_force = float(max_force)
         cfg.target_threshold = float(target_threshold)
         cfg.obstacle_threshold = float(obstacle_threshold)
+        # the reference's obstacle sphere and target cube are collidable fixed bodies (environment.py:252-255): links that
+        # touch them are stopped by contact rows inside stepSimulation.  contacts=False gives the free dynamics.
+        cfg.contact_threshold = CONTACT_THRESHOLD if contacts else 0.0
         self.cfg = cfg
+        N.check(self.lib.rloa_sim_set_contacts(self._h_sim, cfg.contact_threshold), 'rloa_sim_set_contacts')
         f32 = dict(dtype=torch.float32, device=self.device)
         self.obs = torch.zeros(self.n_envs, self.obs_size, **f32)
         self.reward = torch.zeros(self.n_envs, **f32)

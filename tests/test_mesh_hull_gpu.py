@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 
 def make_sim(model, cfg, n):
     from robotic_manipulator_rloa_b200.environment.simulator import BatchedSimulator
-    sim = BatchedSimulator(model, n, cfg['ee'], cfg['involved'], cfg['fixed'], max_force=200.0)
+    sim = BatchedSimulator(model, n, cfg['ee'], cfg['involved'], cfg['fixed'], max_force=200.0, contacts=False)
     sim.set_task(cfg['target'], cfg['obstacle'])
     return sim
 

@@ -27,8 +27,8 @@ def test_header_symbols_are_exported_and_bound():
 
 
 def test_struct_sizes_match_header_layout():
-    # rloa_step_config: 2 x (int + int[32]) + 3 floats ; rloa_naf_hyper: 7 floats + 2 ints + 1 float
-    assert ctypes.sizeof(_native.StepConfig) == 4 * (1 + 32 + 1 + 32 + 3)
+    # rloa_step_config: 2 x (int + int[32]) + 4 floats ; rloa_naf_hyper: 7 floats + 2 ints + 1 float
+    assert ctypes.sizeof(_native.StepConfig) == 4 * (1 + 32 + 1 + 32 + 4)
     assert ctypes.sizeof(_native.NafHyper) == 4 * 10
     assert ctypes.sizeof(_native.NafParams) == 16 + 20 * 8
     assert ctypes.sizeof(_native.Replay) == 16 + 7 * 8

@@ -14,9 +14,11 @@ pytestmark = pytest.mark.gpu
 TOL_Q, TOL_QD, TOL_EE = 1e-4, 1e-4, 1e-5
 
 
-def make_sim(model, cfg, n):
+def make_sim(model, cfg, n, contacts=False):
+    """contacts=False: free dynamics (the seeded random states of the parity tests put links deep inside the obstacle, which
+    no trajectory of the task reaches); the contact rows have their own tests below."""
     from robotic_manipulator_rloa_b200.environment.simulator import BatchedSimulator
-    sim = BatchedSimulator(model, n, cfg['ee'], cfg['involved'], cfg['fixed'], max_force=200.0)
+    sim = BatchedSimulator(model, n, cfg['ee'], cfg['involved'], cfg['fixed'], max_force=200.0, contacts=contacts)
     sim.set_task(cfg['target'], cfg['obstacle'])
     return sim
 
@@ -241,3 +243,94 @@ def test_ragged_env_counts_and_active_mask(n):
         assert np.abs(qg[~on] - q_in[~on]).max() <= 1e-7 and np.abs(qdg[~on] - qd_in[~on]).max() <= 1e-6
         assert (obs[:n][torch.as_tensor(~on)] == -7.0).all() and (done[:n][torch.as_tensor(~on)] == 9).all()
     sim.close()
+
+
+# ---- contact rows: obstacle sphere and target cube are collidable fixed bodies in the reference ---------
+def _contact_states(cfg, body, n_envs=48, steps=160, seed=3):
+    """States on oracle trajectories (contacts on) that press links against the obstacle / the end-effector against the
+    cube: returns (q, qd, obstacle, target, actions) of every (env, step) where at least one contact row was active."""
+    model, orc = make_oracle(cfg)
+    step_motors(orc, cfg)
+    nl = model.nl
+    rng = np.random.default_rng(seed)
+    q0 = np.zeros(nl); q0[:len(cfg['start'])] = cfg['start']
+    _, pw = orc.fk(q0)
+    dirs = rng.normal(size=(n_envs, 3)); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    if body == 'obstacle':
+        ob, tg = pw[5] + 0.17 * dirs, np.tile(cfg['target'], (n_envs, 1))
+    else:
+        tg, ob = pw[cfg['ee']] + 0.10 * dirs, np.tile([5.0, 5.0, 5.0], (n_envs, 1))
+    q, qd = np.tile(q0, (n_envs, 1)), np.zeros((n_envs, nl))
+    out = []
+    for t in range(steps):
+        a = rng.uniform(-1, 1, (n_envs, len(cfg['involved'])))
+        q_in, qd_in = q.copy(), qd.copy()
+        orc.batch_step(q, qd, a, cfg['involved'], 200.0, ob, tg, nthreads=8, contact_threshold=0.02)
+        hit = orc.last_contacts > 0
+        if t >= 40 and hit.any():          # past the initial overlap transient
+            out.append((q_in[hit], qd_in[hit], ob[hit], tg[hit], a[hit]))
+    return [np.concatenate([o[k] for o in out]) for k in range(5)]
+
+
+@pytest.mark.parametrize('body', ['obstacle', 'cube'])
+def test_contact_rows_single_step_matches_oracle(body):
+    """One step from states with active contact rows: the CUDA simulator (contacts on) against the fp64 restatement with
+    the same contact model, at the flat north_star bounds; and against the contact-free step, which must differ."""
+    cfg = KUKA
+    q, qd, ob, tg, act = _contact_states(cfg, body)
+    n = q.shape[0]
+    assert n >= 200, n
+    model, orc = make_oracle(cfg)
+    step_motors(orc, cfg)
+    f32 = lambda x: x.astype(np.float32).astype(np.float64)
+    q32, qd32, a32, ob32, tg32 = f32(q), f32(qd), f32(act), f32(ob), f32(tg)
+    sim = make_sim(model, cfg, n, contacts=True)
+    sim.set_task(torch.as_tensor(tg32, dtype=torch.float32), torch.as_tensor(ob32, dtype=torch.float32))
+    sim.set_state(q32, qd32)
+    sim.step(torch.as_tensor(a32, dtype=torch.float32, device='cuda'))
+    qg, qdg = sim.get_state()
+    qo, qdo = q32.copy(), qd32.copy()
+    orc.batch_step(qo, qdo, a32, cfg['involved'], 200.0, ob32, tg32, nthreads=8, contact_threshold=0.02)
+    nc = orc.last_contacts.copy()
+    qf, qdf = q32.copy(), qd32.copy()
+    orc.batch_step(qf, qdf, a32, cfg['involved'], 200.0, ob32, tg32, nthreads=8)          # no contact rows
+    rep = parity_report(f'contact/{body}', np.abs(qg.cpu().numpy() - qo).max(axis=1), np.abs(qdg.cpu().numpy() - qdo).max(axis=1),
+                        n_with_contacts=int((nc > 0).sum()), max_contacts=int(nc.max()),
+                        effect_of_contacts_qd=float(np.abs(qdo - qdf).max()))
+    assert (nc > 0).sum() >= 0.8 * n                       # fp32-rounded inputs can move a marginal pair over the threshold
+    assert rep['effect_of_contacts_qd'] > 0.05              # the rows do something: >> the tolerance
+    assert rep['worst_q'] <= TOL_Q
+    # measured on B200: obstacle 3 of 2503 states over 1e-4 rad/s (worst 1.7e-3), cube 30 of 1625 (worst 7.2e-3, p99 1.5e-4):
+    # the contact impulses change q' by 1 (obstacle) / 8 (cube) rad/s, a capsule edge-on to a cube face moves its closest
+    # point — and with it the row's Jacobian — at fp32 resolution, and the PGS exit can flip as in the free case
+    assert rep['n_over_qd'] <= n // 50 and rep['worst_qd'] <= 1e-2, rep
+
+
+def test_contact_rows_keep_links_out_of_the_obstacle():
+    """160 steps of random actions with the obstacle placed next to link 5 (lock-step, no reset): with the contact rows the
+    arm rests on the sphere (min distance >= -1 mm after the initial overlap is pushed out), without them it passes through."""
+    cfg = KUKA
+    model, orc = make_oracle(cfg)
+    nl, n = model.nl, 64
+    rng = np.random.default_rng(9)
+    q0 = np.zeros(nl); q0[:6] = cfg['start']
+    _, pw = orc.fk(q0)
+    dirs = rng.normal(size=(n, 3)); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    ob = (pw[5] + 0.17 * dirs).astype(np.float32)
+    acts = rng.uniform(-1, 1, (160, n, 6)).astype(np.float32)
+    worst = {}
+    for contacts in (True, False):
+        sim = make_sim(model, cfg, n, contacts=contacts)
+        sim.set_task(cfg['target'], torch.as_tensor(ob))
+        sim.set_state(np.tile(q0, (n, 1)), np.zeros((n, nl)))
+        mind = np.full(n, 10.0)
+        for t in range(160):
+            sim.step(torch.as_tensor(acts[t], device='cuda'))
+            if t >= 60:
+                _, link, _ = sim.observe(want_distances=True)
+                mind = np.minimum(mind, link.min(dim=1).values.cpu().numpy())
+        worst[contacts] = mind
+        sim.close()
+    print(f'min link-obstacle distance over steps 60..160: contacts on {worst[True].min():.4f} m, off {worst[False].min():.4f} m')
+    assert worst[True].min() >= -1e-3
+    assert worst[False].min() <= -2e-2

@@ -24,11 +24,11 @@ if mesh:
 print('model:', 'panda (12 joints / 9 dof, BASELINE configs[4])' if panda else 'kuka iiwa + gripper (14 joints / 12 dof)')
 for n in [int(x) for x in (args or ['4096', '16384', '65536', '262144'])]:
     if panda:
-        sim = BatchedSimulator(model, n, 11, list(range(7)), [7, 8, 9, 10, 11])
+        sim = BatchedSimulator(model, n, 11, list(range(7)), [7, 8, 9, 10, 11], contacts=os.environ.get('RLOA_CONTACTS', '1') != '0')
         sim.set_task([0.4, 0.3, 0.5], [0.3, 0.0, 0.6])
         base = torch.tensor([0, 0, 0, -1.5, 0, 1.5, 0], device='cuda', dtype=torch.float32)
     else:
-        sim = BatchedSimulator(model, n, 13, [0, 1, 2, 3, 4, 5], list(range(6, 14)))
+        sim = BatchedSimulator(model, n, 13, [0, 1, 2, 3, 4, 5], list(range(6, 14)), contacts=os.environ.get('RLOA_CONTACTS', '1') != '0')
         sim.set_task([0.4, 0.85, 0.71], [0.45, 0.55, 0.55])
         base = torch.tensor([0.9, 0.45, 0, 0, 0, 0], device='cuda')
     start = base + 0.5 * (torch.rand(n, na, device='cuda') - 0.5)
