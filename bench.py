@@ -307,7 +307,7 @@ def workload_config(args, c, where):
             'initial_positions_variation_range': list(c['var']),
             'contacts': 'normal contact rows against the obstacle sphere and the target cube (threshold 0.02 m), as in the reference world',
             'l2': 'flushed between timed step pairs (256 MiB fill, untimed)' if where == 'gpu' else 'n/a',
-            'steady_state': f'{2 * PREROLL_PAIRS} untimed iterations before the timed region' if where == 'gpu' else 'n/a',
+            'steady_state': f'{2 * getattr(args, "preroll", PREROLL_PAIRS)} untimed iterations before the timed region' if where == 'gpu' else 'n/a',
             'naf_trunk': ('tcgen05: bf16 operands (tf32 for the S-wide input layer), fp32 TMEM accumulate (fused policy kernel + trunk); heads, BatchNorm, '
                           'backward and optimiser fp32' if getattr(args, 'trunk', 'tc') == 'tc' and where == 'gpu' else 'fp32'),
             'launch': 'eager' if getattr(args, 'no_graph', False) or where == 'cpu' else 'cuda-graph of 2 loop iterations'}
@@ -387,7 +387,7 @@ def train_workload(ctx, args, c, steps, full):
     graphed = bool(use_graph and loop.capture())
     # ---- roll past the start-up transient: every env has finished an episode and gone through its 50 reset sub-steps
     # at least once, so the share of envs emitting transitions is the stationary one ----
-    for _ in range(PREROLL_PAIRS):
+    for _ in range(args.preroll):
         if graphed:
             loop.replay_pair()
         else:
@@ -815,6 +815,8 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly instead of replaying the CUDA graph')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-extras', action='store_true', help='skip the other_configs sub-records')
+    ap.add_argument('--preroll', type=int, default=PREROLL_PAIRS,
+                    help='untimed iteration pairs before the timed region (steady state needs >= 225; profiling runs pass a small number)')
     args = ap.parse_args()
     if args.impl == 'reference':
         reference_arm(args)

@@ -154,6 +154,11 @@ int rloa_sim_step(rloa_sim* s, const rloa_step_config* cfg, const float* actions
 /* Contact breaking threshold used by rloa_sim_reset's sub-steps (Environment.reset steps the same world as step, contact
  * rows included; rloa_sim_step takes its threshold from the config).  0 = off. */
 int rloa_sim_set_contacts(rloa_sim* s, float contact_threshold);
+/* Number of contact rows each env's NEXT stepSimulation will carry (what the last step's distance pass found within the
+ * contact threshold: Bullet's contact manifold points of the arm against the two bodies of environment.py:252-255);
+ * -1 = unknown, the pose was set from outside a step and the collision phase runs inside the next step.
+ * counts: int32 [n_envs] DEVICE. */
+int rloa_sim_contact_counts(rloa_sim* s, int32_t* counts, void* stream);
 
 /* Software pipelining of the step.  A stepSimulation has an action-independent half (forward kinematics,
  * articulated-body factorisation, free accelerations, M^-1: two of the three kernels) that only needs the

@@ -98,6 +98,7 @@ SIGNATURES = {
     'rloa_sim_clear': (C.c_int, [_VP, _VP]),
     'rloa_sim_step': (C.c_int, [_VP, C.POINTER(StepConfig), _fp, _fp, _fp, _fp, _fp, _fp, _VP]),
     'rloa_sim_set_contacts': (C.c_int, [_VP, _F]),
+    'rloa_sim_contact_counts': (C.c_int, [_VP, _VP, _VP]),
     'rloa_sim_prepare': (C.c_int, [_VP, _VP]),
     'rloa_sim_join': (C.c_int, [_VP, _VP]),
     'rloa_sim_begin_reset': (C.c_int, [_VP, _fp, _fp, _I, _I, _VP]),

@@ -66,6 +66,20 @@ struct PgsState<D, false> {
     __device__ __forceinline__ float get(int d) const { return dv[d]; }
     __device__ __forceinline__ float mat(int a, int b) const { return Mi[tri(a, b)]; }
     __device__ __forceinline__ void add(int d, float x) { dv[d] += x; }
+    // contact rows: J and U = M^-1 J^T are stored as pairs (dof 2k, 2k + 1), zero beyond D
+    __device__ __forceinline__ float cdot(const float2* __restrict__ j) const {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const float jk = (k & 1) ? j[k >> 1].y : j[k >> 1].x;
+            if (k & 1) a1 = fmaf(jk, dv[k], a1); else a0 = fmaf(jk, dv[k], a0);
+        }
+        return a0 + a1;
+    }
+    __device__ __forceinline__ void caxpy(float delta, const float2* __restrict__ u) {
+#pragma unroll
+        for (int k = 0; k < D; k++) dv[k] = fmaf(delta, (k & 1) ? u[k >> 1].y : u[k >> 1].x, dv[k]);
+    }
     // dv += delta * M^-1[d][:]; the component the next row reads (`first`) is issued first
     __device__ __forceinline__ void axpy(int d, float delta, int first) {
         if (first >= 0 && first < D) dv[first] = fmaf(delta, Mi[tri(d, first)], dv[first]);
@@ -97,6 +111,22 @@ struct PgsState<D, true> {
     __device__ __forceinline__ float mat(int a, int b) const { return (b & 1) ? M[a][b >> 1].y : M[a][b >> 1].x; }
     __device__ __forceinline__ void add(int d, float x) {
         if (d & 1) dv[d >> 1].y += x; else dv[d >> 1].x += x;
+    }
+    // contact rows: J and U = M^-1 J^T are stored as the same pairs as dv (zero beyond D), so the row's J dv is DP packed
+    // FFMA2 in two chains and its update another DP - a third of the scalar instruction count of a row visit, which is what a
+    // lone warp per SM pays for
+    __device__ __forceinline__ float cdot(const float2* __restrict__ j) const {
+        float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < DP; k++) {
+            if (k & 1) a1 = __ffma2_rn(j[k], dv[k], a1); else a0 = __ffma2_rn(j[k], dv[k], a0);
+        }
+        return (a0.x + a0.y) + (a1.x + a1.y);
+    }
+    __device__ __forceinline__ void caxpy(float delta, const float2* __restrict__ u) {
+        const float2 dl = make_float2(delta, delta);
+#pragma unroll
+        for (int k = 0; k < DP; k++) dv[k] = __ffma2_rn(dl, u[k], dv[k]);
     }
     // dv += delta * M^-1[d][:]; the pair holding the component the next row reads (`first`) is issued first
     __device__ __forceinline__ void axpy(int d, float delta, int first) {
@@ -199,34 +229,39 @@ sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_c
         // as collidable fixed bodies).  Only arms flagged `near` by the previous step's distance pass pay for the
         // collision phase; their rows live in local memory (dynamic contact index) ----
         int nc = 0;
-        float cJ[kMaxContacts * kMaxDof], cU[kMaxContacts * kMaxDof], crhs[kMaxContacts], cjdi[kMaxContacts], capp[kMaxContacts],
-            cjmj[kMaxContacts];
+        constexpr int kCP = kMaxDof / 2;
+        __align__(16) float2 cJ2[kMaxContacts * kCP], cU2[kMaxContacts * kCP];        // pairs (dof 2k, 2k + 1) like dv
+        float* cJ = reinterpret_cast<float*>(cJ2);
+        float* cU = reinterpret_cast<float*>(cU2);
+        float crhs[kMaxContacts], cjdi[kMaxContacts], capp[kMaxContacts], cjmj[kMaxContacts];
         const int nflag = cfg.contact_thr > 0.f ? S.near[env] : 0;
-        if (nflag != 0 && cfg.contact_dbg != 2) {
+        if (nflag != 0 && !(cfg.contact_dbg & 2)) {
             float cd[kMaxContacts];
             if (nflag > 0) {        // rows left by the previous step's distance pass (same pose)
                 nc = min(nflag, kMaxContacts);
                 const float* row = S.crow + (size_t)env * kMaxContacts * kContactRec;
                 for (int c = 0; c < nc; c++) {
 #pragma unroll
-                    for (int a = 0; a < D; a++) cJ[c * kMaxDof + a] = row[c * kContactRec + a];
+                    for (int a = 0; a < kMaxDof; a++) cJ[c * kMaxDof + a] = a < D ? row[c * kContactRec + a] : 0.f;
                     cd[c] = row[c * kContactRec + kMaxDof];
                 }
             } else {                // the pose was set from outside a step: collision phase from scratch
                 const V3 tg0 = ld3(S.target + 3 * (size_t)env), ob0 = ld3(S.obstacle + 3 * (size_t)env);
                 nc = build_contacts<NLMAX>(M, S.q + env, N, ob0, tg0, cfg.contact_thr, cJ, cd);
             }
-            if (cfg.contact_dbg == 1) nc = 0;          // diagnostics: pay for the collision phase only
+            if (cfg.contact_dbg & 1) nc = 0;          // diagnostics: pay for the collision phase only
             for (int c = 0; c < nc; c++) {
                 float jmj = 0.f, rel = 0.f;
 #pragma unroll
-                for (int a = 0; a < D; a++) {
+                for (int a = 0; a < kMaxDof; a++) {
                     float u = 0.f;
+                    if (a < D) {
 #pragma unroll
-                    for (int b = 0; b < D; b++) u = fmaf(P.mat(a, b), cJ[c * kMaxDof + b], u);     // (M^-1 J^T)_a
+                        for (int b = 0; b < D; b++) u = fmaf(P.mat(a, b), cJ[c * kMaxDof + b], u);     // (M^-1 J^T)_a
+                        jmj = fmaf(cJ[c * kMaxDof + a], u, jmj);
+                        rel = fmaf(cJ[c * kMaxDof + a], qs0[a], rel);
+                    }
                     cU[c * kMaxDof + a] = u;
-                    jmj = fmaf(cJ[c * kMaxDof + a], u, jmj);
-                    rel = fmaf(cJ[c * kMaxDof + a], qs0[a], rel);
                 }
                 const float jd = jmj > 1e-12f ? 1.f / jmj : 0.f;
                 const float d = cd[c];
@@ -302,16 +337,11 @@ sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_c
 #pragma unroll
                 for (int c = 0; c < kMaxContacts; c++) {
                     if (c < nc && cjdi[c] != 0.f) {
-                        float jv[3] = {0.f, 0.f, 0.f};        // three chains instead of one of D dependent FMAs
-#pragma unroll
-                        for (int a = 0; a < D; a++) jv[a % 3] = fmaf(cJ[c * kMaxDof + a], P.get(a), jv[a % 3]);
-                        const float jdv = (jv[0] + jv[1]) + jv[2];
-                        float delta = crhs[c] - jdv * cjdi[c];
-                        const float sum = capp[c] + delta;
-                        if (sum < 0.f) { delta = -capp[c]; capp[c] = 0.f; }
-                        else capp[c] = sum;
-#pragma unroll
-                        for (int a = 0; a < D; a++) P.add(a, delta * cU[c * kMaxDof + a]);
+                        const float jdv = P.cdot(cJ2 + c * kCP);
+                        const float sum = fmaxf(fmaf(-jdv, cjdi[c], capp[c] + crhs[c]), 0.f);      // applied impulse >= 0
+                        const float delta = sum - capp[c];
+                        capp[c] = sum;
+                        P.caxpy(delta, cU2 + c * kCP);
                         const float dvel = delta * cjmj[c];
                         resid = fmaxf(resid, dvel * dvel);
                     }
@@ -1067,6 +1097,13 @@ static int launch_substep(const rloa_sim* s, const StepCfgDev& c, int mode, cons
 extern "C" int rloa_sim_set_contacts(rloa_sim* s, float contact_threshold) {
     RLOA_REQUIRE(s != nullptr && contact_threshold >= 0.f, "rloa_sim_set_contacts: bad argument");
     s->contact_thr = contact_threshold;
+    return RLOA_OK;
+}
+
+extern "C" int rloa_sim_contact_counts(rloa_sim* s, int32_t* counts, void* stream) {
+    RLOA_REQUIRE(s != nullptr && counts != nullptr, "rloa_sim_contact_counts: bad argument");
+    RLOA_CUDA(cudaMemcpyAsync(counts, s->a.near, sizeof(int32_t) * (size_t)s->a.n_envs, cudaMemcpyDeviceToDevice,
+                              as_stream(stream)));
     return RLOA_OK;
 }
 

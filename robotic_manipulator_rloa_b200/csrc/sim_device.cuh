@@ -92,7 +92,8 @@ struct StepCfgDev {
     float pos_maximp;                       // 1e5 * dt (pybullet POSITION_CONTROL default force)
     float target_thr, obstacle_thr;
     float contact_thr;                      // contact breaking threshold (Bullet: 0.02); 0 = contact rows off
-    int contact_dbg;                        // RLOA_CONTACT_DEBUG: 1 = collision phase only, 2 = near flags only (timing splits)
+    int contact_dbg;                        // RLOA_CONTACT_DEBUG bits: 1 = drop the rows after loading them, 2 = do not load them
+                                            // (collision phase only): timing splits, tools/prof_contacts.py
 };
 
 struct V3 {
@@ -249,6 +250,32 @@ __device__ __noinline__ float segment_box(V3 a, V3 b, V3 h) {
 // order as oracle/bullet_restatement.c::find_contacts.
 __device__ __noinline__ float segment_box_argmin(V3 a, V3 b, V3 h);
 
+// sphere / capsule (position ps, world axis ax) against the axis-aligned target cube.  Needs the shape's axis only, not its
+// whole frame.  Cheap exact pre-test first: the cube lies inside its bounding sphere, so a shape farther than that from the
+// cube's centre cannot be a contact (for a capsule: distance from the centre to its axis) - the piecewise segment / box routine
+// then runs only for shapes within a few centimetres of the cube.
+template <class Add>
+__device__ __forceinline__ void cube_contact(int type, int l, V3 dim, V3 ps, V3 ax, V3 target, V3 th, float thr, Add&& add) {
+    const float r_s = dim.x;
+    {
+        const V3 t = target - ps;
+        const float tz = dot(t, ax);
+        const float ez = type == RLOA_SHAPE_CAPSULE ? tz - fminf(fmaxf(tz, -dim.y), dim.y) : tz;
+        const float r2 = fmaxf(fmaf(ez, ez, fmaf(-tz, tz, dot(t, t))), 0.f);
+        const float dc = sqrtf(r2) - r_s - sqrtf(dot(th, th));
+        if (!(dc < thr + 1e-5f)) return;         // 1e-5: the pre-test is a filter, rounding must not decide a contact
+    }
+    V3 x = ps;
+    if (type == RLOA_SHAPE_CAPSULE) {
+        const V3 a1 = ps - target - dim.y * ax, b1 = ps - target + dim.y * ax;
+        const float tb = segment_box_argmin(a1, b1, th);
+        x = target + a1 + tb * (b1 - a1);
+    }
+    const V3 c = x - target;
+    const V3 y = target + v3(fminf(fmaxf(c.x, -th.x), th.x), fminf(fmaxf(c.y, -th.y), th.y), fminf(fmaxf(c.z, -th.z), th.z));
+    add(l, x, r_s, y, 0.f);
+}
+
 template <class Add>
 __device__ __forceinline__ void shape_contacts(const ModelDev& M, int s, const M3& Rs, V3 ps, V3 obstacle, V3 target, V3 th,
                                                bool near_o, bool near_t, float M_contact_thr, Add&& add) {
@@ -269,26 +296,7 @@ __device__ __forceinline__ void shape_contacts(const ModelDev& M, int s, const M
         }
         add(l, x, r_s, obstacle, M.obstacle_radius);
     }
-    if (type != RLOA_SHAPE_BOX && near_t) {   // target cube
-        // cheap exact pre-test: the cube lies inside its bounding sphere, so a shape farther than that from the cube's centre
-        // cannot be a contact (for a capsule: distance from the centre to its axis) — the piecewise segment / box routine
-        // below then runs only for shapes within a few centimetres of the cube
-        {
-            const V3 t_s = mulT(Rs, target - ps);
-            const float ez = type == RLOA_SHAPE_CAPSULE ? t_s.z - fminf(fmaxf(t_s.z, -dim.y), dim.y) : t_s.z;
-            const float dc = sqrtf(fmaf(t_s.x, t_s.x, fmaf(t_s.y, t_s.y, ez * ez))) - r_s - sqrtf(dot(th, th));
-            if (!(dc < M_contact_thr)) return;
-        }
-        V3 x = ps;
-        if (type == RLOA_SHAPE_CAPSULE) {
-            const V3 a1 = ps - target - dim.y * ax, b1 = ps - target + dim.y * ax;
-            const float tb = segment_box_argmin(a1, b1, th);
-            x = target + a1 + tb * (b1 - a1);
-        }
-        const V3 c = x - target;
-        const V3 y = target + v3(fminf(fmaxf(c.x, -th.x), th.x), fminf(fmaxf(c.y, -th.y), th.y), fminf(fmaxf(c.z, -th.z), th.z));
-        add(l, x, r_s, y, 0.f);
-    }
+    if (type != RLOA_SHAPE_BOX && near_t) cube_contact(type, l, dim, ps, ax, target, th, M_contact_thr, add);
 }
 
 // one contact: keep it when closer than thr, write its Jacobian row J[d] = d(n . p_contact)/dq_d (0 off the link's chain) and
@@ -318,29 +326,64 @@ __device__ __forceinline__ int contact_row(const ModelDev& M, const float* Rw, c
     return 1;
 }
 
-// the same with the world joint axes aw[k] and pivots pv[k] cached by the kinematics loop (12 instructions per chain link
-// instead of two matrix-vector products)
-__device__ __forceinline__ int contact_row_cached(const ModelDev& M, const float* aw, const float* pv, int link, V3 x, float r_shape,
-                                                  V3 from, float r_body, float thr, float* __restrict__ Jc, float* __restrict__ dist_out) {
+constexpr int kContactRec = kMaxDof + 1;      // floats per stored contact row: J[kMaxDof] | signed distance
+
+// The distance pass of a step records its contact CANDIDATES (link, normal, point on the link, distance) while it walks the
+// shapes and writes their Jacobian rows afterwards, in one walk over the links shared by all candidates: the world axis and
+// pivot of a joint are formed once and serve every candidate whose chain holds the link.  Arms without a candidate - nearly
+// all of them, nearly always - pay nothing for the rows.
+struct ContactCands {
+    int n;
+    int link[kMaxContacts];
+    V3 nrm[kMaxContacts], pA[kMaxContacts];
+    float dist[kMaxContacts];
+};
+
+__device__ __forceinline__ void contact_candidate(ContactCands& cc, int link, V3 x, float r_shape, V3 from, float r_body, float thr) {
+    if (cc.n >= kMaxContacts) return;
     const V3 v = x - from;
     const float L = sqrtf(dot(v, v));
-    if (L < 1e-9f) return 0;
+    if (L < 1e-9f) return;
     const float d = L - r_shape - r_body;
-    if (!(d < thr)) return 0;
+    if (!(d < thr)) return;
     const V3 n = (1.f / L) * v;
-    const V3 pA = x - r_shape * n;
-    for (int k = 0; k < kMaxDof; k++) Jc[k] = 0.f;
-    for (int k = link; k >= 0; k = M.parent[k]) {
-        const int di = M.dofidx[k];
-        if (di < 0) continue;
-        const V3 a = ld3(aw + k * 3);
-        Jc[di] = M.jtype[k] == RLOA_JOINT_PRISMATIC ? dot(n, a) : dot(n, cross(a, pA - ld3(pv + k * 3)));
-    }
-    *dist_out = d;
-    return 1;
+    cc.link[cc.n] = link;
+    cc.nrm[cc.n] = n;
+    cc.pA[cc.n] = x - r_shape * n;
+    cc.dist[cc.n] = d;
+    cc.n++;
 }
 
-constexpr int kContactRec = kMaxDof + 1;      // floats per stored contact row: J[kMaxDof] | signed distance
+__device__ __noinline__ void contact_rows_from_candidates(const ModelDev& M, const float* Rw, const float* pw, const ContactCands& cc,
+                                                          float* __restrict__ crow) {
+    unsigned anc[kMaxContacts], any = 0;
+#pragma unroll
+    for (int c = 0; c < kMaxContacts; c++) {
+        anc[c] = 0;
+        if (c < cc.n) {
+            for (int k = cc.link[c]; k >= 0; k = M.parent[k]) anc[c] |= 1u << k;
+            for (int a = 0; a < kMaxDof; a++) crow[c * kContactRec + a] = 0.f;
+            crow[c * kContactRec + kMaxDof] = cc.dist[c];
+        }
+        any |= anc[c];
+    }
+    const int nl = M.nl;
+    for (int k = 0; k < nl; k++) {
+        const int di = M.dofidx[k];
+        if (di < 0 || !((any >> k) & 1u)) continue;
+        M3 Rk;
+#pragma unroll
+        for (int e = 0; e < 9; e++) Rk.m[e] = Rw[k * 9 + e];
+        const V3 aw = mul(Rk, v3(M.axis[k][0], M.axis[k][1], M.axis[k][2]));
+        const V3 pivot = ld3(pw + k * 3) - mul(Rk, v3(M.d[k][0], M.d[k][1], M.d[k][2]));
+        const bool prismatic = M.jtype[k] == RLOA_JOINT_PRISMATIC;
+#pragma unroll
+        for (int c = 0; c < kMaxContacts; c++)
+            if ((anc[c] >> k) & 1u)
+                crow[c * kContactRec + di] = prismatic ? dot(cc.nrm[c], aw) : dot(cc.nrm[c], cross(aw, cc.pA[c] - pivot));
+    }
+}
+
 
 struct ObsOut {
     float ee_target;     // closest distance end-effector link <-> target cube (10 when no shape)
@@ -358,7 +401,6 @@ __device__ __forceinline__ ObsOut fk_and_distances(const ModelDev& M, const floa
                                                    float* __restrict__ link_dist, int ld_stride, float contact_thr = 0.f,
                                                    bool want_near = false, float* __restrict__ crow = nullptr) {
     float Rw[NLMAX * 9], pw[NLMAX * 3];
-    float aw[NLMAX * 3], pv[NLMAX * 3];          // world joint axes / pivots for the contact Jacobians (want_near only)
     const int nl = M.nl;
     for (int i = 0; i < nl; i++) {
         const int par = M.parent[i];
@@ -377,10 +419,6 @@ __device__ __forceinline__ ObsOut fk_and_distances(const ModelDev& M, const floa
 #pragma unroll
         for (int k = 0; k < 9; k++) Rw[i * 9 + k] = R.m[k];
         st3(pw + i * 3, p);
-        if (want_near) {
-            st3(aw + i * 3, mul(R, v3(M.axis[i][0], M.axis[i][1], M.axis[i][2])));
-            st3(pv + i * 3, p - mul(R, dd));
-        }
     }
     ObsOut o;
     o.ee_pos = ld3(pw + M.ee_link * 3);
@@ -393,6 +431,11 @@ __device__ __forceinline__ ObsOut fk_and_distances(const ModelDev& M, const floa
     const int ns = M.ns;
     const V3 th = v3(M.target_half[0], M.target_half[1], M.target_half[2]);
     const float reach = M.obstacle_radius + fmaxf(obstacle_thr, 0.f);
+    ContactCands cc;
+    cc.n = 0;
+    auto candidate = [&](int link, V3 x, float r_shape, V3 from, float r_body) {
+        contact_candidate(cc, link, x, r_shape, from, r_body, contact_thr);
+    };
     for (int s = 0; s < ns; s++) {
         const int l = M.s_link[s];
         M3 Rl, sR;
@@ -408,31 +451,33 @@ __device__ __forceinline__ ObsOut fk_and_distances(const ModelDev& M, const floa
             const V3 rel = obstacle - bc;
             const float rr = M.s_bs[s][3] + reach + (want_near ? contact_thr : 0.f);
             far = dot(rel, rel) >= rr * rr;
-            if (want_near) {        // bounding sphere against the cube's bounding sphere; refined below
-                const V3 rt = target - bc;
-                const float rc = M.s_bs[s][3] + sqrtf(dot(th, th)) + contact_thr;
-                near_t = dot(rt, rt) < rc * rc;
+            if (want_near) {        // bounding sphere against the cube itself (point - box distance); refined below
+                const V3 rt = bc - target;
+                const V3 ex = v3(fmaxf(fabsf(rt.x) - th.x, 0.f), fmaxf(fabsf(rt.y) - th.y, 0.f), fmaxf(fabsf(rt.z) - th.z, 0.f));
+                const float rc = M.s_bs[s][3] + contact_thr;
+                near_t = dot(ex, ex) < rc * rc;
             }
             if (!want_dist && far && !near_t) continue;
             if (want_dist && far && l != M.ee_link && !near_t) continue;
         }
-#pragma unroll
-        for (int k = 0; k < 9; k++) sR.m[k] = M.s_R[s][k];
         const V3 sp = v3(M.s_p[s][0], M.s_p[s][1], M.s_p[s][2]);
         const V3 dim = v3(M.s_dim[s][0], M.s_dim[s][1], M.s_dim[s][2]);
         const int type = M.s_type[s];
-        const M3 Rs = mul(Rl, sR);               // world <- shape
         const V3 ps = pl + mul(Rl, sp);
-        const V3 o_s = mulT(Rs, obstacle - ps);  // obstacle centre in the shape frame
-        if (want_near && (near_t || !far)) {
-            // contact rows of THIS pose for the next step's collision phase (stepSimulation detects collisions on the pose
-            // it starts from): written while the world frames are at hand, so that the step does not redo the kinematics
-            shape_contacts(M, s, Rs, ps, obstacle, target, th, !far, near_t, contact_thr, [&](int link, V3 x, float r_shape, V3 from, float r_body) {
-                if (o.ncontacts < kMaxContacts)
-                    o.ncontacts += contact_row_cached(M, aw, pv, link, x, r_shape, from, r_body, contact_thr,
-                                                      crow + o.ncontacts * kContactRec, crow + o.ncontacts * kContactRec + kMaxDof);
-            });
+        if (far && !(want_dist && l == M.ee_link)) {
+            // here only because the cube is close: the pair needs the shape's position and axis, not its whole frame
+            if (type == RLOA_SHAPE_SPHERE || type == RLOA_SHAPE_CAPSULE)
+                cube_contact(type, l, dim, ps, mul(Rl, v3(M.s_R[s][2], M.s_R[s][5], M.s_R[s][8])), target, th, contact_thr, candidate);
+            continue;
         }
+#pragma unroll
+        for (int k = 0; k < 9; k++) sR.m[k] = M.s_R[s][k];
+        const M3 Rs = mul(Rl, sR);               // world <- shape
+        const V3 o_s = mulT(Rs, obstacle - ps);  // obstacle centre in the shape frame
+        if (want_near && (near_t || !far))
+            // contact candidates of THIS pose for the next step's collision phase (stepSimulation detects collisions on the
+            // pose it starts from): found while the world frames are at hand, so that the step does not redo the kinematics
+            shape_contacts(M, s, Rs, ps, obstacle, target, th, !far, near_t, contact_thr, candidate);
         float dist;
         if (far) {
             dist = reach + (want_near ? contact_thr : 0.f);     // not a hit and not a contact candidate
@@ -467,6 +512,10 @@ __device__ __forceinline__ ObsOut fk_and_distances(const ModelDev& M, const floa
             }
             o.ee_target = fminf(o.ee_target, d_tgt);
         }
+    }
+    if (want_near) {
+        o.ncontacts = cc.n;
+        if (cc.n > 0) contact_rows_from_candidates(M, Rw, pw, cc, crow);
     }
     return o;
 }

@@ -10,6 +10,8 @@ import ctypes as C
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
+import os
+
 import torch
 
 from .. import _native as N
@@ -52,6 +54,8 @@ class BatchedSimulator:
         cfg.obstacle_threshold = float(obstacle_threshold)
         # the reference's obstacle sphere and target cube are collidable fixed bodies (environment.py:252-255): links that
         # touch them are stopped by contact rows inside stepSimulation.  contacts=False gives the free dynamics.
+        if os.environ.get('RLOA_CONTACTS') == '0':       # developer A/B switch (cost of the contact rows in bench.py)
+            contacts = False
         cfg.contact_threshold = CONTACT_THRESHOLD if contacts else 0.0
         self.cfg = cfg
         N.check(self.lib.rloa_sim_set_contacts(self._h_sim, cfg.contact_threshold), 'rloa_sim_set_contacts')
@@ -183,6 +187,12 @@ class BatchedSimulator:
         """[n_envs][nl][nl] link-link closest distances (10 on the diagonal / adjacent links / shapeless links)."""
         out = torch.empty(self.n_envs, self.nl, self.nl, dtype=torch.float32, device=self.device)
         N.check(self.lib.rloa_sim_self_distances(self._h_sim, out.data_ptr(), self._stream()), 'rloa_sim_self_distances')
+        return out
+
+    def contact_counts(self) -> torch.Tensor:
+        """Contact rows each env's next step will carry (-1: unknown until that step's own collision phase)."""
+        out = torch.empty(self.n_envs, dtype=torch.int32, device=self.device)
+        N.check(self.lib.rloa_sim_contact_counts(self._h_sim, out.data_ptr(), self._stream()), 'rloa_sim_contact_counts')
         return out
 
     def last_iterations(self) -> torch.Tensor:
