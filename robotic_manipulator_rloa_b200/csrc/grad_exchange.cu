@@ -182,16 +182,16 @@ struct rloa_xchg {
     float* block = nullptr;                 // [n grad][pad][ready][done]
     float* sum = nullptr;                   // [n] summed gradient (local)
     unsigned* tickets = nullptr;            // [0] publish ticket, [1] barrier arrivals, [2] barrier generation
-    int* status = nullptr;
+    int* status = nullptr;                  // [0] sticky time-out flag, [1] exchanges done by the fused learn kernel (its word tag)
     float* sq_partial = nullptr;            // [kXchgBlocks]
     void* mapped[kXchgMaxWorld] = {};
     XchgPeers peers{};
     bool connected = false;
 };
 
-// block layout: [ n floats: this rank's gradient, pulled by the peers (whole-gradient kernels) | kXchgPushRegions x n floats:
-// region s = the gradient rank s PUSHED here (fused learn kernel) | ready flags | done flags ]
-static size_t xchg_flag_offset(int n) { return (((size_t)n * (1 + kXchgPushRegions) * sizeof(float)) + 255) & ~(size_t)255; }
+// block layout: xchg_block_floats(n) floats (grad_exchange.cuh: the pulled gradient, then the tagged words of the fused learn
+// kernel's two exchange rounds) | ready flags | done flags
+static size_t xchg_flag_offset(int n) { return ((xchg_block_floats(n) * sizeof(float)) + 255) & ~(size_t)255; }
 
 extern "C" int rloa_xchg_create(int32_t n_floats, rloa_xchg** out) {
     RLOA_REQUIRE(out != nullptr && n_floats >= 1, "rloa_xchg_create: bad argument");
@@ -200,7 +200,7 @@ extern "C" int rloa_xchg_create(int32_t n_floats, rloa_xchg** out) {
     x->n = n_floats;
     const size_t bytes = xchg_flag_offset(n_floats) + 2 * kXchgSlices * kXchgMaxWorld * sizeof(unsigned long long);
     if (cudaMalloc(&x->block, bytes) != cudaSuccess || cudaMalloc(&x->sum, (size_t)n_floats * sizeof(float)) != cudaSuccess ||
-        cudaMalloc(&x->tickets, 4 * sizeof(unsigned)) != cudaSuccess || cudaMalloc(&x->status, sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&x->tickets, 4 * sizeof(unsigned)) != cudaSuccess || cudaMalloc(&x->status, 2 * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&x->sq_partial, kXchgBlocks * sizeof(float)) != cudaSuccess) {
         set_error("rloa_xchg_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete x;
@@ -208,7 +208,7 @@ extern "C" int rloa_xchg_create(int32_t n_floats, rloa_xchg** out) {
     }
     cudaMemset(x->block, 0, bytes);
     cudaMemset(x->tickets, 0, 4 * sizeof(unsigned));
-    cudaMemset(x->status, 0, sizeof(int));
+    cudaMemset(x->status, 0, 2 * sizeof(int));
     cudaDeviceSynchronize();
     *out = x;
     return RLOA_OK;

@@ -44,6 +44,42 @@ __device__ __forceinline__ float4 ld_peer_f32x4(const float* p) {
 }
 
 
+// ---- tagged words of the fused learn kernel's exchange (naf_learn_cluster.cu) ----------------------------------------
+// Every fp32 value travels as one 64-bit word {value bits | update number << 32} written with a single 8-byte store: the
+// receiver polls the word itself until the tag is the current update's - no flag, no fence, no round trip behind the
+// data (what NCCL's LL protocol does).  Layout of a block, in floats from its start:
+//   [0, n)                       the rank's gradient, pulled by the peers (whole-gradient kernels of grad_exchange.cu)
+//   [n, n + 16 n)                round 1: kXchgPushRegions regions of n words; region s word e = element e as summed by rank s
+//   [17 n, 19 n)                 round 2: n words, the reduced elements written by their owner ranks
+__host__ __device__ constexpr size_t xchg_ll1_offset(int n) { return (size_t)n; }
+__host__ __device__ constexpr size_t xchg_ll2_offset(int n) { return (size_t)n * (1 + 2 * kXchgPushRegions); }
+__host__ __device__ constexpr size_t xchg_block_floats(int n) { return (size_t)n * (3 + 2 * kXchgPushRegions); }
+
+__device__ __forceinline__ unsigned long long ll_word(float v, unsigned tag) {
+    return ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
+}
+__device__ __forceinline__ void st_ll(unsigned long long* p, float v, unsigned tag) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(ll_word(v, tag)) : "memory");
+}
+__device__ __forceinline__ void st_ll4(unsigned long long* p, float4 v, unsigned tag) {      // p 32-byte aligned
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(ll_word(v.x, tag)), "l"(ll_word(v.y, tag)) : "memory");
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p + 2), "l"(ll_word(v.z, tag)), "l"(ll_word(v.w, tag)) : "memory");
+}
+// one attempt: true when the word(s) carry the tag
+__device__ __forceinline__ bool ld_ll(const unsigned long long* p, unsigned tag, float& v) {
+    unsigned long long w;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    v = __uint_as_float((unsigned)w);
+    return (unsigned)(w >> 32) == tag;
+}
+__device__ __forceinline__ bool ld_ll4(const unsigned long long* p, unsigned tag, float4& v) {
+    unsigned long long w0, w1, w2, w3;
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "l"(p + 2) : "memory");
+    v = make_float4(__uint_as_float((unsigned)w0), __uint_as_float((unsigned)w1), __uint_as_float((unsigned)w2), __uint_as_float((unsigned)w3));
+    return (unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag && (unsigned)(w2 >> 32) == tag && (unsigned)(w3 >> 32) == tag;
+}
+
 // the mapped peer blocks of an exchange handle and its sticky time-out flag (device pointer)
 void xchg_peers(const rloa_xchg* x, XchgPeers* out, int** status);
 int xchg_connected_world(const rloa_xchg* x);

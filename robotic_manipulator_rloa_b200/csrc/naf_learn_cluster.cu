@@ -970,31 +970,24 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
         const int me = g.xp.rank, world = g.xp.world;
         const unsigned long long tstep = xch ? (unsigned long long)(*g.step) + 1ull : 0ull;
         __shared__ int s_xbad;
-        auto wait_flags = [&](const unsigned long long* local, unsigned long long want) {
-            if (tid == 0) {
-                const long long t0 = clock64();
-                bool ok = true;
-                for (int rr = 0; rr < world && ok; rr++) {
-                    if (rr == me) continue;
-                    while (ld_sys(local + rank * kXchgMaxWorld + rr) < want)
-                        if (clock64() - t0 > kXchgTimeoutCycles) { ok = false; break; }
-                }
-                if (!ok) atomicExch(g.xstatus, 1);
-                __threadfence_system();
-            }
-            __syncthreads();
+        // N > 1: reduce-scatter + all-gather over NVLink in tagged words (grad_exchange.cuh), per CTA slice.  Every element has
+        // an OWNER rank (contiguous index ranges of the slice).  Round 1: this rank's local sums are STORED into the owner's
+        // block (posted NVLink writes); the owner adds the `world` contributions in rank order - one result, so every rank
+        // applies the same bits.  Round 2: the owner stores the sum into every rank's block; all ranks read the reduced
+        // gradient from their own.  A rank moves 2 (world - 1) / world of a gradient through NVLink, and nothing waits for a
+        // fence or a flag: the receiver polls the data words for the update's tag.
+        // the tag counts this handle's exchanges, not optimiser steps: a restored training state may rewind the step counter,
+        // and a repeated number would let last run's words pass for this update's
+        const unsigned tag = xch ? (unsigned)g.xstatus[1] + 1u : 0u;
+        const size_t np = (size_t)g.n_params;
+        auto ll1 = [&](int owner, int src) {      // round-1 region `src` in rank `owner`'s block
+            return reinterpret_cast<unsigned long long*>(const_cast<float*>(g.xp.grad[owner]) + xchg_ll1_offset(g.n_params)) + (size_t)src * np;
         };
-        auto push_flags = [&](unsigned long long* const* remote, unsigned long long val) {      // after a __syncthreads
-            if (tid == 0) {
-                __threadfence_system();
-                for (int rr = 0; rr < world; rr++)
-                    if (rr != me) st_sys(remote[rr] + rank * kXchgMaxWorld + me, val);
-            }
+        auto ll2 = [&](int dst) {
+            return reinterpret_cast<unsigned long long*>(const_cast<float*>(g.xp.grad[dst]) + xchg_ll2_offset(g.n_params));
         };
-        // push model: this rank's local sums are STORED into region (1 + me) of every rank's exchange block (posted NVLink
-        // writes, no round trip); the cross-rank sum then reads only local memory
-        const size_t xreg = (size_t)(1 + me) * (size_t)g.n_params;
-        if (xch) wait_flags(g.xp.done[me], tstep - 1ull);
+        bool xbad = false;
+        const long long xt0 = clock64();
         float sq = 0.f;
         {   // (a) this CTA's eighth of dW2 (16384 float4 in all, 2048 per CTA, 4 per thread): two rounds of 16 loads in flight
             const float4* pw = reinterpret_cast<const float4*>(g.part_w2);
@@ -1012,10 +1005,9 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
                     for (int c = 1; c < CL; c++) { s4.x += pv[u][c].x; s4.y += pv[u][c].y; s4.z += pv[u][c].z; s4.w += pv[u][c].w; }
                     t_gw[(2 * jj + u) * THREADS + tid] = s4;
                     if (xch) {
-#pragma unroll
-                        for (int rr = 0; rr < kXchgInKernelWorld; rr++)
-                            if (rr < world)
-                                reinterpret_cast<float4*>(const_cast<float*>(g.xp.grad[rr]) + xreg + g.off_w2)[rank * 2048 + (2 * jj + u) * 512 + tid] = s4;
+                        const int idx = (2 * jj + u) * 512 + tid;
+                        const int owner = (idx * world) >> 11;
+                        if (owner != me) st_ll4(ll1(owner, me) + g.off_w2 + 4 * (rank * 2048 + idx), s4, tag);
                     } else {
                         reinterpret_cast<float4*>(g.grad + g.off_w2)[rank * 2048 + (2 * jj + u) * 512 + tid] = s4;
                     }
@@ -1070,9 +1062,8 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
                 t_gi[j * THREADS + tid] = gi3[u];
                 if (gi3[u] >= 0) {
                     if (xch) {
-#pragma unroll
-                        for (int rr = 0; rr < kXchgInKernelWorld; rr++)
-                            if (rr < world) const_cast<float*>(g.xp.grad[rr])[xreg + gi3[u]] = ssum;
+                        const int owner = ((j * THREADS + tid) * world) / (kSlots * THREADS);
+                        if (owner != me) st_ll(ll1(owner, me) + gi3[u], ssum, tag);
                     } else {
                         g.grad[gi3[u]] = ssum;
                     }
@@ -1082,60 +1073,70 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
             }
         }
         if (xch) {
-            __syncthreads();
-            push_flags(g.xp.ready, tstep);
-            wait_flags(g.xp.ready[me], tstep);
-            sq = 0.f;
-            // all ranks' contributions now sit in THIS rank's block: local loads, all in flight, summed in rank order
-            const float* xl = g.xp.grad[me];
-            const size_t np = (size_t)g.n_params;
+            __syncthreads();                                   // t_gw / t_gr / t_gi of this thread's elements are its own: no hazard;
+                                                               // the barrier only keeps the phases of the timeline apart
+            // round 1 (owner): the peers' words of the owned elements, polled; sum in rank order; round 2: the sum to everyone
 #pragma unroll 1
-            for (int jj = 0; jj < 2; jj++) {
-                float4 pv[2][kXchgInKernelWorld];
-#pragma unroll
-                for (int u = 0; u < 2; u++)
-#pragma unroll
-                    for (int rr = 0; rr < kXchgInKernelWorld; rr++)
-                        if (rr < world)
-                            pv[u][rr] = __ldcg(reinterpret_cast<const float4*>(xl + (size_t)(1 + rr) * np + g.off_w2) + rank * 2048 + (2 * jj + u) * 512 + tid);
-#pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    const int j = 2 * jj + u, i4 = rank * 2048 + j * 512 + tid;
-                    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int rr = 0; rr < kXchgInKernelWorld; rr++)      // rank order: the same bits on every rank
-                        if (rr < world) { s4.x += pv[u][rr].x; s4.y += pv[u][rr].y; s4.z += pv[u][rr].z; s4.w += pv[u][rr].w; }
-                    t_gw[j * THREADS + tid] = s4;
-                    reinterpret_cast<float4*>(g.grad + g.off_w2)[i4] = s4;
-                    const float x0 = s4.x * gs, x1 = s4.y * gs, x2 = s4.z * gs, x3 = s4.w * gs;
-                    sq = fmaf(x0, x0, sq); sq = fmaf(x1, x1, sq); sq = fmaf(x2, x2, sq); sq = fmaf(x3, x3, sq);
+            for (int j = 0; j < 4; j++) {
+                const int idx = j * THREADS + tid;
+                if (((idx * world) >> 11) != me) continue;
+                const size_t e = (size_t)g.off_w2 + 4 * (size_t)(rank * 2048 + idx);
+                float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int rr = 0; rr < world; rr++) {
+                    float4 v = t_gw[j * THREADS + tid];
+                    if (rr != me)
+                        while (!ld_ll4(ll1(me, rr) + e, tag, v))
+                            if (clock64() - xt0 > kXchgTimeoutCycles) { xbad = true; break; }
+                    s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
                 }
+                for (int rr = 0; rr < world; rr++) st_ll4(ll2(rr) + e, s4, tag);
             }
-            {
-                float pr[kSlots][kXchgInKernelWorld];
-                int ii[kSlots];
-#pragma unroll
-                for (int j = 0; j < kSlots; j++) {
-                    ii[j] = t_gi[j * THREADS + tid];
-#pragma unroll
-                    for (int rr = 0; rr < kXchgInKernelWorld; rr++)
-                        pr[j][rr] = (ii[j] >= 0 && rr < world) ? __ldcg(xl + (size_t)(1 + rr) * np + ii[j]) : 0.f;
+#pragma unroll 1
+            for (int j = 0; j < kSlots; j++) {
+                const int i = t_gi[j * THREADS + tid];
+                if (i < 0 || ((j * THREADS + tid) * world) / (kSlots * THREADS) != me) continue;
+                float ssum = 0.f;
+                for (int rr = 0; rr < world; rr++) {
+                    float v = t_gr[j * THREADS + tid];
+                    if (rr != me)
+                        while (!ld_ll(ll1(me, rr) + i, tag, v))
+                            if (clock64() - xt0 > kXchgTimeoutCycles) { xbad = true; break; }
+                    ssum += v;
                 }
-#pragma unroll
-                for (int j = 0; j < kSlots; j++)
-                    if (ii[j] >= 0) {
-                        float ssum = 0.f;
-#pragma unroll
-                        for (int rr = 0; rr < kXchgInKernelWorld; rr++)
-                            if (rr < world) ssum += pr[j][rr];
-                        t_gr[j * THREADS + tid] = ssum;
-                        g.grad[ii[j]] = ssum;
-                        const float x = ssum * gs;
-                        sq = fmaf(x, x, sq);
-                    }
+                for (int rr = 0; rr < world; rr++) st_ll(ll2(rr) + i, ssum, tag);
+            }
+            // round 2 (everyone): the reduced elements of this thread from its own block
+            sq = 0.f;
+            const unsigned long long* l2 = ll2(me);
+#pragma unroll 1
+            for (int j = 0; j < 4; j++) {
+                float4 s4;
+                while (!ld_ll4(l2 + g.off_w2 + 4 * (size_t)(rank * 2048 + j * THREADS + tid), tag, s4))
+                    if (clock64() - xt0 > kXchgTimeoutCycles) { xbad = true; break; }
+                t_gw[j * THREADS + tid] = s4;
+                reinterpret_cast<float4*>(g.grad + g.off_w2)[rank * 2048 + j * THREADS + tid] = s4;
+                const float x0 = s4.x * gs, x1 = s4.y * gs, x2 = s4.z * gs, x3 = s4.w * gs;
+                sq = fmaf(x0, x0, sq); sq = fmaf(x1, x1, sq); sq = fmaf(x2, x2, sq); sq = fmaf(x3, x3, sq);
+            }
+#pragma unroll 1
+            for (int j = 0; j < kSlots; j++) {
+                const int i = t_gi[j * THREADS + tid];
+                if (i < 0) continue;
+                float v;
+                while (!ld_ll(l2 + i, tag, v))
+                    if (clock64() - xt0 > kXchgTimeoutCycles) { xbad = true; break; }
+                t_gr[j * THREADS + tid] = v;
+                g.grad[i] = v;
+                const float x = v * gs;
+                sq = fmaf(x, x, sq);
+            }
+            if (xbad) atomicExch(g.xstatus, 1);
+            // keep the flag protocol of the whole-gradient kernels (slice 0) in step, should the caller switch paths
+            if (rank == 0 && tid < world && tid != me) {
+                st_sys(g.xp.ready[tid] + me, tstep);
+                st_sys(g.xp.done[tid] + me, tstep);
             }
             __syncthreads();
-            push_flags(g.xp.done, tstep);                      // the peers' blocks are not read any more for this update
         }
         stamp(19);
         // squared norm: warp tree, warps in order, CTAs in rank order over DSMEM
@@ -1217,6 +1218,7 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
     // a CTA's shared memory must outlive every DSMEM read of it; the step counter moves after everybody has read it
     cluster_sync_all();
     if (net == 1 && g.do_adam && rank == 0 && tid == 0) *g.step += 1;      // also after a timed-out exchange: the flags count updates
+    if (net == 1 && g.use_xchg && rank == 0 && tid == 0) g.xstatus[1] += 1;
     fence_before_sync();
     __syncthreads();
     stamp(22);

@@ -272,11 +272,15 @@ class NAFAgent:
         b = self._learn_buffers()
         m = self.memory
         ws = self._workspace(self.batch_size)
-        if self.fused_learn and m._rb is not None and ws.lib.rloa_naf_learn_fused_supported(ws.handle, self.batch_size):
+        xchg = self._exchange()
+        # N > 1 without the peer-memory exchange (RLOA_GRAD_EXCHANGE=nccl): the all-reduce sits between two native calls, so
+        # the update cannot be one launch
+        one_launch = self.world_size == 1 or xchg is not None
+        if self.fused_learn and one_launch and m._rb is not None and \
+                ws.lib.rloa_naf_learn_fused_supported(ws.handle, self.batch_size):
             hp = self._hyper()
             pm, pt = self.qnetwork_main.native_params(), self.qnetwork_target.native_params()
             adam = self.optimizer.native()
-            xchg = self._exchange()
             draw = m._draws if tick is None else (int(sub) << 32)
             N.check(ws.lib.rloa_naf_learn_step_replay(ws.handle, C.byref(pm), C.byref(pt), C.byref(adam),
                                                       xchg.handle if xchg is not None else None, C.byref(m._rb), m.seed, draw,

@@ -79,6 +79,19 @@ def _worker(rank, world, port, out_dir):
         gathered = [torch.empty_like(vec) for _ in range(world)]
         dist.all_gather(gathered, vec)
         out[mode] = torch.stack(gathered).cpu().numpy()
+        # the loop's entry point: sample + learn from the rank's own ring (one launch where the path allows it)
+        g = torch.Generator().manual_seed(1000 + rank)
+        n = 900
+        s = torch.randn(n, S, generator=g)
+        agent.memory.add_batch(s.to(dev), torch.clamp(torch.randn(n, A, generator=g) * 1.5, -1, 1).to(dev),
+                               (-torch.rand(n, generator=g)).to(dev), (s + 0.1 * torch.randn(n, S, generator=g)).to(dev),
+                               torch.zeros(n, dtype=torch.uint8).to(dev))
+        for step in range(3):
+            agent.learn_from_memory()
+        torch.cuda.synchronize()
+        vec = _params(agent)
+        dist.all_gather(gathered, vec)
+        out[mode + '+ring'] = torch.stack(gathered).cpu().numpy()
     if rank == 0:
         np.savez(os.path.join(out_dir, 'out.npz'), **out)
     dist.barrier()
@@ -95,6 +108,8 @@ def test_two_rank_peer_exchange_matches_nccl(tmp_path):
     out = np.load(tmp_path / 'out.npz')
     for mode in ('peer', 'nccl', 'peer-tc', 'nccl-tc'):
         assert np.array_equal(out[mode][0], out[mode][1]), f'{mode}: ranks diverged'
+        assert np.array_equal(out[mode + '+ring'][0], out[mode + '+ring'][1]), f'{mode}: ranks diverged in learn_from_memory'
+        assert not np.array_equal(out[mode + '+ring'][0], out[mode][0])
     # tensor-core path: the exchange inside the fused learn kernel against NCCL between its two-call form.  The clip
     # coefficient differs in the last ulp (8 norm partials vs 80), which is enough to re-roll the rounding-noise gradients
     # of the linear biases under BatchNorm (analytically 0) — Adam turns those into lr-sized steps — so: all but a handful of
