@@ -51,7 +51,9 @@ FLOP_PER_ENV_STEP = 1.0e5        # KUKA 14 links / 12 do
 FLOP_PER_SWEEP = 34 * (2 * 12 + 8)   # one Gauss-Seidel sweep over the 34 rows (same table)
 BYTES_PER_ENV_STEP = 329         # sim_step kernel only: q,qd r/w 192 + action 24 + task 24 + obs 84 + reward/done 5
 NAF_FLOP_PER_SAMPLE = 600064     # fwd main + fwd target (V only) + backward
-NAF_BYTES = lambda B: 200 * B + 9 * 318576 + 8 * B * 256 * 4
+NAF_BYTES = lambda B: 200 * B + 9 * 318576 + 8 * B * 256 * 4       # multi-launch path: activations cross HBM between kernels
+NAF_BYTES_FUSED = lambda B: 200 * B + 9 * 318576 + 2 * 198912       # one-kernel update: sampled rows, parameters / optimiser
+                                                                     # state read + written, the two weight images
 METRIC = 'env-steps/sec KUKA IIWA (4096 envs/GPU, 400-step episodes, NAF batch 1024, 1 update/step)'
 
 TRAIN_CONFIGS = {
@@ -740,7 +742,8 @@ def ours(args):
         gbs = BYTES_PER_ENV_STEP * envs / (sim_avg_ms * 1e-3) / 1e9
         learn_us = (naf or {}).get('ours_graph_us_per_update') or rec['learn_avg_ms'] * 1e3
         naf_tf = NAF_FLOP_PER_SAMPLE * batch / (learn_us * 1e-6) / 1e12
-        naf_gbs = NAF_BYTES(batch) / (learn_us * 1e-6) / 1e9
+        naf_bytes = NAF_BYTES_FUSED(batch) if args.trunk == 'tc' else NAF_BYTES(batch)
+        naf_gbs = naf_bytes / (learn_us * 1e-6) / 1e9
         line = {
             'metric': METRIC, 'value': rec['value'], 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': rec['ms_per_step'], 'higher_is_better': True,
@@ -757,17 +760,20 @@ def ours(args):
                          'at_measured_sweeps': {'mean_pgs_sweeps': sweeps, 'flop_per_env_step': flop_measured,
                                                 'achieved': tflops_measured, 'frac': tflops_measured / fp32_peak},
                          'avg_launch_ms': sim_avg_ms, 'share_of_step': sim_avg_ms / max(rec['phase_sum_ms'], 1e-9),
-                         'traffic': 8.07e6, 'traffic_source': 'ncu --set full at 4096 arms, dram read+write of the three kernels per '
-                                                              'launch, caches flushed by ncu (profiles/r1m_sim4096_ncu_full.md)',
+                         'traffic': 8.18e6, 'traffic_source': 'ncu --set full at 4096 arms, dram read+write of the three kernels per '
+                                                              'launch, caches flushed by ncu (profiles/r2w_sim4096_ncu_full.md)',
                          'hbm': {'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak, 'peak_source': which,
                                  'bytes_per_env_step': BYTES_PER_ENV_STEP}},
             'roofline_naf_update': {'kernel': 'NAFAgent.learn (replay batch %d, both networks, backward, clip + Adam + soft update)' % batch,
                                     'bound': 'tensor', 'achieved': naf_tf, 'peak': tensor_peak, 'unit': 'TFLOP/s',
                                     'frac': naf_tf / tensor_peak, 'flop_per_update': NAF_FLOP_PER_SAMPLE * batch,
                                     'us_per_update': learn_us, 'hbm_gbs': naf_gbs, 'hbm_frac': naf_gbs / hbm_peak,
-                                    'bytes_per_update': NAF_BYTES(batch), 'peak_source': which + ' bf16_tflops_sustained',
-                                    'note': 'latency-bound at this batch: both floors (0.45 us tensor, 1.8 us HBM) are far below the '
-                                            'launch / barrier latency of the chain'},
+                                    'bytes_per_update': naf_bytes, 'peak_source': which + ' bf16_tflops_sustained',
+                                    'traffic': 2.74e6 if args.trunk == 'tc' else None,
+                                    'traffic_source': 'ncu --set full, dram read+write of learn_pack_kernel + naf_learn_cluster_kernel per update '
+                                                      '(profiles/r2w_learn_cluster_ncu_full.md; the writes stay in L2)',
+                                    'note': 'latency-bound at this batch: both floors (0.45 us tensor, 0.5 - 1.8 us HBM) are far below the '
+                                            'barrier / epilogue latency of the chain'},
             'cpu_baseline': cpu,
             'e2e': rec['e2e'],
             'fp32_trunk': rec.get('fp32_trunk'),
