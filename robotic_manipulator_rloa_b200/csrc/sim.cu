@@ -376,13 +376,23 @@ sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_c
         // ---- state / reward / done from the post-step configuration ----
         const V3 tg = ld3(S.target + 3 * (size_t)env), ob = ld3(S.obstacle + 3 * (size_t)env);
         const bool contacts_on = cfg.contact_thr > 0.f;
+        // the observed joint states are requested before the kinematics, so their round trip hides behind it
+        const int n = M.n_obs;
+        float oq[kMaxDof], oqd[kMaxDof];
+#pragma unroll
+        for (int i = 0; i < kMaxDof; i++) {
+            oq[i] = (i < n && obs != nullptr) ? S.q[(size_t)i * sN + env] : 0.f;
+            oqd[i] = (i < n && obs != nullptr) ? S.qd[(size_t)i * sN + env] : 0.f;
+        }
         const ObsOut o = fk_and_distances<NLMAX, GJK>(M, S.q + env, N, ob, tg, cfg.obstacle_thr, !is_reset, nullptr, 0,
                                                       cfg.contact_thr, contacts_on,
                                                       contacts_on ? S.crow + (size_t)env * kMaxContacts * kContactRec : nullptr);
         if (contacts_on) S.near[env] = o.ncontacts;
         if (obs != nullptr) {
-            const int n = M.n_obs;
-            for (int i = 0; i < n; i++) {
+#pragma unroll
+            for (int i = 0; i < kMaxDof; i++)
+                if (i < n) { sm_obs[i] = oq[i]; sm_obs[n + i] = oqd[i]; }
+            for (int i = kMaxDof; i < n; i++) {
                 sm_obs[i] = S.q[(size_t)i * sN + env];
                 sm_obs[n + i] = S.qd[(size_t)i * sN + env];
             }

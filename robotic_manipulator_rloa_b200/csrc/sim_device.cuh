@@ -402,11 +402,15 @@ __device__ __forceinline__ ObsOut fk_and_distances(const ModelDev& M, const floa
                                                    bool want_near = false, float* __restrict__ crow = nullptr) {
     float Rw[NLMAX * 9], pw[NLMAX * 3];
     const int nl = M.nl;
+    // every joint coordinate is requested before the serial walk: one memory round trip instead of one per link
+    float qv[NLMAX];
+#pragma unroll
+    for (int i = 0; i < NLMAX; i++) qv[i] = i < nl ? qcol[(size_t)i * N] : 0.f;
     for (int i = 0; i < nl; i++) {
         const int par = M.parent[i];
         M3 Rl;
         V3 pl, dd;
-        joint_transform(M, i, qcol[(size_t)i * N], Rl, pl, dd);
+        joint_transform(M, i, qv[i], Rl, pl, dd);
         M3 R = Rl;
         V3 p = pl;
         if (par >= 0) {

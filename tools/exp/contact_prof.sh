@@ -1,7 +1,8 @@
-for v in A B; do
-if [ $v = B ]; then cp tools/exp/librloa_B.so robotic_manipulator_rloa_b200/librloa_b200.so; fi
-python -m pytest tests/test_sim_gpu.py -x -q -m gpu 2>&1 | tail -2
-for dbg in 0 2; do
-RLOA_CONTACT_DEBUG=$dbg timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:sim_solve --csv --log-file gpurun_out/r2p_dur_${v}_$dbg.csv python tools/prof_contacts.py 400 > gpurun_out/r2p_log_${v}_$dbg.log 2>&1
-tail -1 gpurun_out/r2p_log_${v}_$dbg.log
-done; done
+python -m pytest tests/test_sim_gpu.py tests/test_mesh_hull_gpu.py -x -q -m gpu 2>&1 | tail -2
+for sp in 1 0; do
+RLOA_SIM_SPLIT=$sp timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"sim_solve|sim_post" --csv --log-file gpurun_out/r2y_dur_$sp.csv python tools/prof_contacts.py 400 > gpurun_out/r2y_log_$sp.log 2>&1
+RLOA_SIM_SPLIT=$sp python bench.py --steps 200 --warmup 20 --no-cpu --no-extras | python -c "
+import sys,json
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('split=$sp', d['ms_per_step'], d['phases_ms'], d['warm_l2']['ms_per_step'], d['gpu_launches'])"
+done
