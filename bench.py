@@ -531,7 +531,10 @@ def train_workload(ctx, args, c, steps, full):
         rec['ranks_identical'] = all(bool(torch.equal(s, sigs[0])) for s in sigs)
         to = 1.0 if (agent._xchg is not None and agent._xchg.timed_out()) else 0.0
         rec['xchg_timed_out'] = ctx.reduce(to, 'MAX') > 0
-        rec['grad_exchange'] = ('NVLink peer memory inside the optimiser kernels (csrc/grad_exchange.cu)'
+        fused = agent._xchg is not None and args.trunk == 'tc' and world <= 8
+        rec['grad_exchange'] = ('reduce-scatter + all-gather over NVLink peer memory in tagged 64-bit words, inside the tail of the '
+                                'learn kernel (csrc/naf_learn_cluster.cu)' if fused else
+                                'NVLink peer memory inside the optimiser kernels (csrc/grad_exchange.cu)'
                                 if agent._xchg is not None else 'NCCL all-reduce (torch.distributed)')
     rec['_agent'], rec['_loop'], rec['_env'] = agent, loop, env
     return rec
