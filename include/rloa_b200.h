@@ -384,6 +384,13 @@ typedef struct {
 int rloa_replay_append(const rloa_replay* rb, int32_t n, const float* states, const float* actions,
                        const float* rewards, const float* next_states, const uint8_t* dones,
                        const uint8_t* valid, void* stream);
+/* rloa_replay_append in two halves: _rows copies the (valid) rows into the slots the cursor points at without moving it,
+ * _commit moves the cursor by the number of valid rows.  Between the two the ring's readers still see the old window
+ * (rloa_naf_learn_step_pending reads the new rows from the caller's arrays meanwhile). */
+int rloa_replay_append_rows(const rloa_replay* rb, int32_t n, const float* states, const float* actions,
+                            const float* rewards, const float* next_states, const uint8_t* dones,
+                            const uint8_t* valid, void* stream);
+int rloa_replay_commit(const rloa_replay* rb, int32_t n, const uint8_t* valid, void* stream);
 /* ReplayBuffer.sample (replay_buffer.py:47-67): `batch` distinct slots drawn uniformly from the
  * live window with a keyed Feistel permutation (seed, draw + *draw_offset); draw_offset is a DEVICE
  * counter and may be NULL; gathers the five fields. */
@@ -400,6 +407,19 @@ int rloa_naf_learn_step_replay(rloa_naf_ws* ws, const rloa_naf_params* main_net,
                                const rloa_adam_state* adam, rloa_xchg* xchg, const rloa_replay* rb, uint64_t seed, uint64_t draw,
                                const uint64_t* draw_offset, int32_t batch, const rloa_naf_hyper* hyper, float* grad, float* loss,
                                float* grad_norm, void* stream);
+/* The same with the step's transitions still PENDING (naf_algorithm.py:149-154: `self.memory.add(...)` immediately followed by
+ * sample + learn): the caller copies the n_pending rows into the ring with rloa_replay_append_rows on ANOTHER stream, in
+ * parallel with this call, and moves the cursor with rloa_replay_commit only after this call has completed.  The kernel
+ * samples the ring as it will be after the commit - the same slots rloa_replay_append + rloa_naf_learn_step_replay draw - and
+ * reads a drawn slot of the pending range from the caller's arrays (its k-th valid row) instead of the ring, so the copy is
+ * off the update's critical path and the result is bit-identical.  dones / valid may be NULL (no done mask / all rows valid);
+ * valid must be 16-byte aligned; n_pending <= 16384.  Layout of the pending arrays as for rloa_replay_append. */
+int rloa_naf_learn_step_pending(rloa_naf_ws* ws, const rloa_naf_params* main_net, const rloa_naf_params* target_net,
+                                const rloa_adam_state* adam, rloa_xchg* xchg, const rloa_replay* rb, uint64_t seed, uint64_t draw,
+                                const uint64_t* draw_offset, int32_t batch, const rloa_naf_hyper* hyper, int32_t n_pending,
+                                const float* states, const float* actions, const float* rewards, const float* next_states,
+                                const uint8_t* dones, const uint8_t* valid, float* grad, float* loss, float* grad_norm,
+                                void* stream);
 /* Optional: writes the tensor-core weight images the next rloa_naf_learn_* call of this workspace needs on the workspace's
  * side stream NOW (the caller promises not to modify the parameters before that call), so that the call itself starts with
  * the images ready.  A no-op on the other paths. */

@@ -128,6 +128,9 @@ SIGNATURES = {
     'rloa_naf_learn_fused_supported': (C.c_int, [_VP, _I]),
     'rloa_naf_learn_step_replay': (C.c_int, [_VP, C.POINTER(NafParams), C.POINTER(NafParams), C.POINTER(AdamState), _VP,
                                              C.POINTER(Replay), _U64, _U64, _fp, _I, C.POINTER(NafHyper), _fp, _fp, _fp, _VP]),
+    'rloa_naf_learn_step_pending': (C.c_int, [_VP, C.POINTER(NafParams), C.POINTER(NafParams), C.POINTER(AdamState), _VP,
+                                              C.POINTER(Replay), _U64, _U64, _fp, _I, C.POINTER(NafHyper), _I, _fp, _fp, _fp, _fp,
+                                              _fp, _fp, _fp, _fp, _fp, _VP]),
     'rloa_naf_learn_prepack': (C.c_int, [_VP, C.POINTER(NafParams), C.POINTER(NafParams), _VP]),
     'rloa_xchg_create': (C.c_int, [_I, C.POINTER(_VP)]),
     'rloa_xchg_handle': (C.c_int, [_VP, C.c_char_p]),
@@ -140,6 +143,8 @@ SIGNATURES = {
                                            _fp, _fp, _fp, _I, C.POINTER(NafHyper), _fp, _fp, _fp, _VP]),
     'rloa_naf_soft_update': (C.c_int, [C.POINTER(NafParams), C.POINTER(NafParams), _F, _VP]),
     'rloa_replay_append': (C.c_int, [C.POINTER(Replay), _I, _fp, _fp, _fp, _fp, _fp, _fp, _VP]),
+    'rloa_replay_append_rows': (C.c_int, [C.POINTER(Replay), _I, _fp, _fp, _fp, _fp, _fp, _fp, _VP]),
+    'rloa_replay_commit': (C.c_int, [C.POINTER(Replay), _I, _fp, _VP]),
     'rloa_replay_sample': (C.c_int, [C.POINTER(Replay), _I, _U64, _U64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _VP]),
 }
 

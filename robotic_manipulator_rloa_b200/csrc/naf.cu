@@ -1667,6 +1667,24 @@ extern "C" int rloa_naf_learn_step_replay(rloa_naf_ws* ws, const rloa_naf_params
     return xchg_exchange_adam(xchg, grad, ReduceArgs{}, pt, adam->m, adam->v, adam->step, *hp, grad_norm, as_stream(stream));
 }
 
+extern "C" int rloa_naf_learn_step_pending(rloa_naf_ws* ws, const rloa_naf_params* mn, const rloa_naf_params* tg,
+                                           const rloa_adam_state* adam, rloa_xchg* xchg, const rloa_replay* rb, uint64_t seed,
+                                           uint64_t draw, const uint64_t* draw_offset, int32_t batch, const rloa_naf_hyper* hp,
+                                           int32_t n_pending, const float* states, const float* actions, const float* rewards,
+                                           const float* next_states, const uint8_t* dones, const uint8_t* valid, float* grad,
+                                           float* loss, float* grad_norm, void* stream) {
+    RLOA_REQUIRE(ws && adam && adam->m && adam->v && adam->step && rb && hp, "rloa_naf_learn_step_pending: null argument");
+    RLOA_REQUIRE(cluster_learn_applies(ws, batch) && (xchg == nullptr || xchg_connected_world(xchg) <= kLearnClusterMaxWorld),
+                 "rloa_naf_learn_step_pending: needs the one-kernel update (rloa_naf_learn_fused_supported, at most 8 ranks)");
+    RLOA_REQUIRE(rb->state_size == ws->S && rb->action_size == ws->A, "rloa_naf_learn_step_pending: replay row layout does not match the network");
+    RLOA_REQUIRE(n_pending >= 1 && n_pending <= kLearnClusterMaxPending && n_pending <= rb->capacity && states && actions && rewards &&
+                     next_states, "rloa_naf_learn_step_pending: bad pending rows");
+    LearnClusterReplay rp{rb, seed, draw, draw_offset};
+    rp.pd_states = states; rp.pd_actions = actions; rp.pd_rewards = rewards; rp.pd_next_states = next_states;
+    rp.pd_dones = dones; rp.pd_valid = valid; rp.pd_n = n_pending;
+    return cluster_learn(ws, mn, tg, adam, nullptr, nullptr, nullptr, nullptr, nullptr, batch, hp, grad, loss, grad_norm, 1, stream, &rp, xchg);
+}
+
 extern "C" int rloa_naf_soft_update(const rloa_naf_params* mn, const rloa_naf_params* tg, float tau, void* stream) {
     RLOA_REQUIRE(mn && tg, "rloa_naf_soft_update: null argument");
     RLOA_REQUIRE(mn->state_size == tg->state_size && mn->action_size == tg->action_size && mn->hidden == tg->hidden,

@@ -148,6 +148,12 @@ struct LearnClusterArgs {
     rloa_replay rb;
     unsigned long long rs_seed, rs_draw;
     const unsigned long long* rs_draw_offset;
+    // pending rows: the step's transitions, being copied into the ring by a concurrent rloa_replay_append_rows and not
+    // committed yet (the ring's cursor still excludes them).  The sampler sees the ring as it will be after the commit; a
+    // drawn slot that falls into the pending range is read from these arrays (row = the k-th valid one) instead of the ring.
+    const float *pd_states, *pd_actions, *pd_rewards, *pd_next_states;
+    const uint8_t *pd_dones, *pd_valid;
+    int pd_n;                               // 0: none; at most kPendingMax
 };
 
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -535,16 +541,78 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
         mbar_expect_tx(&bars[1], W2_BYTES);
         bulk_g2s(sm + R0, image + OFF_W2, W2_BYTES, &bars[1]);
     }
+    // pending rows (see LearnClusterArgs): valid-row counts of the groups of 32 step rows, exclusive prefix, in the statistics
+    // buffers (unused until the first BatchNorm pass): thread t owns group t
+    uint32_t* pd_mask = reinterpret_cast<uint32_t*>(sm + COEF);       // [512] valid bits of group t
+    int* pd_pre = reinterpret_cast<int*>(sm + COEF + 2048);           // [512] valid rows before group t
+    int pd_total = 0;
+    if (g.use_replay && g.pd_n > 0) {
+        uint32_t m = 0;
+        if (tid * 32 < g.pd_n) {
+            if (g.pd_valid == nullptr) {
+                const int left = g.pd_n - tid * 32;
+                m = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+            } else {
+                if (tid * 32 + 32 <= g.pd_n) {            // a whole group: two 16-byte loads (the mask is 16-byte aligned)
+                    const uint4 v0 = *reinterpret_cast<const uint4*>(g.pd_valid + tid * 32);
+                    const uint4 v1 = *reinterpret_cast<const uint4*>(g.pd_valid + tid * 32 + 16);
+                    const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+#pragma unroll
+                        for (int b = 0; b < 4; b++)
+                            if (((w[k] >> (8 * b)) & 0xffu) != 0u) m |= 1u << (4 * k + b);
+                } else {
+                    for (int b = 0; tid * 32 + b < g.pd_n; b++)
+                        if (g.pd_valid[tid * 32 + b] != 0) m |= 1u << b;
+                }
+            }
+        }
+        int inc = __popc(m);
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += o;
+        }
+        int* wtot = reinterpret_cast<int*>(sm + COEF + 4096);         // [16] inclusive totals of the warps
+        if (lane == 31) wtot[warp] = inc;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < THREADS / 32; w++) {
+            if (w < warp) wbase += wtot[w];
+            pd_total += wtot[w];
+        }
+        pd_mask[tid] = m;
+        pd_pre[tid] = wbase + inc - __popc(m);
+        __syncthreads();
+    }
     // this thread's 8 observation values (row r, k = 8 q .. 8 q + 7); kept in registers for the z1 recompute and dW1
     float xk[8];
     size_t src_row = (size_t)row;                                     // row of the batch arrays, or ring slot of the sample
-    if (g.use_replay && valid)
-        src_row = replay_sample_slot(g.rb, row, g.rs_seed, g.rs_draw + (g.rs_draw_offset != nullptr ? *g.rs_draw_offset : 0ull));
     const float* in_actions = g.use_replay ? g.rb.actions : g.actions;
     const float* in_rewards = g.use_replay ? g.rb.rewards : g.rewards;
     const float* in_dones = g.use_replay ? g.rb.dones : g.dones;
+    const float* x = g.use_replay ? (net == 0 ? g.rb.next_states : g.rb.states) : (net == 0 ? g.next_states : g.states);
+    const uint8_t* in_dones_u8 = nullptr;                             // pending rows keep their done flags as bytes
+    if (g.use_replay && valid) {
+        const long long cur = *g.rb.cursor;
+        src_row = replay_sample_slot_at(g.rb, cur + pd_total, row, g.rs_seed, g.rs_draw + (g.rs_draw_offset != nullptr ? *g.rs_draw_offset : 0ull));
+        if (pd_total > 0) {
+            const long long cap = g.rb.capacity;
+            const long long off = ((long long)src_row - cur % cap + cap) % cap;      // distance from the first pending slot
+            if (off < pd_total) {
+                int lo = 0, hi = (g.pd_n + 31) / 32 - 1;                              // last group with pd_pre <= off
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (pd_pre[mid] <= (int)off) lo = mid; else hi = mid - 1;
+                }
+                src_row = (size_t)(lo * 32 + (int)__fns(pd_mask[lo], 0, (int)off - pd_pre[lo] + 1));
+                in_actions = g.pd_actions; in_rewards = g.pd_rewards; in_dones = nullptr; in_dones_u8 = g.pd_dones;
+                x = net == 0 ? g.pd_next_states : g.pd_states;
+            }
+        }
+    }
     {
-        const float* x = g.use_replay ? (net == 0 ? g.rb.next_states : g.rb.states) : (net == 0 ? g.next_states : g.states);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int k = q * 8 + i;
@@ -691,6 +759,7 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
         if (q == 0 && valid) {
             float vv = zo[A];
             if (g.hp.use_done_mask && in_dones != nullptr) vv *= (1.f - in_dones[src_row]);
+            if (g.hp.use_done_mask && in_dones_u8 != nullptr) vv *= (1.f - (float)in_dones_u8[src_row]);
             g.y[row] = fmaf(g.hp.gamma, vv, in_rewards[src_row]);
         }
         __threadfence();
@@ -1316,6 +1385,14 @@ int learn_cluster_step(LearnCluster* lcw, const rloa_naf_params* mn, const rloa_
         a.rb = *replay->rb;
         a.rs_seed = replay->seed; a.rs_draw = replay->draw;
         a.rs_draw_offset = reinterpret_cast<const unsigned long long*>(replay->draw_offset);
+        if (replay->pd_n > 0) {
+            RLOA_REQUIRE(replay->pd_n <= kLearnClusterMaxPending && replay->pd_states && replay->pd_actions && replay->pd_rewards &&
+                             replay->pd_next_states && (reinterpret_cast<uintptr_t>(replay->pd_valid) & 15u) == 0,
+                         "learn cluster: bad pending-row arguments");
+            a.pd_states = replay->pd_states; a.pd_actions = replay->pd_actions; a.pd_rewards = replay->pd_rewards;
+            a.pd_next_states = replay->pd_next_states; a.pd_dones = replay->pd_dones; a.pd_valid = replay->pd_valid;
+            a.pd_n = replay->pd_n;
+        }
     }
     naf_learn_cluster_kernel<<<2 * lc::CL, lc::THREADS, lc::SMEM_BYTES, st>>>(a);
     RLOA_LAUNCHED();

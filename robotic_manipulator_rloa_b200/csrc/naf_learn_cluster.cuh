@@ -25,7 +25,12 @@ struct LearnClusterReplay {          // fused ReplayBuffer.sample: the kernel re
     const rloa_replay* rb;
     uint64_t seed, draw;
     const uint64_t* draw_offset;
+    // optional pending rows (appended to the ring concurrently, not committed yet): the kernel samples the ring as it will be
+    const float *pd_states = nullptr, *pd_actions = nullptr, *pd_rewards = nullptr, *pd_next_states = nullptr;
+    const uint8_t *pd_dones = nullptr, *pd_valid = nullptr;
+    int pd_n = 0;
 };
+constexpr int kLearnClusterMaxPending = 16384;      // 32 rows per thread of a CTA
 
 bool learn_cluster_supported(int S, int A, int H, int B);
 constexpr int kLearnClusterMaxWorld = 8;     // the in-kernel gradient exchange; larger worlds use the separate exchange kernels

@@ -25,16 +25,17 @@ __global__ void __launch_bounds__(kAppendRows) replay_count_kernel(const uint8_t
 // copies are flat loops over the block's [256][S] / [256][A] sub-matrices (coalesced reads, and coalesced writes
 // because ranks of neighbouring rows are consecutive).  The last block to finish bumps the cursor: every block
 // reads the cursor before it takes its ticket, so the bump cannot overtake a reader.
+template <int ROWS>
 __global__ void __launch_bounds__(kAppendThreads)
 replay_append_kernel(rloa_replay rb, int n, const float* __restrict__ states, const float* __restrict__ actions,
                      const float* __restrict__ rewards, const float* __restrict__ next_states,
                      const uint8_t* __restrict__ dones, const uint8_t* __restrict__ valid,
-                     const int* __restrict__ block_counts, unsigned* __restrict__ ticket) {
-    __shared__ int s_slot[kAppendRows];
+                     const int* __restrict__ block_counts, unsigned* __restrict__ ticket, int commit) {
+    __shared__ int s_slot[ROWS];
     __shared__ int s_red[2][kAppendThreads / 32];
-    __shared__ int s_wsum[kAppendRows / 32];
+    __shared__ int s_wsum[ROWS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int row0 = blockIdx.x * kAppendRows;
+    const int row0 = blockIdx.x * ROWS;
     const long long cur = *reinterpret_cast<const volatile long long*>(rb.cursor);
     // valid rows of the earlier blocks / of all blocks: from the per-block counts of replay_count_kernel, or — for
     // the batch sizes of a training loop (n <= 16384) — counted here straight from the mask, which saves the launch
@@ -66,10 +67,10 @@ replay_append_kernel(rloa_replay rb, int n, const float* __restrict__ states, co
         before = row0;
         total = n;
     }
-    // ranks of this block's rows: the first kAppendRows threads own one row each
+    // ranks of this block's rows: the first ROWS threads own one row each
     bool v = false;
     int in_warp = 0;
-    if (tid < kAppendRows) {
+    if (tid < ROWS) {
         const int i = row0 + tid;
         v = i < n && (valid == nullptr || valid[i] != 0);
         const unsigned bal = __ballot_sync(0xffffffffu, v);
@@ -77,7 +78,7 @@ replay_append_kernel(rloa_replay rb, int n, const float* __restrict__ states, co
         if (lane == 0) s_wsum[warp] = __popc(bal);
     }
     __syncthreads();
-    if (tid < kAppendRows) {
+    if (tid < ROWS) {
         int wbase = 0;
         for (int w = 0; w < warp; w++) wbase += s_wsum[w];
         const int rank = before + wbase + in_warp;
@@ -90,7 +91,7 @@ replay_append_kernel(rloa_replay rb, int n, const float* __restrict__ states, co
     }
     __syncthreads();
     const int S = rb.state_size, A = rb.action_size;
-    const int rows = min(kAppendRows, n - row0);
+    const int rows = min(ROWS, n - row0);
     // flat copies of the block's [rows][S] / [rows][A] sub-matrices, four independent loads in flight per thread
     for (int e0 = tid; e0 < rows * S; e0 += 4 * kAppendThreads) {
         float a[4], b[4];
@@ -118,6 +119,7 @@ replay_append_kernel(rloa_replay rb, int n, const float* __restrict__ states, co
         const int slot = s_slot[r];
         if (slot >= 0) rb.actions[(size_t)slot * A + k] = actions[(size_t)row0 * A + e];
     }
+    if (!commit) return;            // rows only: rloa_replay_commit moves the cursor later
     __syncthreads();
     if (tid == 0) {
         __threadfence();
@@ -127,6 +129,24 @@ replay_append_kernel(rloa_replay rb, int n, const float* __restrict__ states, co
             *reinterpret_cast<long long*>(rb.cursor) = cur + total;
         }
     }
+}
+
+// the second half of a deferred append: cursor += number of valid rows (one block)
+__global__ void __launch_bounds__(256) replay_commit_kernel(rloa_replay rb, int n, const uint8_t* __restrict__ valid) {
+    __shared__ int s_red[8];
+    int cnt = 0;
+    if (valid != nullptr) {
+        for (int i = threadIdx.x; i < n; i += 256) cnt += valid[i] != 0 ? 1 : 0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = cnt;
+        __syncthreads();
+        cnt = 0;
+        for (int w = 0; w < 8; w++) cnt += s_red[w];
+    } else {
+        cnt = n;
+    }
+    if (threadIdx.x == 0) *reinterpret_cast<long long*>(rb.cursor) += cnt;
 }
 
 __global__ void __launch_bounds__(256)
@@ -164,9 +184,9 @@ static int check_rb(const rloa_replay* rb, const char* who) {
     return RLOA_OK;
 }
 
-extern "C" int rloa_replay_append(const rloa_replay* rb, int32_t n, const float* states, const float* actions,
-                                  const float* rewards, const float* next_states, const uint8_t* dones,
-                                  const uint8_t* valid, void* stream) {
+static int replay_append_impl(const rloa_replay* rb, int32_t n, const float* states, const float* actions,
+                              const float* rewards, const float* next_states, const uint8_t* dones,
+                              const uint8_t* valid, void* stream, int commit) {
     int rc = check_rb(rb, "rloa_replay_append");
     if (rc != RLOA_OK) return rc;
     RLOA_REQUIRE(n >= 1 && states && actions && rewards && next_states, "rloa_replay_append: null argument");
@@ -180,9 +200,36 @@ extern "C" int rloa_replay_append(const rloa_replay* rb, int32_t n, const float*
         RLOA_LAUNCHED();
     }
     // scratch[0] = ticket counter (zero at rest), scratch[1..] = per-block valid counts (large appends only)
-    replay_append_kernel<<<nblocks, kAppendThreads, 0, st>>>(*rb, n, states, actions, rewards, next_states, dones, valid,
-                                                            count_pass ? rb->scratch + 1 : nullptr,
-                                                            reinterpret_cast<unsigned*>(rb->scratch));
+    if (!commit && !count_pass) {
+        // rows-only copy beside the learn kernel (whose CTAs need EMPTY SMs): 256 rows per block, a quarter of the blocks
+        replay_append_kernel<256><<<(n + 255) / 256, kAppendThreads, 0, st>>>(*rb, n, states, actions, rewards, next_states, dones, valid,
+                                                                              nullptr, reinterpret_cast<unsigned*>(rb->scratch), 0);
+    } else {
+        replay_append_kernel<kAppendRows><<<nblocks, kAppendThreads, 0, st>>>(*rb, n, states, actions, rewards, next_states, dones, valid,
+                                                                               count_pass ? rb->scratch + 1 : nullptr,
+                                                                               reinterpret_cast<unsigned*>(rb->scratch), commit);
+    }
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
+extern "C" int rloa_replay_append(const rloa_replay* rb, int32_t n, const float* states, const float* actions,
+                                  const float* rewards, const float* next_states, const uint8_t* dones,
+                                  const uint8_t* valid, void* stream) {
+    return replay_append_impl(rb, n, states, actions, rewards, next_states, dones, valid, stream, 1);
+}
+
+extern "C" int rloa_replay_append_rows(const rloa_replay* rb, int32_t n, const float* states, const float* actions,
+                                       const float* rewards, const float* next_states, const uint8_t* dones,
+                                       const uint8_t* valid, void* stream) {
+    return replay_append_impl(rb, n, states, actions, rewards, next_states, dones, valid, stream, 0);
+}
+
+extern "C" int rloa_replay_commit(const rloa_replay* rb, int32_t n, const uint8_t* valid, void* stream) {
+    int rc = check_rb(rb, "rloa_replay_commit");
+    if (rc != RLOA_OK) return rc;
+    RLOA_REQUIRE(n >= 1 && n <= rb->capacity, "rloa_replay_commit: bad row count");
+    replay_commit_kernel<<<1, 256, 0, as_stream(stream)>>>(*rb, n, valid);
     RLOA_LAUNCHED();
     return RLOA_OK;
 }

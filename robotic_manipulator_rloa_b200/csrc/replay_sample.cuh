@@ -25,8 +25,9 @@ __device__ __forceinline__ uint32_t feistel(uint32_t x, int bits, uint32_t k0, u
 }
 
 // ring slot of sample number `i` of the batch drawn with (seed, draw): distinct for distinct i < live
-__device__ __forceinline__ size_t replay_sample_slot(const rloa_replay& rb, int i, unsigned long long seed, unsigned long long draw) {
-    const long long cur = *rb.cursor;
+// `cur`: transitions ever appended (the ring's cursor, or the cursor as it will be once pending rows are committed)
+__device__ __forceinline__ size_t replay_sample_slot_at(const rloa_replay& rb, long long cur, int i, unsigned long long seed,
+                                                        unsigned long long draw) {
     const uint32_t live = (uint32_t)(cur < rb.capacity ? cur : rb.capacity);
     if (live == 0) return 0;
     int bits = 1;
@@ -39,6 +40,9 @@ __device__ __forceinline__ size_t replay_sample_slot(const rloa_replay& rb, int 
     } while (x >= live);                          // cycle walking keeps the map a bijection of [0, live)
     // x counts from the oldest live transition, like indexing the deque
     return (size_t)(((cur < rb.capacity ? 0 : cur) + x) % rb.capacity);
+}
+__device__ __forceinline__ size_t replay_sample_slot(const rloa_replay& rb, int i, unsigned long long seed, unsigned long long draw) {
+    return replay_sample_slot_at(rb, *rb.cursor, i, seed, draw);
 }
 
 }  // namespace rloa

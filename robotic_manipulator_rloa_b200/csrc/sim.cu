@@ -18,9 +18,13 @@ namespace rloa {
 enum { kModeStep = 0, kModeResetOnly = 1 };
 
 // launch 1 of an env-step: thread = arm
+// Block = 1 warp for large batches (measured best at 131,072 arms) or 4 warps for small ones: at 4096 arms every warp is
+// latency-bound, four of them on one SM (one per scheduler) run as fast as alone, and the launch then occupies 32 SMs instead
+// of 128 - the 16-CTA learn kernel that runs beside it needs 16 EMPTY SMs (a CTA takes all registers of one).
+constexpr int kDynWideTpb = 128;
 template <int NLMAX>
-__global__ void __launch_bounds__(kTpb) sim_dynamics_kernel(const __grid_constant__ ModelDev M, SimArrays S) {
-    const int env = blockIdx.x * kTpb + threadIdx.x;
+__global__ void __launch_bounds__(kDynWideTpb) sim_dynamics_kernel(const __grid_constant__ ModelDev M, SimArrays S) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env < S.n_envs) arm_dynamics<NLMAX>(M, S, env);
 }
 
@@ -1084,8 +1088,10 @@ static int launch_solve(const rloa_sim* s, const StepCfgDev& c, int mode, const 
 static int launch_dynamics(const rloa_sim* s, cudaStream_t st) {
     const ModelDev& h = s->model->host;
     const unsigned blocks = (unsigned)((s->a.n_envs + kTpb - 1) / kTpb);
-    if (h.nl <= 16) sim_dynamics_kernel<16><<<blocks, kTpb, 0, st>>>(h, s->a);
-    else sim_dynamics_kernel<32><<<blocks, kTpb, 0, st>>>(h, s->a);
+    const int dtpb = s->a.n_envs <= 16384 ? kDynWideTpb : kTpb;
+    const unsigned dblocks = (unsigned)((s->a.n_envs + dtpb - 1) / dtpb);
+    if (h.nl <= 16) sim_dynamics_kernel<16><<<dblocks, dtpb, 0, st>>>(h, s->a);
+    else sim_dynamics_kernel<32><<<dblocks, dtpb, 0, st>>>(h, s->a);
     RLOA_LAUNCHED();
     sim_minv_kernel<<<blocks, dim3(32, h.ndof), (size_t)h.nl * kFRec * 32 * sizeof(float), st>>>(h, s->a);
     RLOA_LAUNCHED();

@@ -265,16 +265,33 @@ class NAFAgent:
             for u in range(self.num_updates):
                 self.learn_from_memory(tick=tick, sub=u)
 
-    def learn_from_memory(self, tick: Optional[torch.Tensor] = None, sub: int = 0) -> None:
+    MAX_PENDING_ROWS = 16384
+
+    def one_launch_learn(self) -> bool:
+        """True when learn_from_memory is a single kernel (tensor-core trunk, supported batch, and - with N > 1 ranks - the
+        peer-memory exchange): the precondition of `pending=` below."""
+        m = self.memory
+        if not self.fused_learn or m._rb is None or self._ws is None:
+            return False
+        xchg = self._exchange()
+        # N > 1 without the peer-memory exchange (RLOA_GRAD_EXCHANGE=nccl): the all-reduce sits between two native calls, so
+        # the update cannot be one launch
+        if not (self.world_size == 1 or (xchg is not None and self.world_size <= 8)):
+            return False
+        ws = self._workspace(self.batch_size)
+        return bool(ws.lib.rloa_naf_learn_fused_supported(ws.handle, self.batch_size))
+
+    def learn_from_memory(self, tick: Optional[torch.Tensor] = None, sub: int = 0, pending=None) -> None:
         """sample + learn without leaving the device (replay_buffer.py:47-67 + naf_algorithm.py:180-213).  With the tensor-core
         trunk and a batch of at most 1024 rows this is ONE kernel: the fused learn kernel draws the sampler's slots itself
-        and reads its rows straight from the ring (rloa_naf_learn_step_replay)."""
+        and reads its rows straight from the ring (rloa_naf_learn_step_replay).
+        pending = (states, actions, rewards, next_states, dones, valid | None): rows being copied into the ring right now
+        (ReplayBuffer.add_batch(..., commit=False) on another stream) and committed after this call - the update samples the
+        ring as it will be (rloa_naf_learn_step_pending); needs one_launch_learn()."""
         b = self._learn_buffers()
         m = self.memory
         ws = self._workspace(self.batch_size)
         xchg = self._exchange()
-        # N > 1 without the peer-memory exchange (RLOA_GRAD_EXCHANGE=nccl): the all-reduce sits between two native calls, so
-        # the update cannot be one launch
         one_launch = self.world_size == 1 or xchg is not None
         if self.fused_learn and one_launch and m._rb is not None and \
                 ws.lib.rloa_naf_learn_fused_supported(ws.handle, self.batch_size):
@@ -282,14 +299,25 @@ class NAFAgent:
             pm, pt = self.qnetwork_main.native_params(), self.qnetwork_target.native_params()
             adam = self.optimizer.native()
             draw = m._draws if tick is None else (int(sub) << 32)
-            N.check(ws.lib.rloa_naf_learn_step_replay(ws.handle, C.byref(pm), C.byref(pt), C.byref(adam),
-                                                      xchg.handle if xchg is not None else None, C.byref(m._rb), m.seed, draw,
-                                                      N.ptr(tick), self.batch_size, C.byref(hp), b['grad'].data_ptr(),
-                                                      b['loss'].data_ptr(), b['gnorm'].data_ptr(), self._stream()),
-                    'rloa_naf_learn_step_replay')
+            if pending is not None:
+                ps, pa, pr, ps2, pd, pv = pending
+                N.check(ws.lib.rloa_naf_learn_step_pending(ws.handle, C.byref(pm), C.byref(pt), C.byref(adam),
+                                                           xchg.handle if xchg is not None else None, C.byref(m._rb), m.seed,
+                                                           draw, N.ptr(tick), self.batch_size, C.byref(hp), ps.shape[0],
+                                                           ps.data_ptr(), pa.data_ptr(), pr.data_ptr(), ps2.data_ptr(),
+                                                           N.ptr(pd), N.ptr(pv), b['grad'].data_ptr(), b['loss'].data_ptr(),
+                                                           b['gnorm'].data_ptr(), self._stream()), 'rloa_naf_learn_step_pending')
+            else:
+                N.check(ws.lib.rloa_naf_learn_step_replay(ws.handle, C.byref(pm), C.byref(pt), C.byref(adam),
+                                                          xchg.handle if xchg is not None else None, C.byref(m._rb), m.seed, draw,
+                                                          N.ptr(tick), self.batch_size, C.byref(hp), b['grad'].data_ptr(),
+                                                          b['loss'].data_ptr(), b['gnorm'].data_ptr(), self._stream()),
+                        'rloa_naf_learn_step_replay')
             m._draws += 1
             self.last_loss, self.last_grad_norm = b['loss'], b['gnorm']
             return
+        if pending is not None:
+            raise RuntimeError('learn_from_memory(pending=...) needs the one-kernel update (one_launch_learn())')
         self.memory.sample_into(b['s'], b['a'], b['r'], b['s2'], b['d'], tick=tick, sub=sub)
         self._learn_device(b['s'], b['a'], b['r'], b['s2'], b['d'])
 
@@ -506,6 +534,11 @@ class VectorLoop:
         self._host = None               # pinned host buffers bound by bind_host_buffers
         self._host_ready = None         # event behind the D2H of (state, reward, done) in the host-facing iteration
         self._copy_stream = None
+        # one-kernel update: the copy into the replay ring runs beside it (see _body); RLOA_OVERLAP_STORE=0: in sequence (A/B)
+        self.overlap_store = os.environ.get('RLOA_OVERLAP_STORE', '1') != '0'
+        self._store_stream = None
+        self._fork_stream = None
+        self._store_pending = False     # a commit on the store stream that the main stream has not waited for yet
         self._host_graphs = None
 
     @property
@@ -528,7 +561,12 @@ class VectorLoop:
         if self.phase_events is not None:
             self.phase_events[parity][k].record()
 
-    def _body(self, auto_reset: bool, learn_now: bool, parity: int) -> None:
+    def _join_store(self) -> None:
+        if self._store_pending:
+            torch.cuda.current_stream(self.agent.device).wait_stream(self._store_stream)
+            self._store_pending = False
+
+    def _body(self, auto_reset: bool, learn_now: bool, parity: int, join_store: bool = True) -> None:
         a, env = self.agent, self.env
         self._mark(parity, 0)
         if learn_now:             # the weights are final since the last update: their images are written beside act / step
@@ -536,13 +574,16 @@ class VectorLoop:
         a.act_batch(self.state, out=self.actions, tick=self.tick)
         self._mark(parity, 1)
         env.sim.step(self.actions, out=(self.next_state, self.reward, self.done), valid=self.valid)
-        if self.pipeline_sim:     # dynamics + M^-1 of the NEXT step overlap the replay / learn phase of this one
-            env.sim.prepare()
-        self._mark(parity, 2)
-        if self.store:
-            a.memory.add_batch(self.state, self.actions, self.reward, self.next_state, self.done,
-                               valid=self.valid if auto_reset else None)
-        self._mark(parity, 3)
+        # One-kernel update (tensor-core trunk): its 16 CTAs need a whole SM each (all 64 K registers, 231 KB of shared memory),
+        # so it is enqueued FIRST after the step - behind it, on forked streams that only wait for the step: the dynamics +
+        # M^-1 of the next step, the episode bookkeeping and the copy of the step's rows into the replay ring (the update
+        # reads drawn slots of the pending range from the loop's own buffers; the cursor moves once it has finished: same
+        # samples, same ring).  Launched the other way round, the 128 one-warp blocks of the dynamics kernel sit on 128 SMs
+        # and the update waits ~15 us for 16 empty ones.
+        valid = self.valid if auto_reset else None
+        overlap = (self.store and learn_now and self.overlap_store and a.num_updates == 1 and self.n <= a.MAX_PENDING_ROWS
+                   and a.memory._rb is not None and self.n <= a.memory.buffer_size and a.one_launch_learn())
+        cur = torch.cuda.current_stream(a.device)
         tick = self.tick
         common = (self.reward.data_ptr(), self.done.data_ptr(), self.valid.data_ptr(), self.score.data_ptr(),
                   self.frame.data_ptr(), self.reset_mask.data_ptr(), self.log_score.data_ptr(), self.log_frame.data_ptr(),
@@ -559,18 +600,50 @@ class VectorLoop:
                     'rloa_episode_update_reset')
 
         early = auto_reset and self.pipeline_sim      # beside the update, on the simulator's side stream
-        if early:
-            bookkeeping_reset()
-        if learn_now:
-            for u in range(a.num_updates):
-                a.learn_from_memory(tick=tick, sub=u)
-        self._mark(parity, 4)
+        self._join_store()                            # the previous step's commit (long finished)
+        if overlap:
+            if self._store_stream is None:
+                self._store_stream, self._fork_stream = torch.cuda.Stream(a.device), torch.cuda.Stream(a.device)
+            stepped = cur.record_event()
+            self._mark(parity, 2)
+            self._mark(parity, 3)
+            a.learn_from_memory(tick=tick, sub=0, pending=(self.state, self.actions, self.reward, self.next_state, self.done, valid))
+            self._mark(parity, 4)
+            self._fork_stream.wait_event(stepped)
+            with torch.cuda.stream(self._fork_stream):
+                if self.pipeline_sim:
+                    env.sim.prepare()
+                if early:
+                    bookkeeping_reset()
+            self._store_stream.wait_event(stepped)
+            with torch.cuda.stream(self._store_stream):
+                a.memory.add_batch(self.state, self.actions, self.reward, self.next_state, self.done, valid=valid, commit=False)
+            self._store_stream.wait_stream(cur)
+            with torch.cuda.stream(self._store_stream):
+                a.memory.commit_rows(self.n, valid)
+            self._store_pending = True
+            cur.wait_stream(self._fork_stream)        # nothing but the fork itself lives there; the work is joined below
+        else:
+            if self.pipeline_sim:     # dynamics + M^-1 of the NEXT step overlap the replay / learn phase of this one
+                env.sim.prepare()
+            self._mark(parity, 2)
+            if self.store:
+                a.memory.add_batch(self.state, self.actions, self.reward, self.next_state, self.done, valid=valid)
+            self._mark(parity, 3)
+            if early:
+                bookkeeping_reset()
+            if learn_now:
+                for u in range(a.num_updates):
+                    a.learn_from_memory(tick=tick, sub=u)
+            self._mark(parity, 4)
         if auto_reset and not early:
             bookkeeping_reset()
         elif not auto_reset:
             N.check(self.lib.rloa_episode_update(self.n, self.frames, *common, a._stream()), 'rloa_episode_update')
         if self.pipeline_sim:
             env.sim.join()
+        if join_store:            # eager steps leave the ring committed on the caller's stream; inside the captured pair only
+            self._join_store()    # the last iteration joins (the next one waits where it touches the ring)
         self._mark(parity, 5)
         self.state, self.next_state = self.next_state, self.state
         self._odd ^= 1
@@ -606,7 +679,7 @@ class VectorLoop:
             launched = self.lib.rloa_launch_count()
             # thread_local: other host threads (NCCL watchdog, clock sampler) may keep calling the CUDA API
             with torch.cuda.graph(g, capture_error_mode='thread_local'):
-                self._body(True, self.learn, 0)
+                self._body(True, self.learn, 0, join_store=False)
                 self._body(True, self.learn, 1)
             self._graph, self._graph_learn = g, self.learn
             self._odd, self._graph_par = 0, self._par

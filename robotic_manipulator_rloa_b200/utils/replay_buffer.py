@@ -80,8 +80,11 @@ class ReplayBuffer:
                        torch.tensor([1 if done else 0], dtype=torch.uint8, device=dev))
 
     def add_batch(self, states: torch.Tensor, actions: torch.Tensor, rewards: torch.Tensor, next_states: torch.Tensor,
-                  dones: torch.Tensor, valid: Optional[torch.Tensor] = None, n_valid: Optional[int] = None) -> None:
-        """n transitions already on the device (fp32 rows, uint8 dones / valid)."""
+                  dones: torch.Tensor, valid: Optional[torch.Tensor] = None, n_valid: Optional[int] = None,
+                  commit: bool = True) -> None:
+        """n transitions already on the device (fp32 rows, uint8 dones / valid).  commit=False copies the rows without moving
+        the cursor (rloa_replay_append_rows): the caller finishes with `commit_rows` once the ring's concurrent readers are
+        done (VectorLoop runs the copy beside the update, which reads the pending rows from the step's own buffers)."""
         n = states.shape[0]
         if self._rb is None:
             self._allocate(states.shape[1], actions.shape[1])
@@ -89,15 +92,19 @@ class ReplayBuffer:
             self._max_append = n
             self.scratch = torch.zeros((n + 63) // 64 + 2, dtype=torch.int32, device=self.device)
             self._rb.scratch = self.scratch.data_ptr()
-        N.check(self.lib.rloa_replay_append(C.byref(self._rb), n, states.data_ptr(), actions.data_ptr(),
-                                            rewards.data_ptr(), next_states.data_ptr(), N.ptr(dones), N.ptr(valid),
-                                            self._stream()), 'rloa_replay_append')
+        fn = self.lib.rloa_replay_append if commit else self.lib.rloa_replay_append_rows
+        N.check(fn(C.byref(self._rb), n, states.data_ptr(), actions.data_ptr(), rewards.data_ptr(), next_states.data_ptr(),
+                   N.ptr(dones), N.ptr(valid), self._stream()), 'rloa_replay_append')
         # host mirror of the live count; with a valid mask and no n_valid it is an upper bound (exact value:
         # sync_len()) — the `len(memory) > batch_size` gate only matters before the ring first fills a batch
         added = n if (valid is None or n_valid is None) else int(n_valid)
         if valid is not None and n_valid is None:
             self._len_exact = False
         self._len = min(self.buffer_size, self._len + added)
+
+    def commit_rows(self, n: int, valid: Optional[torch.Tensor] = None) -> None:
+        """Second half of add_batch(..., commit=False): the cursor moves past the rows copied then."""
+        N.check(self.lib.rloa_replay_commit(C.byref(self._rb), int(n), N.ptr(valid), self._stream()), 'rloa_replay_commit')
 
     def gate_open(self, pending: int = 0, pending_exact: bool = True) -> bool:
         """The `len(memory) > batch_size` gate of NAFAgent.step (naf_algorithm.py:150), evaluated on the EXACT live count:

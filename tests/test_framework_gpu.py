@@ -160,6 +160,36 @@ def test_short_training_run_learns_something():
     assert np.isfinite(d1)
 
 
+def test_store_beside_the_update_is_bit_identical():
+    """With the one-kernel update the step's rows are copied into the replay ring on another stream WHILE the update runs (it
+    reads drawn slots of the pending range from the loop's own buffers) and the cursor moves afterwards.  Against append ->
+    sample + learn in sequence: same samples, same parameters, same ring - through wrap-around (ring of 4096 rows, 256 arms),
+    partial valid masks (20-frame episodes, 50 reset sub-steps), eager launches and the captured graph."""
+    runs = []
+    for overlap in (False, True):
+        env, agent, loop = _twin(256)
+        agent.set_trunk_mode(1)
+        loop.overlap_store = overlap
+        for _ in range(24):
+            loop.step()
+        assert loop.capture(), loop.graph_error
+        for _ in range(20):
+            loop.replay_pair()
+        loop.step(); loop.step()
+        torch.cuda.synchronize()
+        assert (loop._store_stream is not None) == overlap
+        m = agent.memory
+        runs.append(dict(cursor=int(m.cursor.item()), ring=[t.clone() for t in (m.states, m.actions, m.rewards, m.next_states, m.dones)],
+                         params=torch.cat([p.detach().reshape(-1) for net in (agent.qnetwork_main, agent.qnetwork_target)
+                                           for p in net.parameters()]).clone(),
+                         loss=float(agent.last_loss.item()), transitions=int(loop.transitions.item())))
+    a, b = runs
+    assert a['cursor'] == b['cursor'] > 4096 and a['transitions'] == b['transitions']
+    for x, y in zip(a['ring'], b['ring']):
+        assert torch.equal(x, y)
+    assert torch.equal(a['params'], b['params']) and a['loss'] == b['loss']
+
+
 def test_step_host_moves_every_step_through_pinned_buffers():
     """step_host: the caller's pinned buffers carry states in and actions / states / rewards / dones out; the graph
     replays and the eager launches of the same path produce the same trajectory."""
