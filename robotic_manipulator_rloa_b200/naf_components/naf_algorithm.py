@@ -734,23 +734,46 @@ class VectorLoop:
         a, env = self.agent, self.env
         self.actions.copy_(h_action, non_blocking=True)                   # H2D: actions into Environment.step
         env.sim.step(self.actions, out=(self.next_state, self.reward, self.done), valid=self.valid)
-        if self.pipeline_sim:
-            env.sim.prepare()
-        # D2H of (state, reward, done) on a copy stream: it overlaps the store / learn phase and is joined at the end
         cur = torch.cuda.current_stream(a.device)
+        # same schedule as _body: the one-kernel update first, everything that only needs the step forked behind it
+        overlap = (learn_now and self.overlap_store and a.num_updates == 1 and self.n <= a.MAX_PENDING_ROWS
+                   and a.memory._rb is not None and self.n <= a.memory.buffer_size and a.one_launch_learn())
+        self._join_store()
+        stepped = cur.record_event()
+        # D2H of (state, reward, done) on a copy stream: it overlaps the store / learn phase and is joined at the end
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(a.device)
-        self._copy_stream.wait_stream(cur)
+        self._copy_stream.wait_event(stepped)
         with torch.cuda.stream(self._copy_stream):
             h_state.copy_(self.next_state, non_blocking=True)
             h_reward.copy_(self.reward, non_blocking=True)
             h_done.copy_(self.done, non_blocking=True)
             if self._host_ready is not None:      # what step_host waits for: the caller's buffers are complete here
                 self._host_ready.record(self._copy_stream)
-        a.memory.add_batch(self.state, self.actions, self.reward, self.next_state, self.done, valid=self.valid)
-        if learn_now:
-            for u in range(a.num_updates):
-                a.learn_from_memory(tick=self.tick, sub=u)
+        if overlap:
+            if self._store_stream is None:
+                self._store_stream, self._fork_stream = torch.cuda.Stream(a.device), torch.cuda.Stream(a.device)
+            a.learn_from_memory(tick=self.tick, sub=0,
+                                pending=(self.state, self.actions, self.reward, self.next_state, self.done, self.valid))
+            if self.pipeline_sim:
+                self._fork_stream.wait_event(stepped)
+                with torch.cuda.stream(self._fork_stream):
+                    env.sim.prepare()
+                cur.wait_stream(self._fork_stream)
+            self._store_stream.wait_event(stepped)
+            with torch.cuda.stream(self._store_stream):
+                a.memory.add_batch(self.state, self.actions, self.reward, self.next_state, self.done, valid=self.valid, commit=False)
+            self._store_stream.wait_stream(cur)
+            with torch.cuda.stream(self._store_stream):
+                a.memory.commit_rows(self.n, self.valid)
+            self._store_pending = True
+        else:
+            if self.pipeline_sim:
+                env.sim.prepare()
+            a.memory.add_batch(self.state, self.actions, self.reward, self.next_state, self.done, valid=self.valid)
+            if learn_now:
+                for u in range(a.num_updates):
+                    a.learn_from_memory(tick=self.tick, sub=u)
         N.check(self.lib.rloa_episode_update_reset(
             env.sim._h_sim, self.frames, self.reward.data_ptr(), self.done.data_ptr(), self.valid.data_ptr(),
             self.score.data_ptr(), self.frame.data_ptr(), self.reset_mask.data_ptr(), self.log_score.data_ptr(),
@@ -761,6 +784,7 @@ class VectorLoop:
         if self.pipeline_sim:
             env.sim.join()
         cur.wait_stream(self._copy_stream)
+        self._join_store()
 
     def step_host(self, use_graph: bool = True) -> None:
         """One iteration through the bound host buffers: [H2D states, act, D2H actions] sync
