@@ -485,8 +485,8 @@ def train_workload(ctx, args, c, steps, full):
         h_rew = torch.zeros(n).pin_memory(); h_done = torch.zeros(n, dtype=torch.uint8).pin_memory()
         h_state.copy_(loop.state)
         loop.bind_host_buffers(h_state, h_act, h_rew, h_done)
-        e2e_steps = max(10, steps // 4)
-        for _ in range(3):                     # warm-up of the host-facing path (captures its two graphs)
+        e2e_steps = max(20, steps)
+        for _ in range(10):                    # warm-up of the host-facing path (captures its two graphs)
             loop.step_host(use_graph=use_graph)
         loop.transitions.zero_()
         ctx.barrier()
@@ -499,7 +499,9 @@ def train_workload(ctx, args, c, steps, full):
         e2e_ms = ctx.reduce(e0.elapsed_time(e1), 'MAX')
         e2e_tr = ctx.reduce(float(loop.transitions.item()), 'SUM')
         rec['e2e'] = {'value': e2e_tr / (e2e_ms * 1e-3), 'unit': 'env-steps/s', 'h2d_bytes_per_step': n * (S + A) * 4,
-                      'd2h_bytes_per_step': n * (A * 4 + S * 4 + 4 + 1), 'steps': e2e_steps}
+                      'd2h_bytes_per_step': n * (A * 4 + S * 4 + 4 + 1), 'steps': e2e_steps,
+                      'ms_per_step': e2e_ms / e2e_steps, 'valid_fraction': e2e_tr / (world * n * e2e_steps),
+                      'graphed': bool(loop._host_graphs), 'graph_error': loop.graph_error}
 
         # ---- the reference-exact arithmetic (all-fp32 NAF, no tensor cores) on the same loop, driver-run ----
         loop.state.copy_(loop.next_state)      # step_host keeps the newest observation in next_state / the host buffer

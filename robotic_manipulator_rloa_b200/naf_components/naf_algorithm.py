@@ -800,6 +800,9 @@ class VectorLoop:
                 (not self.learn or a._bufs is not None):
             host_len = a.memory._len
             try:
+                if self.pipeline_sim:      # the graphs bake in whether Environment.step finds its first half prepared: capture
+                    self.env.sim.prepare()  # the steady state (every replay leaves the next step prepared), not a cold start
+                    self.env.sim.join()
                 torch.cuda.synchronize(a.device)
                 g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g1, capture_error_mode='thread_local'):

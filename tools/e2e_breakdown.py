@@ -42,3 +42,9 @@ torch.cuda.synchronize()
 loop.transitions.zero_() if False else None
 print('per step us: launch g1 %.1f | wait act+D2H actions %.1f | launch g2 %.1f | wait step+D2H results %.1f | total %.1f' % (
     *(x / K * 1e6 for x in T), t_all / K * 1e6))
+t_all = time.perf_counter()
+for _ in range(K):
+    loop.step_host()
+t_all = time.perf_counter() - t_all
+torch.cuda.synchronize()
+print('through VectorLoop.step_host: %.1f us per step' % (t_all / K * 1e6))
