@@ -485,7 +485,7 @@ def train_workload(ctx, args, c, steps, full):
         h_rew = torch.zeros(n).pin_memory(); h_done = torch.zeros(n, dtype=torch.uint8).pin_memory()
         h_state.copy_(loop.state)
         loop.bind_host_buffers(h_state, h_act, h_rew, h_done)
-        e2e_steps = max(20, steps)
+        e2e_steps = max(20, min(5 * steps, 1000))      # ~0.2 s of host-driven steps: a single host hiccup of a few ms must not decide the number
         for _ in range(10):                    # warm-up of the host-facing path (captures its two graphs)
             loop.step_host(use_graph=use_graph)
         loop.transitions.zero_()
