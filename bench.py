@@ -766,7 +766,7 @@ def ours(args):
                                                 'achieved': tflops_measured, 'frac': tflops_measured / fp32_peak},
                          'avg_launch_ms': sim_avg_ms, 'share_of_step': sim_avg_ms / max(rec['phase_sum_ms'], 1e-9),
                          'traffic': 8.18e6, 'traffic_source': 'ncu --set full at 4096 arms, dram read+write of the three kernels per '
-                                                              'launch, caches flushed by ncu (profiles/r2w_sim4096_ncu_full.md)',
+                                                              'launch, caches flushed by ncu (profiles/r3c_sim4096_ncu_full.md)',
                          'hbm': {'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak, 'peak_source': which,
                                  'bytes_per_env_step': BYTES_PER_ENV_STEP}},
             'roofline_naf_update': {'kernel': 'NAFAgent.learn (replay batch %d, both networks, backward, clip + Adam + soft update)' % batch,
@@ -774,9 +774,9 @@ def ours(args):
                                     'frac': naf_tf / tensor_peak, 'flop_per_update': NAF_FLOP_PER_SAMPLE * batch,
                                     'us_per_update': learn_us, 'hbm_gbs': naf_gbs, 'hbm_frac': naf_gbs / hbm_peak,
                                     'bytes_per_update': naf_bytes, 'peak_source': which + ' bf16_tflops_sustained',
-                                    'traffic': 2.74e6 if args.trunk == 'tc' else None,
+                                    'traffic': 2.77e6 if args.trunk == 'tc' else None,
                                     'traffic_source': 'ncu --set full, dram read+write of learn_pack_kernel + naf_learn_cluster_kernel per update '
-                                                      '(profiles/r2w_learn_cluster_ncu_full.md; the writes stay in L2)',
+                                                      '(profiles/r3c_learn_cluster_ncu_full.md; the writes stay in L2)',
                                     'note': 'latency-bound at this batch: both floors (0.45 us tensor, 0.5 - 1.8 us HBM) are far below the '
                                             'barrier / epilogue latency of the chain'},
             'cpu_baseline': cpu,
