@@ -151,12 +151,13 @@ typedef struct {
 int rloa_sim_step(rloa_sim* s, const rloa_step_config* cfg, const float* actions, const uint8_t* active,
                   float* obs, float* reward, uint8_t* done, uint8_t* valid, void* stream);
 
-/* Contact breaking threshold used by rloa_sim_reset's sub-steps (Environment.reset steps the same world as step, contact
- * rows included; rloa_sim_step takes its threshold from the config).  0 = off. */
+/* Contact breaking threshold used by rloa_sim_reset's sub-steps and by rloa_sim_prepare's collision phase (Environment.reset
+ * steps the same world as step, contact rows included; rloa_sim_step takes its threshold from the config and repeats the
+ * collision phase when a prepare ran with another one).  0 = off. */
 int rloa_sim_set_contacts(rloa_sim* s, float contact_threshold);
-/* Number of contact rows each env's NEXT stepSimulation will carry (what the last step's distance pass found within the
- * contact threshold: Bullet's contact manifold points of the arm against the two bodies of environment.py:252-255);
- * -1 = unknown, the pose was set from outside a step and the collision phase runs inside the next step.
+/* Number of contact rows the latest collision phase found per env (Bullet's contact manifold points of the arm against the two
+ * bodies of environment.py:252-255, at most 4).  The collision phase runs on the pose a stepSimulation starts from: inside
+ * rloa_sim_prepare (so after a prepare the counts are those of the NEXT step) or at the start of rloa_sim_step.
  * counts: int32 [n_envs] DEVICE. */
 int rloa_sim_contact_counts(rloa_sim* s, int32_t* counts, void* stream);
 

@@ -28,6 +28,19 @@ __global__ void __launch_bounds__(kDynWideTpb) sim_dynamics_kernel(const __grid_
     if (env < S.n_envs) arm_dynamics<NLMAX>(M, S, env);
 }
 
+// collision phase of a stepSimulation: the contact rows of the CURRENT pose against the obstacle sphere and the
+// target cube -> crow / near.  Runs with the action-independent half of the step (rloa_sim_prepare: beside the NAF update),
+// so the solve kernel finds its rows ready and its own distance pass looks for hits only; thread = arm.
+template <int NLMAX>
+__global__ void __launch_bounds__(kDynWideTpb) sim_contacts_kernel(const __grid_constant__ ModelDev M, SimArrays S, float thr) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= S.n_envs) return;
+    const V3 tg = ld3(S.target + 3 * (size_t)env), ob = ld3(S.obstacle + 3 * (size_t)env);
+    const ObsOut o = fk_and_distances<NLMAX, false>(M, S.q + env, S.n_envs, ob, tg, 0.f, false, nullptr, 0, thr, true,
+                                                    S.crow + (size_t)env * kMaxContacts * kContactRec);
+    S.near[env] = o.ncontacts;
+}
+
 // launch 2: block = 32 arms x ndof columns, warp = one column of M^-1 for 32 arms.  The factor records of the
 // block's 32 arms are staged once in shared memory ([link][component][arm], conflict-free) by all warps, so the
 // ndof column warps stop re-reading them from L2 and the serial tree walks see shared-memory latency.
@@ -230,8 +243,8 @@ sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_c
         }
 
         // ---- contact rows against the obstacle sphere / the target cube (environment.py:252-255 loads both
-        // as collidable fixed bodies).  Only arms flagged `near` by the previous step's distance pass pay for the
-        // collision phase; their rows live in local memory (dynamic contact index) ----
+        // as collidable fixed bodies).  The rows come from the collision phase (sim_contacts_kernel); they live in local memory
+        // here (dynamic contact index) ----
         int nc = 0;
         constexpr int kCP = kMaxDof / 2;
         __align__(16) float2 cJ2[kMaxContacts * kCP], cU2[kMaxContacts * kCP];        // pairs (dof 2k, 2k + 1) like dv
@@ -239,9 +252,9 @@ sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_c
         float* cU = reinterpret_cast<float*>(cU2);
         float crhs[kMaxContacts], cjdi[kMaxContacts], capp[kMaxContacts], cjmj[kMaxContacts];
         const int nflag = cfg.contact_thr > 0.f ? S.near[env] : 0;
-        if (nflag != 0 && !(cfg.contact_dbg & 2)) {
+        if (nflag > 0 && !(cfg.contact_dbg & 2)) {
             float cd[kMaxContacts];
-            if (nflag > 0) {        // rows left by the previous step's distance pass (same pose)
+            {                       // rows left by the collision phase (sim_contacts_kernel, same pose)
                 nc = min(nflag, kMaxContacts);
                 const float* row = S.crow + (size_t)env * kMaxContacts * kContactRec;
                 for (int c = 0; c < nc; c++) {
@@ -249,9 +262,6 @@ sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_c
                     for (int a = 0; a < kMaxDof; a++) cJ[c * kMaxDof + a] = a < D ? row[c * kContactRec + a] : 0.f;
                     cd[c] = row[c * kContactRec + kMaxDof];
                 }
-            } else {                // the pose was set from outside a step: collision phase from scratch
-                const V3 tg0 = ld3(S.target + 3 * (size_t)env), ob0 = ld3(S.obstacle + 3 * (size_t)env);
-                nc = build_contacts<NLMAX>(M, S.q + env, N, ob0, tg0, cfg.contact_thr, cJ, cd);
             }
             if (cfg.contact_dbg & 1) nc = 0;          // diagnostics: pay for the collision phase only
             for (int c = 0; c < nc; c++) {
@@ -379,7 +389,6 @@ sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_c
 
         // ---- state / reward / done from the post-step configuration ----
         const V3 tg = ld3(S.target + 3 * (size_t)env), ob = ld3(S.obstacle + 3 * (size_t)env);
-        const bool contacts_on = cfg.contact_thr > 0.f;
         // the observed joint states are requested before the kinematics, so their round trip hides behind it
         const int n = M.n_obs;
         float oq[kMaxDof], oqd[kMaxDof];
@@ -388,10 +397,7 @@ sim_solve_kernel(const __grid_constant__ ModelDev M, SimArrays S, const __grid_c
             oq[i] = (i < n && obs != nullptr) ? S.q[(size_t)i * sN + env] : 0.f;
             oqd[i] = (i < n && obs != nullptr) ? S.qd[(size_t)i * sN + env] : 0.f;
         }
-        const ObsOut o = fk_and_distances<NLMAX, GJK>(M, S.q + env, N, ob, tg, cfg.obstacle_thr, !is_reset, nullptr, 0,
-                                                      cfg.contact_thr, contacts_on,
-                                                      contacts_on ? S.crow + (size_t)env * kMaxContacts * kContactRec : nullptr);
-        if (contacts_on) S.near[env] = o.ncontacts;
+        const ObsOut o = fk_and_distances<NLMAX, GJK>(M, S.q + env, N, ob, tg, cfg.obstacle_thr, !is_reset, nullptr, 0);
         if (obs != nullptr) {
 #pragma unroll
             for (int i = 0; i < kMaxDof; i++)
@@ -726,7 +732,8 @@ struct rloa_sim {
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     bool prepared = false;           // F / qs / M^-1 hold the current (q, qd): rloa_sim_step launches the solve only
     bool join_pending = false;       // the caller's stream has not yet waited for the side stream
-    float contact_thr = 0.f;         // contact rows of the synchronous reset (rloa_sim_set_contacts); steps carry theirs in the config
+    float contact_thr = 0.f;         // contact rows of rloa_sim_prepare / rloa_sim_reset (rloa_sim_set_contacts); steps carry theirs in the config
+    float prepared_thr = -1.f;       // threshold the prepared collision phase ran with (-1: none)
 };
 
 // the caller's stream waits for an outstanding rloa_sim_prepare; with invalidate the prepared half is dropped
@@ -736,11 +743,6 @@ static int sim_sync_prepared(rloa_sim* s, cudaStream_t st, bool invalidate) {
         s->join_pending = false;
     }
     if (invalidate) s->prepared = false;
-    return RLOA_OK;
-}
-// the pose changed outside a step (set_state / clear): the contact-candidate flags are unknown -> conservative
-static int sim_mark_near(rloa_sim* s, cudaStream_t st) {
-    RLOA_CUDA(cudaMemsetAsync(s->a.near, 0xff, (size_t)s->a.n_envs * sizeof(int), st));        // -1: unknown
     return RLOA_OK;
 }
 
@@ -934,7 +936,7 @@ extern "C" int rloa_sim_create(const rloa_model* m, int32_t n_envs, rloa_sim** o
     cudaEventCreateWithFlags(&s->join_ev, cudaEventDisableTiming);
     cudaFuncSetAttribute(sim_minv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxLinks * kFRec * 32 * (int)sizeof(float));
     cudaMemset(s->block, 0, floats * sizeof(float));
-    cudaMemset(s->a.near, 0xff, N * sizeof(int));        // -1 = unknown pose: every arm runs the collision phase on its first step
+    cudaMemset(s->a.near, 0, N * sizeof(int));
     sim_clear_kernel<<<(unsigned)((n + 255) / 256), 256>>>(s->a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (cudaDeviceSynchronize() != cudaSuccess) {
@@ -989,7 +991,7 @@ extern "C" int rloa_sim_set_state(rloa_sim* s, const float* q, const float* qd, 
     if (rc != RLOA_OK) return rc;
     if (q && (rc = scatter(s, q, s->a.q, stream)) != RLOA_OK) return rc;
     if (qd && (rc = scatter(s, qd, s->a.qd, stream)) != RLOA_OK) return rc;
-    return sim_mark_near(s, as_stream(stream));
+    return RLOA_OK;
 }
 
 extern "C" int rloa_sim_get_state(const rloa_sim* s, float* q, float* qd, void* stream) {
@@ -1020,7 +1022,7 @@ extern "C" int rloa_sim_clear(rloa_sim* s, void* stream) {
     const size_t n = (size_t)s->a.n_envs * s->a.nl;
     sim_clear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(s->a);
     RLOA_LAUNCHED();
-    return sim_mark_near(s, as_stream(stream));
+    return RLOA_OK;
 }
 
 static int make_step_cfg(const rloa_sim* s, const rloa_step_config* c, StepCfgDev* out) {
@@ -1085,6 +1087,18 @@ static int launch_solve(const rloa_sim* s, const StepCfgDev& c, int mode, const 
 
 // one stepSimulation for every env = three launches on the caller's stream
 // the action-independent half of a stepSimulation: dynamics + M^-1 columns for the current (q, qd)
+// the collision phase for the current pose (contact rows -> crow / near); thr <= 0: none, the solve sees no rows
+static int launch_contacts(const rloa_sim* s, float thr, cudaStream_t st) {
+    if (!(thr > 0.f)) return RLOA_OK;       // the solve ignores `near` without a threshold
+    const ModelDev& h = s->model->host;
+    const int tpb = s->a.n_envs <= 16384 ? kDynWideTpb : kTpb;
+    const unsigned blocks = (unsigned)((s->a.n_envs + tpb - 1) / tpb);
+    if (h.nl <= 16) sim_contacts_kernel<16><<<blocks, tpb, 0, st>>>(h, s->a, thr);
+    else sim_contacts_kernel<32><<<blocks, tpb, 0, st>>>(h, s->a, thr);
+    RLOA_LAUNCHED();
+    return RLOA_OK;
+}
+
 static int launch_dynamics(const rloa_sim* s, cudaStream_t st) {
     const ModelDev& h = s->model->host;
     const unsigned blocks = (unsigned)((s->a.n_envs + kTpb - 1) / kTpb);
@@ -1100,10 +1114,15 @@ static int launch_dynamics(const rloa_sim* s, cudaStream_t st) {
 
 // one stepSimulation for every env = three launches on the caller's stream
 static int launch_substep(const rloa_sim* s, const StepCfgDev& c, int mode, const float* actions, const uint8_t* active,
-                          float* obs, float* reward, uint8_t* done, uint8_t* valid, cudaStream_t st, bool skip_dynamics = false) {
+                          float* obs, float* reward, uint8_t* done, uint8_t* valid, cudaStream_t st, bool skip_dynamics = false,
+                          float prepared_thr = -1.f) {
     const ModelDev& h = s->model->host;
     if (!skip_dynamics) {
         const int rc = launch_dynamics(s, st);
+        if (rc != RLOA_OK) return rc;
+    }
+    if (!skip_dynamics || prepared_thr != c.contact_thr) {        // collision phase on the pose the step starts from
+        const int rc = launch_contacts(s, c.contact_thr, st);
         if (rc != RLOA_OK) return rc;
     }
     if (h.nl <= 16) return launch_solve<16>(s, c, mode, actions, active, obs, reward, done, valid, st);
@@ -1132,6 +1151,9 @@ extern "C" int rloa_sim_prepare(rloa_sim* s, void* stream) {
     RLOA_CUDA(cudaStreamWaitEvent(s->side, s->fork_ev, 0));
     rc = launch_dynamics(s, s->side);
     if (rc != RLOA_OK) return rc;
+    rc = launch_contacts(s, s->contact_thr, s->side);
+    if (rc != RLOA_OK) return rc;
+    s->prepared_thr = s->contact_thr;
     RLOA_CUDA(cudaEventRecord(s->join_ev, s->side));
     s->prepared = true;
     s->join_pending = true;
@@ -1152,7 +1174,8 @@ extern "C" int rloa_sim_step(rloa_sim* s, const rloa_step_config* cfg, const flo
     const bool prepared = s->prepared;
     rc = sim_sync_prepared(s, as_stream(stream), true);     // the step consumes (and ends) the prepared state
     if (rc != RLOA_OK) return rc;
-    return launch_substep(s, c, kModeStep, actions, active, obs, reward, done, valid, as_stream(stream), prepared);
+    return launch_substep(s, c, kModeStep, actions, active, obs, reward, done, valid, as_stream(stream), prepared,
+                          prepared ? s->prepared_thr : -1.f);
 }
 
 extern "C" int rloa_sim_begin_reset(rloa_sim* s, const uint8_t* mask, const float* init_targets, int32_t n_init,

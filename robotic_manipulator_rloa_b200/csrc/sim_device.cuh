@@ -76,8 +76,7 @@ struct SimArrays {
     float *target, *obstacle;               // [N][3]
     int* iters;                             // [N]
     int* reset_left;                        // [N] pending reset sub-steps (lock-step asynchronous reset)
-    int* near;                              // [N] contact rows of the CURRENT pose stored in crow (written by the step's distance
-                                            //     pass); -1 = unknown (the pose was set from outside): the step rebuilds them
+    int* near;                              // [N] contact rows stored in crow by the latest collision phase (sim_contacts_kernel)
     float* crow;                            // [N][kMaxContacts][kMaxDof + 1] J row | signed distance (NULL-safe: only with contacts)
     float* F;                               // [nl][kFRec][N] ABA factor records (dynamics -> minv)
     float* qs;                              // [nl][N] free velocity qd + dt*qdd, clamped
@@ -297,33 +296,6 @@ __device__ __forceinline__ void shape_contacts(const ModelDev& M, int s, const M
         add(l, x, r_s, obstacle, M.obstacle_radius);
     }
     if (type != RLOA_SHAPE_BOX && near_t) cube_contact(type, l, dim, ps, ax, target, th, M_contact_thr, add);
-}
-
-// one contact: keep it when closer than thr, write its Jacobian row J[d] = d(n . p_contact)/dq_d (0 off the link's chain) and
-// its distance; Rw / pw = world frames of all links.  Returns 1 when a row was written.
-__device__ __forceinline__ int contact_row(const ModelDev& M, const float* Rw, const float* pw, int link, V3 x, float r_shape, V3 from,
-                                           float r_body, float thr, float* __restrict__ Jc, float* __restrict__ dist_out) {
-    const V3 v = x - from;
-    const float L = sqrtf(dot(v, v));
-    if (L < 1e-9f) return 0;
-    const float d = L - r_shape - r_body;
-    if (!(d < thr)) return 0;
-    const V3 n = (1.f / L) * v;
-    const V3 pA = x - r_shape * n;
-    for (int k = 0; k < kMaxDof; k++) Jc[k] = 0.f;
-    for (int k = link; k >= 0; k = M.parent[k]) {          // the contact link's chain
-        const int di = M.dofidx[k];
-        if (di < 0) continue;
-        M3 Rk;
-#pragma unroll
-        for (int e = 0; e < 9; e++) Rk.m[e] = Rw[k * 9 + e];
-        const V3 aw = mul(Rk, v3(M.axis[k][0], M.axis[k][1], M.axis[k][2]));
-        if (M.jtype[k] == RLOA_JOINT_PRISMATIC) { Jc[di] = dot(n, aw); continue; }
-        const V3 dw = mul(Rk, v3(M.d[k][0], M.d[k][1], M.d[k][2]));      // pivot -> COM of link k, world
-        Jc[di] = dot(n, cross(aw, pA - ld3(pw + k * 3) + dw));
-    }
-    *dist_out = d;
-    return 1;
 }
 
 constexpr int kContactRec = kMaxDof + 1;      // floats per stored contact row: J[kMaxDof] | signed distance
@@ -876,54 +848,6 @@ __device__ __noinline__ float segment_box_argmin(V3 a, V3 b, V3 h) {
         }
     }
     return tb;
-}
-
-template <int NLMAX>
-__device__ __noinline__ int build_contacts(const ModelDev& M, const float* __restrict__ qcol, int N, V3 obstacle, V3 target,
-                                           float thr, float* __restrict__ J /*[kMaxContacts][kMaxDof]*/,
-                                           float* __restrict__ dist /*[kMaxContacts]*/) {
-    float Rw[NLMAX * 9], pw[NLMAX * 3];
-    const int nl = M.nl;
-    for (int i = 0; i < nl; i++) {
-        const int par = M.parent[i];
-        M3 Rl;
-        V3 pl, dd;
-        joint_transform(M, i, qcol[(size_t)i * N], Rl, pl, dd);
-        M3 R = Rl;
-        V3 p = pl;
-        if (par >= 0) {
-            M3 Rp;
-#pragma unroll
-            for (int k = 0; k < 9; k++) Rp.m[k] = Rw[par * 9 + k];
-            p = ld3(pw + par * 3) + mul(Rp, pl);
-            R = mul(Rp, Rl);
-        }
-#pragma unroll
-        for (int k = 0; k < 9; k++) Rw[i * 9 + k] = R.m[k];
-        st3(pw + i * 3, p);
-    }
-    const V3 th = v3(M.target_half[0], M.target_half[1], M.target_half[2]);
-    int nc = 0;
-    const int ns = M.ns;
-    for (int s = 0; s < ns; s++) {
-        const int l = M.s_link[s];
-        M3 Rl, sR;
-#pragma unroll
-        for (int k = 0; k < 9; k++) { Rl.m[k] = Rw[l * 9 + k]; sR.m[k] = M.s_R[s][k]; }
-        const V3 pl = ld3(pw + l * 3);
-        // broad phase on the shape's bounding sphere (exact: a shape outside it cannot be within thr)
-        const V3 bc = pl + mul(Rl, v3(M.s_bs[s][0], M.s_bs[s][1], M.s_bs[s][2]));
-        const float ro = M.s_bs[s][3] + M.obstacle_radius + thr, rc = M.s_bs[s][3] + sqrtf(dot(th, th)) + thr;
-        const V3 relo = obstacle - bc, relt = target - bc;
-        const bool near_o = dot(relo, relo) < ro * ro, near_t = dot(relt, relt) < rc * rc;
-        if (!near_o && !near_t) continue;
-        const M3 Rs = mul(Rl, sR);
-        const V3 ps = pl + mul(Rl, v3(M.s_p[s][0], M.s_p[s][1], M.s_p[s][2]));
-        shape_contacts(M, s, Rs, ps, obstacle, target, th, near_o, near_t, thr, [&](int link, V3 x, float r_shape, V3 from, float r_body) {
-            if (nc < kMaxContacts) nc += contact_row(M, Rw, pw, link, x, r_shape, from, r_body, thr, J + nc * kMaxDof, dist + nc);
-        });
-    }
-    return nc;
 }
 
 }  // namespace rloa
