@@ -758,15 +758,15 @@ def ours(args):
             'sim_substeps_per_s': rec['sim_substeps_per_s'],
             'valid_fraction': rec['valid_fraction'],
             'wall_ms_per_step_incl_flush': rec['wall_ms_per_step_incl_flush'],
-            'roofline': {'kernel': 'rloa_sim_step = sim_dynamics_kernel + sim_minv_kernel + sim_solve_kernel', 'bound': 'fp32',
+            'roofline': {'kernel': 'rloa_sim_step = sim_dynamics_kernel + sim_minv_kernel + sim_contacts_kernel + sim_solve_kernel', 'bound': 'fp32',
                          'achieved': tflops_nominal, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': tflops_nominal / fp32_peak,
                          'flop_per_env_step': FLOP_PER_ENV_STEP,
                          'peak_source': f'148 SMs x 128 FMA lanes x 2 flop x {sm_mhz:.0f} MHz (median SM clock sampled during the timed region)',
                          'at_measured_sweeps': {'mean_pgs_sweeps': sweeps, 'flop_per_env_step': flop_measured,
                                                 'achieved': tflops_measured, 'frac': tflops_measured / fp32_peak},
                          'avg_launch_ms': sim_avg_ms, 'share_of_step': sim_avg_ms / max(rec['phase_sum_ms'], 1e-9),
-                         'traffic': 8.18e6, 'traffic_source': 'ncu --set full at 4096 arms, dram read+write of the three kernels per '
-                                                              'launch, caches flushed by ncu (profiles/r3c_sim4096_ncu_full.md)',
+                         'traffic': 8.47e6, 'traffic_source': 'ncu --set full at 4096 arms, dram read+write of the four kernels per '
+                                                              'launch, caches flushed by ncu (profiles/r3i_sim4096_ncu_full.md)',
                          'hbm': {'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak, 'peak_source': which,
                                  'bytes_per_env_step': BYTES_PER_ENV_STEP}},
             'roofline_naf_update': {'kernel': 'NAFAgent.learn (replay batch %d, both networks, backward, clip + Adam + soft update)' % batch,
