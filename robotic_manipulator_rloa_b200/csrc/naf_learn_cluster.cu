@@ -125,6 +125,8 @@ struct LearnClusterArgs {
     rloa_naf_hyper hp;
     float* y;                               // [1024] TD targets, target cluster -> main cluster
     unsigned* yflag;                        // [8], zero at rest
+    unsigned* aflag;                        // [8], zero at rest: main CTA r -> target CTA r, "the optimiser coefficients are final"
+    float* acoef;                           // [8][8]: clip | bc1 | bc2s | norm | skip (a timed-out exchange) of that hand-over
     float *part_w2, *part_w1, *part_wh;     // [8][256*256], [8][256*S], [8][NH][256]
     float *part_hb, *part_loss;             // [8][64], [8]
     float *grad, *loss, *gnorm;             // outputs
@@ -502,6 +504,53 @@ constexpr int kXchgInKernelWorld = 8;      // ranks the in-kernel exchange keeps
 struct TrueT { static constexpr bool value = true; };
 struct FalseT { static constexpr bool value = false; };
 
+// clip + Adam + soft target update on one half of CTA `rank`'s share of the parameters: W2 chunks [j0, j1) of its four and
+// slots [s0, s1) of its six other elements.  The main CTA takes its gradients from shared memory (t_* from the gather pass);
+// the target-cluster CTA of the same rank - idle since its forward pass - takes the other half from the flat gradient in
+// global memory and recomputes the flat indices.  Every element is touched by exactly one thread of the grid.
+__device__ __forceinline__ void lc_adam_apply(const LearnClusterArgs& g, const AdamCoef& c, int rank, int tid, int j0, int j1, int s0,
+                                              int s1, const float4* t_gw, const float* t_gr, const int* t_gi) {
+    using namespace lc;
+#pragma unroll 2
+    for (int j = j0; j < j1; j++) {                            // W2: operands as float4 straight from the tensors
+        const int i4 = rank * 2048 + j * THREADS + tid;
+        float4 am = reinterpret_cast<const float4*>(g.m + g.off_w2)[i4], av = reinterpret_cast<const float4*>(g.v + g.off_w2)[i4];
+        float4 ap = reinterpret_cast<const float4*>(g.pt.main[4])[i4], at = reinterpret_cast<const float4*>(g.pt.target[4])[i4];
+        const float4 gw = t_gw != nullptr ? t_gw[j * THREADS + tid] : __ldcg(reinterpret_cast<const float4*>(g.grad + g.off_w2) + i4);
+        adam_math(gw.x, c, g.hp, am.x, av.x, ap.x, at.x);
+        adam_math(gw.y, c, g.hp, am.y, av.y, ap.y, at.y);
+        adam_math(gw.z, c, g.hp, am.z, av.z, ap.z, at.z);
+        adam_math(gw.w, c, g.hp, am.w, av.w, ap.w, at.w);
+        reinterpret_cast<float4*>(g.m + g.off_w2)[i4] = am;
+        reinterpret_cast<float4*>(g.v + g.off_w2)[i4] = av;
+        reinterpret_cast<float4*>(g.pt.main[4])[i4] = ap;
+        reinterpret_cast<float4*>(g.pt.target[4])[i4] = at;
+    }
+    const int rest = g.n_params - H * H, per = (rest + CL - 1) / CL;
+#pragma unroll 3
+    for (int j = s0; j < s1; j++) {
+        int i = -1;
+        if (t_gi != nullptr) {
+            i = t_gi[j * THREADS + tid];
+        } else {
+            const int e = rank * per + j * THREADS + tid;
+            if (j * THREADS + tid < per && e < rest) i = e < g.off_w2 ? e : e + H * H;
+        }
+        if (i >= 0) {
+            int t = 0;
+#pragma unroll
+            for (int k = 1; k < 14; k++) t += (i >= g.pt.offset[k]) ? 1 : 0;
+            const int jj = i - g.pt.offset[t];
+            float rm = g.m[i], rv = g.v[i], rp = g.pt.main[t][jj], rt = g.pt.target[t][jj];
+            adam_math(t_gr != nullptr ? t_gr[j * THREADS + tid] : __ldcg(g.grad + i), c, g.hp, rm, rv, rp, rt);
+            g.m[i] = rm;
+            g.v[i] = rv;
+            g.pt.main[t][jj] = rp;
+            g.pt.target[t][jj] = rt;
+        }
+    }
+}
+
 __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(lc::THREADS, 1)
 naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
     using namespace lc;
@@ -767,6 +816,24 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
         if (tid == 0) {
             unsigned one = 1u;
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(g.yflag + rank), "r"(one) : "memory");
+        }
+        if (g.do_adam) {
+            // the optimiser tail is shared: this CTA stays for the second half of main CTA `rank`'s elements
+            if (tid == 0) {
+                unsigned f = 0u;
+                const long long t0 = clock64();
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(g.aflag + rank) : "memory");
+                    if (f == 0u && clock64() - t0 > 4000000000ll) __trap();      // the main cluster never got there: abort, do not hang
+                } while (f == 0u);
+                g.aflag[rank] = 0u;                              // consumed: zero at rest
+            }
+            __syncthreads();
+            stamp(20);
+            const float* ac = g.acoef + rank * 8;
+            AdamCoef c;
+            c.clip = __ldcg(ac); c.bc1 = __ldcg(ac + 1); c.bc2s = __ldcg(ac + 2); c.norm = __ldcg(ac + 3);
+            if (__ldcg(ac + 4) == 0.f) lc_adam_apply(g, c, rank, tid, 2, 4, 3, 6, nullptr, nullptr, nullptr);
         }
     } else {
         // ---- main network: TD error, loss, gradients of the head pre-activations; thread (r, q) owns actions k = q, q + 4, q + 8
@@ -1241,42 +1308,22 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
                     }
                 }
             }
-            if (tid == 0) s_xbad = xch ? *reinterpret_cast<volatile int*>(g.xstatus) : 0;
+            if (tid == 0) {
+                s_xbad = xch ? *reinterpret_cast<volatile int*>(g.xstatus) : 0;
+                // hand the second half of this CTA's elements to the target-cluster CTA of the same rank (idle since its
+                // forward pass): coefficients + "skip" behind a release flag; the gradients it needs are in g.grad
+                const AdamCoef cc = *reinterpret_cast<const AdamCoef*>(red + 20);
+                float* ac = g.acoef + rank * 8;
+                ac[0] = cc.clip; ac[1] = cc.bc1; ac[2] = cc.bc2s; ac[3] = cc.norm; ac[4] = s_xbad ? 1.f : 0.f;
+                __threadfence();
+                unsigned one = 1u;
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(g.aflag + rank), "r"(one) : "memory");
+            }
             __syncthreads();
             const AdamCoef c = *reinterpret_cast<const AdamCoef*>(red + 20);
             // a wait that gave up (now or in an earlier update: the flag is sticky) means a peer's gradient may be stale:
             // nobody applies the update, so the ranks stop instead of drifting apart; rloa_xchg_status reports it
-#pragma unroll 2
-            for (int j = 0; j < (s_xbad ? 0 : 4); j++) {       // W2: operands as float4 straight from the tensors
-                const int i4 = rank * 2048 + j * 512 + tid;
-                float4 am = reinterpret_cast<const float4*>(g.m + g.off_w2)[i4], av = reinterpret_cast<const float4*>(g.v + g.off_w2)[i4];
-                float4 ap = reinterpret_cast<const float4*>(g.pt.main[4])[i4], at = reinterpret_cast<const float4*>(g.pt.target[4])[i4];
-                const float4 gw = t_gw[j * THREADS + tid];
-                adam_math(gw.x, c, g.hp, am.x, av.x, ap.x, at.x);
-                adam_math(gw.y, c, g.hp, am.y, av.y, ap.y, at.y);
-                adam_math(gw.z, c, g.hp, am.z, av.z, ap.z, at.z);
-                adam_math(gw.w, c, g.hp, am.w, av.w, ap.w, at.w);
-                reinterpret_cast<float4*>(g.m + g.off_w2)[i4] = am;
-                reinterpret_cast<float4*>(g.v + g.off_w2)[i4] = av;
-                reinterpret_cast<float4*>(g.pt.main[4])[i4] = ap;
-                reinterpret_cast<float4*>(g.pt.target[4])[i4] = at;
-            }
-#pragma unroll 3
-            for (int j = 0; j < kSlots; j++) {
-                const int i = s_xbad ? -1 : t_gi[j * THREADS + tid];
-                if (i >= 0) {
-                    int t = 0;
-#pragma unroll
-                    for (int k = 1; k < 14; k++) t += (i >= g.pt.offset[k]) ? 1 : 0;
-                    const int jj = i - g.pt.offset[t];
-                    float rm = g.m[i], rv = g.v[i], rp = g.pt.main[t][jj], rt = g.pt.target[t][jj];
-                    adam_math(t_gr[j * THREADS + tid], c, g.hp, rm, rv, rp, rt);
-                    g.m[i] = rm;
-                    g.v[i] = rv;
-                    g.pt.main[t][jj] = rp;
-                    g.pt.target[t][jj] = rt;
-                }
-            }
+            if (!s_xbad) lc_adam_apply(g, c, rank, tid, 0, 2, 0, 3, t_gw, t_gr, t_gi);
         } else if (rank == 0 && tid == 0 && g.loss != nullptr) {
             float l = 0.f;
             for (int cc = 0; cc < CL; cc++) l += __ldcg(g.part_loss + cc);
@@ -1304,7 +1351,7 @@ int learn_cluster_prepare(LearnCluster* lcw, int S, int A) {
     if (lcw->images != nullptr) return RLOA_OK;
     const int NH = A + 1 + A * (A + 1) / 2;
     RLOA_CUDA(cudaFuncSetAttribute(naf_learn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc::SMEM_BYTES));
-    const size_t floats = 1024 + (size_t)lc::CL * (lc::H * lc::H + lc::H * S + (size_t)NH * lc::H + 64 + 1) + 16;
+    const size_t floats = 1024 + (size_t)lc::CL * (lc::H * lc::H + lc::H * S + (size_t)NH * lc::H + 64 + 1) + 16 + 8 + 64;
     RLOA_CUDA(cudaMalloc(&lcw->images, learn_cluster_image_bytes()));
     if (cudaMalloc(&lcw->block, floats * sizeof(float)) != cudaSuccess) {
         cudaFree(lcw->images);
@@ -1320,7 +1367,9 @@ int learn_cluster_prepare(LearnCluster* lcw, int S, int A) {
     lcw->part_wh = p; p += (size_t)lc::CL * NH * lc::H;
     lcw->part_hb = p; p += lc::CL * 64;
     lcw->part_loss = p; p += lc::CL;
-    lcw->yflag = reinterpret_cast<unsigned*>(p);
+    lcw->yflag = reinterpret_cast<unsigned*>(p); p += 16;
+    lcw->aflag = reinterpret_cast<unsigned*>(p); p += 8;
+    lcw->acoef = p;
     RLOA_CUDA(cudaEventCreateWithFlags(&lcw->pack_done, cudaEventDisableTiming));
     RLOA_CUDA(cudaEventCreateWithFlags(&lcw->pack_fork, cudaEventDisableTiming));
     return RLOA_OK;
@@ -1362,7 +1411,7 @@ int learn_cluster_step(LearnCluster* lcw, const rloa_naf_params* mn, const rloa_
     a.states = states; a.actions = actions; a.rewards = rewards; a.next_states = next_states; a.dones = dones;
     a.B = B; a.S = S; a.A = A; a.NL = A * (A + 1) / 2; a.NH = A + 1 + a.NL;
     a.hp = *hp;
-    a.y = lcw->y; a.yflag = lcw->yflag;
+    a.y = lcw->y; a.yflag = lcw->yflag; a.aflag = lcw->aflag; a.acoef = lcw->acoef;
     a.part_w2 = lcw->part_w2; a.part_w1 = lcw->part_w1; a.part_wh = lcw->part_wh; a.part_hb = lcw->part_hb; a.part_loss = lcw->part_loss;
     a.grad = grad; a.loss = loss; a.gnorm = gnorm;
     a.pt = pt;

@@ -15,6 +15,8 @@ struct LearnCluster {
     float* block = nullptr;          // y | partial weight gradients | head-bias / loss partials | hand-over flags
     float *y = nullptr, *part_w2 = nullptr, *part_w1 = nullptr, *part_wh = nullptr, *part_hb = nullptr, *part_loss = nullptr;
     unsigned* yflag = nullptr;
+    unsigned* aflag = nullptr;       // optimiser hand-over main CTA -> target CTA (flags, coefficients)
+    float* acoef = nullptr;
     float* dbg = nullptr;            // optional intermediate dump (tests)
     long long* prof = nullptr;       // optional clock64 phase stamps
     bool prepacked = false;          // rloa_naf_learn_prepack wrote the images on a side stream; the next learn joins pack_done
