@@ -824,7 +824,9 @@ naf_learn_cluster_kernel(const __grid_constant__ LearnClusterArgs g) {
                 const long long t0 = clock64();
                 do {
                     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(g.aflag + rank) : "memory");
-                    if (f == 0u && clock64() - t0 > 4000000000ll) __trap();      // the main cluster never got there: abort, do not hang
+                    // the main cluster's backward pass lies between (60 us; seconds under compute-sanitizer): a generous bound,
+                    // its own waits abort within 2 s if anything is stuck
+                    if (f == 0u && clock64() - t0 > 120000000000ll) __trap();
                 } while (f == 0u);
                 g.aflag[rank] = 0u;                              // consumed: zero at rest
             }
