@@ -432,8 +432,11 @@ def train_workload(ctx, args, c, steps, full):
         launches = lib.rloa_launch_count() - l0
         if graphed and loop._graph is not None:
             launches = loop.graph_kernels * npairs + launches
+        trans_local = float(loop.transitions.item())
+        if odd:                                # an odd K leaves the ping-pong buffers off the phase the graph was captured in:
+            loop._body(True, True, 1)          # one untimed, uncounted iteration realigns them for the passes that follow
         total_ms = ctx.reduce(sum(a.elapsed_time(b) for a, b in ev), 'MAX')
-        trans = ctx.reduce(float(loop.transitions.item()), 'SUM')
+        trans = ctx.reduce(trans_local, 'SUM')
         return dict(value=trans / (total_ms * 1e-3), ms_per_step=total_ms / n_steps, total_ms=total_ms,
                     sim_substeps_per_s=world * envs * n_steps / (total_ms * 1e-3),
                     valid_fraction=trans / (world * envs * n_steps), launches=int(launches),
