@@ -46,3 +46,19 @@ def test_solve_kernel_uses_packed_ffma2():
     s = sass('_ZN4rloa16sim_solve_kernelILi12ELi16ELb1ELb1ELb0EEEvNS_8ModelDevENS_9SimArraysENS_10StepCfgDevEiPKfPKhPfS8_PhS9_')
     assert count(s, 'FFMA2') >= 288                    # 12 rows x 6 pairs x (2 sweep directions + limit rows)
     assert count(s, 'UTCHMMA') == 0                    # nothing GEMM-shaped in the simulator, by design
+
+
+def test_learn_cluster_kernel_is_tcgen05_with_cluster_barriers_and_system_scope_words():
+    """NAFAgent.learn as one kernel: every contraction of forward and backward is a tcgen05 MMA (layer 1 twice as tf32 hi / lo,
+    layer 2, heads, dWh^T, da2, da1, dW1, dW2), operands arrive by TMA bulk copies, the BatchNorm statistics cross the cluster
+    (barrier.cluster arrive / wait pairs), and the in-kernel gradient exchange moves system-scope 64-bit words."""
+    s = sass('_ZN4rloa24naf_learn_cluster_kernelENS_16LearnClusterArgsE')
+    assert count(s, 'UTCHMMA') >= 100
+    assert count(s, 'UBLKCP') >= 5 and count(s, 'LDTM') >= 10 and count(s, 'UTCBAR') >= 8
+    assert count(s, 'UCGABAR_ARV') >= 5 and count(s, 'UCGABAR_WAIT') >= 5
+    assert count(s, 'STRONG.SYS') >= 20
+
+
+def test_collision_phase_and_deferred_replay_commit_kernels_exist():
+    sass('_ZN4rloa19sim_contacts_kernelILi16EEEvNS_8ModelDevENS_9SimArraysEf')
+    sass('_ZN4rloa20replay_commit_kernelE11rloa_replayiPKh')
